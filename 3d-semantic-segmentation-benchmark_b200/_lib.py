@@ -1,0 +1,107 @@
+"""ctypes binding of libpcnbr.so (include/pcnbr.h).  No torch types cross this boundary: only raw
+device pointers, sizes and the current CUDA stream handle.
+
+The product path has NO CPU fallback: if the library is missing, or a tensor is not a CUDA tensor,
+the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_long, c_size_t, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpcnbr.so")
+ABI_VERSION = 1
+
+_P, _I, _L, _F, _Z = c_void_p, c_int, c_long, c_float, c_size_t
+
+# name -> (restype, argtypes): mirrors include/pcnbr.h one to one
+PROTOTYPES = {
+    "pcnbr_abi_version": (_I, []),
+    "pcnbr_error_string": (c_char_p, [_I]),
+    "pcnbr_fps_ws_bytes": (_Z, [_I, _I]),
+    "pcnbr_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "pcnbr_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
+    "pcnbr_knn_direct_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "pcnbr_knn_expand_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "pcnbr_knn_expand_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P]),
+    "pcnbr_group_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "pcnbr_csr_ws_bytes": (_Z, [_I, _I, _I]),
+    "pcnbr_csr_build": (_I, [_P, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "pcnbr_group_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_maxpool_f32": (_I, [_P, _L, _I, _I, _L, _L, _L, _P, _P, _P]),
+    "pcnbr_maxpool_bwd_f32": (_I, [_P, _P, _L, _I, _I, _L, _L, _L, _P, _P]),
+    "pcnbr_interp_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pcnbr_interp_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_edge_feature_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_edge_feature_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+}
+
+# CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
+KERNELS_PER_CALL = {"pcnbr_csr_build": 4, "pcnbr_knn_expand_f32": 2}
+
+_lib = None
+launches = 0          # number of libpcnbr CUDA kernels launched by this process (bench.py reports it)
+timing = None         # None, or {name: [(start_event, end_event), ...]} while bench.py profiles a region
+
+
+class PcnbrError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """dlopen libpcnbr.so and bind every prototype; raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PcnbrError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built "
+            "(run `python __graft_entry__.py build`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.pcnbr_abi_version() != ABI_VERSION:
+        raise PcnbrError(f"libpcnbr ABI {lib.pcnbr_abi_version()} != host layer ABI {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke a compute entry point and turn a non-zero return code into an exception."""
+    global launches
+    lib = load()
+    if timing is not None:
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()                      # on the current stream = the stream handed to the kernel
+        rc = getattr(lib, name)(*args)
+        ev1.record()
+        timing.setdefault(name, []).append((ev0, ev1))
+    else:
+        rc = getattr(lib, name)(*args)
+    launches += KERNELS_PER_CALL.get(name, 1)
+    if rc != 0:
+        raise PcnbrError(f"{name} failed: {lib.pcnbr_error_string(rc).decode()} (code {rc})")
+
+
+def size(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))
+
+
+def start_timing() -> None:
+    """Bracket every C-ABI call with CUDA events on the launching stream (bench.py roofline)."""
+    global timing
+    timing = {}
+
+
+def stop_timing() -> dict:
+    """-> {entry point: (calls, total ms)}; synchronises the device."""
+    global timing
+    import torch
+    torch.cuda.synchronize()
+    out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (timing or {}).items()}
+    timing = None
+    return out

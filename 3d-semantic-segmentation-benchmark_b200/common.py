@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's models/utils/common.py on top of libpcnbr.
+
+Same names, argument meaning, return layouts, parameter names (state_dict keys) and error behaviour
+as /root/reference/models/utils/common.py, so PointNetpp / PointNeXt and train.py use it as a
+drop-in; every neighbourhood op runs in a hand-written sm_100a kernel.  CUDA tensors only.
+
+Selection follows the canonical tie rule (lowest index wins), which is what a stable sort of the
+reference's distance rows yields; torch.topk's own tie order is unspecified.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+__all__ = ["sample", "group", "reduce", "interpolate", "MiniPointNet", "UnitPointNet", "SetAbstraction",
+           "FeaturePropagation", "InvResMLP"]
+
+
+def sample(coords: torch.Tensor, C: int, start_idx: torch.Tensor | None = None) -> torch.Tensor:
+    """Farthest point sampling -> coordinates (B,C,3) of the picks   [reference common.py:6-34].
+
+    The first pick is drawn like the reference (one torch.randint on coords.device) unless
+    `start_idx` (B,) is given."""
+    return ops.farthest_point_sample(coords, C, start_idx, return_coords=True)[1]
+
+
+def group(centroid_coords: torch.Tensor, coords: torch.Tensor, features: torch.Tensor, r: float, K: int,
+          normalize: bool = False) -> torch.Tensor:
+    """Ball query + gather + centre-subtract (+ /r) + concat -> (B,C,K,3+D)   [common.py:37-71]."""
+    nbr = ops.NeighborIndex(ops.query_ball_point(r, K, coords, centroid_coords), coords.shape[1])
+    return ops.group_points(coords, features, centroid_coords, nbr, r if normalize else None)
+
+
+def reduce(x: torch.Tensor, type: str) -> torch.Tensor:
+    """Pooling over the K axis of (B,C,K,D')   [common.py:74-91].
+
+    'avg' reproduces the reference literally, including its `[0]` (batch element 0 of the mean,
+    common.py:89); it is unused by the models and runs as plain torch ops."""
+    if type == 'max':
+        return ops.max_pool_neighbors(x, 2)
+    if type == 'avg':
+        return torch.mean(x, dim=2)[0]
+    raise ValueError(f"'{type}' pooling not supported; use 'max' or 'avg'.")
+
+
+def interpolate(points: torch.Tensor, coords_1: torch.Tensor, coords_2: torch.Tensor, k: int = 3) -> torch.Tensor:
+    """k-NN inverse-squared-distance interpolation (B,M,D) -> (B,N,D)   [common.py:94-122]."""
+    idx, d2 = ops.knn_points(coords_1, coords_2, k)
+    return ops.three_interpolate(points, ops.NeighborIndex(idx, coords_2.shape[1]), d2)
+
+
+class MiniPointNet(nn.Module):
+    """[Conv2d 1x1 -> BatchNorm2d -> ReLU] x len(mlps)   [common.py:125-150]; library convolutions."""
+
+    def __init__(self, in_channels: int, mlps: list[int]):
+        super().__init__()
+        self.conv = nn.ModuleList()
+        self.batch = nn.ModuleList()
+        width = in_channels
+        for m in mlps:
+            self.conv.append(nn.Conv2d(width, m, (1, 1)))
+            self.batch.append(nn.BatchNorm2d(m))
+            width = m
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        for conv, bn in zip(self.conv, self.batch):
+            x = F.relu(bn(conv(x)))
+        return x
+
+
+class UnitPointNet(nn.Module):
+    """[Conv1d -> BatchNorm1d -> ReLU] x len(mlps)   [common.py:153-178]."""
+
+    def __init__(self, in_channels: int, mlps: list[int]):
+        super().__init__()
+        self.conv = nn.ModuleList()
+        self.batch = nn.ModuleList()
+        width = in_channels
+        for m in mlps:
+            self.conv.append(nn.Conv1d(width, m, 1))
+            self.batch.append(nn.BatchNorm1d(m))
+            width = m
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        for conv, bn in zip(self.conv, self.batch):
+            x = F.relu(bn(conv(x)))
+        return x
+
+
+class SetAbstraction(nn.Module):
+    """FPS -> ball-query group -> MiniPointNet -> max over K   [common.py:180-214]."""
+
+    def __init__(self, C: int, radius: float, in_channels: int, mlps: list[int], K: int = 32,
+                 pooling_type: str = 'max', grouping_norm: bool = False):
+        super().__init__()
+        self.point_net = MiniPointNet(in_channels, mlps)
+        self.C = C
+        self.radius = radius
+        self.K = K
+        self.pooling_type = pooling_type
+        self.grouping_norm = grouping_norm
+        self.fps_start = None          # optional (B,) first FPS pick (tests); None = reference's randint
+
+    def forward(self, coords: torch.Tensor, features: torch.Tensor):
+        centroid_coords = sample(coords, self.C, self.fps_start)
+        grouped = group(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
+        x = self.point_net(grouped.permute(0, 3, 1, 2))      # channels-last view: no copy
+        return centroid_coords, reduce(x.permute(0, 2, 3, 1), self.pooling_type)
+
+
+class FeaturePropagation(nn.Module):
+    """3-NN interpolation -> skip concat -> UnitPointNet   [common.py:217-243]."""
+
+    def __init__(self, in_channels: int, mlps: list[int]):
+        super().__init__()
+        self.point_net = UnitPointNet(in_channels, mlps)
+
+    def forward(self, coords_1, coords_2, features_1, features_2):
+        up = interpolate(features_2, coords_1, coords_2)
+        feats = up if features_1 is None else torch.cat([features_1, up], dim=-1)
+        return self.point_net(feats.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+class InvResMLP(nn.Module):
+    """Inverted-residual block of PointNeXt: self ball query (always /r) -> MLP -> max -> MLP -> +x
+    [common.py:246-301]."""
+
+    def __init__(self, radius: int, in_channels: int, mlp_size: int, K: int, pooling_type: str = 'max'):
+        super().__init__()
+        self.radius = radius
+        self.K = K
+        self.pooling_type = pooling_type
+        self.neighbour_features_mlp = MiniPointNet(in_channels, [mlp_size])
+        self.point_features_mlp = UnitPointNet(mlp_size, [4 * mlp_size, mlp_size])
+
+    def forward(self, centroid_coords, coords, features):
+        grouped = group(centroid_coords, coords, features, self.radius, self.K, True)
+        x = self.neighbour_features_mlp(grouped.permute(0, 3, 1, 2))
+        x = reduce(x.permute(0, 2, 3, 1), self.pooling_type)
+        x = self.point_features_mlp(x.permute(0, 2, 1)).permute(0, 2, 1)
+        return centroid_coords, x + features

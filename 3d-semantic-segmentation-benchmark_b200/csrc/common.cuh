@@ -1,0 +1,83 @@
+// common.cuh -- shared device helpers for libpcnbr (sm_100a).
+//
+// Exact-arithmetic rule: every distance that decides an index is computed with explicit
+// round-to-nearest intrinsics (__fsub_rn/__fmul_rn/__fadd_rn/__fmaf_rn/__fsqrt_rn) so nvcc can never
+// contract or reassociate; the forms are the ones pinned against the reference in oracle/canon.c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pcnbr.h"
+
+#define PCNBR_FULL 0xffffffffu
+#define PCNBR_KEY_MAX 0xffffffffffffffffull
+
+#define PCNBR_CHECK_LAUNCH()                         \
+    do {                                             \
+        cudaError_t e__ = cudaGetLastError();        \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+namespace pcnbr {
+
+typedef unsigned long long u64;
+
+// Monotone map float -> uint32 (total order of the reals incl. negatives; -0 < +0).
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+// (key, index) -> one u64 whose unsigned order is ascending (key, index).
+__device__ __forceinline__ u64 pack_key(uint32_t ord, uint32_t idx) { return ((u64)ord << 32) | idx; }
+
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+    uint32_t lo = __shfl_sync(PCNBR_FULL, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(PCNBR_FULL, (uint32_t)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl64_up1(u64 v) {
+    uint32_t lo = __shfl_up_sync(PCNBR_FULL, (uint32_t)v, 1);
+    uint32_t hi = __shfl_up_sync(PCNBR_FULL, (uint32_t)(v >> 32), 1);
+    return ((u64)hi << 32) | lo;
+}
+
+// reference group()/interpolate() distance: ((dx*dx + dy*dy) + dz*dz), dx = src - query.
+__device__ __forceinline__ float d2_direct(float px, float py, float pz, float qx, float qy, float qz) {
+    const float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Sorted K-list spread over a warp: position p = slot*32 + lane holds the p-th smallest key.
+// NSLOT*32 >= K.  All lanes call insert() with the same candidate.
+template <int NSLOT>
+struct WarpList {
+    u64 v[NSLOT];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) v[s] = PCNBR_KEY_MAX;
+    }
+    // key at list position p (warp-uniform p)
+    __device__ __forceinline__ u64 at(int p) const {
+        u64 r = 0;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            if ((p >> 5) == s) r = shfl64(v[s], p & 31);
+        return r;
+    }
+    __device__ __forceinline__ void insert(u64 cand, int lane) {
+        u64 carry = 0;  // key at position p-1 of lane 0 of the current slot (0 = -inf)
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            u64 up = shfl64_up1(v[s]);
+            if (lane == 0) up = carry;
+            const u64 last = shfl64(v[s], 31);
+            if (v[s] > cand) v[s] = (up > cand) ? up : cand;
+            carry = last;
+        }
+    }
+};
+
+}  // namespace pcnbr

@@ -1,0 +1,147 @@
+// csr.cu -- K7 support: inverse of a neighbour index (CSR by source point).
+//
+// The reference's backward of every gather (autograd IndexBackward -> index_put_(accumulate=True),
+// models/utils/common.py:65,117 and models/dgcnn/dgcnn.py:48) is a scatter-add.  We turn it into a
+// gather: for each source point s, the list of positions e (flattened (m,k)) with idx[e] == s, in
+// ascending e.  Each backward kernel then sums a segment in that fixed order: no float atomics,
+// bitwise deterministic.  Built once per forward and reused by the backward.
+//
+// count (int atomics: order-independent) -> per-cloud exclusive scan -> fill (int atomic cursor,
+// arbitrary order) -> per-segment rank-by-counting sort (out of place) which restores ascending e.
+#include "common.cuh"
+
+namespace pcnbr {
+
+__global__ void csr_count_kernel(const int32_t* __restrict__ idx, int E, int N, int32_t* __restrict__ cnt) {
+    const int b = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int s = idx[(size_t)b * E + e];
+        atomicAdd(&cnt[(size_t)b * (N + 1) + s], 1);
+    }
+}
+
+// one CTA per cloud: offsets[b, 0..N] = exclusive scan of cnt[b, 0..N-1]; cursor = copy of offsets
+__global__ void __launch_bounds__(1024)
+csr_scan_kernel(const int32_t* cnt, int N, int32_t* __restrict__ offsets, int32_t* cursor) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* c = cnt + (size_t)b * (N + 1);
+    int32_t* o = offsets + (size_t)b * (N + 1);
+    int32_t* cur = cursor + (size_t)b * (N + 1);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < N + 1; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < N) ? c[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(PCNBR_FULL, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(PCNBR_FULL, w, d);
+                if (lane >= d) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        if (i < N + 1) { o[i] = excl; cur[i] = excl; }
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+}
+
+__global__ void csr_fill_kernel(const int32_t* __restrict__ idx, int E, int N, int32_t* __restrict__ cursor,
+                                int32_t* __restrict__ tmp) {
+    const int b = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int s = idx[(size_t)b * E + e];
+        const int pos = atomicAdd(&cursor[(size_t)b * (N + 1) + s], 1);
+        tmp[(size_t)b * E + pos] = e;
+    }
+}
+
+// rank(x) = #{y in segment : y < x} (positions are unique), written out of place.
+// One warp ranks the 32 entries [c0, c0+32) of a segment against the whole segment.
+__device__ __forceinline__ void csr_rank_chunk(const int32_t* __restrict__ t, int32_t* __restrict__ pm, int beg,
+                                               int len, int c0, int lane) {
+    const bool mine = c0 + lane < len;
+    const int x = mine ? t[beg + c0 + lane] : 0x7fffffff;
+    int rank = 0;
+    for (int y0 = 0; y0 < len; y0 += 32) {
+        const int y = (y0 + lane < len) ? t[beg + y0 + lane] : 0x7fffffff;
+        const int n = min(32, len - y0);
+        for (int l = 0; l < n; ++l) rank += (__shfl_sync(PCNBR_FULL, y, l) < x);
+    }
+    if (mine) pm[beg + rank] = x;
+}
+
+// A CTA of 8 warps takes 8 consecutive segments: short ones are sorted by one warp each, long ones
+// (the padded / duplicated heavy hitters, up to M entries) by all 8 warps together.
+constexpr int CSR_HEAVY = 128;
+__global__ void __launch_bounds__(256)
+csr_sort_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ tmp, int E, int N,
+                int32_t* __restrict__ perm) {
+    __shared__ int s_beg[8], s_len[8];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* o = offsets + (size_t)b * (N + 1);
+    const int32_t* t = tmp + (size_t)b * E;
+    int32_t* pm = perm + (size_t)b * E;
+    for (int s0 = blockIdx.x * 8; s0 < N; s0 += gridDim.x * 8) {
+        const int s = s0 + warp;
+        const int beg = (s < N) ? o[s] : 0;
+        const int len = (s < N) ? o[s + 1] - beg : 0;
+        if (lane == 0) { s_beg[warp] = beg; s_len[warp] = len; }
+        if (len == 1) { if (lane == 0) pm[beg] = t[beg]; }
+        else if (len <= CSR_HEAVY)
+            for (int c0 = 0; c0 < len; c0 += 32) csr_rank_chunk(t, pm, beg, len, c0, lane);
+        __syncthreads();
+        for (int w = 0; w < 8; ++w) {
+            const int hl = s_len[w];
+            if (hl > CSR_HEAVY)
+                for (int c0 = warp * 32; c0 < hl; c0 += 8 * 32) csr_rank_chunk(t, pm, s_beg[w], hl, c0, lane);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pcnbr
+
+using namespace pcnbr;
+
+extern "C" size_t pcnbr_csr_ws_bytes(int B, int E, int N) {
+    // cnt/cursor (B,N+1) + tmp (B,E)
+    return sizeof(int32_t) * ((size_t)B * (N + 1) + (size_t)B * E);
+}
+
+extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t* offsets, int32_t* perm,
+                               void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (!idx || !offsets || !perm || B <= 0 || E <= 0 || N <= 0) return PCNBR_E_BADARG;
+    if (!ws || ws_bytes < pcnbr_csr_ws_bytes(B, E, N)) return PCNBR_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t* cnt = (int32_t*)ws;
+    int32_t* tmp = cnt + (size_t)B * (N + 1);
+    cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)B * (N + 1), s);
+    if (e != cudaSuccess) return (int)e;
+    const int gx = min((E + 255) / 256, 1184);
+    csr_count_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt);
+    PCNBR_CHECK_LAUNCH();
+    csr_scan_kernel<<<B, 1024, 0, s>>>(cnt, N, offsets, cnt);       // cursor overwrites cnt in place
+    PCNBR_CHECK_LAUNCH();
+    csr_fill_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt, tmp);
+    PCNBR_CHECK_LAUNCH();
+    const int gs = min((N + 7) / 8, 1184);
+    csr_sort_kernel<<<dim3(gs, B), 256, 0, s>>>(offsets, tmp, E, N, perm);
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}

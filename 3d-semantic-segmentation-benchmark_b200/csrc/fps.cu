@@ -1,0 +1,161 @@
+// fps.cu -- K1 farthest point sampling (reference: models/utils/common.py:6-34).
+//
+// One CTA per cloud.  Each thread keeps PPT points (xyz + running min distance) in registers for the
+// whole kernel; per pick the only traffic is one 64-bit partial per warp through shared memory.
+// The argmax with "lowest index wins" is a max over the key (dist_bits << 32 | ~index): distances
+// are >= +0 so their bit patterns are monotone.  Warp stage = two REDUX ops, block stage = one
+// __syncthreads per pick (double-buffered partials).  Compulsory HBM traffic is 12N + 16C bytes per
+// cloud, so the kernel is ALU/latency bound on the SMs it occupies.
+#include "common.cuh"
+
+namespace pcnbr {
+
+__device__ __forceinline__ float fps_dist(float x, float y, float z, float cx, float cy, float cz) {
+    // linalg.vector_norm over 3 components on the reference's CPU path: FMA chain, then sqrt
+    const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy), dz = __fsub_rn(z, cz);
+    return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+}
+
+// warp-wide max of (hi, lo) pairs in lexicographic order, result broadcast to all lanes
+__device__ __forceinline__ void warp_max_pair(uint32_t& hi, uint32_t& lo) {
+    const uint32_t mh = __reduce_max_sync(PCNBR_FULL, hi);
+    const uint32_t ml = __reduce_max_sync(PCNBR_FULL, hi == mh ? lo : 0u);
+    hi = mh;
+    lo = ml;
+}
+
+template <int PPT, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __restrict__ start,
+               int32_t* __restrict__ idx_out, float* __restrict__ xyz_out) {
+    constexpr int W = T / 32;
+    __shared__ uint32_t s_hi[2][W], s_lo[2][W];
+    __shared__ float s_xyz[2][W][3];
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ p = xyz + (size_t)b * N * 3;
+
+    float x[PPT], y[PPT], z[PPT], md[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int n = j * T + tid;
+        if (n < N) {
+            x[j] = p[n * 3 + 0]; y[j] = p[n * 3 + 1]; z[j] = p[n * 3 + 2];
+            md[j] = __int_as_float(0x7f800000);          // +inf (common.py:21)
+        } else {
+            x[j] = y[j] = z[j] = 0.f;
+            md[j] = 0.f;                                 // padding lanes can never beat a real point
+        }
+    }
+
+    int cur = start[b];
+    float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
+
+    for (int i = 0; i < C; ++i) {
+        if (tid == 0) {
+            idx_out[(size_t)b * C + i] = cur;
+            if (xyz_out) {
+                float* o = xyz_out + ((size_t)b * C + i) * 3;
+                o[0] = cx; o[1] = cy; o[2] = cz;
+            }
+        }
+        if (i + 1 == C) break;
+        const int buf = i & 1;
+
+        uint32_t bh = 0, bl = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = fps_dist(x[j], y[j], z[j], cx, cy, cz);
+            md[j] = fminf(md[j], d);                     // common.py:29-30
+            const uint32_t h = __float_as_uint(md[j]);
+            const uint32_t l = 0xffffffffu - (uint32_t)(j * T + tid);
+            if (h > bh || (h == bh && l > bl)) { bh = h; bl = l; }
+        }
+        uint32_t wh = bh, wl = bl;
+        warp_max_pair(wh, wl);
+        if (bh == wh && bl == wl) {                      // exactly one lane: indices are unique
+            const int n = (int)(0xffffffffu - wl);
+            float wx = 0.f, wy = 0.f, wz = 0.f;
+#pragma unroll
+            for (int j = 0; j < PPT; ++j)
+                if (j * T + tid == n) { wx = x[j]; wy = y[j]; wz = z[j]; }
+            s_hi[buf][warp] = wh; s_lo[buf][warp] = wl;
+            s_xyz[buf][warp][0] = wx; s_xyz[buf][warp][1] = wy; s_xyz[buf][warp][2] = wz;
+        }
+        __syncthreads();
+        uint32_t gh = (lane < W) ? s_hi[buf][lane] : 0u;
+        uint32_t gl = (lane < W) ? s_lo[buf][lane] : 0u;
+        const uint32_t mh = gh, ml = gl;
+        warp_max_pair(gh, gl);
+        const uint32_t who = __ballot_sync(PCNBR_FULL, lane < W && mh == gh && ml == gl);
+        const int w = __ffs(who) - 1;
+        cur = (int)(0xffffffffu - gl);                   // torch.max: lowest index on ties (common.py:31)
+        cx = s_xyz[buf][w][0]; cy = s_xyz[buf][w][1]; cz = s_xyz[buf][w][2];
+    }
+}
+
+// Any N: running distances live in a global workspace, coordinates are re-read through L1/L2.
+template <int T>
+__global__ void __launch_bounds__(T, 1)
+fps_big_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __restrict__ start,
+               int32_t* __restrict__ idx_out, float* __restrict__ xyz_out, float* __restrict__ ws) {
+    constexpr int W = T / 32;
+    __shared__ uint32_t s_hi[2][W], s_lo[2][W];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ p = xyz + (size_t)b * N * 3;
+    float* __restrict__ md = ws + (size_t)b * N;
+    for (int n = tid; n < N; n += T) md[n] = __int_as_float(0x7f800000);
+    int cur = start[b];
+    for (int i = 0; i < C; ++i) {
+        const float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
+        if (tid == 0) {
+            idx_out[(size_t)b * C + i] = cur;
+            if (xyz_out) {
+                float* o = xyz_out + ((size_t)b * C + i) * 3;
+                o[0] = cx; o[1] = cy; o[2] = cz;
+            }
+        }
+        if (i + 1 == C) break;
+        const int buf = i & 1;
+        uint32_t bh = 0, bl = 0;
+        for (int n = tid; n < N; n += T) {
+            const float d = fps_dist(p[n * 3 + 0], p[n * 3 + 1], p[n * 3 + 2], cx, cy, cz);
+            const float m = fminf(md[n], d);
+            md[n] = m;
+            const uint32_t h = __float_as_uint(m), l = 0xffffffffu - (uint32_t)n;
+            if (h > bh || (h == bh && l > bl)) { bh = h; bl = l; }
+        }
+        warp_max_pair(bh, bl);
+        if (lane == 0) { s_hi[buf][warp] = bh; s_lo[buf][warp] = bl; }
+        __syncthreads();
+        uint32_t gh = (lane < W) ? s_hi[buf][lane] : 0u;
+        uint32_t gl = (lane < W) ? s_lo[buf][lane] : 0u;
+        warp_max_pair(gh, gl);
+        cur = (int)(0xffffffffu - gl);
+    }
+}
+
+}  // namespace pcnbr
+
+extern "C" size_t pcnbr_fps_ws_bytes(int B, int N) {
+    return (N > 8192) ? sizeof(float) * (size_t)B * (size_t)N : 0;
+}
+
+extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_t* start, int32_t* idx_out,
+                             float* xyz_out, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    using namespace pcnbr;
+    if (!xyz || !start || !idx_out || B <= 0 || N <= 0 || C <= 0) return PCNBR_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N <= 256)        fps_reg_kernel<1, 256><<<B, 256, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    else if (N <= 512)   fps_reg_kernel<1, 512><<<B, 512, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    else if (N <= 1024)  fps_reg_kernel<1, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    else if (N <= 2048)  fps_reg_kernel<2, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    else if (N <= 4096)  fps_reg_kernel<4, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    else if (N <= 8192)  fps_reg_kernel<8, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    else {
+        if (!ws || ws_bytes < pcnbr_fps_ws_bytes(B, N)) return PCNBR_E_WORKSPACE;
+        fps_big_kernel<1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out, (float*)ws);
+    }
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,88 @@
+// interp.cu -- K8 inverse-distance interpolation over the k (=3) nearest coarse points, fwd + bwd.
+//
+// Reference: models/utils/common.py:115-122 -- gather (B,N,k,D), weights 1/(d2 + 1e-9) on the SQUARED
+// distance, normalise, multiply, sum over k: four (B,N,k,D)-sized temporaries.  Here one warp owns
+// one fine point: it reads the k indices / distances once, forms the weights, and streams the k
+// coarse rows (L2-resident, coalesced over D) into one coalesced output row.
+// HBM-bound: 4*N*D written + 4*M*D read + 8*N*k (idx, d2) read + 4*N*k coef written per cloud.
+// Arithmetic order as the reference: w = 1/(d2 + 1e-9f); norm = (w0+w1)+w2; out = sum_k (f*w_k)/norm.
+#include "common.cuh"
+#include "segsum.cuh"
+
+namespace pcnbr {
+
+constexpr int INTERP_KMAX = 8;
+
+__global__ void __launch_bounds__(256)
+interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, const float* __restrict__ d2,
+                  int N, int M, int D, int K, float* __restrict__ out, float* __restrict__ coef) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    const float* __restrict__ fb = feat + (size_t)b * M * D;
+    for (int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < N; n += nw) {
+        const size_t base = ((size_t)b * N + n) * K;
+        float w[INTERP_KMAX];
+        int id[INTERP_KMAX];
+        float norm = 0.f;
+#pragma unroll
+        for (int k = 0; k < INTERP_KMAX; ++k)
+            if (k < K) {
+                id[k] = idx[base + k];
+                w[k] = __fdiv_rn(1.0f, __fadd_rn(d2[base + k], 1e-9f));       // common.py:119
+                norm = (k == 0) ? w[0] : __fadd_rn(norm, w[k]);              // common.py:120
+            }
+        if (coef && lane < K) {
+            float wl = 0.f;
+#pragma unroll
+            for (int k = 0; k < INTERP_KMAX; ++k) if (k == lane) wl = w[k];
+            coef[base + lane] = __fdiv_rn(wl, norm);
+        }
+        for (int c = lane; c < D; c += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < INTERP_KMAX; ++k)
+                if (k < K) {
+                    const float t = __fdiv_rn(__fmul_rn(fb[(size_t)id[k] * D + c], w[k]), norm);   // common.py:122
+                    acc = (k == 0) ? t : __fadd_rn(acc, t);
+                }
+            out[((size_t)b * N + n) * D + c] = acc;
+        }
+    }
+}
+
+// gfeat[b,m,:] = sum over incoming positions e = n*K + k of coef[e] * g[b,n,:]
+struct InterpBwdSrc {
+    const float* g; const float* cf; long N; int D; int K;
+    __device__ __forceinline__ const float* row(int b, int e) const { return g + ((size_t)b * N + e / K) * D; }
+    __device__ __forceinline__ float coef(int b, int e) const { return cf[(size_t)b * N * K + e]; }
+};
+struct InterpDst {
+    float* out; long M; int D;
+    __device__ __forceinline__ void store(int b, int s, int c, float v) const { out[((size_t)b * M + s) * D + c] = v; }
+};
+
+}  // namespace pcnbr
+
+using namespace pcnbr;
+
+extern "C" int pcnbr_interp_f32(const float* feat, const int32_t* idx, const float* d2, int B, int N, int M, int D,
+                                int K, float* out, float* coef, pcnbr_stream_t stream) {
+    if (!feat || !idx || !d2 || !out || B <= 0 || N <= 0 || M <= 0 || D <= 0 || K <= 0) return PCNBR_E_BADARG;
+    if (K > INTERP_KMAX) return PCNBR_E_TOOLARGE;
+    int gx = (N + 7) / 8;
+    if (gx > 148 * 8) gx = 148 * 8;
+    interp_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, K, out, coef);
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_interp_bwd_f32(const float* g, const float* coef, const int32_t* offsets, const int32_t* perm,
+                                    int B, int N, int M, int D, int K, float* gfeat, pcnbr_stream_t stream) {
+    if (!g || !coef || !offsets || !perm || !gfeat || B <= 0 || N <= 0 || M <= 0 || D <= 0 || K <= 0)
+        return PCNBR_E_BADARG;
+    InterpBwdSrc src{g, coef, (long)N, D, K};
+    InterpDst dst{gfeat, (long)M, D};
+    segsum_kernel<<<segsum_grid(M, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, M, N * K, D);
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,271 @@
+// select.cu -- K2 ball query, K3 xyz kNN (direct distances) and the generic expanded-form kNN.
+//
+// Reference: models/utils/common.py:54-61 (ball query inside group()), :110-114 (3-NN of
+// interpolate()), models/dgcnn/dgcnn.py:7-21 (knn()).  The reference materialises the full (B,M,N)
+// distance tensor and runs torch.topk over it; here one warp owns one query, source points stream
+// through a shared-memory tile shared by all warps of the CTA, and the warp keeps its K best
+// (key,index) pairs as a sorted list spread over its lanes (WarpList).  A candidate is compared
+// against the current K-th key first (one compare per point); only the rare survivors are inserted.
+// Nothing of size M*N is ever written.
+//
+// Ordering is the unsigned order of (ord(key) << 32 | index): ascending key, lowest index on ties.
+// Ball query needs no special padding code: out-of-ball points simply get key = +inf, so the K-list
+// fills with in-ball points by (d2,index) followed by the lowest-index out-of-ball points -- exactly
+// what a stable sort of the reference's masked distance row yields.
+#include "common.cuh"
+
+namespace pcnbr {
+
+constexpr int SEL_TILE = 1024;   // source points per shared-memory tile (12 KB SoA)
+
+template <int NSLOT, bool RADIUS>
+__global__ void __launch_bounds__(256)
+select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N, float r2, int K,
+                  int32_t* __restrict__ idx, float* __restrict__ d2out) {
+    __shared__ float sx[SEL_TILE], sy[SEL_TILE], sz[SEL_TILE];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool active = m < M;
+    const float* __restrict__ pb = p + (size_t)b * N * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        const float* c = q + ((size_t)b * M + m) * 3;
+        qx = c[0]; qy = c[1]; qz = c[2];
+    }
+    WarpList<NSLOT> list;
+    list.init();
+    u64 thr = PCNBR_KEY_MAX;
+
+    for (int t0 = 0; t0 < N; t0 += SEL_TILE) {
+        const int tn = min(SEL_TILE, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) {
+            const float v = pb[(size_t)t0 * 3 + i];
+            const int pt = i / 3, c = i - pt * 3;
+            (c == 0 ? sx : (c == 1 ? sy : sz))[pt] = v;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int c0 = 0; c0 < tn; c0 += 32) {
+            const int j = c0 + lane;
+            u64 key = PCNBR_KEY_MAX;
+            if (j < tn) {
+                float d2 = d2_direct(sx[j], sy[j], sz[j], qx, qy, qz);
+                if (RADIUS && !(d2 <= r2)) d2 = __int_as_float(0x7f800000);   // common.py:58-59
+                key = pack_key(f2ord(d2), (uint32_t)(t0 + j));
+            }
+            uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
+            while (pass) {
+                const int src = __ffs(pass) - 1;
+                pass &= pass - 1;
+                const u64 cand = shfl64(key, src);
+                if (cand < thr) {
+                    list.insert(cand, lane);
+                    thr = list.at(K - 1);
+                }
+            }
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int pos = s * 32 + lane;
+        if (pos < K) {
+            const size_t o = ((size_t)b * M + m) * K + pos;
+            idx[o] = (int32_t)(uint32_t)list.v[s];
+            if (d2out) d2out[o] = ord2f((uint32_t)(list.v[s] >> 32));
+        }
+    }
+}
+
+// ---- expanded-form kNN, any F (dgcnn.py:16-20) ------------------------------------------------
+
+// ATen's outer-dimension sum (torch.sum(x**2, dim=1), dgcnn.py:17), restated in oracle/canon.c:
+// cascade: rows accumulate in runs of 16 (acc0), runs fold into acc1, 16 runs into acc2, ...; tail rows
+// stay in acc0; result ((acc0+acc1)+acc2)+acc3.  Columns n < (N & ~31) cascade over all F rows; the
+// last N % 32 columns take ATen's ILP-4 path: four interleaved cascades (rows 4t+k), the F % 4
+// left-over rows added to partial 0, then ((p0+p1)+p2)+p3.
+__device__ __forceinline__ float cascade_sumsq(const float* __restrict__ xp, int count, size_t stride) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int i = 0;
+    while (i + 16 <= count) {
+        for (int j = 0; j < 16; ++j, ++i) {
+            const float v = xp[(size_t)i * stride];
+            acc0 = __fadd_rn(acc0, __fmul_rn(v, v));
+        }
+        acc1 = __fadd_rn(acc1, acc0); acc0 = 0.f;
+        if ((i & 0xf0) == 0) {
+            acc2 = __fadd_rn(acc2, acc1); acc1 = 0.f;
+            if ((i & 0xf00) == 0) { acc3 = __fadd_rn(acc3, acc2); acc2 = 0.f; }
+        }
+    }
+    for (; i < count; ++i) {
+        const float v = xp[(size_t)i * stride];
+        acc0 = __fadd_rn(acc0, __fmul_rn(v, v));
+    }
+    return __fadd_rn(__fadd_rn(__fadd_rn(acc0, acc1), acc2), acc3);
+}
+
+__global__ void sumsq_cascade_kernel(const float* __restrict__ x, int F, int N, long sf, long sn,
+                                     float* __restrict__ xx) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* __restrict__ xp = x + (size_t)b * F * N + (size_t)n * sn;
+    float r;
+    if (n < (N & ~31)) {
+        r = cascade_sumsq(xp, F, (size_t)sf);
+    } else {
+        const int q = F / 4;
+        float p0 = cascade_sumsq(xp, q, (size_t)sf * 4);
+        const float p1 = cascade_sumsq(xp + sf, q, (size_t)sf * 4);
+        const float p2 = cascade_sumsq(xp + 2 * sf, q, (size_t)sf * 4);
+        const float p3 = cascade_sumsq(xp + 3 * sf, q, (size_t)sf * 4);
+        for (int i = q * 4; i < F; ++i) {
+            const float v = xp[(size_t)i * sf];
+            p0 = __fadd_rn(p0, __fmul_rn(v, v));
+        }
+        r = __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3);
+    }
+    xx[(size_t)b * N + n] = r;
+}
+
+// dynamic smem: xs[F][TP] (TP = tile + 1 pad when staged transposed) + xq[WARPS][F] + sxx[tile]
+template <int NSLOT>
+__global__ void __launch_bounds__(1024)
+knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int F, int N, long sf, long sn,
+                  int K, int tile, int32_t* __restrict__ idx) {
+    extern __shared__ float smem[];
+    const int warps = blockDim.x >> 5;
+    const int TP = tile + 1;
+    float* xs = smem;                        // [F][TP]
+    float* xq = xs + (size_t)F * TP;         // [warps][F]
+    float* sxx = xq + (size_t)warps * F;     // [tile]
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * warps + warp;
+    const bool active = i < N;
+    const float* __restrict__ xb = x + (size_t)b * F * N;
+    const float* __restrict__ xxb = xx + (size_t)b * N;
+
+    if (active)
+        for (int f = lane; f < F; f += 32) xq[warp * F + f] = xb[(size_t)f * sf + (size_t)i * sn];
+    const float xxi = active ? xxb[i] : 0.f;
+    const float* __restrict__ myq = xq + warp * F;
+
+    WarpList<NSLOT> list;
+    list.init();
+    u64 thr = PCNBR_KEY_MAX;
+
+    for (int t0 = 0; t0 < N; t0 += tile) {
+        const int tn = min(tile, N - t0);
+        __syncthreads();
+        if (sn == 1) {          // channel-major source: consecutive threads -> consecutive points
+            for (int e = threadIdx.x; e < F * tn; e += blockDim.x) {
+                const int f = e / tn, j = e - f * tn;
+                xs[f * TP + j] = xb[(size_t)f * sf + (size_t)(t0 + j)];
+            }
+        } else {                // point-major source: consecutive threads -> consecutive channels
+            for (int e = threadIdx.x; e < F * tn; e += blockDim.x) {
+                const int j = e / F, f = e - j * F;
+                xs[f * TP + j] = xb[(size_t)f * sf + (size_t)(t0 + j) * sn];
+            }
+        }
+        for (int j = threadIdx.x; j < tn; j += blockDim.x) sxx[j] = xxb[t0 + j];
+        __syncthreads();
+        if (!active) continue;
+        for (int c0 = 0; c0 < tn; c0 += 32) {
+            const int j = c0 + lane;
+            u64 key = PCNBR_KEY_MAX;
+            if (j < tn) {
+                float c = __fmul_rn(myq[0], xs[j]);                     // sgemm: FMA chain over f
+                for (int f = 1; f < F; ++f) c = __fmaf_rn(myq[f], xs[f * TP + j], c);
+                const float inner = __fmul_rn(-2.0f, c);                // dgcnn.py:16
+                const float pd = __fsub_rn(__fsub_rn(-sxx[j], inner), xxi);   // dgcnn.py:18
+                key = pack_key(f2ord(-pd), (uint32_t)(t0 + j));        // largest pd first
+            }
+            uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
+            while (pass) {
+                const int src = __ffs(pass) - 1;
+                pass &= pass - 1;
+                const u64 cand = shfl64(key, src);
+                if (cand < thr) {
+                    list.insert(cand, lane);
+                    thr = list.at(K - 1);
+                }
+            }
+        }
+    }
+    if (!active) return;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        const int pos = s * 32 + lane;
+        if (pos < K) idx[((size_t)b * N + i) * K + pos] = (int32_t)(uint32_t)list.v[s];
+    }
+}
+
+static inline int expand_tile(int F) {
+    int t = (8192 / F) & ~31;
+    if (t < 32) t = 32;
+    if (t > 1024) t = 1024;
+    return t;
+}
+
+}  // namespace pcnbr
+
+using namespace pcnbr;
+
+template <bool RADIUS>
+static int launch_select(const float* q, const float* p, int B, int M, int N, float r2, int K, int32_t* idx,
+                         float* d2, cudaStream_t s) {
+    if (!q || !p || !idx || B <= 0 || M <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
+    if (K > 128) return PCNBR_E_TOOLARGE;
+    dim3 grid((M + 7) / 8, B), block(256);
+    if (K <= 32)      select_xyz_kernel<1, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2);
+    else if (K <= 64) select_xyz_kernel<2, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2);
+    else              select_xyz_kernel<4, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2);
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_ball_query_f32(const float* q, const float* p, int B, int M, int N, float r2, int K,
+                                    int32_t* idx, pcnbr_stream_t stream) {
+    return launch_select<true>(q, p, B, M, N, r2, K, idx, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M, int N, int K, int32_t* idx,
+                                    float* d2, pcnbr_stream_t stream) {
+    return launch_select<false>(q, p, B, M, N, 0.f, K, idx, d2, (cudaStream_t)stream);
+}
+
+extern "C" size_t pcnbr_knn_expand_ws_bytes(int B, int F, int N, int K) {
+    (void)F; (void)K;
+    return sizeof(float) * (size_t)B * (size_t)N;      // xx
+}
+
+extern "C" int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
+                                    int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (!x || !idx || B <= 0 || F <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
+    if (K > 128 || F > 256) return PCNBR_E_TOOLARGE;
+    if (!ws || ws_bytes < pcnbr_knn_expand_ws_bytes(B, F, N, K)) return PCNBR_E_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    float* xx = (float*)ws;
+    sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, stride_f, stride_n, xx);
+    PCNBR_CHECK_LAUNCH();
+    const int warps = (F >= 16) ? 32 : 8;
+    const int tile = expand_tile(F);
+    const size_t smem = sizeof(float) * ((size_t)F * (tile + 1) + (size_t)warps * F + tile);
+    dim3 grid((N + warps - 1) / warps, B), block(warps * 32);
+#define PCNBR_LAUNCH_EXPAND(NS)                                                                          \
+    do {                                                                                                 \
+        cudaError_t e = cudaFuncSetAttribute(knn_expand_kernel<NS>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e != cudaSuccess) return (int)e;                                                             \
+        knn_expand_kernel<NS><<<grid, block, smem, s>>>(x, xx, F, N, stride_f, stride_n, K, tile, idx);  \
+    } while (0)
+    if (K <= 32)      PCNBR_LAUNCH_EXPAND(1);
+    else if (K <= 64) PCNBR_LAUNCH_EXPAND(2);
+    else              PCNBR_LAUNCH_EXPAND(4);
+#undef PCNBR_LAUNCH_EXPAND
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's models/dgcnn/dgcnn.py on top of libpcnbr.
+
+knn / get_graph_feature / EdgeConv / DGCNN / DGCNNWithColor / get_model / get_loss keep the
+reference's signatures, return layouts and state_dict keys (/root/reference/models/dgcnn/dgcnn.py).
+Differences, all deliberate: the device comes from the input tensor (the reference asks
+torch.cuda.is_available(), dgcnn.py:39); ties in the k-NN selection go to the lowest index; the
+(B,N,N) distance matrix and the three (B,N,k,F)-sized temporaries are never materialised.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+__all__ = ["knn", "get_graph_feature", "EdgeConv", "DGCNN", "DGCNNWithColor", "get_model", "get_loss"]
+
+
+def knn(x: torch.Tensor, k: int) -> torch.Tensor:
+    """x (B,F,N) -> LongTensor (B,N,k) of the k nearest points in feature space, self first
+    [dgcnn.py:7-21]."""
+    return ops.knn_graph(x, k).long()
+
+
+def _point_major(x: torch.Tensor) -> torch.Tensor:
+    """(B,F,N) -> (B,N,F) contiguous; free when x is already a transposed view of point-major memory."""
+    return x.transpose(2, 1).contiguous()
+
+
+def get_graph_feature(x: torch.Tensor, k: int = 20, idx: torch.Tensor | None = None, dim9: bool = False):
+    """x (B,F,N) -> edge features (B,2F,N,k) = cat(x_j - x_i, x_i) [(B,3F,N,k) when dim9]
+    [dgcnn.py:24-57].  The result is laid out point-major in memory (channels-last)."""
+    B, N = x.size(0), x.size(2)
+    x = x.reshape(B, -1, N)
+    if idx is None:
+        idx32 = ops.knn_graph(x if not dim9 else x[:, 6:], k)
+    else:
+        idx32 = ops._as_i32(idx.reshape(B, N, -1))
+    nbr = ops.NeighborIndex(idx32, N)
+    out = ops.edge_features(_point_major(x), nbr).permute(0, 3, 1, 2)
+    if dim9:
+        out = torch.cat((out, out[:, x.size(1):]), dim=1)
+    return out
+
+
+class EdgeConv(nn.Module):
+    """get_graph_feature -> Conv2d 1x1 (no bias) -> BatchNorm2d -> LeakyReLU(0.2) -> max over k
+    [dgcnn.py:60-77]."""
+
+    def __init__(self, in_channels, out_channels, k=20):
+        super().__init__()
+        self.k = k
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_channels * 2, out_channels, kernel_size=1, bias=False),
+            nn.BatchNorm2d(out_channels),
+            nn.LeakyReLU(negative_slope=0.2),
+        )
+
+    def forward(self, x):
+        x = get_graph_feature(x, k=self.k)
+        x = self.conv(x)
+        return ops.max_pool_neighbors(x, -1)
+
+
+def _pointwise(cin, cout, dropout=None):
+    layers = [nn.Conv1d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm1d(cout), nn.LeakyReLU(negative_slope=0.2)]
+    if dropout is not None:
+        layers.append(nn.Dropout(dropout))
+    return nn.Sequential(*layers)
+
+
+class DGCNN(nn.Module):
+    """DGCNN semantic segmentation on xyz   [dgcnn.py:80-162].  Returns (logits (B,N,cls), x5, None)."""
+
+    def __init__(self, num_classes=13, k=20, emb_dims=1024, dropout=0.5):
+        super().__init__()
+        self.k = k
+        self.num_classes = num_classes
+        self.conv1 = EdgeConv(3, 64, k)
+        self.conv2 = EdgeConv(64, 64, k)
+        self.conv3 = EdgeConv(64, 64, k)
+        self.conv4 = EdgeConv(64, 128, k)
+        self.conv5 = _pointwise(320, emb_dims)
+        self.conv6 = _pointwise(emb_dims + 320, 512, dropout)
+        self.conv7 = _pointwise(512, 256, dropout)
+        self.conv8 = nn.Conv1d(256, num_classes, kernel_size=1)
+
+    def forward(self, x):
+        xyz = x[:, :3, :] if x.size(1) == 6 else x
+        x1 = self.conv1(xyz)
+        x2 = self.conv2(x1)
+        x3 = self.conv3(x2)
+        x4 = self.conv4(x3)
+        x_cat = torch.cat((x1, x2, x3, x4), dim=1)
+        x5 = self.conv5(x_cat)
+        x7 = self.conv7(self.conv6(torch.cat((x_cat, x5), dim=1)))
+        logits = self.conv8(x7).transpose(2, 1).contiguous()
+        return logits, x5, None
+
+
+class DGCNNWithColor(nn.Module):
+    """DGCNN with an RGB branch   [dgcnn.py:165-257]; expects (B,6,N), raises ValueError otherwise."""
+
+    def __init__(self, num_classes=13, k=20, emb_dims=1024, dropout=0.5):
+        super().__init__()
+        self.k = k
+        self.num_classes = num_classes
+        self.conv1 = EdgeConv(3, 64, k)
+        self.conv2 = EdgeConv(64, 64, k)
+        self.conv3 = EdgeConv(64, 64, k)
+        self.conv4 = EdgeConv(64, 128, k)
+        self.color_conv = _pointwise(3, 64)
+        self.conv5 = _pointwise(384, emb_dims)
+        self.conv6 = _pointwise(emb_dims + 384, 512, dropout)
+        self.conv7 = _pointwise(512, 256, dropout)
+        self.conv8 = nn.Conv1d(256, num_classes, kernel_size=1)
+
+    def forward(self, x):
+        if x.size(1) != 6:
+            raise ValueError("DGCNNWithColor expects 6-channel input (xyz + rgb)")
+        x1 = self.conv1(x[:, :3, :])
+        x2 = self.conv2(x1)
+        x3 = self.conv3(x2)
+        x4 = self.conv4(x3)
+        color_feat = self.color_conv(x[:, 3:6, :])
+        x_cat = torch.cat((x1, x2, x3, x4, color_feat), dim=1)
+        x5 = self.conv5(x_cat)
+        x7 = self.conv7(self.conv6(torch.cat((x_cat, x5), dim=1)))
+        logits = self.conv8(x7).transpose(2, 1).contiguous()
+        return logits, x5, None
+
+
+def get_model(num_classes=13, use_color=True, **kwargs):
+    """[dgcnn.py:260-273]"""
+    return DGCNNWithColor(num_classes=num_classes, **kwargs) if use_color else DGCNN(num_classes=num_classes, **kwargs)
+
+
+def get_loss():
+    """[dgcnn.py:276-280]"""
+    return nn.CrossEntropyLoss(ignore_index=-1)

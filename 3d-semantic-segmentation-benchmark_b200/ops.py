@@ -1,0 +1,361 @@
+"""Primitive neighbourhood ops on CUDA tensors, bound to libpcnbr.so (include/pcnbr.h).
+
+North-star primitive names (index-returning): farthest_point_sample, query_ball_point, knn_points,
+knn_graph, square_distance, index_points; plus the fused value ops with autograd: group_points,
+max_pool_neighbors, three_interpolate, edge_features.
+
+Host code is plumbing only (shape checks, output allocation, stream handle, autograd wiring).  There
+is no CPU path: CPU tensors raise.  Reference citations are relative to /root/reference/.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+__all__ = [
+    "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
+    "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
+    "edge_features",
+]
+
+
+# ----------------------------------------------------------------------------- plumbing
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"pcnbr: {name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"pcnbr: {name} must be a CUDA tensor (this build has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"pcnbr: {name} must be {dtype}, got {t.dtype}")
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 4), dtype=torch.uint8, device=device)
+
+
+def _as_i32(idx: torch.Tensor) -> torch.Tensor:
+    if idx.dtype == torch.int32:
+        return _c(idx)
+    if idx.dtype == torch.int64:
+        return idx.to(torch.int32).contiguous()
+    raise TypeError(f"pcnbr: index tensor must be int32 or int64, got {idx.dtype}")
+
+
+class NeighborIndex:
+    """A neighbour table idx (B,M,K) int32 into N source points, with its lazily built inverse
+    (CSR by source point) that the atomic-free backward kernels consume."""
+
+    __slots__ = ("idx", "num_src", "_csr")
+
+    def __init__(self, idx: torch.Tensor, num_src: int):
+        _check(idx, "idx", torch.int32)
+        self.idx = _c(idx)
+        self.num_src = int(num_src)
+        self._csr = None
+
+    def csr(self):
+        """(offsets (B,N+1) int32, perm (B,E) int32): positions grouped by source, ascending."""
+        if self._csr is None:
+            B = self.idx.shape[0]
+            E = self.idx[0].numel()
+            N = self.num_src
+            dev = self.idx.device
+            offsets = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
+            perm = torch.empty(B, E, dtype=torch.int32, device=dev)
+            nb = _lib.size("pcnbr_csr_ws_bytes", B, E, N)
+            ws = _ws(nb, dev)
+            _lib.call("pcnbr_csr_build", self.idx.data_ptr(), B, E, N, offsets.data_ptr(), perm.data_ptr(),
+                      ws.data_ptr(), nb, _stream())
+            self._csr = (offsets, perm)
+        return self._csr
+
+
+# ----------------------------------------------------------------------------- index-returning primitives
+
+
+def farthest_point_sample(xyz: torch.Tensor, C: int, start_idx: torch.Tensor | None = None,
+                          return_coords: bool = False):
+    """K1.  xyz (B,N,3) -> picked indices (B,C) int32 [and coords (B,C,3)].
+
+    Same picks as the loop of models/utils/common.py:25-31.  `start_idx` (B,) is the first pick; when
+    None it is drawn exactly as the reference does (common.py:22: torch.randint(0, N, (B,),
+    dtype=torch.int, device=coords.device)), so the generator is consumed identically."""
+    _check(xyz, "xyz")
+    if xyz.dim() != 3 or xyz.shape[-1] != 3:
+        raise ValueError(f"pcnbr: xyz must be (B,N,3), got {tuple(xyz.shape)}")
+    B, N, _ = xyz.shape
+    C = int(C)
+    if C <= 0:
+        raise ValueError("pcnbr: C must be positive")
+    xyz = _c(xyz)
+    if start_idx is None:
+        start_idx = torch.randint(0, N, (B,), dtype=torch.int, device=xyz.device)
+    start = start_idx.to(device=xyz.device, dtype=torch.int32).contiguous()
+    if start.shape != (B,):
+        raise ValueError("pcnbr: start_idx must have shape (B,)")
+    idx = torch.empty(B, C, dtype=torch.int32, device=xyz.device)
+    out = torch.empty(B, C, 3, dtype=torch.float32, device=xyz.device)
+    nb = _lib.size("pcnbr_fps_ws_bytes", B, N)
+    ws = _ws(nb, xyz.device)
+    _lib.call("pcnbr_fps_f32", xyz.data_ptr(), B, N, C, start.data_ptr(), idx.data_ptr(), out.data_ptr(),
+              ws.data_ptr(), nb, _stream())
+    return (idx, out) if return_coords else idx
+
+
+def _r2(r: float) -> float:
+    # the reference compares fp32 distances with the python double r**2 -> fp32(double(r)**2)
+    return torch.tensor(float(r) ** 2, dtype=torch.float32).item()
+
+
+def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+    """K2.  xyz (B,N,3) points, new_xyz (B,M,3) centroids -> idx (B,M,nsample) int32.
+
+    The selection of models/utils/common.py:54-61 with the canonical tie rule: in-ball points by
+    ascending (squared distance, index), then -- if the ball holds fewer than nsample points -- the
+    out-of-ball points in ascending index (what a stable sort of the masked distance row gives)."""
+    _check(xyz, "xyz"); _check(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    K = int(nsample)
+    if K > N:
+        raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={N})")   # torch.topk's error
+    xyz, new_xyz = _c(xyz), _c(new_xyz)
+    idx = torch.empty(B, M, K, dtype=torch.int32, device=xyz.device)
+    _lib.call("pcnbr_ball_query_f32", new_xyz.data_ptr(), xyz.data_ptr(), B, M, N, _r2(radius), K,
+              idx.data_ptr(), _stream())
+    return idx
+
+
+def knn_points(query: torch.Tensor, src: torch.Tensor, k: int):
+    """K3 (direct form).  query (B,M,3), src (B,N,3) -> (idx (B,M,k) int32, d2 (B,M,k)): the k smallest
+    ((src - query)**2).sum(-1), ascending, lowest index on ties (models/utils/common.py:110-114)."""
+    _check(query, "query"); _check(src, "src")
+    B, M, _ = query.shape
+    N = src.shape[1]
+    k = int(k)
+    if k > N:
+        raise RuntimeError(f"pcnbr: selected index k out of range (k={k} > N={N})")
+    query, src = _c(query), _c(src)
+    idx = torch.empty(B, M, k, dtype=torch.int32, device=src.device)
+    d2 = torch.empty(B, M, k, dtype=torch.float32, device=src.device)
+    _lib.call("pcnbr_knn_direct_f32", query.data_ptr(), src.data_ptr(), B, M, N, k, idx.data_ptr(),
+              d2.data_ptr(), _stream())
+    return idx, d2
+
+
+def knn_graph(x: torch.Tensor, k: int) -> torch.Tensor:
+    """K3/K4 (expanded form).  x (B,F,N) in any (F,N) layout -> idx (B,N,k) int32: the k largest
+    -xx_j + 2 x_i.x_j - xx_i per row, i.e. models/dgcnn/dgcnn.py:16-20 with lowest index on ties."""
+    _check(x, "x")
+    if x.dim() != 3:
+        raise ValueError(f"pcnbr: x must be (B,F,N), got {tuple(x.shape)}")
+    B, F, N = x.shape
+    k = int(k)
+    if k > N:
+        raise RuntimeError(f"pcnbr: selected index k out of range (k={k} > N={N})")
+    sb, sf, sn = x.stride()
+    if not (sb == F * N and ((sn == 1 and sf == N) or (sf == 1 and sn == F))):
+        x = x.contiguous()
+        sf, sn = N, 1
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
+    nb = _lib.size("pcnbr_knn_expand_ws_bytes", B, F, N, k)
+    ws = _ws(nb, x.device)
+    _lib.call("pcnbr_knn_expand_f32", x.data_ptr(), B, F, N, sf, sn, k, idx.data_ptr(), ws.data_ptr(), nb, _stream())
+    return idx
+
+
+def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """(B,N,3),(B,M,3) -> (B,N,M) squared distances ((dst - src)**2).sum(-1).  Debug/inspection helper
+    only (plain torch; the kernels never materialise this matrix)."""
+    _check(src, "src"); _check(dst, "dst")
+    return ((dst.unsqueeze(1) - src.unsqueeze(2)) ** 2).sum(dim=-1)
+
+
+def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """points (B,N,D), idx (B,M,K) or (B,M) -> points[b, idx] (the gathers of common.py:64-65,117)."""
+    _check(points, "points")
+    squeeze = idx.dim() == 2
+    idx3 = idx.unsqueeze(-1) if squeeze else idx
+    B, N, D = points.shape
+    zeros = torch.zeros(B, idx3.shape[1], 3, dtype=torch.float32, device=points.device)
+    pz = torch.zeros(B, N, 3, dtype=torch.float32, device=points.device)
+    out = group_points(pz, points, zeros, NeighborIndex(_as_i32(idx3), N), None)[..., 3:]
+    return out.squeeze(2) if squeeze else out
+
+
+# ----------------------------------------------------------------------------- K5 group (+ K7 backward)
+
+
+class _GroupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, features, centroids, nbr: NeighborIndex, rdiv: float):
+        B, N, _ = coords.shape
+        M, K = nbr.idx.shape[1], nbr.idx.shape[2]
+        D = features.shape[2]
+        out = torch.empty(B, M, K, 3 + D, dtype=torch.float32, device=coords.device)
+        _lib.call("pcnbr_group_f32", coords.data_ptr(), features.data_ptr() if D else None, centroids.data_ptr(),
+                  nbr.idx.data_ptr(), B, N, M, K, D, float(rdiv), out.data_ptr(), _stream())
+        ctx.nbr = nbr
+        ctx.dims = (B, N, M, K, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, N, M, K, D = ctx.dims
+        if D == 0 or not ctx.needs_input_grad[1]:
+            return None, None, None, None, None
+        gout = _c(gout)
+        offsets, perm = ctx.nbr.csr()
+        gfeat = torch.empty(B, N, D, dtype=torch.float32, device=gout.device)
+        _lib.call("pcnbr_group_bwd_f32", gout.data_ptr(), offsets.data_ptr(), perm.data_ptr(), B, N, M * K, D,
+                  gfeat.data_ptr(), _stream())
+        return None, gfeat, None, None, None
+
+
+def group_points(coords, features, centroids, nbr: NeighborIndex, r_div: float | None):
+    """K5.  -> (B,M,K,3+D): [coords[idx] - centroid (optionally / r_div), features[idx]]
+    (models/utils/common.py:62-71).  Differentiable w.r.t. `features` only: the reference models never
+    need coordinate gradients, and asking for them raises."""
+    _check(coords, "coords"); _check(features, "features"); _check(centroids, "centroids")
+    if coords.requires_grad or centroids.requires_grad:
+        raise NotImplementedError("pcnbr: gradients w.r.t. coordinates are not implemented")
+    rdiv = 0.0 if r_div is None else torch.tensor(float(r_div), dtype=torch.float32).item()
+    return _GroupFn.apply(_c(coords), _c(features), _c(centroids), nbr, rdiv)
+
+
+# ----------------------------------------------------------------------------- K6 max-pool over neighbours
+
+
+def _pool_plan(x: torch.Tensor, dim: int):
+    """Map a 4-D tensor and its neighbour axis onto (R, K, D, stride_r, stride_k, stride_d) without a
+    copy when the layout allows; returns (x, plan, out_view_fn)."""
+    if x.dim() != 4:
+        raise ValueError("pcnbr: max-pool expects a 4-D tensor")
+    dim = dim % 4
+    if dim == 2:                                   # (B,C,K,D) -> (B,C,D)      common.py:85-86
+        B, C, K, D = x.shape
+        if not (x.stride(3) == 1 and (B == 1 or x.stride(0) == C * x.stride(1))):
+            x = x.contiguous()
+        plan = (B * C, K, D, x.stride(1), x.stride(2), 1)
+        return x, plan, (lambda o: o.view(B, C, D)), (lambda g: _c(g))
+    if dim == 3:                                   # (B,O,N,K) -> (B,O,N)      dgcnn.py:76
+        B, O, N, K = x.shape
+        if x.stride(1) == 1 and (B == 1 or x.stride(0) == N * x.stride(2)):      # channels-last memory
+            plan = (B * N, K, O, x.stride(2), x.stride(3), 1)
+            return x, plan, (lambda o: o.view(B, N, O).permute(0, 2, 1)), (lambda g: _c(g.permute(0, 2, 1)))
+        x = _c(x)
+        plan = (B * O * N, K, 1, K, 1, 1)
+        return x, plan, (lambda o: o.view(B, O, N)), (lambda g: _c(g))
+    raise ValueError("pcnbr: max-pool supports dim=2 of (B,C,K,D) and dim=-1 of (B,O,N,K)")
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dim):
+        x, plan, view, gprep = _pool_plan(x, dim)
+        R, K, D, sr, sk, sd = plan
+        out = torch.empty(R * D, dtype=torch.float32, device=x.device)
+        arg = torch.empty(R * D, dtype=torch.uint8, device=x.device)
+        _lib.call("pcnbr_maxpool_f32", x.data_ptr(), R, K, D, sr, sk, sd, out.data_ptr(), arg.data_ptr(), _stream())
+        ctx.plan, ctx.gprep = plan, gprep
+        ctx.xmeta = (tuple(x.shape), tuple(x.stride()))
+        ctx.save_for_backward(arg)
+        return view(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        R, K, D, sr, sk, sd = ctx.plan
+        g = ctx.gprep(g)
+        shape, stride = ctx.xmeta
+        gx = torch.empty_strided(shape, stride, dtype=torch.float32, device=g.device)
+        _lib.call("pcnbr_maxpool_bwd_f32", g.data_ptr(), arg.data_ptr(), R, K, D, sr, sk, sd, gx.data_ptr(), _stream())
+        return gx, None
+
+
+def max_pool_neighbors(x: torch.Tensor, dim: int = 2) -> torch.Tensor:
+    """K6.  Max over the neighbour axis: dim=2 of (B,C,K,D) (reduce(), common.py:85-86) or dim=-1 of
+    (B,O,N,k) (EdgeConv, dgcnn.py:76).  First maximum wins, as torch.max."""
+    _check(x, "x")
+    if x.shape[dim] > 255:
+        raise RuntimeError("pcnbr: neighbour axis longer than 255 is not supported")
+    return _MaxPoolFn.apply(x, dim)
+
+
+# ----------------------------------------------------------------------------- K8 three-point interpolation
+
+
+class _InterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, nbr: NeighborIndex, d2):
+        B, M, D = feats.shape
+        N, K = nbr.idx.shape[1], nbr.idx.shape[2]
+        out = torch.empty(B, N, D, dtype=torch.float32, device=feats.device)
+        coef = torch.empty(B, N, K, dtype=torch.float32, device=feats.device)
+        _lib.call("pcnbr_interp_f32", feats.data_ptr(), nbr.idx.data_ptr(), d2.data_ptr(), B, N, M, D, K,
+                  out.data_ptr(), coef.data_ptr(), _stream())
+        ctx.nbr, ctx.dims = nbr, (B, N, M, D, K)
+        ctx.save_for_backward(coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (coef,) = ctx.saved_tensors
+        B, N, M, D, K = ctx.dims
+        g = _c(g)
+        offsets, perm = ctx.nbr.csr()
+        gfeat = torch.empty(B, M, D, dtype=torch.float32, device=g.device)
+        _lib.call("pcnbr_interp_bwd_f32", g.data_ptr(), coef.data_ptr(), offsets.data_ptr(), perm.data_ptr(),
+                  B, N, M, D, K, gfeat.data_ptr(), _stream())
+        return gfeat, None, None
+
+
+def three_interpolate(feats: torch.Tensor, nbr: NeighborIndex, d2: torch.Tensor) -> torch.Tensor:
+    """K8.  feats (B,M,D) coarse features, nbr/d2 from knn_points(fine, coarse, k) -> (B,N,D):
+    inverse-SQUARED-distance weighted mean, w = 1/(d2 + 1e-9) (models/utils/common.py:115-122)."""
+    _check(feats, "feats"); _check(d2, "d2")
+    if nbr.idx.shape[2] > 8:
+        raise RuntimeError("pcnbr: interpolate supports k <= 8")
+    return _InterpFn.apply(_c(feats), nbr, _c(d2))
+
+
+# ----------------------------------------------------------------------------- K9 edge features
+
+
+class _EdgeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xt, nbr: NeighborIndex):
+        B, N, F = xt.shape
+        K = nbr.idx.shape[2]
+        out = torch.empty(B, N, K, 2 * F, dtype=torch.float32, device=xt.device)
+        _lib.call("pcnbr_edge_feature_f32", xt.data_ptr(), nbr.idx.data_ptr(), B, N, F, K, out.data_ptr(), _stream())
+        ctx.nbr, ctx.dims = nbr, (B, N, F, K)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N, F, K = ctx.dims
+        g = _c(g)
+        offsets, perm = ctx.nbr.csr()
+        gxt = torch.empty(B, N, F, dtype=torch.float32, device=g.device)
+        _lib.call("pcnbr_edge_feature_bwd_f32", g.data_ptr(), offsets.data_ptr(), perm.data_ptr(), B, N, F, K,
+                  gxt.data_ptr(), _stream())
+        return gxt, None
+
+
+def edge_features(xt: torch.Tensor, nbr: NeighborIndex) -> torch.Tensor:
+    """K9.  xt (B,N,F) point-major, nbr over the same N points -> (B,N,k,2F) point-major:
+    [x_j - x_i, x_i] (models/dgcnn/dgcnn.py:47-53).  `.permute(0,3,1,2)` is the reference's (B,2F,N,k)."""
+    _check(xt, "xt")
+    return _EdgeFn.apply(_c(xt), nbr)

@@ -1,0 +1,61 @@
+"""Training-step plumbing around the hot path: the masked one-hot cross entropy the reference's
+train.py uses, and a batch-sharded data-parallel gradient exchange (one flat fp32 bucket, one NCCL
+all-reduce per step over NVLink).  The reference itself is single-device; per-cloud
+ops are independent, so the only collective is the gradient sum.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def masked_onehot_cross_entropy(logits: torch.Tensor, targets_onehot: torch.Tensor, pad_starts: torch.Tensor):
+    """Mean cross entropy over the unpadded points; same value as the reference's
+    Training/train_model.py:15-57 but without its host sync (`total_non_pad.item()`, :53)."""
+    B, L, _ = logits.shape
+    logp = F.log_softmax(logits, dim=-1)
+    tok = -(targets_onehot.to(logp.dtype) * logp).sum(dim=-1)
+    mask = (torch.arange(L, device=logits.device).unsqueeze(0) < pad_starts.to(logits.device).long().unsqueeze(1)).to(logp.dtype)
+    return (tok * mask).sum() / mask.sum().clamp_min(1.0)
+
+
+class FlatGradBucket:
+    """All parameter gradients live in ONE contiguous fp32 buffer (p.grad are views into it), so the
+    data-parallel exchange is a single all-reduce of 4-17 MB instead of 90-150 small ones, and
+    zeroing the gradients is one memset."""
+
+    def __init__(self, module: torch.nn.Module, group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self) -> None:
+        """Sum the bucket over ranks and divide by the world size (standard DDP semantics)."""
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Make every rank start from rank `src`'s parameters and buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def shard_batch(n_clouds: int, rank: int, world: int) -> slice:
+    """Contiguous slice of the global batch owned by `rank` (clouds are independent units)."""
+    per = (n_clouds + world - 1) // world
+    return slice(min(rank * per, n_clouds), min((rank + 1) * per, n_clouds))

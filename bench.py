@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- train points/s of the neighbourhood hot path behind the reference's model interface.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model dgcnn|pointnetpp|pointnext]
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU, NCCL)
+
+A step = one full train step (forward + backward + Adam, lr 1e-3 as the reference's train.py:17,79) of
+the model on one batch of synthetic S3DIS-shaped blocks; every neighbourhood op runs in libpcnbr
+(hand-written sm_100a kernels through the C ABI), the 1x1 convolutions / BatchNorm are library calls.
+Default workload = BASELINE.json configs[1]: DGCNN (DGCNNWithColor, the class train.py builds) k=20,
+batch 16 x 4096 points per GPU, 13 classes, strict fp32 (TF32 off).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_POINTS = 4096
+N_CLASSES = 13
+METRIC = "train_points_per_sec"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "pointnetpp", "pointnext"])
+    ap.add_argument("--batch", type=int, default=0, help="clouds per GPU (default 16 dgcnn / 32 pointnet++)")
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="clouds per CPU-baseline step (bounded sample)")
+    return ap.parse_args()
+
+
+def default_batch(model):
+    return {"dgcnn": 16, "pointnetpp": 32, "pointnext": 4}[model]
+
+
+def workload_name(model, B, N):
+    return {
+        "dgcnn": f"DGCNNWithColor semseg k=20 emb=1024, batch {B} x {N} pts x 6 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
+        "pointnetpp": f"PointNet++ SSG semseg, batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
+        "pointnext": f"PointNeXt semseg, batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
+    }[model]
+
+
+# --------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- data / models
+
+
+def model_input(model, pts):
+    # train.py feeds (B,N,9); DGCNNWithColor wants (B,6,N) (adapter outside the reference files)
+    return pts[:, :, :6].transpose(1, 2) if model == "dgcnn" else pts
+
+
+def build_model(impl_pkg, model):
+    if model == "dgcnn":
+        return impl_pkg.DGCNNWithColor(num_classes=N_CLASSES, k=20)
+    if model == "pointnetpp":
+        return impl_pkg.PointNetpp(N_CLASSES)
+    return impl_pkg.PointNeXt(N_CLASSES)
+
+
+def logits_of(out):
+    return out[0] if isinstance(out, tuple) else out
+
+
+# --------------------------------------------------------------------------- reference arm / cpu baseline
+
+
+def cpu_reference_steps(model, cloud_batch, N, steps, warmup):
+    """The reference's own CPU implementation of the path (oracle/ref_ops.py: the same ATen op sequence,
+    raw torch.topk selection) timed on the host cores: fwd + bwd + Adam on `cloud_batch` clouds."""
+    from oracle import ref_ops as O
+    s3dis_blocks = O.s3dis_blocks
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    net = {"dgcnn": lambda: O.DGCNNWithColor(N_CLASSES, k=20, tie="raw"),
+           "pointnetpp": lambda: O.PointNetpp(N_CLASSES, tie="raw"),
+           "pointnext": lambda: O.PointNeXt(N_CLASSES, tie="raw")}[model]()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    pts, lab, lens = s3dis_blocks(cloud_batch, N, 0, N_CLASSES)
+
+    def ce(logits, onehot, lens):
+        logp = torch.log_softmax(logits, dim=-1)
+        tok = -(onehot.float() * logp).sum(-1)
+        mask = (torch.arange(logits.shape[1]).unsqueeze(0) < lens.unsqueeze(1)).float()
+        return (tok * mask).sum() / mask.sum()
+
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = ce(logits_of(net(model_input(model, pts))), lab, lens)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.cpu_batch
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    times, cores = cpu_reference_steps(args.model, B, args.points, steps, warmup)
+    ms = 1e3 * sum(times) / len(times)
+    value = B * args.points / (ms / 1e3)
+    sample = f"{steps} steps of {B} clouds x {args.points} pts (bounded sample of the per-GPU batch), {warmup} warm-up, mean"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic S3DIS-shaped blocks, random-init weights",
+        "config": {"workload": workload_name(args.model, args.batch or default_batch(args.model), args.points),
+                   "reference_path": "oracle port of the reference's torch CPU path (the Python reference does not travel to the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+
+
+def roofline_for(model, timing, B, N, peaks):
+    """Dominant libpcnbr kernel of the timed steps, against the roofline that bounds it."""
+    if not timing:
+        return None
+    name, (calls, ms) = max(timing.items(), key=lambda kv: kv[1][1])
+    per_launch_s = ms / 1e3 / max(calls, 1)
+    k, F = 20, 64
+    alg = {
+        # algorithmic bytes / flops per launch (SURVEY.md §8d figures x units per launch)
+        "pcnbr_knn_expand_f32": ("tensor", 2.0 * N * N * F * B, "TFLOP/s", 1e12),
+        "pcnbr_edge_feature_f32": ("hbm", B * (8.0 * F * N * k + 4.0 * F * N + 4.0 * N * k), "GB/s", 1e9),
+        "pcnbr_edge_feature_bwd_f32": ("hbm", B * (8.0 * F * N * k + 4.0 * F * N + 8.0 * N * k), "GB/s", 1e9),
+        "pcnbr_maxpool_f32": ("hbm", B * (4.0 * N * k * F + 5.0 * N * F), "GB/s", 1e9),
+        "pcnbr_maxpool_bwd_f32": ("hbm", B * (4.0 * N * k * F + 5.0 * N * F), "GB/s", 1e9),
+    }.get(name)
+    if alg is None:
+        return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
+                "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls}
+    bound, work, unit, scale = alg
+    achieved = work / per_launch_s / scale
+    peak = peaks["hbm_gbs"] if bound == "hbm" else peaks["tf32_tflops"]
+    return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls, "peak_source": peaks["source"],
+            "note": "per-launch work is the mean over this entry point's calls in a step (layer shapes differ)"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf32_tflops": d["bf16_tflops_sustained"] / 2, "source": "MEASURED_PEAKS.json (tf32 = sustained bf16 / 2)"}
+    return {"hbm_gbs": 6650.0, "tf32_tflops": 700.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False       # strict fp32, as the north-star parity bar
+    torch.backends.cudnn.allow_tf32 = False
+
+    pkg = ge.load_package()
+    pkg._lib.load()
+    s3dis_blocks = pkg.synthetic.s3dis_blocks
+    B = args.batch or default_batch(args.model)
+    N = args.points
+    torch.manual_seed(0)
+    net = build_model(pkg, args.model).to(dev)
+    pkg.train.broadcast_parameters(net)
+    bucket = pkg.train.FlatGradBucket(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+    n_batches = 4                                        # rotate inputs; activations (GBs) >> L2 anyway
+    host, devb = [], []
+    for i in range(n_batches):
+        pts, lab, lens = s3dis_blocks(B, N, seed=1000 * rank + i, classes=N_CLASSES)
+        host.append((pts.pin_memory(), lab.pin_memory(), lens.pin_memory()))
+        devb.append((pts.to(dev), lab.to(dev), lens.to(dev)))
+
+    def step(pts, lab, lens):
+        bucket.zero()
+        loss = pkg.train.masked_onehot_cross_entropy(logits_of(net(model_input(args.model, pts))), lab, lens)
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(region_steps, from_host):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        last = None
+        for i in range(region_steps):
+            if from_host:
+                hp, hl, hn = host[i % n_batches]
+                pts, lab, lens = hp.to(dev, non_blocking=True), hl.to(dev, non_blocking=True), hn.to(dev, non_blocking=True)
+                last = step(pts, lab, lens).item()       # D2H read of the step's loss
+            else:
+                last = step(*devb[i % n_batches])
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, last
+
+    for i in range(args.warmup):
+        step(*devb[i % n_batches])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = pkg._lib.launches
+    pkg._lib.start_timing()
+    ms_total, _ = timed(args.steps, from_host=False)
+    timing = pkg._lib.stop_timing()
+    launches = pkg._lib.launches - launches0
+    ms_e2e, last_loss = timed(args.steps, from_host=True)
+    clk = clocks.stop() if rank == 0 else None
+
+    pts_per_step = B * N * world
+    value = pts_per_step * args.steps / (ms_total / 1e3)
+    e2e = pts_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    peaks = load_peaks()
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_reference_steps(args.model, args.cpu_batch, N, 2, 1)
+        cms = sum(times) / len(times)
+        cpu_base = {"value": args.cpu_batch * N / cms, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"2 steps of {args.cpu_batch} clouds x {N} pts (oracle port of the reference's torch CPU path), 1 warm-up, mean"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic S3DIS-shaped blocks (SURVEY.md 8d generator), random-init weights",
+            "config": {"workload": workload_name(args.model, B, N), "global_batch": B * world, "parallelism": f"dp{world}",
+                       "precision": "strict fp32 (TF32 disabled for cuBLAS and cuDNN)",
+                       "l2": "no explicit flush: per-step activations (GBs) far exceed the 126 MB L2; 4 input batches rotate"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "loss": last_loss},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": roofline_for(args.model, timing, B, N, peaks),
+            "cpu_baseline": cpu_base,
+            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(timing.items(), key=lambda kv: -kv[1][1])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

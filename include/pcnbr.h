@@ -1,0 +1,125 @@
+/*
+ * pcnbr.h -- C ABI of libpcnbr.so: the B200 (sm_100a) point-cloud neighbourhood hot path.
+ *
+ * The reference (piotr-bledowski/3D-Semantic-Segmentation-Benchmark) has no FFI layer: the seam is
+ * the set of Python functions in models/utils/common.py and models/dgcnn/dgcnn.py.  Each entry point
+ * below replaces the op sequence of the cited reference lines; the Python host layer
+ * (3d-semantic-segmentation-benchmark_b200/) binds them with ctypes and keeps the reference's
+ * signatures.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain device pointers, row-major contiguous unless a stride argument says otherwise;
+ *     the caller owns every buffer (including workspaces, sized by the *_ws_bytes helpers);
+ *   - fp32 values, int32 indices (the reference's int64 topk indices are widened by the host);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, never
+ *     synchronises the host, keeps no global state and is re-entrant;
+ *   - return value: 0 on success, otherwise a cudaError_t (>0) or PCNBR_E_* (<0); never throws.
+ *   - selection order everywhere: ascending (key, index) -- "lowest index wins" on equal keys.
+ */
+#ifndef PCNBR_H_
+#define PCNBR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCNBR_ABI_VERSION 1
+
+#define PCNBR_E_BADARG   (-1)   /* null pointer, non-positive size, K > N ... */
+#define PCNBR_E_TOOLARGE (-2)   /* outside the compiled limits (K > 128, F > 256, ...) */
+#define PCNBR_E_WORKSPACE (-3)  /* workspace missing or too small */
+
+#if defined(__GNUC__)
+#define PCNBR_API __attribute__((visibility("default")))
+#else
+#define PCNBR_API
+#endif
+
+typedef void* pcnbr_stream_t;
+
+PCNBR_API int pcnbr_abi_version(void);
+/* Human-readable text for a return code of this library. */
+PCNBR_API const char* pcnbr_error_string(int code);
+
+/* ---- K1 farthest point sampling ------------------------------------------ common.py:6-34
+ * xyz (B,N,3); start (B) first pick per cloud (the reference's randint draw, common.py:22);
+ * idx_out (B,C); xyz_out (B,C,3) = xyz[b, idx] (what sample() returns), may be NULL.
+ * dist = sqrt_rn(fma(dz,dz,fma(dy,dy,dx*dx))), running min, argmax with lowest index on ties.
+ * ws: pcnbr_fps_ws_bytes(B,N) bytes (0 when N <= 8192). */
+PCNBR_API size_t pcnbr_fps_ws_bytes(int B, int N);
+PCNBR_API int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_t* start,
+                  int32_t* idx_out, float* xyz_out, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
+/* ---- K2 ball query ------------------------------------------------------- common.py:54-61
+ * q (B,M,3) centroids, p (B,N,3) points, r2 = (float)((double)r*r).  idx (B,M,K):
+ * in-ball points by ascending (d2, index), then out-of-ball points by ascending index.
+ * d2 = (dx*dx + dy*dy) + dz*dz without contraction.  1 <= K <= min(N,128). */
+PCNBR_API int pcnbr_ball_query_f32(const float* q, const float* p, int B, int M, int N, float r2, int K,
+                         int32_t* idx, pcnbr_stream_t stream);
+
+/* ---- K3 kNN on xyz, direct distances ----------------------------------- common.py:110-114
+ * Same distance form, no radius.  idx (B,M,K) ascending (d2,index); d2 (B,M,K) may be NULL. */
+PCNBR_API int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M, int N, int K,
+                         int32_t* idx, float* d2, pcnbr_stream_t stream);
+
+/* ---- K3/K4 kNN in the reference's expanded form ----------------------- dgcnn.py:7-21
+ * x[b, f*stride_f + n*stride_n] (batch stride F*N), any layout of the (F,N) plane.
+ * pd_ij = ((-xx_j) - (-2*c_ij)) - xx_i, c = FMA chain over f ascending, xx = ATen cascade sum of
+ * squares; idx (B,N,K) by descending pd, lowest index on ties.  F <= 256, K <= min(N,128).
+ * ws: pcnbr_knn_expand_ws_bytes(B,F,N,K) bytes. */
+PCNBR_API size_t pcnbr_knn_expand_ws_bytes(int B, int F, int N, int K);
+PCNBR_API int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
+                         int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
+/* ---- K5 gather + centre-subtract (+ /r) + concat ------------------------ common.py:62-71
+ * p (B,N,3), feat (B,N,D) (D may be 0), q (B,M,3), idx (B,M,K) -> out (B,M,K,3+D).
+ * rdiv > 0: local coordinates are divided (true fp32 division) by rdiv (common.py:69). */
+PCNBR_API int pcnbr_group_f32(const float* p, const float* feat, const float* q, const int32_t* idx,
+                    int B, int N, int M, int K, int D, float rdiv, float* out, pcnbr_stream_t stream);
+
+/* ---- K7 inverse index (CSR by source point) for the atomic-free scatter-add backward
+ * idx (B,E) values in [0,N).  offsets (B,N+1): segment bounds; perm (B,E): positions e grouped
+ * by source, ascending e inside a segment (deterministic).  ws: pcnbr_csr_ws_bytes(B,E,N). */
+PCNBR_API size_t pcnbr_csr_ws_bytes(int B, int E, int N);
+PCNBR_API int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t* offsets, int32_t* perm,
+                    void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
+/* Backward of K5 w.r.t. feat (autograd IndexBackward of common.py:65):
+ * gout (B,M,K,3+D) -> gfeat (B,N,D) = sum over incoming (m,k) of gout[..., 3:], fixed order. */
+PCNBR_API int pcnbr_group_bwd_f32(const float* gout, const int32_t* offsets, const int32_t* perm,
+                        int B, int N, int E, int D, float* gfeat, pcnbr_stream_t stream);
+
+/* ---- K6 grouped max-pool over K (+ argmax) -------------- common.py:85-86, dgcnn.py:76
+ * x[r*stride_r + k*stride_k + d*stride_d], r < R rows, reduce k < K; out (R,D) contiguous,
+ * arg (R,D) uint8 (first max wins, as torch.max).  One of stride_d / stride_k must be 1. */
+PCNBR_API int pcnbr_maxpool_f32(const float* x, long R, int K, int D, long stride_r, long stride_k, long stride_d,
+                      float* out, uint8_t* arg, pcnbr_stream_t stream);
+/* gx has the same strides as x: gx[r,k,d] = (k == arg[r,d]) ? g[r,d] : 0. */
+PCNBR_API int pcnbr_maxpool_bwd_f32(const float* g, const uint8_t* arg, long R, int K, int D, long stride_r,
+                          long stride_k, long stride_d, float* gx, pcnbr_stream_t stream);
+
+/* ---- K8 three-point interpolation ------------------------------------- common.py:115-122
+ * feat (B,M,D) coarse, idx/d2 (B,N,K) from pcnbr_knn_direct_f32 (K <= 8) -> out (B,N,D);
+ * coef (B,N,K) receives w_k/norm (saved for the backward).  w = 1/(d2+1e-9f). */
+PCNBR_API int pcnbr_interp_f32(const float* feat, const int32_t* idx, const float* d2, int B, int N, int M, int D,
+                     int K, float* out, float* coef, pcnbr_stream_t stream);
+/* gfeat (B,M,D) = sum over incoming (n,k) of coef[n,k] * g[n,:]; CSR over idx viewed as (B, N*K). */
+PCNBR_API int pcnbr_interp_bwd_f32(const float* g, const float* coef, const int32_t* offsets, const int32_t* perm,
+                         int B, int N, int M, int D, int K, float* gfeat, pcnbr_stream_t stream);
+
+/* ---- K9 edge features -------------------------------------------------- dgcnn.py:41-55
+ * xt (B,N,F) point-major, idx (B,N,K) -> out (B,N,K,2F) point-major (the host returns it as the
+ * (B,2F,N,K) view): out[..., f] = xt[idx] - xt[n]; out[..., F+f] = xt[n]. */
+PCNBR_API int pcnbr_edge_feature_f32(const float* xt, const int32_t* idx, int B, int N, int F, int K, float* out,
+                           pcnbr_stream_t stream);
+/* gxt (B,N,F) = sum_incoming g[e, :F] - sum_k g[n,k,:F] + sum_k g[n,k,F:]. */
+PCNBR_API int pcnbr_edge_feature_bwd_f32(const float* g, const int32_t* offsets, const int32_t* perm, int B, int N,
+                               int F, int K, float* gxt, pcnbr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCNBR_H_ */

@@ -127,13 +127,16 @@ ORC_API void orc_knn_direct(const float* q, const float* p, int B, int M, int N,
 }
 
 /* --------------------------------------- kNN, expanded form (DGCNN knn) */
-/* ATen's sum over a non-innermost dim: rows are added into acc0 in runs of 16, each
- * full run is folded into acc1, 16 runs of acc1 into acc2, ... ; the tail rows stay
- * in acc0; result = ((acc0 + acc1) + acc2) + acc3.        (dgcnn.py:17)        */
-static float cascade_sumsq(const float* x, int F, size_t stride) {
+/* ATen's sum over a non-innermost dim (dgcnn.py:17, torch CPU build, 8-float vectors):
+ * cascade_sumsq(): rows are added into acc0 in runs of 16, each full run is folded into acc1,
+ * 16 runs of acc1 into acc2, ...; the tail rows stay in acc0; result = ((acc0+acc1)+acc2)+acc3.
+ * Columns n < (N & ~31) are summed that way over all F rows (4x8-float vector path).  The last N % 32
+ * columns go through ATen's scalar path instead: four interleaved partial sums (rows i = 4t+k),
+ * each cascaded over t, the F % 4 left-over rows added to partial 0, then ((p0+p1)+p2)+p3. */
+static float cascade_sumsq(const float* x, int count, size_t stride) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int i = 0;
-    while (i + 16 <= F) {
+    while (i + 16 <= count) {
         for (int j = 0; j < 16; ++j, ++i) { const float v = x[i * stride]; acc[0] = acc[0] + v * v; }
         for (int lvl = 1; lvl < 4; ++lvl) {
             acc[lvl] = acc[lvl] + acc[lvl - 1];
@@ -141,16 +144,26 @@ static float cascade_sumsq(const float* x, int F, size_t stride) {
             if ((i & (15 << (lvl * 4))) != 0) break;
         }
     }
-    for (; i < F; ++i) { const float v = x[i * stride]; acc[0] = acc[0] + v * v; }
+    for (; i < count; ++i) { const float v = x[i * stride]; acc[0] = acc[0] + v * v; }
     float r = acc[0];
     for (int lvl = 1; lvl < 4; ++lvl) r = r + acc[lvl];
     return r;
 }
 
+static float column_sumsq(const float* x, int F, int N, int n) {
+    const float* col = x + n;
+    if (n < (N & ~31)) return cascade_sumsq(col, F, (size_t)N);
+    const int q = F / 4;
+    float p[4];
+    for (int k = 0; k < 4; ++k) p[k] = cascade_sumsq(col + (size_t)k * N, q, (size_t)N * 4);
+    for (int i = q * 4; i < F; ++i) { const float v = col[(size_t)i * N]; p[0] = p[0] + v * v; }
+    return ((p[0] + p[1]) + p[2]) + p[3];
+}
+
 ORC_API void orc_sumsq(const float* x, int B, int F, int N, float* xx) {
     for (int b = 0; b < B; ++b)
         for (int n = 0; n < N; ++n)
-            xx[(size_t)b * N + n] = cascade_sumsq(x + (size_t)b * F * N + n, F, (size_t)N);
+            xx[(size_t)b * N + n] = column_sumsq(x + (size_t)b * F * N, F, N, n);
 }
 
 /* dgcnn.py:16-20.  x (B,F,N) channel-first; idx (B,N,k) int32, descending pd, ties by
@@ -162,7 +175,7 @@ ORC_API void orc_knn_expand(const float* x, int B, int F, int N, int K, int32_t*
     for (int b = 0; b < B; ++b) {
         const float* xb = x + (size_t)b * F * N;
         for (int n = 0; n < N; ++n) {
-            xx[n] = cascade_sumsq(xb + n, F, (size_t)N);
+            xx[n] = column_sumsq(xb, F, N, n);
             for (int f = 0; f < F; ++f) xt[(size_t)n * F + f] = xb[(size_t)f * N + n];
         }
         for (int i = 0; i < N; ++i) {
