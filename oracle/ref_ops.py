@@ -54,6 +54,7 @@ def fps_indices(coords: torch.Tensor, C: int, start: torch.Tensor | None = None)
     B, N, _ = coords.shape
     if start is None:
         start = torch.randint(0, N, (B,), dtype=torch.int, device=coords.device)
+    coords = coords.float()          # selections are always made in the reference's fp32 arithmetic
     far = start.to(torch.int64)
     rows = torch.arange(B)
     picks = torch.zeros(B, C, dtype=torch.int32)
@@ -73,8 +74,8 @@ def sample(coords: torch.Tensor, C: int, start: torch.Tensor | None = None) -> t
 
 
 def ball_query_indices(centroids, coords, r: float, K: int, tie: str = "canon") -> torch.Tensor:
-    """common.py:54-61 -> (B,C,K) int64."""
-    diff = coords.unsqueeze(1) - centroids.unsqueeze(2)          # (B,C,N,3) points - centroids
+    """common.py:54-61 -> (B,C,K) int64.  (fp32 arithmetic even when the features run in fp64.)"""
+    diff = coords.float().unsqueeze(1) - centroids.float().unsqueeze(2)          # (B,C,N,3) points - centroids
     d2 = (diff ** 2).sum(dim=-1)
     d2 = torch.where(d2 <= r ** 2, d2, torch.full_like(d2, torch.inf))
     return _select_smallest(d2, K, tie)[1]
@@ -102,9 +103,10 @@ def reduce(x: torch.Tensor, type: str) -> torch.Tensor:
 
 def three_nn(coords_1, coords_2, k: int = 3, tie: str = "canon"):
     """common.py:110-114 -> (d2 (B,N,k), idx (B,N,k) int64); coords_1 are the queries."""
-    diff = coords_2.unsqueeze(1) - coords_1.unsqueeze(2)         # (B,N,M,3)
+    diff = coords_2.float().unsqueeze(1) - coords_1.float().unsqueeze(2)         # (B,N,M,3)
     d2 = (diff ** 2).sum(dim=-1)
-    return _select_smallest(d2, k, tie)
+    vals, idx = _select_smallest(d2, k, tie)
+    return vals.to(coords_1.dtype), idx
 
 
 def interpolate(points, coords_1, coords_2, k: int = 3, tie: str = "canon") -> torch.Tensor:

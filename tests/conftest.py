@@ -8,6 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# the parity bar is fp32 (north star: 1e-4 relative): keep the library convolutions out of TF32
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
