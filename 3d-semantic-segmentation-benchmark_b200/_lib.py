@@ -26,6 +26,7 @@ PROTOTYPES = {
     "pcnbr_knn_direct_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "pcnbr_knn_expand_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "pcnbr_knn_expand_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P]),
+    "pcnbr_knn_tc_debug_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P, _P, _P]),
     "pcnbr_group_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "pcnbr_csr_ws_bytes": (_Z, [_I, _I, _I]),
     "pcnbr_csr_build": (_I, [_P, _I, _I, _I, _P, _P, _P, _Z, _P]),
@@ -39,7 +40,7 @@ PROTOTYPES = {
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
-KERNELS_PER_CALL = {"pcnbr_csr_build": 4, "pcnbr_knn_expand_f32": 2}
+KERNELS_PER_CALL = {"pcnbr_csr_build": 4, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_tc_debug_f32": 5}
 
 _lib = None
 launches = 0          # number of libpcnbr CUDA kernels launched by this process (bench.py reports it)

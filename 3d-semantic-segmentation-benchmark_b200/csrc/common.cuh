@@ -80,4 +80,11 @@ struct WarpList {
     }
 };
 
+// cross-file host helpers
+int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, float* xx, cudaStream_t s);     // select.cu
+bool knn_tc_supported(int F, int N, int K);                                                              // knn_tc.cu
+size_t knn_tc_ws_bytes(int B, int F, int N);
+int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int32_t* idx, void* ws, float* dump,
+               int32_t* stats_out, cudaStream_t s);
+
 }  // namespace pcnbr

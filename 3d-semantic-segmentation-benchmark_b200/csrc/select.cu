@@ -13,6 +13,7 @@
 // fills with in-ball points by (d2,index) followed by the lowest-index out-of-ball points -- exactly
 // what a stable sort of the reference's masked distance row yields.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace pcnbr {
 
@@ -203,6 +204,12 @@ knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
     }
 }
 
+int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, float* xx, cudaStream_t s) {
+    sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, sf, sn, xx);
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
 static inline int expand_tile(int F) {
     int t = (8192 / F) & ~31;
     if (t < 32) t = 32;
@@ -237,9 +244,24 @@ extern "C" int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M
     return launch_select<false>(q, p, B, M, N, 0.f, K, idx, d2, (cudaStream_t)stream);
 }
 
+static bool use_tensor_cores(int F, int N, int K) {
+    static const bool forced_generic = getenv("PCNBR_KNN_GENERIC") != nullptr;
+    return !forced_generic && knn_tc_supported(F, N, K);
+}
+
 extern "C" size_t pcnbr_knn_expand_ws_bytes(int B, int F, int N, int K) {
-    (void)F; (void)K;
-    return sizeof(float) * (size_t)B * (size_t)N;      // xx
+    const size_t generic = sizeof(float) * (size_t)B * (size_t)N;      // xx
+    const size_t tc = knn_tc_supported(F, N, K) ? knn_tc_ws_bytes(B, F, N) : 0;
+    return tc > generic ? tc : generic;
+}
+
+extern "C" int pcnbr_knn_tc_debug_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
+                                      int32_t* idx, void* ws, size_t ws_bytes, float* scores, int32_t* stats,
+                                      pcnbr_stream_t stream) {
+    if (!x || !idx || B <= 0 || F <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
+    if (!knn_tc_supported(F, N, K)) return PCNBR_E_TOOLARGE;
+    if (!ws || ws_bytes < pcnbr_knn_expand_ws_bytes(B, F, N, K)) return PCNBR_E_WORKSPACE;
+    return knn_tc_run(x, B, F, N, stride_f, stride_n, K, idx, ws, scores, stats, (cudaStream_t)stream);
 }
 
 extern "C" int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
@@ -248,9 +270,11 @@ extern "C" int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long st
     if (K > 128 || F > 256) return PCNBR_E_TOOLARGE;
     if (!ws || ws_bytes < pcnbr_knn_expand_ws_bytes(B, F, N, K)) return PCNBR_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
+    if (use_tensor_cores(F, N, K))
+        return knn_tc_run(x, B, F, N, stride_f, stride_n, K, idx, ws, nullptr, nullptr, s);
     float* xx = (float*)ws;
-    sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, stride_f, stride_n, xx);
-    PCNBR_CHECK_LAUNCH();
+    int rc = launch_sumsq(x, B, F, N, stride_f, stride_n, xx, s);
+    if (rc) return rc;
     const int warps = (F >= 16) ? 32 : 8;
     const int tile = expand_tile(F);
     const size_t smem = sizeof(float) * ((size_t)F * (tile + 1) + (size_t)warps * F + tile);

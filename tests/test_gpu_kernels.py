@@ -275,3 +275,63 @@ def test_error_behaviour(pkg, dev):
         pkg.dgcnn.knn(torch.rand(1, 3, 10, device=dev), 11)
     with pytest.raises(TypeError):
         pkg.common.sample(x.double(), 4)
+
+
+# --------------------------------------------------------------------------- K4 tensor-core kNN (tcgen05)
+
+def _tc_debug(pkg, x, k, want_scores=False):
+    from ctypes import c_void_p
+    B, F, N = x.shape
+    lib = pkg._lib
+    idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
+    nb = lib.size("pcnbr_knn_expand_ws_bytes", B, F, N, k)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    scores = torch.full((B, N, N), float("nan"), device=x.device) if want_scores else None
+    stats = torch.zeros(2, dtype=torch.int32, device=x.device)
+    sb, sf, sn = x.stride()
+    lib.call("pcnbr_knn_tc_debug_f32", x.data_ptr(), B, F, N, sf, sn, k, idx.data_ptr(), ws.data_ptr(), nb,
+             scores.data_ptr() if want_scores else None, stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return idx, scores, stats.cpu()
+
+
+def test_knn_tc_scores_match_fp32_within_margin(pkg, dev):
+    """The tcgen05 3xTF32 tile (TMA + UMMA descriptors + TMEM readback) reproduces s = 2 x_i.x_j - |x_j|^2
+    far inside the margin the survivor filter assumes (2e-4 * |x_i| * max|x_j|)."""
+    x = torch.randn(2, 64, 512, generator=_gen(21))
+    idx, scores, stats = _tc_debug(pkg, x.to(dev), 20, want_scores=True)
+    xd = x.double()
+    exact = 2 * torch.matmul(xd.transpose(1, 2), xd) - (xd ** 2).sum(1).unsqueeze(1)
+    err = (scores.cpu().double() - exact).abs()
+    norm = (xd ** 2).sum(1).sqrt()
+    bound = 2e-4 * norm.unsqueeze(2) * norm.amax(dim=1).view(-1, 1, 1)
+    assert not torch.isnan(scores).any()
+    assert (err <= 0.05 * bound).all(), f"max err/bound {(err / bound).max().item():.3e}"
+    assert torch.equal(idx.cpu(), canon.knn_expand(x, 20)[0])
+    assert stats[1] == 0 and stats[0] <= 2 * 512 * 32        # ~k+4 survivors per row, no overflow
+
+
+@pytest.mark.parametrize("F,N,k,B", [(64, 4096, 20, 2), (64, 1000, 20, 3), (32, 2048, 16, 2), (64, 300, 32, 2), (64, 4096, 1, 1)])
+def test_knn_tc_vs_oracle(pkg, dev, F, N, k, B):
+    x = torch.randn(B, F, N, generator=_gen(F + N + k))
+    if N == 1000:                                  # post-LeakyReLU-like features: common offset, small spread
+        x = x * 0.05 + 1.0
+    want = canon.knn_expand(x, k)[0]
+    idx, _, stats = _tc_debug(pkg, x.to(dev), k)
+    assert torch.equal(idx.cpu(), want)
+    xt = x.to(dev).transpose(1, 2).contiguous().transpose(1, 2)       # point-major input: no transposing copy
+    assert torch.equal(pkg.ops.knn_graph(xt, k).cpu(), want)
+    assert stats[1] == 0
+
+
+def test_knn_tc_degenerate_rows_fall_back_to_exact_scan(pkg, dev):
+    """Duplicated points / lattice ties blow the survivor queue for some rows: those rows are re-ranked by an
+    exact full scan, the result must still be the canonical one."""
+    x = torch.randint(-3, 4, (2, 64, 512), generator=_gen(33)).float() / 4
+    x[:, :, 256:] = x[:, :, :256]
+    want = canon.knn_expand(x, 20)[0]
+    idx, _, stats = _tc_debug(pkg, x.to(dev), 20)
+    assert torch.equal(idx.cpu(), want)
+    x2 = torch.zeros(1, 64, 300)                   # all points identical: every row overflows
+    idx2, _, stats2 = _tc_debug(pkg, x2.to(dev), 20)
+    assert torch.equal(idx2.cpu(), canon.knn_expand(x2, 20)[0]) and stats2[1] == 300
