@@ -11,7 +11,9 @@
 //                   3xTF32 split  hi*hi' + lo*hi' + hi*lo'  (~fp32 accuracy) into one of two TMEM
 //                   accumulators (2 x 256 columns = all 512 TMEM columns);
 //   4 epilogue warps: tcgen05.ld the finished tile (thread = query row) while the next tile is being
-//                   multiplied, form the ranking score s = 2*x_i.x_j - |x_j|^2, and
+//                   multiplied, form the ranking score s = 2*x'_i.x'_j - |x'_j|^2 (x' = x - per-cloud channel
+//                   mean: distances are translation invariant, and centring keeps the TF32 error relative to
+//                   the SPREAD of the features instead of their common offset), and
 //        pass 1: keep 64 interleaved group maxima per row in registers (branch-free); the k-th largest
 //                of them is a lower bound tau on the row's k-th best score;
 //        pass 2: (tiles are recomputed -- cheaper than storing N^2 floats) append every column with
@@ -35,7 +37,12 @@ constexpr int TC_QCAP = 64;        // survivors kept per row (uint16 indices)
 constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 constexpr uint32_t TC_SLAB_A = 128 * 128;      // bytes: 128 rows x 128 B (one swizzle atom of K)
 constexpr uint32_t TC_SLAB_B = 256 * 128;
-constexpr float TC_MARGIN = 2e-4f;             // x sqrt(xx_i * max_j xx_j), see header
+// Survivor margin (see header): 2 x |tensor-core score - exact reference score| is bounded by
+//   C_FILT * |x'_i| max|x'_j|   3xTF32 split (3*2^-22) + fp32 accumulation of 24 MMAs, centred features x' = x - mean
+// + C_REF  * |x_i|  max|x_j|    rounding of the REFERENCE's own fp32 value (64-term FMA chain, cascade |x|^2): its
+//                               ranking deviates from the true distances by that much, and we must follow it
+// + C_CTR  * max|x_j| max|x'_j| rounding of the centring subtraction itself
+constexpr float TC_C_FILT = 5e-5f, TC_C_REF = 1e-5f, TC_C_CTR = 1e-6f;
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 
@@ -105,45 +112,82 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------------------------ operand preparation
 
-// x (any (F,N) layout) -> point-major copies: xt exact fp32, xhi = tf32(x), xlo = tf32(x - xhi).
+// Per-cloud channel sums over a slice of the points: part[b][chunk][f] (fixed order -> deterministic).
+constexpr int TC_MEAN_CHUNKS = 16;
 __global__ void __launch_bounds__(256)
-knn_tc_prep_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, float* __restrict__ xt,
-                   float* __restrict__ xhi, float* __restrict__ xlo) {
-    const int b = blockIdx.y;
-    const long total = (long)N * F;
-    const float* __restrict__ xb = x + (size_t)b * total;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const long n = e / F;
-        const int f = (int)(e - n * F);
-        const float v = xb[(size_t)f * sf + (size_t)n * sn];
-        uint32_t h, l;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        const float rem = __fsub_rn(v, __uint_as_float(h));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
-        const size_t o = (size_t)b * total + e;
-        if (xt) xt[o] = v;
-        xhi[o] = __uint_as_float(h);
-        xlo[o] = __uint_as_float(l);
+knn_tc_mean_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, float* __restrict__ part) {
+    __shared__ float red[256];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int groups = 256 / F;                                   // F in {32, 64}
+    const int f = threadIdx.x % F, g = threadIdx.x / F;
+    const int per = (N + TC_MEAN_CHUNKS - 1) / TC_MEAN_CHUNKS;
+    const int n0 = chunk * per, n1 = min(N, n0 + per);
+    const float* __restrict__ xb = x + (size_t)b * F * N;
+    float acc = 0.f;
+    for (int n = n0 + g; n < n1; n += groups) acc += xb[(size_t)f * sf + (size_t)n * sn];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0) {
+        for (int k = 1; k < groups; ++k) acc += red[k * F + f];
+        part[((size_t)b * TC_MEAN_CHUNKS + chunk) * F + f] = acc;
     }
 }
 
-__global__ void knn_tc_xxmax_kernel(const float* __restrict__ xx, int N, uint32_t* __restrict__ xxmax) {
-    const int b = blockIdx.y;
-    float m = 0.f;
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) m = fmaxf(m, xx[(size_t)b * N + n]);
-    const uint32_t wm = __reduce_max_sync(PCNBR_FULL, __float_as_uint(m));      // xx >= 0: bit order = value order
-    if ((threadIdx.x & 31) == 0) atomicMax(&xxmax[b], wm);
+// One warp per point: x' = x - mean; xhi = tf32(x'), xlo = tf32(x' - xhi) (point-major, K-major for the
+// MMA); xt = exact copy of x (only when the input is not already point-major); xxc = |x'|^2;
+// maxima of |x|^2 and |x'|^2 per cloud (bit patterns of non-negative floats order like the values).
+__global__ void __launch_bounds__(256)
+knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, const float* __restrict__ xx,
+                   int F, int N, long sf, long sn, float* __restrict__ xt, float* __restrict__ xhi,
+                   float* __restrict__ xlo, float* __restrict__ xxc, uint32_t* __restrict__ maxes) {
+    __shared__ float mu[64];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < F) {
+        float m = 0.f;
+        for (int c = 0; c < TC_MEAN_CHUNKS; ++c) m += part[((size_t)b * TC_MEAN_CHUNKS + c) * F + threadIdx.x];
+        mu[threadIdx.x] = m / (float)N;
+    }
+    __syncthreads();
+    const float* __restrict__ xb = x + (size_t)b * F * N;
+    float mx = 0.f, mxc = 0.f;
+    for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+        float ss = 0.f;
+        for (int f = lane; f < F; f += 32) {
+            const float v = xb[(size_t)f * sf + (size_t)n * sn];
+            const float vc = __fsub_rn(v, mu[f]);
+            uint32_t h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(vc));
+            const float rem = __fsub_rn(vc, __uint_as_float(h));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
+            const size_t o = ((size_t)b * N + n) * F + f;
+            if (xt) xt[o] = v;
+            xhi[o] = __uint_as_float(h);
+            xlo[o] = __uint_as_float(l);
+            ss = fmaf(vc, vc, ss);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(PCNBR_FULL, ss, d);
+        if (lane == 0) xxc[(size_t)b * N + n] = ss;
+        mxc = fmaxf(mxc, ss);
+        mx = fmaxf(mx, xx[(size_t)b * N + n]);
+    }
+    if (lane == 0) {
+        atomicMax(&maxes[2 * b], __float_as_uint(mx));
+        atomicMax(&maxes[2 * b + 1], __float_as_uint(mxc));
+    }
 }
 
 // ------------------------------------------------------------------------------------ main kernel
 
-template <int KATOMS>      // F = 32 * KATOMS
+template <int KATOMS, bool DUMP>      // F = 32 * KATOMS; DUMP: also write the raw scores (tests only)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-              const float* __restrict__ xx, const uint32_t* __restrict__ xxmax, int B, int N, int K,
+              const float* __restrict__ xx, const float* __restrict__ xxc, const uint32_t* __restrict__ maxes,
+              int B, int N, int K,
               int32_t* __restrict__ qcnt, uint16_t* __restrict__ qidx, float* __restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (128B-swizzle atoms) by OFFSET, so the compiler keeps the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sAhi = smem;                                         // KATOMS x 16 KB
     uint8_t* sAlo = sAhi + KATOMS * TC_SLAB_A;                    // KATOMS x 16 KB
     uint8_t* sRing = sAlo + KATOMS * TC_SLAB_A;                   // TC_RING x 32 KB
@@ -260,6 +304,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             const int b = unit / RT, row = (unit - b * RT) * TC_M + rloc;
             const bool vrow = row < N;
             const float xxi = vrow ? xx[(size_t)b * N + row] : 0.f;
+            const float xxci = vrow ? xxc[(size_t)b * N + row] : 0.f;
             float gmax[64];
 #pragma unroll
             for (int g = 0; g < 64; ++g) gmax[g] = NEG_INF;
@@ -269,12 +314,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                 for (int ct = 0; ct < CT; ++ct, ++tile) {
                     const uint32_t buf = tile & 1, tphase = (tile >> 1) & 1;
                     const int j0 = ct * TC_N;
-                    float* sx = sXX + buf * TC_N;
+                    float* sx = sXX + buf * TC_N;                   // staged -|x'_j|^2 (masked columns: -inf)
                     for (int t = et; t < TC_N; t += 128)
-                        sx[t] = (j0 + t < N) ? xx[(size_t)b * N + j0 + t] : __int_as_float(0x7f800000);
+                        sx[t] = (j0 + t < N) ? -xxc[(size_t)b * N + j0 + t] : NEG_INF;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     mbar_wait(&tmem_full[buf], tphase);
                     tc_fence_after();
+                    const float4* sx4 = reinterpret_cast<const float4*>(sx);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         uint32_t r[32];
@@ -282,20 +328,40 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                         tmem_wait_ld();
                         if (pass == 0) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float s = fmaf(2.0f, __uint_as_float(r[i]), -sx[q * 32 + i]);
-                                gmax[(q & 1) * 32 + i] = fmaxf(gmax[(q & 1) * 32 + i], s);
-                                if (dump && vrow && j0 + q * 32 + i < N)
-                                    dump[((size_t)b * N + row) * N + j0 + q * 32 + i] = s;
+                            for (int i4 = 0; i4 < 8; ++i4) {
+                                const float4 nx = sx4[q * 8 + i4];          // one broadcast LDS.128 per 4 columns
+                                const float s0 = fmaf(2.0f, __uint_as_float(r[4 * i4 + 0]), nx.x);
+                                const float s1 = fmaf(2.0f, __uint_as_float(r[4 * i4 + 1]), nx.y);
+                                const float s2 = fmaf(2.0f, __uint_as_float(r[4 * i4 + 2]), nx.z);
+                                const float s3 = fmaf(2.0f, __uint_as_float(r[4 * i4 + 3]), nx.w);
+                                const int g = (q & 1) * 32 + 4 * i4;
+                                gmax[g + 0] = fmaxf(gmax[g + 0], s0);
+                                gmax[g + 1] = fmaxf(gmax[g + 1], s1);
+                                gmax[g + 2] = fmaxf(gmax[g + 2], s2);
+                                gmax[g + 3] = fmaxf(gmax[g + 3], s3);
+                                if (DUMP) {
+                                    const float sv[4] = {s0, s1, s2, s3};
+                                    for (int u = 0; u < 4; ++u) {
+                                        const int j = j0 + q * 32 + 4 * i4 + u;
+                                        if (dump && vrow && j < N) dump[((size_t)b * N + row) * N + j] = sv[u];
+                                    }
+                                }
                             }
                         } else {
+                            uint32_t hit = 0;                              // branch-free filter: one bit per column
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float s = fmaf(2.0f, __uint_as_float(r[i]), -sx[q * 32 + i]);
-                                if (s >= thr) {
-                                    if (cnt < TC_QCAP) sQ[rloc * TC_QCAP + cnt] = (uint16_t)(j0 + q * 32 + i);
-                                    ++cnt;
-                                }
+                            for (int i4 = 0; i4 < 8; ++i4) {
+                                const float4 nx = sx4[q * 8 + i4];
+                                hit |= (fmaf(2.0f, __uint_as_float(r[4 * i4 + 0]), nx.x) >= thr ? 1u : 0u) << (4 * i4 + 0);
+                                hit |= (fmaf(2.0f, __uint_as_float(r[4 * i4 + 1]), nx.y) >= thr ? 1u : 0u) << (4 * i4 + 1);
+                                hit |= (fmaf(2.0f, __uint_as_float(r[4 * i4 + 2]), nx.z) >= thr ? 1u : 0u) << (4 * i4 + 2);
+                                hit |= (fmaf(2.0f, __uint_as_float(r[4 * i4 + 3]), nx.w) >= thr ? 1u : 0u) << (4 * i4 + 3);
+                            }
+                            while (hit) {                                  // rare: ~k+4 survivors per 4096 columns
+                                const int i = __ffs(hit) - 1;
+                                hit &= hit - 1;
+                                if (cnt < TC_QCAP) sQ[rloc * TC_QCAP + cnt] = (uint16_t)(j0 + q * 32 + i);
+                                ++cnt;
                             }
                         }
                     }
@@ -312,7 +378,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                         for (int g = 0; g < 64; ++g) m = (gmax[g] < tau) ? fmaxf(m, gmax[g]) : m;
                         tau = m;
                     }
-                    const float margin = TC_MARGIN * sqrtf(xxi * __uint_as_float(xxmax[b]));
+                    const float xm = __uint_as_float(maxes[2 * b]), xcm = __uint_as_float(maxes[2 * b + 1]);
+                    const float margin = TC_C_FILT * sqrtf(xxci * xcm) + TC_C_REF * sqrtf(xxi * xm) + TC_C_CTR * sqrtf(xm * xcm);
                     thr = fmaxf(tau - margin, -3.0e38f);           // finite: masked columns (s = -inf) never pass
                 }
             }
@@ -427,8 +494,8 @@ static int make_map(CUtensorMap* map, const float* base, int B, int N, int F) {
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct TcWorkspace {
-    float *xx, *xt, *xhi, *xlo;
-    uint32_t* xxmax;
+    float *xx, *xxc, *part, *xt, *xhi, *xlo;
+    uint32_t* maxes;
     int32_t *qcnt, *stats;
     uint16_t* qidx;
     size_t bytes;
@@ -440,7 +507,9 @@ static TcWorkspace tc_carve(void* ws, int B, int F, int N, bool need_xt) {
     auto take = [&](size_t n) { size_t o = off; off += align256(n); return (uint8_t*)ws + o; };
     const size_t bn = (size_t)B * N;
     w.xx = (float*)take(bn * 4);
-    w.xxmax = (uint32_t*)take((size_t)B * 4);
+    w.xxc = (float*)take(bn * 4);
+    w.part = (float*)take((size_t)B * TC_MEAN_CHUNKS * F * 4);
+    w.maxes = (uint32_t*)take((size_t)B * 8);
     w.stats = (int32_t*)take(16);
     w.xhi = (float*)take(bn * F * 4);
     w.xlo = (float*)take(bn * F * 4);
@@ -457,18 +526,18 @@ bool knn_tc_supported(int F, int N, int K) {
     return (F == 32 || F == 64) && K <= 32 && N >= 256 && N <= 65535;
 }
 
-template <int KATOMS>
+template <int KATOMS, bool DUMP>
 static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcWorkspace& w, int B, int N, int K,
                      float* dump, cudaStream_t s) {
     const size_t smem = 2 * KATOMS * TC_SLAB_A + TC_RING * TC_SLAB_B + TC_M * TC_QCAP * 2 + 2 * TC_N * 4 + 32 * 8 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<KATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<KATOMS, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int units = B * ((N + TC_M - 1) / TC_M);
     const int grid = units < sms ? units : sms;
-    knn_tc_kernel<KATOMS><<<grid, TC_THREADS, smem, s>>>(mh, ml, w.xx, w.xxmax, B, N, K, w.qcnt, w.qidx, dump);
+    knn_tc_kernel<KATOMS, DUMP><<<grid, TC_THREADS, smem, s>>>(mh, ml, w.xx, w.xxc, w.maxes, B, N, K, w.qcnt, w.qidx, dump);
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -479,23 +548,25 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
     const bool point_major = (sf == 1 && sn == F);
     TcWorkspace w = tc_carve(ws, B, F, N, !point_major);
     const float* xt = point_major ? x : w.xt;
-    cudaError_t e = cudaMemsetAsync(w.xxmax, 0, (size_t)((uint8_t*)w.stats + 16 - (uint8_t*)w.xxmax), s);   // xxmax + stats
+    cudaError_t e = cudaMemsetAsync(w.maxes, 0, (size_t)((uint8_t*)w.stats + 16 - (uint8_t*)w.maxes), s);   // maxes + stats
     if (e != cudaSuccess) return (int)e;
-    // exact |x|^2 in the reference's summation order (select.cu), its per-cloud maximum, TF32 split
+    // exact |x|^2 in the reference's summation order (select.cu); channel means; centred TF32 split
     int rc0 = launch_sumsq(x, B, F, N, sf, sn, w.xx, s);
     if (rc0) return rc0;
-    knn_tc_xxmax_kernel<<<dim3(8, B), 256, 0, s>>>(w.xx, N, w.xxmax);
+    knn_tc_mean_kernel<<<dim3(TC_MEAN_CHUNKS, B), 256, 0, s>>>(x, F, N, sf, sn, w.part);
     PCNBR_CHECK_LAUNCH();
-    long pb = ((long)N * F + 255) / 256;
-    if (pb > 148 * 8) pb = 148 * 8;
-    knn_tc_prep_kernel<<<dim3((unsigned)pb, B), 256, 0, s>>>(x, F, N, sf, sn, point_major ? nullptr : w.xt, w.xhi, w.xlo);
+    int pb = (N + 7) / 8;
+    if (pb > 148) pb = 148;
+    knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, N, sf, sn, point_major ? nullptr : w.xt, w.xhi,
+                                                   w.xlo, w.xxc, w.maxes);
     PCNBR_CHECK_LAUNCH();
     CUtensorMap mh, ml;
     int rc = make_map(&mh, w.xhi, B, N, F);
     if (rc) return rc;
     rc = make_map(&ml, w.xlo, B, N, F);
     if (rc) return rc;
-    rc = (F == 64) ? launch_tc<2>(mh, ml, w, B, N, K, dump, s) : launch_tc<1>(mh, ml, w, B, N, K, dump, s);
+    if (dump) rc = (F == 64) ? launch_tc<2, true>(mh, ml, w, B, N, K, dump, s) : launch_tc<1, true>(mh, ml, w, B, N, K, dump, s);
+    else      rc = (F == 64) ? launch_tc<2, false>(mh, ml, w, B, N, K, dump, s) : launch_tc<1, false>(mh, ml, w, B, N, K, dump, s);
     if (rc) return rc;
     knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, 8 * F * sizeof(float), s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats);
     PCNBR_CHECK_LAUNCH();

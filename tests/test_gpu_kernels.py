@@ -296,19 +296,22 @@ def _tc_debug(pkg, x, k, want_scores=False):
 
 
 def test_knn_tc_scores_match_fp32_within_margin(pkg, dev):
-    """The tcgen05 3xTF32 tile (TMA + UMMA descriptors + TMEM readback) reproduces s = 2 x_i.x_j - |x_j|^2
-    far inside the margin the survivor filter assumes (2e-4 * |x_i| * max|x_j|)."""
-    x = torch.randn(2, 64, 512, generator=_gen(21))
-    idx, scores, stats = _tc_debug(pkg, x.to(dev), 20, want_scores=True)
-    xd = x.double()
-    exact = 2 * torch.matmul(xd.transpose(1, 2), xd) - (xd ** 2).sum(1).unsqueeze(1)
-    err = (scores.cpu().double() - exact).abs()
-    norm = (xd ** 2).sum(1).sqrt()
-    bound = 2e-4 * norm.unsqueeze(2) * norm.amax(dim=1).view(-1, 1, 1)
-    assert not torch.isnan(scores).any()
-    assert (err <= 0.05 * bound).all(), f"max err/bound {(err / bound).max().item():.3e}"
-    assert torch.equal(idx.cpu(), canon.knn_expand(x, 20)[0])
-    assert stats[1] == 0 and stats[0] <= 2 * 512 * 32        # ~k+4 survivors per row, no overflow
+    """The tcgen05 3xTF32 tile (TMA + UMMA descriptors + TMEM readback) reproduces the centred score
+    s = 2 x'_i.x'_j - |x'_j|^2 (x' = x - channel mean) far inside the error the survivor filter assumes
+    (C_FILT/2 * |x'_i| * max|x'_j| with C_FILT = 5e-5) -- with and without a large common offset."""
+    for offset, scale in ((0.0, 1.0), (3.0, 0.1)):
+        x = torch.randn(2, 64, 512, generator=_gen(21)) * scale + offset
+        idx, scores, stats = _tc_debug(pkg, x.to(dev), 20, want_scores=True)
+        xd = x.double()
+        xc = xd - xd.mean(dim=2, keepdim=True)
+        exact = 2 * torch.matmul(xc.transpose(1, 2), xc) - (xc ** 2).sum(1).unsqueeze(1)
+        err = (scores.cpu().double() - exact).abs()
+        norm = (xc ** 2).sum(1).sqrt()
+        eps = 2.5e-5 * norm.unsqueeze(2) * norm.amax(dim=1).view(-1, 1, 1)
+        assert not torch.isnan(scores).any()
+        assert (err <= 0.5 * eps).all(), f"max err/eps {(err / eps).max().item():.3e}"
+        assert torch.equal(idx.cpu(), canon.knn_expand(x, 20)[0])
+        assert stats[1] == 0 and stats[0] <= 2 * 512 * 32        # ~k+4 survivors per row, no overflow
 
 
 @pytest.mark.parametrize("F,N,k,B", [(64, 4096, 20, 2), (64, 1000, 20, 3), (32, 2048, 16, 2), (64, 300, 32, 2), (64, 4096, 1, 1)])
