@@ -37,6 +37,9 @@ PROTOTYPES = {
     "pcnbr_interp_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "pcnbr_edge_feature_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "pcnbr_edge_feature_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_edgeconv_fwd_blocks": (_I, [_I]),
+    "pcnbr_edgeconv_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pcnbr_edgeconv_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
@@ -70,7 +73,7 @@ def load() -> ctypes.CDLL:
     return lib
 
 
-def call(name: str, *args) -> None:
+def call(name: str, *args, tag: str = "") -> None:
     """Invoke a compute entry point and turn a non-zero return code into an exception."""
     global launches
     lib = load()
@@ -80,7 +83,7 @@ def call(name: str, *args) -> None:
         ev0.record()                      # on the current stream = the stream handed to the kernel
         rc = getattr(lib, name)(*args)
         ev1.record()
-        timing.setdefault(name, []).append((ev0, ev1))
+        timing.setdefault(name + tag, []).append((ev0, ev1))
     else:
         rc = getattr(lib, name)(*args)
     launches += KERNELS_PER_CALL.get(name, 1)

@@ -1,0 +1,136 @@
+// edgeconv.cu -- fused EdgeConv: conv1x1 + BatchNorm + LeakyReLU + max over k WITHOUT the k-inflated tensors.
+//
+// Reference: models/dgcnn/dgcnn.py:73-76 builds the (B,2F,N,k) edge tensor (671 MB at B=16), runs a 1x1
+// convolution to (B,O,N,k) (335-671 MB), BatchNorm, LeakyReLU and a max over k: ~4 GB of HBM traffic per
+// layer forward and ~3x that backward.  Algebra:
+//     W . [x_j - x_i ; x_i] = A x_j + (B - A) x_i =: P[j] + Q[i]            (W = [A | B], two per-point GEMMs)
+//     max_j act(bn(u_j)) = act(bn(max_j u_j))   when gamma >= 0  (min_j when gamma < 0):  BN+LeakyReLU is
+//     monotone per channel, and fl(P_j + Q_i) is monotone in P_j, so max_j (P_j + Q_i) = (max_j P_j) + Q_i exactly.
+// So one gather pass over the kNN table gives, per (point, channel): the selected P (max or min over the k
+// neighbours) with its argmax, sum_j P_j (for the backward), and the BatchNorm batch statistics of ALL N*k
+// pre-activations u = P_j + Q_i (shifted sums, per-block partials, combined in fp64 in a fixed order).
+// HBM traffic per layer: the (B,N,k) table + a few (B,N,O) tensors (~100 MB instead of ~4 GB).
+// The convolution itself stays a library GEMM on (B*N, F) x (F, 2O).  Rounding differs from the reference's
+// order of operations (within 1e-4, tests/test_gpu_fused.py); get_graph_feature/EdgeConv keep an exact path.
+#include "common.cuh"
+#include "segsum.cuh"
+
+namespace pcnbr {
+
+// PQ (B,N,2O): P = [..., :O], Q = [..., O:].  idx (B,N,K).  selmax[o] != 0: keep max_j P_j, else min_j.
+// shift[o]: any constant near the typical u (variance is accumulated about it).  VPL = O / 32.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ idx, const uint8_t* __restrict__ selmax,
+                    const float* __restrict__ shift, int N, int K, float* __restrict__ psel, uint8_t* __restrict__ arg,
+                    float* __restrict__ s1, float* __restrict__ partial) {
+    constexpr int O = 32 * VPL;
+    __shared__ float red[8][2 * O];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* __restrict__ pq = PQ + (size_t)b * N * 2 * O;
+    const int32_t* __restrict__ ib = idx + (size_t)b * N * K;
+    float c[VPL], a1[VPL], a2[VPL];
+    bool smax[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        c[v] = shift[lane + 32 * v];
+        smax[v] = selmax[lane + 32 * v] != 0;
+        a1[v] = 0.f; a2[v] = 0.f;
+    }
+    for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
+        float q[VPL], best[VPL], sum[VPL];
+        int ba[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            q[v] = pq[(size_t)n * 2 * O + O + lane + 32 * v];
+            best[v] = 0.f; sum[v] = 0.f; ba[v] = 0;
+        }
+        for (int j0 = 0; j0 < K; j0 += 32) {
+            const int mine = (j0 + lane < K) ? ib[(size_t)n * K + j0 + lane] : 0;
+            const int cnt = min(32, K - j0);
+            for (int l = 0; l < cnt; ++l) {
+                const int m = __shfl_sync(PCNBR_FULL, mine, l);
+                const float* __restrict__ row = pq + (size_t)m * 2 * O;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const float p = row[lane + 32 * v];
+                    const float d = (p + q[v]) - c[v];
+                    a1[v] += d;
+                    a2[v] = fmaf(d, d, a2[v]);
+                    sum[v] += p;
+                    const bool take = (j0 + l == 0) || (smax[v] ? (p > best[v]) : (p < best[v]));
+                    if (take) { best[v] = p; ba[v] = j0 + l; }
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const size_t o = ((size_t)b * N + n) * O + lane + 32 * v;
+            psel[o] = best[v];
+            arg[o] = (uint8_t)ba[v];
+            s1[o] = sum[v];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { red[warp][lane + 32 * v] = a1[v]; red[warp][O + lane + 32 * v] = a2[v]; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * O; t += 256) {
+        float s = red[0][t];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += red[w][t];
+        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * O + t] = s;
+    }
+}
+
+// Backward gather over the inverse table: for source point m and column c
+//   c <  O : T1 = sum over incoming edges (n,j) with arg[n,c] == j of gs[n,c]     (gradient through the selected edge)
+//   c >= O : T2 = sum over incoming edges of Q[n, c-O]                           (for the BatchNorm variance term)
+struct EdgeConvBwdSrc {
+    const float* gs; const uint8_t* arg; const float* PQ; long N; int K; int O;
+    __device__ __forceinline__ float accum(int b, int e, int c, float acc) const {
+        const int n = e / K, j = e - n * K;
+        const size_t r = (size_t)b * N + n;
+        if (c < O) return (arg[r * O + c] == j) ? acc + gs[r * O + c] : acc;
+        return acc + PQ[r * 2 * O + c];
+    }
+};
+struct EdgeConvBwdDst {
+    float* T; long N; int O2;
+    __device__ __forceinline__ void store(int b, int s, int c, float v) const { T[((size_t)b * N + s) * O2 + c] = v; }
+};
+
+}  // namespace pcnbr
+
+using namespace pcnbr;
+
+extern "C" int pcnbr_edgeconv_fwd_blocks(int N) {
+    int gx = (N + 7) / 8;
+    return gx > 74 ? 74 : gx;
+}
+
+extern "C" int pcnbr_edgeconv_fwd_f32(const float* PQ, const int32_t* idx, const uint8_t* selmax, const float* shift,
+                                      int B, int N, int K, int O, float* psel, uint8_t* arg, float* s1, float* partial,
+                                      pcnbr_stream_t stream) {
+    if (!PQ || !idx || !selmax || !shift || !psel || !arg || !s1 || !partial || B <= 0 || N <= 0 || K <= 0) return PCNBR_E_BADARG;
+    if (K > 255 || (O != 32 && O != 64 && O != 128 && O != 256)) return PCNBR_E_TOOLARGE;
+    dim3 grid(pcnbr_edgeconv_fwd_blocks(N), B);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (O) {
+        case 32:  edgeconv_fwd_kernel<1><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
+        case 64:  edgeconv_fwd_kernel<2><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
+        case 128: edgeconv_fwd_kernel<4><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
+        default:  edgeconv_fwd_kernel<8><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
+    }
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const float* PQ, const int32_t* offsets,
+                                      const int32_t* perm, int B, int N, int K, int O, float* T, pcnbr_stream_t stream) {
+    if (!gs || !arg || !PQ || !offsets || !perm || !T || B <= 0 || N <= 0 || K <= 0 || O <= 0) return PCNBR_E_BADARG;
+    EdgeConvBwdSrc src{gs, arg, PQ, (long)N, K, O};
+    EdgeConvBwdDst dst{T, (long)N, 2 * O};
+    segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, N * K, 2 * O);
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}

@@ -53,8 +53,9 @@ interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ id
 // gfeat[b,m,:] = sum over incoming positions e = n*K + k of coef[e] * g[b,n,:]
 struct InterpBwdSrc {
     const float* g; const float* cf; long N; int D; int K;
-    __device__ __forceinline__ const float* row(int b, int e) const { return g + ((size_t)b * N + e / K) * D; }
-    __device__ __forceinline__ float coef(int b, int e) const { return cf[(size_t)b * N * K + e]; }
+    __device__ __forceinline__ float accum(int b, int e, int c, float acc) const {
+        return __fmaf_rn(cf[(size_t)b * N * K + e], g[((size_t)b * N + e / K) * D + c], acc);
+    }
 };
 struct InterpDst {
     float* out; long M; int D;

@@ -1,6 +1,6 @@
 // segsum.cuh -- K7: atomic-free segmented scatter-add, shared by the backward of K5/K8/K9.
 //
-// out[b, s, c] = sum_{t in segment(s)} coef(e_t) * src_row(e_t)[c],   e_t = perm[t]  (ascending e)
+// out[b, s, c] = sum_{t in segment(s)} src.term(b, e_t, c),   e_t = perm[t]  (ascending e)
 //
 // A CTA of 8 warps takes 8 consecutive source points.  Lanes stride over the columns, so every
 // gathered row is read with coalesced 128-byte requests.  Short segments are summed by one warp;
@@ -25,16 +25,15 @@ __device__ __forceinline__ void seg_accumulate(const Src& src, int b, const int3
 #pragma unroll 4
         for (int l = 0; l < n; ++l) {
             const int e = __shfl_sync(PCNBR_FULL, my_e, l);
-            const float* __restrict__ row = src.row(b, e) + c0;
-            const float w = src.coef(b, e);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (lane + 32 * i < ncols - c0) acc[i] = __fmaf_rn(w, row[lane + 32 * i], acc[i]);
+                if (lane + 32 * i < ncols - c0) acc[i] = src.accum(b, e, c0 + lane + 32 * i, acc[i]);
         }
     }
 }
 
-// Src: row(b,e) -> const float*, coef(b,e) -> float.   Dst: store(b, s, col, value).
+// Src: accum(b, e, col, acc) -> acc + contribution of position e to column col.
+// Dst: store(b, s, col, value).
 template <class Src, class Dst>
 __global__ void __launch_bounds__(256)
 segsum_kernel(Src src, Dst dst, const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm, int N,

@@ -8,6 +8,8 @@ torch.cuda.is_available(), dgcnn.py:39); ties in the k-NN selection go to the lo
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -55,11 +57,24 @@ class EdgeConv(nn.Module):
             nn.BatchNorm2d(out_channels),
             nn.LeakyReLU(negative_slope=0.2),
         )
+        # fused = algebraic split W.[xj-xi; xi] = A.xj + (B-A).xi: no (B,*,N,k) tensor is ever built
+        # (SURVEY.md 8f-2).  fused=False runs the reference's op sequence literally on the K9/K6 kernels.
+        self.fused = os.environ.get("PCNBR_EDGECONV_EXACT") is None and out_channels in (32, 64, 128, 256)
 
     def forward(self, x):
-        x = get_graph_feature(x, k=self.k)
-        x = self.conv(x)
-        return ops.max_pool_neighbors(x, -1)
+        if not self.fused:
+            x = get_graph_feature(x, k=self.k)
+            x = self.conv(x)
+            return ops.max_pool_neighbors(x, -1)
+        conv, bn, act = self.conv[0], self.conv[1], self.conv[2]
+        B, F, N = x.shape
+        O = conv.out_channels
+        nbr = ops.NeighborIndex(ops.knn_graph(x, self.k), N)
+        W = conv.weight.view(O, 2 * F)
+        Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
+        PQ = torch.matmul(_point_major(x), Wcat.t())                        # library GEMM (B,N,F) x (F,2O)
+        out = ops.edgeconv_fused(PQ, nbr, bn, act.negative_slope)           # (B,N,O), point-major
+        return out.permute(0, 2, 1)
 
 
 def _pointwise(cin, cout, dropout=None):

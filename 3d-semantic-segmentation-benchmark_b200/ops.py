@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features",
+    "edge_features", "edgeconv_fused",
 ]
 
 
@@ -359,3 +359,96 @@ def edge_features(xt: torch.Tensor, nbr: NeighborIndex) -> torch.Tensor:
     [x_j - x_i, x_i] (models/dgcnn/dgcnn.py:47-53).  `.permute(0,3,1,2)` is the reference's (B,2F,N,k)."""
     _check(xt, "xt")
     return _EdgeFn.apply(_c(xt), nbr)
+
+
+# ----------------------------------------------------------------------------- fused EdgeConv (SURVEY 8f-2)
+
+
+class _EdgeConvFusedFn(torch.autograd.Function):
+    """max_j LeakyReLU(BatchNorm(P[idx[n,j]] + Q[n])) from the per-point GEMM outputs PQ = [P | Q] (B,N,2O).
+
+    Forward: one gather kernel (selected P = max_j or min_j by the sign of gamma, argmax, sum_j P, BatchNorm
+    partial sums over all N*k pre-activations), then O(B*N*O) elementwise work.  Backward: the exact
+    BatchNorm + max backward written in terms of (B,N,O) tensors and one atomic-free CSR gather."""
+
+    @staticmethod
+    def forward(ctx, PQ, nbr, gamma, beta, running_mean, running_var, training, momentum, eps, slope):
+        B, N, O2 = PQ.shape
+        O, K = O2 // 2, nbr.idx.shape[2]
+        dev = PQ.device
+        selmax = (gamma >= 0).to(torch.uint8)
+        shift = (PQ[0, 0, :O] + PQ[0, 0, O:]).contiguous()
+        psel = torch.empty(B, N, O, dtype=torch.float32, device=dev)
+        s1 = torch.empty(B, N, O, dtype=torch.float32, device=dev)
+        arg = torch.empty(B, N, O, dtype=torch.uint8, device=dev)
+        nblk = _lib.size("pcnbr_edgeconv_fwd_blocks", N)
+        partial = torch.empty(B * nblk, 2 * O, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_edgeconv_fwd_f32", PQ.data_ptr(), nbr.idx.data_ptr(), selmax.data_ptr(), shift.data_ptr(),
+                  B, N, K, O, psel.data_ptr(), arg.data_ptr(), s1.data_ptr(), partial.data_ptr(), _stream())
+        M = B * N * K
+        if training:
+            tot = partial.double().sum(dim=0)
+            m1 = tot[:O] / M
+            mean64 = shift.double() + m1
+            var64 = (tot[O:] / M - m1 * m1).clamp_min(0.0)                # biased, as BatchNorm normalises with
+            mean, var = mean64.float(), var64.float()
+            if running_mean is not None:
+                with torch.no_grad():
+                    running_mean.mul_(1.0 - momentum).add_(mean, alpha=momentum)
+                    running_var.mul_(1.0 - momentum).add_((var64 * (M / max(M - 1, 1))).float(), alpha=momentum)
+        else:
+            mean, var = running_mean, running_var
+        rstd = torch.rsqrt(var.double() + eps).float()
+        Q = PQ[..., O:]
+        y = (psel + Q - mean) * (gamma * rstd) + beta
+        out = torch.nn.functional.leaky_relu(y, slope)
+        ctx.nbr, ctx.consts = nbr, (B, N, O, K, M, bool(training), float(slope))
+        ctx.save_for_backward(PQ, psel, arg, s1, out, mean, rstd, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        PQ, psel, arg, s1, out, mean, rstd, gamma = ctx.saved_tensors
+        B, N, O, K, M, training, slope = ctx.consts
+        P, Q = PQ[..., :O], PQ[..., O:]
+        gs = (g * torch.where(out > 0, 1.0, slope)).contiguous()          # dL/dy on the selected edge
+        yhat = (psel + Q - mean) * rstd
+        dbeta = gs.sum(dim=(0, 1))
+        dgamma = (gs * yhat).sum(dim=(0, 1))
+        gr = gamma * rstd
+        offsets, perm = ctx.nbr.csr()
+        T = torch.empty(B, N, 2 * O, dtype=torch.float32, device=g.device)
+        _lib.call("pcnbr_edgeconv_bwd_f32", gs.data_ptr(), arg.data_ptr(), PQ.data_ptr(), offsets.data_ptr(),
+                  perm.data_ptr(), B, N, K, O, T.data_ptr(), _stream())
+        dPQ = torch.empty_like(PQ)
+        if training:
+            c1 = gr * dbeta / M
+            c2r = gr * dgamma / M * rstd
+            deg = (offsets[:, 1:] - offsets[:, :-1]).to(torch.float32).unsqueeze(-1)
+            dPQ[..., :O] = gr * T[..., :O] - deg * c1 - c2r * (deg * (P - mean) + T[..., O:])
+            dPQ[..., O:] = gr * gs - K * c1 - c2r * (s1 + K * (Q - mean))
+        else:
+            dPQ[..., :O] = gr * T[..., :O]
+            dPQ[..., O:] = gr * gs
+        return dPQ, None, dgamma, dbeta, None, None, None, None, None, None
+
+
+def edgeconv_fused(PQ: torch.Tensor, nbr: NeighborIndex, bn: torch.nn.BatchNorm2d, negative_slope: float) -> torch.Tensor:
+    """(B,N,2O) per-point GEMM outputs + kNN table -> (B,N,O) = max over k of LeakyReLU(BatchNorm(conv(edge features)))
+    (models/dgcnn/dgcnn.py:73-76) without materialising any (B,*,N,k) tensor.  Updates bn's running statistics in
+    training mode exactly as nn.BatchNorm2d would."""
+    _check(PQ, "PQ")
+    O = PQ.shape[-1] // 2
+    if O not in (32, 64, 128, 256) or nbr.idx.shape[2] > 255:
+        raise RuntimeError("pcnbr: fused EdgeConv supports 32/64/128/256 output channels and k <= 255")
+    training = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if training and bn.running_mean is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    gamma = bn.weight if bn.weight is not None else torch.ones(O, device=PQ.device)
+    beta = bn.bias if bn.bias is not None else torch.zeros(O, device=PQ.device)
+    return _EdgeConvFusedFn.apply(_c(PQ), nbr, gamma, beta, bn.running_mean, bn.running_var, training,
+                                  0.0 if momentum is None else float(momentum), float(bn.eps), float(negative_slope))

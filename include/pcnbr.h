@@ -128,6 +128,21 @@ PCNBR_API int pcnbr_edge_feature_f32(const float* xt, const int32_t* idx, int B,
 PCNBR_API int pcnbr_edge_feature_bwd_f32(const float* g, const int32_t* offsets, const int32_t* perm, int B, int N,
                                int F, int K, float* gxt, pcnbr_stream_t stream);
 
+/* ---- fused EdgeConv: conv1x1 + BatchNorm + LeakyReLU + max over k ---- dgcnn.py:73-76
+ * PQ (B,N,2O) = x_t @ [A ; B-A]^T (library GEMM by the host), idx (B,N,K).  selmax[o] = (gamma_o >= 0),
+ * shift[o] = any constant near the pre-activations.  Outputs, all (B,N,O): psel = max_j (or min_j) P[idx[n,j]],
+ * arg = its j (uint8), s1 = sum_j P[idx[n,j]]; partial (B * pcnbr_edgeconv_fwd_blocks(N), 2O): per-block
+ * sum(u - shift) and sum((u - shift)^2) over all N*K pre-activations u = P_j + Q_i (BatchNorm statistics).
+ * O in {32,64,128,256}, K <= 255. */
+PCNBR_API int pcnbr_edgeconv_fwd_blocks(int N);
+PCNBR_API int pcnbr_edgeconv_fwd_f32(const float* PQ, const int32_t* idx, const uint8_t* selmax, const float* shift,
+                           int B, int N, int K, int O, float* psel, uint8_t* arg, float* s1, float* partial,
+                           pcnbr_stream_t stream);
+/* T (B,N,2O): T[m, :O] = sum over incoming edges (n,j) of m with arg[n,o]==j of gs[n,o];
+ * T[m, O:] = sum over incoming edges of Q[n,:].  CSR of idx viewed as (B, N*K). */
+PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const float* PQ, const int32_t* offsets,
+                           const int32_t* perm, int B, int N, int K, int O, float* T, pcnbr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
