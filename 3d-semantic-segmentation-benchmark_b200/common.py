@@ -66,9 +66,34 @@ class MiniPointNet(nn.Module):
             width = m
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,Cin,C,K).  When x is the channels-last view the set-abstraction modules hand in (memory
+        (B,C,K,Cin)), each 1x1 convolution is one cuBLAS SGEMM over the (B*C*K, Cin) rows and BatchNorm2d runs as
+        a batch norm over the same rows (identical statistics); otherwise the plain cuDNN path is used."""
+        B, _, C, K = x.shape
+        rows = x.permute(0, 2, 3, 1)
+        if not (x.is_cuda and rows.is_contiguous()):
+            for conv, bn in zip(self.conv, self.batch):
+                x = F.relu(bn(conv(x)))
+            return x
+        h = rows
         for conv, bn in zip(self.conv, self.batch):
-            x = F.relu(bn(conv(x)))
-        return x
+            h = F.linear(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+            h = F.relu(_batch_norm_rows(bn, h.view(-1, conv.out_channels))).view(B, C, K, conv.out_channels)
+        return h.permute(0, 3, 1, 2)
+
+
+def _batch_norm_rows(bn: nn.modules.batchnorm._BatchNorm, rows: torch.Tensor) -> torch.Tensor:
+    """nn.BatchNorm{1,2}d applied to a (rows, channels) matrix: same statistics, running-stat update and
+    num_batches_tracked bookkeeping as the module's own forward."""
+    training = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return F.batch_norm(rows, bn.running_mean if (not training or bn.track_running_stats) else None,
+                        bn.running_var if (not training or bn.track_running_stats) else None,
+                        bn.weight, bn.bias, training, 0.0 if momentum is None else momentum, bn.eps)
 
 
 class UnitPointNet(nn.Module):
@@ -85,9 +110,20 @@ class UnitPointNet(nn.Module):
             width = m
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,Cin,N).  When x is the transposed view of point-major memory (B,N,Cin) -- what the feature
+        propagation / InvResMLP modules hand in -- the 1x1 convolutions run as cuBLAS SGEMMs over the (B*N, Cin)
+        rows; otherwise the plain cuDNN path is used."""
+        B, _, N = x.shape
+        rows = x.permute(0, 2, 1)
+        if not (x.is_cuda and rows.is_contiguous()):
+            for conv, bn in zip(self.conv, self.batch):
+                x = F.relu(bn(conv(x)))
+            return x
+        h = rows
         for conv, bn in zip(self.conv, self.batch):
-            x = F.relu(bn(conv(x)))
-        return x
+            h = F.linear(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+            h = F.relu(_batch_norm_rows(bn, h.view(-1, conv.out_channels))).view(B, N, conv.out_channels)
+        return h.permute(0, 2, 1)
 
 
 class SetAbstraction(nn.Module):

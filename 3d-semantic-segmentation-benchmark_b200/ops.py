@@ -171,7 +171,8 @@ def knn_graph(x: torch.Tensor, k: int) -> torch.Tensor:
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
     nb = _lib.size("pcnbr_knn_expand_ws_bytes", B, F, N, k)
     ws = _ws(nb, x.device)
-    _lib.call("pcnbr_knn_expand_f32", x.data_ptr(), B, F, N, sf, sn, k, idx.data_ptr(), ws.data_ptr(), nb, _stream())
+    _lib.call("pcnbr_knn_expand_f32", x.data_ptr(), B, F, N, sf, sn, k, idx.data_ptr(), ws.data_ptr(), nb, _stream(),
+              tag=f"[F={F}]")
     return idx
 
 

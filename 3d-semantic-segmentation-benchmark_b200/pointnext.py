@@ -47,5 +47,5 @@ class PointNeXt(nn.Module):
         features_2 = self.fp3(coords_2, coords_3, features_2, features_3)
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2)
         features_0 = self.fp1(coords_0, coords_1, features_0, features_1)
-        x = self.drop(features_0).permute(0, 2, 1)
-        return self.conv(x).permute(0, 2, 1)
+        x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
+        return torch.nn.functional.linear(x, self.conv.weight.squeeze(-1), self.conv.bias)

@@ -178,29 +178,38 @@ def run_reference(args):
 
 
 def roofline_for(model, timing, B, N, peaks):
-    """Dominant libpcnbr kernel of the timed steps, against the roofline that bounds it."""
+    """Dominant libpcnbr entry point of the timed steps, against the roofline that bounds it.
+    `achieved` = algorithmic bytes or flops per launch (SURVEY.md 8d figure x units per launch) / mean launch time."""
     if not timing:
         return None
     name, (calls, ms) = max(timing.items(), key=lambda kv: kv[1][1])
     per_launch_s = ms / 1e3 / max(calls, 1)
-    k, F = 20, 64
+    k, F, O = 20, 64, 64
+    base = name.split("[")[0]
+    if base == "pcnbr_knn_expand_f32" and "[F=" in name:
+        F = int(name.split("[F=")[1].rstrip("]"))
     alg = {
-        # algorithmic bytes / flops per launch (SURVEY.md §8d figures x units per launch)
-        "pcnbr_knn_expand_f32": ("tensor", 2.0 * N * N * F * B, "TFLOP/s", 1e12),
+        "pcnbr_knn_expand_f32": ("tensor" if F in (32, 64) else "cuda-core", 2.0 * N * N * F * B, "TFLOP/s", 1e12),
         "pcnbr_edge_feature_f32": ("hbm", B * (8.0 * F * N * k + 4.0 * F * N + 4.0 * N * k), "GB/s", 1e9),
         "pcnbr_edge_feature_bwd_f32": ("hbm", B * (8.0 * F * N * k + 4.0 * F * N + 8.0 * N * k), "GB/s", 1e9),
-        "pcnbr_maxpool_f32": ("hbm", B * (4.0 * N * k * F + 5.0 * N * F), "GB/s", 1e9),
-        "pcnbr_maxpool_bwd_f32": ("hbm", B * (4.0 * N * k * F + 5.0 * N * F), "GB/s", 1e9),
-    }.get(name)
+        "pcnbr_maxpool_f32": ("hbm", B * (4.0 * N * k * O + 5.0 * N * O), "GB/s", 1e9),
+        "pcnbr_maxpool_bwd_f32": ("hbm", B * (4.0 * N * k * O + 5.0 * N * O), "GB/s", 1e9),
+        # fused EdgeConv gather: table + PQ rows (L2-resident, counted once) + 3 outputs + argmax
+        "pcnbr_edgeconv_fwd_f32": ("hbm", B * (4.0 * N * k + 8.0 * N * O + 13.0 * N * O), "GB/s", 1e9),
+        "pcnbr_edgeconv_bwd_f32": ("hbm", B * (8.0 * N * k + 13.0 * N * O + 8.0 * N * O), "GB/s", 1e9),
+        "pcnbr_csr_build": ("hbm", B * (4.0 * N * k * 3 + 8.0 * N), "GB/s", 1e9),
+    }.get(base)
     if alg is None:
         return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
                 "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls}
     bound, work, unit, scale = alg
     achieved = work / per_launch_s / scale
     peak = peaks["hbm_gbs"] if bound == "hbm" else peaks["tf32_tflops"]
-    return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-            "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls, "peak_source": peaks["source"],
-            "note": "per-launch work is the mean over this entry point's calls in a step (layer shapes differ)"}
+    return {"kernel": name, "bound": "tensor" if bound != "hbm" else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak, "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls,
+            "peak_source": peaks["source"],
+            "note": "flops counted once (2*N^2*F per cloud) although the kernel issues 6x (2 passes x 3xTF32 split)"
+                    if base == "pcnbr_knn_expand_f32" else "algorithmic bytes per launch, mean over this entry point's calls"}
 
 
 def load_peaks():
