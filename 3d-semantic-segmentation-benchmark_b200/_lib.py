@@ -39,7 +39,7 @@ PROTOTYPES = {
     "pcnbr_edge_feature_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pcnbr_edgeconv_fwd_blocks": (_I, [_I]),
     "pcnbr_edgeconv_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "pcnbr_edgeconv_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_edgeconv_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)

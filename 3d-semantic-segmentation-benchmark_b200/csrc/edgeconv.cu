@@ -82,22 +82,108 @@ edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ id
     }
 }
 
-// Backward gather over the inverse table: for source point m and column c
-//   c <  O : T1 = sum over incoming edges (n,j) with arg[n,c] == j of gs[n,c]     (gradient through the selected edge)
-//   c >= O : T2 = sum over incoming edges of Q[n, c-O]                           (for the BatchNorm variance term)
-struct EdgeConvBwdSrc {
-    const float* gs; const uint8_t* arg; const float* PQ; long N; int K; int O;
-    __device__ __forceinline__ float accum(int b, int e, int c, float acc) const {
-        const int n = e / K, j = e - n * K;
-        const size_t r = (size_t)b * N + n;
-        if (c < O) return (arg[r * O + c] == j) ? acc + gs[r * O + c] : acc;
-        return acc + PQ[r * 2 * O + c];
+// Backward: exact BatchNorm(train) + LeakyReLU + max backward in terms of (B,N,O) tensors.
+//   u[n,j] = P[idx[n,j]] + Q[n];  y = gamma (u - mu) r + beta;  out[n] = act(y[n, arg[n]])
+//   gs[n,o]  = dL/dy on the selected edge (host: g_out * act'(out))
+//   dL/du[n,j] = gr gs [j == arg] - c1 - c2r (u[n,j] - mu)            gr = gamma r, c1 = gr sum(gs)/M, c2r = gr r sum(gs yhat)/M
+//   dP[m] = sum over incoming edges (n,j) of m of dL/du[n,j]
+//         = gr T1[m] - deg(m) c1 - c2r (deg(m) (P[m] - mu) + T2[m]),  T1 = sum_{incoming, arg[n]==j} gs[n],  T2 = sum_incoming Q[n]
+//   dQ[n] = sum_j dL/du[n,j] = gr gs[n] - K c1 - c2r (s1[n] + K (Q[n] - mu))
+// One warp per point m gathers its incoming edges through the CSR inverse (ascending position: deterministic,
+// no atomics); segments longer than 64 edges (hub points) are split over the 8 warps of the CTA.
+template <int VPL>
+__device__ __forceinline__ void edgeconv_bwd_accumulate(const float* __restrict__ gs, const uint8_t* __restrict__ arg,
+                                                        const float* __restrict__ PQ, const int32_t* __restrict__ pm,
+                                                        size_t rowbase, int beg, int end, int K, int lane,
+                                                        float (&t1)[VPL], float (&t2)[VPL]) {
+    constexpr int O = 32 * VPL;
+    for (int t0 = beg; t0 < end; t0 += 32) {
+        const int e = (t0 + lane < end) ? pm[t0 + lane] : 0;
+        const int nl = e / K, jl = e - nl * K;
+        const int cnt = min(32, end - t0);
+#pragma unroll 4
+        for (int l = 0; l < cnt; ++l) {
+            const int n = __shfl_sync(PCNBR_FULL, nl, l), j = __shfl_sync(PCNBR_FULL, jl, l);
+            const size_t r = rowbase + n;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int c = lane + 32 * v;
+                const float g = gs[r * O + c];
+                t1[v] += (arg[r * O + c] == j) ? g : 0.f;
+                t2[v] += PQ[r * 2 * O + O + c];
+            }
+        }
     }
-};
-struct EdgeConvBwdDst {
-    float* T; long N; int O2;
-    __device__ __forceinline__ void store(int b, int s, int c, float v) const { T[((size_t)b * N + s) * O2 + c] = v; }
-};
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+edgeconv_bwd_kernel(const float* __restrict__ gs, const uint8_t* __restrict__ arg, const float* __restrict__ PQ,
+                    const float* __restrict__ s1, const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
+                    const float* __restrict__ coef, int N, int K, float* __restrict__ dPQ) {
+    constexpr int O = 32 * VPL;
+    __shared__ int s_beg[8], s_len[8];
+    __shared__ float s_part[8][2 * O];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* o = offsets + (size_t)b * (N + 1);
+    const int32_t* pm = perm + (size_t)b * N * K;
+    const size_t rowbase = (size_t)b * N;
+    float gr[VPL], c1[VPL], c2r[VPL], mu[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        const int c = lane + 32 * v;
+        gr[v] = coef[c]; c1[v] = coef[O + c]; c2r[v] = coef[2 * O + c]; mu[v] = coef[3 * O + c];
+    }
+    auto finish = [&](int m, int deg, const float (&t1)[VPL], const float (&t2)[VPL]) {
+        const size_t r = rowbase + m;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const int c = lane + 32 * v;
+            const float P = PQ[r * 2 * O + c], Q = PQ[r * 2 * O + O + c];
+            dPQ[r * 2 * O + c] = gr[v] * t1[v] - (float)deg * c1[v] - c2r[v] * ((float)deg * (P - mu[v]) + t2[v]);
+            dPQ[r * 2 * O + O + c] = gr[v] * gs[r * O + c] - (float)K * c1[v] - c2r[v] * (s1[r * O + c] + (float)K * (Q - mu[v]));
+        }
+    };
+    for (int m0 = blockIdx.x * 8; m0 < N; m0 += gridDim.x * 8) {
+        const int m = m0 + warp;
+        const int beg = (m < N) ? o[m] : 0;
+        const int len = (m < N) ? o[m + 1] - beg : 0;
+        if (lane == 0) { s_beg[warp] = beg; s_len[warp] = len; }
+        if (m < N && len <= SEG_HEAVY) {
+            float t1[VPL], t2[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) { t1[v] = 0.f; t2[v] = 0.f; }
+            edgeconv_bwd_accumulate<VPL>(gs, arg, PQ, pm, rowbase, beg, beg + len, K, lane, t1, t2);
+            finish(m, len, t1, t2);
+        }
+        __syncthreads();
+        for (int w = 0; w < 8; ++w) {
+            const int hl = s_len[w];
+            if (hl <= SEG_HEAVY) continue;
+            const int hb = s_beg[w];
+            const int piece = (hl + 7) / 8;
+            const int pb = min(hb + warp * piece, hb + hl), pe = min(pb + piece, hb + hl);
+            float t1[VPL], t2[VPL];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) { t1[v] = 0.f; t2[v] = 0.f; }
+            edgeconv_bwd_accumulate<VPL>(gs, arg, PQ, pm, rowbase, pb, pe, K, lane, t1, t2);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) { s_part[warp][lane + 32 * v] = t1[v]; s_part[warp][O + lane + 32 * v] = t2[v]; }
+            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    t1[v] = s_part[0][lane + 32 * v]; t2[v] = s_part[0][O + lane + 32 * v];
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) { t1[v] += s_part[k][lane + 32 * v]; t2[v] += s_part[k][O + lane + 32 * v]; }
+                }
+                finish(m0 + w, hl, t1, t2);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
 
 }  // namespace pcnbr
 
@@ -125,12 +211,19 @@ extern "C" int pcnbr_edgeconv_fwd_f32(const float* PQ, const int32_t* idx, const
     return 0;
 }
 
-extern "C" int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const float* PQ, const int32_t* offsets,
-                                      const int32_t* perm, int B, int N, int K, int O, float* T, pcnbr_stream_t stream) {
-    if (!gs || !arg || !PQ || !offsets || !perm || !T || B <= 0 || N <= 0 || K <= 0 || O <= 0) return PCNBR_E_BADARG;
-    EdgeConvBwdSrc src{gs, arg, PQ, (long)N, K, O};
-    EdgeConvBwdDst dst{T, (long)N, 2 * O};
-    segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, N * K, 2 * O);
+extern "C" int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const float* PQ, const float* s1,
+                                      const int32_t* offsets, const int32_t* perm, const float* coef, int B, int N,
+                                      int K, int O, float* dPQ, pcnbr_stream_t stream) {
+    if (!gs || !arg || !PQ || !s1 || !offsets || !perm || !coef || !dPQ || B <= 0 || N <= 0 || K <= 0) return PCNBR_E_BADARG;
+    if (K > 255 || (O != 32 && O != 64 && O != 128 && O != 256)) return PCNBR_E_TOOLARGE;
+    dim3 grid = segsum_grid(N, B);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (O) {
+        case 32:  edgeconv_bwd_kernel<1><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
+        case 64:  edgeconv_bwd_kernel<2><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
+        case 128: edgeconv_bwd_kernel<4><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
+        default:  edgeconv_bwd_kernel<8><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
+    }
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -42,7 +42,8 @@ constexpr uint32_t TC_SLAB_B = 256 * 128;
 // + C_REF  * |x_i|  max|x_j|    rounding of the REFERENCE's own fp32 value (64-term FMA chain, cascade |x|^2): its
 //                               ranking deviates from the true distances by that much, and we must follow it
 // + C_CTR  * max|x_j| max|x'_j| rounding of the centring subtraction itself
-constexpr float TC_C_FILT = 5e-5f, TC_C_REF = 1e-5f, TC_C_CTR = 1e-6f;
+//                               = 2 (F + 8) 2^-24 (F chain roundings + cascade |x|^2 + the two subtractions), 8.6e-6 at F=64
+constexpr float TC_C_FILT = 5e-5f, TC_C_CTR = 1e-6f;
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 
@@ -118,13 +119,14 @@ __global__ void __launch_bounds__(256)
 knn_tc_mean_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, float* __restrict__ part) {
     __shared__ float red[256];
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const int groups = 256 / F;                                   // F in {32, 64}
+    const int groups = 256 / F;                                   // F <= 64
     const int f = threadIdx.x % F, g = threadIdx.x / F;
     const int per = (N + TC_MEAN_CHUNKS - 1) / TC_MEAN_CHUNKS;
     const int n0 = chunk * per, n1 = min(N, n0 + per);
     const float* __restrict__ xb = x + (size_t)b * F * N;
     float acc = 0.f;
-    for (int n = n0 + g; n < n1; n += groups) acc += xb[(size_t)f * sf + (size_t)n * sn];
+    if (g < groups)
+        for (int n = n0 + g; n < n1; n += groups) acc += xb[(size_t)f * sf + (size_t)n * sn];
     red[threadIdx.x] = acc;
     __syncthreads();
     if (g == 0) {
@@ -138,7 +140,7 @@ knn_tc_mean_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, 
 // maxima of |x|^2 and |x'|^2 per cloud (bit patterns of non-negative floats order like the values).
 __global__ void __launch_bounds__(256)
 knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, const float* __restrict__ xx,
-                   int F, int N, long sf, long sn, float* __restrict__ xt, float* __restrict__ xhi,
+                   int F, int Fp, int N, long sf, long sn, float* __restrict__ xt, float* __restrict__ xhi,
                    float* __restrict__ xlo, float* __restrict__ xxc, uint32_t* __restrict__ maxes) {
     __shared__ float mu[64];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,15 +154,18 @@ knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, 
     float mx = 0.f, mxc = 0.f;
     for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
         float ss = 0.f;
-        for (int f = lane; f < F; f += 32) {
-            const float v = xb[(size_t)f * sf + (size_t)n * sn];
-            const float vc = __fsub_rn(v, mu[f]);
+        for (int f = lane; f < Fp; f += 32) {                     // channels F..Fp-1 are zero padding of the K dimension
+            float v = 0.f, vc = 0.f;
+            if (f < F) {
+                v = xb[(size_t)f * sf + (size_t)n * sn];
+                vc = __fsub_rn(v, mu[f]);
+                if (xt) xt[((size_t)b * N + n) * F + f] = v;
+            }
             uint32_t h, l;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(vc));
             const float rem = __fsub_rn(vc, __uint_as_float(h));
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
-            const size_t o = ((size_t)b * N + n) * F + f;
-            if (xt) xt[o] = v;
+            const size_t o = ((size_t)b * N + n) * Fp + f;
             xhi[o] = __uint_as_float(h);
             xlo[o] = __uint_as_float(l);
             ss = fmaf(vc, vc, ss);
@@ -183,7 +188,7 @@ template <int KATOMS, bool DUMP>      // F = 32 * KATOMS; DUMP: also write the r
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
               const float* __restrict__ xx, const float* __restrict__ xxc, const uint32_t* __restrict__ maxes,
-              int B, int N, int K,
+              int B, int N, int K, float c_ref,
               int32_t* __restrict__ qcnt, uint16_t* __restrict__ qidx, float* __restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (128B-swizzle atoms) by OFFSET, so the compiler keeps the shared address space
@@ -379,7 +384,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                         tau = m;
                     }
                     const float xm = __uint_as_float(maxes[2 * b]), xcm = __uint_as_float(maxes[2 * b + 1]);
-                    const float margin = TC_C_FILT * sqrtf(xxci * xcm) + TC_C_REF * sqrtf(xxi * xm) + TC_C_CTR * sqrtf(xm * xcm);
+                    const float margin = TC_C_FILT * sqrtf(xxci * xcm) + c_ref * sqrtf(xxi * xm) + TC_C_CTR * sqrtf(xm * xcm);
                     thr = fmaxf(tau - margin, -3.0e38f);           // finite: masked columns (s = -inf) never pass
                 }
             }
@@ -432,14 +437,20 @@ knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx,
         u64 key = PCNBR_KEY_MAX;
         if (c < total) {
             const int j = overflow ? c : (int)qidx[((size_t)b * N + i) * TC_QCAP + c];
-            const float4* __restrict__ xj = reinterpret_cast<const float4*>(xb + (size_t)j * F);
             float acc = 0.f;
-            for (int f4 = 0; f4 < F / 4; ++f4) {
-                const float4 v = xj[f4];
-                acc = (f4 == 0) ? __fmul_rn(myq[0], v.x) : __fmaf_rn(myq[4 * f4], v.x, acc);   // sgemm: FMA chain over f
-                acc = __fmaf_rn(myq[4 * f4 + 1], v.y, acc);
-                acc = __fmaf_rn(myq[4 * f4 + 2], v.z, acc);
-                acc = __fmaf_rn(myq[4 * f4 + 3], v.w, acc);
+            if ((F & 3) == 0) {
+                const float4* __restrict__ xj = reinterpret_cast<const float4*>(xb + (size_t)j * F);
+                for (int f4 = 0; f4 < F / 4; ++f4) {
+                    const float4 v = xj[f4];
+                    acc = (f4 == 0) ? __fmul_rn(myq[0], v.x) : __fmaf_rn(myq[4 * f4], v.x, acc);   // sgemm: FMA chain over f
+                    acc = __fmaf_rn(myq[4 * f4 + 1], v.y, acc);
+                    acc = __fmaf_rn(myq[4 * f4 + 2], v.z, acc);
+                    acc = __fmaf_rn(myq[4 * f4 + 3], v.w, acc);
+                }
+            } else {
+                const float* __restrict__ xj = xb + (size_t)j * F;
+                acc = __fmul_rn(myq[0], xj[0]);
+                for (int f = 1; f < F; ++f) acc = __fmaf_rn(myq[f], xj[f], acc);
             }
             const float inner = __fmul_rn(-2.0f, acc);                                         // dgcnn.py:16
             const float pd = __fsub_rn(__fsub_rn(-xx[(size_t)b * N + j], inner), xxi);         // dgcnn.py:18
@@ -501,18 +512,21 @@ struct TcWorkspace {
     size_t bytes;
 };
 
+static inline int tc_padded(int F) { return F <= 32 ? 32 : 64; }
+
 static TcWorkspace tc_carve(void* ws, int B, int F, int N, bool need_xt) {
+    const int Fp = tc_padded(F);
     TcWorkspace w;
     size_t off = 0;
     auto take = [&](size_t n) { size_t o = off; off += align256(n); return (uint8_t*)ws + o; };
     const size_t bn = (size_t)B * N;
     w.xx = (float*)take(bn * 4);
     w.xxc = (float*)take(bn * 4);
-    w.part = (float*)take((size_t)B * TC_MEAN_CHUNKS * F * 4);
+    w.part = (float*)take((size_t)B * TC_MEAN_CHUNKS * 64 * 4);
     w.maxes = (uint32_t*)take((size_t)B * 8);
     w.stats = (int32_t*)take(16);
-    w.xhi = (float*)take(bn * F * 4);
-    w.xlo = (float*)take(bn * F * 4);
+    w.xhi = (float*)take(bn * Fp * 4);
+    w.xlo = (float*)take(bn * Fp * 4);
     w.xt = need_xt ? (float*)take(bn * F * 4) : nullptr;
     w.qcnt = (int32_t*)take(bn * 4);
     w.qidx = (uint16_t*)take(bn * TC_QCAP * 2);
@@ -523,12 +537,12 @@ static TcWorkspace tc_carve(void* ws, int B, int F, int N, bool need_xt) {
 size_t knn_tc_ws_bytes(int B, int F, int N) { return tc_carve(nullptr, B, F, N, true).bytes; }
 
 bool knn_tc_supported(int F, int N, int K) {
-    return (F == 32 || F == 64) && K <= 32 && N >= 256 && N <= 65535;
+    return F >= 1 && F <= 64 && K <= 32 && N >= 256 && N <= 65535;     // F is zero-padded to 32 or 64 for the MMA
 }
 
 template <int KATOMS, bool DUMP>
 static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcWorkspace& w, int B, int N, int K,
-                     float* dump, cudaStream_t s) {
+                     float c_ref, float* dump, cudaStream_t s) {
     const size_t smem = 2 * KATOMS * TC_SLAB_A + TC_RING * TC_SLAB_B + TC_M * TC_QCAP * 2 + 2 * TC_N * 4 + 32 * 8 + 1024;
     cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<KATOMS, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -537,7 +551,7 @@ static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcWorks
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int units = B * ((N + TC_M - 1) / TC_M);
     const int grid = units < sms ? units : sms;
-    knn_tc_kernel<KATOMS, DUMP><<<grid, TC_THREADS, smem, s>>>(mh, ml, w.xx, w.xxc, w.maxes, B, N, K, w.qcnt, w.qidx, dump);
+    knn_tc_kernel<KATOMS, DUMP><<<grid, TC_THREADS, smem, s>>>(mh, ml, w.xx, w.xxc, w.maxes, B, N, K, c_ref, w.qcnt, w.qidx, dump);
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -557,16 +571,18 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
     PCNBR_CHECK_LAUNCH();
     int pb = (N + 7) / 8;
     if (pb > 148) pb = 148;
-    knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, N, sf, sn, point_major ? nullptr : w.xt, w.xhi,
+    const int Fp = tc_padded(F);
+    knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, Fp, N, sf, sn, point_major ? nullptr : w.xt, w.xhi,
                                                    w.xlo, w.xxc, w.maxes);
     PCNBR_CHECK_LAUNCH();
     CUtensorMap mh, ml;
-    int rc = make_map(&mh, w.xhi, B, N, F);
+    int rc = make_map(&mh, w.xhi, B, N, Fp);
     if (rc) return rc;
-    rc = make_map(&ml, w.xlo, B, N, F);
+    rc = make_map(&ml, w.xlo, B, N, Fp);
     if (rc) return rc;
-    if (dump) rc = (F == 64) ? launch_tc<2, true>(mh, ml, w, B, N, K, dump, s) : launch_tc<1, true>(mh, ml, w, B, N, K, dump, s);
-    else      rc = (F == 64) ? launch_tc<2, false>(mh, ml, w, B, N, K, dump, s) : launch_tc<1, false>(mh, ml, w, B, N, K, dump, s);
+    const float c_ref = 2.0f * (float)(F + 8) * 5.9604645e-8f;             // 2 (F+8) 2^-24, see TC_C_* above
+    if (dump) rc = (Fp == 64) ? launch_tc<2, true>(mh, ml, w, B, N, K, c_ref, dump, s) : launch_tc<1, true>(mh, ml, w, B, N, K, c_ref, dump, s);
+    else      rc = (Fp == 64) ? launch_tc<2, false>(mh, ml, w, B, N, K, c_ref, dump, s) : launch_tc<1, false>(mh, ml, w, B, N, K, c_ref, dump, s);
     if (rc) return rc;
     knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, 8 * F * sizeof(float), s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats);
     PCNBR_CHECK_LAUNCH();

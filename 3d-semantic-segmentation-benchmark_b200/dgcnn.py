@@ -74,19 +74,23 @@ class EdgeConv(nn.Module):
         Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
         PQ = torch.matmul(_point_major(x), Wcat.t())                        # library GEMM (B,N,F) x (F,2O)
         out = ops.edgeconv_fused(PQ, nbr, bn, act.negative_slope)           # (B,N,O), point-major
-        return out.permute(0, 2, 1)
+        return out.permute(0, 2, 1)                                         # (B,O,N) view, no copy
 
 
-def _run_pointwise(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-    """seq = [Conv1d(kernel 1), BatchNorm1d, LeakyReLU(, Dropout)] on x (B,Cin,N).  A 1x1 convolution IS a GEMM:
-    it is issued as one cuBLAS SGEMM (W @ x) instead of cuDNN's fp32 convolution engines, which on B200 pick
-    FFT / implicit-GEMM kernels 3-5x slower for these shapes.  Same parameters, same math."""
-    conv = seq[0]
-    y = torch.matmul(conv.weight.squeeze(-1), x)
-    if conv.bias is not None:
-        y = y + conv.bias.view(1, -1, 1)
-    for m in list(seq)[1:]:
-        y = m(y)
+def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
+    """seq = [Conv1d(kernel 1), BatchNorm1d, LeakyReLU(, Dropout)] applied to point-major rows (B,N,Cin) -> (B,N,Cout).
+    A 1x1 convolution IS a GEMM: it is issued as ONE cuBLAS SGEMM over the B*N rows (no transposes, no per-batch
+    GEMMs) instead of cuDNN's fp32 convolution engines, which on B200 pick FFT / implicit-GEMM kernels 3-5x slower
+    for these shapes.  BatchNorm1d sees the same rows (identical statistics).  Same parameters, same math."""
+    from .common import _batch_norm_rows
+    mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
+    conv = mods[0]
+    y = torch.nn.functional.linear(rows, conv.weight.squeeze(-1), conv.bias)
+    for m in mods[1:]:
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            y = _batch_norm_rows(m, y.view(-1, y.shape[-1])).view(y.shape)
+        else:
+            y = m(y)
     return y
 
 
@@ -119,11 +123,12 @@ class DGCNN(nn.Module):
         x2 = self.conv2(x1)
         x3 = self.conv3(x2)
         x4 = self.conv4(x3)
-        x_cat = torch.cat((x1, x2, x3, x4), dim=1)
-        x5 = _run_pointwise(self.conv5, x_cat)
-        x7 = _run_pointwise(self.conv7, _run_pointwise(self.conv6, torch.cat((x_cat, x5), dim=1)))
-        logits = _run_pointwise(nn.Sequential(self.conv8), x7).transpose(2, 1).contiguous()
-        return logits, x5, None
+        # the head runs point-major: (B,N,C) rows, one GEMM per layer, logits come out as (B,N,classes)
+        r_cat = torch.cat([t.permute(0, 2, 1) for t in (x1, x2, x3, x4)], dim=2)
+        r5 = _run_pointwise(self.conv5, r_cat)
+        r7 = _run_pointwise(self.conv7, _run_pointwise(self.conv6, torch.cat((r_cat, r5), dim=2)))
+        logits = _run_pointwise(self.conv8, r7)
+        return logits, r5.permute(0, 2, 1), None
 
 
 class DGCNNWithColor(nn.Module):
@@ -150,12 +155,13 @@ class DGCNNWithColor(nn.Module):
         x2 = self.conv2(x1)
         x3 = self.conv3(x2)
         x4 = self.conv4(x3)
-        color_feat = _run_pointwise(self.color_conv, x[:, 3:6, :])
-        x_cat = torch.cat((x1, x2, x3, x4, color_feat), dim=1)
-        x5 = _run_pointwise(self.conv5, x_cat)
-        x7 = _run_pointwise(self.conv7, _run_pointwise(self.conv6, torch.cat((x_cat, x5), dim=1)))
-        logits = _run_pointwise(nn.Sequential(self.conv8), x7).transpose(2, 1).contiguous()
-        return logits, x5, None
+        # the head runs point-major: (B,N,C) rows, one GEMM per layer, logits come out as (B,N,classes)
+        color = _run_pointwise(self.color_conv, x[:, 3:6, :].permute(0, 2, 1))
+        r_cat = torch.cat([t.permute(0, 2, 1) for t in (x1, x2, x3, x4)] + [color], dim=2)
+        r5 = _run_pointwise(self.conv5, r_cat)
+        r7 = _run_pointwise(self.conv7, _run_pointwise(self.conv6, torch.cat((r_cat, r5), dim=2)))
+        logits = _run_pointwise(self.conv8, r7)
+        return logits, r5.permute(0, 2, 1), None
 
 
 def get_model(num_classes=13, use_color=True, **kwargs):

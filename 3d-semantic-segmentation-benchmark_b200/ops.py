@@ -417,20 +417,13 @@ class _EdgeConvFusedFn(torch.autograd.Function):
         dbeta = gs.sum(dim=(0, 1))
         dgamma = (gs * yhat).sum(dim=(0, 1))
         gr = gamma * rstd
+        zero = torch.zeros_like(gr)
+        coef = torch.stack((gr, gr * dbeta / M if training else zero, gr * dgamma / M * rstd if training else zero,
+                            mean.to(torch.float32))).contiguous()
         offsets, perm = ctx.nbr.csr()
-        T = torch.empty(B, N, 2 * O, dtype=torch.float32, device=g.device)
-        _lib.call("pcnbr_edgeconv_bwd_f32", gs.data_ptr(), arg.data_ptr(), PQ.data_ptr(), offsets.data_ptr(),
-                  perm.data_ptr(), B, N, K, O, T.data_ptr(), _stream())
         dPQ = torch.empty_like(PQ)
-        if training:
-            c1 = gr * dbeta / M
-            c2r = gr * dgamma / M * rstd
-            deg = (offsets[:, 1:] - offsets[:, :-1]).to(torch.float32).unsqueeze(-1)
-            dPQ[..., :O] = gr * T[..., :O] - deg * c1 - c2r * (deg * (P - mean) + T[..., O:])
-            dPQ[..., O:] = gr * gs - K * c1 - c2r * (s1 + K * (Q - mean))
-        else:
-            dPQ[..., :O] = gr * T[..., :O]
-            dPQ[..., O:] = gr * gs
+        _lib.call("pcnbr_edgeconv_bwd_f32", gs.data_ptr(), arg.data_ptr(), PQ.data_ptr(), s1.data_ptr(),
+                  offsets.data_ptr(), perm.data_ptr(), coef.data_ptr(), B, N, K, O, dPQ.data_ptr(), _stream())
         return dPQ, None, dgamma, dbeta, None, None, None, None, None, None
 
 

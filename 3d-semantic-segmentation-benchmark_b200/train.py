@@ -59,3 +59,42 @@ def shard_batch(n_clouds: int, rank: int, world: int) -> slice:
     """Contiguous slice of the global batch owned by `rank` (clouds are independent units)."""
     per = (n_clouds + world - 1) // world
     return slice(min(rank * per, n_clouds), min((rank + 1) * per, n_clouds))
+
+
+class GraphedTrainStep:
+    """One full train step (forward, loss, backward, gradient all-reduce, Adam) captured ONCE into a CUDA graph and
+    replayed per batch: ~220 libpcnbr + ~400 library launches per step collapse into one graph launch, so the step
+    is bounded by the GPU, not by Python/launch overhead (CPU issue time was 15.6 ms of a 17 ms step).
+
+    Every libpcnbr entry point is capture-safe (asynchronous on the given stream, no host sync, workspaces come from
+    torch's graph-private pool).  Inputs are copied into static buffers; the loss comes back as a static tensor.
+    """
+
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, bucket: FlatGradBucket,
+                 forward_fn, example_batch, warmup: int = 3):
+        self.model, self.opt, self.bucket, self.forward_fn = model, optimizer, bucket, forward_fn
+        self.static = [t.clone() for t in example_batch]
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # eager warm-up on a side stream (allocator, cuBLAS handles)
+            for _ in range(warmup):
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step_body()
+
+    def _step_body(self):
+        self.bucket.zero()
+        loss = self.forward_fn(self.model, *self.static)
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, *batch):
+        for dst, src in zip(self.static, batch):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -69,14 +69,14 @@ PCNBR_API int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M,
  * x[b, f*stride_f + n*stride_n] (batch stride F*N), any layout of the (F,N) plane.
  * pd_ij = ((-xx_j) - (-2*c_ij)) - xx_i, c = FMA chain over f ascending, xx = ATen cascade sum of
  * squares; idx (B,N,K) by descending pd, lowest index on ties.  F <= 256, K <= min(N,128).
- * F in {32,64}, 256 <= N <= 65535, K <= 32 run on the tensor cores (tcgen05 3xTF32 distance tiles fed by
+ * F <= 64 (zero-padded to 32/64), 256 <= N <= 65535, K <= 32 run on the tensor cores (tcgen05 3xTF32 distance tiles fed by
  * TMA, threshold filter out of TMEM, exact fp32 re-rank of the survivors: same bits as the CUDA-core
  * path; set PCNBR_KNN_GENERIC=1 to force the latter).  ws: pcnbr_knn_expand_ws_bytes(B,F,N,K) bytes. */
 PCNBR_API size_t pcnbr_knn_expand_ws_bytes(int B, int F, int N, int K);
 PCNBR_API int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
                          int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
-/* Test hook of the tensor-core path (F in {32,64}, 256 <= N <= 65535, K <= 32): same result as
+/* Test hook of the tensor-core path (F <= 64, 256 <= N <= 65535, K <= 32): same result as
  * pcnbr_knn_expand_f32, plus scores (B,N,N) = the tensor-core ranking scores 2*x_i.x_j - |x_j|^2 (may be
  * NULL) and stats[2] = {sum of survivor-queue lengths, rows that overflowed to the exact full scan}. */
 PCNBR_API int pcnbr_knn_tc_debug_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
@@ -138,10 +138,12 @@ PCNBR_API int pcnbr_edgeconv_fwd_blocks(int N);
 PCNBR_API int pcnbr_edgeconv_fwd_f32(const float* PQ, const int32_t* idx, const uint8_t* selmax, const float* shift,
                            int B, int N, int K, int O, float* psel, uint8_t* arg, float* s1, float* partial,
                            pcnbr_stream_t stream);
-/* T (B,N,2O): T[m, :O] = sum over incoming edges (n,j) of m with arg[n,o]==j of gs[n,o];
- * T[m, O:] = sum over incoming edges of Q[n,:].  CSR of idx viewed as (B, N*K). */
-PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const float* PQ, const int32_t* offsets,
-                           const int32_t* perm, int B, int N, int K, int O, float* T, pcnbr_stream_t stream);
+/* Exact backward of BatchNorm(train)+LeakyReLU+max in (B,N,O) terms.  gs = dL/dy on the selected edge;
+ * coef (4,O) = {gamma*rstd, c1, c2r, mean} (c1 = c2r = 0 in eval mode); CSR of idx viewed as (B, N*K).
+ * dPQ (B,N,2O) = [dL/dP | dL/dQ]; deterministic, no atomics. */
+PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const float* PQ, const float* s1,
+                           const int32_t* offsets, const int32_t* perm, const float* coef, int B, int N, int K,
+                           int O, float* dPQ, pcnbr_stream_t stream);
 
 #ifdef __cplusplus
 }

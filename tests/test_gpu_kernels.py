@@ -314,11 +314,14 @@ def test_knn_tc_scores_match_fp32_within_margin(pkg, dev):
         assert stats[1] == 0 and stats[0] <= 2 * 512 * 32        # ~k+4 survivors per row, no overflow
 
 
-@pytest.mark.parametrize("F,N,k,B", [(64, 4096, 20, 2), (64, 1000, 20, 3), (32, 2048, 16, 2), (64, 300, 32, 2), (64, 4096, 1, 1)])
+@pytest.mark.parametrize("F,N,k,B", [(64, 4096, 20, 2), (64, 1000, 20, 3), (32, 2048, 16, 2), (64, 300, 32, 2), (64, 4096, 1, 1),
+                                     (3, 4096, 20, 2), (6, 1024, 20, 2), (17, 600, 8, 2), (40, 512, 20, 2)])
 def test_knn_tc_vs_oracle(pkg, dev, F, N, k, B):
     x = torch.randn(B, F, N, generator=_gen(F + N + k))
     if N == 1000:                                  # post-LeakyReLU-like features: common offset, small spread
         x = x * 0.05 + 1.0
+    if F == 3:                                     # S3DIS xyz: 1 m x 1 m x 3 m block at a 17 m room offset
+        x = torch.rand(B, F, N, generator=_gen(5)) * torch.tensor([1.0, 1.0, 3.0]).view(1, 3, 1) + torch.tensor([17.0, 12.0, 0.0]).view(1, 3, 1)
     want = canon.knn_expand(x, k)[0]
     idx, _, stats = _tc_debug(pkg, x.to(dev), k)
     assert torch.equal(idx.cpu(), want)
