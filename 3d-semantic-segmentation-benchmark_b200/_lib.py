@@ -40,6 +40,8 @@ PROTOTYPES = {
     "pcnbr_edgeconv_fwd_blocks": (_I, [_I]),
     "pcnbr_edgeconv_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pcnbr_edgeconv_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_prof_enable": (None, [_I]),
+    "pcnbr_prof_collect": (_I, [_P, _Z]),
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
@@ -108,4 +110,26 @@ def stop_timing() -> dict:
     torch.cuda.synchronize()
     out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (timing or {}).items()}
     timing = None
+    return out
+
+
+def prof_enable(on: bool = True) -> None:
+    """Per-KERNEL timing inside libpcnbr (csrc/prof.cu): CUDA events on the launch stream around every kernel,
+    plus the launch's algorithmic bytes / flops.  Keep it off while capturing a CUDA graph."""
+    load().pcnbr_prof_enable(1 if on else 0)
+
+
+def prof_collect() -> dict:
+    """-> {kernel: {"calls", "ms", "bytes", "flops"}} summed over the launches since the last collect; synchronises."""
+    cap = 1 << 22
+    buf = ctypes.create_string_buffer(cap)
+    load().pcnbr_prof_collect(ctypes.cast(buf, c_void_p), cap)
+    out: dict = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, nbytes, flops = line.split("\t")
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+        d["calls"] += 1
+        d["ms"] += float(ms)
+        d["bytes"] += float(nbytes)
+        d["flops"] += float(flops)
     return out

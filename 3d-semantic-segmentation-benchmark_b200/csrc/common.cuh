@@ -80,6 +80,21 @@ struct WarpList {
     }
 };
 
+// ---- optional per-kernel timing (prof.cu): events on the launch stream + the launch's algorithmic work
+bool prof_enabled();
+struct ProfScope {
+    ProfScope(const char* name, cudaStream_t s, double bytes, double flops);
+    ~ProfScope();
+    int slot_;
+    cudaStream_t stream_;
+};
+// PCNBR_TIMED("kernel", stream, algorithmic_bytes, algorithmic_flops, kernel<<<...>>>(...));
+#define PCNBR_TIMED(name, s, bytes, flops, ...)                       \
+    do {                                                              \
+        pcnbr::ProfScope prof_scope__((name), (s), (bytes), (flops)); \
+        __VA_ARGS__;                                                  \
+    } while (0)
+
 // cross-file host helpers
 int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, float* xx, cudaStream_t s);     // select.cu
 bool knn_tc_supported(int F, int N, int K);                                                              // knn_tc.cu

@@ -134,14 +134,15 @@ extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t*
     cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)B * (N + 1), s);
     if (e != cudaSuccess) return (int)e;
     const int gx = min((E + 255) / 256, 1184);
-    csr_count_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt);
+    // algorithmic bytes: the table is read once per pass (4E), plus the pass's own output
+    PCNBR_TIMED("csr_count_kernel", s, (double)B * (4.0 * E + 4.0 * N), 0.0, (csr_count_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt)));
     PCNBR_CHECK_LAUNCH();
-    csr_scan_kernel<<<B, 1024, 0, s>>>(cnt, N, offsets, cnt);       // cursor overwrites cnt in place
+    PCNBR_TIMED("csr_scan_kernel", s, (double)B * 12.0 * N, 0.0, (csr_scan_kernel<<<B, 1024, 0, s>>>(cnt, N, offsets, cnt)));       // cursor overwrites cnt in place
     PCNBR_CHECK_LAUNCH();
-    csr_fill_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt, tmp);
+    PCNBR_TIMED("csr_fill_kernel", s, (double)B * 8.0 * E, 0.0, (csr_fill_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt, tmp)));
     PCNBR_CHECK_LAUNCH();
     const int gs = min((N + 7) / 8, 1184);
-    csr_sort_kernel<<<dim3(gs, B), 256, 0, s>>>(offsets, tmp, E, N, perm);
+    PCNBR_TIMED("csr_sort_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0, (csr_sort_kernel<<<dim3(gs, B), 256, 0, s>>>(offsets, tmp, E, N, perm)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

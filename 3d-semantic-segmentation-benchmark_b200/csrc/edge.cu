@@ -80,7 +80,9 @@ extern "C" int pcnbr_edge_feature_f32(const float* xt, const int32_t* idx, int B
     const long per_warp = (2 * F <= 32) ? 32 / (2 * F) : 1;
     long blocks = (rows + per_warp * 8 - 1) / (per_warp * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    edge_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(xt, idx, N, F, K, rows, out);
+    // K9: 8 F N k written + 4 F N + 4 N k read per cloud
+    PCNBR_TIMED("edge_fwd_kernel", (cudaStream_t)stream, (double)B * (8.0 * F * N * K + 4.0 * F * N + 4.0 * N * K), (double)B * N * K * F,
+                (edge_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(xt, idx, N, F, K, rows, out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -90,7 +92,8 @@ extern "C" int pcnbr_edge_feature_bwd_f32(const float* g, const int32_t* offsets
     if (!g || !offsets || !perm || !gxt || B <= 0 || N <= 0 || F <= 0 || K <= 0) return PCNBR_E_BADARG;
     EdgeBwdSrc src{g, (long)N * K, 2 * F};
     EdgeBwdDst dst{g, gxt, (long)N, F, K};
-    segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, N * K, F);
+    PCNBR_TIMED("segsum_kernel<edge_bwd>", (cudaStream_t)stream, (double)B * (8.0 * F * N * K + 4.0 * F * N + 8.0 * N * K), 3.0 * B * (double)N * K * F,
+                (segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, N * K, F)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

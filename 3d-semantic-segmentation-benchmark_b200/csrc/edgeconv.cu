@@ -201,11 +201,13 @@ extern "C" int pcnbr_edgeconv_fwd_f32(const float* PQ, const int32_t* idx, const
     if (K > 255 || (O != 32 && O != 64 && O != 128 && O != 256)) return PCNBR_E_TOOLARGE;
     dim3 grid(pcnbr_edgeconv_fwd_blocks(N), B);
     cudaStream_t s = (cudaStream_t)stream;
+    // algorithmic bytes per cloud: table 4 N K + PQ rows 8 N O (gathers hit L2) + psel, s1 (8 N O) + arg (N O)
+    const double wb = (double)B * (4.0 * N * K + 17.0 * N * O), wf = 5.0 * B * (double)N * K * O;
     switch (O) {
-        case 32:  edgeconv_fwd_kernel<1><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
-        case 64:  edgeconv_fwd_kernel<2><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
-        case 128: edgeconv_fwd_kernel<4><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
-        default:  edgeconv_fwd_kernel<8><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial); break;
+        case 32:  PCNBR_TIMED("edgeconv_fwd_kernel", s, wb, wf, (edgeconv_fwd_kernel<1><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial))); break;
+        case 64:  PCNBR_TIMED("edgeconv_fwd_kernel", s, wb, wf, (edgeconv_fwd_kernel<2><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial))); break;
+        case 128: PCNBR_TIMED("edgeconv_fwd_kernel", s, wb, wf, (edgeconv_fwd_kernel<4><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial))); break;
+        default:  PCNBR_TIMED("edgeconv_fwd_kernel", s, wb, wf, (edgeconv_fwd_kernel<8><<<grid, 256, 0, s>>>(PQ, idx, selmax, shift, N, K, psel, arg, s1, partial))); break;
     }
     PCNBR_CHECK_LAUNCH();
     return 0;
@@ -218,11 +220,13 @@ extern "C" int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const
     if (K > 255 || (O != 32 && O != 64 && O != 128 && O != 256)) return PCNBR_E_TOOLARGE;
     dim3 grid = segsum_grid(N, B);
     cudaStream_t s = (cudaStream_t)stream;
+    // algorithmic bytes per cloud: perm 4 N K + offsets 4 N + gs, s1 (8 N O) + arg (N O) + PQ (8 N O) + dPQ (8 N O)
+    const double wb = (double)B * (4.0 * N * K + 4.0 * N + 25.0 * N * O), wf = 3.0 * B * (double)N * K * O;
     switch (O) {
-        case 32:  edgeconv_bwd_kernel<1><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
-        case 64:  edgeconv_bwd_kernel<2><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
-        case 128: edgeconv_bwd_kernel<4><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
-        default:  edgeconv_bwd_kernel<8><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ); break;
+        case 32:  PCNBR_TIMED("edgeconv_bwd_kernel", s, wb, wf, (edgeconv_bwd_kernel<1><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ))); break;
+        case 64:  PCNBR_TIMED("edgeconv_bwd_kernel", s, wb, wf, (edgeconv_bwd_kernel<2><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ))); break;
+        case 128: PCNBR_TIMED("edgeconv_bwd_kernel", s, wb, wf, (edgeconv_bwd_kernel<4><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ))); break;
+        default:  PCNBR_TIMED("edgeconv_bwd_kernel", s, wb, wf, (edgeconv_bwd_kernel<8><<<grid, 256, 0, s>>>(gs, arg, PQ, s1, offsets, perm, coef, N, K, dPQ))); break;
     }
     PCNBR_CHECK_LAUNCH();
     return 0;

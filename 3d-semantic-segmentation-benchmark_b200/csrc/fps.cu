@@ -146,15 +146,17 @@ extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_
     using namespace pcnbr;
     if (!xyz || !start || !idx_out || B <= 0 || N <= 0 || C <= 0) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if (N <= 256)        fps_reg_kernel<1, 256><<<B, 256, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
-    else if (N <= 512)   fps_reg_kernel<1, 512><<<B, 512, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
-    else if (N <= 1024)  fps_reg_kernel<1, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
-    else if (N <= 2048)  fps_reg_kernel<2, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
-    else if (N <= 4096)  fps_reg_kernel<4, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
-    else if (N <= 8192)  fps_reg_kernel<8, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out);
+    // algorithmic work: 12N + 16C compulsory bytes, 10 N C lane-ops per cloud
+    const double wb = (double)B * (12.0 * N + 16.0 * C), wf = 10.0 * B * (double)N * C;
+    if (N <= 256)        PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 256><<<B, 256, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
+    else if (N <= 512)   PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 512><<<B, 512, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
+    else if (N <= 1024)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
+    else if (N <= 2048)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<2, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
+    else if (N <= 4096)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<4, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
+    else if (N <= 8192)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<8, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
     else {
         if (!ws || ws_bytes < pcnbr_fps_ws_bytes(B, N)) return PCNBR_E_WORKSPACE;
-        fps_big_kernel<1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out, (float*)ws);
+        PCNBR_TIMED("fps_big_kernel", s, wb, wf, (fps_big_kernel<1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out, (float*)ws)));
     }
     PCNBR_CHECK_LAUNCH();
     return 0;

@@ -82,7 +82,9 @@ extern "C" int pcnbr_group_f32(const float* p, const float* feat, const float* q
     const long per_warp = (W <= 32) ? 32 / W : 1;
     long blocks = (rows + per_warp * 8 - 1) / (per_warp * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    group_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, rows, out);
+    // K5: 4 M K (3+D) written + 4 M K idx + 4 N (3+D) + 12 M read per cloud
+    PCNBR_TIMED("group_fwd_kernel", (cudaStream_t)stream, (double)B * (4.0 * M * K * W + 4.0 * M * K + 4.0 * N * W + 12.0 * M), 0.0,
+                (group_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, rows, out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -92,7 +94,9 @@ extern "C" int pcnbr_group_bwd_f32(const float* gout, const int32_t* offsets, co
     if (!gout || !offsets || !perm || !gfeat || B <= 0 || N <= 0 || E <= 0 || D <= 0) return PCNBR_E_BADARG;
     GroupBwdSrc src{gout, (long)E, 3 + D};
     RowMajorDst dst{gfeat, (long)N, D};
-    segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, E, D);
+    // K7: 4 E D read + 4 E perm + 4 N offsets + 4 N D written per cloud
+    PCNBR_TIMED("segsum_kernel<group_bwd>", (cudaStream_t)stream, (double)B * (4.0 * E * D + 4.0 * E + 4.0 * N + 4.0 * N * D), (double)B * E * D,
+                (segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, E, D)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -72,7 +72,9 @@ extern "C" int pcnbr_interp_f32(const float* feat, const int32_t* idx, const flo
     if (K > INTERP_KMAX) return PCNBR_E_TOOLARGE;
     int gx = (N + 7) / 8;
     if (gx > 148 * 8) gx = 148 * 8;
-    interp_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, K, out, coef);
+    // K8: 4 N D written + 4 M D read + 8 N k (idx, d2) read + 4 N k coef written per cloud
+    PCNBR_TIMED("interp_fwd_kernel", (cudaStream_t)stream, (double)B * (4.0 * N * D + 4.0 * M * D + 12.0 * N * K), 3.0 * B * (double)N * D * K,
+                (interp_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, K, out, coef)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -83,7 +85,9 @@ extern "C" int pcnbr_interp_bwd_f32(const float* g, const float* coef, const int
         return PCNBR_E_BADARG;
     InterpBwdSrc src{g, coef, (long)N, D, K};
     InterpDst dst{gfeat, (long)M, D};
-    segsum_kernel<<<segsum_grid(M, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, M, N * K, D);
+    // bwd: 4 N D read + 8 N k (coef, perm) + 4 M offsets + 4 M D written per cloud (the k re-reads of g hit L2)
+    PCNBR_TIMED("segsum_kernel<interp_bwd>", (cudaStream_t)stream, (double)B * (4.0 * N * D + 8.0 * N * K + 4.0 * M + 4.0 * M * D), 2.0 * B * (double)N * K * D,
+                (segsum_kernel<<<segsum_grid(M, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, M, N * K, D)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

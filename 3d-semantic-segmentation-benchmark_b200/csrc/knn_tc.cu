@@ -551,7 +551,10 @@ static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcWorks
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int units = B * ((N + TC_M - 1) / TC_M);
     const int grid = units < sms ? units : sms;
-    knn_tc_kernel<KATOMS, DUMP><<<grid, TC_THREADS, smem, s>>>(mh, ml, w.xx, w.xxc, w.maxes, B, N, K, c_ref, w.qcnt, w.qidx, dump);
+    // K4: 2 N^2 F flop per cloud counted ONCE (whatever the split / pass count issues); compulsory
+    // bytes: the operands (4 N F) and the survivor queues
+    PCNBR_TIMED("knn_tc_kernel", s, (double)B * N * (4.0 * 32 * KATOMS + 4.0 + 2.0 * TC_QCAP), 2.0 * B * (double)N * N * (32.0 * KATOMS),
+                (knn_tc_kernel<KATOMS, DUMP><<<grid, TC_THREADS, smem, s>>>(mh, ml, w.xx, w.xxc, w.maxes, B, N, K, c_ref, w.qcnt, w.qidx, dump)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -567,13 +570,15 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
     // exact |x|^2 in the reference's summation order (select.cu); channel means; centred TF32 split
     int rc0 = launch_sumsq(x, B, F, N, sf, sn, w.xx, s);
     if (rc0) return rc0;
-    knn_tc_mean_kernel<<<dim3(TC_MEAN_CHUNKS, B), 256, 0, s>>>(x, F, N, sf, sn, w.part);
+    PCNBR_TIMED("knn_tc_mean_kernel", s, 4.0 * B * (double)N * F, (double)B * N * F,
+                (knn_tc_mean_kernel<<<dim3(TC_MEAN_CHUNKS, B), 256, 0, s>>>(x, F, N, sf, sn, w.part)));
     PCNBR_CHECK_LAUNCH();
     int pb = (N + 7) / 8;
     if (pb > 148) pb = 148;
     const int Fp = tc_padded(F);
-    knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, Fp, N, sf, sn, point_major ? nullptr : w.xt, w.xhi,
-                                                   w.xlo, w.xxc, w.maxes);
+    PCNBR_TIMED("knn_tc_prep_kernel", s, (double)B * N * (4.0 * F + 8.0 * Fp + 8.0), 6.0 * B * (double)N * F,
+                (knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, Fp, N, sf, sn, point_major ? nullptr : w.xt, w.xhi,
+                                                                w.xlo, w.xxc, w.maxes)));
     PCNBR_CHECK_LAUNCH();
     CUtensorMap mh, ml;
     int rc = make_map(&mh, w.xhi, B, N, Fp);
@@ -584,7 +589,8 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
     if (dump) rc = (Fp == 64) ? launch_tc<2, true>(mh, ml, w, B, N, K, c_ref, dump, s) : launch_tc<1, true>(mh, ml, w, B, N, K, c_ref, dump, s);
     else      rc = (Fp == 64) ? launch_tc<2, false>(mh, ml, w, B, N, K, c_ref, dump, s) : launch_tc<1, false>(mh, ml, w, B, N, K, c_ref, dump, s);
     if (rc) return rc;
-    knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, 8 * F * sizeof(float), s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats);
+    PCNBR_TIMED("knn_tc_rerank_kernel", s, (double)B * N * (4.0 * F + 8.0 + 2.0 * TC_QCAP + 4.0 * K), 2.0 * B * (double)N * F * K,
+                (knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, 8 * F * sizeof(float), s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats)));
     PCNBR_CHECK_LAUNCH();
     if (stats_out) {
         e = cudaMemcpyAsync(stats_out, w.stats, 8, cudaMemcpyDeviceToDevice, s);

@@ -112,10 +112,11 @@ extern "C" int pcnbr_maxpool_f32(const float* x, long R, int K, int D, long stri
     if (!x || !out || !arg || R <= 0 || K <= 0 || D <= 0) return PCNBR_E_BADARG;
     if (K > 255) return PCNBR_E_TOOLARGE;
     cudaStream_t s = (cudaStream_t)stream;
+    const double wb = (double)R * D * (4.0 * K + 5.0);       // K6: 4 R K D read + 5 R D written
     if (cl4_ok(x, D, stride_r, stride_k, stride_d) && ((uintptr_t)out % 16) == 0 && ((uintptr_t)arg % 4) == 0)
-        maxpool_cl4_kernel<<<pool_blocks(R * (D / 4)), 256, 0, s>>>(x, R, K, D / 4, stride_r, stride_k, out, arg);
+        PCNBR_TIMED("maxpool_cl4_kernel", s, wb, 0.0, (maxpool_cl4_kernel<<<pool_blocks(R * (D / 4)), 256, 0, s>>>(x, R, K, D / 4, stride_r, stride_k, out, arg)));
     else
-        maxpool_generic_kernel<<<pool_blocks(R * D), 256, 0, s>>>(x, R, K, D, stride_r, stride_k, stride_d, out, arg);
+        PCNBR_TIMED("maxpool_generic_kernel", s, wb, 0.0, (maxpool_generic_kernel<<<pool_blocks(R * D), 256, 0, s>>>(x, R, K, D, stride_r, stride_k, stride_d, out, arg)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -125,10 +126,11 @@ extern "C" int pcnbr_maxpool_bwd_f32(const float* g, const uint8_t* arg, long R,
     if (!g || !gx || !arg || R <= 0 || K <= 0 || D <= 0) return PCNBR_E_BADARG;
     if (K > 255) return PCNBR_E_TOOLARGE;
     cudaStream_t s = (cudaStream_t)stream;
+    const double wb = (double)R * D * (4.0 * K + 5.0);       // 5 R D read + 4 R K D written
     if (cl4_ok(gx, D, stride_r, stride_k, stride_d) && ((uintptr_t)g % 16) == 0 && ((uintptr_t)arg % 4) == 0)
-        maxpool_bwd_cl4_kernel<<<pool_blocks(R * (D / 4)), 256, 0, s>>>(g, arg, R, K, D / 4, stride_r, stride_k, gx);
+        PCNBR_TIMED("maxpool_bwd_cl4_kernel", s, wb, 0.0, (maxpool_bwd_cl4_kernel<<<pool_blocks(R * (D / 4)), 256, 0, s>>>(g, arg, R, K, D / 4, stride_r, stride_k, gx)));
     else
-        maxpool_bwd_generic_kernel<<<pool_blocks(R * D), 256, 0, s>>>(g, arg, R, K, D, stride_r, stride_k, stride_d, gx);
+        PCNBR_TIMED("maxpool_bwd_generic_kernel", s, wb, 0.0, (maxpool_bwd_generic_kernel<<<pool_blocks(R * D), 256, 0, s>>>(g, arg, R, K, D, stride_r, stride_k, stride_d, gx)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

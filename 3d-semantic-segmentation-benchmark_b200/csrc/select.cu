@@ -205,7 +205,8 @@ knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
 }
 
 int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, float* xx, cudaStream_t s) {
-    sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, sf, sn, xx);
+    PCNBR_TIMED("sumsq_cascade_kernel", s, 4.0 * B * ((double)N * F + N), 2.0 * B * (double)N * F,
+                (sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, sf, sn, xx)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -227,9 +228,12 @@ static int launch_select(const float* q, const float* p, int B, int M, int N, fl
     if (!q || !p || !idx || B <= 0 || M <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
     if (K > 128) return PCNBR_E_TOOLARGE;
     dim3 grid((M + 7) / 8, B), block(256);
-    if (K <= 32)      select_xyz_kernel<1, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2);
-    else if (K <= 64) select_xyz_kernel<2, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2);
-    else              select_xyz_kernel<4, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2);
+    // K2/K3: 8 M N flop + compares; compulsory 12 (N + M) + 4 M K (+ 4 M K distances) bytes per cloud
+    const double wb = (double)B * (12.0 * (N + M) + (d2 ? 8.0 : 4.0) * M * K), wf = 8.0 * B * (double)M * N;
+    const char* nm = RADIUS ? "select_xyz_kernel<ball>" : "select_xyz_kernel<knn>";
+    if (K <= 32)      PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<1, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2)));
+    else if (K <= 64) PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<2, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2)));
+    else              PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<4, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -284,7 +288,8 @@ extern "C" int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long st
         cudaError_t e = cudaFuncSetAttribute(knn_expand_kernel<NS>,                                      \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         if (e != cudaSuccess) return (int)e;                                                             \
-        knn_expand_kernel<NS><<<grid, block, smem, s>>>(x, xx, F, N, stride_f, stride_n, K, tile, idx);  \
+        PCNBR_TIMED("knn_expand_kernel", s, (double)B * (4.0 * N * F + 4.0 * N * K), 2.0 * B * (double)N * N * F,      \
+                    (knn_expand_kernel<NS><<<grid, block, smem, s>>>(x, xx, F, N, stride_f, stride_n, K, tile, idx)));  \
     } while (0)
     if (K <= 32)      PCNBR_LAUNCH_EXPAND(1);
     else if (K <= 64) PCNBR_LAUNCH_EXPAND(2);

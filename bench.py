@@ -178,39 +178,37 @@ def run_reference(args):
 # --------------------------------------------------------------------------- our arm
 
 
-def roofline_for(model, timing, B, N, peaks):
-    """Dominant libpcnbr entry point of the timed steps, against the roofline that bounds it.
-    `achieved` = algorithmic bytes or flops per launch (SURVEY.md 8d figure x units per launch) / mean launch time."""
-    if not timing:
+TENSOR_KERNELS = {"knn_tc_kernel"}          # tcgen05 kernels: roofline = tensor pipe (TF32); everything else moves bytes
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of this kernel at the bench shapes (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
         return None
-    name, (calls, ms) = max(timing.items(), key=lambda kv: kv[1][1])
-    per_launch_s = ms / 1e3 / max(calls, 1)
-    k, F, O = 20, 64, 64
-    base = name.split("[")[0]
-    if base == "pcnbr_knn_expand_f32" and "[F=" in name:
-        F = int(name.split("[F=")[1].rstrip("]"))
-    alg = {
-        "pcnbr_knn_expand_f32": ("tensor" if F in (32, 64) else "cuda-core", 2.0 * N * N * F * B, "TFLOP/s", 1e12),
-        "pcnbr_edge_feature_f32": ("hbm", B * (8.0 * F * N * k + 4.0 * F * N + 4.0 * N * k), "GB/s", 1e9),
-        "pcnbr_edge_feature_bwd_f32": ("hbm", B * (8.0 * F * N * k + 4.0 * F * N + 8.0 * N * k), "GB/s", 1e9),
-        "pcnbr_maxpool_f32": ("hbm", B * (4.0 * N * k * O + 5.0 * N * O), "GB/s", 1e9),
-        "pcnbr_maxpool_bwd_f32": ("hbm", B * (4.0 * N * k * O + 5.0 * N * O), "GB/s", 1e9),
-        # fused EdgeConv gather: table + PQ rows (L2-resident, counted once) + 3 outputs + argmax
-        "pcnbr_edgeconv_fwd_f32": ("hbm", B * (4.0 * N * k + 8.0 * N * O + 13.0 * N * O), "GB/s", 1e9),
-        "pcnbr_edgeconv_bwd_f32": ("hbm", B * (8.0 * N * k + 13.0 * N * O + 8.0 * N * O), "GB/s", 1e9),
-        "pcnbr_csr_build": ("hbm", B * (4.0 * N * k * 3 + 8.0 * N), "GB/s", 1e9),
-    }.get(base)
-    if alg is None:
-        return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
-                "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls}
-    bound, work, unit, scale = alg
-    achieved = work / per_launch_s / scale
-    peak = peaks["hbm_gbs"] if bound == "hbm" else peaks["tf32_tflops"]
-    return {"kernel": name, "bound": "tensor" if bound != "hbm" else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
-            "frac": achieved / peak, "traffic": None, "avg_launch_ms": per_launch_s * 1e3, "calls": calls,
-            "peak_source": peaks["source"],
-            "note": "flops counted once (2*N^2*F per cloud) although the kernel issues 6x (2 passes x 3xTF32 split)"
-                    if base == "pcnbr_knn_expand_f32" else "algorithmic bytes per launch, mean over this entry point's calls"}
+    ent = json.load(open(p)).get(kernel)
+    return ent.get("dram_bytes_per_launch") if ent else None
+
+
+def roofline_for(kernels, peaks):
+    """Dominant libpcnbr KERNEL of the profiled steps against the roofline that bounds it.
+    `achieved` = algorithmic bytes (or flops) of its launches, as stated by the launch sites from the SURVEY.md 8d
+    formulas, / their summed duration (CUDA events on the launch stream, csrc/prof.cu)."""
+    if not kernels:
+        return None
+    name, d = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    sec = d["ms"] / 1e3
+    tensor = name in TENSOR_KERNELS
+    achieved = (d["flops"] / 1e12 if tensor else d["bytes"] / 1e9) / sec
+    peak = peaks["tf32_tflops"] if tensor else peaks["hbm_gbs"]
+    out = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": achieved, "peak": peak,
+           "unit": "TFLOP/s" if tensor else "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name),
+           "avg_launch_ms": d["ms"] / d["calls"], "calls": d["calls"], "peak_source": peaks["source"],
+           "algorithmic_per_launch": (d["flops"] if tensor else d["bytes"]) / d["calls"]}
+    out["note"] = ("flops counted once (2*N^2*F per cloud), whatever the kernel issues" if tensor else
+                   "algorithmic (compulsory) bytes; gathers that hit L2 are not counted")
+    return out
 
 
 def load_peaks():
@@ -307,13 +305,13 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
     # per-kernel durations: the same kernels launched eagerly with CUDA events around every libpcnbr call
     # (events cannot be recorded inside a graph replay); also counts the libpcnbr launches of one step
-    launches0 = pkg._lib.launches
-    pkg._lib.start_timing()
     prof_steps = 3
+    pkg._lib.prof_enable(True)
     for i in range(prof_steps):
         eager_step(*devb[i % n_batches])
-    timing = pkg._lib.stop_timing()
-    launches = (pkg._lib.launches - launches0) // prof_steps * args.steps
+    kernels = pkg._lib.prof_collect()
+    pkg._lib.prof_enable(False)
+    launches = sum(d["calls"] for d in kernels.values()) // prof_steps * args.steps
 
     pts_per_step = B * N * world
     value = pts_per_step * args.steps / (ms_total / 1e3)
@@ -340,14 +338,22 @@ def run_ours(args):
                     "loss": last_loss},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": roofline_for(args.model, timing, B, N, peaks),
+            "roofline": roofline_for(kernels, peaks),
             "cpu_baseline": cpu_base,
-            "kernel_ms_per_step": {k: round(v[1] / prof_steps, 4) for k, v in sorted(timing.items(), key=lambda kv: -kv[1][1])},
+            "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+            "kernel_roofline_frac": {k: round((v["flops"] / 1e9 / peaks["tf32_tflops"] if k in TENSOR_KERNELS else v["bytes"] / 1e6 / peaks["hbm_gbs"]) / v["ms"], 4)
+                                     for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
             "launch_mode": "eager" if args.no_graph else "whole train step captured in one CUDA graph, replayed per batch",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a captured graph holds NCCL work: tear down in order (graph, then a device sync, then the group) and
+        # leave without the interpreter's atexit pass, which can block on the communicator
+        del step
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

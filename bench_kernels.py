@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""bench_kernels.py -- the kernel sweep of BASELINE.json configs[4]: FPS / ball query / kNN / group / pool /
+interpolate / edge features / scatter-add at N = 4k-100k, k = 16-32, C = 3-256, one GPU (replicas only at N GPUs).
+
+    python bench_kernels.py [--quick] [--iters 10] [--md profiles/rX_kernel_sweep.md]
+
+Every libpcnbr KERNEL is timed by the library's own profiler (csrc/prof.cu: CUDA events on the launch stream
+around each kernel), with L2 flushed between iterations (a 512 MB memset), after 3 warm-up iterations.  The roofline
+fraction is ALGORITHMIC bytes (or flops) -- stated by the launch site from the SURVEY.md 8d formulas -- / time /
+the measured peak in MEASURED_PEAKS.json.  Prints one JSON line per (op, shape, kernel) and a markdown table.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true", help="BASELINE shapes only (no N sweep)")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--md", default="")
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_kernels.py: no CUDA device; the hot path has no CPU fallback")
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    lib, ops = pkg._lib, pkg.ops
+    lib.load()
+    dev = torch.device("cuda:0")
+    peaks = bench.load_peaks()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+
+    def run(op, shape, fn, bwd=False):
+        """fn() -> tensor (its .sum().backward() is also run when bwd)."""
+        def once():
+            out = fn()
+            if bwd:
+                out.backward(torch.ones_like(out))
+        for _ in range(3):
+            once()
+        torch.cuda.synchronize()
+        lib.prof_enable(True)
+        for _ in range(args.iters):
+            flush.zero_()
+            once()
+        kernels = lib.prof_collect()
+        lib.prof_enable(False)
+        for name, d in kernels.items():
+            us = 1e3 * d["ms"] / d["calls"]
+            tensor = name in bench.TENSOR_KERNELS
+            ach = (d["flops"] / 1e12 if tensor else d["bytes"] / 1e9) / (d["ms"] / 1e3)
+            peak = peaks["tf32_tflops"] if tensor else peaks["hbm_gbs"]
+            row = {"op": op, "shape": shape, "kernel": name, "us_per_launch": round(us, 2), "launches_per_call": d["calls"] // args.iters,
+                   "bound": "tensor" if tensor else "hbm", "achieved": round(ach, 2), "unit": "TFLOP/s" if tensor else "GB/s",
+                   "frac": round(ach / peak, 4), "gflop_per_s": round(d["flops"] / 1e9 / (d["ms"] / 1e3), 1)}
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+
+    g = torch.Generator().manual_seed(0)
+
+    def cloud(B, N):
+        pts, _, _ = pkg.synthetic.s3dis_blocks(B, N, seed=N % 997)
+        return pts[:, :, :3].contiguous().to(dev)
+
+    def feats(B, N, D):
+        return torch.randn(B, N, D, generator=g).to(dev)
+
+    # ---- PointNet++ SSG shapes at B=32 (configs[0]/[2]) and the N sweep (configs[4])
+    pn_levels = [(4096, 1024, 0.1, 32, 6, 64), (1024, 256, 0.2, 32, 64, 128), (256, 64, 0.4, 32, 128, 256), (64, 16, 0.8, 32, 256, 512)]
+    sweep_n = [] if args.quick else [8192, 16384, 32768, 65536, 100000]
+    for (N, C, r, K, D, O) in pn_levels + [(n, 1024, 0.1, 32, 6, 64) for n in sweep_n]:
+        B = 32 if N <= 4096 else max(1, min(8, (1 << 18) // N))
+        xyz = cloud(B, N)
+        f = feats(B, N, D).requires_grad_(True)
+        start = torch.zeros(B, dtype=torch.int32, device=dev)
+        sh = f"B={B} N={N} C={C} K={K} D={D}"
+        run("fps", sh, lambda: ops.farthest_point_sample(xyz, C, start).float())
+        _, cen = ops.farthest_point_sample(xyz, C, start, return_coords=True)
+        run("ball_query", sh + f" r={r}", lambda: ops.query_ball_point(r, K, xyz, cen).float())
+        nbr = ops.NeighborIndex(ops.query_ball_point(r, K, xyz, cen), N)
+        run("csr_build", sh, lambda: (setattr(nbr, "_csr", None), nbr.csr()[1].float())[1])
+        run("group(+bwd)", sh, lambda: ops.group_points(xyz, f, cen, nbr, r), bwd=True)
+        conv_out = torch.randn(B, C, K, O, generator=g).to(dev).requires_grad_(True)
+        run("maxpool(+bwd)", f"B={B} C={C} K={K} D'={O}", lambda: ops.max_pool_neighbors(conv_out, 2), bwd=True)
+        coarse = feats(B, C, O).requires_grad_(True)
+        run("knn3", f"B={B} N={N} M={C}", lambda: ops.knn_points(xyz, cen, 3)[1])
+        i3, d3 = ops.knn_points(xyz, cen, 3)
+        n3 = ops.NeighborIndex(i3, C)
+        n3.csr()
+        run("interpolate(+bwd)", f"B={B} N={N} M={C} D={O}", lambda: ops.three_interpolate(coarse, n3, d3), bwd=True)
+        del xyz, f, conv_out, coarse
+
+    # ---- DGCNN shapes at B=16, k=20 (configs[1]) and the sweep
+    for (N, F, k) in [(4096, 3, 20), (4096, 64, 20)] + [(n, 64, kk) for n in sweep_n[:4] for kk in (20,)] + ([] if args.quick else [(4096, 64, 16), (4096, 64, 32), (4096, 32, 20)]):
+        B = 16 if N <= 4096 else max(1, min(8, (1 << 16) // N))
+        xt = feats(B, N, F).requires_grad_(True)
+        sh = f"B={B} N={N} F={F} k={k}"
+        run("knn_feature", sh, lambda: ops.knn_graph(xt.detach().transpose(1, 2), k).float())
+        nbr = ops.NeighborIndex(ops.knn_graph(xt.detach().transpose(1, 2), k), N)
+        run("csr_build", sh, lambda: (setattr(nbr, "_csr", None), nbr.csr()[1].float())[1])
+        if N <= 16384:
+            run("edge_feature(+bwd)", sh, lambda: ops.edge_features(xt, nbr), bwd=True)
+        if F == 64:
+            bn = torch.nn.BatchNorm2d(64).to(dev)
+            PQ = feats(B, N, 128).requires_grad_(True)
+            run("edgeconv_fused(+bwd)", sh + " O=64", lambda: ops.edgeconv_fused(PQ, nbr, bn, 0.2), bwd=True)
+        del xt
+
+    md = ["| op | shape | kernel | µs/launch | algorithmic | roofline | frac |", "|---|---|---|---:|---:|---|---:|"]
+    for r in rows:
+        md.append(f"| {r['op']} | {r['shape']} | `{r['kernel']}` | {r['us_per_launch']} | {r['achieved']} {r['unit']} | {r['bound']} | {r['frac']} |")
+    text = "\n".join(md)
+    if args.md:
+        with open(args.md, "w") as fh:
+            fh.write(f"# kernel sweep ({torch.cuda.get_device_name(0)}; peaks: {peaks['source']}: HBM {peaks['hbm_gbs']} GB/s, TF32 {peaks['tf32_tflops']} TFLOP/s)\n\n")
+            fh.write("Per-kernel CUDA-event timings from libpcnbr's profiler, L2 flushed between iterations; ALGORITHMIC bytes/flops per launch.\n\n")
+            fh.write(text + "\n")
+    print(text)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,6 +145,14 @@ PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const 
                            const int32_t* offsets, const int32_t* perm, const float* coef, int B, int N, int K,
                            int O, float* dPQ, pcnbr_stream_t stream);
 
+/* ---- measurement hook (bench.py roofline, kernel sweep) -- not part of the reference interface
+ * pcnbr_prof_enable(1): bracket every kernel this library launches with CUDA events on its launch stream and
+ * remember the launch's ALGORITHMIC bytes / flops.  Must be off while a CUDA graph is captured.
+ * pcnbr_prof_collect: synchronise, write one line "kernel\tms\tbytes\tflops\n" per launch into out (cap
+ * bytes, NUL-terminated), clear the log and return the number of launches recorded. */
+PCNBR_API void pcnbr_prof_enable(int on);
+PCNBR_API int pcnbr_prof_collect(char* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif
