@@ -69,16 +69,18 @@ PCNBR_API int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M,
  * x[b, f*stride_f + n*stride_n] (batch stride F*N), any layout of the (F,N) plane.
  * pd_ij = ((-xx_j) - (-2*c_ij)) - xx_i, c = FMA chain over f ascending, xx = ATen cascade sum of
  * squares; idx (B,N,K) by descending pd, lowest index on ties.  F <= 256, K <= min(N,128).
- * F <= 64 (zero-padded to 32/64), 256 <= N <= 65535, K <= 32 run on the tensor cores (tcgen05 3xTF32 distance tiles fed by
- * TMA, threshold filter out of TMEM, exact fp32 re-rank of the survivors: same bits as the CUDA-core
- * path; set PCNBR_KNN_GENERIC=1 to force the latter).  ws: pcnbr_knn_expand_ws_bytes(B,F,N,K) bytes. */
+ * F <= 64, 256 <= N <= 65535, K <= 32 run on the tensor cores: tcgen05 kind::f16 tiles of the centred, scaled
+ * features fed by TMA, with the |x_j|^2 term, the per-pair fp16 error bound and the row threshold folded into a
+ * 16-wide tail K-slice, so the epilogue reads finished scores out of TMEM (group maxima, then sign bits); the
+ * survivors are re-ranked in exact fp32: same bits as the CUDA-core path (PCNBR_KNN_GENERIC=1 forces the latter).
+ * ws: pcnbr_knn_expand_ws_bytes(B,F,N,K) bytes. */
 PCNBR_API size_t pcnbr_knn_expand_ws_bytes(int B, int F, int N, int K);
 PCNBR_API int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
                          int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
 /* Test hook of the tensor-core path (F <= 64, 256 <= N <= 65535, K <= 32): same result as
- * pcnbr_knn_expand_f32, plus scores (B,N,N) = the tensor-core ranking scores 2*x_i.x_j - |x_j|^2 (may be
- * NULL) and stats[2] = {sum of survivor-queue lengths, rows that overflowed to the exact full scan}. */
+ * pcnbr_knn_expand_f32, plus scores (B,N,N) = the pass-1 tensor-core values a_i.a_j - |a_j|^2/2 - C1|a_i||a_j| of the
+ * centred, scaled features a (lower bounds of the exact ranking score; may be NULL) and stats[2] = {sum of survivor-queue lengths, rows that overflowed to the exact full scan}. */
 PCNBR_API int pcnbr_knn_tc_debug_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
                            int32_t* idx, void* ws, size_t ws_bytes, float* scores, int32_t* stats,
                            pcnbr_stream_t stream);

@@ -295,23 +295,30 @@ def _tc_debug(pkg, x, k, want_scores=False):
     return idx, scores, stats.cpu()
 
 
-def test_knn_tc_scores_match_fp32_within_margin(pkg, dev):
-    """The tcgen05 3xTF32 tile (TMA + UMMA descriptors + TMEM readback) reproduces the centred score
-    s = 2 x'_i.x'_j - |x'_j|^2 (x' = x - channel mean) far inside the error the survivor filter assumes
-    (C_FILT/2 * |x'_i| * max|x'_j| with C_FILT = 5e-5) -- with and without a large common offset."""
+def test_knn_tc_scores_are_lower_bounds_within_margin(pkg, dev):
+    """The tcgen05 fp16 tile (TMA + bulk-copied tail slice + UMMA descriptors + TMEM readback) delivers, in pass 1,
+    L_ij = a_i.a_j - |a_j|^2/2 - C1 |a_i||a_j| for the centred, power-of-two scaled features a = (x - mean)/S:
+    a LOWER bound of the exact score that is at most 2 C1 |a_i||a_j| + C0 below it (C1 = 1e-3 covers the fp16
+    rounding of both operands) -- with and without a large common offset."""
     for offset, scale in ((0.0, 1.0), (3.0, 0.1)):
         x = torch.randn(2, 64, 512, generator=_gen(21)) * scale + offset
         idx, scores, stats = _tc_debug(pkg, x.to(dev), 20, want_scores=True)
         xd = x.double()
-        xc = xd - xd.mean(dim=2, keepdim=True)
-        exact = 2 * torch.matmul(xc.transpose(1, 2), xc) - (xc ** 2).sum(1).unsqueeze(1)
-        err = (scores.cpu().double() - exact).abs()
-        norm = (xc ** 2).sum(1).sqrt()
-        eps = 2.5e-5 * norm.unsqueeze(2) * norm.amax(dim=1).view(-1, 1, 1)
+        mean = xd.mean(dim=2, keepdim=True)
+        v = (x.abs().amax(dim=(1, 2)) + mean.abs().amax(dim=(1, 2)).float()).double()
+        S = 2.0 ** (torch.floor(torch.log2(v)) + 1)                   # next binade above max|x| + max|mean|
+        a = (xd - mean) / S.view(-1, 1, 1)
+        exact = torch.matmul(a.transpose(1, 2), a) - 0.5 * (a ** 2).sum(1).unsqueeze(1)
+        norm = (a ** 2).sum(1).sqrt()
+        pair = norm.unsqueeze(2) * norm.unsqueeze(1)
+        bmax = norm.amax(dim=1).view(-1, 1, 1)
+        c0 = 2e-5 * bmax ** 2 + 1e-6 * bmax + 1e-7
+        gap = exact - scores.cpu().double()
         assert not torch.isnan(scores).any()
-        assert (err <= 0.5 * eps).all(), f"max err/eps {(err / eps).max().item():.3e}"
+        assert (gap >= -c0).all(), f"not a lower bound: min gap {gap.min().item():.3e}"
+        assert (gap <= 2.1e-3 * pair + c0).all(), f"max gap/pair {(gap / (pair + 1e-12)).max().item():.3e}"
         assert torch.equal(idx.cpu(), canon.knn_expand(x, 20)[0])
-        assert stats[1] == 0 and stats[0] <= 2 * 512 * 32        # ~k+4 survivors per row, no overflow
+        assert stats[1] == 0 and stats[0] <= 2 * 512 * 48        # ~k + a few survivors per row, no overflow
 
 
 @pytest.mark.parametrize("F,N,k,B", [(64, 4096, 20, 2), (64, 1000, 20, 3), (32, 2048, 16, 2), (64, 300, 32, 2), (64, 4096, 1, 1),
