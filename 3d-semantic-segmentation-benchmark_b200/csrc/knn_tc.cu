@@ -137,6 +137,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+// sign bits of 16 accumulator values, value i -> bit 15 - i; four independent funnel-shift chains
+__device__ __forceinline__ uint32_t sign_bits16(const uint32_t (&r)[16]) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c0 = __funnelshift_l(r[i], c0, 1);
+        c1 = __funnelshift_l(r[4 + i], c1, 1);
+        c2 = __funnelshift_l(r[8 + i], c2, 1);
+        c3 = __funnelshift_l(r[12 + i], c3, 1);
+    }
+    return (c0 << 12) | (c1 << 8) | (c2 << 4) | c3;
+}
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -402,7 +422,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
         const int rloc = rb * 128 + rblk;
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         uint8_t* mytail = sAtail + rb * TC_TAIL_BYTES + tail_offset(rblk, 0);
-        uint16_t* myq = sQ + rloc * TC_QSTRIDE;
+        const uint32_t qaddr = smem_u32(sQ + rloc * TC_QSTRIDE);
         uint32_t tile = 0;
         const float NEG_INF = __int_as_float(0xff800000);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -437,49 +457,44 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
                     const uint32_t tcol = tmem_base + tlane + buf * TC_N;
                     mbar_wait(&tmem_full[buf], tphase);
                     tc_fence_after();
+                    // four 32-column quarters, TMEM loads double-buffered: quarter q+1 is in flight while q is processed
+                    uint32_t ra[2][16], rb2[2][16];
+                    tmem_ld16(tcol, ra[0]);
+                    tmem_ld16(tcol + 16, rb2[0]);
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t r0[32], r1[32];
-                        tmem_ld32(tcol + half * 64, r0);
-                        tmem_ld32(tcol + half * 64 + 32, r1);
+                    for (int q = 0; q < 4; ++q) {
                         tmem_wait_ld();
-                        if (half == 1) {                                   // accumulator fully read: hand it back early
+                        if (q < 3) {
+                            tmem_ld16(tcol + (q + 1) * 32, ra[(q + 1) & 1]);
+                            tmem_ld16(tcol + (q + 1) * 32 + 16, rb2[(q + 1) & 1]);
+                        } else {                                           // accumulator fully read: hand it back early
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                         }
+                        const uint32_t (&a)[16] = ra[q & 1];
+                        const uint32_t (&c)[16] = rb2[q & 1];
                         if (pass == 0) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                gmax[half * 32 + i] = fmax3(gmax[half * 32 + i], __uint_as_float(r0[i]), __uint_as_float(r1[i]));
+                            for (int i = 0; i < 16; ++i)
+                                gmax[q * 16 + i] = fmax3(gmax[q * 16 + i], __uint_as_float(a[i]), __uint_as_float(c[i]));
                             if (DUMP) {
                                 if (dump && vrow)
-                                    for (int i = 0; i < 64; ++i) {
-                                        const int j = ct * TC_N + half * 64 + i;
-                                        const uint32_t v = (i < 32) ? r0[i & 31] : r1[i & 31];
+                                    for (int i = 0; i < 32; ++i) {
+                                        const int j = ct * TC_N + q * 32 + i;
+                                        const uint32_t v = (i < 16) ? a[i & 15] : c[i & 15];
                                         if (j < N) dump[((size_t)b * N + row) * N + j] = __uint_as_float(v);
                                     }
                             }
                         } else {
-                            uint32_t s0 = 0, s1 = 0;                           // sign bits, column i -> bit 31 - i
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                s0 = __funnelshift_l(r0[i], s0, 1);
-                                s1 = __funnelshift_l(r1[i], s1, 1);
-                            }
-                            const int j0 = ct * TC_N + half * 64;
-                            uint32_t hit = ~s0;                                // acc >= +0  <=>  survivor
-                            while (hit) {                                      // rare: ~k+8 survivors per 4096 columns
+                            // acc >= +0  <=>  survivor; column i of the quarter -> bit 31 - i
+                            uint32_t hit = ~((sign_bits16(a) << 16) | sign_bits16(c));
+                            const int j0 = ct * TC_N + q * 32;
+                            while (hit) {                                      // rare: ~k+5 survivors per 4096 columns
                                 const int i = __clz(hit);
                                 hit &= ~(0x80000000u >> i);
-                                if (cnt < TC_QCAP) myq[cnt] = (uint16_t)(j0 + i);
-                                ++cnt;
-                            }
-                            hit = ~s1;
-                            while (hit) {
-                                const int i = __clz(hit);
-                                hit &= ~(0x80000000u >> i);
-                                if (cnt < TC_QCAP) myq[cnt] = (uint16_t)(j0 + 32 + i);
+                                if (cnt < TC_QCAP)
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(qaddr + 2u * cnt), "h"((uint16_t)(j0 + i)) : "memory");
                                 ++cnt;
                             }
                         }
@@ -536,54 +551,141 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
 
 // ------------------------------------------------------------------------------------ exact re-rank
 
-// One warp per query row: exact reference arithmetic on the survivors (or on all N columns when the
-// queue overflowed), sorted by (value, index) with the same WarpList as the CUDA-core kernels.
+constexpr int RR_STRIDE = 68;          // floats per staged survivor row: 16-byte aligned, LDS.128 conflict-free
+
+// exact reference score (dgcnn.py:16-18) of column j, whose features are at xj (stride 1), for the query row q,
+// as an ascending sort key
+__device__ __forceinline__ u64 rerank_key(const float* xj, const float* q, float xxj, float xxi, int j, int F) {
+    float acc;
+    if ((F & 3) == 0) {
+        acc = 0.f;
+        for (int f4 = 0; f4 < F / 4; ++f4) {
+            const float4 v = reinterpret_cast<const float4*>(xj)[f4];
+            const float4 w = reinterpret_cast<const float4*>(q)[f4];
+            acc = (f4 == 0) ? __fmul_rn(w.x, v.x) : __fmaf_rn(w.x, v.x, acc);           // sgemm: FMA chain over f
+            acc = __fmaf_rn(w.y, v.y, acc);
+            acc = __fmaf_rn(w.z, v.z, acc);
+            acc = __fmaf_rn(w.w, v.w, acc);
+        }
+    } else {
+        acc = __fmul_rn(q[0], xj[0]);
+        for (int f = 1; f < F; ++f) acc = __fmaf_rn(q[f], xj[f], acc);
+    }
+    const float inner = __fmul_rn(-2.0f, acc);                                         // dgcnn.py:16
+    const float pd = __fsub_rn(__fsub_rn(-xxj, inner), xxi);                           // dgcnn.py:18
+    return pack_key(f2ord(-pd), (uint32_t)j);
+}
+
+// One warp per query row.  The survivors' feature rows are gathered with COALESCED loads (one row per warp
+// instruction; a lane-per-row gather costs 25+ L1 wavefronts per instruction) into a padded shared-memory tile,
+// then each lane runs the reference's sequential FMA chain for one survivor out of shared memory, and the
+// (value, index) keys are sorted by rank counting across the warp: the lane with rank r < K writes idx[r].
+// Rows whose queue overflowed are re-ranked by an exact full scan with the same WarpList as the CUDA-core kernels.
+// dynamic smem: 8 warps x (32 x RR_STRIDE + 64) floats
 __global__ void __launch_bounds__(256)
 knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx, const int32_t* __restrict__ qcnt,
                      const uint16_t* __restrict__ qidx, int N, int F, int K, int32_t* __restrict__ idx,
                      int32_t* __restrict__ stats) {
-    extern __shared__ float sq[];                 // [8 warps][F]
+    extern __shared__ __align__(16) float rr_smem[];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * 8 + warp;
     if (i >= N) return;
+    float* xs = rr_smem + warp * (32 * RR_STRIDE + 64);      // [32][RR_STRIDE]
+    float* myq = xs + 32 * RR_STRIDE;                         // [64]
     const float* __restrict__ xb = xt + (size_t)b * N * F;
-    float* myq = sq + warp * F;
+    const float* __restrict__ xxb = xx + (size_t)b * N;
     for (int f = lane; f < F; f += 32) myq[f] = xb[(size_t)i * F + f];
-    __syncwarp();
-    const float xxi = xx[(size_t)b * N + i];
+    const float xxi = xxb[i];
     const int cnt = qcnt[(size_t)b * N + i];
     const bool overflow = cnt > TC_QCAP;
-    const int total = overflow ? N : cnt;
     if (stats && lane == 0) {
         atomicAdd(&stats[0], cnt);
         if (overflow) atomicAdd(&stats[1], 1);
     }
+    int32_t* __restrict__ out = idx + ((size_t)b * N + i) * K;
+    if (!overflow) {
+        constexpr int R = TC_QCAP / 32;
+        const uint16_t* __restrict__ q = qidx + ((size_t)b * N + i) * TC_QCAP;
+        u64 key[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            key[r] = PCNBR_KEY_MAX;
+            if (r * 32 < cnt) {                                       // warp-uniform
+                const int c = r * 32 + lane;
+                const int j = (c < cnt) ? (int)q[c] : 0;
+                const float xxj = xxb[j];
+                const int n = min(32, cnt - r * 32);
+                __syncwarp();
+                if (F == 64) {
+                    // half a warp per row: one LDG.128 + one STS.128 move two 256-byte rows; 8 loads in flight
+                    const int hl = lane & 15, hi = lane >> 4;
+                    for (int l0 = 0; l0 < n; l0 += 16) {
+                        float4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int jj = __shfl_sync(PCNBR_FULL, j, min(l0 + 2 * u + hi, n - 1));
+                            v[u] = reinterpret_cast<const float4*>(xb + (size_t)jj * 64)[hl];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (l0 + 2 * u + hi < n)
+                                reinterpret_cast<float4*>(xs + (l0 + 2 * u + hi) * RR_STRIDE)[hl] = v[u];
+                    }
+                } else {
+                    for (int l0 = 0; l0 < n; l0 += 8) {               // 8 coalesced rows (16 loads) in flight per batch
+                        float v0[8], v1[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float* __restrict__ src = xb + (size_t)__shfl_sync(PCNBR_FULL, j, min(l0 + u, n - 1)) * F;
+                            v0[u] = (lane < F) ? src[lane] : 0.f;
+                            v1[u] = (lane + 32 < F) ? src[lane + 32] : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (l0 + u < n) {
+                                xs[(l0 + u) * RR_STRIDE + lane] = v0[u];
+                                xs[(l0 + u) * RR_STRIDE + lane + 32] = v1[u];
+                            }
+                    }
+                }
+                __syncwarp();
+                if (c < cnt) key[r] = rerank_key(xs + lane * RR_STRIDE, myq, xxj, xxi, j, F);
+            }
+        }
+        int rank[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rank[r] = 0;
+#pragma unroll
+        for (int sr = 0; sr < R; ++sr) {
+            if (sr * 32 < cnt) {                                      // warp-uniform
+                const int n = min(32, cnt - sr * 32);
+                for (int l = 0; l < n; ++l) {
+                    const u64 other = shfl64(key[sr], l);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r * 32 < cnt) rank[r] += (other < key[r]) ? 1 : 0;       // warp-uniform guard
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r * 32 + lane < cnt && rank[r] < K) out[rank[r]] = (int32_t)(uint32_t)key[r];
+        return;
+    }
+    __syncwarp();
     WarpList<1> list;
     list.init();
     u64 thr = PCNBR_KEY_MAX;
-    for (int c0 = 0; c0 < total; c0 += 32) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
         const int c = c0 + lane;
         u64 key = PCNBR_KEY_MAX;
-        if (c < total) {
-            const int j = overflow ? c : (int)qidx[((size_t)b * N + i) * TC_QCAP + c];
-            float acc = 0.f;
-            if ((F & 3) == 0) {
-                const float4* __restrict__ xj = reinterpret_cast<const float4*>(xb + (size_t)j * F);
-                for (int f4 = 0; f4 < F / 4; ++f4) {
-                    const float4 v = xj[f4];
-                    acc = (f4 == 0) ? __fmul_rn(myq[0], v.x) : __fmaf_rn(myq[4 * f4], v.x, acc);   // sgemm: FMA chain over f
-                    acc = __fmaf_rn(myq[4 * f4 + 1], v.y, acc);
-                    acc = __fmaf_rn(myq[4 * f4 + 2], v.z, acc);
-                    acc = __fmaf_rn(myq[4 * f4 + 3], v.w, acc);
-                }
-            } else {
-                const float* __restrict__ xj = xb + (size_t)j * F;
-                acc = __fmul_rn(myq[0], xj[0]);
-                for (int f = 1; f < F; ++f) acc = __fmaf_rn(myq[f], xj[f], acc);
-            }
-            const float inner = __fmul_rn(-2.0f, acc);                                         // dgcnn.py:16
-            const float pd = __fsub_rn(__fsub_rn(-xx[(size_t)b * N + j], inner), xxi);         // dgcnn.py:18
-            key = pack_key(f2ord(-pd), (uint32_t)j);
+        if (c < N) {
+            const float* __restrict__ xj = xb + (size_t)c * F;        // direct (uncoalesced) reads: rare path
+            float acc = __fmul_rn(myq[0], xj[0]);
+            for (int f = 1; f < F; ++f) acc = __fmaf_rn(myq[f], xj[f], acc);
+            const float inner = __fmul_rn(-2.0f, acc);
+            const float pd = __fsub_rn(__fsub_rn(-xxb[c], inner), xxi);
+            key = pack_key(f2ord(-pd), (uint32_t)c);
         }
         uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
         while (pass) {
@@ -596,7 +698,7 @@ knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx,
             }
         }
     }
-    if (lane < K) idx[((size_t)b * N + i) * K + lane] = (int32_t)(uint32_t)list.v[0];
+    if (lane < K) out[lane] = (int32_t)(uint32_t)list.v[0];
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -724,8 +826,11 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
         default: rc = dump ? launch_tc<4, true>(mm, w, B, F, N, K, c_ref, dump, s) : launch_tc<4, false>(mm, w, B, F, N, K, c_ref, dump, s); break;
     }
     if (rc) return rc;
+    const size_t rr_smem = 8 * (32 * RR_STRIDE + 64) * sizeof(float);
+    e = cudaFuncSetAttribute(knn_tc_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem);
+    if (e != cudaSuccess) return (int)e;
     PCNBR_TIMED("knn_tc_rerank_kernel", s, (double)B * N * (4.0 * F + 8.0 + 2.0 * TC_QCAP + 4.0 * K), 2.0 * B * (double)N * F * K,
-                (knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, 8 * F * sizeof(float), s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats)));
+                (knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, rr_smem, s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats)));
     PCNBR_CHECK_LAUNCH();
     if (stats_out) {
         e = cudaMemcpyAsync(stats_out, w.stats, 8, cudaMemcpyDeviceToDevice, s);
