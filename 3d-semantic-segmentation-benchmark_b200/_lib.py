@@ -40,6 +40,10 @@ PROTOTYPES = {
     "pcnbr_edgeconv_fwd_blocks": (_I, [_I]),
     "pcnbr_edgeconv_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pcnbr_edgeconv_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_split_tf32": (_I, [_P, _L, _L, _P, _P, _P, _P, _P]),
+    "pcnbr_gemm3x_splits": (_I, [_I, _I, _I]),
+    "pcnbr_gemm3x_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "pcnbr_gemm3x_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "pcnbr_prof_enable": (None, [_I]),
     "pcnbr_prof_collect": (_I, [_P, _Z]),
 }

@@ -77,7 +77,7 @@ class MiniPointNet(nn.Module):
             return x
         h = rows
         for conv, bn in zip(self.conv, self.batch):
-            h = F.linear(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+            h = ops.linear_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
             h = F.relu(_batch_norm_rows(bn, h.view(-1, conv.out_channels))).view(B, C, K, conv.out_channels)
         return h.permute(0, 3, 1, 2)
 
@@ -121,7 +121,7 @@ class UnitPointNet(nn.Module):
             return x
         h = rows
         for conv, bn in zip(self.conv, self.batch):
-            h = F.linear(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
+            h = ops.linear_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
             h = F.relu(_batch_norm_rows(bn, h.view(-1, conv.out_channels))).view(B, N, conv.out_channels)
         return h.permute(0, 2, 1)
 

@@ -85,7 +85,7 @@ def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
     from .common import _batch_norm_rows
     mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
     conv = mods[0]
-    y = torch.nn.functional.linear(rows, conv.weight.squeeze(-1), conv.bias)
+    y = ops.linear_rows(rows, conv.weight.squeeze(-1), conv.bias)
     for m in mods[1:]:
         if isinstance(m, nn.modules.batchnorm._BatchNorm):
             y = _batch_norm_rows(m, y.view(-1, y.shape[-1])).view(y.shape)

@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused",
+    "edge_features", "edgeconv_fused", "linear_rows",
 ]
 
 
@@ -446,3 +446,73 @@ def edgeconv_fused(PQ: torch.Tensor, nbr: NeighborIndex, bn: torch.nn.BatchNorm2
     beta = bn.bias if bn.bias is not None else torch.zeros(O, device=PQ.device)
     return _EdgeConvFusedFn.apply(_c(PQ), nbr, gamma, beta, bn.running_mean, bn.running_var, training,
                                   0.0 if momentum is None else float(momentum), float(bn.eps), float(negative_slope))
+
+
+# ----------------------------------------------------------------------------- 1x1 convolution as a tensor-core GEMM
+
+
+def _split_tf32(x: torch.Tensor, plain: bool, transposed: bool):
+    """x (R,C) contiguous -> (hi, lo, hiT, loT): tf32 halves of x (hi + lo = x to 2^-21) and/or their transposes."""
+    R, C = x.shape
+    hi = torch.empty_like(x) if plain else None
+    lo = torch.empty_like(x) if plain else None
+    hiT = torch.empty(C, R, dtype=torch.float32, device=x.device) if transposed else None
+    loT = torch.empty(C, R, dtype=torch.float32, device=x.device) if transposed else None
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _lib.call("pcnbr_split_tf32", x.data_ptr(), R, C, ptr(hi), ptr(lo), ptr(hiT), ptr(loT), _stream())
+    return hi, lo, hiT, loT
+
+
+def _gemm3x(a_hi, a_lo, b_hi, b_lo, bias=None) -> torch.Tensor:
+    """(M,K) . (N,K)^T (+ bias) -> (M,N) on tcgen05, 3xTF32 (fp32-grade accuracy)."""
+    M, K = a_hi.shape
+    N = b_hi.shape[0]
+    splits = 1 if bias is not None else _lib.size("pcnbr_gemm3x_splits", M, N, K)
+    nb = _lib.size("pcnbr_gemm3x_ws_bytes", M, N, K, splits)
+    ws = _ws(nb, a_hi.device)
+    out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
+    _lib.call("pcnbr_gemm3x_f32", a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), M, N, K,
+              bias.data_ptr() if bias is not None else None, out.data_ptr(), splits, ws.data_ptr(), nb, _stream())
+    return out
+
+
+class _LinearRowsFn(torch.autograd.Function):
+    """y = x W^T + b over the rows of x, all three GEMMs of the layer (output, input gradient, weight gradient) on the
+    tensor cores in 3xTF32.  The operands are split once per tensor; the transposed halves make every GEMM K-major."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        xh, xl, xhT, xlT = _split_tf32(x, True, need_dw)
+        wh, wl, whT, wlT = _split_tf32(w, True, need_dx)
+        ctx.save_for_backward(xhT, xlT, whT, wlT)
+        ctx.has_bias = b is not None
+        return _gemm3x(xh, xl, wh, wl, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xhT, xlT, whT, wlT = ctx.saved_tensors
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gy = _c(gy)
+        gh, gl, ghT, glT = _split_tf32(gy, need_dx, need_dw)
+        dx = _gemm3x(gh, gl, whT, wlT) if need_dx else None                 # (R,Cout) . (Cin,Cout)^T
+        dw = _gemm3x(ghT, glT, xhT, xlT) if need_dw else None               # (Cout,R) . (Cin,R)^T, split along R
+        db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+_GEMM_LIBRARY = __import__("os").environ.get("PCNBR_GEMM_LIBRARY") is not None
+
+
+def linear_rows(rows: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+    """rows (..., Cin) @ weight (Cout, Cin)^T + bias: the 1x1 convolutions of models/utils/common.py:125-178 and
+    models/dgcnn/dgcnn.py:66-126 on point-major rows.  Wide layers (Cin >= 128, >= 4096 rows, 4-aligned sizes) run on
+    the hand-written 3xTF32 tcgen05 GEMM; narrow ones stay on the library SGEMM (PCNBR_GEMM_LIBRARY=1 forces it)."""
+    cin, cout = weight.shape[1], weight.shape[0]
+    nrows = rows.numel() // max(cin, 1)
+    ok = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
+          and cin >= 128 and cin % 4 == 0 and cout % 4 == 0 and cout >= 64 and nrows >= 4096 and nrows % 4 == 0)
+    if not ok:
+        return torch.nn.functional.linear(rows, weight, bias)
+    y = _LinearRowsFn.apply(_c(rows).view(nrows, cin), _c(weight), bias)
+    return y.view(*rows.shape[:-1], cout)

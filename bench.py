@@ -178,7 +178,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------- our arm
 
 
-TENSOR_KERNELS = {"knn_tc_kernel"}          # tcgen05 kernels: roofline = tensor pipe (TF32); everything else moves bytes
+TENSOR_KERNELS = {"knn_tc_kernel", "gemm3x_kernel"}          # tcgen05 kernels: roofline = tensor pipe (TF32); everything else moves bytes
 
 
 def ncu_traffic(kernel):

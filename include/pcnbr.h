@@ -147,6 +147,23 @@ PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const 
                            const int32_t* offsets, const int32_t* perm, const float* coef, int B, int N, int K,
                            int O, float* dPQ, pcnbr_stream_t stream);
 
+/* ---- fp32-accurate tensor-core GEMM for the 1x1 convolutions ---- common.py:125-178, dgcnn.py:66-126
+ * Not a reference entry point: the reference's Conv1d/Conv2d(kernel 1) are library GEMMs; under the fp32 parity bar
+ * they run as SIMT SGEMMs.  Here C (M,N) = A (M,K) . B (N,K)^T (+ bias (N)) runs as 3xTF32 on tcgen05 (hi.hi' + lo.hi' +
+ * hi.lo', fp32 accumulation in TMEM; error ~2^-21 |a||b|).
+ * pcnbr_split_tf32: x (R,C) row-major -> hi = tf32(x), lo = tf32(x - hi), (R,C) each (NULL to skip), and/or their
+ *   transposes hiT, loT (C,R) (NULL to skip) -- so that every GEMM of a layer (output, input gradient, weight gradient)
+ *   is K-major.
+ * pcnbr_gemm3x_f32: all four operands 16-byte aligned, K % 4 == 0.  splits > 1 (from pcnbr_gemm3x_splits; weight
+ *   gradients, where M and N are small and K is the number of points) cuts K over the CTAs; the partial tiles go to
+ *   ws (pcnbr_gemm3x_ws_bytes) and are summed in a fixed order: deterministic, no atomics; bias must be NULL then. */
+PCNBR_API int pcnbr_split_tf32(const float* x, long R, long C, float* hi, float* lo, float* hiT, float* loT,
+                     pcnbr_stream_t stream);
+PCNBR_API int pcnbr_gemm3x_splits(int M, int N, int K);
+PCNBR_API size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits);
+PCNBR_API int pcnbr_gemm3x_f32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int M, int N,
+                     int K, const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
 /* ---- measurement hook (bench.py roofline, kernel sweep) -- not part of the reference interface
  * pcnbr_prof_enable(1): bracket every kernel this library launches with CUDA events on its launch stream and
  * remember the launch's ALGORITHMIC bytes / flops.  Must be off while a CUDA graph is captured.
