@@ -125,7 +125,8 @@ __device__ __forceinline__ uint64_t gm_desc(uint32_t saddr) {
     return lo | (hi << 32);
 }
 
-// Work unit = (split, n tile, m tile), m fastest.  C tile goes to out + split * M * ldc (partials) -- splits == 1
+// Work unit = (split, m tile, n tile), n fastest: the CTAs that run side by side share the same A slab, so the
+// streamed operand (the activations) is read from HBM once and hits L2 for the other n tiles.  C tile goes to out + split * M * ldc (partials) -- splits == 1
 // writes the result (plus bias) directly.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 1)
@@ -172,7 +173,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-                const int mt = unit % MT, nt = (unit / MT) % NT, sp = unit / (MT * NT);
+                const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
                 const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     gm_mbar_wait(&empty[stage], phase ^ 1);
@@ -229,7 +230,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
         uint32_t tile = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
-            const int mt = unit % MT, nt = (unit / MT) % NT, sp = unit / (MT * NT);
+            const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
             const uint32_t buf = tile & 1, tphase = (tile >> 1) & 1;
             const long row = (long)mt * GM_BM + quarter * 32 + lane;
             float* __restrict__ dst = out + ((long)sp * M + row) * ldc + (long)nt * BN;
@@ -352,17 +353,25 @@ extern "C" int pcnbr_split_tf32(const float* x, long R, long C, float* hi, float
 }
 
 extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
-    // split K when the output has too few tiles to fill the chip (weight gradients: K = number of points)
+    // Split K when the output has too few tiles to fill the chip (weight gradients: K = number of points).
+    // Cost model: waves of work units over the SMs x K blocks per unit; the smallest split count that minimises it.
     const int bn = (N > 128) ? 256 : 128;
     const long tiles = (long)((M + GM_BM - 1) / GM_BM) * ((N + bn - 1) / bn);
     const int kb = (K + GM_BK - 1) / GM_BK;
-    if (tiles >= 74 || kb < 64) return 1;
-    long s = (148 + tiles - 1) / tiles;
-    if (s > kb / 16) s = kb / 16;
-    if (s > 32) s = 32;
-    if (s < 1) s = 1;
-    const long per = (kb + s - 1) / s;                                    // every split owns at least one K block
-    return (int)((kb + per - 1) / per);
+    if (tiles >= 148 || kb < 64) return 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long best_cost = -1;
+    int best = 1;
+    for (int s = 1; s <= 32 && s <= kb / 16; ++s) {
+        const long per = (kb + s - 1) / s;
+        const long eff = (kb + per - 1) / per;                            // every split owns at least one K block
+        const long waves = (tiles * eff + sms - 1) / sms;
+        const long cost = waves * (per + 4);                              // + tile prologue / epilogue
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = (int)eff; }
+    }
+    return best;
 }
 
 extern "C" size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits) {
