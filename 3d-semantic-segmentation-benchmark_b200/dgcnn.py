@@ -72,7 +72,7 @@ class EdgeConv(nn.Module):
         nbr = ops.NeighborIndex(ops.knn_graph(x, self.k), N)
         W = conv.weight.view(O, 2 * F)
         Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
-        PQ = torch.matmul(_point_major(x), Wcat.t())                        # library GEMM (B,N,F) x (F,2O)
+        PQ = ops.linear_rows(_point_major(x), Wcat, None)                   # (B,N,F) x (F,2O): tensor-core GEMM / split-K wgrad
         out = ops.edgeconv_fused(PQ, nbr, bn, act.negative_slope)           # (B,N,O), point-major
         return out.permute(0, 2, 1)                                         # (B,O,N) view, no copy
 

@@ -501,18 +501,51 @@ class _LinearRowsFn(torch.autograd.Function):
         return dx, dw, db
 
 
+class _LinearRowsWgradFn(torch.autograd.Function):
+    """Narrow layers (Cin or Cout too small / unaligned for the K dimension of a tensor-core tile): output and input
+    gradient stay on the library SGEMM, but the WEIGHT gradient -- a (Cout,Cin) output contracted over all the points,
+    which the library runs on one or two CTAs (150-400 us per layer) -- goes through the split-K 3xTF32 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _c(gy)
+        dx = gy.matmul(w) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            _, _, ghT, glT = _split_tf32(gy, False, True)
+            _, _, xhT, xlT = _split_tf32(x, False, True)
+            dw = _gemm3x(ghT, glT, xhT, xlT)                                # (Cout,R) . (Cin,R)^T, split along R
+        db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
 _GEMM_LIBRARY = __import__("os").environ.get("PCNBR_GEMM_LIBRARY") is not None
 
 
 def linear_rows(rows: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
     """rows (..., Cin) @ weight (Cout, Cin)^T + bias: the 1x1 convolutions of models/utils/common.py:125-178 and
-    models/dgcnn/dgcnn.py:66-126 on point-major rows.  Wide layers (Cin >= 128, >= 4096 rows, 4-aligned sizes) run on
-    the hand-written 3xTF32 tcgen05 GEMM; narrow ones stay on the library SGEMM (PCNBR_GEMM_LIBRARY=1 forces it)."""
+    models/dgcnn/dgcnn.py:66-126 on point-major rows.  Layers with Cin, Cout >= 64 (4-aligned, >= 4096 rows) run all
+    three GEMMs on the hand-written 3xTF32 tcgen05 kernel; narrower ones keep the library SGEMM for the output and the
+    input gradient and use the split-K tensor-core GEMM for the weight gradient only (PCNBR_GEMM_LIBRARY=1 forces
+    the library everywhere)."""
     cin, cout = weight.shape[1], weight.shape[0]
     nrows = rows.numel() // max(cin, 1)
-    ok = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
-          and cin >= 128 and cin % 4 == 0 and cout % 4 == 0 and cout >= 64 and nrows >= 4096 and nrows % 4 == 0)
-    if not ok:
+    usable = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
+              and nrows >= 4096 and nrows % 4 == 0)
+    if not usable:
         return torch.nn.functional.linear(rows, weight, bias)
-    y = _LinearRowsFn.apply(_c(rows).view(nrows, cin), _c(weight), bias)
+    x2 = _c(rows).view(nrows, cin)
+    if cin >= 64 and cin % 4 == 0 and cout % 4 == 0 and cout >= 64:
+        y = _LinearRowsFn.apply(x2, _c(weight), bias)
+    elif nrows >= 16384 and torch.is_grad_enabled() and weight.requires_grad:
+        y = _LinearRowsWgradFn.apply(x2, _c(weight), bias)
+    else:
+        return torch.nn.functional.linear(rows, weight, bias)
     return y.view(*rows.shape[:-1], cout)
