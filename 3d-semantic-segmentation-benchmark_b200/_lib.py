@@ -8,13 +8,13 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_long, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libpcnbr.so")
 ABI_VERSION = 1
 
-_P, _I, _L, _F, _Z = c_void_p, c_int, c_long, c_float, c_size_t
+_P, _I, _L, _F, _Z, _D = c_void_p, c_int, c_long, c_float, c_size_t, c_double
 
 # name -> (restype, argtypes): mirrors include/pcnbr.h one to one
 PROTOTYPES = {
@@ -40,10 +40,17 @@ PROTOTYPES = {
     "pcnbr_edgeconv_fwd_blocks": (_I, [_I]),
     "pcnbr_edgeconv_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pcnbr_edgeconv_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "pcnbr_split_tf32": (_I, [_P, _L, _L, _P, _P, _P, _P, _P]),
+    "pcnbr_bn_supported": (_I, [_L, _I]),
+    "pcnbr_bn_blocks": (_I, [_L, _I]),
+    "pcnbr_bn_stats_f32": (_I, [_P, _L, _I, _P, _P]),
+    "pcnbr_bn_finalize_f32": (_I, [_P, _I, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P]),
+    "pcnbr_bn_act_fwd_f32": (_I, [_P, _L, _P, _L, _L, _I, _P, _F, _P, _P]),
+    "pcnbr_bn_act_bwd_reduce_f32": (_I, [_P, _P, _L, _P, _L, _L, _I, _P, _F, _P, _P, _P]),
+    "pcnbr_bn_bwd_finalize_f32": (_I, [_P, _I, _P, _D, _I, _I, _P, _P, _P, _P]),
+    "pcnbr_bn_act_bwd_apply_f32": (_I, [_P, _P, _L, _I, _P, _P, _F, _P, _P]),
     "pcnbr_gemm3x_splits": (_I, [_I, _I, _I]),
     "pcnbr_gemm3x_ws_bytes": (_Z, [_I, _I, _I, _I]),
-    "pcnbr_gemm3x_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
+    "pcnbr_gemm3x_f32": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "pcnbr_prof_enable": (None, [_I]),
     "pcnbr_prof_collect": (_I, [_P, _Z]),
 }

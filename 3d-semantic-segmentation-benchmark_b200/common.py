@@ -78,7 +78,7 @@ class MiniPointNet(nn.Module):
         h = rows
         for conv, bn in zip(self.conv, self.batch):
             h = ops.linear_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
-            h = F.relu(_batch_norm_rows(bn, h.view(-1, conv.out_channels))).view(B, C, K, conv.out_channels)
+            h = ops.batchnorm_act_rows(h, bn, 0.0)                          # BatchNorm2d + ReLU, fused (B,C,K,Cout)
         return h.permute(0, 3, 1, 2)
 
 
@@ -122,7 +122,7 @@ class UnitPointNet(nn.Module):
         h = rows
         for conv, bn in zip(self.conv, self.batch):
             h = ops.linear_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
-            h = F.relu(_batch_norm_rows(bn, h.view(-1, conv.out_channels))).view(B, N, conv.out_channels)
+            h = ops.batchnorm_act_rows(h, bn, 0.0)                          # BatchNorm1d + ReLU, fused (B,N,Cout)
         return h.permute(0, 2, 1)
 
 

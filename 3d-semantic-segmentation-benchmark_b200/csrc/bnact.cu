@@ -1,0 +1,416 @@
+// bnact.cu -- BatchNorm (training or eval) + LeakyReLU/ReLU over the rows of a (R, C) point-major matrix,
+// forward and backward, in the minimum number of passes over HBM.
+//
+// Reference: every "Conv -> BatchNorm -> ReLU" of models/utils/common.py:125-178 (MiniPointNet / UnitPointNet) and
+// "Conv -> BatchNorm -> LeakyReLU(0.2)" of models/dgcnn/dgcnn.py:66-71,95-126.  The reference runs them as three
+// library ops per direction (statistics, normalise, activation; activation', reduce, input gradient): 6 passes
+// over the activation tensor forward and 8 backward.  Here:
+//   forward : bn_stats_kernel (1 read)  -> bn_finalize_kernel (tiny) -> bn_act_fwd_kernel (1 read, 1 write)
+//   backward: bn_act_bwd_reduce_kernel (2 reads) -> bn_bwd_finalize_kernel (tiny) -> bn_act_bwd_apply_kernel (2 reads, 1 write)
+// The activation output is never needed by the backward: its sign is recomputed from the saved pre-BatchNorm rows.
+// The row source may be the sum of two strided matrices (x = a[r*lda + c] + b[r*ldb + c]): the fused EdgeConv path
+// (edgeconv.cu) normalises psel + Q without materialising it, and takes its statistics partials from its own
+// gather kernel.  Statistics: per-block sums of (x - shift) and (x - shift)^2 about a per-channel shift (row 0),
+// combined over the blocks in fp64 in a fixed order -- deterministic, no atomics.
+//
+// Thread mapping: C % 4 == 0 and CV = C/4 a power of two <= 512.  A thread owns max(1, CV/256) float4 columns and
+// walks rows; consecutive threads read consecutive 16-byte words, so every warp request is a full 512-byte span.
+#include "common.cuh"
+
+namespace pcnbr {
+
+constexpr int BA_T = 256;
+
+struct BaMap {
+    int cvb;    // float4 columns covered by one sweep of the block (min(CV, 256))
+    int ncol;   // float4 columns per thread (1 or 2)
+    int ty;     // row lane of this thread
+    int TY;     // rows per sweep
+    int col;    // first float (not float4) column of this thread
+};
+__device__ __forceinline__ BaMap ba_map(int C) {
+    BaMap m;
+    const int CV = C >> 2;
+    m.cvb = CV < BA_T ? CV : BA_T;
+    m.ncol = CV > BA_T ? CV / BA_T : 1;
+    m.ty = threadIdx.x / m.cvb;
+    m.TY = BA_T / m.cvb;
+    m.col = (threadIdx.x % m.cvb) * 4;
+    return m;
+}
+__device__ __forceinline__ float4 ba_ld(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb, long r, int c) {
+    float4 v = *reinterpret_cast<const float4*>(a + r * lda + c);
+    if (b) {
+        const float4 w = *reinterpret_cast<const float4*>(b + r * ldb + c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    return v;
+}
+
+// block tree reduction over the row lanes of (s1, s2) per column, result written by row lane 0 to partial[blk][2][C]
+template <int NCOL>
+__device__ __forceinline__ void ba_block_reduce(const BaMap& m, float4 (&s1)[NCOL], float4 (&s2)[NCOL], int C, float* __restrict__ partial) {
+    __shared__ float4 red[2 * BA_T];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        red[threadIdx.x] = s1[j];
+        red[BA_T + threadIdx.x] = s2[j];
+        __syncthreads();
+        for (int s = m.TY >> 1; s > 0; s >>= 1) {
+            if (m.ty < s) {
+                const float4 u = red[threadIdx.x + s * m.cvb], w = red[BA_T + threadIdx.x + s * m.cvb];
+                float4& p = red[threadIdx.x];
+                float4& q = red[BA_T + threadIdx.x];
+                p.x += u.x; p.y += u.y; p.z += u.z; p.w += u.w;
+                q.x += w.x; q.y += w.y; q.z += w.z; q.w += w.w;
+            }
+            __syncthreads();
+        }
+        if (m.ty == 0) {
+            float* dst = partial + (size_t)blockIdx.x * 2 * C + m.col + j * 4 * BA_T;
+            *reinterpret_cast<float4*>(dst) = red[threadIdx.x];
+            *reinterpret_cast<float4*>(dst + C) = red[BA_T + threadIdx.x];
+        }
+        __syncthreads();
+    }
+}
+
+// partial[blk] = { sum_r (x - shift), sum_r (x - shift)^2 } over the block's rows; shift = row 0 of x.
+template <int NCOL>
+__global__ void __launch_bounds__(BA_T)
+bn_stats_kernel(const float* __restrict__ x, long R, int C, int rows_per_block, float* __restrict__ partial) {
+    const BaMap m = ba_map(C);
+    float4 sh[NCOL], s1[NCOL], s2[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        sh[j] = *reinterpret_cast<const float4*>(x + m.col + j * 4 * BA_T);
+        s1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s2[j] = s1[j];
+    }
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+#pragma unroll 4
+    for (long r = r0 + m.ty; r < r1; r += m.TY) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(x + r * C + m.col + j * 4 * BA_T);
+            const float dx = v.x - sh[j].x, dy = v.y - sh[j].y, dz = v.z - sh[j].z, dw = v.w - sh[j].w;
+            s1[j].x += dx; s1[j].y += dy; s1[j].z += dz; s1[j].w += dw;
+            s2[j].x = fmaf(dx, dx, s2[j].x); s2[j].y = fmaf(dy, dy, s2[j].y);
+            s2[j].z = fmaf(dz, dz, s2[j].z); s2[j].w = fmaf(dw, dw, s2[j].w);
+        }
+    }
+    ba_block_reduce<NCOL>(m, s1, s2, C, partial);
+}
+
+// Combine the block partials (fp64, ascending block order) into the BatchNorm constants
+//   stats (4,C) = { mean, rstd, gamma*rstd, beta }      and update the running statistics (momentum, unbiased variance).
+// nblk == 0: eval mode, mean/var come from running_mean / running_var.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ shift, double count, int C,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ stats) {
+    __shared__ double a1[8][32], a2[8][32];
+    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        const int per = (nblk + 7) / 8;
+        const int b0 = sy * per, b1 = min(nblk, b0 + per);
+#pragma unroll 4
+        for (int b = b0; b < b1; ++b) {
+            s1 += (double)partial[(size_t)b * 2 * C + c];
+            s2 += (double)partial[(size_t)b * 2 * C + C + c];
+        }
+    }
+    a1[sy][cx] = s1; a2[sy][cx] = s2;
+    __syncthreads();
+    if (sy != 0 || c >= C) return;
+    for (int k = 1; k < 8; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
+    double mean, var;
+    if (nblk > 0) {
+        const double m1 = s1 / count;
+        mean = (double)shift[c] + m1;
+        var = s2 / count - m1 * m1;
+        if (var < 0.0) var = 0.0;
+        if (running_mean) {
+            const double unb = count > 1.0 ? var * (count / (count - 1.0)) : var;
+            running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+            running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unb);
+        }
+    } else {
+        mean = (double)running_mean[c];
+        var = (double)running_var[c];
+    }
+    const float meanf = (float)mean;
+    const float rstd = (float)(1.0 / sqrt((double)(float)var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f;
+    stats[c] = meanf;
+    stats[C + c] = rstd;
+    stats[2 * C + c] = g * rstd;
+    stats[3 * C + c] = beta ? beta[c] : 0.f;
+}
+
+__device__ __forceinline__ float ba_act(float x, float mean, float scale, float beta, float slope) {
+    const float y = fmaf(x - mean, scale, beta);
+    return y > 0.f ? y : y * slope;
+}
+
+// y[r, c] = act((x[r, c] - mean) * gamma * rstd + beta)
+template <int NCOL>
+__global__ void __launch_bounds__(BA_T)
+bn_act_fwd_kernel(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb, long R, int C,
+                  const float* __restrict__ stats, float slope, float* __restrict__ y) {
+    const BaMap m = ba_map(C);
+    float4 mu[NCOL], sc[NCOL], be[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        const int c = m.col + j * 4 * BA_T;
+        mu[j] = *reinterpret_cast<const float4*>(stats + c);
+        sc[j] = *reinterpret_cast<const float4*>(stats + 2 * C + c);
+        be[j] = *reinterpret_cast<const float4*>(stats + 3 * C + c);
+    }
+#pragma unroll 4
+    for (long r = (long)blockIdx.x * m.TY + m.ty; r < R; r += (long)gridDim.x * m.TY) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const int c = m.col + j * 4 * BA_T;
+            const float4 v = ba_ld(a, lda, b, ldb, r, c);
+            float4 o;
+            o.x = ba_act(v.x, mu[j].x, sc[j].x, be[j].x, slope);
+            o.y = ba_act(v.y, mu[j].y, sc[j].y, be[j].y, slope);
+            o.z = ba_act(v.z, mu[j].z, sc[j].z, be[j].z, slope);
+            o.w = ba_act(v.w, mu[j].w, sc[j].w, be[j].w, slope);
+            *reinterpret_cast<float4*>(y + r * C + c) = o;
+        }
+    }
+}
+
+// g' = gy * act'(pre);  partial[blk] = { sum_r g', sum_r g' * xhat };  optionally gs = g' is written out.
+template <int NCOL>
+__global__ void __launch_bounds__(BA_T)
+bn_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ a, long lda, const float* __restrict__ b,
+                         long ldb, long R, int C, int rows_per_block, const float* __restrict__ stats, float slope,
+                         float* __restrict__ partial, float* __restrict__ gs) {
+    const BaMap m = ba_map(C);
+    float4 mu[NCOL], rs[NCOL], sc[NCOL], be[NCOL], s1[NCOL], s2[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        const int c = m.col + j * 4 * BA_T;
+        mu[j] = *reinterpret_cast<const float4*>(stats + c);
+        rs[j] = *reinterpret_cast<const float4*>(stats + C + c);
+        sc[j] = *reinterpret_cast<const float4*>(stats + 2 * C + c);
+        be[j] = *reinterpret_cast<const float4*>(stats + 3 * C + c);
+        s1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s2[j] = s1[j];
+    }
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+#pragma unroll 4
+    for (long r = r0 + m.ty; r < r1; r += m.TY) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const int c = m.col + j * 4 * BA_T;
+            const float4 v = ba_ld(a, lda, b, ldb, r, c);
+            float4 g = *reinterpret_cast<const float4*>(gy + r * C + c);
+            const float dx = v.x - mu[j].x, dy = v.y - mu[j].y, dz = v.z - mu[j].z, dw = v.w - mu[j].w;
+            g.x = fmaf(dx, sc[j].x, be[j].x) > 0.f ? g.x : g.x * slope;
+            g.y = fmaf(dy, sc[j].y, be[j].y) > 0.f ? g.y : g.y * slope;
+            g.z = fmaf(dz, sc[j].z, be[j].z) > 0.f ? g.z : g.z * slope;
+            g.w = fmaf(dw, sc[j].w, be[j].w) > 0.f ? g.w : g.w * slope;
+            if (gs) *reinterpret_cast<float4*>(gs + r * C + c) = g;
+            s1[j].x += g.x; s1[j].y += g.y; s1[j].z += g.z; s1[j].w += g.w;
+            s2[j].x = fmaf(g.x, dx * rs[j].x, s2[j].x); s2[j].y = fmaf(g.y, dy * rs[j].y, s2[j].y);
+            s2[j].z = fmaf(g.z, dz * rs[j].z, s2[j].z); s2[j].w = fmaf(g.w, dw * rs[j].w, s2[j].w);
+        }
+    }
+    ba_block_reduce<NCOL>(m, s1, s2, C, partial);
+}
+
+// dbeta = sum g', dgamma = sum g' xhat (fp64 over the blocks, fixed order);
+// coef (4,C) = { gr = gamma*rstd, gr*dbeta/count, gr*rstd*dgamma/count, mean }   (the two middle rows are 0 in eval mode)
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ stats, double count, int C,
+                       int training, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+    __shared__ double a1[8][32], a2[8][32];
+    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    double s1 = 0.0, s2 = 0.0;
+    if (c < C) {
+        const int per = (nblk + 7) / 8;
+        const int b0 = sy * per, b1 = min(nblk, b0 + per);
+#pragma unroll 4
+        for (int b = b0; b < b1; ++b) {
+            s1 += (double)partial[(size_t)b * 2 * C + c];
+            s2 += (double)partial[(size_t)b * 2 * C + C + c];
+        }
+    }
+    a1[sy][cx] = s1; a2[sy][cx] = s2;
+    __syncthreads();
+    if (sy != 0 || c >= C) return;
+    for (int k = 1; k < 8; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+    const double gr = (double)stats[2 * C + c], rstd = (double)stats[C + c];
+    coef[c] = (float)gr;
+    coef[C + c] = training ? (float)(gr * s1 / count) : 0.f;
+    coef[2 * C + c] = training ? (float)(gr * rstd * s2 / count) : 0.f;
+    coef[3 * C + c] = stats[c];
+}
+
+// dx = gr g' - c1 - c2r (x - mean)
+template <int NCOL>
+__global__ void __launch_bounds__(BA_T)
+bn_act_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ x, long R, int C,
+                        const float* __restrict__ stats, const float* __restrict__ coef, float slope, float* __restrict__ dx) {
+    const BaMap m = ba_map(C);
+    float4 mu[NCOL], sc[NCOL], be[NCOL], gr[NCOL], c1[NCOL], c2[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+        const int c = m.col + j * 4 * BA_T;
+        mu[j] = *reinterpret_cast<const float4*>(stats + c);
+        sc[j] = *reinterpret_cast<const float4*>(stats + 2 * C + c);
+        be[j] = *reinterpret_cast<const float4*>(stats + 3 * C + c);
+        gr[j] = *reinterpret_cast<const float4*>(coef + c);
+        c1[j] = *reinterpret_cast<const float4*>(coef + C + c);
+        c2[j] = *reinterpret_cast<const float4*>(coef + 2 * C + c);
+    }
+#pragma unroll 4
+    for (long r = (long)blockIdx.x * m.TY + m.ty; r < R; r += (long)gridDim.x * m.TY) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const int c = m.col + j * 4 * BA_T;
+            const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
+            float4 g = *reinterpret_cast<const float4*>(gy + r * C + c);
+            const float ex = v.x - mu[j].x, ey = v.y - mu[j].y, ez = v.z - mu[j].z, ew = v.w - mu[j].w;
+            g.x = fmaf(ex, sc[j].x, be[j].x) > 0.f ? g.x : g.x * slope;
+            g.y = fmaf(ey, sc[j].y, be[j].y) > 0.f ? g.y : g.y * slope;
+            g.z = fmaf(ez, sc[j].z, be[j].z) > 0.f ? g.z : g.z * slope;
+            g.w = fmaf(ew, sc[j].w, be[j].w) > 0.f ? g.w : g.w * slope;
+            float4 o;
+            o.x = fmaf(gr[j].x, g.x, -c1[j].x) - c2[j].x * ex;
+            o.y = fmaf(gr[j].y, g.y, -c1[j].y) - c2[j].y * ey;
+            o.z = fmaf(gr[j].z, g.z, -c1[j].z) - c2[j].z * ez;
+            o.w = fmaf(gr[j].w, g.w, -c1[j].w) - c2[j].w * ew;
+            *reinterpret_cast<float4*>(dx + r * C + c) = o;
+        }
+    }
+}
+
+static bool ba_supported(long R, int C) {
+    if (R <= 0 || C < 4 || C % 4) return false;
+    const int cv = C / 4;
+    return (cv & (cv - 1)) == 0 && cv <= 512;
+}
+static int ba_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+static int ba_sweep_rows(int C) { const int cv = C / 4; return cv >= BA_T ? 1 : BA_T / cv; }
+// elementwise kernels: enough CTAs for 8 per SM, never more than one sweep each
+static int ba_grid(long R, int C) {
+    const long sweeps = (R + ba_sweep_rows(C) - 1) / ba_sweep_rows(C);
+    const long cap = 8L * ba_sms();
+    return (int)(sweeps < cap ? sweeps : cap);
+}
+
+}  // namespace pcnbr
+
+using namespace pcnbr;
+
+extern "C" int pcnbr_bn_supported(long R, int C) { return ba_supported(R, C) ? 1 : 0; }
+
+// number of partial blocks the reducing kernels use for an (R, C) matrix: >= 128 KB of rows per block, <= 4 per SM
+extern "C" int pcnbr_bn_blocks(long R, int C) {
+    if (!ba_supported(R, C)) return 0;
+    const long by_bytes = (R * (long)C * 4 + 131071) / 131072;
+    const long sweeps = (R + ba_sweep_rows(C) - 1) / ba_sweep_rows(C);
+    long n = by_bytes < 4L * 148 ? by_bytes : 4L * 148;
+    if (n > sweeps) n = sweeps;
+    if (n < 1) n = 1;
+    const long rpb = (R + n - 1) / n;
+    return (int)((R + rpb - 1) / rpb);
+}
+
+extern "C" int pcnbr_bn_stats_f32(const float* x, long R, int C, float* partial, pcnbr_stream_t stream) {
+    if (!x || !partial) return PCNBR_E_BADARG;
+    if (!ba_supported(R, C) || ((uintptr_t)x & 15)) return PCNBR_E_TOOLARGE;
+    const int nblk = pcnbr_bn_blocks(R, C);
+    const int rpb = (int)((R + nblk - 1) / nblk);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double wb = 4.0 * R * C, wf = 3.0 * R * C;
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_stats_kernel", s, wb, wf, (bn_stats_kernel<2><<<nblk, BA_T, 0, s>>>(x, R, C, rpb, partial)));
+    else              PCNBR_TIMED("bn_stats_kernel", s, wb, wf, (bn_stats_kernel<1><<<nblk, BA_T, 0, s>>>(x, R, C, rpb, partial)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float* shift, double count, int C,
+                                     const float* gamma, const float* beta, float eps, float momentum,
+                                     float* running_mean, float* running_var, float* stats, pcnbr_stream_t stream) {
+    if (!stats || C <= 0 || nblk < 0) return PCNBR_E_BADARG;
+    if (nblk > 0 && (!partial || !shift || count <= 0.0)) return PCNBR_E_BADARG;
+    if (nblk == 0 && (!running_mean || !running_var)) return PCNBR_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    PCNBR_TIMED("bn_finalize_kernel", s, 8.0 * nblk * C + 32.0 * C, 4.0 * nblk * C,
+                (bn_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partial, nblk, shift, count, C, gamma, beta, eps, momentum,
+                                                                  running_mean, running_var, stats)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, long ldb, long R, int C, const float* stats,
+                                    float slope, float* y, pcnbr_stream_t stream) {
+    if (!a || !stats || !y) return PCNBR_E_BADARG;
+    if (!ba_supported(R, C) || (lda % 4) || (b && (ldb % 4)) || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y | (uintptr_t)stats) & 15))
+        return PCNBR_E_TOOLARGE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = ba_grid(R, C);
+    const double wb = 4.0 * R * C * (b ? 3.0 : 2.0), wf = 4.0 * R * C;
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<2><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y)));
+    else              PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<1><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_bn_act_bwd_reduce_f32(const float* gy, const float* a, long lda, const float* b, long ldb, long R, int C,
+                                           const float* stats, float slope, float* partial, float* gs, pcnbr_stream_t stream) {
+    if (!gy || !a || !stats || !partial) return PCNBR_E_BADARG;
+    if (!ba_supported(R, C) || (lda % 4) || (b && (ldb % 4)) ||
+        (((uintptr_t)a | (uintptr_t)b | (uintptr_t)gy | (uintptr_t)gs | (uintptr_t)stats) & 15))
+        return PCNBR_E_TOOLARGE;
+    const int nblk = pcnbr_bn_blocks(R, C);
+    const int rpb = (int)((R + nblk - 1) / nblk);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double wb = 4.0 * R * C * (2.0 + (b ? 1.0 : 0.0) + (gs ? 1.0 : 0.0)), wf = 8.0 * R * C;
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_reduce_kernel", s, wb, wf, (bn_act_bwd_reduce_kernel<2><<<nblk, BA_T, 0, s>>>(gy, a, lda, b, ldb, R, C, rpb, stats, slope, partial, gs)));
+    else              PCNBR_TIMED("bn_act_bwd_reduce_kernel", s, wb, wf, (bn_act_bwd_reduce_kernel<1><<<nblk, BA_T, 0, s>>>(gy, a, lda, b, ldb, R, C, rpb, stats, slope, partial, gs)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const float* stats, double count, int C, int training,
+                                         float* dgamma, float* dbeta, float* coef, pcnbr_stream_t stream) {
+    if (!partial || !stats || !dgamma || !dbeta || !coef || C <= 0 || nblk <= 0 || count <= 0.0) return PCNBR_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    PCNBR_TIMED("bn_bwd_finalize_kernel", s, 8.0 * nblk * C + 40.0 * C, 4.0 * nblk * C,
+                (bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partial, nblk, stats, count, C, training, dgamma, dbeta, coef)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
+                                          float slope, float* dx, pcnbr_stream_t stream) {
+    if (!gy || !x || !stats || !coef || !dx) return PCNBR_E_BADARG;
+    if (!ba_supported(R, C) || (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)dx | (uintptr_t)stats | (uintptr_t)coef) & 15))
+        return PCNBR_E_TOOLARGE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = ba_grid(R, C);
+    const double wb = 12.0 * R * C, wf = 8.0 * R * C;
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<2><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx)));
+    else              PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<1><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,21 +1,25 @@
-// gemm_tc.cu -- fp32-accurate GEMM on the 5th-generation tensor cores (3xTF32), for the 1x1 convolutions that
-// sit between the neighbourhood kernels.
+// gemm_tc.cu -- fp32-accurate GEMM on the 5th-generation tensor cores (3xTF32) straight from the fp32 operands,
+// for the 1x1 convolutions that sit between the neighbourhood kernels.
 //
 // Reference: every Conv1d/Conv2d with kernel size 1 in models/utils/common.py:125-178 and
 // models/dgcnn/dgcnn.py:66-71,95-126 is a GEMM over the (points, channels) matrix.  Under the parity bar (fp32,
-// 1e-4 relative; TF32 is off) the library runs them as SIMT SGEMMs at ~55 TFLOP/s, which is 60 % of a DGCNN train
-// step.  Here   C[M,N] = A[M,K] . B[N,K]^T (+ bias[N])   runs as three TF32 tensor-core products of pre-split
-// operands,  hi.hi' + lo.hi' + hi.lo'  with hi = tf32(x), lo = tf32(x - hi)  (error ~2^-21 |a||b|: fp32-grade), all
-// accumulated in one fp32 TMEM accumulator:
-//
-//   split kernel  : x -> hi, lo (and, for the weight-gradient GEMM, their transposes, so every GEMM is K-major);
-//   producer warp : TMA (128-byte swizzle) of 128-row x 32-float slabs of A_hi, A_lo, B_hi, B_lo into a ring;
-//   MMA warp      : one elected lane issues tcgen05.mma kind::tf32, M=128 x N=BN x K=8, 12 per 32-wide K block,
-//                   into one of two TMEM accumulators (2 x 256 columns);
-//   4 epilogue warps: tcgen05.ld the finished tile while the next one is being multiplied, add the bias, store
-//                   full 128-byte lines.
-//   Weight gradients (M, N small, K = number of points) are split along K over the CTAs; the partial tiles are
-//   summed in a fixed order by a second kernel (deterministic, no atomics).
+// 1e-4 relative; TF32 is off) the library runs them as SIMT SGEMMs at ~55 TFLOP/s.  Here
+//     C[M,N] = A[M,K] . B[N,K]^T (+ bias[N])
+// runs as three TF32 tensor-core products  hi.hi' + lo.hi' + hi.lo'  accumulated in one fp32 TMEM accumulator
+// (error ~2^-20 |a||b|: fp32-grade).  No operand is pre-processed in HBM:
+//   * hi is the fp32 word itself: kind::tf32 reads the top 19 bits of each operand word and ignores the low 13
+//     (measured on B200, scratch/tf32_trunc_probe.py), so hi = trunc_tf32(x) costs nothing;
+//   * lo = tf32_rna(x - trunc_tf32(x)) is produced INSIDE the kernel: eight converter warps read the freshly landed
+//     TMA tile from shared memory and write the residual tile next to it (same offsets, so the 128-byte swizzle is
+//     preserved without address arithmetic), publish it to the async proxy and hand the stage to the MMA warp;
+//     the hi.hi' products are issued while the converters run;
+//   * both operands may be K-major (row-major (rows, K)) or MN-major (row-major (K, rows)): the input-gradient GEMM
+//     reads the weight as stored and the weight-gradient GEMM reads the two activation matrices as stored --
+//     no transposed copies (tcgen05 supports MN-major TF32 operands through the shared-memory descriptor).
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (tcgen05.ld, + bias, 128-byte row
+// stores) double-buffered against the next tile's MMAs, warps 6-13 converters.
+// Weight gradients (M, N small, K = number of points) are split along K over the CTAs; the partial tiles are summed
+// in a fixed order by a second kernel (deterministic, no atomics).
 #include "common.cuh"
 #include <cuda.h>
 
@@ -23,8 +27,10 @@ namespace pcnbr {
 
 constexpr int GM_BM = 128;                 // rows per tile (TMEM lanes)
 constexpr int GM_BK = 32;                  // floats per K block = one 128-byte swizzle atom
-constexpr int GM_THREADS = 192;            // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
-constexpr uint32_t GM_SLAB = 128 * 128;    // bytes: 128 rows x 128 B
+constexpr int GM_CONV_WARPS = 8;
+constexpr int GM_THREADS = 192 + 32 * GM_CONV_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6.. converters
+constexpr uint32_t GM_SLAB = 128 * 128;    // bytes of a 128 x 32-float operand tile
+constexpr uint32_t GM_CHUNK = 32 * 128;    // bytes of a 32 x 32-float MN-major chunk
 
 __device__ __forceinline__ uint32_t gm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void gm_mbar_init(uint64_t* bar, uint32_t count) {
@@ -45,15 +51,16 @@ __device__ __forceinline__ void gm_mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(gm_smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void gm_tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void gm_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(gm_smem_u32(dst)), "l"(map), "r"(gm_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+        ::"r"(dst), "l"(map), "r"(gm_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-// kind::tf32, D = fp32, A/B K-major, M = 128, N = BN (cute::UMMA::InstrDescriptor)
-template <int BN>
+// kind::tf32, D = fp32, M = 128, N = BN; A / B major-ness in bits 15 / 16 (cute::UMMA::InstrDescriptor)
+template <int BN, bool A_MN, bool B_MN>
 __device__ __forceinline__ void gm_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, bool accumulate) {
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
     const uint32_t acc = accumulate ? 1u : 0u;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -76,73 +83,52 @@ __device__ __forceinline__ void gm_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
         : "r"(taddr) : "memory");
 }
 
-// ------------------------------------------------------------------------------------ operand split
-
-// x (R,C) row-major -> hi = tf32_rna(x), lo = tf32_rna(x - hi), both (R,C); optionally the transposes (C,R).
-// 32x32 tiles through shared memory: all four outputs are written with coalesced 128-byte rows.
-__global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ x, long R, long C, float* __restrict__ hi, float* __restrict__ lo,
-                  float* __restrict__ hiT, float* __restrict__ loT) {
-    __shared__ float th[32][33], tl[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
-    const long tiles_c = (C + 31) / 32, tiles_r = (R + 31) / 32;
-    for (long t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
-        const long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long r = r0 + ty + 8 * i, c = c0 + tx;
-            float h = 0.f, l = 0.f;
-            if (r < R && c < C) {
-                const float v = x[r * C + c];
-                uint32_t hb, lb;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-                h = __uint_as_float(hb);
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(v, h)));
-                l = __uint_as_float(lb);
-                if (hi) { hi[r * C + c] = h; lo[r * C + c] = l; }
-            }
-            th[ty + 8 * i][tx] = h;
-            tl[ty + 8 * i][tx] = l;
-        }
-        if (hiT) {
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long c = c0 + ty + 8 * i, r = r0 + tx;
-                if (r < R && c < C) { hiT[c * R + r] = th[tx][ty + 8 * i]; loT[c * R + r] = tl[tx][ty + 8 * i]; }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------ main kernel
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (see knn_tc.cu)
-__device__ __forceinline__ uint64_t gm_desc(uint32_t saddr) {
+// Shared-memory matrix descriptors, descriptor version 1 (cute::UMMA::SmemDescriptor).
+//   K-major : 128-byte swizzle (16-byte units; TMA SWIZZLE_128B, layout type 2): rows of 128 B (32 floats of K),
+//             8-row groups 1024 B apart (SBO); a K step of 8 floats = +32 B.
+//   MN-major: 32-bit operands only exist in the "128B, 32-byte atom" swizzle (TMA SWIZZLE_128B_ATOM_32B, layout type 1,
+//             cute Layout_MN_SW128_32B_Atom): chunks of 32 MN-floats x 32 K-rows, 128 B per K row, the 32-byte units of
+//             a row XORed with (row & 3); 4-K-row groups 512 B apart (SBO), the next 32 MN-floats one chunk (4096 B)
+//             further (LBO); a K step of 8 = +1024 B.
+__device__ __forceinline__ uint64_t gm_desc_k(uint32_t saddr) {
     const uint64_t lo = (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16);
     const uint64_t hi = (uint64_t)(1024 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)2 << 29);
     return lo | (hi << 32);
 }
+__device__ __forceinline__ uint64_t gm_desc_mn(uint32_t saddr) {
+    const uint64_t lo = (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(GM_CHUNK >> 4) << 16);
+    const uint64_t hi = (uint64_t)(512 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)1 << 29);
+    return lo | (hi << 32);
+}
+template <bool MN> __device__ __forceinline__ uint64_t gm_desc(uint32_t saddr) { return MN ? gm_desc_mn(saddr) : gm_desc_k(saddr); }
+template <bool MN> __device__ __forceinline__ uint64_t gm_kstep(int s) { return MN ? (uint64_t)(64 * s) : (uint64_t)(2 * s); }
+
+// residual of the tensor core's truncation, rounded to tf32: lo = rna_tf32(x - (x & ~0x1fff))
+__device__ __forceinline__ float gm_residual(float v) {
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    uint32_t lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(v, h)));
+    return __uint_as_float(lb);
+}
 
 // Work unit = (split, m tile, n tile), n fastest: the CTAs that run side by side share the same A slab, so the
-// streamed operand (the activations) is read from HBM once and hits L2 for the other n tiles.  C tile goes to out + split * M * ldc (partials) -- splits == 1
-// writes the result (plus bias) directly.
-template <int BN, int STAGES>
+// streamed operand (the activations) is read from HBM once and hits L2 for the other n tiles.  The C tile goes to
+// out + split * M * ldc (partials); splits == 1 writes the result (plus bias) directly.
+template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
-              const __grid_constant__ CUtensorMap tm_bh, const __grid_constant__ CUtensorMap tm_bl,
+gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
               int M, int N, int K, int splits, const float* __restrict__ bias, float* __restrict__ out, long ldc) {
     extern __shared__ uint8_t gm_smem_raw[];
     uint8_t* smem = gm_smem_raw + ((1024u - (gm_smem_u32(gm_smem_raw) & 1023u)) & 1023u);
-    constexpr uint32_t A_BYTES = GM_SLAB, B_BYTES = (BN / 128) * GM_SLAB;
-    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;       // A_hi | A_lo | B_hi | B_lo
+    constexpr uint32_t A_BYTES = GM_SLAB, B_BYTES = (uint32_t)BN * 128u;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;       // A | A_lo | B | B_lo
     uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;                                            // [STAGES]
-    uint64_t* empty = bars + STAGES;                                  // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;                          // [2]
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2;                     // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+    uint64_t* full = bars;                                            // [STAGES]  TMA landed          (count 1 + tx)
+    uint64_t* conv = bars + STAGES;                                   // [STAGES]  residual tiles ready (count GM_CONV_WARPS)
+    uint64_t* empty = bars + 2 * STAGES;                              // [STAGES]  MMAs retired        (count 1)
+    uint64_t* tmem_full = bars + 3 * STAGES;                          // [2]
+    uint64_t* tmem_empty = bars + 3 * STAGES + 2;                     // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MT = (M + GM_BM - 1) / GM_BM, NT = (N + BN - 1) / BN;
@@ -151,11 +137,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
     const int units = MT * NT * splits;
 
     if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ah) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_al) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bh) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bl) : "memory");
-        for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&empty[i], 1); }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+        for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&conv[i], GM_CONV_WARPS); gm_mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { gm_mbar_init(&tmem_full[i], 1); gm_mbar_init(&tmem_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -177,14 +161,24 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
                 const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     gm_mbar_wait(&empty[stage], phase ^ 1);
-                    gm_mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    uint8_t* st = smem + stage * STAGE_BYTES;
-                    gm_tma_load_2d(st, &tm_ah, &full[stage], kb * GM_BK, mt * GM_BM);
-                    gm_tma_load_2d(st + A_BYTES, &tm_al, &full[stage], kb * GM_BK, mt * GM_BM);
+                    gm_mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+                    const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
+                    if (A_MN) {
 #pragma unroll
-                    for (int h = 0; h < BN / 128; ++h) {
-                        gm_tma_load_2d(st + 2 * A_BYTES + h * GM_SLAB, &tm_bh, &full[stage], kb * GM_BK, nt * BN + h * 128);
-                        gm_tma_load_2d(st + 2 * A_BYTES + B_BYTES + h * GM_SLAB, &tm_bl, &full[stage], kb * GM_BK, nt * BN + h * 128);
+                        for (int c = 0; c < GM_BM / 32; ++c)
+                            gm_tma_load_2d(st + c * GM_CHUNK, &tm_a, &full[stage], mt * GM_BM + c * 32, kb * GM_BK);
+                    } else {
+                        gm_tma_load_2d(st, &tm_a, &full[stage], kb * GM_BK, mt * GM_BM);
+                    }
+                    const uint32_t sb = st + 2 * A_BYTES;
+                    if (B_MN) {
+#pragma unroll
+                        for (int c = 0; c < BN / 32; ++c)
+                            gm_tma_load_2d(sb + c * GM_CHUNK, &tm_b, &full[stage], nt * BN + c * 32, kb * GM_BK);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < (BN + 127) / 128; ++h)
+                            gm_tma_load_2d(sb + h * GM_SLAB, &tm_b, &full[stage], kb * GM_BK, nt * BN + h * 128);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -204,18 +198,26 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + buf * 256;
             for (int kb = kb0; kb < kb1; ++kb) {
-                gm_mbar_wait(&full[stage], phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
-                const uint64_t ah = gm_desc(st), al = gm_desc(st + A_BYTES);
-                const uint64_t bh = gm_desc(st + 2 * A_BYTES), bl = gm_desc(st + 2 * A_BYTES + B_BYTES);
+                const uint64_t ah = gm_desc<A_MN>(st), al = gm_desc<A_MN>(st + A_BYTES);
+                const uint64_t bh = gm_desc<B_MN>(st + 2 * A_BYTES), bl = gm_desc<B_MN>(st + 2 * A_BYTES + B_BYTES);
+                gm_mbar_wait(&full[stage], phase);                    // raw tiles landed: hi . hi' can start
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) gm_umma_tf32<BN>(d, ah + 2 * s, bh + 2 * s, kb > kb0 || s > 0);   // hi . hi'
+                    for (int s = 0; s < 4; ++s)
+                        gm_umma_tf32<BN, A_MN, B_MN>(d, ah + gm_kstep<A_MN>(s), bh + gm_kstep<B_MN>(s), kb > kb0 || s > 0);
+                }
+                __syncwarp();
+                gm_mbar_wait(&conv[stage], phase);                    // residual tiles written and published
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (leader) {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) gm_umma_tf32<BN>(d, al + 2 * s, bh + 2 * s, true);                // lo . hi'
+                    for (int s = 0; s < 4; ++s)
+                        gm_umma_tf32<BN, A_MN, B_MN>(d, al + gm_kstep<A_MN>(s), bh + gm_kstep<B_MN>(s), true);             // lo . hi'
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) gm_umma_tf32<BN>(d, ah + 2 * s, bl + 2 * s, true);                // hi . lo'
+                    for (int s = 0; s < 4; ++s)
+                        gm_umma_tf32<BN, A_MN, B_MN>(d, ah + gm_kstep<A_MN>(s), bl + gm_kstep<B_MN>(s), true);             // hi . lo'
                     gm_umma_commit(&empty[stage]);
                 }
                 __syncwarp();
@@ -224,7 +226,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
             if (leader) gm_umma_commit(&tmem_full[buf]);
             __syncwarp();
         }
-    } else {
+    } else if (warp < 6) {
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
@@ -267,6 +269,35 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__
             __syncwarp();
             if (lane == 0) gm_mbar_arrive(&tmem_empty[buf]);
         }
+    } else {
+        // ===================================================== converters: residual tiles A_lo, B_lo from the raw tiles
+        const int t = threadIdx.x - 192;                              // 0 .. 32*GM_CONV_WARPS-1
+        constexpr int NT_CONV = 32 * GM_CONV_WARPS;
+        uint32_t stage = 0, phase = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int sp = unit / (MT * NT);
+            const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                uint8_t* st = smem + stage * STAGE_BYTES;
+                gm_mbar_wait(&full[stage], phase);
+#pragma unroll 4
+                for (int i = t; i < (int)(A_BYTES / 16); i += NT_CONV) {
+                    const float4 v = *reinterpret_cast<const float4*>(st + 16 * i);
+                    *reinterpret_cast<float4*>(st + A_BYTES + 16 * i) =
+                        make_float4(gm_residual(v.x), gm_residual(v.y), gm_residual(v.z), gm_residual(v.w));
+                }
+#pragma unroll 4
+                for (int i = t; i < (int)(B_BYTES / 16); i += NT_CONV) {
+                    const float4 v = *reinterpret_cast<const float4*>(st + 2 * A_BYTES + 16 * i);
+                    *reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES + 16 * i) =
+                        make_float4(gm_residual(v.x), gm_residual(v.y), gm_residual(v.z), gm_residual(v.w));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) gm_mbar_arrive(&conv[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -304,58 +335,61 @@ static GmEncodeFn gm_encode_fn() {
     return fn;
 }
 
-// (K, rows) fp32 matrix with leading dimension K, box = 32 floats x 128 rows, 128-byte swizzle; out of range reads as 0
-static int gm_make_map(CUtensorMap* map, const float* base, long rows, long K) {
+// fp32 matrix of `outer` rows x `inner` contiguous floats with row pitch ld (floats), box = 32 floats x box_rows,
+// swizzled for a K-major (inner = K) or MN-major (inner = M or N) UMMA operand; out-of-range elements read as 0.
+static int gm_make_map(CUtensorMap* map, const float* base, long inner, long outer, long ld, int box_rows, bool mn_major) {
     GmEncodeFn enc = gm_encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {32, 128};
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int BN, int STAGES>
-static int gm_launch(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, int M, int N,
-                     int K, int splits, const float* bias, float* out, long ldc, cudaStream_t s) {
-    const size_t smem = (size_t)STAGES * (2 * GM_SLAB + 2 * (BN / 128) * GM_SLAB) + 32 * 8 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static int gm_tile_n(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)); }
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits, const float* bias,
+                     float* out, long ldc, cudaStream_t s) {
+    const size_t smem = (size_t)STAGES * (2 * GM_SLAB + 2 * (size_t)BN * 128) + 64 * 8 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int units = ((M + GM_BM - 1) / GM_BM) * ((N + BN - 1) / BN) * splits;
     const int grid = units < sms ? units : sms;
-    // algorithmic work: 2 M N K flop counted once (the kernel issues 3x); operands + result bytes
-    PCNBR_TIMED("gemm3x_kernel", s, 4.0 * ((double)M * K * 2 + (double)N * K * 2 + (double)M * N * splits), 2.0 * M * (double)N * K,
-                (gemm3x_kernel<BN, STAGES><<<grid, GM_THREADS, smem, s>>>(ah, al, bh, bl, M, N, K, splits, bias, out, ldc)));
+    // algorithmic work: 2 M N K flop counted once (the kernel issues 3x); operands once + result bytes
+    PCNBR_TIMED("gemm3x_kernel", s, 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), 2.0 * M * (double)N * K,
+                (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, tb, M, N, K, splits, bias, out, ldc)));
     PCNBR_CHECK_LAUNCH();
     return 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int gm_dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits, const float* bias,
+                       float* out, long ldc, cudaStream_t s) {
+    switch (gm_tile_n(N)) {
+        case 256: return gm_launch<256, 2, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
+        case 128: return gm_launch<128, 3, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
+        case 64:  return gm_launch<64, 4, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
+        default:  return gm_launch<32, 5, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
+    }
 }
 
 }  // namespace pcnbr
 
 using namespace pcnbr;
 
-extern "C" int pcnbr_split_tf32(const float* x, long R, long C, float* hi, float* lo, float* hiT, float* loT,
-                                pcnbr_stream_t stream) {
-    if (!x || R <= 0 || C <= 0 || (!hi && !hiT) || (hi && !lo) || (hiT && !loT)) return PCNBR_E_BADARG;
-    const long tiles = ((R + 31) / 32) * ((C + 31) / 32);
-    const int grid = (int)(tiles < 148L * 16 ? tiles : 148L * 16);
-    cudaStream_t s = (cudaStream_t)stream;
-    PCNBR_TIMED("split_tf32_kernel", s, 4.0 * R * C * (1.0 + (hi ? 2.0 : 0.0) + (hiT ? 2.0 : 0.0)), 3.0 * R * C,
-                (split_tf32_kernel<<<grid, 256, 0, s>>>(x, R, C, hi, lo, hiT, loT)));
-    PCNBR_CHECK_LAUNCH();
-    return 0;
-}
-
 extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
     // Split K when the output has too few tiles to fill the chip (weight gradients: K = number of points).
     // Cost model: waves of work units over the SMs x K blocks per unit; the smallest split count that minimises it.
-    const int bn = (N > 128) ? 256 : 128;
+    const int bn = gm_tile_n(N);
     const long tiles = (long)((M + GM_BM - 1) / GM_BM) * ((N + bn - 1) / bn);
     const int kb = (K + GM_BK - 1) / GM_BK;
     if (tiles >= 148 || kb < 64) return 1;
@@ -364,7 +398,8 @@ extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long best_cost = -1;
     int best = 1;
-    for (int s = 1; s <= 32 && s <= kb / 16; ++s) {
+    const int smax = (int)(2L * sms / tiles) > 1 ? (int)(2L * sms / tiles) : 1;
+    for (int s = 1; s <= smax && s <= kb / 16; ++s) {
         const long per = (kb + s - 1) / s;
         const long eff = (kb + per - 1) / per;                            // every split owns at least one K block
         const long waves = (tiles * eff + sms - 1) / sms;
@@ -379,12 +414,11 @@ extern "C" size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits) {
     return splits > 1 ? sizeof(float) * (size_t)splits * (size_t)M * (size_t)N : 0;
 }
 
-extern "C" int pcnbr_gemm3x_f32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int M, int N,
-                                int K, const float* bias, float* C, int splits, void* ws, size_t ws_bytes,
-                                pcnbr_stream_t stream) {
-    if (!a_hi || !a_lo || !b_hi || !b_lo || !C || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
-    if (K % 4 != 0) return PCNBR_E_TOOLARGE;                              // TMA needs 16-byte row pitch
-    if (((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) & 15) return PCNBR_E_BADARG;
+extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, int M, int N, int K,
+                                const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
+    if ((lda % 4) || (ldb % 4) || (((uintptr_t)A | (uintptr_t)B) & 15)) return PCNBR_E_BADARG;    // TMA: 16-byte pitch and base
+    if (lda < (a_mn ? M : K) || ldb < (b_mn ? N : K)) return PCNBR_E_BADARG;
     if (splits > 1 && (!ws || ws_bytes < pcnbr_gemm3x_ws_bytes(M, N, K, splits))) return PCNBR_E_WORKSPACE;
     if (splits > 1 && bias) return PCNBR_E_BADARG;                        // bias with split-K is not supported
     {
@@ -392,16 +426,15 @@ extern "C" int pcnbr_gemm3x_f32(const float* a_hi, const float* a_lo, const floa
         if ((kb + per - 1) / per != splits) return PCNBR_E_BADARG;        // use pcnbr_gemm3x_splits(): no empty split
     }
     cudaStream_t s = (cudaStream_t)stream;
-    CUtensorMap ah, al, bh, bl;
-    int rc = gm_make_map(&ah, a_hi, M, K);
-    if (!rc) rc = gm_make_map(&al, a_lo, M, K);
-    if (!rc) rc = gm_make_map(&bh, b_hi, N, K);
-    if (!rc) rc = gm_make_map(&bl, b_lo, N, K);
+    const int bn = gm_tile_n(N);
+    CUtensorMap ta, tb;
+    int rc = a_mn ? gm_make_map(&ta, A, M, K, lda, 32, true) : gm_make_map(&ta, A, K, M, lda, 128, false);
+    if (!rc) rc = b_mn ? gm_make_map(&tb, B, N, K, ldb, 32, true) : gm_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128, false);
     if (rc) return rc;
     float* out = splits > 1 ? (float*)ws : C;
     const float* b = splits > 1 ? nullptr : bias;
-    if (N > 128) rc = gm_launch<256, 2>(ah, al, bh, bl, M, N, K, splits, b, out, N, s);
-    else         rc = gm_launch<128, 3>(ah, al, bh, bl, M, N, K, splits, b, out, N, s);
+    if (a_mn) rc = b_mn ? gm_dispatch<true, true>(ta, tb, M, N, K, splits, b, out, N, s) : gm_dispatch<true, false>(ta, tb, M, N, K, splits, b, out, N, s);
+    else      rc = b_mn ? gm_dispatch<false, true>(ta, tb, M, N, K, splits, b, out, N, s) : gm_dispatch<false, false>(ta, tb, M, N, K, splits, b, out, N, s);
     if (rc) return rc;
     if (splits > 1) {
         const long n = (long)M * N;

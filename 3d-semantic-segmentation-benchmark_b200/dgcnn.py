@@ -79,18 +79,25 @@ class EdgeConv(nn.Module):
 
 def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
     """seq = [Conv1d(kernel 1), BatchNorm1d, LeakyReLU(, Dropout)] applied to point-major rows (B,N,Cin) -> (B,N,Cout).
-    A 1x1 convolution IS a GEMM: it is issued as ONE cuBLAS SGEMM over the B*N rows (no transposes, no per-batch
-    GEMMs) instead of cuDNN's fp32 convolution engines, which on B200 pick FFT / implicit-GEMM kernels 3-5x slower
-    for these shapes.  BatchNorm1d sees the same rows (identical statistics).  Same parameters, same math."""
+    A 1x1 convolution IS a GEMM: it is issued as ONE GEMM over the B*N rows (no transposes, no per-batch GEMMs) instead
+    of cuDNN's fp32 convolution engines; BatchNorm1d + LeakyReLU run as the fused row kernels over the same rows
+    (identical statistics).  Same parameters, same math."""
     from .common import _batch_norm_rows
     mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
     conv = mods[0]
     y = ops.linear_rows(rows, conv.weight.squeeze(-1), conv.bias)
-    for m in mods[1:]:
+    i = 1
+    while i < len(mods):
+        m = mods[i]
         if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
+                y = ops.batchnorm_act_rows(y, m, mods[i + 1].negative_slope)
+                i += 2
+                continue
             y = _batch_norm_rows(m, y.view(-1, y.shape[-1])).view(y.shape)
         else:
             y = m(y)
+        i += 1
     return y
 
 

@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused", "linear_rows",
+    "edge_features", "edgeconv_fused", "linear_rows", "batchnorm_act_rows",
 ]
 
 
@@ -388,38 +388,35 @@ class _EdgeConvFusedFn(torch.autograd.Function):
                   B, N, K, O, psel.data_ptr(), arg.data_ptr(), s1.data_ptr(), partial.data_ptr(), _stream())
         M = B * N * K
         if training:
-            tot = partial.double().sum(dim=0)
-            m1 = tot[:O] / M
-            mean64 = shift.double() + m1
-            var64 = (tot[O:] / M - m1 * m1).clamp_min(0.0)                # biased, as BatchNorm normalises with
-            mean, var = mean64.float(), var64.float()
-            if running_mean is not None:
-                with torch.no_grad():
-                    running_mean.mul_(1.0 - momentum).add_(mean, alpha=momentum)
-                    running_var.mul_(1.0 - momentum).add_((var64 * (M / max(M - 1, 1))).float(), alpha=momentum)
+            stats = _bn_finalize(partial, B * nblk, shift, M, O, gamma, beta, eps, momentum, running_mean, running_var, dev)
         else:
-            mean, var = running_mean, running_var
-        rstd = torch.rsqrt(var.double() + eps).float()
-        Q = PQ[..., O:]
-        y = (psel + Q - mean) * (gamma * rstd) + beta
-        out = torch.nn.functional.leaky_relu(y, slope)
+            stats = _bn_finalize(None, 0, None, M, O, gamma, beta, eps, 0.0, running_mean, running_var, dev)
+        out = torch.empty(B, N, O, dtype=torch.float32, device=dev)
+        # out = LeakyReLU(BatchNorm(psel + Q)): the two-source form of the fused row kernel, Q read in place from PQ
+        _lib.call("pcnbr_bn_act_fwd_f32", psel.data_ptr(), O, PQ.data_ptr() + 4 * O, 2 * O, B * N, O, stats.data_ptr(),
+                  float(slope), out.data_ptr(), _stream())
         ctx.nbr, ctx.consts = nbr, (B, N, O, K, M, bool(training), float(slope))
-        ctx.save_for_backward(PQ, psel, arg, s1, out, mean, rstd, gamma)
+        ctx.save_for_backward(PQ, psel, arg, s1, stats)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        PQ, psel, arg, s1, out, mean, rstd, gamma = ctx.saved_tensors
+        PQ, psel, arg, s1, stats = ctx.saved_tensors
         B, N, O, K, M, training, slope = ctx.consts
-        P, Q = PQ[..., :O], PQ[..., O:]
-        gs = (g * torch.where(out > 0, 1.0, slope)).contiguous()          # dL/dy on the selected edge
-        yhat = (psel + Q - mean) * rstd
-        dbeta = gs.sum(dim=(0, 1))
-        dgamma = (gs * yhat).sum(dim=(0, 1))
-        gr = gamma * rstd
-        zero = torch.zeros_like(gr)
-        coef = torch.stack((gr, gr * dbeta / M if training else zero, gr * dgamma / M * rstd if training else zero,
-                            mean.to(torch.float32))).contiguous()
+        dev = PQ.device
+        g = _c(g)
+        R = B * N
+        # gs = dL/dy on the selected edge, dbeta = sum gs, dgamma = sum gs * yhat: one pass
+        gs = torch.empty(B, N, O, dtype=torch.float32, device=dev)
+        nblk = _lib.size("pcnbr_bn_blocks", R, O)
+        partial = torch.empty(nblk, 2, O, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_act_bwd_reduce_f32", g.data_ptr(), psel.data_ptr(), O, PQ.data_ptr() + 4 * O, 2 * O, R, O,
+                  stats.data_ptr(), slope, partial.data_ptr(), gs.data_ptr(), _stream())
+        dgamma = torch.empty(O, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(O, dtype=torch.float32, device=dev)
+        coef = torch.empty(4, O, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(M), O, int(training),
+                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
         offsets, perm = ctx.nbr.csr()
         dPQ = torch.empty_like(PQ)
         _lib.call("pcnbr_edgeconv_bwd_f32", gs.data_ptr(), arg.data_ptr(), PQ.data_ptr(), s1.data_ptr(),
@@ -448,80 +445,126 @@ def edgeconv_fused(PQ: torch.Tensor, nbr: NeighborIndex, bn: torch.nn.BatchNorm2
                                   0.0 if momentum is None else float(momentum), float(bn.eps), float(negative_slope))
 
 
+# ----------------------------------------------------------------------------- fused BatchNorm + (Leaky)ReLU on rows
+
+
+def _bn_mode(bn):
+    """nn.BatchNorm bookkeeping exactly as the module's own forward: -> (training, momentum, running_mean, running_var)."""
+    training = bn.training or bn.running_mean is None
+    momentum = bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        with torch.no_grad():
+            bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    use_running = (not training) or bn.track_running_stats
+    return (training, 0.0 if momentum is None else float(momentum),
+            bn.running_mean if use_running else None, bn.running_var if use_running else None)
+
+
+def _bn_finalize(partial, nblk, shift, count, C, gamma, beta, eps, momentum, rm, rv, dev):
+    stats = torch.empty(4, C, dtype=torch.float32, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _lib.call("pcnbr_bn_finalize_f32", ptr(partial), nblk, ptr(shift), float(count), C, ptr(gamma), ptr(beta), float(eps),
+              float(momentum), ptr(rm), ptr(rv), stats.data_ptr(), _stream())
+    return stats
+
+
+class _BnActRowsFn(torch.autograd.Function):
+    """y = act(BatchNorm(x)) over the rows of x (R,C): 1 read for the statistics, 1 read + 1 write to apply; the
+    backward needs x and gy only (2 reads to reduce, 2 reads + 1 write for dx)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rm, rv, training, momentum, eps, slope):
+        R, C = x.shape
+        dev = x.device
+        if training:
+            nblk = _lib.size("pcnbr_bn_blocks", R, C)
+            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+            _lib.call("pcnbr_bn_stats_f32", x.data_ptr(), R, C, partial.data_ptr(), _stream())
+            stats = _bn_finalize(partial, nblk, x, R, C, gamma, beta, eps, momentum, rm, rv, dev)
+        else:
+            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        y = torch.empty_like(x)
+        _lib.call("pcnbr_bn_act_fwd_f32", x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), _stream())
+        ctx.save_for_backward(x, stats)
+        ctx.consts = (bool(training), float(slope), gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, stats = ctx.saved_tensors
+        training, slope, has_gamma, has_beta = ctx.consts
+        R, C = x.shape
+        dev = x.device
+        gy = _c(gy)
+        nblk = _lib.size("pcnbr_bn_blocks", R, C)
+        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
+                  partial.data_ptr(), None, _stream())
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        coef = torch.empty(4, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
+                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), x.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
+                      dx.data_ptr(), _stream())
+        return dx, (dgamma if has_gamma else None), (dbeta if has_beta else None), None, None, None, None, None, None
+
+
+def batchnorm_act_rows(rows: torch.Tensor, bn, negative_slope: float) -> torch.Tensor:
+    """act(bn(rows)) for a (..., C) point-major tensor: nn.BatchNorm1d/2d (training or eval, running statistics and
+    num_batches_tracked updated like the module) followed by ReLU (negative_slope 0, models/utils/common.py:146,175) or
+    LeakyReLU (models/dgcnn/dgcnn.py:69) in fused kernels.  Channel counts the kernels do not cover (C/4 not a power of
+    two) go through the library ops."""
+    C = rows.shape[-1]
+    R = rows.numel() // max(C, 1)
+    training, momentum, rm, rv = _bn_mode(bn)
+    if not (rows.is_cuda and rows.dtype == torch.float32 and _lib.size("pcnbr_bn_supported", R, C)):
+        y = torch.nn.functional.batch_norm(rows.reshape(R, C), rm, rv, bn.weight, bn.bias, training, momentum, bn.eps)
+        return torch.nn.functional.leaky_relu(y, negative_slope).view(rows.shape)
+    y = _BnActRowsFn.apply(_c(rows).view(R, C), bn.weight, bn.bias, rm, rv, training, momentum, float(bn.eps),
+                           float(negative_slope))
+    return y.view(rows.shape)
+
+
 # ----------------------------------------------------------------------------- 1x1 convolution as a tensor-core GEMM (SURVEY 8f-2)
 
 
-def _split_tf32(x: torch.Tensor, plain: bool, transposed: bool):
-    """x (R,C) contiguous -> (hi, lo, hiT, loT): tf32 halves of x (hi + lo = x to 2^-21) and/or their transposes."""
-    R, C = x.shape
-    hi = torch.empty_like(x) if plain else None
-    lo = torch.empty_like(x) if plain else None
-    hiT = torch.empty(C, R, dtype=torch.float32, device=x.device) if transposed else None
-    loT = torch.empty(C, R, dtype=torch.float32, device=x.device) if transposed else None
-    ptr = lambda t: t.data_ptr() if t is not None else None
-    _lib.call("pcnbr_split_tf32", x.data_ptr(), R, C, ptr(hi), ptr(lo), ptr(hiT), ptr(loT), _stream())
-    return hi, lo, hiT, loT
-
-
-def _gemm3x(a_hi, a_lo, b_hi, b_lo, bias=None) -> torch.Tensor:
-    """(M,K) . (N,K)^T (+ bias) -> (M,N) on tcgen05, 3xTF32 (fp32-grade accuracy)."""
-    M, K = a_hi.shape
-    N = b_hi.shape[0]
+def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None) -> torch.Tensor:
+    """C (M,N) = A (M,K) . B (N,K)^T (+ bias) on tcgen05, 3xTF32 from the fp32 operands (fp32-grade accuracy).
+    a_mn / b_mn: the operand is stored transposed ((K,M) / (K,N) row-major).  Operands are 2-D, unit inner stride."""
     splits = 1 if bias is not None else _lib.size("pcnbr_gemm3x_splits", M, N, K)
     nb = _lib.size("pcnbr_gemm3x_ws_bytes", M, N, K, splits)
-    ws = _ws(nb, a_hi.device)
-    out = torch.empty(M, N, dtype=torch.float32, device=a_hi.device)
-    _lib.call("pcnbr_gemm3x_f32", a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), M, N, K,
+    ws = _ws(nb, A.device)
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.call("pcnbr_gemm3x_f32", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
               bias.data_ptr() if bias is not None else None, out.data_ptr(), splits, ws.data_ptr(), nb, _stream())
     return out
 
 
 class _LinearRowsFn(torch.autograd.Function):
     """y = x W^T + b over the rows of x, all three GEMMs of the layer (output, input gradient, weight gradient) on the
-    tensor cores in 3xTF32.  The operands are split once per tensor; the transposed halves make every GEMM K-major."""
-
-    @staticmethod
-    def forward(ctx, x, w, b):
-        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        xh, xl, xhT, xlT = _split_tf32(x, True, need_dw)
-        wh, wl, whT, wlT = _split_tf32(w, True, need_dx)
-        ctx.save_for_backward(xhT, xlT, whT, wlT)
-        ctx.has_bias = b is not None
-        return _gemm3x(xh, xl, wh, wl, b)
-
-    @staticmethod
-    def backward(ctx, gy):
-        xhT, xlT, whT, wlT = ctx.saved_tensors
-        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gy = _c(gy)
-        gh, gl, ghT, glT = _split_tf32(gy, need_dx, need_dw)
-        dx = _gemm3x(gh, gl, whT, wlT) if need_dx else None                 # (R,Cout) . (Cin,Cout)^T
-        dw = _gemm3x(ghT, glT, xhT, xlT) if need_dw else None               # (Cout,R) . (Cin,R)^T, split along R
-        db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return dx, dw, db
-
-
-class _LinearRowsWgradFn(torch.autograd.Function):
-    """Narrow layers (Cin or Cout too small / unaligned for the K dimension of a tensor-core tile): output and input
-    gradient stay on the library SGEMM, but the WEIGHT gradient -- a (Cout,Cin) output contracted over all the points,
-    which the library runs on one or two CTAs (150-400 us per layer) -- goes through the split-K 3xTF32 GEMM."""
+    tensor cores in 3xTF32, each reading x, W and gy exactly as they lie in memory (no split or transposed copies)."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        return torch.nn.functional.linear(x, w, b)
+        R, Cin = x.shape
+        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
+        R, Cin = x.shape
+        Cout = w.shape[0]
         gy = _c(gy)
-        dx = gy.matmul(w) if ctx.needs_input_grad[0] else None
-        dw = None
-        if ctx.needs_input_grad[1]:
-            _, _, ghT, glT = _split_tf32(gy, False, True)
-            _, _, xhT, xlT = _split_tf32(x, False, True)
-            dw = _gemm3x(ghT, glT, xhT, xlT)                                # (Cout,R) . (Cin,R)^T, split along R
+        dx = _gemm3x(gy, False, w, True, R, Cin, Cout) if ctx.needs_input_grad[0] else None       # gy (R,Cout) . W (Cout,Cin)
+        dw = _gemm3x(gy, True, x, True, Cout, Cin, R) if ctx.needs_input_grad[1] else None         # gy^T . x, split along R
         db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 
@@ -531,21 +574,16 @@ _GEMM_LIBRARY = __import__("os").environ.get("PCNBR_GEMM_LIBRARY") is not None
 
 def linear_rows(rows: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
     """rows (..., Cin) @ weight (Cout, Cin)^T + bias: the 1x1 convolutions of models/utils/common.py:125-178 and
-    models/dgcnn/dgcnn.py:66-126 on point-major rows.  Layers with Cin, Cout >= 64 (4-aligned, >= 4096 rows) run all
-    three GEMMs on the hand-written 3xTF32 tcgen05 kernel; narrower ones keep the library SGEMM for the output and the
-    input gradient and use the split-K tensor-core GEMM for the weight gradient only (PCNBR_GEMM_LIBRARY=1 forces
-    the library everywhere)."""
+    models/dgcnn/dgcnn.py:66-126 on point-major rows.  Layers with 4-aligned channel counts and >= 1024 rows run all
+    three GEMMs on the hand-written 3xTF32 tcgen05 kernel; the rest (odd widths such as the 13-class head) stay on the
+    library SGEMM (PCNBR_GEMM_LIBRARY=1 forces the library everywhere).  `rows` may be a row-pitched view (unit inner
+    stride, uniform row pitch that is a multiple of 4 floats)."""
     cin, cout = weight.shape[1], weight.shape[0]
     nrows = rows.numel() // max(cin, 1)
     usable = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
-              and nrows >= 4096 and nrows % 4 == 0)
+              and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4)
     if not usable:
         return torch.nn.functional.linear(rows, weight, bias)
     x2 = _c(rows).view(nrows, cin)
-    if cin >= 64 and cin % 4 == 0 and cout % 4 == 0 and cout >= 64:
-        y = _LinearRowsFn.apply(x2, _c(weight), bias)
-    elif nrows >= 16384 and torch.is_grad_enabled() and weight.requires_grad:
-        y = _LinearRowsWgradFn.apply(x2, _c(weight), bias)
-    else:
-        return torch.nn.functional.linear(rows, weight, bias)
+    y = _LinearRowsFn.apply(x2, _c(weight), bias)
     return y.view(*rows.shape[:-1], cout)

@@ -147,22 +147,50 @@ PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const 
                            const int32_t* offsets, const int32_t* perm, const float* coef, int B, int N, int K,
                            int O, float* dPQ, pcnbr_stream_t stream);
 
+/* ---- fused BatchNorm + (Leaky)ReLU over point-major rows ---- common.py:125-178, dgcnn.py:66-71,95-126
+ * Replaces the library triple BatchNorm -> activation (and its three backward ops) behind MiniPointNet / UnitPointNet /
+ * the DGCNN head on a (R, C) row matrix (C % 4 == 0, C/4 a power of two <= 512: pcnbr_bn_supported).
+ *   pcnbr_bn_stats_f32      : partial (pcnbr_bn_blocks(R,C), 2, C) = per-block sum(x - x[0,:]) and sum((x - x[0,:])^2)
+ *   pcnbr_bn_finalize_f32   : fp64 combine in block order -> stats (4,C) = {mean, rstd, gamma*rstd, beta}; updates
+ *                             running_mean / running_var (momentum, unbiased variance) when they are non-NULL.
+ *                             nblk == 0 = eval mode: mean / var are the running statistics.  `count` = values per channel.
+ *   pcnbr_bn_act_fwd_f32    : y (R,C) = act((x - mean) * gamma*rstd + beta), x[r,c] = a[r*lda+c] (+ b[r*ldb+c] if b != NULL),
+ *                             act(t) = t > 0 ? t : slope*t   (slope 0 = ReLU, 0.2 = the DGCNN LeakyReLU)
+ *   pcnbr_bn_act_bwd_reduce_f32 : g' = gy * act'(pre);  partial = per-block {sum g', sum g' * xhat};  gs (R,C) <- g' if non-NULL
+ *   pcnbr_bn_bwd_finalize_f32   : dgamma, dbeta (C) and coef (4,C) = {gamma*rstd, c1, c2r, mean} (c1 = c2r = 0 unless training)
+ *   pcnbr_bn_act_bwd_apply_f32  : dx (R,C) = gamma*rstd * g' - c1 - c2r * (x - mean)
+ * Deterministic (fixed-order reductions, no atomics). */
+PCNBR_API int pcnbr_bn_supported(long R, int C);
+PCNBR_API int pcnbr_bn_blocks(long R, int C);
+PCNBR_API int pcnbr_bn_stats_f32(const float* x, long R, int C, float* partial, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float* shift, double count, int C,
+                          const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                          float* running_var, float* stats, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, long ldb, long R, int C, const float* stats,
+                         float slope, float* y, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_bn_act_bwd_reduce_f32(const float* gy, const float* a, long lda, const float* b, long ldb, long R, int C,
+                                const float* stats, float slope, float* partial, float* gs, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const float* stats, double count, int C, int training,
+                              float* dgamma, float* dbeta, float* coef, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
+                               float slope, float* dx, pcnbr_stream_t stream);
+
 /* ---- fp32-accurate tensor-core GEMM for the 1x1 convolutions ---- common.py:125-178, dgcnn.py:66-126
  * Not a reference entry point: the reference's Conv1d/Conv2d(kernel 1) are library GEMMs; under the fp32 parity bar
  * they run as SIMT SGEMMs.  Here C (M,N) = A (M,K) . B (N,K)^T (+ bias (N)) runs as 3xTF32 on tcgen05 (hi.hi' + lo.hi' +
- * hi.lo', fp32 accumulation in TMEM; error ~2^-21 |a||b|).
- * pcnbr_split_tf32: x (R,C) row-major -> hi = tf32(x), lo = tf32(x - hi), (R,C) each (NULL to skip), and/or their
- *   transposes hiT, loT (C,R) (NULL to skip) -- so that every GEMM of a layer (output, input gradient, weight gradient)
- *   is K-major.
- * pcnbr_gemm3x_f32: all four operands 16-byte aligned, K % 4 == 0.  splits > 1 (from pcnbr_gemm3x_splits; weight
- *   gradients, where M and N are small and K is the number of points) cuts K over the CTAs; the partial tiles go to
- *   ws (pcnbr_gemm3x_ws_bytes) and are summed in a fixed order: deterministic, no atomics; bias must be NULL then. */
-PCNBR_API int pcnbr_split_tf32(const float* x, long R, long C, float* hi, float* lo, float* hiT, float* loT,
-                     pcnbr_stream_t stream);
+ * hi.lo', fp32 accumulation in TMEM; error ~2^-20 |a||b|) directly from the fp32 operands: hi is the operand word
+ * itself (the tensor core ignores the low 13 mantissa bits), lo is produced in shared memory inside the kernel.
+ *   a_mn == 0: A is row-major (M,K) with row pitch lda;  a_mn != 0: A is stored transposed, row-major (K,M), pitch lda.
+ *   b_mn == 0: B is row-major (N,K) with row pitch ldb;  b_mn != 0: B is stored transposed, row-major (K,N), pitch ldb.
+ *   (so y = x W^T, dx = gy W and dW = gy^T x all read x, W and gy as they lie in memory).
+ *   Bases 16-byte aligned, lda % 4 == 0, ldb % 4 == 0; C is (M,N) contiguous.
+ *   splits > 1 (from pcnbr_gemm3x_splits; weight gradients, where M and N are small and K is the number of points)
+ *   cuts K over the CTAs; the partial tiles go to ws (pcnbr_gemm3x_ws_bytes) and are summed in a fixed order:
+ *   deterministic, no atomics; bias must be NULL then. */
 PCNBR_API int pcnbr_gemm3x_splits(int M, int N, int K);
 PCNBR_API size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits);
-PCNBR_API int pcnbr_gemm3x_f32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int M, int N,
-                     int K, const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, int M, int N, int K,
+                     const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
 /* ---- measurement hook (bench.py roofline, kernel sweep) -- not part of the reference interface
  * pcnbr_prof_enable(1): bracket every kernel this library launches with CUDA events on its launch stream and

@@ -69,7 +69,8 @@ def test_fused_equals_exact_cuda_path(pkg, dev):
 
 # --------------------------------------------------------------------------- 1x1 convolutions on the 3xTF32 tcgen05 GEMM
 
-@pytest.mark.parametrize("R,Cin,Cout,bias", [(8192, 1408, 512, False), (4096, 384, 1024, True), (5000, 132, 68, True), (65536, 512, 256, False)])
+@pytest.mark.parametrize("R,Cin,Cout,bias", [(8192, 1408, 512, False), (4096, 384, 1024, True), (5000, 132, 68, True), (65536, 512, 256, False),
+                                             (16384, 12, 32, True), (32768, 32, 64, False), (8192, 64, 32, True), (1024, 260, 256, True)])
 def test_linear_rows_tensor_core_matches_fp64(pkg, dev, R, Cin, Cout, bias):
     """ops.linear_rows (the Conv1d/Conv2d kernel-1 layers of common.py:125-178 / dgcnn.py:95-126 on point-major rows):
     output, input gradient, weight gradient (split-K, deterministic) and bias gradient against float64, well inside the
@@ -101,6 +102,24 @@ def test_linear_rows_tensor_core_matches_fp64(pkg, dev, R, Cin, Cout, bias):
     assert torch.equal(wd2.grad, wd.grad) and torch.equal(xd2.grad, xd.grad)
 
 
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,K", [(300, 72, 100), (128, 256, 64), (1000, 40, 2048), (64, 12, 40000)])
+def test_gemm3x_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K):
+    """pcnbr_gemm3x_f32 with K-major and MN-major (transposed-in-memory) operands, ragged sizes, split-K: all against
+    float64.  The operands are plain fp32 matrices; the hi/lo split happens inside the kernel."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g) + 0.25
+    Bm = torch.randn(N, K, generator=g) - 0.1
+    pad = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 4))            # 16-byte row pitch, logical width kept
+    Am = pad(A.t().contiguous() if a_mn else A).to(dev)
+    Bmm = pad(Bm.t().contiguous() if b_mn else Bm).to(dev)
+    out = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K)
+    ref = A.double() @ Bm.double().t()
+    _close(out, ref, 3e-5)
+    assert torch.equal(out, pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K))
+
+
 def test_linear_rows_narrow_layers_stay_on_the_library(pkg, dev):
     x = torch.randn(4096, 9, device=dev)
     w = torch.randn(32, 9, device=dev)
@@ -108,3 +127,60 @@ def test_linear_rows_narrow_layers_stay_on_the_library(pkg, dev):
     y = pkg.ops.linear_rows(x, w, None)
     assert pkg._lib.launches == launches0
     _close(y, x.double() @ w.double().t(), 1e-5)
+
+
+# --------------------------------------------------------------------------- fused BatchNorm + (Leaky)ReLU over rows
+
+@pytest.mark.parametrize("R,C,slope", [(65536, 64, 0.0), (4099, 32, 0.0), (8192, 1024, 0.2), (1000, 2048, 0.2), (300, 8, 0.0),
+                                       (16384, 256, 0.2)])
+@pytest.mark.parametrize("train", [True, False])
+def test_batchnorm_act_rows_matches_fp64(pkg, dev, R, C, slope, train):
+    """ops.batchnorm_act_rows = nn.BatchNorm1d -> ReLU / LeakyReLU of common.py:146,175 and dgcnn.py:67-70 on point-major
+    rows: output, input / gamma / beta gradients, running statistics and num_batches_tracked against the float64 module,
+    with a large per-channel offset (S3DIS coordinates are tens of metres from the origin)."""
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C, generator=g) * (0.2 + torch.rand(C, generator=g)) + 20.0 * torch.randn(C, generator=g)
+    gy = torch.randn(R, C, generator=g)
+    bn = torch.nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(C, generator=g))
+        bn.bias.copy_(torch.randn(C, generator=g))
+        bn.running_mean.copy_(x.mean(0) + 0.1 * torch.randn(C, generator=g))
+        bn.running_var.copy_(x.var(0) * (0.5 + torch.rand(C, generator=g)))
+    import copy
+    bn64 = copy.deepcopy(bn).double()
+    bnd = copy.deepcopy(bn).to(dev)
+    bn64.train(train); bnd.train(train)
+    # the activation's derivative jumps at 0: keep the upstream gradient off the pre-activations that fp32 and fp64
+    # could put on different sides of it
+    with torch.no_grad():
+        pre = copy.deepcopy(bn64)(x.double())
+        gy = gy * (pre.abs() > 1e-3).float()
+    xd = x.to(dev).requires_grad_(True)
+    launches0 = pkg._lib.launches
+    y = pkg.ops.batchnorm_act_rows(xd, bnd, slope)
+    y.backward(gy.to(dev))
+    assert pkg._lib.launches >= launches0 + 5, "batchnorm_act_rows did not run on libpcnbr"
+    x64 = x.double().requires_grad_(True)
+    y64 = torch.nn.functional.leaky_relu(bn64(x64), slope)
+    y64.backward(gy.double())
+    _close(y, y64, 2e-5)
+    _close(xd.grad, x64.grad, 1e-4)
+    _close(bnd.weight.grad, bn64.weight.grad, 1e-4)
+    _close(bnd.bias.grad, bn64.bias.grad, 1e-4)
+    _close(bnd.running_mean, bn64.running_mean, 1e-6)
+    _close(bnd.running_var, bn64.running_var, 1e-5)
+    assert int(bnd.num_batches_tracked) == int(bn64.num_batches_tracked)
+    # deterministic
+    xd2 = x.to(dev).requires_grad_(True)
+    bnd.zero_grad()
+    pkg.ops.batchnorm_act_rows(xd2, bnd, slope).backward(gy.to(dev))
+    assert torch.equal(xd2.grad, xd.grad)
+
+
+def test_batchnorm_act_rows_unsupported_width_uses_library(pkg, dev):
+    x = torch.randn(512, 13, device=dev)
+    bn = torch.nn.BatchNorm1d(13).to(dev)
+    y = pkg.ops.batchnorm_act_rows(x, bn, 0.2)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(x.double(), None, None, bn.weight.double(), bn.bias.double(), True), 0.2)
+    _close(y, ref, 1e-5)
