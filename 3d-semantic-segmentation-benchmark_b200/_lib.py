@@ -27,10 +27,10 @@ PROTOTYPES = {
     "pcnbr_knn_expand_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "pcnbr_knn_expand_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P]),
     "pcnbr_knn_tc_debug_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P, _P, _P]),
-    "pcnbr_group_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "pcnbr_group_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "pcnbr_csr_ws_bytes": (_Z, [_I, _I, _I]),
     "pcnbr_csr_build": (_I, [_P, _I, _I, _I, _P, _P, _P, _Z, _P]),
-    "pcnbr_group_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_group_bwd_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pcnbr_maxpool_f32": (_I, [_P, _L, _I, _I, _L, _L, _L, _P, _P, _P]),
     "pcnbr_maxpool_bwd_f32": (_I, [_P, _P, _L, _I, _I, _L, _L, _L, _P, _P]),
     "pcnbr_interp_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),

@@ -34,6 +34,13 @@ def group(centroid_coords: torch.Tensor, coords: torch.Tensor, features: torch.T
     return ops.group_points(coords, features, centroid_coords, nbr, r if normalize else None)
 
 
+def _group_rows(centroid_coords, coords, features, r, K, normalize):
+    """group() for the modules below: the same tensor with its rows zero-padded to a multiple of 4 floats, the pitch
+    the tensor-core GEMM of the first 1x1 convolution reads in place (MiniPointNet.forward_rows)."""
+    nbr = ops.NeighborIndex(ops.query_ball_point(r, K, coords, centroid_coords), coords.shape[1])
+    return ops.group_points(coords, features, centroid_coords, nbr, r if normalize else None, pad4=True)
+
+
 def reduce(x: torch.Tensor, type: str) -> torch.Tensor:
     """Pooling over the K axis of (B,C,K,D')   [common.py:74-91].
 
@@ -75,11 +82,19 @@ class MiniPointNet(nn.Module):
             for conv, bn in zip(self.conv, self.batch):
                 x = F.relu(bn(conv(x)))
             return x
+        return self.forward_rows(rows).permute(0, 3, 1, 2)
+
+    def forward_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        """rows (B,C,K,Cin') point-major, Cin' = Cin or Cin rounded up to a multiple of 4 with zero columns
+        (ops.group_points(pad4=True)) -> (B,C,K,Cout).  The first weight is zero-padded to match, so the result and all
+        gradients are those of the unpadded layer."""
         h = rows
-        for conv, bn in zip(self.conv, self.batch):
-            h = ops.linear_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
-            h = ops.batchnorm_act_rows(h, bn, 0.0)                          # BatchNorm2d + ReLU, fused (B,C,K,Cout)
-        return h.permute(0, 3, 1, 2)
+        for i, (conv, bn) in enumerate(zip(self.conv, self.batch)):
+            w = conv.weight.view(conv.out_channels, conv.in_channels)
+            if i == 0 and h.shape[-1] != conv.in_channels:
+                w = F.pad(w, (0, h.shape[-1] - conv.in_channels))
+            h = ops.linear_bn_act_rows(h, w, conv.bias, bn, 0.0)            # conv 1x1 + BatchNorm2d + ReLU (B,C,K,Cout)
+        return h
 
 
 def _batch_norm_rows(bn: nn.modules.batchnorm._BatchNorm, rows: torch.Tensor) -> torch.Tensor:
@@ -121,8 +136,7 @@ class UnitPointNet(nn.Module):
             return x
         h = rows
         for conv, bn in zip(self.conv, self.batch):
-            h = ops.linear_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
-            h = ops.batchnorm_act_rows(h, bn, 0.0)                          # BatchNorm1d + ReLU, fused (B,N,Cout)
+            h = ops.linear_bn_act_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias, bn, 0.0)
         return h.permute(0, 2, 1)
 
 
@@ -142,9 +156,9 @@ class SetAbstraction(nn.Module):
 
     def forward(self, coords: torch.Tensor, features: torch.Tensor):
         centroid_coords = sample(coords, self.C, self.fps_start)
-        grouped = group(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
-        x = self.point_net(grouped.permute(0, 3, 1, 2))      # channels-last view: no copy
-        return centroid_coords, reduce(x.permute(0, 2, 3, 1), self.pooling_type)
+        grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
+        x = self.point_net.forward_rows(grouped)             # point-major rows (B,C,K,*): no permute, no copy
+        return centroid_coords, reduce(x, self.pooling_type)
 
 
 class FeaturePropagation(nn.Module):
@@ -173,8 +187,7 @@ class InvResMLP(nn.Module):
         self.point_features_mlp = UnitPointNet(mlp_size, [4 * mlp_size, mlp_size])
 
     def forward(self, centroid_coords, coords, features):
-        grouped = group(centroid_coords, coords, features, self.radius, self.K, True)
-        x = self.neighbour_features_mlp(grouped.permute(0, 3, 1, 2))
-        x = reduce(x.permute(0, 2, 3, 1), self.pooling_type)
+        grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, True)
+        x = reduce(self.neighbour_features_mlp.forward_rows(grouped), self.pooling_type)
         x = self.point_features_mlp(x.permute(0, 2, 1)).permute(0, 2, 1)
         return centroid_coords, x + features

@@ -106,18 +106,20 @@ bn_stats_kernel(const float* __restrict__ x, long R, int C, int rows_per_block, 
 // Combine the block partials (fp64, ascending block order) into the BatchNorm constants
 //   stats (4,C) = { mean, rstd, gamma*rstd, beta }      and update the running statistics (momentum, unbiased variance).
 // nblk == 0: eval mode, mean/var come from running_mean / running_var.
-__global__ void __launch_bounds__(256)
+constexpr int BA_FS = 32;   // partial-row slices per channel in the finalize kernels (32 channels x 32 slices per CTA)
+
+__global__ void __launch_bounds__(32 * BA_FS)
 bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ shift, double count, int C,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ stats) {
-    __shared__ double a1[8][32], a2[8][32];
+    __shared__ double a1[BA_FS][32], a2[BA_FS][32];
     const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-        const int per = (nblk + 7) / 8;
+        const int per = (nblk + BA_FS - 1) / BA_FS;
         const int b0 = sy * per, b1 = min(nblk, b0 + per);
-#pragma unroll 4
+#pragma unroll 8
         for (int b = b0; b < b1; ++b) {
             s1 += (double)partial[(size_t)b * 2 * C + c];
             s2 += (double)partial[(size_t)b * 2 * C + C + c];
@@ -126,7 +128,7 @@ bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __r
     a1[sy][cx] = s1; a2[sy][cx] = s2;
     __syncthreads();
     if (sy != 0 || c >= C) return;
-    for (int k = 1; k < 8; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
+    for (int k = 1; k < BA_FS; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
     double mean, var;
     if (nblk > 0) {
         const double m1 = s1 / count;
@@ -229,17 +231,17 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__
 
 // dbeta = sum g', dgamma = sum g' xhat (fp64 over the blocks, fixed order);
 // coef (4,C) = { gr = gamma*rstd, gr*dbeta/count, gr*rstd*dgamma/count, mean }   (the two middle rows are 0 in eval mode)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * BA_FS)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ stats, double count, int C,
                        int training, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-    __shared__ double a1[8][32], a2[8][32];
+    __shared__ double a1[BA_FS][32], a2[BA_FS][32];
     const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     double s1 = 0.0, s2 = 0.0;
     if (c < C) {
-        const int per = (nblk + 7) / 8;
+        const int per = (nblk + BA_FS - 1) / BA_FS;
         const int b0 = sy * per, b1 = min(nblk, b0 + per);
-#pragma unroll 4
+#pragma unroll 8
         for (int b = b0; b < b1; ++b) {
             s1 += (double)partial[(size_t)b * 2 * C + c];
             s2 += (double)partial[(size_t)b * 2 * C + C + c];
@@ -248,7 +250,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float*
     a1[sy][cx] = s1; a2[sy][cx] = s2;
     __syncthreads();
     if (sy != 0 || c >= C) return;
-    for (int k = 1; k < 8; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
+    for (int k = 1; k < BA_FS; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
     const double gr = (double)stats[2 * C + c], rstd = (double)stats[C + c];
@@ -355,7 +357,7 @@ extern "C" int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float
     if (nblk == 0 && (!running_mean || !running_var)) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     PCNBR_TIMED("bn_finalize_kernel", s, 8.0 * nblk * C + 32.0 * C, 4.0 * nblk * C,
-                (bn_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partial, nblk, shift, count, C, gamma, beta, eps, momentum,
+                (bn_finalize_kernel<<<(C + 31) / 32, 32 * BA_FS, 0, s>>>(partial, nblk, shift, count, C, gamma, beta, eps, momentum,
                                                                   running_mean, running_var, stats)));
     PCNBR_CHECK_LAUNCH();
     return 0;
@@ -396,7 +398,7 @@ extern "C" int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const f
     if (!partial || !stats || !dgamma || !dbeta || !coef || C <= 0 || nblk <= 0 || count <= 0.0) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     PCNBR_TIMED("bn_bwd_finalize_kernel", s, 8.0 * nblk * C + 40.0 * C, 4.0 * nblk * C,
-                (bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partial, nblk, stats, count, C, training, dgamma, dbeta, coef)));
+                (bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * BA_FS, 0, s>>>(partial, nblk, stats, count, C, training, dgamma, dbeta, coef)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

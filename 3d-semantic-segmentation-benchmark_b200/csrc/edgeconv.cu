@@ -17,62 +17,123 @@
 
 namespace pcnbr {
 
+// A lane owns VEC = O/32 CONSECUTIVE channels, so one neighbour row is one 128/256/512/1024-byte warp request.
+template <int VEC>
+__device__ __forceinline__ void ec_ld(const float* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        v[0] = *p;
+    } else if constexpr (VEC == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void ec_st(float* __restrict__ p, const float (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        *p = v[0];
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i)
+            *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void ec_ld_u8(const uint8_t* __restrict__ p, int (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        v[0] = *p;
+    } else if constexpr (VEC == 2) {
+        const uchar2 t = *reinterpret_cast<const uchar2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i) {
+            const uchar4 t = *reinterpret_cast<const uchar4*>(p + 4 * i);
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void ec_st_u8(uint8_t* __restrict__ p, const int (&v)[VEC]) {
+    if constexpr (VEC == 1) {
+        *p = (uint8_t)v[0];
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<uchar2*>(p) = make_uchar2((uint8_t)v[0], (uint8_t)v[1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 4; ++i)
+            *reinterpret_cast<uchar4*>(p + 4 * i) = make_uchar4((uint8_t)v[4 * i], (uint8_t)v[4 * i + 1], (uint8_t)v[4 * i + 2], (uint8_t)v[4 * i + 3]);
+    }
+}
+
 // PQ (B,N,2O): P = [..., :O], Q = [..., O:].  idx (B,N,K).  selmax[o] != 0: keep max_j P_j, else min_j.
-// shift[o]: any constant near the typical u (variance is accumulated about it).  VPL = O / 32.
-template <int VPL>
+// shift[o]: any constant near the typical u (variance is accumulated about it).  VEC = O / 32.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ idx, const uint8_t* __restrict__ selmax,
                     const float* __restrict__ shift, int N, int K, float* __restrict__ psel, uint8_t* __restrict__ arg,
                     float* __restrict__ s1, float* __restrict__ partial) {
-    constexpr int O = 32 * VPL;
+    constexpr int O = 32 * VEC;
     __shared__ float red[8][2 * O];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = lane * VEC;
     const float* __restrict__ pq = PQ + (size_t)b * N * 2 * O;
     const int32_t* __restrict__ ib = idx + (size_t)b * N * K;
-    float c[VPL], a1[VPL], a2[VPL];
-    bool smax[VPL];
+    float c[VEC], a1[VEC], a2[VEC];
+    int smax_i[VEC];
+    ec_ld<VEC>(shift + c0, c);
+    ec_ld_u8<VEC>(selmax + c0, smax_i);
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        c[v] = shift[lane + 32 * v];
-        smax[v] = selmax[lane + 32 * v] != 0;
-        a1[v] = 0.f; a2[v] = 0.f;
-    }
+    for (int v = 0; v < VEC; ++v) { a1[v] = 0.f; a2[v] = 0.f; }
     for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
-        float q[VPL], best[VPL], sum[VPL];
-        int ba[VPL];
+        float q[VEC], best[VEC], sum[VEC];
+        int ba[VEC];
+        ec_ld<VEC>(pq + (size_t)n * 2 * O + O + c0, q);
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            q[v] = pq[(size_t)n * 2 * O + O + lane + 32 * v];
-            best[v] = 0.f; sum[v] = 0.f; ba[v] = 0;
-        }
+        for (int v = 0; v < VEC; ++v) { best[v] = 0.f; sum[v] = 0.f; ba[v] = 0; }
+        auto take_row = [&](const float (&p)[VEC], int j) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float d = (p[v] + q[v]) - c[v];
+                a1[v] += d;
+                a2[v] = fmaf(d, d, a2[v]);
+                sum[v] += p[v];
+                const bool take = (j == 0) || (smax_i[v] ? (p[v] > best[v]) : (p[v] < best[v]));
+                if (take) { best[v] = p[v]; ba[v] = j; }
+            }
+        };
         for (int j0 = 0; j0 < K; j0 += 32) {
             const int mine = (j0 + lane < K) ? ib[(size_t)n * K + j0 + lane] : 0;
             const int cnt = min(32, K - j0);
-            for (int l = 0; l < cnt; ++l) {
-                const int m = __shfl_sync(PCNBR_FULL, mine, l);
-                const float* __restrict__ row = pq + (size_t)m * 2 * O;
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    const float p = row[lane + 32 * v];
-                    const float d = (p + q[v]) - c[v];
-                    a1[v] += d;
-                    a2[v] = fmaf(d, d, a2[v]);
-                    sum[v] += p;
-                    const bool take = (j0 + l == 0) || (smax[v] ? (p > best[v]) : (p < best[v]));
-                    if (take) { best[v] = p; ba[v] = j0 + l; }
-                }
+            int l = 0;
+            for (; l + 4 <= cnt; l += 4) {                      // four neighbour rows in flight
+                float p0[VEC], p1[VEC], p2[VEC], p3[VEC];
+                ec_ld<VEC>(pq + (size_t)__shfl_sync(PCNBR_FULL, mine, l) * 2 * O + c0, p0);
+                ec_ld<VEC>(pq + (size_t)__shfl_sync(PCNBR_FULL, mine, l + 1) * 2 * O + c0, p1);
+                ec_ld<VEC>(pq + (size_t)__shfl_sync(PCNBR_FULL, mine, l + 2) * 2 * O + c0, p2);
+                ec_ld<VEC>(pq + (size_t)__shfl_sync(PCNBR_FULL, mine, l + 3) * 2 * O + c0, p3);
+                take_row(p0, j0 + l); take_row(p1, j0 + l + 1); take_row(p2, j0 + l + 2); take_row(p3, j0 + l + 3);
+            }
+            for (; l < cnt; ++l) {
+                float p0[VEC];
+                ec_ld<VEC>(pq + (size_t)__shfl_sync(PCNBR_FULL, mine, l) * 2 * O + c0, p0);
+                take_row(p0, j0 + l);
             }
         }
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const size_t o = ((size_t)b * N + n) * O + lane + 32 * v;
-            psel[o] = best[v];
-            arg[o] = (uint8_t)ba[v];
-            s1[o] = sum[v];
-        }
+        const size_t o = ((size_t)b * N + n) * O + c0;
+        ec_st<VEC>(psel + o, best);
+        ec_st_u8<VEC>(arg + o, ba);
+        ec_st<VEC>(s1 + o, sum);
     }
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) { red[warp][lane + 32 * v] = a1[v]; red[warp][O + lane + 32 * v] = a2[v]; }
+    for (int v = 0; v < VEC; ++v) { red[warp][c0 + v] = a1[v]; red[warp][O + c0 + v] = a2[v]; }
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * O; t += 256) {
         float s = red[0][t];
@@ -84,65 +145,74 @@ edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ id
 
 // Backward: exact BatchNorm(train) + LeakyReLU + max backward in terms of (B,N,O) tensors.
 //   u[n,j] = P[idx[n,j]] + Q[n];  y = gamma (u - mu) r + beta;  out[n] = act(y[n, arg[n]])
-//   gs[n,o]  = dL/dy on the selected edge (host: g_out * act'(out))
+//   gs[n,o]  = dL/dy on the selected edge (g_out * act'(out))
 //   dL/du[n,j] = gr gs [j == arg] - c1 - c2r (u[n,j] - mu)            gr = gamma r, c1 = gr sum(gs)/M, c2r = gr r sum(gs yhat)/M
 //   dP[m] = sum over incoming edges (n,j) of m of dL/du[n,j]
 //         = gr T1[m] - deg(m) c1 - c2r (deg(m) (P[m] - mu) + T2[m]),  T1 = sum_{incoming, arg[n]==j} gs[n],  T2 = sum_incoming Q[n]
 //   dQ[n] = sum_j dL/du[n,j] = gr gs[n] - K c1 - c2r (s1[n] + K (Q[n] - mu))
 // One warp per point m gathers its incoming edges through the CSR inverse (ascending position: deterministic,
 // no atomics); segments longer than 64 edges (hub points) are split over the 8 warps of the CTA.
-template <int VPL>
+template <int VEC>
 __device__ __forceinline__ void edgeconv_bwd_accumulate(const float* __restrict__ gs, const uint8_t* __restrict__ arg,
                                                         const float* __restrict__ PQ, const int32_t* __restrict__ pm,
                                                         size_t rowbase, int beg, int end, int K, int lane,
-                                                        float (&t1)[VPL], float (&t2)[VPL]) {
-    constexpr int O = 32 * VPL;
+                                                        float (&t1)[VEC], float (&t2)[VEC]) {
+    constexpr int O = 32 * VEC;
+    const int c0 = lane * VEC;
+    auto edge = [&](int n, int j) {
+        const size_t r = rowbase + n;
+        float g[VEC], qv[VEC];
+        int av[VEC];
+        ec_ld<VEC>(gs + r * O + c0, g);
+        ec_ld_u8<VEC>(arg + r * O + c0, av);
+        ec_ld<VEC>(PQ + r * 2 * O + O + c0, qv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            t1[v] += (av[v] == j) ? g[v] : 0.f;
+            t2[v] += qv[v];
+        }
+    };
     for (int t0 = beg; t0 < end; t0 += 32) {
         const int e = (t0 + lane < end) ? pm[t0 + lane] : 0;
         const int nl = e / K, jl = e - nl * K;
         const int cnt = min(32, end - t0);
 #pragma unroll 4
-        for (int l = 0; l < cnt; ++l) {
-            const int n = __shfl_sync(PCNBR_FULL, nl, l), j = __shfl_sync(PCNBR_FULL, jl, l);
-            const size_t r = rowbase + n;
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const int c = lane + 32 * v;
-                const float g = gs[r * O + c];
-                t1[v] += (arg[r * O + c] == j) ? g : 0.f;
-                t2[v] += PQ[r * 2 * O + O + c];
-            }
-        }
+        for (int l = 0; l < cnt; ++l) edge(__shfl_sync(PCNBR_FULL, nl, l), __shfl_sync(PCNBR_FULL, jl, l));
     }
 }
 
-template <int VPL>
+template <int VEC>
 __global__ void __launch_bounds__(256)
 edgeconv_bwd_kernel(const float* __restrict__ gs, const uint8_t* __restrict__ arg, const float* __restrict__ PQ,
                     const float* __restrict__ s1, const int32_t* __restrict__ offsets, const int32_t* __restrict__ perm,
                     const float* __restrict__ coef, int N, int K, float* __restrict__ dPQ) {
-    constexpr int O = 32 * VPL;
+    constexpr int O = 32 * VEC;
     __shared__ int s_beg[8], s_len[8];
     __shared__ float s_part[8][2 * O];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = lane * VEC;
     const int32_t* o = offsets + (size_t)b * (N + 1);
     const int32_t* pm = perm + (size_t)b * N * K;
     const size_t rowbase = (size_t)b * N;
-    float gr[VPL], c1[VPL], c2r[VPL], mu[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        const int c = lane + 32 * v;
-        gr[v] = coef[c]; c1[v] = coef[O + c]; c2r[v] = coef[2 * O + c]; mu[v] = coef[3 * O + c];
-    }
-    auto finish = [&](int m, int deg, const float (&t1)[VPL], const float (&t2)[VPL]) {
+    float gr[VEC], c1[VEC], c2r[VEC], mu[VEC];
+    ec_ld<VEC>(coef + c0, gr);
+    ec_ld<VEC>(coef + O + c0, c1);
+    ec_ld<VEC>(coef + 2 * O + c0, c2r);
+    ec_ld<VEC>(coef + 3 * O + c0, mu);
+    auto finish = [&](int m, int deg, const float (&t1)[VEC], const float (&t2)[VEC]) {
         const size_t r = rowbase + m;
+        float P[VEC], Q[VEC], g[VEC], sv[VEC], dP[VEC], dQ[VEC];
+        ec_ld<VEC>(PQ + r * 2 * O + c0, P);
+        ec_ld<VEC>(PQ + r * 2 * O + O + c0, Q);
+        ec_ld<VEC>(gs + r * O + c0, g);
+        ec_ld<VEC>(s1 + r * O + c0, sv);
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-            const int c = lane + 32 * v;
-            const float P = PQ[r * 2 * O + c], Q = PQ[r * 2 * O + O + c];
-            dPQ[r * 2 * O + c] = gr[v] * t1[v] - (float)deg * c1[v] - c2r[v] * ((float)deg * (P - mu[v]) + t2[v]);
-            dPQ[r * 2 * O + O + c] = gr[v] * gs[r * O + c] - (float)K * c1[v] - c2r[v] * (s1[r * O + c] + (float)K * (Q - mu[v]));
+        for (int v = 0; v < VEC; ++v) {
+            dP[v] = gr[v] * t1[v] - (float)deg * c1[v] - c2r[v] * ((float)deg * (P[v] - mu[v]) + t2[v]);
+            dQ[v] = gr[v] * g[v] - (float)K * c1[v] - c2r[v] * (sv[v] + (float)K * (Q[v] - mu[v]));
         }
+        ec_st<VEC>(dPQ + r * 2 * O + c0, dP);
+        ec_st<VEC>(dPQ + r * 2 * O + O + c0, dQ);
     };
     for (int m0 = blockIdx.x * 8; m0 < N; m0 += gridDim.x * 8) {
         const int m = m0 + warp;
@@ -150,10 +220,10 @@ edgeconv_bwd_kernel(const float* __restrict__ gs, const uint8_t* __restrict__ ar
         const int len = (m < N) ? o[m + 1] - beg : 0;
         if (lane == 0) { s_beg[warp] = beg; s_len[warp] = len; }
         if (m < N && len <= SEG_HEAVY) {
-            float t1[VPL], t2[VPL];
+            float t1[VEC], t2[VEC];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) { t1[v] = 0.f; t2[v] = 0.f; }
-            edgeconv_bwd_accumulate<VPL>(gs, arg, PQ, pm, rowbase, beg, beg + len, K, lane, t1, t2);
+            for (int v = 0; v < VEC; ++v) { t1[v] = 0.f; t2[v] = 0.f; }
+            edgeconv_bwd_accumulate<VEC>(gs, arg, PQ, pm, rowbase, beg, beg + len, K, lane, t1, t2);
             finish(m, len, t1, t2);
         }
         __syncthreads();
@@ -163,19 +233,19 @@ edgeconv_bwd_kernel(const float* __restrict__ gs, const uint8_t* __restrict__ ar
             const int hb = s_beg[w];
             const int piece = (hl + 7) / 8;
             const int pb = min(hb + warp * piece, hb + hl), pe = min(pb + piece, hb + hl);
-            float t1[VPL], t2[VPL];
+            float t1[VEC], t2[VEC];
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) { t1[v] = 0.f; t2[v] = 0.f; }
-            edgeconv_bwd_accumulate<VPL>(gs, arg, PQ, pm, rowbase, pb, pe, K, lane, t1, t2);
+            for (int v = 0; v < VEC; ++v) { t1[v] = 0.f; t2[v] = 0.f; }
+            edgeconv_bwd_accumulate<VEC>(gs, arg, PQ, pm, rowbase, pb, pe, K, lane, t1, t2);
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) { s_part[warp][lane + 32 * v] = t1[v]; s_part[warp][O + lane + 32 * v] = t2[v]; }
+            for (int v = 0; v < VEC; ++v) { s_part[warp][c0 + v] = t1[v]; s_part[warp][O + c0 + v] = t2[v]; }
             __syncthreads();
             if (warp == 0) {
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    t1[v] = s_part[0][lane + 32 * v]; t2[v] = s_part[0][O + lane + 32 * v];
+                for (int v = 0; v < VEC; ++v) {
+                    t1[v] = s_part[0][c0 + v]; t2[v] = s_part[0][O + c0 + v];
 #pragma unroll
-                    for (int k = 1; k < 8; ++k) { t1[v] += s_part[k][lane + 32 * v]; t2[v] += s_part[k][O + lane + 32 * v]; }
+                    for (int k = 1; k < 8; ++k) { t1[v] += s_part[k][c0 + v]; t2[v] += s_part[k][O + c0 + v]; }
                 }
                 finish(m0 + w, hl, t1, t2);
             }

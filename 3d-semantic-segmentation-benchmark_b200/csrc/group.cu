@@ -14,9 +14,9 @@ namespace pcnbr {
 // when W < 32 (lane -> (row, col)), or one row per pass with lanes striding over the columns.
 __global__ void __launch_bounds__(256)
 group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, const float* __restrict__ q,
-                 const int32_t* __restrict__ idx, int N, int M, int K, int D, float rdiv, long rows,
+                 const int32_t* __restrict__ idx, int N, int M, int K, int D, float rdiv, long rows, int ldo,
                  float* __restrict__ out) {
-    const int W = 3 + D;
+    const int W = ldo;                                     // output row pitch >= 3 + D; the pad columns are written as 0
     const int lane = threadIdx.x & 31;
     const long warp_global = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
@@ -34,8 +34,10 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
                 if (col < 3) {
                     v = __fsub_rn(p[((size_t)b * N + s) * 3 + col], q[((size_t)b * M + m) * 3 + col]);
                     if (rdiv > 0.f) v = __fdiv_rn(v, rdiv);                       // common.py:69
-                } else {
+                } else if (col < 3 + D) {
                     v = feat[((size_t)b * N + s) * D + (col - 3)];
+                } else {
+                    v = 0.f;
                 }
                 out[(size_t)r * W + col] = v;
             }
@@ -53,6 +55,7 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
                 o[lane] = v;
             }
             for (int c = lane; c < D; c += 32) o[3 + c] = fs[c];
+            if (lane < W - 3 - D) o[3 + D + lane] = 0.f;
         }
     }
 }
@@ -74,25 +77,25 @@ struct RowMajorDst {
 using namespace pcnbr;
 
 extern "C" int pcnbr_group_f32(const float* p, const float* feat, const float* q, const int32_t* idx, int B,
-                               int N, int M, int K, int D, float rdiv, float* out, pcnbr_stream_t stream) {
-    if (!p || !q || !idx || !out || (D > 0 && !feat) || B <= 0 || N <= 0 || M <= 0 || K <= 0 || D < 0)
+                               int N, int M, int K, int D, float rdiv, float* out, int ldo, pcnbr_stream_t stream) {
+    if (!p || !q || !idx || !out || (D > 0 && !feat) || B <= 0 || N <= 0 || M <= 0 || K <= 0 || D < 0 || ldo < 3 + D || ldo > 3 + D + 32)
         return PCNBR_E_BADARG;
     const long rows = (long)B * M * K;
-    const int W = 3 + D;
+    const int W = ldo;
     const long per_warp = (W <= 32) ? 32 / W : 1;
     long blocks = (rows + per_warp * 8 - 1) / (per_warp * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
     // K5: 4 M K (3+D) written + 4 M K idx + 4 N (3+D) + 12 M read per cloud
     PCNBR_TIMED("group_fwd_kernel", (cudaStream_t)stream, (double)B * (4.0 * M * K * W + 4.0 * M * K + 4.0 * N * W + 12.0 * M), 0.0,
-                (group_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, rows, out)));
+                (group_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, rows, ldo, out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
-extern "C" int pcnbr_group_bwd_f32(const float* gout, const int32_t* offsets, const int32_t* perm, int B, int N,
+extern "C" int pcnbr_group_bwd_f32(const float* gout, int ldg, const int32_t* offsets, const int32_t* perm, int B, int N,
                                    int E, int D, float* gfeat, pcnbr_stream_t stream) {
-    if (!gout || !offsets || !perm || !gfeat || B <= 0 || N <= 0 || E <= 0 || D <= 0) return PCNBR_E_BADARG;
-    GroupBwdSrc src{gout, (long)E, 3 + D};
+    if (!gout || !offsets || !perm || !gfeat || B <= 0 || N <= 0 || E <= 0 || D <= 0 || ldg < 3 + D) return PCNBR_E_BADARG;
+    GroupBwdSrc src{gout, (long)E, ldg};
     RowMajorDst dst{gfeat, (long)N, D};
     // K7: 4 E D read + 4 E perm + 4 N offsets + 4 N D written per cloud
     PCNBR_TIMED("segsum_kernel<group_bwd>", (cudaStream_t)stream, (double)B * (4.0 * E * D + 4.0 * E + 4.0 * N + 4.0 * N * D), (double)B * E * D,

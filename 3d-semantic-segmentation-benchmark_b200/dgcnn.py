@@ -85,19 +85,18 @@ def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
     from .common import _batch_norm_rows
     mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
     conv = mods[0]
-    y = ops.linear_rows(rows, conv.weight.squeeze(-1), conv.bias)
-    i = 1
-    while i < len(mods):
-        m = mods[i]
+    w = conv.weight.squeeze(-1)
+    if len(mods) >= 3 and isinstance(mods[1], nn.modules.batchnorm._BatchNorm) and isinstance(mods[2], nn.LeakyReLU):
+        y = ops.linear_bn_act_rows(rows, w, conv.bias, mods[1], mods[2].negative_slope)
+        rest = mods[3:]
+    else:
+        y = ops.linear_rows(rows, w, conv.bias)
+        rest = mods[1:]
+    for m in rest:
         if isinstance(m, nn.modules.batchnorm._BatchNorm):
-            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU):
-                y = ops.batchnorm_act_rows(y, m, mods[i + 1].negative_slope)
-                i += 2
-                continue
             y = _batch_norm_rows(m, y.view(-1, y.shape[-1])).view(y.shape)
         else:
             y = m(y)
-        i += 1
     return y
 
 

@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused", "linear_rows", "batchnorm_act_rows",
+    "edge_features", "edgeconv_fused", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows",
 ]
 
 
@@ -200,39 +200,42 @@ def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 class _GroupFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, coords, features, centroids, nbr: NeighborIndex, rdiv: float):
+    def forward(ctx, coords, features, centroids, nbr: NeighborIndex, rdiv: float, pitch: int):
         B, N, _ = coords.shape
         M, K = nbr.idx.shape[1], nbr.idx.shape[2]
         D = features.shape[2]
-        out = torch.empty(B, M, K, 3 + D, dtype=torch.float32, device=coords.device)
+        out = torch.empty(B, M, K, pitch, dtype=torch.float32, device=coords.device)
         _lib.call("pcnbr_group_f32", coords.data_ptr(), features.data_ptr() if D else None, centroids.data_ptr(),
-                  nbr.idx.data_ptr(), B, N, M, K, D, float(rdiv), out.data_ptr(), _stream())
+                  nbr.idx.data_ptr(), B, N, M, K, D, float(rdiv), out.data_ptr(), pitch, _stream())
         ctx.nbr = nbr
-        ctx.dims = (B, N, M, K, D)
+        ctx.dims = (B, N, M, K, D, pitch)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        B, N, M, K, D = ctx.dims
+        B, N, M, K, D, pitch = ctx.dims
         if D == 0 or not ctx.needs_input_grad[1]:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         gout = _c(gout)
         offsets, perm = ctx.nbr.csr()
         gfeat = torch.empty(B, N, D, dtype=torch.float32, device=gout.device)
-        _lib.call("pcnbr_group_bwd_f32", gout.data_ptr(), offsets.data_ptr(), perm.data_ptr(), B, N, M * K, D,
+        _lib.call("pcnbr_group_bwd_f32", gout.data_ptr(), pitch, offsets.data_ptr(), perm.data_ptr(), B, N, M * K, D,
                   gfeat.data_ptr(), _stream())
-        return None, gfeat, None, None, None
+        return None, gfeat, None, None, None, None
 
 
-def group_points(coords, features, centroids, nbr: NeighborIndex, r_div: float | None):
+def group_points(coords, features, centroids, nbr: NeighborIndex, r_div: float | None, pad4: bool = False):
     """K5.  -> (B,M,K,3+D): [coords[idx] - centroid (optionally / r_div), features[idx]]
-    (models/utils/common.py:62-71).  Differentiable w.r.t. `features` only: the reference models never
-    need coordinate gradients, and asking for them raises."""
+    (models/utils/common.py:62-71).  pad4=True returns (B,M,K,W') with W' = 3+D rounded up to a multiple of 4 and zeros
+    in the extra columns: rows with a 16-byte pitch, which the tensor-core GEMM of the following 1x1 convolution reads
+    in place (the set-abstraction modules use it; `[..., :3+D]` is the reference tensor).  Differentiable w.r.t.
+    `features` only: the reference models never need coordinate gradients, and asking for them raises."""
     _check(coords, "coords"); _check(features, "features"); _check(centroids, "centroids")
     if coords.requires_grad or centroids.requires_grad:
         raise NotImplementedError("pcnbr: gradients w.r.t. coordinates are not implemented")
     rdiv = 0.0 if r_div is None else torch.tensor(float(r_div), dtype=torch.float32).item()
-    return _GroupFn.apply(_c(coords), _c(features), _c(centroids), nbr, rdiv)
+    W = 3 + features.shape[2]
+    return _GroupFn.apply(_c(coords), _c(features), _c(centroids), nbr, rdiv, (W + 3) // 4 * 4 if pad4 else W)
 
 
 # ----------------------------------------------------------------------------- K6 max-pool over neighbours
@@ -567,6 +570,74 @@ class _LinearRowsFn(torch.autograd.Function):
         dw = _gemm3x(gy, True, x, True, Cout, Cin, R) if ctx.needs_input_grad[1] else None         # gy^T . x, split along R
         db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
+
+
+class _LinearBnActFn(torch.autograd.Function):
+    """act(BatchNorm(x W^T + b)) over the rows of x as ONE autograd node: 3 tensor-core GEMMs (output, input gradient,
+    weight gradient) + the fused BatchNorm/activation row kernels.  The gradient of a bias that sits in front of a
+    BatchNorm needs no pass over the data: it is the column sum of dL/dh, which is identically 0 in training mode
+    (BatchNorm removes any per-channel shift) and gamma*rstd*sum(g') in eval mode."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope):
+        R, Cin = x.shape
+        C = w.shape[0]
+        dev = x.device
+        h = _gemm3x(x, False, w, False, R, C, Cin, b)
+        if training:
+            nblk = _lib.size("pcnbr_bn_blocks", R, C)
+            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+            _lib.call("pcnbr_bn_stats_f32", h.data_ptr(), R, C, partial.data_ptr(), _stream())
+            stats = _bn_finalize(partial, nblk, h, R, C, gamma, beta, eps, momentum, rm, rv, dev)
+        else:
+            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        y = torch.empty_like(h)
+        _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), _stream())
+        ctx.save_for_backward(x, w, h, stats)
+        ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, h, stats = ctx.saved_tensors
+        training, slope, has_b, has_gamma, has_beta = ctx.consts
+        R, Cin = x.shape
+        C = w.shape[0]
+        dev = x.device
+        gy = _c(gy)
+        nblk = _lib.size("pcnbr_bn_blocks", R, C)
+        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
+                  partial.data_ptr(), None, _stream())
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        coef = torch.empty(4, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
+                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+        dh = torch.empty_like(h)
+        _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
+                  dh.data_ptr(), _stream())
+        dx = _gemm3x(dh, False, w, True, R, Cin, C) if ctx.needs_input_grad[0] else None
+        dw = _gemm3x(dh, True, x, True, C, Cin, R) if ctx.needs_input_grad[1] else None
+        db = None
+        if has_b and ctx.needs_input_grad[2]:
+            db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
+        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None, None, None, None, None, None, None)
+
+
+def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float) -> torch.Tensor:
+    """act(bn(rows @ weight^T + bias)): one "Conv(kernel 1) -> BatchNorm -> ReLU / LeakyReLU" block of
+    models/utils/common.py:125-178 / models/dgcnn/dgcnn.py:95-126 on point-major rows (..., Cin) -> (..., Cout)."""
+    cin, cout = weight.shape[1], weight.shape[0]
+    nrows = rows.numel() // max(cin, 1)
+    fused = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
+             and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4 and _lib.size("pcnbr_bn_supported", nrows, cout))
+    if not fused:
+        return batchnorm_act_rows(linear_rows(rows, weight, bias), bn, negative_slope)
+    training, momentum, rm, rv = _bn_mode(bn)
+    y = _LinearBnActFn.apply(_c(rows).view(nrows, cin), _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
+                             float(bn.eps), float(negative_slope))
+    return y.view(*rows.shape[:-1], cout)
 
 
 _GEMM_LIBRARY = __import__("os").environ.get("PCNBR_GEMM_LIBRARY") is not None

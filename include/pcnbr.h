@@ -86,10 +86,12 @@ PCNBR_API int pcnbr_knn_tc_debug_f32(const float* x, int B, int F, int N, long s
                            pcnbr_stream_t stream);
 
 /* ---- K5 gather + centre-subtract (+ /r) + concat ------------------------ common.py:62-71
- * p (B,N,3), feat (B,N,D) (D may be 0), q (B,M,3), idx (B,M,K) -> out (B,M,K,3+D).
+ * p (B,N,3), feat (B,N,D) (D may be 0), q (B,M,3), idx (B,M,K) -> out (B,M,K,3+D) with row pitch ldo >= 3+D floats
+ * (ldo == 3+D: the reference layout; ldo = 3+D rounded up to 4 gives the 16-byte pitch the tensor-core GEMM reads in
+ * place -- the pad columns are written as zeros).
  * rdiv > 0: local coordinates are divided (true fp32 division) by rdiv (common.py:69). */
 PCNBR_API int pcnbr_group_f32(const float* p, const float* feat, const float* q, const int32_t* idx,
-                    int B, int N, int M, int K, int D, float rdiv, float* out, pcnbr_stream_t stream);
+                    int B, int N, int M, int K, int D, float rdiv, float* out, int ldo, pcnbr_stream_t stream);
 
 /* ---- K7 inverse index (CSR by source point) for the atomic-free scatter-add backward
  * idx (B,E) values in [0,N).  offsets (B,N+1): segment bounds; perm (B,E): positions e grouped
@@ -99,8 +101,8 @@ PCNBR_API int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t* 
                     void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
 /* Backward of K5 w.r.t. feat (autograd IndexBackward of common.py:65):
- * gout (B,M,K,3+D) -> gfeat (B,N,D) = sum over incoming (m,k) of gout[..., 3:], fixed order. */
-PCNBR_API int pcnbr_group_bwd_f32(const float* gout, const int32_t* offsets, const int32_t* perm,
+ * gout (B,M,K,*) with row pitch ldg >= 3+D -> gfeat (B,N,D) = sum over incoming (m,k) of gout[..., 3:3+D], fixed order. */
+PCNBR_API int pcnbr_group_bwd_f32(const float* gout, int ldg, const int32_t* offsets, const int32_t* perm,
                         int B, int N, int E, int D, float* gfeat, pcnbr_stream_t stream);
 
 /* ---- K6 grouped max-pool over K (+ argmax) -------------- common.py:85-86, dgcnn.py:76

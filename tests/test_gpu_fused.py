@@ -184,3 +184,45 @@ def test_batchnorm_act_rows_unsupported_width_uses_library(pkg, dev):
     y = pkg.ops.batchnorm_act_rows(x, bn, 0.2)
     ref = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(x.double(), None, None, bn.weight.double(), bn.bias.double(), True), 0.2)
     _close(y, ref, 1e-5)
+
+
+@pytest.mark.parametrize("R,Cin,Cout,slope,bias", [(16384, 12, 32, 0.0, True), (8192, 384, 1024, 0.2, False), (2048, 768, 256, 0.0, True)])
+@pytest.mark.parametrize("train", [True, False])
+def test_linear_bn_act_rows_matches_fp64(pkg, dev, R, Cin, Cout, slope, bias, train):
+    """ops.linear_bn_act_rows = one Conv(kernel 1) -> BatchNorm -> (Leaky)ReLU block (common.py:141-147,170-176,
+    dgcnn.py:95-126) as a single autograd node, against the float64 modules: output, input / weight / BatchNorm
+    gradients.  The conv bias gradient is exactly 0 in training mode (BatchNorm removes per-channel shifts; the fp64
+    value is ~1e-12 of the weight gradients) and gamma*rstd*sum(g') in eval mode."""
+    import copy
+    g = torch.Generator().manual_seed(R + Cin + Cout)
+    x = torch.randn(R, Cin, generator=g) * 0.5 + 0.2
+    lin = torch.nn.Linear(Cin, Cout, bias=bias)
+    bn = torch.nn.BatchNorm1d(Cout)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(Cout, generator=g)); bn.bias.copy_(torch.randn(Cout, generator=g) * 0.5)
+        bn.running_mean.copy_(torch.randn(Cout, generator=g) * 0.1); bn.running_var.copy_(torch.rand(Cout, generator=g) * 0.2 + 0.05)
+    lin64, bn64 = copy.deepcopy(lin).double(), copy.deepcopy(bn).double()
+    lind, bnd = copy.deepcopy(lin).to(dev), copy.deepcopy(bn).to(dev)
+    bn64.train(train); bnd.train(train)
+    with torch.no_grad():
+        pre = copy.deepcopy(bn64)(lin64(x.double()))
+    gy = torch.randn(R, Cout, generator=g) * (pre.abs() > 1e-3).float()
+    xd = x.to(dev).requires_grad_(True)
+    y = pkg.ops.linear_bn_act_rows(xd, lind.weight, lind.bias, bnd, slope)
+    y.backward(gy.to(dev))
+    x64 = x.double().requires_grad_(True)
+    y64 = torch.nn.functional.leaky_relu(bn64(lin64(x64)), slope)
+    y64.backward(gy.double())
+    _close(y, y64, 3e-5)
+    _close(xd.grad, x64.grad, 1e-4)
+    _close(lind.weight.grad, lin64.weight.grad, 1e-4)
+    _close(bnd.weight.grad, bn64.weight.grad, 1e-4)
+    _close(bnd.bias.grad, bn64.bias.grad, 1e-4)
+    _close(bnd.running_mean, bn64.running_mean, 1e-5)
+    _close(bnd.running_var, bn64.running_var, 1e-4)
+    if bias:
+        if train:
+            assert float(lind.bias.grad.abs().max()) == 0.0
+            assert float(lin64.bias.grad.abs().max()) < 1e-9 * float(lin64.weight.grad.abs().max())
+        else:
+            _close(lind.bias.grad, lin64.bias.grad, 1e-4)

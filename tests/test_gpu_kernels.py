@@ -120,6 +120,28 @@ def test_group_values_and_backward(pkg, dev, D):
     assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("D", [6, 64, 128, 29])
+def test_group_padded_rows_equal_reference_layout(pkg, dev, D):
+    """pad4=True (16-byte row pitch for the tensor-core GEMM that follows): the first 3+D columns are the reference
+    tensor bit for bit, the pad columns are zero, and the feature gradient is unchanged."""
+    B, N, M, K = 2, 400, 50, 16
+    pts, _, _ = O.s3dis_blocks(B, N, seed=D)
+    xyz = pts[:, :, :3].contiguous().to(dev)
+    feat = torch.randn(B, N, D, generator=_gen(D)).to(dev)
+    cen = xyz[:, :M].contiguous()
+    nbr = pkg.ops.NeighborIndex(pkg.ops.query_ball_point(0.3, K, xyz, cen), N)
+    f1, f2 = feat.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    ref = pkg.ops.group_points(xyz, f1, cen, nbr, 0.3)
+    pad = pkg.ops.group_points(xyz, f2, cen, nbr, 0.3, pad4=True)
+    W = 3 + D
+    assert pad.shape[-1] == (W + 3) // 4 * 4 and pad.is_contiguous()
+    assert torch.equal(pad[..., :W], ref) and bool((pad[..., W:] == 0).all())
+    w = torch.randn(pad.shape, generator=_gen(2)).to(dev)
+    (ref * w[..., :W]).sum().backward()
+    (pad * w).sum().backward()
+    assert torch.equal(f1.grad, f2.grad)
+
+
 def test_csr_is_sorted_inverse(pkg, dev):
     B, N, M, K = 2, 300, 150, 32
     idx = torch.randint(0, N, (B, M, K), generator=_gen(3), dtype=torch.int32)
