@@ -106,20 +106,20 @@ bn_stats_kernel(const float* __restrict__ x, long R, int C, int rows_per_block, 
 // Combine the block partials (fp64, ascending block order) into the BatchNorm constants
 //   stats (4,C) = { mean, rstd, gamma*rstd, beta }      and update the running statistics (momentum, unbiased variance).
 // nblk == 0: eval mode, mean/var come from running_mean / running_var.
-constexpr int BA_FS = 32;   // partial-row slices per channel in the finalize kernels (32 channels x 32 slices per CTA)
+// Finalize kernels: a CTA of 1024 threads owns BA_FC = 8 channels and cuts the partial rows into BA_FS = 128 slices
+// (few channels per CTA = many CTAs and a short dependent-load chain per thread: the kernel is pure latency).
+constexpr int BA_FC = 8, BA_FS = 128;
 
-__global__ void __launch_bounds__(32 * BA_FS)
-bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ shift, double count, int C,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
-                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ stats) {
-    __shared__ double a1[BA_FS][32], a2[BA_FS][32];
-    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cx;
-    double s1 = 0.0, s2 = 0.0;
+// sum over the partial rows of partial[:, 0, c] and partial[:, 1, c] in fp64; fixed order (slice-major tree); valid in
+// the threads with slice 0
+__device__ __forceinline__ void ba_finalize_sums(const float* __restrict__ partial, int nblk, int C, int c, int sy, int cx,
+                                                 double& s1, double& s2) {
+    __shared__ double a1[BA_FS][BA_FC], a2[BA_FS][BA_FC];
+    s1 = 0.0; s2 = 0.0;
     if (c < C) {
         const int per = (nblk + BA_FS - 1) / BA_FS;
         const int b0 = sy * per, b1 = min(nblk, b0 + per);
-#pragma unroll 8
+#pragma unroll 4
         for (int b = b0; b < b1; ++b) {
             s1 += (double)partial[(size_t)b * 2 * C + c];
             s2 += (double)partial[(size_t)b * 2 * C + C + c];
@@ -127,8 +127,32 @@ bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __r
     }
     a1[sy][cx] = s1; a2[sy][cx] = s2;
     __syncthreads();
+    if (sy < 8) {                                             // 8 x 16 slices
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { t1 += a1[sy * 16 + k][cx]; t2 += a2[sy * 16 + k][cx]; }
+        __syncthreads();
+        a1[sy][cx] = t1; a2[sy][cx] = t2;
+    } else {
+        __syncthreads();
+    }
+    __syncthreads();
+    if (sy == 0) {
+        s1 = 0.0; s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
+    }
+}
+
+__global__ void __launch_bounds__(BA_FC * BA_FS)
+bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ shift, double count, int C,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ stats) {
+    const int cx = threadIdx.x % BA_FC, sy = threadIdx.x / BA_FC;
+    const int c = blockIdx.x * BA_FC + cx;
+    double s1, s2;
+    ba_finalize_sums(partial, nblk, C, c, sy, cx, s1, s2);
     if (sy != 0 || c >= C) return;
-    for (int k = 1; k < BA_FS; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
     double mean, var;
     if (nblk > 0) {
         const double m1 = s1 / count;
@@ -231,26 +255,14 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__
 
 // dbeta = sum g', dgamma = sum g' xhat (fp64 over the blocks, fixed order);
 // coef (4,C) = { gr = gamma*rstd, gr*dbeta/count, gr*rstd*dgamma/count, mean }   (the two middle rows are 0 in eval mode)
-__global__ void __launch_bounds__(32 * BA_FS)
+__global__ void __launch_bounds__(BA_FC * BA_FS)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ stats, double count, int C,
                        int training, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-    __shared__ double a1[BA_FS][32], a2[BA_FS][32];
-    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cx;
-    double s1 = 0.0, s2 = 0.0;
-    if (c < C) {
-        const int per = (nblk + BA_FS - 1) / BA_FS;
-        const int b0 = sy * per, b1 = min(nblk, b0 + per);
-#pragma unroll 8
-        for (int b = b0; b < b1; ++b) {
-            s1 += (double)partial[(size_t)b * 2 * C + c];
-            s2 += (double)partial[(size_t)b * 2 * C + C + c];
-        }
-    }
-    a1[sy][cx] = s1; a2[sy][cx] = s2;
-    __syncthreads();
+    const int cx = threadIdx.x % BA_FC, sy = threadIdx.x / BA_FC;
+    const int c = blockIdx.x * BA_FC + cx;
+    double s1, s2;
+    ba_finalize_sums(partial, nblk, C, c, sy, cx, s1, s2);
     if (sy != 0 || c >= C) return;
-    for (int k = 1; k < BA_FS; ++k) { s1 += a1[k][cx]; s2 += a2[k][cx]; }
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
     const double gr = (double)stats[2 * C + c], rstd = (double)stats[C + c];
@@ -357,7 +369,7 @@ extern "C" int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float
     if (nblk == 0 && (!running_mean || !running_var)) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     PCNBR_TIMED("bn_finalize_kernel", s, 8.0 * nblk * C + 32.0 * C, 4.0 * nblk * C,
-                (bn_finalize_kernel<<<(C + 31) / 32, 32 * BA_FS, 0, s>>>(partial, nblk, shift, count, C, gamma, beta, eps, momentum,
+                (bn_finalize_kernel<<<(C + BA_FC - 1) / BA_FC, BA_FC * BA_FS, 0, s>>>(partial, nblk, shift, count, C, gamma, beta, eps, momentum,
                                                                   running_mean, running_var, stats)));
     PCNBR_CHECK_LAUNCH();
     return 0;
@@ -398,7 +410,7 @@ extern "C" int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const f
     if (!partial || !stats || !dgamma || !dbeta || !coef || C <= 0 || nblk <= 0 || count <= 0.0) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     PCNBR_TIMED("bn_bwd_finalize_kernel", s, 8.0 * nblk * C + 40.0 * C, 4.0 * nblk * C,
-                (bn_bwd_finalize_kernel<<<(C + 31) / 32, 32 * BA_FS, 0, s>>>(partial, nblk, stats, count, C, training, dgamma, dbeta, coef)));
+                (bn_bwd_finalize_kernel<<<(C + BA_FC - 1) / BA_FC, BA_FC * BA_FS, 0, s>>>(partial, nblk, stats, count, C, training, dgamma, dbeta, coef)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

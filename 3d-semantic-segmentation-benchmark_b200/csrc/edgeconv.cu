@@ -159,13 +159,13 @@ __device__ __forceinline__ void edgeconv_bwd_accumulate(const float* __restrict_
                                                         float (&t1)[VEC], float (&t2)[VEC]) {
     constexpr int O = 32 * VEC;
     const int c0 = lane * VEC;
-    auto edge = [&](int n, int j) {
+    auto load = [&](int n, float (&g)[VEC], int (&av)[VEC], float (&qv)[VEC]) {
         const size_t r = rowbase + n;
-        float g[VEC], qv[VEC];
-        int av[VEC];
         ec_ld<VEC>(gs + r * O + c0, g);
         ec_ld_u8<VEC>(arg + r * O + c0, av);
         ec_ld<VEC>(PQ + r * 2 * O + O + c0, qv);
+    };
+    auto add = [&](int j, const float (&g)[VEC], const int (&av)[VEC], const float (&qv)[VEC]) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             t1[v] += (av[v] == j) ? g[v] : 0.f;
@@ -176,8 +176,25 @@ __device__ __forceinline__ void edgeconv_bwd_accumulate(const float* __restrict_
         const int e = (t0 + lane < end) ? pm[t0 + lane] : 0;
         const int nl = e / K, jl = e - nl * K;
         const int cnt = min(32, end - t0);
-#pragma unroll 4
-        for (int l = 0; l < cnt; ++l) edge(__shfl_sync(PCNBR_FULL, nl, l), __shfl_sync(PCNBR_FULL, jl, l));
+        int l = 0;
+        for (; l + 4 <= cnt; l += 4) {                          // four incoming edges (12 row loads) in flight
+            float g0[VEC], g1[VEC], g2[VEC], g3[VEC], q0[VEC], q1[VEC], q2[VEC], q3[VEC];
+            int a0[VEC], a1[VEC], a2[VEC], a3[VEC];
+            load(__shfl_sync(PCNBR_FULL, nl, l), g0, a0, q0);
+            load(__shfl_sync(PCNBR_FULL, nl, l + 1), g1, a1, q1);
+            load(__shfl_sync(PCNBR_FULL, nl, l + 2), g2, a2, q2);
+            load(__shfl_sync(PCNBR_FULL, nl, l + 3), g3, a3, q3);
+            add(__shfl_sync(PCNBR_FULL, jl, l), g0, a0, q0);
+            add(__shfl_sync(PCNBR_FULL, jl, l + 1), g1, a1, q1);
+            add(__shfl_sync(PCNBR_FULL, jl, l + 2), g2, a2, q2);
+            add(__shfl_sync(PCNBR_FULL, jl, l + 3), g3, a3, q3);
+        }
+        for (; l < cnt; ++l) {
+            float g0[VEC], q0[VEC];
+            int a0[VEC];
+            load(__shfl_sync(PCNBR_FULL, nl, l), g0, a0, q0);
+            add(__shfl_sync(PCNBR_FULL, jl, l), g0, a0, q0);
+        }
     }
 }
 

@@ -36,6 +36,8 @@ select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int 
     WarpList<NSLOT> list;
     list.init();
     u64 thr = PCNBR_KEY_MAX;
+    bool full = false;                                       // the list holds K real entries (thr is a real key)
+    float thr_f = 0.f;                                       // distance of the K-th entry once full
 
     for (int t0 = 0; t0 < N; t0 += SEL_TILE) {
         const int tn = min(SEL_TILE, N - t0);
@@ -47,24 +49,39 @@ select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int 
         }
         __syncthreads();
         if (!active) continue;
-        for (int c0 = 0; c0 < tn; c0 += 32) {
-            const int j = c0 + lane;
-            u64 key = PCNBR_KEY_MAX;
-            if (j < tn) {
-                float d2 = d2_direct(sx[j], sy[j], sz[j], qx, qy, qz);
+        // 128 points per step (4 per lane).  Hot path = 8 flops + one float compare per point: a candidate (index j,
+        // larger than every index already in the list) beats the current K-th entry iff its distance is STRICTLY
+        // smaller, so the 64-bit (key,index) order is only materialised for the rare survivors.
+        for (int c0 = 0; c0 < tn; c0 += 128) {
+            float d[4];
+            bool hit = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = c0 + u * 32 + lane;
+                const int jc = min(j, tn - 1);
+                float d2 = d2_direct(sx[jc], sy[jc], sz[jc], qx, qy, qz);
                 if (RADIUS && !(d2 <= r2)) d2 = __int_as_float(0x7f800000);   // common.py:58-59
-                key = pack_key(f2ord(d2), (uint32_t)(t0 + j));
+                d[u] = d2;
+                hit |= (j < tn) && (!full || d2 < thr_f);
             }
-            uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
-            while (pass) {
-                const int src = __ffs(pass) - 1;
-                pass &= pass - 1;
-                const u64 cand = shfl64(key, src);
-                if (cand < thr) {
-                    list.insert(cand, lane);
-                    thr = list.at(K - 1);
+            if (!__any_sync(PCNBR_FULL, hit)) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = c0 + u * 32 + lane;
+                const u64 key = (j < tn) ? pack_key(f2ord(d[u]), (uint32_t)(t0 + j)) : PCNBR_KEY_MAX;
+                uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
+                while (pass) {
+                    const int src = __ffs(pass) - 1;
+                    pass &= pass - 1;
+                    const u64 cand = shfl64(key, src);
+                    if (cand < thr) {
+                        list.insert(cand, lane);
+                        thr = list.at(K - 1);
+                    }
                 }
             }
+            full = thr != PCNBR_KEY_MAX;
+            thr_f = ord2f((uint32_t)(thr >> 32));
         }
     }
     if (!active) return;
