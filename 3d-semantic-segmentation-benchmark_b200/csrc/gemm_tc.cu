@@ -16,8 +16,12 @@
 //   * both operands may be K-major (row-major (rows, K)) or MN-major (row-major (K, rows)): the input-gradient GEMM
 //     reads the weight as stored and the weight-gradient GEMM reads the two activation matrices as stored --
 //     no transposed copies (tcgen05 supports MN-major TF32 operands through the shared-memory descriptor).
-// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (tcgen05.ld, + bias, 128-byte row
-// stores) double-buffered against the next tile's MMAs, warps 6-13 converters.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue, warps 6-13 converters.
+// Epilogue: tcgen05.ld a 128 x 32 slab (+ bias), write it into a 128-byte-swizzled shared-memory staging buffer and
+// hand it to a TMA store (cp.async.bulk.tensor, clipped at the matrix edge by the tensor map): full-line writes whatever
+// the row pitch, and the accumulator (one of 512/BN TMEM buffers, up to 8) is released as soon as it is in registers.
+// A lane-per-row store pattern touched 32 cache lines per instruction and made the narrow layers (K = 12..64, where the
+// output IS the traffic) 5x slower than their HBM time.
 // Weight gradients (M, N small, K = number of points) are split along K over the CTAs; the partial tiles are summed
 // in a fixed order by a second kernel (deterministic, no atomics).
 #include "common.cuh"
@@ -56,6 +60,11 @@ __device__ __forceinline__ void gm_tma_load_2d(uint32_t dst, const CUtensorMap* 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(gm_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void gm_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void gm_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 // kind::tf32, D = fp32, M = 128, N = BN; A / B major-ness in bits 15 / 16 (cute::UMMA::InstrDescriptor)
 template <int BN, bool A_MN, bool B_MN>
 __device__ __forceinline__ void gm_umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, bool accumulate) {
@@ -117,18 +126,20 @@ __device__ __forceinline__ float gm_residual(float v) {
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-              int M, int N, int K, int splits, const float* __restrict__ bias, float* __restrict__ out, long ldc) {
+              const __grid_constant__ CUtensorMap tm_c, int M, int N, int K, int splits, const float* __restrict__ bias) {
     extern __shared__ uint8_t gm_smem_raw[];
     uint8_t* smem = gm_smem_raw + ((1024u - (gm_smem_u32(gm_smem_raw) & 1023u)) & 1023u);
     constexpr uint32_t A_BYTES = GM_SLAB, B_BYTES = (uint32_t)BN * 128u;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;       // A | A_lo | B | B_lo
-    uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    constexpr int NBUF = (512 / BN) < 8 ? (512 / BN) : 8;             // TMEM accumulators of BN columns
+    uint8_t* cstage = smem + STAGES * STAGE_BYTES;                    // 2 x (128 rows x 128 B), swizzled: TMA-store staging
+    uint64_t* bars = (uint64_t*)(cstage + 2 * GM_SLAB);
     uint64_t* full = bars;                                            // [STAGES]  TMA landed          (count 1 + tx)
     uint64_t* conv = bars + STAGES;                                   // [STAGES]  residual tiles ready (count GM_CONV_WARPS)
     uint64_t* empty = bars + 2 * STAGES;                              // [STAGES]  MMAs retired        (count 1)
-    uint64_t* tmem_full = bars + 3 * STAGES;                          // [2]
-    uint64_t* tmem_empty = bars + 3 * STAGES + 2;                     // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
+    uint64_t* tmem_full = bars + 3 * STAGES;                          // [NBUF]
+    uint64_t* tmem_empty = bars + 3 * STAGES + NBUF;                  // [NBUF]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MT = (M + GM_BM - 1) / GM_BM, NT = (N + BN - 1) / BN;
@@ -139,8 +150,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
         for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&conv[i], GM_CONV_WARPS); gm_mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { gm_mbar_init(&tmem_full[i], 1); gm_mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < NBUF; ++i) { gm_mbar_init(&tmem_full[i], 1); gm_mbar_init(&tmem_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -193,10 +205,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
             const int sp = unit / (MT * NT);
             const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
-            const uint32_t buf = tile & 1, tphase = (tile >> 1) & 1;
+            const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
             gm_mbar_wait(&tmem_empty[buf], tphase ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d = tmem_base + buf * 256;
+            const uint32_t d = tmem_base + buf * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
                 const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
                 const uint64_t ah = gm_desc<A_MN>(st), al = gm_desc<A_MN>(st + A_BYTES);
@@ -230,45 +242,47 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
         const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
-        uint32_t tile = 0;
+        const int rloc = quarter * 32 + lane;                         // row of the tile owned by this thread
+        const bool issuer = (warp == 2 && lane == 0);                 // issues and tracks the TMA stores
+        uint32_t tile = 0, slab = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
             const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
-            const uint32_t buf = tile & 1, tphase = (tile >> 1) & 1;
-            const long row = (long)mt * GM_BM + quarter * 32 + lane;
-            float* __restrict__ dst = out + ((long)sp * M + row) * ldc + (long)nt * BN;
+            const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
             const int ncols = min(BN, N - nt * BN);
-            const bool vec = (ldc % 4 == 0) && ((((uintptr_t)out) & 15) == 0);
+            const int nq = (ncols + 31) / 32;
             gm_mbar_wait(&tmem_full[buf], tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int q = 0; q < BN / 32; ++q) {
-                if (q * 32 >= ncols) break;                            // warp-uniform
+            for (int q = 0; q < nq; ++q, ++slab) {
                 uint32_t r[32];
-                gm_tmem_ld32(tmem_base + tlane + buf * 256 + q * 32, r);
+                gm_tmem_ld32(tmem_base + tlane + buf * BN + q * 32, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-                    if (vec && q * 32 + 32 <= ncols) {
+                if (q == nq - 1) {                                    // accumulator fully in registers: release it
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) gm_mbar_arrive(&tmem_empty[buf]);
+                }
+                if (bias) {
+                    const int c0 = nt * BN + q * 32;
 #pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
-                            float4 v = make_float4(__uint_as_float(r[4 * i4]), __uint_as_float(r[4 * i4 + 1]),
-                                                   __uint_as_float(r[4 * i4 + 2]), __uint_as_float(r[4 * i4 + 3]));
-                            if (bias) {
-                                const float4 bv = *reinterpret_cast<const float4*>(bias + nt * BN + q * 32 + 4 * i4);
-                                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                            }
-                            *reinterpret_cast<float4*>(dst + q * 32 + 4 * i4) = v;
-                        }
-                    } else {
-                        for (int i = 0; i < 32; ++i)
-                            if (q * 32 + i < ncols)
-                                dst[q * 32 + i] = __uint_as_float(r[i]) + (bias ? bias[nt * BN + q * 32 + i] : 0.f);
-                    }
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i < N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bias + c0 + i));
+                }
+                uint8_t* sb = cstage + (slab & 1) * GM_SLAB;
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read sb is done
+                gm_epi_barrier();
+                uint8_t* rowp = sb + rloc * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(rowp + ((c ^ (rloc & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                gm_epi_barrier();
+                if (issuer) {
+                    gm_tma_store_3d(&tm_c, gm_smem_u32(sb), nt * BN + q * 32, mt * GM_BM, sp);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) gm_mbar_arrive(&tmem_empty[buf]);
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                 // all stores landed before exit
     } else {
         // ===================================================== converters: residual tiles A_lo, B_lo from the raw tiles
         const int t = threadIdx.x - 192;                              // 0 .. 32*GM_CONV_WARPS-1
@@ -351,12 +365,26 @@ static int gm_make_map(CUtensorMap* map, const float* base, long inner, long out
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+// C as a (N, M, splits) fp32 tensor (row pitch ldc, split pitch M * ldc), box = 32 floats x 128 rows, 128-byte swizzle
+static int gm_make_map_c(CUtensorMap* map, float* base, long M, long N, long ldc, int splits) {
+    GmEncodeFn enc = gm_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)M * (cuuint64_t)ldc * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 static int gm_tile_n(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)); }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits, const float* bias,
-                     float* out, long ldc, cudaStream_t s) {
-    const size_t smem = (size_t)STAGES * (2 * GM_SLAB + 2 * (size_t)BN * 128) + 64 * 8 + 1024;
+static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
+                     const float* bias, cudaStream_t s) {
+    const size_t smem = (size_t)STAGES * (2 * GM_SLAB + 2 * (size_t)BN * 128) + 2 * GM_SLAB + 64 * 8 + 1024;
     cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
@@ -366,19 +394,19 @@ static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
     const int grid = units < sms ? units : sms;
     // algorithmic work: 2 M N K flop counted once (the kernel issues 3x); operands once + result bytes
     PCNBR_TIMED("gemm3x_kernel", s, 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), 2.0 * M * (double)N * K,
-                (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, tb, M, N, K, splits, bias, out, ldc)));
+                (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, tb, tc, M, N, K, splits, bias)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
 template <bool A_MN, bool B_MN>
-static int gm_dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits, const float* bias,
-                       float* out, long ldc, cudaStream_t s) {
-    switch (gm_tile_n(N)) {
-        case 256: return gm_launch<256, 2, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
-        case 128: return gm_launch<128, 3, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
-        case 64:  return gm_launch<64, 4, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
-        default:  return gm_launch<32, 5, A_MN, B_MN>(ta, tb, M, N, K, splits, bias, out, ldc, s);
+static int gm_dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
+                       const float* bias, cudaStream_t s) {
+    switch (gm_tile_n(N)) {                                               // stages: what fits beside the 32 KB store staging
+        case 256: return gm_launch<256, 2, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
+        case 128: return gm_launch<128, 3, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
+        case 64:  return gm_launch<64, 4, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
+        default:  return gm_launch<32, 4, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
     }
 }
 
@@ -433,8 +461,12 @@ extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float*
     if (rc) return rc;
     float* out = splits > 1 ? (float*)ws : C;
     const float* b = splits > 1 ? nullptr : bias;
-    if (a_mn) rc = b_mn ? gm_dispatch<true, true>(ta, tb, M, N, K, splits, b, out, N, s) : gm_dispatch<true, false>(ta, tb, M, N, K, splits, b, out, N, s);
-    else      rc = b_mn ? gm_dispatch<false, true>(ta, tb, M, N, K, splits, b, out, N, s) : gm_dispatch<false, false>(ta, tb, M, N, K, splits, b, out, N, s);
+    if (((uintptr_t)out & 15) || (N % 4)) return PCNBR_E_BADARG;          // TMA store: 16-byte base and row pitch
+    CUtensorMap tc;
+    rc = gm_make_map_c(&tc, out, M, N, N, splits);
+    if (rc) return rc;
+    if (a_mn) rc = b_mn ? gm_dispatch<true, true>(ta, tb, tc, M, N, K, splits, b, s) : gm_dispatch<true, false>(ta, tb, tc, M, N, K, splits, b, s);
+    else      rc = b_mn ? gm_dispatch<false, true>(ta, tb, tc, M, N, K, splits, b, s) : gm_dispatch<false, false>(ta, tb, tc, M, N, K, splits, b, s);
     if (rc) return rc;
     if (splits > 1) {
         const long n = (long)M * N;
