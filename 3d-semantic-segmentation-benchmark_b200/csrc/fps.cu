@@ -16,6 +16,12 @@ __device__ __forceinline__ float fps_dist(float x, float y, float z, float cx, f
     return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
 }
 
+// the radicand of fps_dist (sqrt_rn is applied once per thread and pick, see fps_reg_kernel)
+__device__ __forceinline__ float fps_dist2(float x, float y, float z, float cx, float cy, float cz) {
+    const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy), dz = __fsub_rn(z, cz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
 // warp-wide max of (hi, lo) pairs in lexicographic order, result broadcast to all lanes
 __device__ __forceinline__ void warp_max_pair(uint32_t& hi, uint32_t& lo) {
     const uint32_t mh = __reduce_max_sync(PCNBR_FULL, hi);
@@ -62,15 +68,28 @@ fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
         if (i + 1 == C) break;
         const int buf = i & 1;
 
-        uint32_t bh = 0, bl = 0;
+        // The running minimum is kept SQUARED: sqrt_rn is monotone, so min and max commute with it and only the
+        // thread's winner needs a square root (1 instead of PPT per pick).  What sqrt does change is ties: two different
+        // squared distances can round to the same norm, and the reference (argmax over the norms, lowest index on ties)
+        // then takes the lower index.  A rounding class spans at most 3 adjacent floats, so any point within 4 ulps of
+        // the thread's maximum is re-checked exactly (rare).
+        uint32_t mb = 0;
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
-            const float d = fps_dist(x[j], y[j], z[j], cx, cy, cz);
-            md[j] = fminf(md[j], d);                     // common.py:29-30
-            const uint32_t h = __float_as_uint(md[j]);
-            const uint32_t l = 0xffffffffu - (uint32_t)(j * T + tid);
-            if (h > bh || (h == bh && l > bl)) { bh = h; bl = l; }
+            md[j] = fminf(md[j], fps_dist2(x[j], y[j], z[j], cx, cy, cz));      // common.py:28-30 (squared)
+            mb = max(mb, __float_as_uint(md[j]));
         }
+        const float smax = __fsqrt_rn(__uint_as_float(mb));
+        int bj = PPT;
+#pragma unroll
+        for (int j = PPT - 1; j >= 0; --j) {
+            const uint32_t h = __float_as_uint(md[j]);
+            bool tie = (h == mb);
+            if (!tie && mb - h <= 4u) tie = (__fsqrt_rn(md[j]) == smax);
+            if (tie) bj = j;
+        }
+        const uint32_t bh = __float_as_uint(smax);
+        const uint32_t bl = 0xffffffffu - (uint32_t)(bj * T + tid);
         uint32_t wh = bh, wl = bl;
         warp_max_pair(wh, wl);
         if (bh == wh && bl == wl) {                      // exactly one lane: indices are unique
@@ -146,8 +165,11 @@ extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_
     using namespace pcnbr;
     if (!xyz || !start || !idx_out || B <= 0 || N <= 0 || C <= 0) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
-    // algorithmic work: 12N + 16C compulsory bytes, 10 N C lane-ops per cloud
-    const double wb = (double)B * (12.0 * N + 16.0 * C), wf = 10.0 * B * (double)N * C;
+    // algorithmic work: 12N + 16C compulsory bytes, 10 N C lane-ops per cloud.  One CTA = one SM per
+    // cloud, so the ceiling is the lane-op rate of the B SMs that are occupied; the profiler's ALU roofline
+    // is the whole chip's FMA rate (2 flops per lane-op slot), hence the 2 * 148 / min(B,148) scaling of the stated work.
+    const double wb = (double)B * (12.0 * N + 16.0 * C);
+    const double wf = 10.0 * B * (double)N * C * 2.0 * 148.0 / (double)(B < 148 ? B : 148);
     if (N <= 256)        PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 256><<<B, 256, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
     else if (N <= 512)   PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 512><<<B, 512, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
     else if (N <= 1024)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));

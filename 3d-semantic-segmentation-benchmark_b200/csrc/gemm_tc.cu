@@ -321,13 +321,31 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     }
 }
 
-// out[i] = sum_s part[s][i] in ascending s (fixed order)
+// out[i] = sum_s part[s][i]: the splits are cut into 8 contiguous groups, one thread per (element, group) sums its group
+// in ascending s, the 8 group sums are added in ascending group order -- a fixed summation tree (deterministic, no
+// atomics) with 8 independent load chains per element instead of one serial chain of `splits` dependent L2 round trips.
 __global__ void __launch_bounds__(256)
 gemm_reduce_kernel(const float* __restrict__ part, long n, int splits, float* __restrict__ out) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        float a = part[i];
-        for (int s = 1; s < splits; ++s) a = __fadd_rn(a, part[(long)s * n + i]);
-        out[i] = a;
+    __shared__ float red[8][32];
+    const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int per = (splits + 7) / 8;
+    const int s0 = grp * per, s1 = min(splits, s0 + per);
+    for (long base = (long)blockIdx.x * 32; base < n; base += (long)gridDim.x * 32) {
+        const long i = base + e;
+        float a = 0.f;
+        if (i < n) {
+#pragma unroll 4
+            for (int s = s0; s < s1; ++s) a = __fadd_rn(a, part[(long)s * n + i]);
+        }
+        red[grp][e] = a;
+        __syncthreads();
+        if (grp == 0 && i < n) {
+            float t = red[0][e];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) t = __fadd_rn(t, red[k][e]);
+            out[i] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -379,7 +397,18 @@ static int gm_make_map_c(CUtensorMap* map, float* base, long M, long N, long ldc
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-static int gm_tile_n(int N) { return N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)); }
+// Tile width: the widest BN <= N (rounded up) that still gives every SM at least two work units -- narrower tiles mean
+// more units and a deeper smem ring (more bytes in flight per SM), which is what the many small, latency-bound layer
+// GEMMs need; the big tensor-bound ones (>= 296 units at BN = 256) keep the widest tile and its operand reuse.
+// (Long-K GEMMs -- the weight gradients -- get their units from split-K instead and keep the widest tile.)
+static int gm_tile_n(int M, int N, int K) {
+    const int widest = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+    if (K >= 64 * GM_BK) return widest;
+    const long mt = (M + GM_BM - 1) / GM_BM;
+    int bn = widest;
+    while (bn > 64 && mt * ((N + bn - 1) / bn) < 2 * 148) bn >>= 1;
+    return bn;
+}
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
@@ -402,7 +431,7 @@ static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 template <bool A_MN, bool B_MN>
 static int gm_dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
                        const float* bias, cudaStream_t s) {
-    switch (gm_tile_n(N)) {                                               // stages: what fits beside the 32 KB store staging
+    switch (gm_tile_n(M, N, K)) {                                            // stages: what fits beside the 32 KB store staging
         case 256: return gm_launch<256, 2, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
         case 128: return gm_launch<128, 3, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
         case 64:  return gm_launch<64, 4, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
@@ -417,7 +446,7 @@ using namespace pcnbr;
 extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
     // Split K when the output has too few tiles to fill the chip (weight gradients: K = number of points).
     // Cost model: waves of work units over the SMs x K blocks per unit; the smallest split count that minimises it.
-    const int bn = gm_tile_n(N);
+    const int bn = gm_tile_n(M, N, K);
     const long tiles = (long)((M + GM_BM - 1) / GM_BM) * ((N + bn - 1) / bn);
     const int kb = (K + GM_BK - 1) / GM_BK;
     if (tiles >= 148 || kb < 64) return 1;
@@ -454,7 +483,7 @@ extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float*
         if ((kb + per - 1) / per != splits) return PCNBR_E_BADARG;        // use pcnbr_gemm3x_splits(): no empty split
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const int bn = gm_tile_n(N);
+    const int bn = gm_tile_n(M, N, K);
     CUtensorMap ta, tb;
     int rc = a_mn ? gm_make_map(&ta, A, M, K, lda, 32, true) : gm_make_map(&ta, A, K, M, lda, 128, false);
     if (!rc) rc = b_mn ? gm_make_map(&tb, B, N, K, ldb, 32, true) : gm_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128, false);
@@ -470,7 +499,7 @@ extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float*
     if (rc) return rc;
     if (splits > 1) {
         const long n = (long)M * N;
-        const int grid = (int)((n + 255) / 256 < 148L * 8 ? (n + 255) / 256 : 148L * 8);
+        const int grid = (int)((n + 31) / 32 < 148L * 8 ? (n + 31) / 32 : 148L * 8);
         PCNBR_TIMED("gemm_reduce_kernel", s, 4.0 * n * (splits + 1), (double)n * splits,
                     (gemm_reduce_kernel<<<grid, 256, 0, s>>>((const float*)ws, n, splits, C)));
         PCNBR_CHECK_LAUNCH();

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="BASELINE shapes only (no N sweep)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--md", default="")
+    ap.add_argument("--only", default="", help="comma-separated op groups: pointnet, dgcnn, gemm (default all)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_kernels.py: no CUDA device; the hot path has no CPU fallback")
@@ -59,16 +60,16 @@ def main():
         lib.prof_enable(False)
         for name, d in kernels.items():
             us = 1e3 * d["ms"] / d["calls"]
-            tensor = name in bench.TENSOR_KERNELS
-            ach = (d["flops"] / 1e12 if tensor else d["bytes"] / 1e9) / (d["ms"] / 1e3)
-            peak = peaks["tf32_tflops"] if tensor else peaks["hbm_gbs"]
+            b = bench.kernel_bound(name, d, peaks)
             row = {"op": op, "shape": shape, "kernel": name, "us_per_launch": round(us, 2), "launches_per_call": d["calls"] // args.iters,
-                   "bound": "tensor" if tensor else "hbm", "achieved": round(ach, 2), "unit": "TFLOP/s" if tensor else "GB/s",
-                   "frac": round(ach / peak, 4), "gflop_per_s": round(d["flops"] / 1e9 / (d["ms"] / 1e3), 1)}
+                   "bound": b["bound"], "achieved": round(b["achieved"], 2), "unit": b["unit"],
+                   "frac": round(b["frac"], 4), "gflop_per_s": round(d["flops"] / 1e9 / (d["ms"] / 1e3), 1)}
             rows.append(row)
             print(json.dumps(row), flush=True)
 
     g = torch.Generator().manual_seed(0)
+    only = set(filter(None, args.only.split(",")))
+    want = lambda grp: not only or grp in only
 
     def cloud(B, N):
         pts, _, _ = pkg.synthetic.s3dis_blocks(B, N, seed=N % 997)
@@ -80,7 +81,7 @@ def main():
     # ---- PointNet++ SSG shapes at B=32 (configs[0]/[2]) and the N sweep (configs[4])
     pn_levels = [(4096, 1024, 0.1, 32, 6, 64), (1024, 256, 0.2, 32, 64, 128), (256, 64, 0.4, 32, 128, 256), (64, 16, 0.8, 32, 256, 512)]
     sweep_n = [] if args.quick else [8192, 16384, 32768, 65536, 100000]
-    for (N, C, r, K, D, O) in pn_levels + [(n, 1024, 0.1, 32, 6, 64) for n in sweep_n]:
+    for (N, C, r, K, D, O) in (pn_levels + [(n, 1024, 0.1, 32, 6, 64) for n in sweep_n]) if want("pointnet") else []:
         B = 32 if N <= 4096 else max(1, min(8, (1 << 18) // N))
         xyz = cloud(B, N)
         f = feats(B, N, D).requires_grad_(True)
@@ -103,7 +104,8 @@ def main():
         del xyz, f, conv_out, coarse
 
     # ---- DGCNN shapes at B=16, k=20 (configs[1]) and the sweep
-    for (N, F, k) in [(4096, 3, 20), (4096, 64, 20)] + [(n, 64, kk) for n in sweep_n[:4] for kk in (20,)] + ([] if args.quick else [(4096, 64, 16), (4096, 64, 32), (4096, 32, 20)]):
+    dg_shapes = [(4096, 3, 20), (4096, 64, 20)] + [(n, 64, kk) for n in sweep_n[:4] for kk in (20,)] + ([] if args.quick else [(4096, 64, 16), (4096, 64, 32), (4096, 32, 20)])
+    for (N, F, k) in dg_shapes if want("dgcnn") else []:
         B = 16 if N <= 4096 else max(1, min(8, (1 << 16) // N))
         xt = feats(B, N, F).requires_grad_(True)
         sh = f"B={B} N={N} F={F} k={k}"
@@ -117,6 +119,21 @@ def main():
             PQ = feats(B, N, 128).requires_grad_(True)
             run("edgeconv_fused(+bwd)", sh + " O=64", lambda: ops.edgeconv_fused(PQ, nbr, bn, 0.2), bwd=True)
         del xt
+
+    # ---- the 1x1-convolution GEMMs of both models (rows x Cin -> Cout): output, input-gradient and weight-gradient GEMM
+    gemm_shapes = [(32 * 1024 * 32, 12, 32), (32 * 1024 * 32, 32, 32), (32 * 1024 * 32, 32, 64),          # PointNet++ SA1, B=32
+                   (32 * 256 * 32, 68, 64), (32 * 256 * 32, 64, 128), (32 * 64 * 32, 132, 128), (32 * 64 * 32, 128, 256),
+                   (32 * 16 * 32, 260, 256), (32 * 16 * 32, 256, 512), (32 * 1024, 320, 256), (32 * 4096, 128, 128),
+                   (16 * 4096, 64, 128), (16 * 4096, 64, 256), (16 * 4096, 384, 1024), (16 * 4096, 1408, 512), (16 * 4096, 512, 256)]   # DGCNN, B=16
+    for (R, Cin, Cout) in gemm_shapes if want("gemm") else []:
+        x = torch.randn(R, Cin, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin, generator=g) / Cin ** 0.5).to(dev)
+        gy = torch.randn(R, Cout, generator=g).to(dev)
+        sh = f"R={R} Cin={Cin} Cout={Cout}"
+        run("conv1x1 y=xW^T", sh, lambda: ops._gemm3x(x, False, w, False, R, Cout, Cin))
+        run("conv1x1 dx=gyW", sh, lambda: ops._gemm3x(gy, False, w, True, R, Cin, Cout))
+        run("conv1x1 dW=gy^Tx", sh, lambda: ops._gemm3x(gy, True, x, True, Cout, Cin, R))
+        del x, w, gy
 
     md = ["| op | shape | kernel | µs/launch | algorithmic | roofline | frac |", "|---|---|---|---:|---:|---|---:|"]
     for r in rows:
