@@ -189,7 +189,7 @@ def ncu_traffic(kernel):
     if not os.path.exists(p):
         return None
     ent = json.load(open(p)).get(kernel)
-    return ent.get("dram_bytes_per_launch") if ent else None
+    return ent if ent else None
 
 
 # kernels whose stated flops are CUDA-core work (lane-ops / flops on the FP32 pipe): the roofline that can bind them
@@ -225,7 +225,10 @@ def roofline_for(kernels, peaks):
     name, d = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     b = kernel_bound(name, d, peaks)
     out = {"kernel": name, "bound": b["bound"], "achieved": b["achieved"], "peak": b["peak"], "unit": b["unit"], "frac": b["frac"],
-           "traffic": ncu_traffic(name), "avg_launch_ms": d["ms"] / d["calls"], "calls": d["calls"], "peak_source": peaks["source"],
+           "traffic": (ncu_traffic(name) or {}).get("dram_bytes_per_launch"),
+           "traffic_shape": (ncu_traffic(name) or {}).get("shape"),
+           "traffic_algorithmic_bytes_same_shape": (ncu_traffic(name) or {}).get("algorithmic_bytes_same_shape"),
+           "avg_launch_ms": d["ms"] / d["calls"], "calls": d["calls"], "peak_source": peaks["source"],
            "algorithmic_per_launch": b["algorithmic"] / d["calls"]}
     out["note"] = ("flops counted once (2 M N K per GEMM, 2 N^2 F per kNN cloud), whatever the 3xTF32 kernel issues" if b["bound"] == "tensor" else
                    "algorithmic (compulsory) bytes; gathers that hit L2 are not counted" if b["bound"] == "hbm" else
