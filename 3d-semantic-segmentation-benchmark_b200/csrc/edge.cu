@@ -54,9 +54,8 @@ edge_fwd_kernel(const float* __restrict__ xt, const int32_t* __restrict__ idx, i
 // d/dx of the neighbour term: gather of g[b,e,0:F] over the CSR segment of the source point.
 struct EdgeBwdSrc {
     const float* g; long E; int W;
-    __device__ __forceinline__ float accum(int b, int e, int c, float acc) const {
-        return acc + g[((size_t)b * E + e) * W + c];
-    }
+    __device__ __forceinline__ const float* row(int b, int e) const { return g + ((size_t)b * E + e) * W; }
+    __device__ __forceinline__ float scale(int, int) const { return 1.0f; }
 };
 // ... plus the dense centre term: - sum_j g[n,j,0:F] + sum_j g[n,j,F:2F], added at store time.
 struct EdgeBwdDst {

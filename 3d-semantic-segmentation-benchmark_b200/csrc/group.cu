@@ -63,9 +63,8 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
 // Backward w.r.t. feat: gfeat[b,s,:] = sum over the CSR segment of s of gout[b,e,3:3+D]  (segsum.cuh).
 struct GroupBwdSrc {
     const float* g; long E; int W;
-    __device__ __forceinline__ float accum(int b, int e, int c, float acc) const {
-        return acc + g[((size_t)b * E + e) * W + 3 + c];
-    }
+    __device__ __forceinline__ const float* row(int b, int e) const { return g + ((size_t)b * E + e) * W + 3; }
+    __device__ __forceinline__ float scale(int, int) const { return 1.0f; }
 };
 struct RowMajorDst {
     float* out; long N; int D;

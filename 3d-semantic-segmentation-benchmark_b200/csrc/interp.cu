@@ -19,6 +19,7 @@ interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ id
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int nw = gridDim.x * (blockDim.x >> 5);
     const float* __restrict__ fb = feat + (size_t)b * M * D;
+    const bool vec4 = (D % 4 == 0) && ((((uintptr_t)feat | (uintptr_t)out) & 15) == 0);
     for (int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < N; n += nw) {
         const size_t base = ((size_t)b * N + n) * K;
         float w[INTERP_KMAX];
@@ -37,6 +38,26 @@ interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ id
             for (int k = 0; k < INTERP_KMAX; ++k) if (k == lane) wl = w[k];
             coef[base + lane] = __fdiv_rn(wl, norm);
         }
+        if (vec4) {
+            // 4 channels per lane: K coalesced 512-byte row requests in flight, 4K independent divide chains
+            for (int c = lane * 4; c < D; c += 128) {
+                float4 f[INTERP_KMAX];
+#pragma unroll
+                for (int k = 0; k < INTERP_KMAX; ++k)
+                    if (k < K) f[k] = *reinterpret_cast<const float4*>(fb + (size_t)id[k] * D + c);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < INTERP_KMAX; ++k)
+                    if (k < K) {
+                        const float tx = __fdiv_rn(__fmul_rn(f[k].x, w[k]), norm), ty = __fdiv_rn(__fmul_rn(f[k].y, w[k]), norm);
+                        const float tz = __fdiv_rn(__fmul_rn(f[k].z, w[k]), norm), tw = __fdiv_rn(__fmul_rn(f[k].w, w[k]), norm);
+                        if (k == 0) acc = make_float4(tx, ty, tz, tw);
+                        else { acc.x = __fadd_rn(acc.x, tx); acc.y = __fadd_rn(acc.y, ty); acc.z = __fadd_rn(acc.z, tz); acc.w = __fadd_rn(acc.w, tw); }
+                    }
+                *reinterpret_cast<float4*>(out + ((size_t)b * N + n) * D + c) = acc;
+            }
+            continue;
+        }
         for (int c = lane; c < D; c += 32) {
             float acc = 0.f;
 #pragma unroll
@@ -53,9 +74,8 @@ interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ id
 // gfeat[b,m,:] = sum over incoming positions e = n*K + k of coef[e] * g[b,n,:]
 struct InterpBwdSrc {
     const float* g; const float* cf; long N; int D; int K;
-    __device__ __forceinline__ float accum(int b, int e, int c, float acc) const {
-        return __fmaf_rn(cf[(size_t)b * N * K + e], g[((size_t)b * N + e / K) * D + c], acc);
-    }
+    __device__ __forceinline__ const float* row(int b, int e) const { return g + ((size_t)b * N + e / K) * D; }
+    __device__ __forceinline__ float scale(int b, int e) const { return cf[(size_t)b * N * K + e]; }
 };
 struct InterpDst {
     float* out; long M; int D;

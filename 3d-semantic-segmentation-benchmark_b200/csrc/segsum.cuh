@@ -16,23 +16,47 @@ constexpr int SEG_HEAVY = 64;      // segments longer than this are summed by th
 constexpr int SEG_COLS = 128;      // columns per pass (4 per lane)
 
 // Accumulate rows perm[beg..end) into acc[4] for columns c0 + lane + 32*i < ncols.
+// Src: row(b, e) -> pointer to the gathered row of position e, scale(b, e) -> its weight (1 for plain sums; the
+// product is a single-rounding fma, so scale 1 adds exactly).  Row pointer and weight are formed once per position,
+// four positions (16 loads per lane) are in flight before the first add.
 template <class Src>
 __device__ __forceinline__ void seg_accumulate(const Src& src, int b, const int32_t* __restrict__ pm, int beg,
                                                int end, int c0, int ncols, int lane, float acc[4]) {
+    const int rem = ncols - c0;
     for (int t0 = beg; t0 < end; t0 += 32) {
         const int my_e = (t0 + lane < end) ? pm[t0 + lane] : 0;
         const int n = min(32, end - t0);
-#pragma unroll 4
-        for (int l = 0; l < n; ++l) {
+        int l = 0;
+        for (; l + 4 <= n; l += 4) {
+            const float* r[4];
+            float w[4], v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = __shfl_sync(PCNBR_FULL, my_e, l + u);
+                r[u] = src.row(b, e) + c0 + lane;
+                w[u] = src.scale(b, e);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[u][i] = (lane + 32 * i < rem) ? r[u][32 * i] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = __fmaf_rn(w[u], v[u][i], acc[i]);
+        }
+        for (; l < n; ++l) {
             const int e = __shfl_sync(PCNBR_FULL, my_e, l);
+            const float* r = src.row(b, e) + c0 + lane;
+            const float w = src.scale(b, e);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (lane + 32 * i < ncols - c0) acc[i] = src.accum(b, e, c0 + lane + 32 * i, acc[i]);
+                if (lane + 32 * i < rem) acc[i] = __fmaf_rn(w, r[32 * i], acc[i]);
         }
     }
 }
 
-// Src: accum(b, e, col, acc) -> acc + contribution of position e to column col.
+// Src: row(b, e) / scale(b, e), see seg_accumulate.
 // Dst: store(b, s, col, value).
 template <class Src, class Dst>
 __global__ void __launch_bounds__(256)

@@ -226,16 +226,19 @@ class _GroupFn(torch.autograd.Function):
 
 def group_points(coords, features, centroids, nbr: NeighborIndex, r_div: float | None, pad4: bool = False):
     """K5.  -> (B,M,K,3+D): [coords[idx] - centroid (optionally / r_div), features[idx]]
-    (models/utils/common.py:62-71).  pad4=True returns (B,M,K,W') with W' = 3+D rounded up to a multiple of 4 and zeros
-    in the extra columns: rows with a 16-byte pitch, which the tensor-core GEMM of the following 1x1 convolution reads
-    in place (the set-abstraction modules use it; `[..., :3+D]` is the reference tensor).  Differentiable w.r.t.
+    (models/utils/common.py:62-71).  pad4=True returns (B,M,K,W') with W' = 3+D rounded up to a multiple of 4 (to 32 when
+    3+D <= 32) and zeros in the extra columns: rows with a 16-byte pitch, which the tensor-core GEMM of the following
+    1x1 convolution reads in place (the set-abstraction modules use it; `[..., :3+D]` is the reference tensor).  Differentiable w.r.t.
     `features` only: the reference models never need coordinate gradients, and asking for them raises."""
     _check(coords, "coords"); _check(features, "features"); _check(centroids, "centroids")
     if coords.requires_grad or centroids.requires_grad:
         raise NotImplementedError("pcnbr: gradients w.r.t. coordinates are not implemented")
     rdiv = 0.0 if r_div is None else torch.tensor(float(r_div), dtype=torch.float32).item()
     W = 3 + features.shape[2]
-    return _GroupFn.apply(_c(coords), _c(features), _c(centroids), nbr, rdiv, (W + 3) // 4 * 4 if pad4 else W)
+    pitch = W
+    if pad4:                                          # narrow rows go to a full 128-byte line: TMA moves whole lines
+        pitch = 32 if W <= 32 else (W + 3) // 4 * 4
+    return _GroupFn.apply(_c(coords), _c(features), _c(centroids), nbr, rdiv, pitch)
 
 
 # ----------------------------------------------------------------------------- K6 max-pool over neighbours
@@ -549,6 +552,22 @@ def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None) -> 
     return out
 
 
+def _wgrad3x(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW (Cout,Cin) = gy^T x for gy (R,Cout), x (R,Cin), both contiguous.  For narrow layers the 128 x BN tile of the
+    split-K GEMM would be mostly zero padding (too few useful bytes in flight per SM), so p consecutive rows are viewed
+    as one row of p*Cout / p*Cin channels: the (p*Cout, p*Cin) product of the two views has dW as the sum of its p
+    diagonal blocks.  p-fold redundant flops on dense tiles -- still below the HBM time of these layers."""
+    R, Cout = gy.shape
+    Cin = x.shape[1]
+    p = 1
+    while 2 * p * Cout <= 128 and 2 * p * Cin <= 256 and R % (2 * p) == 0 and R // (2 * p) >= 4096:
+        p *= 2
+    if p == 1:
+        return _gemm3x(gy, True, x, True, Cout, Cin, R)
+    big = _gemm3x(gy.view(R // p, p * Cout), True, x.view(R // p, p * Cin), True, p * Cout, p * Cin, R // p)
+    return big.view(p, Cout, p, Cin).diagonal(dim1=0, dim2=2).sum(dim=-1)
+
+
 class _LinearRowsFn(torch.autograd.Function):
     """y = x W^T + b over the rows of x, all three GEMMs of the layer (output, input gradient, weight gradient) on the
     tensor cores in 3xTF32, each reading x, W and gy exactly as they lie in memory (no split or transposed copies)."""
@@ -567,7 +586,7 @@ class _LinearRowsFn(torch.autograd.Function):
         Cout = w.shape[0]
         gy = _c(gy)
         dx = _gemm3x(gy, False, w, True, R, Cin, Cout) if ctx.needs_input_grad[0] else None       # gy (R,Cout) . W (Cout,Cin)
-        dw = _gemm3x(gy, True, x, True, Cout, Cin, R) if ctx.needs_input_grad[1] else None         # gy^T . x, split along R
+        dw = _wgrad3x(gy, x) if ctx.needs_input_grad[1] else None                                  # gy^T . x, split along R
         db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 
@@ -618,7 +637,7 @@ class _LinearBnActFn(torch.autograd.Function):
         _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
                   dh.data_ptr(), _stream())
         dx = _gemm3x(dh, False, w, True, R, Cin, C) if ctx.needs_input_grad[0] else None
-        dw = _gemm3x(dh, True, x, True, C, Cin, R) if ctx.needs_input_grad[1] else None
+        dw = _wgrad3x(dh, x) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
