@@ -84,15 +84,18 @@ class MiniPointNet(nn.Module):
             return x
         return self.forward_rows(rows).permute(0, 3, 1, 2)
 
-    def forward_rows(self, rows: torch.Tensor) -> torch.Tensor:
-        """rows (B,C,K,Cin') point-major, Cin' = Cin or Cin rounded up to a multiple of 4 with zero columns
-        (ops.group_points(pad4=True)) -> (B,C,K,Cout).  The first weight is zero-padded to match, so the result and all
-        gradients are those of the unpadded layer."""
+    def forward_rows(self, rows: torch.Tensor, pool_max: bool = False) -> torch.Tensor:
+        """rows (B,C,K,Cin') point-major, Cin' = Cin or Cin padded with zero columns (ops.group_points(pad4=True))
+        -> (B,C,K,Cout), or (B,C,Cout) = its max over K when pool_max (the last layer is then fused with the pooling).
+        The first weight is zero-padded to match, so the result and all gradients are those of the unpadded layer."""
         h = rows
+        last = len(self.conv) - 1
         for i, (conv, bn) in enumerate(zip(self.conv, self.batch)):
             w = conv.weight.view(conv.out_channels, conv.in_channels)
             if i == 0 and h.shape[-1] != conv.in_channels:
                 w = F.pad(w, (0, h.shape[-1] - conv.in_channels))
+            if pool_max and i == last:
+                return ops.linear_bn_act_maxpool_rows(h, w, conv.bias, bn, 0.0)   # conv + BatchNorm2d + ReLU + max over K
             h = ops.linear_bn_act_rows(h, w, conv.bias, bn, 0.0)            # conv 1x1 + BatchNorm2d + ReLU (B,C,K,Cout)
         return h
 
@@ -157,6 +160,8 @@ class SetAbstraction(nn.Module):
     def forward(self, coords: torch.Tensor, features: torch.Tensor):
         centroid_coords = sample(coords, self.C, self.fps_start)
         grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
+        if self.pooling_type == 'max':
+            return centroid_coords, self.point_net.forward_rows(grouped, pool_max=True)   # (B,C,mlp[-1])
         x = self.point_net.forward_rows(grouped)             # point-major rows (B,C,K,*): no permute, no copy
         return centroid_coords, reduce(x, self.pooling_type)
 
@@ -188,6 +193,9 @@ class InvResMLP(nn.Module):
 
     def forward(self, centroid_coords, coords, features):
         grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, True)
-        x = reduce(self.neighbour_features_mlp.forward_rows(grouped), self.pooling_type)
+        if self.pooling_type == 'max':
+            x = self.neighbour_features_mlp.forward_rows(grouped, pool_max=True)
+        else:
+            x = reduce(self.neighbour_features_mlp.forward_rows(grouped), self.pooling_type)
         x = self.point_features_mlp(x.permute(0, 2, 1)).permute(0, 2, 1)
         return centroid_coords, x + features

@@ -311,6 +311,76 @@ bn_act_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ 
     }
 }
 
+// ---- BatchNorm + activation + max over the K rows of a group, without writing the activated (G*K, C) tensor.
+// act(bn(.)) is monotone per channel (increasing for gamma*rstd >= 0, decreasing otherwise), so
+//     max_k act(bn(h[g,k,c])) = act(bn(sel_k h[g,k,c])),  sel = max for scale >= 0, min otherwise   (exactly, in fp32),
+// the same identity the fused EdgeConv uses.  Forward: one pass over h -> out (G,C), the selected pre-BN value psel and
+// its k (uint8).  Backward: g' and the BatchNorm sums live on (G,C) (bn_act_bwd_reduce on psel), and
+//     dh[g,k,c] = gr g'[g,c] [k == arg] - c1 - c2r (h[g,k,c] - mean)
+// is one read of h and one write of dh.  Thread = (group, float4 column), K rows walked with 8 loads in flight.
+__global__ void __launch_bounds__(BA_T)
+pool_bn_act_fwd_kernel(const float* __restrict__ h, long G, int K, int C, const float* __restrict__ stats, float slope,
+                       float* __restrict__ out, float* __restrict__ psel, uint8_t* __restrict__ arg) {
+    const int CV = C >> 2;
+    const long total = G * CV;
+    for (long t = (long)blockIdx.x * BA_T + threadIdx.x; t < total; t += (long)gridDim.x * BA_T) {
+        const long g = t / CV;
+        const int c = (int)(t - g * CV) * 4;
+        const float4 mu = *reinterpret_cast<const float4*>(stats + c);
+        const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + c);
+        const float4 be = *reinterpret_cast<const float4*>(stats + 3 * C + c);
+        const float* __restrict__ hp = h + (g * K) * C + c;
+        float4 best = *reinterpret_cast<const float4*>(hp);
+        int ax = 0, ay = 0, az = 0, aw = 0;
+#pragma unroll 8
+        for (int k = 1; k < K; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(hp + (long)k * C);
+            if (sc.x >= 0.f ? v.x > best.x : v.x < best.x) { best.x = v.x; ax = k; }
+            if (sc.y >= 0.f ? v.y > best.y : v.y < best.y) { best.y = v.y; ay = k; }
+            if (sc.z >= 0.f ? v.z > best.z : v.z < best.z) { best.z = v.z; az = k; }
+            if (sc.w >= 0.f ? v.w > best.w : v.w < best.w) { best.w = v.w; aw = k; }
+        }
+        float4 o;
+        o.x = ba_act(best.x, mu.x, sc.x, be.x, slope);
+        o.y = ba_act(best.y, mu.y, sc.y, be.y, slope);
+        o.z = ba_act(best.z, mu.z, sc.z, be.z, slope);
+        o.w = ba_act(best.w, mu.w, sc.w, be.w, slope);
+        *reinterpret_cast<float4*>(out + g * C + c) = o;
+        *reinterpret_cast<float4*>(psel + g * C + c) = best;
+        *reinterpret_cast<uchar4*>(arg + g * C + c) = make_uchar4((uint8_t)ax, (uint8_t)ay, (uint8_t)az, (uint8_t)aw);
+    }
+}
+
+__global__ void __launch_bounds__(BA_T)
+pool_bn_bwd_apply_kernel(const float* __restrict__ h, const float* __restrict__ gs, const uint8_t* __restrict__ arg, long G,
+                         int K, int C, const float* __restrict__ coef, float* __restrict__ dh) {
+    const int CV = C >> 2;
+    const long total = G * CV;
+    for (long t = (long)blockIdx.x * BA_T + threadIdx.x; t < total; t += (long)gridDim.x * BA_T) {
+        const long g = t / CV;
+        const int c = (int)(t - g * CV) * 4;
+        const float4 gr = *reinterpret_cast<const float4*>(coef + c);
+        const float4 c1 = *reinterpret_cast<const float4*>(coef + C + c);
+        const float4 c2 = *reinterpret_cast<const float4*>(coef + 2 * C + c);
+        const float4 mu = *reinterpret_cast<const float4*>(coef + 3 * C + c);
+        const float4 gv = *reinterpret_cast<const float4*>(gs + g * C + c);
+        const uchar4 a = *reinterpret_cast<const uchar4*>(arg + g * C + c);
+        const float sx = gr.x * gv.x, sy = gr.y * gv.y, sz = gr.z * gv.z, sw = gr.w * gv.w;
+        const float* __restrict__ hp = h + (g * K) * C + c;
+        float* __restrict__ dp = dh + (g * K) * C + c;
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(hp + (long)k * C);
+            float4 o;
+            o.x = ((k == a.x) ? sx : 0.f) - c1.x - c2.x * (v.x - mu.x);
+            o.y = ((k == a.y) ? sy : 0.f) - c1.y - c2.y * (v.y - mu.y);
+            o.z = ((k == a.z) ? sz : 0.f) - c1.z - c2.z * (v.z - mu.z);
+            o.w = ((k == a.w) ? sw : 0.f) - c1.w - c2.w * (v.w - mu.w);
+            *reinterpret_cast<float4*>(dp + (long)k * C) = o;
+        }
+    }
+}
+
 static bool ba_supported(long R, int C) {
     if (R <= 0 || C < 4 || C % 4) return false;
     const int cv = C / 4;
@@ -425,6 +495,36 @@ extern "C" int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long 
     const double wb = 12.0 * R * C, wf = 8.0 * R * C;
     if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<2><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx)));
     else              PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<1><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_pool_bn_act_fwd_f32(const float* h, long G, int K, int C, const float* stats, float slope, float* out,
+                                         float* psel, uint8_t* arg, pcnbr_stream_t stream) {
+    if (!h || !stats || !out || !psel || !arg || G <= 0 || K <= 0) return PCNBR_E_BADARG;
+    if (K > 255 || C < 4 || C % 4 || (((uintptr_t)h | (uintptr_t)out | (uintptr_t)psel | (uintptr_t)stats) & 15) || ((uintptr_t)arg & 3))
+        return PCNBR_E_TOOLARGE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long total = G * (C / 4);
+    const long cap = 16L * ba_sms();
+    const int grid = (int)((total + BA_T - 1) / BA_T < cap ? (total + BA_T - 1) / BA_T : cap);
+    PCNBR_TIMED("pool_bn_act_fwd_kernel", s, 4.0 * G * K * C + 9.0 * G * C, 3.0 * G * K * C,
+                (pool_bn_act_fwd_kernel<<<grid, BA_T, 0, s>>>(h, G, K, C, stats, slope, out, psel, arg)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_pool_bn_bwd_apply_f32(const float* h, const float* gs, const uint8_t* arg, long G, int K, int C,
+                                           const float* coef, float* dh, pcnbr_stream_t stream) {
+    if (!h || !gs || !arg || !coef || !dh || G <= 0 || K <= 0) return PCNBR_E_BADARG;
+    if (K > 255 || C < 4 || C % 4 || (((uintptr_t)h | (uintptr_t)gs | (uintptr_t)dh | (uintptr_t)coef) & 15) || ((uintptr_t)arg & 3))
+        return PCNBR_E_TOOLARGE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long total = G * (C / 4);
+    const long cap = 16L * ba_sms();
+    const int grid = (int)((total + BA_T - 1) / BA_T < cap ? (total + BA_T - 1) / BA_T : cap);
+    PCNBR_TIMED("pool_bn_bwd_apply_kernel", s, 8.0 * G * K * C + 5.0 * G * C, 4.0 * G * K * C,
+                (pool_bn_bwd_apply_kernel<<<grid, BA_T, 0, s>>>(h, gs, arg, G, K, C, coef, dh)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

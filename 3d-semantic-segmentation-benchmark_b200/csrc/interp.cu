@@ -71,6 +71,63 @@ interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ id
     }
 }
 
+// k = 3 (the only value the models use), D % 4 == 0: one warp takes FOUR consecutive fine points per step -- lanes 0..11
+// fetch the 12 (index, distance) pairs in one coalesced request each, the weights and norms are formed once, and the
+// 12 coarse rows are in flight as float4 requests (512 B per row and warp) before the first divide.  Same arithmetic
+// order as interp_fwd_kernel, element for element.
+__global__ void __launch_bounds__(256)
+interp3_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, const float* __restrict__ d2,
+                   int N, int M, int D, float* __restrict__ out, float* __restrict__ coef) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    const float* __restrict__ fb = feat + (size_t)b * M * D;
+    const int lp = lane / 3, lk = lane - 3 * lp;                         // this lane's (point, neighbour) slot, lane < 12
+    for (int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; n0 < N; n0 += nw * 4) {
+        const size_t base = ((size_t)b * N + n0) * 3;
+        const bool slot = lane < 12 && n0 + lp < N;
+        const int my_id = slot ? idx[base + lane] : 0;
+        const float my_w = slot ? __fdiv_rn(1.0f, __fadd_rn(d2[base + lane], 1e-9f)) : 1.0f;     // common.py:119
+        int id[4][3];
+        float w[4][3], norm[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                id[p][k] = __shfl_sync(PCNBR_FULL, my_id, 3 * p + k);
+                w[p][k] = __shfl_sync(PCNBR_FULL, my_w, 3 * p + k);
+            }
+            norm[p] = __fadd_rn(__fadd_rn(w[p][0], w[p][1]), w[p][2]);  // common.py:120
+        }
+        if (coef && slot) {
+            float nm = norm[0];
+#pragma unroll
+            for (int p = 1; p < 4; ++p) if (lp == p) nm = norm[p];
+            coef[base + lane] = __fdiv_rn(my_w, nm);
+        }
+        (void)lk;
+        for (int c = lane * 4; c < D; c += 128) {
+            float4 f[4][3];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) f[p][k] = *reinterpret_cast<const float4*>(fb + (size_t)id[p][k] * D + c);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                if (n0 + p >= N) break;
+                float4 acc;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float tx = __fdiv_rn(__fmul_rn(f[p][k].x, w[p][k]), norm[p]), ty = __fdiv_rn(__fmul_rn(f[p][k].y, w[p][k]), norm[p]);
+                    const float tz = __fdiv_rn(__fmul_rn(f[p][k].z, w[p][k]), norm[p]), tw = __fdiv_rn(__fmul_rn(f[p][k].w, w[p][k]), norm[p]);
+                    if (k == 0) acc = make_float4(tx, ty, tz, tw);
+                    else { acc.x = __fadd_rn(acc.x, tx); acc.y = __fadd_rn(acc.y, ty); acc.z = __fadd_rn(acc.z, tz); acc.w = __fadd_rn(acc.w, tw); }
+                }
+                *reinterpret_cast<float4*>(out + ((size_t)b * N + n0 + p) * D + c) = acc;
+            }
+        }
+    }
+}
+
 // gfeat[b,m,:] = sum over incoming positions e = n*K + k of coef[e] * g[b,n,:]
 struct InterpBwdSrc {
     const float* g; const float* cf; long N; int D; int K;
@@ -93,8 +150,16 @@ extern "C" int pcnbr_interp_f32(const float* feat, const int32_t* idx, const flo
     int gx = (N + 7) / 8;
     if (gx > 148 * 8) gx = 148 * 8;
     // K8: 4 N D written + 4 M D read + 8 N k (idx, d2) read + 4 N k coef written per cloud
-    PCNBR_TIMED("interp_fwd_kernel", (cudaStream_t)stream, (double)B * (4.0 * N * D + 4.0 * M * D + 12.0 * N * K), 3.0 * B * (double)N * D * K,
-                (interp_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, K, out, coef)));
+    const double wb = (double)B * (4.0 * N * D + 4.0 * M * D + 12.0 * N * K), wf = 3.0 * B * (double)N * D * K;
+    if (K == 3 && D % 4 == 0 && ((((uintptr_t)feat | (uintptr_t)out) & 15) == 0)) {
+        int g3 = (N + 31) / 32;                                           // 8 warps x 4 points per CTA step
+        if (g3 > 148 * 8) g3 = 148 * 8;
+        PCNBR_TIMED("interp_fwd_kernel", (cudaStream_t)stream, wb, wf,
+                    (interp3_fwd_kernel<<<dim3(g3, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, out, coef)));
+    } else {
+        PCNBR_TIMED("interp_fwd_kernel", (cudaStream_t)stream, wb, wf,
+                    (interp_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, K, out, coef)));
+    }
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

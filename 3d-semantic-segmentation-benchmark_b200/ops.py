@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows",
+    "edge_features", "edgeconv_fused", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows",
 ]
 
 
@@ -642,6 +642,82 @@ class _LinearBnActFn(torch.autograd.Function):
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
         return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None, None, None, None, None, None, None)
+
+
+class _LinearBnActPoolFn(torch.autograd.Function):
+    """max over the K rows of each group of act(BatchNorm(x W^T + b)): the last layer of a set-abstraction MLP together
+    with reduce(.., 'max') (models/utils/common.py:141-147 + 85-86, 211-214).  BatchNorm + (Leaky)ReLU is monotone per
+    channel, so the pool is taken on the pre-BatchNorm rows and only the pooled (G,C) rows are activated: the activated
+    (G*K, C) tensor, its argmax scatter and two of the three backward passes over it never touch HBM."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, K):
+        R, Cin = x.shape
+        C = w.shape[0]
+        G = R // K
+        dev = x.device
+        h = _gemm3x(x, False, w, False, R, C, Cin, b)
+        if training:
+            nblk = _lib.size("pcnbr_bn_blocks", R, C)
+            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+            _lib.call("pcnbr_bn_stats_f32", h.data_ptr(), R, C, partial.data_ptr(), _stream())
+            stats = _bn_finalize(partial, nblk, h, R, C, gamma, beta, eps, momentum, rm, rv, dev)
+        else:
+            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        out = torch.empty(G, C, dtype=torch.float32, device=dev)
+        psel = torch.empty(G, C, dtype=torch.float32, device=dev)
+        arg = torch.empty(G, C, dtype=torch.uint8, device=dev)
+        _lib.call("pcnbr_pool_bn_act_fwd_f32", h.data_ptr(), G, K, C, stats.data_ptr(), float(slope), out.data_ptr(),
+                  psel.data_ptr(), arg.data_ptr(), _stream())
+        ctx.save_for_backward(x, w, h, stats, psel, arg)
+        ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None, int(K))
+        return out
+
+    @staticmethod
+    def backward(ctx, gpool):
+        x, w, h, stats, psel, arg = ctx.saved_tensors
+        training, slope, has_b, has_gamma, has_beta, K = ctx.consts
+        R, Cin = x.shape
+        C = w.shape[0]
+        G = R // K
+        dev = x.device
+        gpool = _c(gpool)
+        gs = torch.empty(G, C, dtype=torch.float32, device=dev)
+        nblk = _lib.size("pcnbr_bn_blocks", G, C)
+        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_act_bwd_reduce_f32", gpool.data_ptr(), psel.data_ptr(), C, None, 0, G, C, stats.data_ptr(), slope,
+                  partial.data_ptr(), gs.data_ptr(), _stream())
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        coef = torch.empty(4, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
+                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+        dh = torch.empty_like(h)
+        _lib.call("pcnbr_pool_bn_bwd_apply_f32", h.data_ptr(), gs.data_ptr(), arg.data_ptr(), G, K, C, coef.data_ptr(),
+                  dh.data_ptr(), _stream())
+        dx = _gemm3x(dh, False, w, True, R, Cin, C) if ctx.needs_input_grad[0] else None
+        dw = _wgrad3x(dh, x) if ctx.needs_input_grad[1] else None
+        db = None
+        if has_b and ctx.needs_input_grad[2]:
+            db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
+        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 7
+
+
+def linear_bn_act_maxpool_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float) -> torch.Tensor:
+    """rows (B,C,K,Cin) -> (B,C,Cout) = max over K of act(bn(rows @ weight^T + bias)): the last MLP layer of a
+    SetAbstraction / InvResMLP block fused with its max pooling (models/utils/common.py:211-214, 289-290)."""
+    Bc, Cc, K, cin = rows.shape
+    cout = weight.shape[0]
+    nrows = Bc * Cc * K
+    fused = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
+             and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4 and K <= 255
+             and _lib.size("pcnbr_bn_supported", nrows, cout) and _lib.size("pcnbr_bn_supported", Bc * Cc, cout))
+    if not fused:
+        return max_pool_neighbors(linear_bn_act_rows(rows, weight, bias, bn, negative_slope), 2)
+    training, momentum, rm, rv = _bn_mode(bn)
+    y = _LinearBnActPoolFn.apply(_c(rows).view(nrows, cin), _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
+                                 float(bn.eps), float(negative_slope), K)
+    return y.view(Bc, Cc, cout)
 
 
 def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float) -> torch.Tensor:

@@ -177,6 +177,17 @@ PCNBR_API int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const fl
 PCNBR_API int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
                                float slope, float* dx, pcnbr_stream_t stream);
 
+/* ---- BatchNorm + (Leaky)ReLU + max over the K rows of a group, fused ---- common.py:141-147 + 85-86 (SetAbstraction / InvResMLP)
+ * h (G*K, C) pre-BatchNorm rows, stats as above.  act(bn(.)) is monotone per channel, so the max over K is taken on h (max
+ * for gamma*rstd >= 0, min otherwise) and only the (G,C) result is activated: out (G,C), psel (G,C) the selected h,
+ * arg (G,C) its k (uint8, K <= 255).  The activated (G*K, C) tensor is never written.
+ * Backward: run pcnbr_bn_act_bwd_reduce_f32 / pcnbr_bn_bwd_finalize_f32 on (gpool, psel) with count = G*K to get
+ * gs (G,C) and coef, then pcnbr_pool_bn_bwd_apply_f32: dh[g,k,c] = gr gs[g,c] [k == arg[g,c]] - c1 - c2r (h[g,k,c] - mean). */
+PCNBR_API int pcnbr_pool_bn_act_fwd_f32(const float* h, long G, int K, int C, const float* stats, float slope, float* out,
+                              float* psel, uint8_t* arg, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_pool_bn_bwd_apply_f32(const float* h, const float* gs, const uint8_t* arg, long G, int K, int C,
+                                const float* coef, float* dh, pcnbr_stream_t stream);
+
 /* ---- fp32-accurate tensor-core GEMM for the 1x1 convolutions ---- common.py:125-178, dgcnn.py:66-126
  * Not a reference entry point: the reference's Conv1d/Conv2d(kernel 1) are library GEMMs; under the fp32 parity bar
  * they run as SIMT SGEMMs.  Here C (M,N) = A (M,K) . B (N,K)^T (+ bias (N)) runs as 3xTF32 on tcgen05 (hi.hi' + lo.hi' +

@@ -226,3 +226,41 @@ def test_linear_bn_act_rows_matches_fp64(pkg, dev, R, Cin, Cout, slope, bias, tr
             assert float(lin64.bias.grad.abs().max()) < 1e-9 * float(lin64.weight.grad.abs().max())
         else:
             _close(lind.bias.grad, lin64.bias.grad, 1e-4)
+
+
+@pytest.mark.parametrize("G,K,Cin,Cout,slope", [(2048, 32, 32, 64, 0.0), (512, 32, 132, 128, 0.0), (300, 16, 64, 32, 0.2)])
+@pytest.mark.parametrize("train", [True, False])
+def test_linear_bn_act_maxpool_rows_matches_fp64(pkg, dev, G, K, Cin, Cout, slope, train):
+    """ops.linear_bn_act_maxpool_rows = last set-abstraction MLP layer + reduce(.., 'max') (common.py:141-147, 85-86,
+    211-214) as one node that pools BEFORE BatchNorm/activation (monotone per channel; negative gammas take the min):
+    pooled output, input / weight / BatchNorm gradients and running statistics against the float64 modules."""
+    import copy
+    g = torch.Generator().manual_seed(G + K + Cin)
+    x = torch.randn(1, G, K, Cin, generator=g) * 0.5 + 0.2
+    lin = torch.nn.Linear(Cin, Cout)
+    bn = torch.nn.BatchNorm1d(Cout)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(Cout, generator=g)); bn.bias.copy_(torch.randn(Cout, generator=g) * 0.5)
+        bn.running_mean.copy_(torch.randn(Cout, generator=g) * 0.1); bn.running_var.copy_(torch.rand(Cout, generator=g) * 0.2 + 0.05)
+    lin64, bn64 = copy.deepcopy(lin).double(), copy.deepcopy(bn).double()
+    lind, bnd = copy.deepcopy(lin).to(dev), copy.deepcopy(bn).to(dev)
+    bn64.train(train); bnd.train(train)
+    with torch.no_grad():                                   # keep the upstream gradient off near-ties and the kink at 0
+        act = torch.nn.functional.leaky_relu(copy.deepcopy(bn64)(lin64(x.double()).view(-1, Cout)), slope).view(G, K, Cout)
+        top2 = act.topk(2, dim=1).values
+        safe = ((top2[:, 0] - top2[:, 1]) > 1e-4) & (top2[:, 0].abs() > 1e-3)
+    gy = torch.randn(G, Cout, generator=g) * safe.float()
+    xd = x.to(dev).requires_grad_(True)
+    y = pkg.ops.linear_bn_act_maxpool_rows(xd, lind.weight, lind.bias, bnd, slope)
+    assert y.shape == (1, G, Cout)
+    y.backward(gy.to(dev).view(1, G, Cout))
+    x64 = x.double().requires_grad_(True)
+    y64 = torch.nn.functional.leaky_relu(bn64(lin64(x64).view(-1, Cout)), slope).view(G, K, Cout).max(dim=1).values
+    y64.backward(gy.double())
+    _close(y, y64.view(1, G, Cout), 3e-5)
+    _close(xd.grad, x64.grad, 1e-4)
+    _close(lind.weight.grad, lin64.weight.grad, 1e-4)
+    _close(bnd.weight.grad, bn64.weight.grad, 1e-4)
+    _close(bnd.bias.grad, bn64.bias.grad, 1e-4)
+    _close(bnd.running_mean, bn64.running_mean, 1e-5)
+    _close(bnd.running_var, bn64.running_var, 1e-4)

@@ -220,7 +220,8 @@ def test_interpolate_golden(pkg, dev, golden):
     assert torch.equal(out.cpu(), g["out"])
 
 
-@pytest.mark.parametrize("N,M,D,k", [(4096, 1024, 128, 3), (1024, 256, 256, 3), (64, 16, 512, 3), (333, 77, 50, 5), (100, 8, 7, 8)])
+@pytest.mark.parametrize("N,M,D,k", [(4096, 1024, 128, 3), (1024, 256, 256, 3), (64, 16, 512, 3), (333, 77, 50, 5), (100, 8, 7, 8),
+                                     (335, 77, 64, 3), (1001, 40, 132, 3), (50, 9, 6, 3)])
 def test_interpolate_vs_oracle_with_backward(pkg, dev, N, M, D, k):
     pts, _, _ = O.s3dis_blocks(2, N, seed=N + M)
     fine = pts[:, :, :3].contiguous()
