@@ -86,13 +86,55 @@ __device__ __forceinline__ void csr_rank_chunk(const int32_t* __restrict__ t, in
     if (mine) pm[beg + rank] = x;
 }
 
-// A CTA of 8 warps takes 8 consecutive segments: short ones are sorted by one warp each, long ones
-// (the padded / duplicated heavy hitters, up to M entries) by all 8 warps together.
+// A CTA of 8 warps takes 8 consecutive segments: short ones are rank-sorted by one warp each.  Long ones -- the
+// padded / duplicated heavy hitters of an under-filled ball query (up to M*K entries on a few low-index points) and the
+// hubs of a feature-space kNN graph -- would cost O(len^2) that way; positions are distinct integers below E, so the
+// whole CTA instead marks them in a shared-memory bitmap of E bits and reads the set bits back in order
+// (popcount prefix over the words): O(E/32 + len) per long segment.
 constexpr int CSR_HEAVY = 128;
+constexpr int CSR_BITMAP_MAX_E = 1 << 20;          // 128 KB of bitmap at most (dynamic shared memory)
+
+__device__ __forceinline__ void csr_bitmap_sort(const int32_t* __restrict__ t, int32_t* __restrict__ pm, int beg, int len,
+                                                int E, uint32_t* bm, int* s_scan) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = (E + 31) >> 5;
+    for (int i = tid; i < W; i += 256) bm[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < len; i += 256) {
+        const int e = t[beg + i];
+        atomicOr(&bm[e >> 5], 1u << (e & 31));
+    }
+    __syncthreads();
+    const int wpt = (W + 255) / 256;                // words per thread, contiguous slice
+    const int w0 = min(tid * wpt, W), w1 = min(w0 + wpt, W);
+    int cnt = 0;
+    for (int w = w0; w < w1; ++w) cnt += __popc(bm[w]);
+    int x = cnt;                                     // block exclusive scan of cnt
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(PCNBR_FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_scan[warp] = x;
+    __syncthreads();
+    int base = x - cnt;
+    for (int k = 0; k < warp; ++k) base += s_scan[k];
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bits = bm[w];
+        while (bits) {
+            const int bpos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            pm[beg + base++] = (w << 5) + bpos;
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256)
 csr_sort_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ tmp, int E, int N,
-                int32_t* __restrict__ perm) {
-    __shared__ int s_beg[8], s_len[8];
+                int32_t* __restrict__ perm, int use_bitmap) {
+    extern __shared__ uint32_t csr_bm[];
+    __shared__ int s_beg[8], s_len[8], s_scan[8];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t* o = offsets + (size_t)b * (N + 1);
     const int32_t* t = tmp + (size_t)b * E;
@@ -108,7 +150,9 @@ csr_sort_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__
         __syncthreads();
         for (int w = 0; w < 8; ++w) {
             const int hl = s_len[w];
-            if (hl > CSR_HEAVY)
+            if (hl <= CSR_HEAVY) continue;                             // uniform over the CTA
+            if (use_bitmap) csr_bitmap_sort(t, pm, s_beg[w], hl, E, csr_bm, s_scan);
+            else
                 for (int c0 = warp * 32; c0 < hl; c0 += 8 * 32) csr_rank_chunk(t, pm, s_beg[w], hl, c0, lane);
         }
         __syncthreads();
@@ -142,7 +186,14 @@ extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t*
     PCNBR_TIMED("csr_fill_kernel", s, (double)B * 8.0 * E, 0.0, (csr_fill_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, E, N, cnt, tmp)));
     PCNBR_CHECK_LAUNCH();
     const int gs = min((N + 7) / 8, 1184);
-    PCNBR_TIMED("csr_sort_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0, (csr_sort_kernel<<<dim3(gs, B), 256, 0, s>>>(offsets, tmp, E, N, perm)));
+    const int use_bitmap = E <= CSR_BITMAP_MAX_E ? 1 : 0;
+    const size_t bm_bytes = use_bitmap ? (size_t)((E + 31) / 32) * 4 : 0;
+    if (bm_bytes > 48 * 1024) {
+        cudaError_t ea = cudaFuncSetAttribute(csr_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_bytes);
+        if (ea != cudaSuccess) return (int)ea;
+    }
+    PCNBR_TIMED("csr_sort_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0,
+                (csr_sort_kernel<<<dim3(gs, B), 256, bm_bytes, s>>>(offsets, tmp, E, N, perm, use_bitmap)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
