@@ -159,13 +159,103 @@ csr_sort_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------ stable counting sort (no sort pass)
+// For N <= CSR_STABLE_MAX_N the inverse is built as a STABLE counting sort, so the positions of a segment come out in
+// ascending order by construction and the O(len^2) rank sort above (the whole cost on hub-heavy kNN graphs and padded
+// ball tables) disappears.  Each warp owns a contiguous range of CSR_CH positions and a private shared-memory counter
+// row of N words:
+//   csr_hist_kernel  : per (cloud, warp range) key histogram -> cm (B, P, N)           (__match_any_sync groups equal keys
+//                      inside a 32-position step; the lowest lane of a group adds the group size: no atomics)
+//   csr_colscan_kernel: exclusive prefix over the P ranges for every key, in place; the per-key totals go to cnt
+//   csr_scan_kernel  : exclusive scan of the totals over the keys -> offsets              (as before)
+//   csr_place_kernel : each warp reloads its prefix row (+ offsets) as cursors and walks its range in order:
+//                      position = cursor[key] + (rank of the lane among equal keys of the step).
+// Deterministic: no atomics, no scheduling dependence.
+constexpr int CSR_CH = 2048;               // positions per warp range (64 steps of 32)
+constexpr int CSR_SW = 4;                  // warps per CTA (each with N words of shared memory)
+constexpr int CSR_STABLE_MAX_N = 12288;    // 4 warps x 48 KB = 192 KB of dynamic shared memory at most
+
+__global__ void __launch_bounds__(32 * CSR_SW)
+csr_hist_kernel(const int32_t* __restrict__ idx, int E, int N, int P, uint32_t* __restrict__ cm) {
+    extern __shared__ uint32_t csr_sm[];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * CSR_SW + warp;
+    if (p >= P) return;
+    uint32_t* h = csr_sm + (size_t)warp * N;
+    for (int i = lane; i < N; i += 32) h[i] = 0u;
+    __syncwarp();
+    const int e0 = p * CSR_CH, e1 = min(E, e0 + CSR_CH);
+    const int32_t* __restrict__ ib = idx + (size_t)b * E;
+    for (int e = e0 + lane; e - lane < e1; e += 32) {
+        const bool v = e < e1;
+        const int key = v ? ib[e] : -1 - lane;                            // invalid lanes get unique dummy keys
+        const uint32_t peers = __match_any_sync(PCNBR_FULL, key);
+        if (v && (peers & ((1u << lane) - 1u)) == 0u) h[key] += __popc(peers);
+        __syncwarp();
+    }
+    uint32_t* __restrict__ row = cm + ((size_t)b * P + p) * N;
+    for (int i = lane; i < N; i += 32) row[i] = h[i];
+}
+
+__global__ void __launch_bounds__(256)
+csr_colscan_kernel(uint32_t* __restrict__ cm, int N, int P, int32_t* __restrict__ cnt) {
+    const int b = blockIdx.y;
+    const int key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= N) return;
+    uint32_t* __restrict__ col = cm + (size_t)b * P * N + key;
+    uint32_t run = 0;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+        const uint32_t c = col[(size_t)p * N];
+        col[(size_t)p * N] = run;
+        run += c;
+    }
+    cnt[(size_t)b * (N + 1) + key] = (int32_t)run;
+}
+
+__global__ void __launch_bounds__(32 * CSR_SW)
+csr_place_kernel(const int32_t* __restrict__ idx, int E, int N, int P, const uint32_t* __restrict__ cm,
+                 const int32_t* __restrict__ offsets, int32_t* __restrict__ perm) {
+    extern __shared__ uint32_t csr_sm[];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * CSR_SW + warp;
+    if (p >= P) return;
+    uint32_t* cur = csr_sm + (size_t)warp * N;
+    const uint32_t* __restrict__ row = cm + ((size_t)b * P + p) * N;
+    const int32_t* __restrict__ off = offsets + (size_t)b * (N + 1);
+    for (int i = lane; i < N; i += 32) cur[i] = row[i] + (uint32_t)off[i];
+    __syncwarp();
+    const int e0 = p * CSR_CH, e1 = min(E, e0 + CSR_CH);
+    const int32_t* __restrict__ ib = idx + (size_t)b * E;
+    int32_t* __restrict__ pm = perm + (size_t)b * E;
+    for (int e = e0 + lane; e - lane < e1; e += 32) {
+        const bool v = e < e1;
+        const int key = v ? ib[e] : -1 - lane;
+        const uint32_t peers = __match_any_sync(PCNBR_FULL, key);
+        const uint32_t below = peers & ((1u << lane) - 1u);
+        if (v) {
+            pm[cur[key] + __popc(below)] = e;                             // every peer reads the cursor before it moves
+        }
+        __syncwarp();
+        if (v && below == 0u) cur[key] += __popc(peers);
+        __syncwarp();
+    }
+}
+
 }  // namespace pcnbr
 
 using namespace pcnbr;
 
+// The stable counting sort pays a fixed 3 N words of shared/global traffic per warp range, so it wins where segments are
+// long on average (kNN graphs, E/N = k >= 16: 0.58 -> 0.47 ms per DGCNN step) and loses on the short-segment tables of
+// PointNet++ (E/N = 8-12), which keep count / scan / fill / sort with the bitmap path for their few long segments.
+static bool csr_use_stable(int E, int N) { return N <= CSR_STABLE_MAX_N && (long)E >= 16L * N; }
+
 extern "C" size_t pcnbr_csr_ws_bytes(int B, int E, int N) {
-    // cnt/cursor (B,N+1) + tmp (B,E)
-    return sizeof(int32_t) * ((size_t)B * (N + 1) + (size_t)B * E);
+    // cnt/cursor (B,N+1) + max(tmp (B,E), per-range count matrix (B,P,N))
+    const size_t P = ((size_t)E + CSR_CH - 1) / CSR_CH;
+    const size_t tmp = (size_t)B * E, cm = csr_use_stable(E, N) ? (size_t)B * P * N : 0;
+    return sizeof(int32_t) * ((size_t)B * (N + 1) + (tmp > cm ? tmp : cm));
 }
 
 extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t* offsets, int32_t* perm,
@@ -175,6 +265,29 @@ extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t*
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* cnt = (int32_t*)ws;
     int32_t* tmp = cnt + (size_t)B * (N + 1);
+    if (csr_use_stable(E, N)) {
+        const int P = (E + CSR_CH - 1) / CSR_CH;
+        uint32_t* cm = (uint32_t*)tmp;
+        const size_t smem = (size_t)CSR_SW * N * sizeof(uint32_t);
+        if (smem > 48 * 1024) {
+            cudaError_t ea = cudaFuncSetAttribute(csr_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(csr_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ea != cudaSuccess) return (int)ea;
+        }
+        const dim3 gw((P + CSR_SW - 1) / CSR_SW, B);
+        PCNBR_TIMED("csr_hist_kernel", s, (double)B * (4.0 * E + 4.0 * P * N), 0.0,
+                    (csr_hist_kernel<<<gw, 32 * CSR_SW, smem, s>>>(idx, E, N, P, cm)));
+        PCNBR_CHECK_LAUNCH();
+        PCNBR_TIMED("csr_colscan_kernel", s, (double)B * (8.0 * P * N + 4.0 * N), 0.0,
+                    (csr_colscan_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(cm, N, P, cnt)));
+        PCNBR_CHECK_LAUNCH();
+        PCNBR_TIMED("csr_scan_kernel", s, (double)B * 12.0 * N, 0.0, (csr_scan_kernel<<<B, 1024, 0, s>>>(cnt, N, offsets, cnt)));
+        PCNBR_CHECK_LAUNCH();
+        PCNBR_TIMED("csr_place_kernel", s, (double)B * (8.0 * E + 4.0 * P * N + 4.0 * N), 0.0,
+                    (csr_place_kernel<<<gw, 32 * CSR_SW, smem, s>>>(idx, E, N, P, cm, offsets, perm)));
+        PCNBR_CHECK_LAUNCH();
+        return 0;
+    }
     cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)B * (N + 1), s);
     if (e != cudaSuccess) return (int)e;
     const int gx = min((E + 255) / 256, 1184);
