@@ -205,6 +205,14 @@ PCNBR_API size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits);
 PCNBR_API int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, int M, int N, int K,
                      const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
+/* ---- evaluation metrics ---------------------------------- Training/metrics.py:3-146
+ * pred (B,N,C) scores (softmax or logits: only the argmax matters), onehot (B,N,C) uint8 labels, lengths (B) int64
+ * unpadded points per cloud (NULL = N).  matrix (C,C) int64 is ACCUMULATED: matrix[label, predicted] += count over the
+ * unpadded points (zero it for a per-batch matrix, keep it across batches for a validation set).  Accuracy and the
+ * per-class intersections / unions of metrics.py are functions of it.  C <= 64. */
+PCNBR_API int pcnbr_confusion_f32(const float* pred, const uint8_t* onehot, const long long* lengths, int B, int N, int C,
+                        long long* matrix, pcnbr_stream_t stream);
+
 /* ---- measurement hook (bench.py roofline, kernel sweep) -- not part of the reference interface
  * pcnbr_prof_enable(1): bracket every kernel this library launches with CUDA events on its launch stream and
  * remember the launch's ALGORITHMIC bytes / flops.  Must be off while a CUDA graph is captured.

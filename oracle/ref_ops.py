@@ -405,3 +405,41 @@ def s3dis_blocks(B: int, N: int = 4096, seed: int = 0, classes: int = 13):
     pts = torch.cat([xyz, rgb, xyz - centre], dim=-1)
     lab = F.one_hot(torch.randint(0, classes, (B, N), generator=g), classes).to(torch.uint8)
     return pts, lab, torch.full((B,), N, dtype=torch.int64)
+
+
+# --------------------------------------------------------------------------- Training/metrics.py
+
+
+def metrics_confusion_matrix(predictions: torch.Tensor, labels: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Restatement of Training/metrics.py:52-78: matrix[i, j] = #points with label i predicted j, unpadded points only
+    (torch.argmax: first maximum wins)."""
+    B, _, C = labels.shape
+    m = torch.zeros(C, C, dtype=torch.int64)
+    for b in range(B):
+        n = int(mask[b])
+        pc = predictions[b, :n].argmax(-1)
+        lc = labels[b, :n].argmax(-1)
+        m += torch.bincount(lc * C + pc, minlength=C * C).view(C, C)
+    return m
+
+
+def metrics_update_accuracy(predictions, labels, mask):
+    """Training/metrics.py:28-50 -> (correct, total)."""
+    m = metrics_confusion_matrix(predictions, labels, mask)
+    return int(m.diagonal().sum()), int(mask.sum())
+
+
+def metrics_update_iou(predictions, labels, mask):
+    """Training/metrics.py:115-146 -> (intersections (C,), unions (C,)) float32.  NB the reference tests
+    `labels[..., c] == 1` while the confusion matrix uses the label argmax: identical for one-hot rows."""
+    m = metrics_confusion_matrix(predictions, labels, mask)
+    inter = m.diagonal()
+    union = m.sum(0) + m.sum(1) - inter
+    return inter.to(torch.float32), union.to(torch.float32)
+
+
+def metrics_iou(predictions, labels, mask):
+    """Training/metrics.py:81-112 -> (mean IoU, per-class IoU) with eps = 1e-6."""
+    inter, union = metrics_update_iou(predictions, labels, mask)
+    ious = ((inter.double() + 1e-6) / (union.double() + 1e-6)).to(torch.float32)
+    return ious.mean().item(), ious

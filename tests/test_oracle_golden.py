@@ -143,3 +143,16 @@ def test_oracle_against_live_reference():
     feats = torch.randn(2, 50, 24, generator=gen)
     i3, d3 = canon.knn_direct(xyz, ref, 3)
     assert torch.equal(canon.interp(feats, i3, d3), RC.interpolate(feats, xyz, ref))
+
+
+def test_metrics_match_reference_golden(golden):
+    """Training/metrics.py: the oracle's restatement against the unmodified reference's outputs
+    (oracle/make_golden_metrics.py), incl. an argmax tie, a padded and an empty cloud."""
+    g = golden("metrics")
+    cm = O.metrics_confusion_matrix(g["pred"], g["labels"], g["mask"])
+    assert torch.equal(cm, g["confusion"])
+    assert O.metrics_update_accuracy(g["pred"], g["labels"], g["mask"]) == (g["correct"], g["total"])
+    inter, union = O.metrics_update_iou(g["pred"], g["labels"], g["mask"])
+    assert torch.equal(inter, g["inter"]) and torch.equal(union, g["union"])
+    miou, ious = O.metrics_iou(g["pred"], g["labels"], g["mask"])
+    assert torch.equal(ious, g["ious"]) and abs(miou - g["miou"]) < 1e-7
