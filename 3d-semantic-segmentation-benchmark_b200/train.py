@@ -26,20 +26,25 @@ class FlatGradBucket:
     zeroing the gradients is one memset."""
 
     def __init__(self, module: torch.nn.Module, group=None, steal_grads: bool = False):
-        """steal_grads (single process only): zero() drops the gradients instead of clearing the bucket, so autograd
-        hands each freshly computed gradient tensor to its parameter (no accumulate kernel per parameter: ~90 tiny
-        launches per PointNet++ step); the bucket is then not used, there being nothing to exchange."""
+        """steal_grads: zero() drops the gradients instead of clearing the bucket, so autograd hands each freshly
+        computed gradient tensor to its parameter (no accumulate kernel per parameter: ~90 tiny launches per PointNet++
+        step).  With several ranks all_reduce_mean() then packs the gradients into the bucket with one multi-tensor
+        copy, reduces it and points every p.grad at its (reduced) bucket view; with one rank there is nothing to do."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = group
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.steal = bool(steal_grads) and self.world == 1
+        self.steal = bool(steal_grads)
+        if not self.steal:
+            for p, v in zip(self.params, self.views):
+                p.grad = v
 
     def zero(self) -> None:
         if self.steal:
@@ -50,9 +55,19 @@ class FlatGradBucket:
 
     def all_reduce_mean(self) -> None:
         """Sum the bucket over ranks and divide by the world size (standard DDP semantics)."""
-        if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / self.world)
+        if self.world <= 1:
+            return
+        if self.steal:
+            have = [(v, p.grad) for p, v in zip(self.params, self.views) if p.grad is not None]
+            if len(have) != len(self.params):
+                self.flat.zero_()                                  # parameters that received no gradient contribute 0
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.mul_(1.0 / self.world)
+        if self.steal:
+            for p, v in zip(self.params, self.views):
+                p.grad = v
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

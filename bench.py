@@ -269,7 +269,7 @@ def run_ours(args):
     torch.manual_seed(0)
     net = build_model(pkg, args.model).to(dev)
     pkg.train.broadcast_parameters(net)
-    bucket = pkg.train.FlatGradBucket(net, steal_grads=(world == 1))
+    bucket = pkg.train.FlatGradBucket(net, steal_grads=True)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=not args.no_graph)
 
     n_batches = 4                                        # rotate inputs; activations (GBs) >> L2 anyway

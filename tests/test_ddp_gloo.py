@@ -14,7 +14,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, steal=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -25,22 +25,27 @@ def _worker(rank, world, port, out):
     torch.manual_seed(100 + rank)                      # different init per rank on purpose
     net = torch.nn.Sequential(torch.nn.Linear(9, 16), torch.nn.ReLU(), torch.nn.Linear(16, 13))
     pkg.train.broadcast_parameters(net)                # -> rank 0's parameters everywhere
-    bucket = pkg.train.FlatGradBucket(net)
+    bucket = pkg.train.FlatGradBucket(net, steal_grads=steal)
     pts, lab, lens = pkg.synthetic.s3dis_blocks(4, 64, seed=0)
     sl = pkg.train.shard_batch(4, rank, world)
     bucket.zero()
     loss = pkg.train.masked_onehot_cross_entropy(net(pts[sl]), lab[sl], lens[sl])
     loss.backward()
     bucket.all_reduce_mean()
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))   # grads live in the bucket
     out[rank] = (bucket.flat.clone(), torch.cat([p.detach().flatten() for p in net.parameters()]), (sl.start, sl.stop))
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_matches_full_batch(pkg):
+import pytest
+
+
+@pytest.mark.parametrize("steal", [False, True])
+def test_flat_bucket_allreduce_matches_full_batch(pkg, steal):
     world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), out, steal), nprocs=world, join=True)
         res = dict(out)
     g0, p0, s0 = res[0]
     g1, p1, s1 = res[1]
