@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows",
+    "edge_features", "edgeconv_fused", "aux_stream", "join_aux", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows",
 ]
 
 
@@ -52,32 +52,86 @@ def _as_i32(idx: torch.Tensor) -> torch.Tensor:
     raise TypeError(f"pcnbr: index tensor must be int32 or int64, got {idx.dtype}")
 
 
-class NeighborIndex:
-    """A neighbour table idx (B,M,K) int32 into N source points, with its lazily built inverse
-    (CSR by source point) that the atomic-free backward kernels consume."""
+_AUX_STREAMS: dict = {}
 
-    __slots__ = ("idx", "num_src", "_csr")
+
+def aux_stream(device) -> torch.cuda.Stream:
+    """The side stream (one per device) on which index-only work runs concurrently with the feature path: CSR inverses
+    (needed only by the backward) and, for PointNet++, the geometry of the deeper levels.  Work is launched on it by
+    handing its handle to the C ABI; every buffer is allocated on the CURRENT stream beforehand and released only after
+    the consumer has waited on the producing event, so no allocator stream bookkeeping is involved (CUDA-graph safe:
+    the side stream joins a capture through the event it waits on, and is joined back by the consumer's wait)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _AUX_STREAMS.get(idx)
+    if st is None:
+        st = _AUX_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
+_PENDING_AUX: list = []      # events of side-stream work not yet waited on by the main stream
+
+
+def join_aux() -> None:
+    """Make the current stream wait for all outstanding side-stream work (end of a step / before a capture ends)."""
+    cur = torch.cuda.current_stream()
+    while _PENDING_AUX:
+        cur.wait_event(_PENDING_AUX.pop())
+
+
+_ASYNC_INDEX = __import__("os").environ.get("PCNBR_NO_AUX_STREAM") is None
+
+
+class NeighborIndex:
+    """A neighbour table idx (B,M,K) int32 into N source points, with its inverse (CSR by source point) that the
+    atomic-free backward kernels consume.  The inverse is built lazily, or -- prefetch_csr() -- on the side stream
+    while the forward pass goes on."""
+
+    __slots__ = ("idx", "num_src", "_csr", "_event", "_keep")
 
     def __init__(self, idx: torch.Tensor, num_src: int):
         _check(idx, "idx", torch.int32)
         self.idx = _c(idx)
         self.num_src = int(num_src)
         self._csr = None
+        self._event = None
+        self._keep = None
+
+    def _build(self, stream_handle: int):
+        B = self.idx.shape[0]
+        E = self.idx[0].numel()
+        N = self.num_src
+        dev = self.idx.device
+        offsets = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
+        perm = torch.empty(B, E, dtype=torch.int32, device=dev)
+        nb = _lib.size("pcnbr_csr_ws_bytes", B, E, N)
+        ws = _ws(nb, dev)
+        _lib.call("pcnbr_csr_build", self.idx.data_ptr(), B, E, N, offsets.data_ptr(), perm.data_ptr(),
+                  ws.data_ptr(), nb, stream_handle)
+        return offsets, perm, ws
+
+    def prefetch_csr(self) -> None:
+        """Start building the inverse on the side stream (no-op if it exists).  Buffers are allocated here, on the
+        current stream; csr() makes the consumer wait for the build."""
+        if self._csr is not None or not _ASYNC_INDEX:
+            return
+        aux = aux_stream(self.idx.device)
+        ready = torch.cuda.current_stream().record_event()          # idx has been written
+        aux.wait_event(ready)
+        offsets, perm, ws = self._build(aux.cuda_stream)
+        self._event = aux.record_event()
+        _PENDING_AUX.append(self._event)
+        self._csr, self._keep = (offsets, perm), ws
 
     def csr(self):
         """(offsets (B,N+1) int32, perm (B,E) int32): positions grouped by source, ascending."""
         if self._csr is None:
-            B = self.idx.shape[0]
-            E = self.idx[0].numel()
-            N = self.num_src
-            dev = self.idx.device
-            offsets = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
-            perm = torch.empty(B, E, dtype=torch.int32, device=dev)
-            nb = _lib.size("pcnbr_csr_ws_bytes", B, E, N)
-            ws = _ws(nb, dev)
-            _lib.call("pcnbr_csr_build", self.idx.data_ptr(), B, E, N, offsets.data_ptr(), perm.data_ptr(),
-                      ws.data_ptr(), nb, _stream())
+            offsets, perm, _ = self._build(_stream())
             self._csr = (offsets, perm)
+        if self._event is not None:
+            torch.cuda.current_stream().wait_event(self._event)
+            if self._event in _PENDING_AUX:
+                _PENDING_AUX.remove(self._event)
+            self._event, self._keep = None, None
         return self._csr
 
 
@@ -209,6 +263,8 @@ class _GroupFn(torch.autograd.Function):
                   nbr.idx.data_ptr(), B, N, M, K, D, float(rdiv), out.data_ptr(), pitch, _stream())
         ctx.nbr = nbr
         ctx.dims = (B, N, M, K, D, pitch)
+        if D and ctx.needs_input_grad[1]:
+            nbr.prefetch_csr()
         return out
 
     @staticmethod
@@ -314,6 +370,8 @@ class _InterpFn(torch.autograd.Function):
                   out.data_ptr(), coef.data_ptr(), _stream())
         ctx.nbr, ctx.dims = nbr, (B, N, M, D, K)
         ctx.save_for_backward(coef)
+        if ctx.needs_input_grad[0]:
+            nbr.prefetch_csr()
         return out
 
     @staticmethod
@@ -348,6 +406,8 @@ class _EdgeFn(torch.autograd.Function):
         out = torch.empty(B, N, K, 2 * F, dtype=torch.float32, device=xt.device)
         _lib.call("pcnbr_edge_feature_f32", xt.data_ptr(), nbr.idx.data_ptr(), B, N, F, K, out.data_ptr(), _stream())
         ctx.nbr, ctx.dims = nbr, (B, N, F, K)
+        if ctx.needs_input_grad[0]:
+            nbr.prefetch_csr()
         return out
 
     @staticmethod
@@ -403,6 +463,8 @@ class _EdgeConvFusedFn(torch.autograd.Function):
                   float(slope), out.data_ptr(), _stream())
         ctx.nbr, ctx.consts = nbr, (B, N, O, K, M, bool(training), float(slope))
         ctx.save_for_backward(PQ, psel, arg, s1, stats)
+        if ctx.needs_input_grad[0]:
+            nbr.prefetch_csr()
         return out
 
     @staticmethod

@@ -109,9 +109,11 @@ class GraphedTrainStep:
             self.loss = self._step_body()
 
     def _step_body(self):
+        from . import ops
         self.bucket.zero()
         loss = self.forward_fn(self.model, *self.static)
         loss.backward()
+        ops.join_aux()                                       # side-stream index work is consumed by the backward; belt and braces
         self.bucket.all_reduce_mean()
         self.opt.step()
         return loss.detach()

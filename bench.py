@@ -286,6 +286,7 @@ def run_ours(args):
         bucket.zero()
         loss = loss_of(net, pts, lab, lens)
         loss.backward()
+        pkg.ops.join_aux()
         bucket.all_reduce_mean()
         opt.step()
         return loss
