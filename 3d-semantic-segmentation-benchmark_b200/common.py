@@ -157,9 +157,15 @@ class SetAbstraction(nn.Module):
         self.grouping_norm = grouping_norm
         self.fps_start = None          # optional (B,) first FPS pick (tests); None = reference's randint
 
-    def forward(self, coords: torch.Tensor, features: torch.Tensor):
-        centroid_coords = sample(coords, self.C, self.fps_start)
-        grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
+    def forward(self, coords: torch.Tensor, features: torch.Tensor, _geom=None):
+        """_geom (internal): (centroid coords, ball-query NeighborIndex) precomputed by ops.PyramidGeometry on the side
+        stream; None computes them here, as the reference does."""
+        if _geom is not None:
+            centroid_coords, nbr = _geom
+            grouped = ops.group_points(coords, features, centroid_coords, nbr, self.radius if self.grouping_norm else None, pad4=True)
+        else:
+            centroid_coords = sample(coords, self.C, self.fps_start)
+            grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
         if self.pooling_type == 'max':
             return centroid_coords, self.point_net.forward_rows(grouped, pool_max=True)   # (B,C,mlp[-1])
         x = self.point_net.forward_rows(grouped)             # point-major rows (B,C,K,*): no permute, no copy
@@ -173,8 +179,9 @@ class FeaturePropagation(nn.Module):
         super().__init__()
         self.point_net = UnitPointNet(in_channels, mlps)
 
-    def forward(self, coords_1, coords_2, features_1, features_2):
-        up = interpolate(features_2, coords_1, coords_2)
+    def forward(self, coords_1, coords_2, features_1, features_2, _geom=None):
+        """_geom (internal): (NeighborIndex, d2) of the 3-NN table precomputed by ops.PyramidGeometry."""
+        up = interpolate(features_2, coords_1, coords_2) if _geom is None else ops.three_interpolate(features_2, _geom[0], _geom[1])
         feats = up if features_1 is None else torch.cat([features_1, up], dim=-1)
         return self.point_net(feats.permute(0, 2, 1)).permute(0, 2, 1)
 

@@ -16,15 +16,39 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused", "aux_stream", "join_aux", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows",
+    "edge_features", "edgeconv_fused", "aux_stream", "join_aux", "on_stream", "PyramidGeometry", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows",
 ]
 
 
 # ----------------------------------------------------------------------------- plumbing
 
 
+_STREAM_OVERRIDE = None       # raw stream handle the C-ABI calls go to instead of the current stream (see on_stream)
+
+
 def _stream() -> int:
+    if _STREAM_OVERRIDE is not None:
+        return _STREAM_OVERRIDE
     return torch.cuda.current_stream().cuda_stream
+
+
+class on_stream:
+    """Route the libpcnbr launches of the enclosed ops to `stream` WITHOUT making it torch's current stream: outputs and
+    workspaces are still allocated on the current stream (whose allocator owns them), only the kernels go elsewhere.
+    The caller orders the two streams with events."""
+
+    def __init__(self, stream: torch.cuda.Stream):
+        self.handle = stream.cuda_stream
+
+    def __enter__(self):
+        global _STREAM_OVERRIDE
+        self.prev, _STREAM_OVERRIDE = _STREAM_OVERRIDE, self.handle
+        return self
+
+    def __exit__(self, *exc):
+        global _STREAM_OVERRIDE
+        _STREAM_OVERRIDE = self.prev
+        return False
 
 
 def _check(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
@@ -133,6 +157,117 @@ class NeighborIndex:
                 _PENDING_AUX.remove(self._event)
             self._event, self._keep = None, None
         return self._csr
+
+
+class PyramidGeometry:
+    """All index-only work of a PointNet++ encoder/decoder for one batch (models/PointNetpp/PointNetpp.py:26-41 call
+    sample/group/interpolate level by level; none of the indices depends on a feature).  Level 1 (FPS + ball query on
+    the input cloud) runs on the current stream because the first set abstraction needs it at once; the deeper FPS
+    levels, their ball queries and the 3-NN tables of the decoder run on the side stream, concurrently with the
+    feature path, and each consumer waits on the event of what it needs.
+
+    sa = [(C, radius, K), ...] per set-abstraction level; starts = per-level first FPS picks or None (drawn here, level
+    by level, exactly as the modules would: torch.randint(0, N_level, (B,), dtype=torch.int), common.py:22)."""
+
+    def __init__(self, coords0: torch.Tensor, sa, starts=None, interp_k: int = 3):
+        dev = coords0.device
+        B = coords0.shape[0]
+        coords0 = _c(coords0)
+        ns = [coords0.shape[1]] + [c for (c, _, _) in sa]
+        starts = list(starts) if starts is not None else [None] * len(sa)
+        draws = [(st if st is not None else torch.randint(0, ns[l], (B,), dtype=torch.int, device=dev))
+                 .to(device=dev, dtype=torch.int32).contiguous() for l, st in enumerate(starts)]      # all on the current stream, before the fork
+        self.coords = [coords0]
+        self.balls, self.ball_events = [], []
+        # Everything a side-stream kernel reads or writes is allocated here on the CURRENT stream and kept alive by this
+        # object until the consumer has waited on the producing event: a buffer released earlier (an unused FPS index
+        # output, a workspace, a start draw) could be handed to a main-stream kernel while the side stream still uses it.
+        self._keep = [draws]
+
+        def fps(src, C, start):
+            Bc, Nc, _ = src.shape
+            idx = torch.empty(Bc, C, dtype=torch.int32, device=dev)
+            out = torch.empty(Bc, C, 3, dtype=torch.float32, device=dev)
+            nb = _lib.size("pcnbr_fps_ws_bytes", Bc, Nc)
+            ws = _ws(nb, dev)
+            self._keep += [idx, ws]
+            _lib.call("pcnbr_fps_f32", src.data_ptr(), Bc, Nc, C, start.data_ptr(), idx.data_ptr(), out.data_ptr(),
+                      ws.data_ptr(), nb, _stream())
+            return out
+
+        def ball(r, K, src, cen):
+            Bc, Nc, _ = src.shape
+            M = cen.shape[1]
+            if K > Nc:
+                raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={Nc})")
+            idx = torch.empty(Bc, M, K, dtype=torch.int32, device=dev)
+            _lib.call("pcnbr_ball_query_f32", cen.data_ptr(), src.data_ptr(), Bc, M, Nc, _r2(r), K, idx.data_ptr(), _stream())
+            return NeighborIndex(idx, Nc)
+
+        def knn3(query, src, k):
+            Bc, M, _ = query.shape
+            Nc = src.shape[1]
+            if k > Nc:
+                raise RuntimeError(f"pcnbr: selected index k out of range (k={k} > N={Nc})")
+            idx = torch.empty(Bc, M, k, dtype=torch.int32, device=dev)
+            d2 = torch.empty(Bc, M, k, dtype=torch.float32, device=dev)
+            _lib.call("pcnbr_knn_direct_f32", query.data_ptr(), src.data_ptr(), Bc, M, Nc, k, idx.data_ptr(), d2.data_ptr(), _stream())
+            return NeighborIndex(idx, Nc), d2
+
+        # level 1 on the current stream
+        C, r, K = sa[0]
+        self.coords.append(fps(coords0, C, draws[0]))
+        self.balls.append(ball(r, K, coords0, self.coords[1]))
+        self.ball_events.append(None)
+        aux = aux_stream(dev) if _ASYNC_INDEX else None
+        if aux is not None:
+            aux.wait_event(torch.cuda.current_stream().record_event())
+        ctx = on_stream(aux) if aux is not None else _NullCtx()
+        with ctx:
+            for l in range(1, len(sa)):
+                C, r, K = sa[l]
+                src = self.coords[l]
+                self.coords.append(fps(src, C, draws[l]))
+                self.balls.append(ball(r, K, src, self.coords[l + 1]))
+                self.ball_events.append(self._mark(aux))
+            # decoder: level l features are interpolated from level l+1 (fine = l, coarse = l+1), deepest first
+            self.knn, self.knn_events = {}, {}
+            for l in range(len(sa) - 1, -1, -1):
+                self.knn[l] = knn3(self.coords[l], self.coords[l + 1], interp_k)
+                self.knn_events[l] = self._mark(aux)
+
+    @staticmethod
+    def _mark(aux):
+        if aux is None:
+            return None
+        ev = aux.record_event()
+        _PENDING_AUX.append(ev)
+        return ev
+
+    @staticmethod
+    def _wait(ev):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            if ev in _PENDING_AUX:
+                _PENDING_AUX.remove(ev)
+
+    def level(self, l: int):
+        """(centroid coords, ball-query NeighborIndex) of set-abstraction level l (0-based), ready on the current stream."""
+        self._wait(self.ball_events[l])
+        return self.coords[l + 1], self.balls[l]
+
+    def three_nn(self, l: int):
+        """(NeighborIndex, d2) for interpolating level l+1 features onto level l, ready on the current stream."""
+        self._wait(self.knn_events[l])
+        return self.knn[l]
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 # ----------------------------------------------------------------------------- index-returning primitives
