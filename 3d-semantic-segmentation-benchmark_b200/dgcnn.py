@@ -72,9 +72,27 @@ class EdgeConv(nn.Module):
         nbr = ops.NeighborIndex(ops.knn_graph(x, self.k), N)
         W = conv.weight.view(O, 2 * F)
         Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
-        PQ = ops.linear_rows(_point_major(x), Wcat, None)                   # (B,N,F) x (F,2O): tensor-core GEMM / split-K wgrad
+        rows = _point_major(x)
+        if F % 4:
+            # xyz layer.  u_ij = A (x_j - x_i) + B x_i is evaluated as P_j + Q_i with P = A x, Q = (B - A) x, which cancels
+            # catastrophically when the cloud sits tens of metres from the origin (S3DIS coordinates).  A is translation
+            # invariant, so work on coordinates centred per cloud, xc = x - m:  P = A xc,  Q = (B - A) xc + B m.  The rows
+            # are then zero-padded 3 -> 4 channels so that all three GEMMs (incl. the 65536-row weight gradient) run on
+            # tcgen05.
+            m = rows.mean(dim=1, keepdim=True)                              # (B,1,F)
+            PQ = ops.linear_rows(_pad4(rows - m), _pad4(Wcat), None)
+            PQ = PQ + torch.nn.functional.pad(torch.matmul(m, W[:, F:].t()), (O, 0))        # [0 | B m] broadcast over the points
+        else:
+            PQ = ops.linear_rows(rows, Wcat, None)                          # (B,N,F) x (F,2O): tensor-core GEMM / split-K wgrad
         out = ops.edgeconv_fused(PQ, nbr, bn, act.negative_slope)           # (B,N,O), point-major
         return out.permute(0, 2, 1)                                         # (B,O,N) view, no copy
+
+
+def _pad4(t: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the last (channel) dimension to a multiple of 4 floats: the 16-byte row pitch TMA needs.  Padding both
+    the rows and the weight leaves the product and every gradient unchanged (the pad columns are sliced away by
+    autograd)."""
+    return torch.nn.functional.pad(t, (0, (-t.shape[-1]) % 4))
 
 
 def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
@@ -86,6 +104,8 @@ def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
     mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
     conv = mods[0]
     w = conv.weight.squeeze(-1)
+    if w.shape[1] % 4 and w.shape[1] <= 16:                                 # the 3-channel colour branch
+        rows, w = _pad4(rows), _pad4(w)
     if len(mods) >= 3 and isinstance(mods[1], nn.modules.batchnorm._BatchNorm) and isinstance(mods[2], nn.LeakyReLU):
         y = ops.linear_bn_act_rows(rows, w, conv.bias, mods[1], mods[2].negative_slope)
         rest = mods[3:]
