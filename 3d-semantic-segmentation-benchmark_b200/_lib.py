@@ -53,6 +53,7 @@ PROTOTYPES = {
     "pcnbr_gemm3x_splits": (_I, [_I, _I, _I]),
     "pcnbr_gemm3x_ws_bytes": (_Z, [_I, _I, _I, _I]),
     "pcnbr_gemm3x_f32": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
+    "pcnbr_gemm3x_ex_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _L, _I, _P, _Z, _P]),
     "pcnbr_confusion_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "pcnbr_prof_enable": (None, [_I]),
     "pcnbr_prof_collect": (_I, [_P, _Z]),

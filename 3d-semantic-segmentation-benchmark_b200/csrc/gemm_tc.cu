@@ -125,8 +125,9 @@ __device__ __forceinline__ float gm_residual(float v) {
 // out + split * M * ldc (partials); splits == 1 writes the result (plus bias) directly.
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-              const __grid_constant__ CUtensorMap tm_c, int M, int N, int K, int splits, const float* __restrict__ bias) {
+gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+              const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c, int M, int N, int K,
+              int kb_split, int splits, const float* __restrict__ bias) {
     extern __shared__ uint8_t gm_smem_raw[];
     uint8_t* smem = gm_smem_raw + ((1024u - (gm_smem_u32(gm_smem_raw) & 1023u)) & 1023u);
     constexpr uint32_t A_BYTES = GM_SLAB, B_BYTES = (uint32_t)BN * 128u;
@@ -149,6 +150,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
         for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&conv[i], GM_CONV_WARPS); gm_mbar_init(&empty[i], 1); }
@@ -180,7 +182,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                         for (int c = 0; c < GM_BM / 32; ++c)
                             gm_tma_load_2d(st + c * GM_CHUNK, &tm_a, &full[stage], mt * GM_BM + c * 32, kb * GM_BK);
                     } else {
-                        gm_tma_load_2d(st, &tm_a, &full[stage], kb * GM_BK, mt * GM_BM);
+                        // K-concatenated A = [A1 | A2] (a torch.cat along the channels that is never materialised): K blocks
+                        // below kb_split come from the first matrix, the rest from the second
+                        if (kb < kb_split) gm_tma_load_2d(st, &tm_a, &full[stage], kb * GM_BK, mt * GM_BM);
+                        else               gm_tma_load_2d(st, &tm_a2, &full[stage], (kb - kb_split) * GM_BK, mt * GM_BM);
                     }
                     const uint32_t sb = st + 2 * A_BYTES;
                     if (B_MN) {
@@ -325,7 +330,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 // in ascending s, the 8 group sums are added in ascending group order -- a fixed summation tree (deterministic, no
 // atomics) with 8 independent load chains per element instead of one serial chain of `splits` dependent L2 round trips.
 __global__ void __launch_bounds__(256)
-gemm_reduce_kernel(const float* __restrict__ part, long n, int splits, float* __restrict__ out) {
+gemm_reduce_kernel(const float* __restrict__ part, long n, int N, long ldc, int splits, float* __restrict__ out) {
     __shared__ float red[8][32];
     const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int per = (splits + 7) / 8;
@@ -343,7 +348,7 @@ gemm_reduce_kernel(const float* __restrict__ part, long n, int splits, float* __
             float t = red[0][e];
 #pragma unroll
             for (int k = 1; k < 8; ++k) t = __fadd_rn(t, red[k][e]);
-            out[i] = t;
+            out[(i / N) * ldc + (i % N)] = t;
         }
         __syncthreads();
     }
@@ -411,8 +416,8 @@ static int gm_tile_n(int M, int N, int K) {
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
-                     const float* bias, cudaStream_t s) {
+static int gm_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
+                     int M, int N, int K, int splits, const float* bias, cudaStream_t s) {
     const size_t smem = (size_t)STAGES * (2 * GM_SLAB + 2 * (size_t)BN * 128) + 2 * GM_SLAB + 64 * 8 + 1024;
     cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -423,19 +428,19 @@ static int gm_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     const int grid = units < sms ? units : sms;
     // algorithmic work: 2 M N K flop counted once (the kernel issues 3x); operands once + result bytes
     PCNBR_TIMED("gemm3x_kernel", s, 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), 2.0 * M * (double)N * K,
-                (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, tb, tc, M, N, K, splits, bias)));
+                (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
 template <bool A_MN, bool B_MN>
-static int gm_dispatch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
-                       const float* bias, cudaStream_t s) {
+static int gm_dispatch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
+                       int M, int N, int K, int splits, const float* bias, cudaStream_t s) {
     switch (gm_tile_n(M, N, K)) {                                            // stages: what fits beside the 32 KB store staging
-        case 256: return gm_launch<256, 2, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
-        case 128: return gm_launch<128, 3, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
-        case 64:  return gm_launch<64, 4, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
-        default:  return gm_launch<32, 4, A_MN, B_MN>(ta, tb, tc, M, N, K, splits, bias, s);
+        case 256: return gm_launch<256, 2, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, s);
+        case 128: return gm_launch<128, 3, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, s);
+        case 64:  return gm_launch<64, 4, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, s);
+        default:  return gm_launch<32, 4, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, s);
     }
 }
 
@@ -471,11 +476,15 @@ extern "C" size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits) {
     return splits > 1 ? sizeof(float) * (size_t)splits * (size_t)M * (size_t)N : 0;
 }
 
-extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, int M, int N, int K,
-                                const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+extern "C" int pcnbr_gemm3x_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
+                                   int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
+                                   size_t ws_bytes, pcnbr_stream_t stream) {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
     if ((lda % 4) || (ldb % 4) || (((uintptr_t)A | (uintptr_t)B) & 15)) return PCNBR_E_BADARG;    // TMA: 16-byte pitch and base
-    if (lda < (a_mn ? M : K) || ldb < (b_mn ? N : K)) return PCNBR_E_BADARG;
+    const int Ka = A2 ? K1 : K;                                           // columns that come from A
+    if (lda < (a_mn ? M : Ka) || ldb < (b_mn ? N : K)) return PCNBR_E_BADARG;
+    if (A2 && (a_mn || K1 <= 0 || K1 >= K || (K1 % GM_BK) || (lda2 % 4) || ((uintptr_t)A2 & 15) || lda2 < K - K1)) return PCNBR_E_BADARG;
+    if (ldc < N || (ldc % 4) || ((uintptr_t)C & 15)) return PCNBR_E_BADARG;                        // TMA store: 16-byte base and pitch
     if (splits > 1 && (!ws || ws_bytes < pcnbr_gemm3x_ws_bytes(M, N, K, splits))) return PCNBR_E_WORKSPACE;
     if (splits > 1 && bias) return PCNBR_E_BADARG;                        // bias with split-K is not supported
     {
@@ -484,25 +493,34 @@ extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float*
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int bn = gm_tile_n(M, N, K);
-    CUtensorMap ta, tb;
-    int rc = a_mn ? gm_make_map(&ta, A, M, K, lda, 32, true) : gm_make_map(&ta, A, K, M, lda, 128, false);
+    CUtensorMap ta, ta2, tb;
+    int rc = a_mn ? gm_make_map(&ta, A, M, K, lda, 32, true) : gm_make_map(&ta, A, Ka, M, lda, 128, false);
+    if (!rc && A2) rc = gm_make_map(&ta2, A2, K - K1, M, lda2, 128, false);
+    if (!A2) ta2 = ta;
     if (!rc) rc = b_mn ? gm_make_map(&tb, B, N, K, ldb, 32, true) : gm_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128, false);
     if (rc) return rc;
+    const int kb_split = A2 ? K1 / GM_BK : (K + GM_BK - 1) / GM_BK;
     float* out = splits > 1 ? (float*)ws : C;
     const float* b = splits > 1 ? nullptr : bias;
-    if (((uintptr_t)out & 15) || (N % 4)) return PCNBR_E_BADARG;          // TMA store: 16-byte base and row pitch
+    if ((uintptr_t)out & 15) return PCNBR_E_BADARG;
     CUtensorMap tc;
-    rc = gm_make_map_c(&tc, out, M, N, N, splits);
+    rc = gm_make_map_c(&tc, out, M, N, splits > 1 ? N : ldc, splits);
     if (rc) return rc;
-    if (a_mn) rc = b_mn ? gm_dispatch<true, true>(ta, tb, tc, M, N, K, splits, b, s) : gm_dispatch<true, false>(ta, tb, tc, M, N, K, splits, b, s);
-    else      rc = b_mn ? gm_dispatch<false, true>(ta, tb, tc, M, N, K, splits, b, s) : gm_dispatch<false, false>(ta, tb, tc, M, N, K, splits, b, s);
+    if (a_mn) rc = b_mn ? gm_dispatch<true, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, s) : gm_dispatch<true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, s);
+    else      rc = b_mn ? gm_dispatch<false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, s) : gm_dispatch<false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, s);
     if (rc) return rc;
     if (splits > 1) {
         const long n = (long)M * N;
         const int grid = (int)((n + 31) / 32 < 148L * 8 ? (n + 31) / 32 : 148L * 8);
         PCNBR_TIMED("gemm_reduce_kernel", s, 4.0 * n * (splits + 1), (double)n * splits,
-                    (gemm_reduce_kernel<<<grid, 256, 0, s>>>((const float*)ws, n, splits, C)));
+                    (gemm_reduce_kernel<<<grid, 256, 0, s>>>((const float*)ws, n, N, ldc, splits, C)));
         PCNBR_CHECK_LAUNCH();
     }
     return 0;
+}
+
+extern "C" int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, int M, int N, int K,
+                                const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (N % 4) return PCNBR_E_BADARG;
+    return pcnbr_gemm3x_ex_f32(A, lda, a_mn, nullptr, 0, 0, B, ldb, b_mn, M, N, K, bias, C, N, splits, ws, ws_bytes, stream);
 }

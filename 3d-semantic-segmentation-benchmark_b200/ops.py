@@ -16,7 +16,7 @@ from . import _lib
 __all__ = [
     "NeighborIndex", "farthest_point_sample", "query_ball_point", "knn_points", "knn_graph",
     "square_distance", "index_points", "group_points", "max_pool_neighbors", "three_interpolate",
-    "edge_features", "edgeconv_fused", "aux_stream", "join_aux", "on_stream", "PyramidGeometry", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows",
+    "edge_features", "edgeconv_fused", "aux_stream", "join_aux", "on_stream", "PyramidGeometry", "linear_rows", "batchnorm_act_rows", "linear_bn_act_rows", "linear_bn_act_maxpool_rows", "linear_bn_act_cat_rows",
 ]
 
 
@@ -737,19 +737,23 @@ def batchnorm_act_rows(rows: torch.Tensor, bn, negative_slope: float) -> torch.T
 # ----------------------------------------------------------------------------- 1x1 convolution as a tensor-core GEMM
 
 
-def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None) -> torch.Tensor:
+def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=None, K1: int = 0, out=None) -> torch.Tensor:
     """C (M,N) = A (M,K) . B (N,K)^T (+ bias) on tcgen05, 3xTF32 from the fp32 operands (fp32-grade accuracy).
-    a_mn / b_mn: the operand is stored transposed ((K,M) / (K,N) row-major).  Operands are 2-D, unit inner stride."""
+    a_mn / b_mn: the operand is stored transposed ((K,M) / (K,N) row-major).  Operands are 2-D, unit inner stride, any
+    16-byte row pitch.  A2: A is the channel concatenation [A (M,K1) | A2 (M,K-K1)] (never materialised).  out: a
+    preallocated (M,N) view with unit inner stride (e.g. a column block of a wider matrix)."""
     splits = 1 if bias is not None else _lib.size("pcnbr_gemm3x_splits", M, N, K)
     nb = _lib.size("pcnbr_gemm3x_ws_bytes", M, N, K, splits)
     ws = _ws(nb, A.device)
-    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
-    _lib.call("pcnbr_gemm3x_f32", A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
-              bias.data_ptr() if bias is not None else None, out.data_ptr(), splits, ws.data_ptr(), nb, _stream())
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.call("pcnbr_gemm3x_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
+              A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+              bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0), splits, ws.data_ptr(), nb, _stream())
     return out
 
 
-def _wgrad3x(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None) -> torch.Tensor:
     """dW (Cout,Cin) = gy^T x for gy (R,Cout), x (R,Cin), both contiguous.  For narrow layers the 128 x BN tile of the
     split-K GEMM would be mostly zero padding (too few useful bytes in flight per SM), so p consecutive rows are viewed
     as one row of p*Cout / p*Cin channels: the (p*Cout, p*Cin) product of the two views has dW as the sum of its p
@@ -759,8 +763,8 @@ def _wgrad3x(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     p = 1
     while 2 * p * Cout <= 128 and 2 * p * Cin <= 256 and R % (2 * p) == 0 and R // (2 * p) >= 4096:
         p *= 2
-    if p == 1:
-        return _gemm3x(gy, True, x, True, Cout, Cin, R)
+    if p == 1 or out is not None:
+        return _gemm3x(gy, True, x, True, Cout, Cin, R, out=out)
     big = _gemm3x(gy.view(R // p, p * Cout), True, x.view(R // p, p * Cin), True, p * Cout, p * Cin, R // p)
     return big.view(p, Cout, p, Cin).diagonal(dim1=0, dim2=2).sum(dim=-1)
 
@@ -915,6 +919,83 @@ def linear_bn_act_maxpool_rows(rows: torch.Tensor, weight: torch.Tensor, bias, b
     y = _LinearBnActPoolFn.apply(_c(rows).view(nrows, cin), _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
                                  float(bn.eps), float(negative_slope), K)
     return y.view(Bc, Cc, cout)
+
+
+class _LinearBnActCatFn(torch.autograd.Function):
+    """act(BatchNorm([x1 | x2] W^T + b)): _LinearBnActFn for a layer whose input is a channel concatenation
+    (models/dgcnn/dgcnn.py:147,233: cat((x1..x4[, colour], x5)) -> conv6).  The concatenated (R, K1+K2) matrix -- 369 MB at
+    16 x 4096 points -- is never built: the forward GEMM streams its K blocks from the two matrices in turn, the backward
+    writes the two input gradients and the two column blocks of the weight gradient directly."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, w, b, gamma, beta, rm, rv, training, momentum, eps, slope):
+        R, K1 = x1.shape
+        K2 = x2.shape[1]
+        C = w.shape[0]
+        dev = x1.device
+        h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1)
+        if training:
+            nblk = _lib.size("pcnbr_bn_blocks", R, C)
+            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+            _lib.call("pcnbr_bn_stats_f32", h.data_ptr(), R, C, partial.data_ptr(), _stream())
+            stats = _bn_finalize(partial, nblk, h, R, C, gamma, beta, eps, momentum, rm, rv, dev)
+        else:
+            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        y = torch.empty_like(h)
+        _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), _stream())
+        ctx.save_for_backward(x1, x2, w, h, stats)
+        ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x1, x2, w, h, stats = ctx.saved_tensors
+        training, slope, has_b, has_gamma, has_beta = ctx.consts
+        R, K1 = x1.shape
+        K2 = x2.shape[1]
+        C = w.shape[0]
+        dev = x1.device
+        gy = _c(gy)
+        nblk = _lib.size("pcnbr_bn_blocks", R, C)
+        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
+                  partial.data_ptr(), None, _stream())
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        coef = torch.empty(4, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
+                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+        dh = torch.empty_like(h)
+        _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
+                  dh.data_ptr(), _stream())
+        # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
+        dx1 = _gemm3x(dh, False, w[:, :K1], True, R, K1, C) if ctx.needs_input_grad[0] else None
+        dx2 = _gemm3x(dh, False, w[:, K1:], True, R, K2, C) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty_like(w)
+            _wgrad3x(dh, x1, out=dw[:, :K1])
+            _wgrad3x(dh, x2, out=dw[:, K1:])
+        db = None
+        if has_b and ctx.needs_input_grad[3]:
+            db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
+        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 6
+
+
+def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float):
+    """act(bn(cat(rows1, rows2, dim=-1) @ weight^T + bias)) without building the concatenation."""
+    k1, k2 = rows1.shape[-1], rows2.shape[-1]
+    cout = weight.shape[0]
+    nrows = rows1.numel() // max(k1, 1)
+    fused = (not _GEMM_LIBRARY and rows1.is_cuda and rows1.dtype == torch.float32 and rows2.dtype == torch.float32
+             and weight.dtype == torch.float32 and nrows >= 1024 and k1 % 32 == 0 and k2 % 4 == 0 and cout % 4 == 0
+             and weight.shape[1] == k1 + k2 and _lib.size("pcnbr_bn_supported", nrows, cout))
+    if not fused:
+        return linear_bn_act_rows(torch.cat((rows1, rows2), dim=-1), weight, bias, bn, negative_slope)
+    training, momentum, rm, rv = _bn_mode(bn)
+    y = _LinearBnActCatFn.apply(_c(rows1).view(nrows, k1), _c(rows2).view(nrows, k2), _c(weight), bias, bn.weight, bn.bias,
+                                rm, rv, training, momentum, float(bn.eps), float(negative_slope))
+    return y.view(*rows1.shape[:-1], cout)
 
 
 def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float) -> torch.Tensor:

@@ -204,6 +204,13 @@ PCNBR_API int pcnbr_gemm3x_splits(int M, int N, int K);
 PCNBR_API size_t pcnbr_gemm3x_ws_bytes(int M, int N, int K, int splits);
 PCNBR_API int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* B, long ldb, int b_mn, int M, int N, int K,
                      const float* bias, float* C, int splits, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+/* Extended form.  A2 != NULL: A is the K-concatenation [A (M,K1) | A2 (M,K-K1)] of two row-major matrices (pitches lda,
+ * lda2; K1 % 32 == 0, a_mn must be 0) -- a torch.cat along the channels in front of a convolution (dgcnn.py:147,
+ * cat((x1..x4, x5)) -> conv6) that is never materialised.  ldc: row pitch of C (>= N, % 4 == 0), so a GEMM can write a
+ * column block of a wider matrix (the two halves of that layer's weight gradient).  A2 == NULL, ldc == N: as above. */
+PCNBR_API int pcnbr_gemm3x_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
+                        int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
+                        size_t ws_bytes, pcnbr_stream_t stream);
 
 /* ---- evaluation metrics ---------------------------------- Training/metrics.py:3-146
  * pred (B,N,C) scores (softmax or logits: only the argmax matters), onehot (B,N,C) uint8 labels, lengths (B) int64

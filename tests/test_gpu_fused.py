@@ -264,3 +264,28 @@ def test_linear_bn_act_maxpool_rows_matches_fp64(pkg, dev, G, K, Cin, Cout, slop
     _close(bnd.bias.grad, bn64.bias.grad, 1e-4)
     _close(bnd.running_mean, bn64.running_mean, 1e-5)
     _close(bnd.running_var, bn64.running_var, 1e-4)
+
+
+@pytest.mark.parametrize("R,K1,K2,Cout", [(8192, 384, 1024, 512), (4096, 64, 36, 128)])
+def test_linear_bn_act_cat_rows_equals_materialised_concatenation(pkg, dev, R, K1, K2, Cout):
+    """ops.linear_bn_act_cat_rows (dgcnn.py:147: cat((x1..x4, x5)) -> conv6 -> bn6 -> LeakyReLU) never builds the
+    concatenated matrix; it must give what the same block gives on torch.cat of the two inputs."""
+    import copy
+    g = torch.Generator().manual_seed(R + K1)
+    x1 = (torch.randn(R, K1, generator=g) * 0.5).to(dev)
+    x2 = (torch.randn(R, K2, generator=g) * 0.5 + 0.1).to(dev)
+    w = (torch.randn(Cout, K1 + K2, generator=g) / (K1 + K2) ** 0.5).to(dev)
+    gy = torch.randn(R, Cout, generator=g).to(dev)
+    bn_a = torch.nn.BatchNorm1d(Cout).to(dev)
+    bn_b = copy.deepcopy(bn_a)
+    a1, a2, wa = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    b1, b2, wb = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ya = pkg.ops.linear_bn_act_cat_rows(a1, a2, wa, None, bn_a, 0.2)
+    yb = pkg.ops.linear_bn_act_rows(torch.cat((b1, b2), dim=1), wb, None, bn_b, 0.2)
+    ya.backward(gy); yb.backward(gy)
+    _close(ya, yb, 1e-6)
+    _close(a1.grad, b1.grad, 1e-5)
+    _close(a2.grad, b2.grad, 1e-5)
+    _close(wa.grad, wb.grad, 1e-5)
+    _close(bn_a.weight.grad, bn_b.weight.grad, 1e-5)
+    _close(bn_a.running_var, bn_b.running_var, 1e-6)
