@@ -270,7 +270,8 @@ def run_ours(args):
     net = build_model(pkg, args.model).to(dev)
     pkg.train.broadcast_parameters(net)
     bucket = pkg.train.FlatGradBucket(net, steal_grads=True)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=not args.no_graph)
+    # torch's fused Adam: one multi-tensor kernel per step instead of ~8 (same update rule as the reference's Adam(lr=1e-3))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
 
     n_batches = 4                                        # rotate inputs; activations (GBs) >> L2 anyway
     host, devb = [], []
