@@ -55,12 +55,14 @@ PROTOTYPES = {
     "pcnbr_gemm3x_f32": (_I, [_P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),
     "pcnbr_gemm3x_ex_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _L, _I, _P, _Z, _P]),
     "pcnbr_confusion_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "pcnbr_masked_ce_blocks": (_I, [_I]),
+    "pcnbr_masked_ce_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "pcnbr_prof_enable": (None, [_I]),
     "pcnbr_prof_collect": (_I, [_P, _Z]),
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
-KERNELS_PER_CALL = {"pcnbr_csr_build": 4, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_tc_debug_f32": 5}
+KERNELS_PER_CALL = {"pcnbr_masked_ce_f32": 2, "pcnbr_csr_build": 4, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_tc_debug_f32": 5}
 
 _lib = None
 launches = 0          # number of libpcnbr CUDA kernels launched by this process (bench.py reports it)

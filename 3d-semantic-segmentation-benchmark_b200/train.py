@@ -10,10 +10,38 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 
+class _MaskedCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, onehot, lengths):
+        from . import _lib
+        from .ops import _stream
+        B, L, C = logits.shape
+        dev = logits.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0]
+        grad = torch.empty_like(logits) if need else None
+        partial = torch.empty(B * _lib.size("pcnbr_masked_ce_blocks", L), dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_masked_ce_f32", logits.data_ptr(), onehot.data_ptr(), lengths.data_ptr(), B, L, C, loss.data_ptr(),
+                  grad.data_ptr() if need else None, partial.data_ptr(), _stream())
+        if need:
+            ctx.save_for_backward(grad)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
 def masked_onehot_cross_entropy(logits: torch.Tensor, targets_onehot: torch.Tensor, pad_starts: torch.Tensor):
-    """Mean cross entropy over the unpadded points; same value as the reference's
-    Training/train_model.py:15-57 but without its host sync (`total_non_pad.item()`, :53)."""
-    B, L, _ = logits.shape
+    """Mean cross entropy over the unpadded points; same value as the reference's Training/train_model.py:15-57 but
+    without its host sync (`total_non_pad.item()`, :53).  On CUDA fp32 logits with <= 64 classes: one fused kernel that
+    also produces the gradient (csrc/loss.cu); otherwise the reference's op sequence in torch."""
+    B, L, C = logits.shape
+    if logits.is_cuda and logits.dtype == torch.float32 and C <= 64:
+        onehot = targets_onehot.to(device=logits.device, dtype=torch.uint8).contiguous()
+        lens = pad_starts.to(device=logits.device, dtype=torch.int64).contiguous()
+        return _MaskedCEFn.apply(logits.contiguous(), onehot, lens)
     logp = F.log_softmax(logits, dim=-1)
     tok = -(targets_onehot.to(logp.dtype) * logp).sum(dim=-1)
     mask = (torch.arange(L, device=logits.device).unsqueeze(0) < pad_starts.to(logits.device).long().unsqueeze(1)).to(logp.dtype)

@@ -220,6 +220,14 @@ PCNBR_API int pcnbr_gemm3x_ex_f32(const float* A, long lda, int a_mn, const floa
 PCNBR_API int pcnbr_confusion_f32(const float* pred, const uint8_t* onehot, const long long* lengths, int B, int N, int C,
                         long long* matrix, pcnbr_stream_t stream);
 
+/* ---- training loss ---------------------------------------- Training/train_model.py:15-57
+ * Masked one-hot cross entropy: loss[0] = mean over the unpadded points (n < lengths[b]) of -sum_c onehot * log_softmax
+ * (0 when every point is padding); dlogits (B,L,C), if non-NULL, receives d loss / d logits in the same pass.
+ * partial: B * pcnbr_masked_ce_blocks(L) floats of scratch.  No host synchronisation; C <= 64. */
+PCNBR_API int pcnbr_masked_ce_blocks(int L);
+PCNBR_API int pcnbr_masked_ce_f32(const float* logits, const uint8_t* onehot, const long long* lengths, int B, int L, int C,
+                        float* loss, float* dlogits, float* partial, pcnbr_stream_t stream);
+
 /* ---- measurement hook (bench.py roofline, kernel sweep) -- not part of the reference interface
  * pcnbr_prof_enable(1): bracket every kernel this library launches with CUDA events on its launch stream and
  * remember the launch's ALGORITHMIC bytes / flops.  Must be off while a CUDA graph is captured.

@@ -65,3 +65,31 @@ def test_pointnetpp_miou_matches_oracle_model_within_bar(pkg, dev):
     agree = (p_ref.argmax(-1) == p_our.cpu().argmax(-1)).float().mean().item()
     assert abs(100.0 * miou_our - 100.0 * miou_ref) <= 0.1, (miou_our, miou_ref)
     assert agree > 0.999
+
+
+@pytest.mark.parametrize("B,L,C", [(16, 4096, 13), (3, 1000, 14), (2, 77, 5)])
+def test_masked_cross_entropy_value_and_gradient(pkg, dev, B, L, C):
+    """train.masked_onehot_cross_entropy on CUDA = Training/train_model.py:15-57 (log_softmax, -sum(onehot*logp), position
+    mask, masked mean) in one fused kernel with its gradient: against the float64 formula, padded and empty clouds."""
+    g = torch.Generator().manual_seed(B * L + C)
+    logits = torch.randn(B, L, C, generator=g) * 3.0
+    lab = torch.nn.functional.one_hot(torch.randint(0, C, (B, L), generator=g), C).to(torch.uint8)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    lens[0], lens[-1] = L, 0
+    x64 = logits.double().requires_grad_(True)
+    logp = torch.log_softmax(x64, dim=-1)
+    tok = -(lab.double() * logp).sum(-1)
+    mask = (torch.arange(L).unsqueeze(0) < lens.unsqueeze(1)).double()
+    want = (tok * mask).sum() / mask.sum()
+    (want * 2.5).backward()
+    xd = logits.to(dev).requires_grad_(True)
+    launches0 = pkg._lib.launches
+    got = pkg.train.masked_onehot_cross_entropy(xd, lab.to(dev), lens.to(dev))
+    assert pkg._lib.launches == launches0 + 2
+    (got * 2.5).backward()
+    assert abs(got.item() - want.item()) <= 2e-6 * abs(want.item())
+    err = (xd.grad.cpu().double() - x64.grad).abs().max().item()
+    assert err <= 1e-6 * x64.grad.abs().max().item() + 1e-12
+    # every point padded: loss 0, gradient 0 (train_model.py:53-54)
+    z = pkg.train.masked_onehot_cross_entropy(xd.detach().requires_grad_(True), lab.to(dev), torch.zeros(B, dtype=torch.int64, device=dev))
+    assert z.item() == 0.0
