@@ -230,6 +230,9 @@ def roofline_for(kernels, peaks):
            "traffic_algorithmic_bytes_same_shape": (ncu_traffic(name) or {}).get("algorithmic_bytes_same_shape"),
            "avg_launch_ms": d["ms"] / d["calls"], "calls": d["calls"], "peak_source": peaks["source"],
            "algorithmic_per_launch": b["algorithmic"] / d["calls"]}
+    if name == "gemm3x_kernel" and b["bound"] == "tensor":
+        # fp32-grade accuracy costs three TF32 instructions per algorithmic flop: the kernel's own ceiling is peak / 3
+        out["issued_frac"] = 3.0 * b["frac"]
     out["note"] = ("flops counted once (2 M N K per GEMM, 2 N^2 F per kNN cloud), whatever the 3xTF32 kernel issues" if b["bound"] == "tensor" else
                    "algorithmic (compulsory) bytes; gathers that hit L2 are not counted" if b["bound"] == "hbm" else
                    "algorithmic lane-ops / flops on the FP32 pipe")
