@@ -143,6 +143,23 @@ class UnitPointNet(nn.Module):
         return h.permute(0, 2, 1)
 
 
+def _unit_forward_rows_cat(self, rows1: torch.Tensor, rows2: torch.Tensor) -> torch.Tensor:
+    """UnitPointNet on the channel concatenation [rows1 | rows2] of two point-major (B,N,*) tensors -> (B,N,Cout): the
+    skip connection of FeaturePropagation (torch.cat, common.py:234-237) is read by the first GEMM from the two tensors in
+    place instead of being materialised."""
+    h = None
+    for i, (conv, bn) in enumerate(zip(self.conv, self.batch)):
+        w = conv.weight.view(conv.out_channels, conv.in_channels)
+        if i == 0:
+            h = ops.linear_bn_act_cat_rows(rows1, rows2, w, conv.bias, bn, 0.0)
+        else:
+            h = ops.linear_bn_act_rows(h, w, conv.bias, bn, 0.0)
+    return h
+
+
+UnitPointNet.forward_rows_cat = _unit_forward_rows_cat
+
+
 class SetAbstraction(nn.Module):
     """FPS -> ball-query group -> MiniPointNet -> max over K   [common.py:180-214]."""
 
@@ -182,8 +199,9 @@ class FeaturePropagation(nn.Module):
     def forward(self, coords_1, coords_2, features_1, features_2, _geom=None):
         """_geom (internal): (NeighborIndex, d2) of the 3-NN table precomputed by ops.PyramidGeometry."""
         up = interpolate(features_2, coords_1, coords_2) if _geom is None else ops.three_interpolate(features_2, _geom[0], _geom[1])
-        feats = up if features_1 is None else torch.cat([features_1, up], dim=-1)
-        return self.point_net(feats.permute(0, 2, 1)).permute(0, 2, 1)
+        if features_1 is None:
+            return self.point_net(up.permute(0, 2, 1)).permute(0, 2, 1)
+        return self.point_net.forward_rows_cat(features_1, up)
 
 
 class InvResMLP(nn.Module):

@@ -1024,6 +1024,15 @@ def linear_rows(rows: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | N
     stride, uniform row pitch that is a multiple of 4 floats)."""
     cin, cout = weight.shape[1], weight.shape[0]
     nrows = rows.numel() // max(cin, 1)
+    if (cout % 4 and cout >= 8 and cin % 4 == 0 and nrows >= 16384 and not _GEMM_LIBRARY and rows.is_cuda
+            and rows.dtype == torch.float32 and weight.dtype == torch.float32):
+        # class heads (13 / 14 outputs): zero-pad the output channels to a multiple of 4 so that the layer -- above all its
+        # weight gradient over all the points, which the library runs on one or two CTAs -- goes through the tensor-core
+        # GEMM; the pad outputs are sliced away again (autograd slices the gradients of the padded weight and bias)
+        pad = (-cout) % 4
+        wp = torch.nn.functional.pad(weight, (0, 0, 0, pad))
+        bp = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
+        return linear_rows(rows, wp, bp)[..., :cout]
     usable = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
               and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4)
     if not usable:

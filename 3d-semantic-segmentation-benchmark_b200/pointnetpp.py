@@ -40,4 +40,4 @@ class PointNetpp(nn.Module):
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2, _geom=geo.three_nn(1))
         features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0))
         x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
-        return torch.nn.functional.linear(x, self.conv.weight.squeeze(-1), self.conv.bias)
+        return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)

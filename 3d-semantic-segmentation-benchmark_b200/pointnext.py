@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import ops
 from .common import FeaturePropagation, InvResMLP, SetAbstraction, UnitPointNet
 
 
@@ -48,4 +49,4 @@ class PointNeXt(nn.Module):
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2)
         features_0 = self.fp1(coords_0, coords_1, features_0, features_1)
         x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
-        return torch.nn.functional.linear(x, self.conv.weight.squeeze(-1), self.conv.bias)
+        return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)
