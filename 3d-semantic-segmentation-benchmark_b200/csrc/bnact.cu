@@ -182,11 +182,31 @@ __device__ __forceinline__ float ba_act(float x, float mean, float scale, float 
     return y > 0.f ? y : y * slope;
 }
 
-// y[r, c] = act((x[r, c] - mean) * gamma * rstd + beta)
+// Dropout fused behind the activation (models/dgcnn/dgcnn.py:117,122: BatchNorm -> LeakyReLU -> Dropout): element i is
+// kept (and scaled by 1/(1-p)) iff a counter-based hash of (seed, i) falls above p.  The seed is a device word drawn by
+// the host layer from torch's generator for every forward pass; the backward kernels recompute the same mask from it,
+// so no mask tensor is stored or re-read.  keep4 returns the four multipliers of one float4.
+__device__ __forceinline__ float ba_keep(unsigned long long seed, unsigned long long i, float p, float scale) {
+    unsigned long long z = seed + (i + 1ull) * 0x9E3779B97F4A7C15ull;       // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f) >= p ? scale : 0.f;
+}
+__device__ __forceinline__ float4 ba_keep4(const unsigned long long* __restrict__ seedp, long r, int C, int c, float p) {
+    if (!seedp) return make_float4(1.f, 1.f, 1.f, 1.f);
+    const unsigned long long seed = *seedp, i = (unsigned long long)r * (unsigned long long)C + (unsigned long long)c;
+    const float scale = 1.0f / (1.0f - p);
+    return make_float4(ba_keep(seed, i, p, scale), ba_keep(seed, i + 1, p, scale), ba_keep(seed, i + 2, p, scale),
+                       ba_keep(seed, i + 3, p, scale));
+}
+
+// y[r, c] = act((x[r, c] - mean) * gamma * rstd + beta)  (* dropout multiplier)
 template <int NCOL>
 __global__ void __launch_bounds__(BA_T)
 bn_act_fwd_kernel(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb, long R, int C,
-                  const float* __restrict__ stats, float slope, float* __restrict__ y) {
+                  const float* __restrict__ stats, float slope, float* __restrict__ y,
+                  const unsigned long long* __restrict__ drop_seed, float drop_p) {
     const BaMap m = ba_map(C);
     float4 mu[NCOL], sc[NCOL], be[NCOL];
 #pragma unroll
@@ -207,6 +227,10 @@ bn_act_fwd_kernel(const float* __restrict__ a, long lda, const float* __restrict
             o.y = ba_act(v.y, mu[j].y, sc[j].y, be[j].y, slope);
             o.z = ba_act(v.z, mu[j].z, sc[j].z, be[j].z, slope);
             o.w = ba_act(v.w, mu[j].w, sc[j].w, be[j].w, slope);
+            if (drop_seed) {
+                const float4 k = ba_keep4(drop_seed, r, C, c, drop_p);
+                o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+            }
             *reinterpret_cast<float4*>(y + r * C + c) = o;
         }
     }
@@ -217,7 +241,8 @@ template <int NCOL>
 __global__ void __launch_bounds__(BA_T)
 bn_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ a, long lda, const float* __restrict__ b,
                          long ldb, long R, int C, int rows_per_block, const float* __restrict__ stats, float slope,
-                         float* __restrict__ partial, float* __restrict__ gs) {
+                         float* __restrict__ partial, float* __restrict__ gs,
+                         const unsigned long long* __restrict__ drop_seed, float drop_p) {
     const BaMap m = ba_map(C);
     float4 mu[NCOL], rs[NCOL], sc[NCOL], be[NCOL], s1[NCOL], s2[NCOL];
 #pragma unroll
@@ -239,6 +264,10 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__
             const int c = m.col + j * 4 * BA_T;
             const float4 v = ba_ld(a, lda, b, ldb, r, c);
             float4 g = *reinterpret_cast<const float4*>(gy + r * C + c);
+            if (drop_seed) {
+                const float4 k = ba_keep4(drop_seed, r, C, c, drop_p);
+                g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+            }
             const float dx = v.x - mu[j].x, dy = v.y - mu[j].y, dz = v.z - mu[j].z, dw = v.w - mu[j].w;
             g.x = fmaf(dx, sc[j].x, be[j].x) > 0.f ? g.x : g.x * slope;
             g.y = fmaf(dy, sc[j].y, be[j].y) > 0.f ? g.y : g.y * slope;
@@ -276,7 +305,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float*
 template <int NCOL>
 __global__ void __launch_bounds__(BA_T)
 bn_act_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ x, long R, int C,
-                        const float* __restrict__ stats, const float* __restrict__ coef, float slope, float* __restrict__ dx) {
+                        const float* __restrict__ stats, const float* __restrict__ coef, float slope, float* __restrict__ dx,
+                        const unsigned long long* __restrict__ drop_seed, float drop_p) {
     const BaMap m = ba_map(C);
     float4 mu[NCOL], sc[NCOL], be[NCOL], gr[NCOL], c1[NCOL], c2[NCOL];
 #pragma unroll
@@ -296,6 +326,10 @@ bn_act_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ 
             const int c = m.col + j * 4 * BA_T;
             const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
             float4 g = *reinterpret_cast<const float4*>(gy + r * C + c);
+            if (drop_seed) {
+                const float4 k = ba_keep4(drop_seed, r, C, c, drop_p);
+                g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+            }
             const float ex = v.x - mu[j].x, ey = v.y - mu[j].y, ez = v.z - mu[j].z, ew = v.w - mu[j].w;
             g.x = fmaf(ex, sc[j].x, be[j].x) > 0.f ? g.x : g.x * slope;
             g.y = fmaf(ey, sc[j].y, be[j].y) > 0.f ? g.y : g.y * slope;
@@ -446,21 +480,25 @@ extern "C" int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float
 }
 
 extern "C" int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, long ldb, long R, int C, const float* stats,
-                                    float slope, float* y, pcnbr_stream_t stream) {
+                                    float slope, float* y, const unsigned long long* drop_seed, float drop_p,
+                                    pcnbr_stream_t stream) {
+    if (drop_seed && !(drop_p >= 0.f && drop_p < 1.f)) return PCNBR_E_BADARG;
     if (!a || !stats || !y) return PCNBR_E_BADARG;
     if (!ba_supported(R, C) || (lda % 4) || (b && (ldb % 4)) || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y | (uintptr_t)stats) & 15))
         return PCNBR_E_TOOLARGE;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = ba_grid(R, C);
     const double wb = 4.0 * R * C * (b ? 3.0 : 2.0), wf = 4.0 * R * C;
-    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<2><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y)));
-    else              PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<1><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y)));
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<2><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y, drop_seed, drop_p)));
+    else              PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<1><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y, drop_seed, drop_p)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int pcnbr_bn_act_bwd_reduce_f32(const float* gy, const float* a, long lda, const float* b, long ldb, long R, int C,
-                                           const float* stats, float slope, float* partial, float* gs, pcnbr_stream_t stream) {
+                                           const float* stats, float slope, float* partial, float* gs,
+                                           const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream) {
+    if (drop_seed && !(drop_p >= 0.f && drop_p < 1.f)) return PCNBR_E_BADARG;
     if (!gy || !a || !stats || !partial) return PCNBR_E_BADARG;
     if (!ba_supported(R, C) || (lda % 4) || (b && (ldb % 4)) ||
         (((uintptr_t)a | (uintptr_t)b | (uintptr_t)gy | (uintptr_t)gs | (uintptr_t)stats) & 15))
@@ -469,8 +507,8 @@ extern "C" int pcnbr_bn_act_bwd_reduce_f32(const float* gy, const float* a, long
     const int rpb = (int)((R + nblk - 1) / nblk);
     cudaStream_t s = (cudaStream_t)stream;
     const double wb = 4.0 * R * C * (2.0 + (b ? 1.0 : 0.0) + (gs ? 1.0 : 0.0)), wf = 8.0 * R * C;
-    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_reduce_kernel", s, wb, wf, (bn_act_bwd_reduce_kernel<2><<<nblk, BA_T, 0, s>>>(gy, a, lda, b, ldb, R, C, rpb, stats, slope, partial, gs)));
-    else              PCNBR_TIMED("bn_act_bwd_reduce_kernel", s, wb, wf, (bn_act_bwd_reduce_kernel<1><<<nblk, BA_T, 0, s>>>(gy, a, lda, b, ldb, R, C, rpb, stats, slope, partial, gs)));
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_reduce_kernel", s, wb, wf, (bn_act_bwd_reduce_kernel<2><<<nblk, BA_T, 0, s>>>(gy, a, lda, b, ldb, R, C, rpb, stats, slope, partial, gs, drop_seed, drop_p)));
+    else              PCNBR_TIMED("bn_act_bwd_reduce_kernel", s, wb, wf, (bn_act_bwd_reduce_kernel<1><<<nblk, BA_T, 0, s>>>(gy, a, lda, b, ldb, R, C, rpb, stats, slope, partial, gs, drop_seed, drop_p)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -486,15 +524,17 @@ extern "C" int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const f
 }
 
 extern "C" int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
-                                          float slope, float* dx, pcnbr_stream_t stream) {
+                                          float slope, float* dx, const unsigned long long* drop_seed, float drop_p,
+                                          pcnbr_stream_t stream) {
+    if (drop_seed && !(drop_p >= 0.f && drop_p < 1.f)) return PCNBR_E_BADARG;
     if (!gy || !x || !stats || !coef || !dx) return PCNBR_E_BADARG;
     if (!ba_supported(R, C) || (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)dx | (uintptr_t)stats | (uintptr_t)coef) & 15))
         return PCNBR_E_TOOLARGE;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = ba_grid(R, C);
     const double wb = 12.0 * R * C, wf = 8.0 * R * C;
-    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<2><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx)));
-    else              PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<1><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx)));
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<2><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx, drop_seed, drop_p)));
+    else              PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<1><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx, drop_seed, drop_p)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -95,6 +95,18 @@ def _pad4(t: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.pad(t, (0, (-t.shape[-1]) % 4))
 
 
+def _fusable_dropout(mods):
+    """(p, remaining modules): a leading nn.Dropout is folded into the fused conv+BatchNorm+activation node (p in training
+    mode; in eval mode or with p = 0 it is the identity and simply dropped)."""
+    if mods and isinstance(mods[0], nn.Dropout):
+        d = mods[0]
+        if not d.training or d.p == 0.0:
+            return 0.0, mods[1:]
+        if d.p < 1.0:
+            return float(d.p), mods[1:]
+    return 0.0, mods
+
+
 def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
     """seq = [Conv1d(kernel 1), BatchNorm1d, LeakyReLU(, Dropout)] applied to point-major rows (B,N,Cin) -> (B,N,Cout).
     A 1x1 convolution IS a GEMM: it is issued as ONE GEMM over the B*N rows (no transposes, no per-batch GEMMs) instead
@@ -107,8 +119,8 @@ def _run_pointwise(seq, rows: torch.Tensor) -> torch.Tensor:
     if w.shape[1] % 4 and w.shape[1] <= 16:                                 # the 3-channel colour branch
         rows, w = _pad4(rows), _pad4(w)
     if len(mods) >= 3 and isinstance(mods[1], nn.modules.batchnorm._BatchNorm) and isinstance(mods[2], nn.LeakyReLU):
-        y = ops.linear_bn_act_rows(rows, w, conv.bias, mods[1], mods[2].negative_slope)
-        rest = mods[3:]
+        p_drop, rest = _fusable_dropout(mods[3:])
+        y = ops.linear_bn_act_rows(rows, w, conv.bias, mods[1], mods[2].negative_slope, p_drop)
     else:
         y = ops.linear_rows(rows, w, conv.bias)
         rest = mods[1:]
@@ -127,8 +139,9 @@ def _run_pointwise_cat(seq, rows1: torch.Tensor, rows2: torch.Tensor) -> torch.T
     conv = mods[0]
     if not (len(mods) >= 3 and isinstance(mods[1], nn.modules.batchnorm._BatchNorm) and isinstance(mods[2], nn.LeakyReLU)):
         return _run_pointwise(seq, torch.cat((rows1, rows2), dim=2))
-    y = ops.linear_bn_act_cat_rows(rows1, rows2, conv.weight.squeeze(-1), conv.bias, mods[1], mods[2].negative_slope)
-    for m in mods[3:]:
+    p_drop, rest = _fusable_dropout(mods[3:])
+    y = ops.linear_bn_act_cat_rows(rows1, rows2, conv.weight.squeeze(-1), conv.bias, mods[1], mods[2].negative_slope, p_drop)
+    for m in rest:
         y = m(y)
     return y
 

@@ -595,7 +595,7 @@ class _EdgeConvFusedFn(torch.autograd.Function):
         out = torch.empty(B, N, O, dtype=torch.float32, device=dev)
         # out = LeakyReLU(BatchNorm(psel + Q)): the two-source form of the fused row kernel, Q read in place from PQ
         _lib.call("pcnbr_bn_act_fwd_f32", psel.data_ptr(), O, PQ.data_ptr() + 4 * O, 2 * O, B * N, O, stats.data_ptr(),
-                  float(slope), out.data_ptr(), _stream())
+                  float(slope), out.data_ptr(), None, 0.0, _stream())
         ctx.nbr, ctx.consts = nbr, (B, N, O, K, M, bool(training), float(slope))
         ctx.save_for_backward(PQ, psel, arg, s1, stats)
         if ctx.needs_input_grad[0]:
@@ -614,7 +614,7 @@ class _EdgeConvFusedFn(torch.autograd.Function):
         nblk = _lib.size("pcnbr_bn_blocks", R, O)
         partial = torch.empty(nblk, 2, O, dtype=torch.float32, device=dev)
         _lib.call("pcnbr_bn_act_bwd_reduce_f32", g.data_ptr(), psel.data_ptr(), O, PQ.data_ptr() + 4 * O, 2 * O, R, O,
-                  stats.data_ptr(), slope, partial.data_ptr(), gs.data_ptr(), _stream())
+                  stats.data_ptr(), slope, partial.data_ptr(), gs.data_ptr(), None, 0.0, _stream())
         dgamma = torch.empty(O, dtype=torch.float32, device=dev)
         dbeta = torch.empty(O, dtype=torch.float32, device=dev)
         coef = torch.empty(4, O, dtype=torch.float32, device=dev)
@@ -689,7 +689,7 @@ class _BnActRowsFn(torch.autograd.Function):
         else:
             stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
         y = torch.empty_like(x)
-        _lib.call("pcnbr_bn_act_fwd_f32", x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), _stream())
+        _lib.call("pcnbr_bn_act_fwd_f32", x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), None, 0.0, _stream())
         ctx.save_for_backward(x, stats)
         ctx.consts = (bool(training), float(slope), gamma is not None, beta is not None)
         return y
@@ -704,7 +704,7 @@ class _BnActRowsFn(torch.autograd.Function):
         nblk = _lib.size("pcnbr_bn_blocks", R, C)
         partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
         _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
-                  partial.data_ptr(), None, _stream())
+                  partial.data_ptr(), None, None, 0.0, _stream())
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dbeta = torch.empty(C, dtype=torch.float32, device=dev)
         coef = torch.empty(4, C, dtype=torch.float32, device=dev)
@@ -714,7 +714,7 @@ class _BnActRowsFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), x.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
-                      dx.data_ptr(), _stream())
+                      dx.data_ptr(), None, 0.0, _stream())
         return dx, (dgamma if has_gamma else None), (dbeta if has_beta else None), None, None, None, None, None, None
 
 
@@ -799,7 +799,7 @@ class _LinearBnActFn(torch.autograd.Function):
     (BatchNorm removes any per-channel shift) and gamma*rstd*sum(g') in eval mode."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope):
+    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0):
         R, Cin = x.shape
         C = w.shape[0]
         dev = x.device
@@ -812,7 +812,12 @@ class _LinearBnActFn(torch.autograd.Function):
         else:
             stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
         y = torch.empty_like(h)
-        _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), _stream())
+        # nn.Dropout behind the activation, fused: one 64-bit seed per forward pass from torch's generator (device side,
+        # so it is redrawn on every CUDA-graph replay); the backward recomputes the mask from it
+        seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=dev) if drop_p > 0.0 else None
+        _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(),
+                  seed.data_ptr() if seed is not None else None, float(drop_p), _stream())
+        ctx.drop = (seed, float(drop_p))
         ctx.save_for_backward(x, w, h, stats)
         ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None)
         return y
@@ -828,7 +833,7 @@ class _LinearBnActFn(torch.autograd.Function):
         nblk = _lib.size("pcnbr_bn_blocks", R, C)
         partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
         _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
-                  partial.data_ptr(), None, _stream())
+                  partial.data_ptr(), None, ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dbeta = torch.empty(C, dtype=torch.float32, device=dev)
         coef = torch.empty(4, C, dtype=torch.float32, device=dev)
@@ -836,13 +841,13 @@ class _LinearBnActFn(torch.autograd.Function):
                   dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
         dh = torch.empty_like(h)
         _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
-                  dh.data_ptr(), _stream())
+                  dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         dx = _gemm3x(dh, False, w, True, R, Cin, C) if ctx.needs_input_grad[0] else None
         dw = _wgrad3x(dh, x) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
-        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None, None, None, None, None, None, None)
+        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None, None, None, None, None, None, None, None)
 
 
 class _LinearBnActPoolFn(torch.autograd.Function):
@@ -887,7 +892,7 @@ class _LinearBnActPoolFn(torch.autograd.Function):
         nblk = _lib.size("pcnbr_bn_blocks", G, C)
         partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
         _lib.call("pcnbr_bn_act_bwd_reduce_f32", gpool.data_ptr(), psel.data_ptr(), C, None, 0, G, C, stats.data_ptr(), slope,
-                  partial.data_ptr(), gs.data_ptr(), _stream())
+                  partial.data_ptr(), gs.data_ptr(), None, 0.0, _stream())
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dbeta = torch.empty(C, dtype=torch.float32, device=dev)
         coef = torch.empty(4, C, dtype=torch.float32, device=dev)
@@ -928,7 +933,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
     writes the two input gradients and the two column blocks of the weight gradient directly."""
 
     @staticmethod
-    def forward(ctx, x1, x2, w, b, gamma, beta, rm, rv, training, momentum, eps, slope):
+    def forward(ctx, x1, x2, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0):
         R, K1 = x1.shape
         K2 = x2.shape[1]
         C = w.shape[0]
@@ -942,7 +947,12 @@ class _LinearBnActCatFn(torch.autograd.Function):
         else:
             stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
         y = torch.empty_like(h)
-        _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), _stream())
+        # nn.Dropout behind the activation, fused: one 64-bit seed per forward pass from torch's generator (device side,
+        # so it is redrawn on every CUDA-graph replay); the backward recomputes the mask from it
+        seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=dev) if drop_p > 0.0 else None
+        _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(),
+                  seed.data_ptr() if seed is not None else None, float(drop_p), _stream())
+        ctx.drop = (seed, float(drop_p))
         ctx.save_for_backward(x1, x2, w, h, stats)
         ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None)
         return y
@@ -959,7 +969,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
         nblk = _lib.size("pcnbr_bn_blocks", R, C)
         partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
         _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
-                  partial.data_ptr(), None, _stream())
+                  partial.data_ptr(), None, ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         dgamma = torch.empty(C, dtype=torch.float32, device=dev)
         dbeta = torch.empty(C, dtype=torch.float32, device=dev)
         coef = torch.empty(4, C, dtype=torch.float32, device=dev)
@@ -967,7 +977,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
                   dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
         dh = torch.empty_like(h)
         _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
-                  dh.data_ptr(), _stream())
+                  dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
         dx1 = _gemm3x(dh, False, w[:, :K1], True, R, K1, C) if ctx.needs_input_grad[0] else None
         dx2 = _gemm3x(dh, False, w[:, K1:], True, R, K2, C) if ctx.needs_input_grad[1] else None
@@ -979,11 +989,13 @@ class _LinearBnActCatFn(torch.autograd.Function):
         db = None
         if has_b and ctx.needs_input_grad[3]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
-        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 6
+        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 7
 
 
-def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float):
-    """act(bn(cat(rows1, rows2, dim=-1) @ weight^T + bias)) without building the concatenation."""
+def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float,
+                           dropout_p: float = 0.0):
+    """act(bn(cat(rows1, rows2, dim=-1) @ weight^T + bias)) without building the concatenation; dropout_p > 0 fuses the
+    nn.Dropout(dropout_p) (training mode) that follows the activation."""
     k1, k2 = rows1.shape[-1], rows2.shape[-1]
     cout = weight.shape[0]
     nrows = rows1.numel() // max(k1, 1)
@@ -991,25 +1003,28 @@ def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: tor
              and weight.dtype == torch.float32 and nrows >= 1024 and k1 % 32 == 0 and k2 % 4 == 0 and cout % 4 == 0
              and weight.shape[1] == k1 + k2 and _lib.size("pcnbr_bn_supported", nrows, cout))
     if not fused:
-        return linear_bn_act_rows(torch.cat((rows1, rows2), dim=-1), weight, bias, bn, negative_slope)
+        return linear_bn_act_rows(torch.cat((rows1, rows2), dim=-1), weight, bias, bn, negative_slope, dropout_p)
     training, momentum, rm, rv = _bn_mode(bn)
     y = _LinearBnActCatFn.apply(_c(rows1).view(nrows, k1), _c(rows2).view(nrows, k2), _c(weight), bias, bn.weight, bn.bias,
-                                rm, rv, training, momentum, float(bn.eps), float(negative_slope))
+                                rm, rv, training, momentum, float(bn.eps), float(negative_slope), float(dropout_p))
     return y.view(*rows1.shape[:-1], cout)
 
 
-def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float) -> torch.Tensor:
+def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float,
+                       dropout_p: float = 0.0) -> torch.Tensor:
     """act(bn(rows @ weight^T + bias)): one "Conv(kernel 1) -> BatchNorm -> ReLU / LeakyReLU" block of
-    models/utils/common.py:125-178 / models/dgcnn/dgcnn.py:95-126 on point-major rows (..., Cin) -> (..., Cout)."""
+    models/utils/common.py:125-178 / models/dgcnn/dgcnn.py:95-126 on point-major rows (..., Cin) -> (..., Cout).
+    dropout_p > 0 fuses the nn.Dropout(dropout_p) (training mode) that follows the activation (dgcnn.py:117,122)."""
     cin, cout = weight.shape[1], weight.shape[0]
     nrows = rows.numel() // max(cin, 1)
     fused = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
              and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4 and _lib.size("pcnbr_bn_supported", nrows, cout))
     if not fused:
-        return batchnorm_act_rows(linear_rows(rows, weight, bias), bn, negative_slope)
+        y = batchnorm_act_rows(linear_rows(rows, weight, bias), bn, negative_slope)
+        return torch.nn.functional.dropout(y, dropout_p, True) if dropout_p > 0.0 else y
     training, momentum, rm, rv = _bn_mode(bn)
     y = _LinearBnActFn.apply(_c(rows).view(nrows, cin), _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
-                             float(bn.eps), float(negative_slope))
+                             float(bn.eps), float(negative_slope), float(dropout_p))
     return y.view(*rows.shape[:-1], cout)
 
 

@@ -161,6 +161,9 @@ PCNBR_API int pcnbr_edgeconv_bwd_f32(const float* gs, const uint8_t* arg, const 
  *   pcnbr_bn_act_bwd_reduce_f32 : g' = gy * act'(pre);  partial = per-block {sum g', sum g' * xhat};  gs (R,C) <- g' if non-NULL
  *   pcnbr_bn_bwd_finalize_f32   : dgamma, dbeta (C) and coef (4,C) = {gamma*rstd, c1, c2r, mean} (c1 = c2r = 0 unless training)
  *   pcnbr_bn_act_bwd_apply_f32  : dx (R,C) = gamma*rstd * g' - c1 - c2r * (x - mean)
+ * drop_seed != NULL (device pointer to one 64-bit word) fuses the nn.Dropout(drop_p) that follows the activation
+ * (dgcnn.py:117,122): y is multiplied by the keep mask / (1 - p) derived from a counter-based hash of (seed, element);
+ * the backward kernels take the same seed and recompute the mask -- nothing is stored.  NULL = no dropout.
  * Deterministic (fixed-order reductions, no atomics). */
 PCNBR_API int pcnbr_bn_supported(long R, int C);
 PCNBR_API int pcnbr_bn_blocks(long R, int C);
@@ -169,13 +172,14 @@ PCNBR_API int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float*
                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                           float* running_var, float* stats, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, long ldb, long R, int C, const float* stats,
-                         float slope, float* y, pcnbr_stream_t stream);
+                         float slope, float* y, const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_act_bwd_reduce_f32(const float* gy, const float* a, long lda, const float* b, long ldb, long R, int C,
-                                const float* stats, float slope, float* partial, float* gs, pcnbr_stream_t stream);
+                                const float* stats, float slope, float* partial, float* gs,
+                                const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const float* stats, double count, int C, int training,
                               float* dgamma, float* dbeta, float* coef, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
-                               float slope, float* dx, pcnbr_stream_t stream);
+                               float slope, float* dx, const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream);
 
 /* ---- BatchNorm + (Leaky)ReLU + max over the K rows of a group, fused ---- common.py:141-147 + 85-86 (SetAbstraction / InvResMLP)
  * h (G*K, C) pre-BatchNorm rows, stats as above.  act(bn(.)) is monotone per channel, so the max over K is taken on h (max

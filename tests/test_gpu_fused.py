@@ -289,3 +289,41 @@ def test_linear_bn_act_cat_rows_equals_materialised_concatenation(pkg, dev, R, K
     _close(wa.grad, wb.grad, 1e-5)
     _close(bn_a.weight.grad, bn_b.weight.grad, 1e-5)
     _close(bn_a.running_var, bn_b.running_var, 1e-6)
+
+
+def test_fused_dropout_mask_and_gradient(pkg, dev):
+    """ops.linear_bn_act_rows(..., dropout_p): the nn.Dropout behind conv6 / conv7 (dgcnn.py:117,122) folded into the
+    BatchNorm+LeakyReLU kernels.  The mask is not stored: the backward recomputes it from the seed -- so the output must be
+    the undropped output times mask/(1-p), the keep rate ~1-p, and all gradients those of multiplying by that same mask."""
+    import copy
+    R, Cin, Cout, p = 16384, 64, 128, 0.5
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(R, Cin, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, generator=g) / 8.0).to(dev)
+    gy = torch.randn(R, Cout, generator=g).to(dev)
+    bn0 = torch.nn.BatchNorm1d(Cout).to(dev)
+    with torch.no_grad():
+        bn0.weight.copy_(torch.rand(Cout, generator=g).to(dev) + 0.5)
+    bn_a, bn_b = copy.deepcopy(bn0), copy.deepcopy(bn0)
+    xa, wa = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    torch.manual_seed(1234)
+    ya = pkg.ops.linear_bn_act_rows(xa, wa, None, bn_a, 0.2, dropout_p=p)
+    ya.backward(gy)
+    xb, wb = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yb = pkg.ops.linear_bn_act_rows(xb, wb, None, bn_b, 0.2)                 # no dropout: LeakyReLU output is never exactly 0
+    mask = (ya != 0).float()
+    keep = mask.mean().item()
+    assert abs(keep - (1 - p)) < 0.01, keep
+    _close(ya, yb.detach() * mask / (1 - p), 1e-6)
+    (yb * mask / (1 - p)).backward(gy)
+    _close(xa.grad, xb.grad, 1e-5)
+    _close(wa.grad, wb.grad, 1e-5)
+    _close(bn_a.weight.grad, bn_b.weight.grad, 1e-5)
+    _close(bn_a.bias.grad, bn_b.bias.grad, 1e-5)
+    # a different draw gives a different mask; the same generator state gives the same one
+    torch.manual_seed(1234)
+    y2 = pkg.ops.linear_bn_act_rows(x, w, None, copy.deepcopy(bn0), 0.2, dropout_p=p)
+    y3 = pkg.ops.linear_bn_act_rows(x, w, None, copy.deepcopy(bn0), 0.2, dropout_p=p)
+    assert torch.equal(y2 != 0, mask.bool()) and not torch.equal(y3 != 0, mask.bool())
+    # rows and columns are both mixed: per-channel and per-row keep rates are all near 1-p
+    assert (mask.mean(0) - (1 - p)).abs().max().item() < 0.03 and (mask.mean(1) - (1 - p)).abs().max().item() < 0.25
