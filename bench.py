@@ -260,6 +260,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version / debug lines off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False       # strict fp32, as the north-star parity bar
     torch.backends.cudnn.allow_tf32 = False
