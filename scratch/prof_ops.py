@@ -18,9 +18,11 @@ for _ in range(reps):
     nbr = ops.NeighborIndex(ops.query_ball_point(0.1, K, xyz, cen), N)
     grouped = ops.group_points(xyz, feat, cen, nbr, None, pad4=True)
     bn = torch.nn.BatchNorm2d(32).to(dev)
-    w = (torch.randn(32, 12, generator=g) * 0.3).to(dev).requires_grad_(True)
+    w = (torch.randn(32, grouped.shape[-1], generator=g) * 0.3).to(dev).requires_grad_(True)
     h = ops.linear_bn_act_rows(grouped, w, None, bn, 0.0)
-    pooled = ops.max_pool_neighbors(h, 2)
+    bn2 = torch.nn.BatchNorm2d(64).to(dev)
+    w2 = (torch.randn(64, 32, generator=g) * 0.2).to(dev).requires_grad_(True)
+    pooled = ops.linear_bn_act_maxpool_rows(h, w2, None, bn2, 0.0)          # last SA1 layer fused with the max pool
     pooled.sum().backward()
     i3, d3 = ops.knn_points(xyz, cen, 3)
     n3 = ops.NeighborIndex(i3, C)
