@@ -23,7 +23,7 @@ template <int NSLOT, bool RADIUS>
 __global__ void __launch_bounds__(256)
 select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N, float r2, int K,
                   int32_t* __restrict__ idx, float* __restrict__ d2out) {
-    __shared__ float sx[SEL_TILE], sy[SEL_TILE], sz[SEL_TILE];
+    __shared__ float4 spt[SEL_TILE];                      // (x, y, z, -) per source point: one LDS.128 per point
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     const bool active = m < M;
@@ -39,36 +39,74 @@ select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int 
     bool full = false;                                       // the list holds K real entries (thr is a real key)
     float thr_f = 0.f;                                       // distance of the K-th entry once full
 
+    // exact path for the 32 points [c0, c0+32) of the tile: 64-bit (key, index) order, insert the survivors
+    auto exact32 = [&](int t0, int tn, int c0) {
+        const int j = c0 + lane;
+        u64 key = PCNBR_KEY_MAX;
+        if (j < tn) {
+            const float4 s = spt[j];
+            float d2 = d2_direct(s.x, s.y, s.z, qx, qy, qz);
+            if (RADIUS && !(d2 <= r2)) d2 = __int_as_float(0x7f800000);       // common.py:58-59
+            key = pack_key(f2ord(d2), (uint32_t)(t0 + j));
+        }
+        uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
+        while (pass) {
+            const int src = __ffs(pass) - 1;
+            pass &= pass - 1;
+            const u64 cand = shfl64(key, src);
+            if (cand < thr) {
+                list.insert(cand, lane);
+                thr = list.at(K - 1);
+            }
+        }
+    };
+
     for (int t0 = 0; t0 < N; t0 += SEL_TILE) {
         const int tn = min(SEL_TILE, N - t0);
+        const int tpad = (tn + 127) & ~127;                  // the fast loop walks whole 128-point steps
         __syncthreads();
-        for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) {
-            const float v = pb[(size_t)t0 * 3 + i];
-            const int pt = i / 3, c = i - pt * 3;
-            (c == 0 ? sx : (c == 1 ? sy : sz))[pt] = v;
+        for (int i = threadIdx.x; i < tpad; i += blockDim.x) {
+            float4 v = make_float4(1e30f, 1e30f, 1e30f, 0.f);   // sentinel: its distance is +inf, never below any threshold
+            if (i < tn) {
+                const float* s = pb + (size_t)(t0 + i) * 3;
+                v = make_float4(s[0], s[1], s[2], 0.f);
+            }
+            spt[i] = v;
         }
         __syncthreads();
         if (!active) continue;
-        // 128 points per step (4 per lane).  Hot path = 8 flops + one float compare per point: a candidate (index j,
-        // larger than every index already in the list) beats the current K-th entry iff its distance is STRICTLY
-        // smaller, so the 64-bit (key,index) order is only materialised for the rare survivors.
-        for (int c0 = 0; c0 < tn; c0 += 128) {
+        int c0 = 0;
+        // start-up: until the list holds K entries every point is a candidate (first tile, first ceil(K/32) groups)
+        for (; !full && c0 < tn; c0 += 32) {
+            exact32(t0, tn, c0);
+            full = thr != PCNBR_KEY_MAX;
+        }
+        thr_f = ord2f((uint32_t)(thr >> 32));
+        for (; c0 < tn && (c0 & 127); c0 += 32) {           // realign to a 128-point boundary
+            exact32(t0, tn, c0);
+            thr_f = ord2f((uint32_t)(thr >> 32));
+        }
+        // Hot loop: 128 points per step (4 per lane), 8 flops + ONE float compare per point.  A candidate's index is
+        // larger than every index already in the list, so it enters iff its distance is STRICTLY smaller than the K-th
+        // entry's: the 64-bit (key, index) order is only materialised for the rare steps with a survivor.
+        for (; c0 < tn; c0 += 128) {
             float d[4];
-            bool hit = false;
+            uint32_t hm = 0;                                 // bit u: this lane's point of sub-group u beats the K-th entry
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = c0 + u * 32 + lane;
-                const int jc = min(j, tn - 1);
-                float d2 = d2_direct(sx[jc], sy[jc], sz[jc], qx, qy, qz);
+                const float4 s = spt[c0 + u * 32 + lane];
+                float d2 = d2_direct(s.x, s.y, s.z, qx, qy, qz);
                 if (RADIUS && !(d2 <= r2)) d2 = __int_as_float(0x7f800000);   // common.py:58-59
                 d[u] = d2;
-                hit |= (j < tn) && (!full || d2 < thr_f);
+                hm |= (d2 < thr_f) ? (1u << u) : 0u;
             }
-            if (!__any_sync(PCNBR_FULL, hit)) continue;
+            const uint32_t any = __reduce_or_sync(PCNBR_FULL, hm);
+            if (!any) continue;
+            // survivors only (sentinels have d = +inf and never get here): sub-groups in ascending index order
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = c0 + u * 32 + lane;
-                const u64 key = (j < tn) ? pack_key(f2ord(d[u]), (uint32_t)(t0 + j)) : PCNBR_KEY_MAX;
+                if (!(any & (1u << u))) continue;            // warp-uniform
+                const u64 key = (hm & (1u << u)) ? pack_key(f2ord(d[u]), (uint32_t)(t0 + c0 + u * 32 + lane)) : PCNBR_KEY_MAX;
                 uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
                 while (pass) {
                     const int src = __ffs(pass) - 1;
@@ -80,7 +118,6 @@ select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int 
                     }
                 }
             }
-            full = thr != PCNBR_KEY_MAX;
             thr_f = ord2f((uint32_t)(thr >> 32));
         }
     }
