@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_longlong, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libpcnbr.so")
@@ -57,6 +57,8 @@ PROTOTYPES = {
     "pcnbr_confusion_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "pcnbr_masked_ce_blocks": (_I, [_I]),
     "pcnbr_masked_ce_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "pcnbr_block_batch": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "pcnbr_window_merge_f32": (_I, [_P, _P, _I, c_longlong, _I, _I, _I, _P, _P, _P, _P]),
     "pcnbr_prof_enable": (None, [_I]),
     "pcnbr_prof_collect": (_I, [_P, _Z]),
 }

@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--cpu-batch", type=int, default=2, help="clouds per CPU-baseline step (bounded sample)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' runs the same oracle port on cuda:0 with stock ATen / cuBLAS / cuDNN "
+                         "kernels at the full per-GPU batch (SURVEY 8d 'also time': the reference's own GPU path)")
     return ap.parse_args()
 
 
@@ -120,32 +123,38 @@ def logits_of(out):
 # --------------------------------------------------------------------------- reference arm / cpu baseline
 
 
-def cpu_reference_steps(model, cloud_batch, N, steps, warmup):
-    """The reference's own CPU implementation of the path (oracle/ref_ops.py: the same ATen op sequence,
-    raw torch.topk selection) timed on the host cores: fwd + bwd + Adam on `cloud_batch` clouds."""
+def cpu_reference_steps(model, cloud_batch, N, steps, warmup, device="cpu"):
+    """The reference's own implementation of the path (oracle/ref_ops.py: the same ATen op sequence, raw torch.topk
+    selection): fwd + bwd + Adam on `cloud_batch` clouds, timed on the host cores -- or, with device="cuda", on cuda:0
+    through the stock ATen / cuBLAS / cuDNN kernels the reference would launch there (torch defaults, as train.py)."""
     from oracle import ref_ops as O
     s3dis_blocks = O.s3dis_blocks
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
+    dev = torch.device(device)
     net = {"dgcnn": lambda: O.DGCNNWithColor(N_CLASSES, k=20, tie="raw"),
            "pointnetpp": lambda: O.PointNetpp(N_CLASSES, tie="raw"),
-           "pointnext": lambda: O.PointNeXt(N_CLASSES, tie="raw")}[model]()
+           "pointnext": lambda: O.PointNeXt(N_CLASSES, tie="raw")}[model]().to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-    pts, lab, lens = s3dis_blocks(cloud_batch, N, 0, N_CLASSES)
+    pts, lab, lens = (t.to(dev) for t in s3dis_blocks(cloud_batch, N, 0, N_CLASSES))
 
     def ce(logits, onehot, lens):
         logp = torch.log_softmax(logits, dim=-1)
         tok = -(onehot.float() * logp).sum(-1)
-        mask = (torch.arange(logits.shape[1]).unsqueeze(0) < lens.unsqueeze(1)).float()
+        mask = (torch.arange(logits.shape[1], device=dev).unsqueeze(0) < lens.unsqueeze(1)).float()
         return (tok * mask).sum() / mask.sum()
 
     times = []
     for i in range(warmup + steps):
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         loss = ce(logits_of(net(model_input(model, pts))), lab, lens)
         loss.backward()
         opt.step()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -156,18 +165,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.cpu_batch
+    on_gpu = args.ref_device == "cuda"
+    B = (args.batch or default_batch(args.model)) if on_gpu else args.cpu_batch
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    times, cores = cpu_reference_steps(args.model, B, args.points, steps, warmup)
+    times, cores = cpu_reference_steps(args.model, B, args.points, steps, warmup, args.ref_device)
     ms = 1e3 * sum(times) / len(times)
     value = B * args.points / (ms / 1e3)
-    sample = f"{steps} steps of {B} clouds x {args.points} pts (bounded sample of the per-GPU batch), {warmup} warm-up, mean"
+    sample = (f"{steps} steps of {B} clouds x {args.points} pts (" + ("the full per-GPU batch on cuda:0, stock ATen kernels"
+              if on_gpu else "bounded sample of the per-GPU batch") + f"), {warmup} warm-up, mean")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic S3DIS-shaped blocks, random-init weights",
         "config": {"workload": workload_name(args.model, args.batch or default_batch(args.model), args.points),
-                   "reference_path": "oracle port of the reference's torch CPU path (the Python reference does not travel to the GPU box)"},
+                   "reference_path": "oracle port of the reference's torch " + ("CUDA path (stock ATen / cuBLAS / cuDNN kernels, torch defaults)"
+                                     if on_gpu else "CPU path") + " (the Python reference does not travel to the GPU box)",
+                   "ref_device": args.ref_device},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

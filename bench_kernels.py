@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="BASELINE shapes only (no N sweep)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--md", default="")
-    ap.add_argument("--only", default="", help="comma-separated op groups: pointnet, dgcnn, gemm (default all)")
+    ap.add_argument("--only", default="", help="comma-separated op groups: pointnet, dgcnn, gemm, io (default all)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_kernels.py: no CUDA device; the hot path has no CPU fallback")
@@ -134,6 +134,30 @@ def main():
         run("conv1x1 dx=gyW", sh, lambda: ops._gemm3x(gy, False, w, True, R, Cin, Cout))
         run("conv1x1 dW=gy^Tx", sh, lambda: ops._gemm3x(gy, True, x, True, Cout, Cin, R))
         del x, w, gy
+
+    # ---- the data formats either side of the path: packed block batches, sliding-window merge
+    if want("io"):
+        BD = pkg.block_datasets
+        sizes = torch.randint(3000, 12000, (512,), generator=g).tolist()          # ~3.8 M points packed in HBM
+        store = BD.PackedBlocks([(torch.randn(n, 9, generator=g), torch.zeros(n, 14, dtype=torch.uint8)) for n in sizes], dev)
+        for B in (16, 32, 256):
+            ids = torch.randint(0, len(store), (B,), generator=g).tolist()
+            sel = store.draw_device(ids, 4096)
+            run("block_batch", f"B={B} S=4096 L=14 ({len(store)} blocks, {store.nbytes() >> 20} MB packed)",
+                lambda: store.batch(ids, 4096, sel)[0])
+        for n_scene in (100_000, 1_000_000):
+            wins = pkg.dgcnn_utils.scene_windows(n_scene, 4096, 512)
+            total = sum(e - s for s, e in wins)
+            logits = torch.randn(total, 13, generator=g).to(dev)
+            offs = torch.tensor([0] + [e - s for s, e in wins[:-1]], dtype=torch.int64).cumsum(0).to(dev)
+            pred = torch.empty(n_scene, dtype=torch.int64, device=dev)
+            conf = torch.empty(n_scene, dtype=torch.float32, device=dev)
+
+            def merge():
+                lib.call("pcnbr_window_merge_f32", logits.data_ptr(), offs.data_ptr(), len(wins), n_scene, 4096, 3584, 13, None,
+                         pred.data_ptr(), conf.data_ptr(), ops._stream())
+                return conf
+            run("window_merge", f"N={n_scene} window=4096 overlap=512 C=13", merge)
 
     md = ["| op | shape | kernel | µs/launch | algorithmic | roofline | frac |", "|---|---|---|---:|---:|---|---:|"]
     for r in rows:

@@ -232,6 +232,29 @@ PCNBR_API int pcnbr_masked_ce_blocks(int L);
 PCNBR_API int pcnbr_masked_ce_f32(const float* logits, const uint8_t* onehot, const long long* lengths, int B, int L, int C,
                         float* loss, float* dlogits, float* partial, pcnbr_stream_t stream);
 
+/* ---- block dataloader in HBM ------------------------------ data_processing/block_datasets.py:5-29,117-128
+ * Replaces, per training step, BlockS3DISDataset.__getitem__ (torch.load of one file per block + row selection) and
+ * collate_blocks (zero-padded batch).  points (T,9) f32 and labels (T,L) uint8 hold every block of the split packed back
+ * to back; block_start (nblocks+1) int64 row offsets; block_ids (B) int32 = the blocks of this batch.
+ *   sel (B,S) int32 != NULL: row sel[b,r] of block block_ids[b] goes to batch row r (the reference's
+ *       randperm(n)[:S] / randint(n,(S,)) draw, :119-125); out_len[b] = S.
+ *   sel == NULL: rows 0..n_b-1 in order, zero padded up to S (collate_blocks; pass S = the longest block of the batch);
+ *       out_len[b] = min(n_b, S).
+ * out_points (B,S,9) f32, out_labels (B,S,L) uint8, out_len (B) int64 -- exactly the tuple the reference's DataLoader
+ * yields, already on the device.  Out-of-range rows read as zeros. */
+PCNBR_API int pcnbr_block_batch(const float* points, const uint8_t* labels, const long long* block_start, const int* block_ids,
+                      const int* sel, int B, int S, int L, float* out_points, uint8_t* out_labels, long long* out_len,
+                      pcnbr_stream_t stream);
+
+/* ---- sliding-window scene inference, merge step ----------- models/dgcnn/utils.py:67-131
+ * predict_single_scene cuts a scene of n_points into W = ceil(n_points / step) windows [w*step, min(n, w*step+window)),
+ * runs the model per window, overlap-adds the logits, divides by the cover count and takes argmax / max softmax.
+ * logits ((sum of window lengths), C): the windows' logits back to back, window w at row win_off[w] (win_off: W int64).
+ * Outputs per scene point: mean_logits (n,C) (may be NULL; bit-identical to all_logits / point_counts: same summation
+ * order), pred (n) int64 (first maximum), conf (n) f32.  step <= window, C <= 64. */
+PCNBR_API int pcnbr_window_merge_f32(const float* logits, const long long* win_off, int W, long long n_points, int window,
+                           int step, int C, float* mean_logits, long long* pred, float* conf, pcnbr_stream_t stream);
+
 /* ---- measurement hook (bench.py roofline, kernel sweep) -- not part of the reference interface
  * pcnbr_prof_enable(1): bracket every kernel this library launches with CUDA events on its launch stream and
  * remember the launch's ALGORITHMIC bytes / flops.  Must be off while a CUDA graph is captured.

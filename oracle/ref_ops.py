@@ -38,7 +38,7 @@ def _select_largest(keys: torch.Tensor, k: int, tie: str):
 
 def _rows(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """t (B,N,D), idx (B,...) int64 -> t[b, idx[b,...]]  (B,...,D)"""
-    b = torch.arange(t.shape[0]).view(-1, *([1] * (idx.dim() - 1))).expand_as(idx)
+    b = torch.arange(t.shape[0], device=idx.device).view(-1, *([1] * (idx.dim() - 1))).expand_as(idx)
     return t[b, idx]
 
 
@@ -56,9 +56,9 @@ def fps_indices(coords: torch.Tensor, C: int, start: torch.Tensor | None = None)
         start = torch.randint(0, N, (B,), dtype=torch.int, device=coords.device)
     coords = coords.float()          # selections are always made in the reference's fp32 arithmetic
     far = start.to(torch.int64)
-    rows = torch.arange(B)
-    picks = torch.zeros(B, C, dtype=torch.int32)
-    running = torch.full((B, N), torch.inf)
+    rows = torch.arange(B, device=coords.device)
+    picks = torch.zeros(B, C, dtype=torch.int32)                 # a CPU tensor, as common.py:20 (one D2H copy per pick on CUDA)
+    running = torch.full((B, N), torch.inf, device=coords.device)
     for i in range(C):
         picks[:, i] = far.to(torch.int32)
         centre = coords[rows, far, :].view(B, 1, 3)
@@ -70,7 +70,7 @@ def fps_indices(coords: torch.Tensor, C: int, start: torch.Tensor | None = None)
 
 def sample(coords: torch.Tensor, C: int, start: torch.Tensor | None = None) -> torch.Tensor:
     """models/utils/common.py:6-34 -> coordinates (B,C,3) of the FPS picks."""
-    return _rows(coords, fps_indices(coords, C, start).long())
+    return _rows(coords, fps_indices(coords, C, start).long().to(coords.device))
 
 
 def ball_query_indices(centroids, coords, r: float, K: int, tie: str = "canon") -> torch.Tensor:
@@ -443,3 +443,56 @@ def metrics_iou(predictions, labels, mask):
     inter, union = metrics_update_iou(predictions, labels, mask)
     ious = ((inter.double() + 1e-6) / (union.double() + 1e-6)).to(torch.float32)
     return ious.mean().item(), ious
+
+
+# --------------------------------------------------------------------------- block dataloader
+
+
+def block_getitem(points: torch.Tensor, labels: torch.Tensor, sampling: int | None):
+    """data_processing/block_datasets.py:117-128 for one loaded block: the random row selection (host generator)."""
+    if sampling is not None:
+        n = points.shape[0]
+        rows = torch.randperm(n)[:sampling] if n > sampling else torch.randint(n, (sampling,))
+        points, labels = points[rows], labels[rows]
+    return points, labels
+
+
+def collate_blocks(batch):
+    """block_datasets.py:5-29 -> (points (B,N,9) f32, labels (B,N,L) u8, lengths (B,) int64), zero padded."""
+    B, N = len(batch), max(p.shape[0] for p, _ in batch)
+    pts = torch.zeros(B, N, batch[0][0].shape[1], dtype=torch.float32)
+    lab = torch.zeros(B, N, batch[0][1].shape[1], dtype=torch.uint8)
+    for b, (p, l) in enumerate(batch):
+        pts[b, :p.shape[0]] = p
+        lab[b, :p.shape[0]] = l
+    return pts, lab, torch.tensor([p.shape[0] for p, _ in batch], dtype=torch.int64)
+
+
+def gather_block_batch(blocks, block_ids, sel):
+    """The batch a given plan produces: rows sel[b] of block block_ids[b] (sel None: all rows, zero padded)."""
+    if sel is None:
+        return collate_blocks([blocks[i] for i in block_ids])
+    return collate_blocks([(blocks[i][0][sel[b].long()], blocks[i][1][sel[b].long()]) for b, i in enumerate(block_ids)])
+
+
+# --------------------------------------------------------------------------- sliding-window inference (SURVEY 8f-4)
+
+
+def predict_single_scene(model, points: torch.Tensor, batch_size: int = 4096, overlap: int = 512):
+    """models/dgcnn/utils.py:67-131: window after window through `model` ((1,F,n) -> (logits (1,n,C), _, _)),
+    overlap-add, divide by the cover count, argmax and max softmax.  -> (mean_logits (N,C), predictions (N,), conf (N,));
+    the reference returns the last two."""
+    n = points.shape[0]
+    with torch.no_grad():
+        if n <= batch_size:
+            mean = model(points.T.unsqueeze(0))[0].squeeze(0)
+        else:
+            step = batch_size - overlap
+            total = torch.zeros(n, model.num_classes, device=points.device)
+            count = torch.zeros(n, device=points.device)
+            for start in range(0, n, step):
+                end = min(start + batch_size, n)
+                total[start:end] += model(points[start:end].T.unsqueeze(0))[0].squeeze(0)
+                count[start:end] += 1
+            mean = total / count.unsqueeze(1)
+    return mean, torch.argmax(mean, dim=1), torch.softmax(mean, dim=1).max(dim=1)[0]

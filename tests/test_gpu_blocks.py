@@ -1,0 +1,209 @@
+"""GPU: the packed block dataloader (csrc/blocks.cu: block_batch_kernel) and sliding-window scene
+inference (8f-4, window_merge_kernel) against the golden vectors made from the unmodified reference and against the
+oracle restatements -- bit-exact for the batches (byte/word gathers) and for the merged logits / predictions."""
+import os
+
+import pytest
+import torch
+
+from oracle import ref_ops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def same_batch(got, want):
+    return len(got) == len(want) and all(torch.equal(a.cpu(), b) for a, b in zip(got, want))
+
+
+# ------------------------------------------------------------------------------------------------ block batches
+
+
+def test_packed_batches_match_reference_golden(pkg, dev, golden):
+    g = golden("blocks")
+    BD = pkg.block_datasets
+    # test split: no sampling, zero-padded ragged batches (collate_blocks)
+    store = BD.PackedBlocks(g["test_blocks"], dev)
+    bs = g["test_batch_size"]
+    for i, want in enumerate(g["test_batches"]):
+        ids = list(range(bs * i, min(bs * (i + 1), len(store))))
+        got = store.batch(ids, None)
+        assert same_batch(got, want)
+        assert got[0].is_cuda and got[2].dtype == torch.int64
+    # train split, two seeded epochs through the loader: host-generator parity with the reference's DataLoader
+    class DS:                                                     # a dataset without files: the loader only needs these
+        packed, sampling = BD.PackedBlocks(g["train_blocks"], dev), g["sampling"]
+
+        def __len__(self):
+            return len(self.packed)
+    torch.manual_seed(g["seed"])
+    loader = BD.BlockLoader(DS(), g["train_batch_size"], shuffle=True)
+    got = [b for _ in range(2) for b in loader]
+    assert len(got) == len(g["train_batches"]) and len(loader) == len(g["train_batches"]) // 2
+    for a, b in zip(got, g["train_batches"]):
+        assert same_batch(a, b)
+
+
+def test_create_block_dataloaders_from_files(pkg, dev, golden, tmp_path):
+    g = golden("blocks")
+    for split in ("train", "test"):
+        for (a, r, b), rec in zip(g[f"{split}_index"].tolist(), g[f"{split}_blocks"]):
+            os.makedirs(tmp_path / f"area_{a}", exist_ok=True)
+            torch.save(rec, tmp_path / f"area_{a}" / f"room{r:02d}_block{b:03d}.pt")
+    BD = pkg.block_datasets
+    train_loader, test_loader = BD.create_block_dataloaders(str(tmp_path), {6}, train_batch_size=g["train_batch_size"],
+                                                            test_batch_size=g["test_batch_size"], num_workers=0,
+                                                            train_sampling=g["sampling"], test_sampling=None)
+    assert torch.equal(train_loader.dataset.blocks, g["train_index"]) and torch.equal(test_loader.dataset.blocks, g["test_index"])
+    torch.manual_seed(g["seed"])
+    got = [b for _ in range(2) for b in train_loader]
+    for a, b in zip(got, g["train_batches"]):
+        assert same_batch(a, b)
+    for a, b in zip(test_loader, g["test_batches"]):
+        assert same_batch(a, b)
+    p, l = test_loader.dataset[2]
+    assert torch.equal(p.cpu(), g["test_blocks"][2][0]) and torch.equal(l.cpu(), g["test_blocks"][2][1])
+    with pytest.raises(FileNotFoundError):
+        BD.BlockS3DISDataset(str(tmp_path / "nowhere"), {1})
+    with pytest.raises(ValueError):
+        BD.BlockS3DISDataset(str(tmp_path), {0, 1})
+
+
+@pytest.mark.parametrize("nblocks,S,B", [(40, 4096, 32), (7, 100, 5), (3, 1, 3)])
+def test_block_batch_vs_oracle_random(pkg, dev, nblocks, S, B):
+    g = torch.Generator().manual_seed(nblocks * S + B)
+    sizes = torch.randint(1, 3 * S + 2, (nblocks,), generator=g).tolist()
+    blocks = [(torch.randn(n, 9, generator=g), torch.randint(0, 256, (n, 14), generator=g).to(torch.uint8)) for n in sizes]
+    store = pkg.block_datasets.PackedBlocks(blocks, dev)
+    ids = torch.randint(0, nblocks, (B,), generator=g).tolist()                 # repeats allowed
+    torch.manual_seed(5)
+    sel = store.draw_host(ids, S)
+    assert same_batch(store.batch(ids, S, sel), O.gather_block_batch(blocks, ids, sel))
+    assert same_batch(store.batch(ids, None), O.gather_block_batch(blocks, ids, None))
+    # the draw made inside batch() is the reference's (same generator consumption as block_getitem per block)
+    torch.manual_seed(9)
+    got = store.batch(ids, S)
+    torch.manual_seed(9)
+    want = O.collate_blocks([O.block_getitem(*blocks[i], S) for i in ids])
+    assert same_batch(got, want)
+    with pytest.raises(IndexError):
+        store.batch([nblocks], S)
+
+
+def test_device_sampling_distribution_properties(pkg, dev):
+    g = torch.Generator().manual_seed(3)
+    sizes = [50, 300, 128, 129, 1000]
+    blocks = [(torch.arange(n, dtype=torch.float32).view(n, 1).repeat(1, 9), torch.zeros(n, 14, dtype=torch.uint8)) for n in sizes]
+    store = pkg.block_datasets.PackedBlocks(blocks, dev)
+    S, ids = 128, [0, 1, 2, 3, 4, 1]
+    gen = torch.Generator(device=dev).manual_seed(11)
+    sel = store.draw_device(ids, S, gen)
+    assert sel.shape == (len(ids), S) and sel.dtype == torch.int32 and sel.is_cuda
+    for b, i in enumerate(ids):
+        row = sel[b].cpu()
+        assert int(row.min()) >= 0 and int(row.max()) < sizes[i]
+        if sizes[i] > S:                                                          # randperm(n)[:S]: no repeats
+            assert len(set(row.tolist())) == S
+    assert not torch.equal(sel[1], sel[5])                                        # independent draws for a repeated block
+    pts, lab, lens = store.batch(ids, S, sel)
+    assert torch.equal(pts[:, :, 0].cpu(), sel.cpu().float()) and lens.tolist() == [S] * len(ids)
+    # means of uniform row draws: within 5 sigma of (n-1)/2 over many draws
+    big = store.draw_device([4] * 64, S, gen).float()
+    assert abs(float(big.mean()) - 499.5) < 5 * 288.7 / (64 * S) ** 0.5 * 1.1
+
+
+# ------------------------------------------------------------------------------------------------ scene windows
+
+
+class TinyModel(torch.nn.Module):
+    num_classes = 13
+
+    def __init__(self, w):
+        super().__init__()
+        self.w = torch.nn.Parameter(w.clone())
+
+    def forward(self, x):
+        x = x - x.mean(dim=2, keepdim=True)
+        return torch.einsum("cf,bfn->bnc", self.w, x), None, None
+
+
+class ElementwiseModel(torch.nn.Module):
+    """Scores that depend on the point AND on its position inside the window through elementwise ops only, so batched
+    and one-by-one windows give bit-identical logits and the merge can be checked exactly."""
+
+    def __init__(self, C):
+        super().__init__()
+        self.num_classes = C
+
+    def forward(self, x):                                                        # (B,F,n)
+        B, F, n = x.shape
+        c = torch.arange(1, self.num_classes + 1, device=x.device, dtype=torch.float32).view(1, 1, -1)
+        pos = torch.arange(n, device=x.device, dtype=torch.float32).view(1, n, 1)
+        a, b = x[:, 0, :].unsqueeze(-1), x[:, 1, :].unsqueeze(-1)
+        return (a * c + b * (c * c) * 0.125) * (1.0 + pos * 0.001), None, None
+
+
+@pytest.mark.parametrize("n,window,overlap,C", [(300, 512, 64, 13), (1000, 256, 64, 13), (777, 200, 50, 14), (20000, 4096, 512, 13),
+                                                 (512, 128, 0, 3), (5000, 1000, 900, 40), (100000, 4096, 512, 13)])
+def test_window_merge_bit_exact_vs_oracle(pkg, dev, n, window, overlap, C):
+    g = torch.Generator().manual_seed(n + window)
+    pts = (torch.randn(n, 6, generator=g).round(decimals=1)).to(dev)              # rounded inputs: real argmax ties
+    model = ElementwiseModel(C).to(dev)
+    pred, conf, mean = pkg.dgcnn_utils.predict_single_scene(model, pts, "cuda", window, overlap, return_logits=True)
+    omean, opred, oconf = O.predict_single_scene(model, pts, window, overlap)      # the reference's loop, same model, on the GPU
+    assert torch.equal(mean, omean)
+    assert torch.equal(pred, opred.cpu()) and pred.dtype == torch.int64
+    torch.testing.assert_close(conf, oconf.cpu(), rtol=2e-6, atol=1e-7)
+    # chunked model calls give the same result
+    pred2, conf2 = pkg.dgcnn_utils.predict_single_scene(model, pts, "cuda", window, overlap, max_windows_per_call=3)
+    assert torch.equal(pred2, pred) and torch.equal(conf2, conf)
+
+
+def test_window_merge_golden(pkg, dev, golden):
+    g = golden("scene_windows")
+    model = TinyModel(g["w"]).to(dev)
+    for case in g["cases"]:
+        pred, conf, mean = pkg.dgcnn_utils.predict_single_scene(model, case["points"], "cuda", case["window"], case["overlap"],
+                                                                return_logits=True)
+        torch.testing.assert_close(mean.cpu(), case["mean_logits"], rtol=1e-5, atol=1e-5)
+        top2 = case["mean_logits"].topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4                                   # GPU einsum rounding may flip exact near-ties only
+        assert torch.equal(pred[clear], case["pred"][clear]) and int(clear.sum()) > 0.99 * len(clear)
+        torch.testing.assert_close(conf, case["conf"], rtol=1e-4, atol=1e-5)
+
+
+def test_scene_inference_with_dgcnn(pkg, dev):
+    torch.manual_seed(0)
+    model = pkg.DGCNNWithColor(num_classes=13, k=20).to(dev)
+    pts, _, _ = O.s3dis_blocks(1, 6000, seed=4)
+    scene = pts[0, :, :6].contiguous()
+    scene[:, 3:] /= 255.0
+    # a few train-mode passes give the BatchNorm layers non-trivial running statistics
+    model.train()
+    with torch.no_grad():
+        for i in range(2):
+            model(scene[i * 2048:(i + 1) * 2048].T.unsqueeze(0).to(dev))
+    pred, conf, mean = pkg.dgcnn_utils.predict_single_scene(model, scene, "cuda", 2048, 256, return_logits=True)
+    omean, opred, oconf = O.predict_single_scene(model, scene.to(dev), 2048, 256)     # window by window through the same model
+    # DGCNN is discontinuous in its activations (a feature-space kNN graph can flip on a 1e-7 rounding difference between
+    # the batched and the one-by-one pass), so the comparison is statistical: all but a handful of elements to 1e-4
+    scale = float(omean.abs().max())
+    diff = (mean - omean).abs()
+    assert float((diff > 1e-4 * scale).float().mean()) < 1e-3 and float(diff.max()) < 2e-2 * scale
+    top2 = omean.topk(2, dim=1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 1e-3 * scale).cpu()
+    assert float((pred[clear] == opred.cpu()[clear]).float().mean()) > 0.999
+    assert pred.shape == (6000,) and conf.shape == (6000,) and float(conf.min()) > 0 and float(conf.max()) <= 1.0 + 1e-6
+
+
+def test_window_merge_rejects_bad_arguments(pkg, dev):
+    L = pkg._lib
+    x = torch.zeros(10, 3, device=dev)
+    off = torch.zeros(1, dtype=torch.int64, device=dev)
+    pred = torch.zeros(10, dtype=torch.int64, device=dev)
+    conf = torch.zeros(10, device=dev)
+    with pytest.raises(L.PcnbrError):                                              # step > window
+        L.call("pcnbr_window_merge_f32", x.data_ptr(), off.data_ptr(), 1, 10, 4, 5, 3, None, pred.data_ptr(), conf.data_ptr(), 0)
+    with pytest.raises(L.PcnbrError):                                              # too few windows for the scene
+        L.call("pcnbr_window_merge_f32", x.data_ptr(), off.data_ptr(), 1, 10, 4, 2, 3, None, pred.data_ptr(), conf.data_ptr(), 0)
+    with pytest.raises(L.PcnbrError):                                              # C above the compiled limit
+        L.call("pcnbr_window_merge_f32", x.data_ptr(), off.data_ptr(), 1, 10, 10, 10, 65, None, pred.data_ptr(), conf.data_ptr(), 0)
