@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from . import ops
 
 __all__ = ["sample", "group", "reduce", "interpolate", "MiniPointNet", "UnitPointNet", "SetAbstraction",
-           "FeaturePropagation", "InvResMLP"]
+           "SetAbstractionMSG", "FeaturePropagation", "InvResMLP"]
 
 
 def sample(coords: torch.Tensor, C: int, start_idx: torch.Tensor | None = None) -> torch.Tensor:
@@ -187,6 +187,42 @@ class SetAbstraction(nn.Module):
             return centroid_coords, self.point_net.forward_rows(grouped, pool_max=True)   # (B,C,mlp[-1])
         x = self.point_net.forward_rows(grouped)             # point-major rows (B,C,K,*): no permute, no copy
         return centroid_coords, reduce(x, self.pooling_type)
+
+
+class SetAbstractionMSG(nn.Module):
+    """Multi-scale-grouping set abstraction (BASELINE configs[2]; the reference has no MSG class, SURVEY.md 8a-2: "MSG" =
+    several `group` calls on ONE centroid set with different (r, K)).  Semantically
+        centroids = sample(coords, C)
+        out = cat([reduce(MiniPointNet_i(group(centroids, coords, features, r_i, K_i, grouping_norm)), pooling_type)], -1)
+    with the reference's own pieces [common.py:6-91,125-150]; here FPS runs once, all ball queries share one scan of the
+    points (ops.query_ball_point_multi) and every scale goes through the fused group -> MLP -> max path.
+    Parameters: `point_nets.<i>.conv.<j>` / `point_nets.<i>.batch.<j>` (a ModuleList of the reference's MiniPointNet)."""
+
+    def __init__(self, C: int, radii: list[float], in_channels: int, mlps_list: list[list[int]], Ks: list[int],
+                 pooling_type: str = 'max', grouping_norm: bool = False):
+        super().__init__()
+        if not (len(radii) == len(mlps_list) == len(Ks)) or len(radii) == 0:
+            raise ValueError("SetAbstractionMSG: radii, mlps_list and Ks must be non-empty lists of the same length")
+        self.point_nets = nn.ModuleList(MiniPointNet(in_channels, mlps) for mlps in mlps_list)
+        self.C = C
+        self.radii = list(radii)
+        self.Ks = list(Ks)
+        self.pooling_type = pooling_type
+        self.grouping_norm = grouping_norm
+        self.fps_start = None          # optional (B,) first FPS pick (tests); None = reference's randint
+
+    def forward(self, coords: torch.Tensor, features: torch.Tensor):
+        centroid_coords = sample(coords, self.C, self.fps_start)
+        tables = ops.query_ball_point_multi(self.radii, self.Ks, coords, centroid_coords)
+        outs = []
+        for r, idx, net in zip(self.radii, tables, self.point_nets):
+            nbr = ops.NeighborIndex(idx, coords.shape[1])
+            grouped = ops.group_points(coords, features, centroid_coords, nbr, r if self.grouping_norm else None, pad4=True)
+            if self.pooling_type == 'max':
+                outs.append(net.forward_rows(grouped, pool_max=True))
+            else:
+                outs.append(reduce(net.forward_rows(grouped), self.pooling_type))
+        return centroid_coords, torch.cat(outs, dim=-1)
 
 
 class FeaturePropagation(nn.Module):

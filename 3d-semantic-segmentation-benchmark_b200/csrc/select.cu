@@ -287,6 +287,60 @@ static inline int expand_tile(int F) {
     return t;
 }
 
+// ---- multi-radius ball query ("MSG": several group() calls on one centroid set, common.py:37-61 per scale) --------
+// One selection pass with the LARGEST radius and the largest K gives, per centroid, the sorted list L of its K_all
+// nearest in-ball points (then the canonical padding).  For a smaller radius r_i the in-ball points are a prefix of L
+// (L is sorted by distance; if fewer than K_all entries of L lie within r_i, no point within r_i is missing from L), so
+// scale i's table is   [first min(c_i, K_i) entries of L, c_i = #{d2 <= r_i^2}]  +  [the lowest-index points with
+// !(d2 <= r_i^2) until K_i entries]   -- exactly what a stable sort of the reference's masked distance row yields.  The
+// padding scan recomputes the distance with the same rounding sequence as the selection and normally ends after one
+// 32-point step (low-index points outside a small ball are plentiful).
+constexpr int MSG_MAXR = 8;
+struct MsgScales {
+    float r2[MSG_MAXR];
+    int K[MSG_MAXR];
+    int32_t* out[MSG_MAXR];
+    int R;
+};
+
+__global__ void __launch_bounds__(256)
+ball_derive_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N, int Kall, float r2max,
+                   const int32_t* __restrict__ idx_all, const float* __restrict__ d2_all, MsgScales sc) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= M) return;
+    const float* __restrict__ pb = p + (size_t)b * N * 3;
+    const float* __restrict__ qp = q + ((size_t)b * M + m) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    const size_t row = ((size_t)b * M + m) * Kall;
+    for (int i = 0; i < sc.R; ++i) {
+        const int K = sc.K[i];
+        const float r2 = sc.r2[i];
+        int32_t* __restrict__ out = sc.out[i] + ((size_t)b * M + m) * K;
+        if (r2 == r2max) {                                   // same ball: a prefix of the list, padding included
+            for (int pos = lane; pos < K; pos += 32) out[pos] = idx_all[row + pos];
+            continue;
+        }
+        int c = 0;
+        for (int pos0 = 0; pos0 < Kall; pos0 += 32) {
+            const int pos = pos0 + lane;
+            const bool in = pos < Kall && d2_all[row + pos] <= r2;           // padding entries carry +inf
+            c += __popc(__ballot_sync(PCNBR_FULL, in));
+        }
+        int filled = c < K ? c : K;
+        for (int pos = lane; pos < filled; pos += 32) out[pos] = idx_all[row + pos];
+        for (int j0 = 0; filled < K && j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            bool outside = false;
+            if (j < N) outside = !(d2_direct(pb[3 * j], pb[3 * j + 1], pb[3 * j + 2], qx, qy, qz) <= r2);   // common.py:58-59
+            const uint32_t mask = __ballot_sync(PCNBR_FULL, outside);
+            const int pos = filled + __popc(mask & ((1u << lane) - 1u));
+            if (outside && pos < K) out[pos] = j;
+            filled += __popc(mask);
+        }
+    }
+}
+
 }  // namespace pcnbr
 
 using namespace pcnbr;
@@ -315,6 +369,39 @@ extern "C" int pcnbr_ball_query_f32(const float* q, const float* p, int B, int M
 extern "C" int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M, int N, int K, int32_t* idx,
                                     float* d2, pcnbr_stream_t stream) {
     return launch_select<false>(q, p, B, M, N, 0.f, K, idx, d2, (cudaStream_t)stream);
+}
+
+extern "C" size_t pcnbr_ball_query_multi_ws_bytes(int B, int M, int Kmax) {
+    return (size_t)B * (size_t)M * (size_t)Kmax * (sizeof(int32_t) + sizeof(float));
+}
+
+extern "C" int pcnbr_ball_query_multi_f32(const float* q, const float* p, int B, int M, int N, const float* r2, const int* K,
+                                          int R, int32_t* const* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (!r2 || !K || !idx || R <= 0) return PCNBR_E_BADARG;
+    if (R > MSG_MAXR) return PCNBR_E_TOOLARGE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (R == 1) return launch_select<true>(q, p, B, M, N, r2[0], K[0], idx[0], nullptr, s);
+    MsgScales sc;
+    sc.R = R;
+    float r2max = r2[0];
+    int Kall = 0;
+    for (int i = 0; i < R; ++i) {
+        if (!idx[i] || K[i] <= 0 || K[i] > N) return PCNBR_E_BADARG;
+        sc.r2[i] = r2[i]; sc.K[i] = K[i]; sc.out[i] = idx[i];
+        if (r2[i] > r2max) r2max = r2[i];
+        if (K[i] > Kall) Kall = K[i];
+    }
+    if (!ws || ws_bytes < pcnbr_ball_query_multi_ws_bytes(B, M, Kall)) return PCNBR_E_WORKSPACE;
+    int32_t* idx_all = (int32_t*)ws;
+    float* d2_all = (float*)(idx_all + (size_t)B * M * Kall);
+    int rc = launch_select<true>(q, p, B, M, N, r2max, Kall, idx_all, d2_all, s);
+    if (rc) return rc;
+    double out_bytes = 0.0;
+    for (int i = 0; i < R; ++i) out_bytes += 4.0 * K[i];
+    PCNBR_TIMED("ball_derive_kernel", s, (double)B * M * (8.0 * Kall + out_bytes + 12.0) + 12.0 * B * N, 0.0,
+                (ball_derive_kernel<<<dim3((M + 7) / 8, B), 256, 0, s>>>(q, p, M, N, Kall, r2max, idx_all, d2_all, sc)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
 }
 
 static bool use_tensor_cores(int F, int N, int K) {

@@ -326,6 +326,32 @@ def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
     return idx
 
 
+def query_ball_point_multi(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor) -> list[torch.Tensor]:
+    """Multi-radius ball query (PointNet++ "MSG": several group() calls on one centroid set, models/utils/common.py:37-61
+    once per scale).  -> [idx_i (B,M,nsamples[i]) int32], each bit-identical to query_ball_point(radii[i], nsamples[i],
+    xyz, new_xyz), from ONE scan of the points: a selection with the largest radius and the largest K, the other scales
+    derived from its sorted list (csrc/select.cu: ball_derive_kernel)."""
+    import ctypes
+    _check(xyz, "xyz"); _check(new_xyz, "new_xyz")
+    radii, nsamples = list(radii), [int(k) for k in nsamples]
+    if len(radii) != len(nsamples) or len(radii) == 0:
+        raise ValueError("pcnbr: radii and nsamples must be non-empty lists of the same length")
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    if max(nsamples) > N:
+        raise RuntimeError(f"pcnbr: selected index k out of range (K={max(nsamples)} > N={N})")   # torch.topk's error
+    xyz, new_xyz = _c(xyz), _c(new_xyz)
+    R = len(radii)
+    out = [torch.empty(B, M, k, dtype=torch.int32, device=xyz.device) for k in nsamples]
+    ws = _ws(_lib.size("pcnbr_ball_query_multi_ws_bytes", B, M, max(nsamples)), xyz.device)
+    r2 = (ctypes.c_float * R)(*[_r2(r) for r in radii])
+    ks = (ctypes.c_int * R)(*nsamples)
+    ptrs = (ctypes.c_void_p * R)(*[t.data_ptr() for t in out])
+    _lib.call("pcnbr_ball_query_multi_f32", new_xyz.data_ptr(), xyz.data_ptr(), B, M, N, ctypes.addressof(r2),
+              ctypes.addressof(ks), R, ctypes.addressof(ptrs), ws.data_ptr(), ws.numel(), _stream())
+    return out
+
+
 def knn_points(query: torch.Tensor, src: torch.Tensor, k: int):
     """K3 (direct form).  query (B,M,3), src (B,N,3) -> (idx (B,M,k) int32, d2 (B,M,k)): the k smallest
     ((src - query)**2).sum(-1), ascending, lowest index on ties (models/utils/common.py:110-114)."""

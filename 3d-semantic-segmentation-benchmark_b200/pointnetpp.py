@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .common import FeaturePropagation, SetAbstraction
+from .common import FeaturePropagation, SetAbstraction, SetAbstractionMSG
 
 
 class PointNetpp(nn.Module):
@@ -40,4 +40,41 @@ class PointNetpp(nn.Module):
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2, _geom=geo.three_nn(1))
         features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0))
         x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
+        return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)
+
+
+class PointNetppMSG(nn.Module):
+    """PointNet++ MSG semantic segmentation (BASELINE configs[2]: multi-radius ball query, batch 32 x 4096 points).
+
+    The reference ships only the SSG network (models/PointNetpp/PointNetpp.py:6-48); this is the same
+    encoder / decoder skeleton with every set abstraction replaced by its multi-scale form -- two radii per level
+    (r/2 with K=16 and r with K=32 for the SSG radii r = 0.1 / 0.2 / 0.4 / 0.8, as in the original PointNet++ MSG
+    segmentation network; each scale's MLP is the SSG MLP of that level, the small scale of level 1 half as wide) --
+    built from the reference's own blocks (MiniPointNet, FeaturePropagation)."""
+
+    def __init__(self, part_classes: int):
+        super().__init__()
+        self.sa1 = SetAbstractionMSG(1024, [0.05, 0.1], 9, [[16, 16, 32], [32, 32, 64]], [16, 32])
+        self.sa2 = SetAbstractionMSG(256, [0.1, 0.2], 96 + 3, [[64, 64, 128], [64, 64, 128]], [16, 32])
+        self.sa3 = SetAbstractionMSG(64, [0.2, 0.4], 256 + 3, [[128, 128, 256], [128, 128, 256]], [16, 32])
+        self.sa4 = SetAbstractionMSG(16, [0.4, 0.8], 512 + 3, [[256, 256, 512], [256, 256, 512]], [16, 32])
+        self.fp4 = FeaturePropagation(1024 + 512, [256, 256])
+        self.fp3 = FeaturePropagation(256 + 256, [256, 256])
+        self.fp2 = FeaturePropagation(256 + 96, [256, 128])
+        self.fp1 = FeaturePropagation(128, [128, 128, 128, 128])
+        self.drop = nn.Dropout(0.5)
+        self.conv = nn.Conv1d(128, part_classes, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes)."""
+        coords_0, features_0 = x[:, :, :3], x[:, :, 3:]
+        coords_1, features_1 = self.sa1(coords_0, features_0)
+        coords_2, features_2 = self.sa2(coords_1, features_1)
+        coords_3, features_3 = self.sa3(coords_2, features_2)
+        coords_4, features_4 = self.sa4(coords_3, features_3)
+        features_3 = self.fp4(coords_3, coords_4, features_3, features_4)
+        features_2 = self.fp3(coords_2, coords_3, features_2, features_3)
+        features_1 = self.fp2(coords_1, coords_2, features_1, features_2)
+        features_0 = self.fp1(coords_0, coords_1, None, features_1)
+        x = self.drop(features_0)
         return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)

@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "pointnetpp", "pointnext"])
+    ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "pointnetpp", "pointnetpp_msg", "pointnext"])
     ap.add_argument("--batch", type=int, default=0, help="clouds per GPU (default 16 dgcnn / 32 pointnet++)")
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -52,13 +52,14 @@ def parse():
 
 
 def default_batch(model):
-    return {"dgcnn": 16, "pointnetpp": 32, "pointnext": 4}[model]
+    return {"dgcnn": 16, "pointnetpp": 32, "pointnetpp_msg": 32, "pointnext": 4}[model]
 
 
 def workload_name(model, B, N):
     return {
         "dgcnn": f"DGCNNWithColor semseg k=20 emb=1024, batch {B} x {N} pts x 6 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
         "pointnetpp": f"PointNet++ SSG semseg, batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
+        "pointnetpp_msg": f"PointNet++ MSG semseg (two radii per level, one multi-radius ball query), batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
         "pointnext": f"PointNeXt semseg, batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
     }[model]
 
@@ -113,6 +114,8 @@ def build_model(impl_pkg, model):
         return impl_pkg.DGCNNWithColor(num_classes=N_CLASSES, k=20)
     if model == "pointnetpp":
         return impl_pkg.PointNetpp(N_CLASSES)
+    if model == "pointnetpp_msg":
+        return impl_pkg.PointNetppMSG(N_CLASSES)
     return impl_pkg.PointNeXt(N_CLASSES)
 
 
@@ -134,6 +137,7 @@ def cpu_reference_steps(model, cloud_batch, N, steps, warmup, device="cpu"):
     dev = torch.device(device)
     net = {"dgcnn": lambda: O.DGCNNWithColor(N_CLASSES, k=20, tie="raw"),
            "pointnetpp": lambda: O.PointNetpp(N_CLASSES, tie="raw"),
+           "pointnetpp_msg": lambda: O.PointNetppMSG(N_CLASSES, tie="raw"),
            "pointnext": lambda: O.PointNeXt(N_CLASSES, tie="raw")}[model]().to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     pts, lab, lens = (t.to(dev) for t in s3dis_blocks(cloud_batch, N, 0, N_CLASSES))

@@ -65,6 +65,15 @@ PCNBR_API int pcnbr_ball_query_f32(const float* q, const float* p, int B, int M,
 PCNBR_API int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M, int N, int K,
                          int32_t* idx, float* d2, pcnbr_stream_t stream);
 
+/* Multi-radius ball query ("MSG": several group() calls on ONE centroid set with different (r, K); BASELINE configs[2]).
+ * Each idx[i] (B,M,K[i]) is bit-identical to pcnbr_ball_query_f32(q, p, .., r2[i], K[i], idx[i]), but the points are
+ * scanned once: one selection with the largest radius and the largest K, the other scales are derived from its sorted
+ * list (in-ball prefix + lowest-index out-of-ball padding).  r2, K and idx are HOST arrays of R <= 8 entries (idx holds
+ * device pointers); ws: pcnbr_ball_query_multi_ws_bytes(B, M, max K) bytes of device scratch (unused when R == 1). */
+PCNBR_API size_t pcnbr_ball_query_multi_ws_bytes(int B, int M, int Kmax);
+PCNBR_API int pcnbr_ball_query_multi_f32(const float* q, const float* p, int B, int M, int N, const float* r2, const int* K,
+                               int R, int32_t* const* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
 /* ---- K3/K4 kNN in the reference's expanded form ----------------------- dgcnn.py:7-21
  * x[b, f*stride_f + n*stride_n] (batch stride F*N), any layout of the (F,N) plane.
  * pd_ij = ((-xx_j) - (-2*c_ij)) - xx_i, c = FMA chain over f ascending, xx = ATen cascade sum of

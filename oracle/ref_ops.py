@@ -264,6 +264,47 @@ class PointNetpp(nn.Module):
         return y.permute(0, 2, 1)
 
 
+class SetAbstractionMSG(nn.Module):
+    """Multi-scale grouping composed from the reference's pieces ("MSG" = several `group` calls on one
+    centroid set): sample once (common.py:6-34), then per scale group -> MiniPointNet -> reduce (common.py:37-91,
+    125-150, 205-214), concatenated along the channels."""
+
+    def __init__(self, C, radii, in_channels, mlps_list, Ks, pooling_type="max", grouping_norm=False, tie="canon"):
+        super().__init__()
+        self.point_nets = nn.ModuleList(MiniPointNet(in_channels, m) for m in mlps_list)
+        self.C, self.radii, self.Ks = C, list(radii), list(Ks)
+        self.pooling_type, self.grouping_norm, self.tie = pooling_type, grouping_norm, tie
+        self.fps_start = None
+
+    def forward(self, coords, features):
+        cen = sample(coords, self.C, self.fps_start)
+        outs = []
+        for r, K, net in zip(self.radii, self.Ks, self.point_nets):
+            g = group(cen, coords, features, r, K, self.grouping_norm, self.tie)
+            g = net(g.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+            outs.append(reduce(g, self.pooling_type))
+        return cen, torch.cat(outs, dim=-1)
+
+
+class PointNetppMSG(nn.Module):
+    """The SSG skeleton of models/PointNetpp/PointNetpp.py:6-48 with multi-scale set abstractions (BASELINE configs[2])."""
+
+    def __init__(self, part_classes, tie="canon"):
+        super().__init__()
+        self.sa1 = SetAbstractionMSG(1024, [0.05, 0.1], 9, [[16, 16, 32], [32, 32, 64]], [16, 32], tie=tie)
+        self.sa2 = SetAbstractionMSG(256, [0.1, 0.2], 96 + 3, [[64, 64, 128], [64, 64, 128]], [16, 32], tie=tie)
+        self.sa3 = SetAbstractionMSG(64, [0.2, 0.4], 256 + 3, [[128, 128, 256], [128, 128, 256]], [16, 32], tie=tie)
+        self.sa4 = SetAbstractionMSG(16, [0.4, 0.8], 512 + 3, [[256, 256, 512], [256, 256, 512]], [16, 32], tie=tie)
+        self.fp4 = FeaturePropagation(1024 + 512, [256, 256], tie=tie)
+        self.fp3 = FeaturePropagation(256 + 256, [256, 256], tie=tie)
+        self.fp2 = FeaturePropagation(256 + 96, [256, 128], tie=tie)
+        self.fp1 = FeaturePropagation(128, [128, 128, 128, 128], tie=tie)
+        self.drop = nn.Dropout(0.5)
+        self.conv = nn.Conv1d(128, part_classes, 1)
+
+    forward = PointNetpp.forward
+
+
 class PointNeXt(nn.Module):
     """models/PointNeXt/PointNeXt.py:17-147 (`version` is unused there too, :22)."""
 
