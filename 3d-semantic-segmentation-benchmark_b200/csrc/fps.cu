@@ -7,6 +7,7 @@
 // __syncthreads per pick (double-buffered partials).  Compulsory HBM traffic is 12N + 16C bytes per
 // cloud, so the kernel is ALU/latency bound on the SMs it occupies.
 #include "common.cuh"
+#include <cstdlib>
 #include <cooperative_groups.h>
 
 namespace pcnbr {
@@ -82,12 +83,19 @@ fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
         }
         const float smax = __fsqrt_rn(__uint_as_float(mb));
         int bj = PPT;
+        bool near = false;                               // some other point lies 1..4 ulps below the maximum (rare)
 #pragma unroll
         for (int j = PPT - 1; j >= 0; --j) {
             const uint32_t h = __float_as_uint(md[j]);
-            bool tie = (h == mb);
-            if (!tie && mb - h <= 4u) tie = (__fsqrt_rn(md[j]) == smax);
-            if (tie) bj = j;
+            if (h == mb) bj = j;
+            near |= (mb - h - 1u) < 4u;
+        }
+        if (near) {                                      // ONE branch per thread and pick; exact re-check of the rounding class
+#pragma unroll
+            for (int j = PPT - 1; j >= 0; --j) {
+                const uint32_t h = __float_as_uint(md[j]);
+                if ((mb - h - 1u) < 4u && j < bj && __fsqrt_rn(md[j]) == smax) bj = j;
+            }
         }
         const uint32_t bh = __float_as_uint(smax);
         const uint32_t bl = 0xffffffffu - (uint32_t)(bj * T + tid);
@@ -176,12 +184,19 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
         }
         const float smax = __fsqrt_rn(__uint_as_float(mb));
         int bj = PPT;
+        bool near = false;                               // some other point lies 1..4 ulps below the maximum (rare)
 #pragma unroll
         for (int j = PPT - 1; j >= 0; --j) {
             const uint32_t h = __float_as_uint(md[j]);
-            bool tie = (h == mb);
-            if (!tie && mb - h <= 4u) tie = (__fsqrt_rn(md[j]) == smax);
-            if (tie) bj = j;
+            if (h == mb) bj = j;
+            near |= (mb - h - 1u) < 4u;
+        }
+        if (near) {                                      // ONE branch per thread and pick; exact re-check of the rounding class
+#pragma unroll
+            for (int j = PPT - 1; j >= 0; --j) {
+                const uint32_t h = __float_as_uint(md[j]);
+                if ((mb - h - 1u) < 4u && j < bj && __fsqrt_rn(md[j]) == smax) bj = j;
+            }
         }
         const uint32_t bh = __float_as_uint(smax);
         // padding slots (beyond the share or the cloud) carry md = 0 and the lowest-priority index: their slot numbers would
@@ -304,13 +319,35 @@ extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_
     // is the whole chip's FMA rate (2 flops per lane-op slot), hence the 2 * 148 / min(B,148) scaling of the stated work.
     const double wb = (double)B * (12.0 * N + 16.0 * C);
     const double wf = 10.0 * B * (double)N * C * 2.0 * 148.0 / (double)(B < 148 ? B : 148);
-    if (N <= 256)        PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 256><<<B, 256, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
-    else if (N <= 512)   PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 512><<<B, 512, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
-    else if (N <= 1024)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<1, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
-    else if (N <= 2048)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<2, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
-    else if (N <= 4096)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<4, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
-    else if (N <= 8192)  PCNBR_TIMED("fps_reg_kernel", s, wb, wf, (fps_reg_kernel<8, 1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));
-    else if (N <= 8 * 8192 && B * 8 <= 148 * 2) {
+    // Threads per cloud (N <= 8192, points in registers): fewer, fatter threads halve the per-warp reduction overhead of a
+    // pick but leave fewer warps to hide the pick-to-pick latency chain.  Measured at 32 x (4096 -> 1024): 1024 threads x 4
+    // points 752 us, 512 x 8 625 us, 256 x 16 588 us (with the single-branch tie re-check; the per-point branches of the
+    // first version made the fat threads slower).  PCNBR_FPS_T=64|128|256|512|1024 forces a width (A/B in the sweep).
+    static const int fps_t_env = getenv("PCNBR_FPS_T") ? atoi(getenv("PCNBR_FPS_T")) : 0;
+    int T = 256;
+    if (fps_t_env == 64 || fps_t_env == 128 || fps_t_env == 256 || fps_t_env == 512 || fps_t_env == 1024) T = fps_t_env;
+    while (T < 1024 && (N + T - 1) / T > (T == 128 ? 32 : 16)) T *= 2;
+    int ppt = 1;
+    while (ppt * T < N) ppt *= 2;
+#define PCNBR_FPS_CASE(P, TT)                                                                                        \
+    if (ppt == P && T == TT) {                                                                                       \
+        PCNBR_TIMED("fps_reg_kernel", s, wb, wf,                                                                     \
+                    (fps_reg_kernel<P, TT><<<B, TT, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));                   \
+        PCNBR_CHECK_LAUNCH();                                                                                        \
+        return 0;                                                                                                    \
+    }
+    if (N <= 8192) {
+        PCNBR_FPS_CASE(1, 64) PCNBR_FPS_CASE(2, 64) PCNBR_FPS_CASE(4, 64) PCNBR_FPS_CASE(8, 64) PCNBR_FPS_CASE(16, 64)
+        PCNBR_FPS_CASE(1, 128) PCNBR_FPS_CASE(2, 128) PCNBR_FPS_CASE(4, 128) PCNBR_FPS_CASE(8, 128) PCNBR_FPS_CASE(16, 128)
+        PCNBR_FPS_CASE(32, 128)
+        PCNBR_FPS_CASE(1, 256) PCNBR_FPS_CASE(2, 256) PCNBR_FPS_CASE(4, 256) PCNBR_FPS_CASE(8, 256) PCNBR_FPS_CASE(16, 256)
+        PCNBR_FPS_CASE(1, 512) PCNBR_FPS_CASE(2, 512) PCNBR_FPS_CASE(4, 512) PCNBR_FPS_CASE(8, 512) PCNBR_FPS_CASE(16, 512)
+        PCNBR_FPS_CASE(1, 1024) PCNBR_FPS_CASE(2, 1024) PCNBR_FPS_CASE(4, 1024) PCNBR_FPS_CASE(8, 1024)
+        return PCNBR_E_TOOLARGE;                            // unreachable: every (ppt, T) above is instantiated
+    }
+#undef PCNBR_FPS_CASE
+    if (N <= 8 * 8192 && B * 8 <= 148 * 2) {
+
         // cluster of 4 (N <= 32768) or 8 CTAs per cloud, 8 points per thread; ceiling: the CL SMs per cloud
         const int CL = N <= 4 * 8192 ? 4 : 8;
         const double wfc = 10.0 * B * (double)N * C * 2.0 * 148.0 / (double)(B * CL < 148 ? B * CL : 148);

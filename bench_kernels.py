@@ -90,6 +90,9 @@ def main():
         run("fps", sh, lambda: ops.farthest_point_sample(xyz, C, start).float())
         _, cen = ops.farthest_point_sample(xyz, C, start, return_coords=True)
         run("ball_query", sh + f" r={r}", lambda: ops.query_ball_point(r, K, xyz, cen).float())
+        if K // 2 <= N:                                    # the MSG pair of this level: (r/2, K/2) + (r, K) from one scan
+            run("ball_query_msg", sh + f" r={r / 2}+{r} K={K // 2}+{K}",
+                lambda: ops.query_ball_point_multi([r / 2, r], [K // 2, K], xyz, cen)[1].float())
         nbr = ops.NeighborIndex(ops.query_ball_point(r, K, xyz, cen), N)
         run("csr_build", sh, lambda: (setattr(nbr, "_csr", None), nbr.csr()[1].float())[1])
         run("group(+bwd)", sh, lambda: ops.group_points(xyz, f, cen, nbr, r), bwd=True)
