@@ -440,10 +440,12 @@ using namespace pcnbr;
 
 extern "C" int pcnbr_bn_supported(long R, int C) { return ba_supported(R, C) ? 1 : 0; }
 
-// number of partial blocks the reducing kernels use for an (R, C) matrix: >= 128 KB of rows per block, <= 4 per SM
+// number of partial blocks the reducing kernels use for an (R, C) matrix: >= 32 KB of rows per block, <= 4 per SM
+// (128 KB left the mid-sized layers -- 2..16 MB, every deeper PointNet++ level and the 64-channel DGCNN layers -- on
+// 16..128 CTAs, fewer than the chip has SMs: 0.7 TB/s for an 8 MB tensor on 64 CTAs)
 extern "C" int pcnbr_bn_blocks(long R, int C) {
     if (!ba_supported(R, C)) return 0;
-    const long by_bytes = (R * (long)C * 4 + 131071) / 131072;
+    const long by_bytes = (R * (long)C * 4 + 32767) / 32768;
     const long sweeps = (R + ba_sweep_rows(C) - 1) / ba_sweep_rows(C);
     long n = by_bytes < 4L * 148 ? by_bytes : 4L * 148;
     if (n > sweeps) n = sweeps;

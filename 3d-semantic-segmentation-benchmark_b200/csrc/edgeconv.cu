@@ -90,14 +90,18 @@ edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ id
     int smax_i[VEC];
     ec_ld<VEC>(shift + c0, c);
     ec_ld_u8<VEC>(selmax + c0, smax_i);
+    float sg[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) { a1[v] = 0.f; a2[v] = 0.f; }
+    for (int v = 0; v < VEC; ++v) { a1[v] = 0.f; a2[v] = 0.f; sg[v] = smax_i[v] ? 1.f : -1.f; }
     for (int n = blockIdx.x * 8 + warp; n < N; n += gridDim.x * 8) {
         float q[VEC], best[VEC], sum[VEC];
         int ba[VEC];
         ec_ld<VEC>(pq + (size_t)n * 2 * O + O + c0, q);
+        // max and min share one branch-free path: t = +-p (exact), keep the first strict maximum of t.  (The per-element
+        // `if (take)` of the first version compiled to a BSSY / BRA / BSYNC group per channel and row: 29 % of the kernel's
+        // instructions were control flow, ncu source page.)
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { best[v] = 0.f; sum[v] = 0.f; ba[v] = 0; }
+        for (int v = 0; v < VEC; ++v) { best[v] = __int_as_float(0xff800000); sum[v] = 0.f; ba[v] = 0; }
         auto take_row = [&](const float (&p)[VEC], int j) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -105,8 +109,10 @@ edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ id
                 a1[v] += d;
                 a2[v] = fmaf(d, d, a2[v]);
                 sum[v] += p[v];
-                const bool take = (j == 0) || (smax_i[v] ? (p[v] > best[v]) : (p[v] < best[v]));
-                if (take) { best[v] = p[v]; ba[v] = j; }
+                const float t = p[v] * sg[v];
+                const bool take = t > best[v];
+                best[v] = take ? t : best[v];
+                ba[v] = take ? j : ba[v];
             }
         };
         for (int j0 = 0; j0 < K; j0 += 32) {
@@ -127,6 +133,8 @@ edgeconv_fwd_kernel(const float* __restrict__ PQ, const int32_t* __restrict__ id
                 take_row(p0, j0 + l);
             }
         }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) best[v] *= sg[v];
         const size_t o = ((size_t)b * N + n) * O + c0;
         ec_st<VEC>(psel + o, best);
         ec_st_u8<VEC>(arg + o, ba);
