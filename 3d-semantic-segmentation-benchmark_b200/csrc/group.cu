@@ -10,52 +10,75 @@
 
 namespace pcnbr {
 
-// rows = B*M*K output rows of width W = 3 + D.  Each warp handles RPW = max(1, 32/W) rows per pass
-// when W < 32 (lane -> (row, col)), or one row per pass with lanes striding over the columns.
 __global__ void __launch_bounds__(256)
 group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, const float* __restrict__ q,
-                 const int32_t* __restrict__ idx, int N, int M, int K, int D, float rdiv, long rows, int ldo,
+                 const int32_t* __restrict__ idx, int N, int M, int K, int D, float rdiv, int ldo,
                  float* __restrict__ out) {
+    // One warp per centroid (b, m): its K output rows are contiguous (K * W floats), the neighbour indices sit in the
+    // lanes, and no address needs a division by M*K or K (the first version spent two 64-bit divisions per output element).
     const int W = ldo;                                     // output row pitch >= 3 + D; the pad columns are written as 0
-    const int lane = threadIdx.x & 31;
-    const long warp_global = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
-    const long MK = (long)M * K;
-    if (W <= 32) {
-        const int rpw = 32 / W;
-        const int sub = lane / W, col = lane - sub * W;
-        for (long r0 = warp_global * rpw; r0 < rows; r0 += nwarps * rpw) {
-            const long r = r0 + sub;
-            if (sub < rpw && r < rows) {
-                const long b = r / MK;
-                const long m = (r - b * MK) / K;
-                const int s = idx[r];
-                float v;
-                if (col < 3) {
-                    v = __fsub_rn(p[((size_t)b * N + s) * 3 + col], q[((size_t)b * M + m) * 3 + col]);
-                    if (rdiv > 0.f) v = __fdiv_rn(v, rdiv);                       // common.py:69
-                } else if (col < 3 + D) {
-                    v = feat[((size_t)b * N + s) * D + (col - 3)];
-                } else {
-                    v = 0.f;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const float* __restrict__ pb = p + (size_t)b * N * 3;
+    const float* __restrict__ fb = feat + (size_t)b * N * D;
+    const float* __restrict__ qc = q + ((size_t)b * M + m) * 3;
+    const float qv = lane < 3 ? qc[lane] : 0.f;            // lane c < 3 holds centroid coordinate c
+    const int32_t* __restrict__ ib = idx + ((size_t)b * M + m) * K;
+    float* __restrict__ ob = out + ((size_t)b * M + m) * (size_t)K * W;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kn = min(32, K - k0);
+        const int mine = lane < kn ? ib[k0 + lane] : 0;
+        float* __restrict__ oc = ob + (size_t)k0 * W;
+        if (W <= 32) {
+            // narrow rows (SA1: 12 floats): the chunk's kn * W floats as one flat, fully coalesced array
+            const int total = kn * W;
+            const float q0 = qc[0], q1 = qc[1], q2 = qc[2];
+            const uint32_t inv = (65536u + (uint32_t)W - 1u) / (uint32_t)W;   // e / W == (e * inv) >> 16 for e < 1024, W <= 32
+            for (int e0 = 0; e0 < total; e0 += 32) {              // warp-uniform trip count: every lane takes part in the shuffle
+                const int e = e0 + lane;
+                const int k = (int)(((uint32_t)min(e, total - 1) * inv) >> 16), col = e - k * W;
+                const int s = __shfl_sync(PCNBR_FULL, mine, k);
+                if (e < total) {
+                    float v = 0.f;
+                    if (col < 3) {
+                        v = __fsub_rn(pb[(size_t)s * 3 + col], col == 0 ? q0 : (col == 1 ? q1 : q2));
+                        if (rdiv > 0.f) v = __fdiv_rn(v, rdiv);                   // common.py:69
+                    } else if (col < 3 + D) {
+                        v = fb[(size_t)s * D + (col - 3)];
+                    }
+                    oc[e] = v;
                 }
-                out[(size_t)r * W + col] = v;
             }
-        }
-    } else {
-        for (long r = warp_global; r < rows; r += nwarps) {
-            const long b = r / MK;
-            const long m = (r - b * MK) / K;
-            const int s = idx[r];
-            float* __restrict__ o = out + (size_t)r * W;
-            const float* __restrict__ fs = feat + ((size_t)b * N + s) * D;
-            if (lane < 3) {
-                float v = __fsub_rn(p[((size_t)b * N + s) * 3 + lane], q[((size_t)b * M + m) * 3 + lane]);
-                if (rdiv > 0.f) v = __fdiv_rn(v, rdiv);
-                o[lane] = v;
+        } else {
+            // wide rows: lanes over the columns of a row, four rows in flight
+            for (int k = 0; k < kn; k += 4) {
+                int s[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s[u] = __shfl_sync(PCNBR_FULL, mine, min(k + u, kn - 1));
+                for (int c0 = 0; c0 < W; c0 += 32) {
+                    const int c = c0 + lane;
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v[u] = 0.f;
+                        if (c < 3) v[u] = pb[(size_t)s[u] * 3 + c];
+                        else if (c < 3 + D) v[u] = fb[(size_t)s[u] * D + (c - 3)];
+                    }
+                    if (c < 3) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            v[u] = __fsub_rn(v[u], qv);
+                            if (rdiv > 0.f) v[u] = __fdiv_rn(v[u], rdiv);
+                        }
+                    }
+                    if (c < W) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (k + u < kn) oc[(size_t)(k + u) * W + c] = v[u];
+                    }
+                }
             }
-            for (int c = lane; c < D; c += 32) o[3 + c] = fs[c];
-            if (lane < W - 3 - D) o[3 + D + lane] = 0.f;
         }
     }
 }
@@ -79,14 +102,11 @@ extern "C" int pcnbr_group_f32(const float* p, const float* feat, const float* q
                                int N, int M, int K, int D, float rdiv, float* out, int ldo, pcnbr_stream_t stream) {
     if (!p || !q || !idx || !out || (D > 0 && !feat) || B <= 0 || N <= 0 || M <= 0 || K <= 0 || D < 0 || ldo < 3 + D || ldo > 3 + D + 32)
         return PCNBR_E_BADARG;
-    const long rows = (long)B * M * K;
+    if (B > 65535) return PCNBR_E_TOOLARGE;
     const int W = ldo;
-    const long per_warp = (W <= 32) ? 32 / W : 1;
-    long blocks = (rows + per_warp * 8 - 1) / (per_warp * 8);
-    if (blocks > 148 * 16) blocks = 148 * 16;
     // K5: 4 M K (3+D) written + 4 M K idx + 4 N (3+D) + 12 M read per cloud
     PCNBR_TIMED("group_fwd_kernel", (cudaStream_t)stream, (double)B * (4.0 * M * K * W + 4.0 * M * K + 4.0 * N * W + 12.0 * M), 0.0,
-                (group_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, rows, ldo, out)));
+                (group_fwd_kernel<<<dim3((M + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, ldo, out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
