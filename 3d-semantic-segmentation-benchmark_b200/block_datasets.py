@@ -46,15 +46,22 @@ def draw_rows_host(counts, block_ids, sampling: int) -> torch.Tensor:
     return sel
 
 
-def loader_plan(num_blocks: int, counts, batch_size: int, shuffle: bool, sampling: int | None, host_draws: bool = True):
+def loader_plan(num_blocks: int, counts, batch_size: int, shuffle: bool, sampling: int | None, host_draws: bool = True,
+                rank: int = 0, world_size: int = 1):
     """Host side of one epoch: yields (block ids, sel (B,S) int32 or None) per batch, consuming torch's host generator
     exactly like `iter(DataLoader(dataset, batch_size, shuffle, num_workers=0))` over the reference's dataset does:
     the iterator's base-seed draw (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__), RandomSampler's seed
-    draw at the first batch, then one row draw per block in batch order."""
+    draw at the first batch, then one row draw per block in batch order.
+
+    world_size > 1 (one process per GPU, same seed on every rank): rank r takes batches r, r + world_size, ... of that
+    same epoch plan -- the batch dimension is sharded, no rank sees another rank's blocks, and every rank makes all the
+    draws so the generators stay in lockstep (the union over the ranks is exactly the single-process epoch)."""
     torch.empty((), dtype=torch.int64).random_()
     sampler = RandomSampler(range(num_blocks)) if shuffle else SequentialSampler(range(num_blocks))
-    for ids in BatchSampler(sampler, batch_size, drop_last=False):
-        yield ids, (draw_rows_host(counts, ids, sampling) if (sampling is not None and host_draws) else None)
+    for i, ids in enumerate(BatchSampler(sampler, batch_size, drop_last=False)):
+        sel = draw_rows_host(counts, ids, sampling) if (sampling is not None and host_draws) else None
+        if i % world_size == rank:
+            yield ids, sel
 
 
 class PackedBlocks:
@@ -198,17 +205,21 @@ class BlockLoader:
     num_workers=0 DataLoader (torch's own RandomSampler / BatchSampler produce the order)."""
 
     def __init__(self, dataset: BlockS3DISDataset, batch_size: int, shuffle: bool, device_sampling: bool = False,
-                 generator: torch.Generator | None = None):
+                 generator: torch.Generator | None = None, rank: int = 0, world_size: int = 1):
+        if not 0 <= rank < world_size:
+            raise ValueError(f"rank {rank} outside [0, {world_size})")
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
         self.device_sampling, self.generator = device_sampling, generator
+        self.rank, self.world_size = rank, world_size
 
     def __len__(self) -> int:
-        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+        total = (len(self.dataset) + self.batch_size - 1) // self.batch_size
+        return (total - self.rank + self.world_size - 1) // self.world_size
 
     def __iter__(self):
         packed, S = self.dataset.packed, self.dataset.sampling
         for ids, sel in loader_plan(len(packed), packed.counts_host, self.batch_size, self.shuffle, S,
-                                    host_draws=not self.device_sampling):
+                                    host_draws=not self.device_sampling, rank=self.rank, world_size=self.world_size):
             if S is not None and self.device_sampling:
                 sel = packed.draw_device(ids, S, self.generator)
             yield packed.batch(ids, S, sel)
@@ -217,11 +228,12 @@ class BlockLoader:
 def create_block_dataloaders(data_dir: str, test_areas: set[int], train_batch_size: int = 4, test_batch_size: int = 4,
                              num_workers: int = 4, train_sampling: int | None = 4096, test_sampling: int | None = None,
                              train_shuffle: bool = True, test_shuffle: bool = False, device="cuda",
-                             device_sampling: bool = False):
+                             device_sampling: bool = False, rank: int = 0, world_size: int = 1):
     """block_datasets.py:134-177 -> (train_loader, test_loader).  `num_workers` is accepted and ignored: there is no
-    per-step host work left to parallelise."""
+    per-step host work left to parallelise.  rank / world_size shard the TRAIN batches across data-parallel ranks (the
+    test loader stays whole on every rank, as an unsharded evaluation would)."""
     areas = {1, 2, 3, 4, 5, 6}
     train = BlockS3DISDataset(data_dir, areas - test_areas, train_sampling, device)
     test = BlockS3DISDataset(data_dir, test_areas, test_sampling, device)
-    return (BlockLoader(train, train_batch_size, train_shuffle, device_sampling),
+    return (BlockLoader(train, train_batch_size, train_shuffle, device_sampling, rank=rank, world_size=world_size),
             BlockLoader(test, test_batch_size, test_shuffle, device_sampling))

@@ -89,3 +89,26 @@ def test_block_store_and_scene_inference_need_cuda(pkg):
         pkg.block_datasets.PackedBlocks([(pts, lab)], device="cpu")
     with pytest.raises(RuntimeError):
         pkg.dgcnn_utils.predict_single_scene(TinyModel(torch.zeros(13, 6)), torch.rand(10, 6), device="cpu")
+
+
+def test_loader_plan_shards_batches_across_ranks(pkg, golden):
+    """world_size 3: the ranks' batches are disjoint, their union in batch order is the single-process epoch, and every
+    rank leaves the host generator in the same state (lockstep draws)."""
+    g = golden("blocks")
+    blocks = g["train_blocks"]
+    counts = [b[0].shape[0] for b in blocks]
+    plan = pkg.block_datasets.loader_plan
+    torch.manual_seed(7)
+    whole = list(plan(len(blocks), counts, 2, True, g["sampling"]))
+    state = torch.get_rng_state()
+    per_rank = []
+    for r in range(3):
+        torch.manual_seed(7)
+        per_rank.append(list(plan(len(blocks), counts, 2, True, g["sampling"], rank=r, world_size=3)))
+        assert torch.equal(torch.get_rng_state(), state)
+    assert sum(len(p) for p in per_rank) == len(whole)
+    for i, (ids, sel) in enumerate(whole):
+        rid, rsel = per_rank[i % 3][i // 3]
+        assert rid == ids and torch.equal(rsel, sel)
+    seen = [tuple(ids) for p in per_rank for ids, _ in p]
+    assert len(set(seen)) == len(seen)
