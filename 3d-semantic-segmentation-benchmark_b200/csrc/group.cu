@@ -12,13 +12,16 @@ namespace pcnbr {
 
 __global__ void __launch_bounds__(256)
 group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, const float* __restrict__ q,
-                 const int32_t* __restrict__ idx, int N, int M, int K, int D, float rdiv, int ldo,
+                 const int32_t* __restrict__ idx, int N, int M, int K, int D, float rdiv, int ldo, int split_log2,
                  float* __restrict__ out) {
     // One warp per centroid (b, m): its K output rows are contiguous (K * W floats), the neighbour indices sit in the
     // lanes, and no address needs a division by M*K or K (the first version spent two 64-bit divisions per output element).
     const int W = ldo;                                     // output row pitch >= 3 + D; the pad columns are written as 0
     const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // wide rows: 2^split_log2 warps share a centroid, each takes a contiguous slice of every 32-row chunk (the deeper levels
+    // have few centroids: 512 at 32 x 16 -- a warp per centroid left most of the chip idle)
+    const int wv = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int m = wv >> split_log2, part = wv & ((1 << split_log2) - 1);
     if (m >= M) return;
     const float* __restrict__ pb = p + (size_t)b * N * 3;
     const float* __restrict__ fb = feat + (size_t)b * N * D;
@@ -52,7 +55,9 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
             }
         } else {
             // wide rows: lanes over the columns of a row, four rows in flight
-            for (int k = 0; k < kn; k += 4) {
+            const int slice = 32 >> split_log2;
+            const int k_hi = min(kn, (part + 1) * slice);
+            for (int k = part * slice; k < k_hi; k += 4) {
                 int s[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) s[u] = __shfl_sync(PCNBR_FULL, mine, min(k + u, kn - 1));
@@ -75,7 +80,7 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
                     if (c < W) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            if (k + u < kn) oc[(size_t)(k + u) * W + c] = v[u];
+                            if (k + u < k_hi) oc[(size_t)(k + u) * W + c] = v[u];
                     }
                 }
             }
@@ -104,9 +109,13 @@ extern "C" int pcnbr_group_f32(const float* p, const float* feat, const float* q
         return PCNBR_E_BADARG;
     if (B > 65535) return PCNBR_E_TOOLARGE;
     const int W = ldo;
+    // measured (32 clouds): splitting helps the deep levels (16 centroids x 260 floats: 39 -> 16 us; 64 x 132: 30 -> 25 us)
+    // and hurts once a warp per centroid already fills the chip (256 centroids x 68 floats: 40 -> 49 us)
+    const int split_log2 = (W <= 32 || (long)B * M > 4096) ? 0 : ((long)B * M <= 1024 ? 3 : 2);
+    const long warps = (long)M << split_log2;
     // K5: 4 M K (3+D) written + 4 M K idx + 4 N (3+D) + 12 M read per cloud
     PCNBR_TIMED("group_fwd_kernel", (cudaStream_t)stream, (double)B * (4.0 * M * K * W + 4.0 * M * K + 4.0 * N * W + 12.0 * M), 0.0,
-                (group_fwd_kernel<<<dim3((M + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, ldo, out)));
+                (group_fwd_kernel<<<dim3((unsigned)((warps + 7) / 8), B), 256, 0, (cudaStream_t)stream>>>(p, feat, q, idx, N, M, K, D, rdiv, ldo, split_log2, out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
