@@ -34,24 +34,26 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
         const int mine = lane < kn ? ib[k0 + lane] : 0;
         float* __restrict__ oc = ob + (size_t)k0 * W;
         if (W <= 32) {
-            // narrow rows (SA1: 12 floats): the chunk's kn * W floats as one flat, fully coalesced array
+            // narrow rows (SA1: 12 floats): the chunk's kn * W floats as one flat, fully coalesced array.  Lane k first
+            // computes the local coordinates of ITS neighbour (3 loads, 3 subtractions, 3 divisions per row instead of a
+            // divergent load + division inside the element loop); the loop then only shuffles and copies.
             const int total = kn * W;
-            const float q0 = qc[0], q1 = qc[1], q2 = qc[2];
+            float lx = 0.f, ly = 0.f, lz = 0.f;
+            if (lane < kn) {
+                const float* __restrict__ ps = pb + (size_t)mine * 3;
+                lx = __fsub_rn(ps[0], qc[0]); ly = __fsub_rn(ps[1], qc[1]); lz = __fsub_rn(ps[2], qc[2]);
+                if (rdiv > 0.f) { lx = __fdiv_rn(lx, rdiv); ly = __fdiv_rn(ly, rdiv); lz = __fdiv_rn(lz, rdiv); }   // common.py:69
+            }
             const uint32_t inv = (65536u + (uint32_t)W - 1u) / (uint32_t)W;   // e / W == (e * inv) >> 16 for e < 1024, W <= 32
-            for (int e0 = 0; e0 < total; e0 += 32) {              // warp-uniform trip count: every lane takes part in the shuffle
+#pragma unroll 2
+            for (int e0 = 0; e0 < total; e0 += 32) {              // warp-uniform trip count: every lane takes part in the shuffles
                 const int e = e0 + lane;
                 const int k = (int)(((uint32_t)min(e, total - 1) * inv) >> 16), col = e - k * W;
                 const int s = __shfl_sync(PCNBR_FULL, mine, k);
-                if (e < total) {
-                    float v = 0.f;
-                    if (col < 3) {
-                        v = __fsub_rn(pb[(size_t)s * 3 + col], col == 0 ? q0 : (col == 1 ? q1 : q2));
-                        if (rdiv > 0.f) v = __fdiv_rn(v, rdiv);                   // common.py:69
-                    } else if (col < 3 + D) {
-                        v = fb[(size_t)s * D + (col - 3)];
-                    }
-                    oc[e] = v;
-                }
+                const float vx = __shfl_sync(PCNBR_FULL, lx, k), vy = __shfl_sync(PCNBR_FULL, ly, k), vz = __shfl_sync(PCNBR_FULL, lz, k);
+                float v = col == 0 ? vx : (col == 1 ? vy : vz);
+                if (col >= 3) v = (col < 3 + D && e < total) ? fb[(size_t)s * D + (col - 3)] : 0.f;
+                if (e < total) oc[e] = v;
             }
         } else {
             // wide rows: lanes over the columns of a row, four rows in flight
