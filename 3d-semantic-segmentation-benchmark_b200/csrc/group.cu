@@ -44,6 +44,29 @@ group_fwd_kernel(const float* __restrict__ p, const float* __restrict__ feat, co
                 lx = __fsub_rn(ps[0], qc[0]); ly = __fsub_rn(ps[1], qc[1]); lz = __fsub_rn(ps[2], qc[2]);
                 if (rdiv > 0.f) { lx = __fdiv_rn(lx, rdiv); ly = __fdiv_rn(ly, rdiv); lz = __fdiv_rn(lz, rdiv); }   // common.py:69
             }
+            if ((W & 3) == 0 && (((uintptr_t)out) & 15) == 0) {
+                // 16-byte pitch (the padded rows the set-abstraction modules ask for): one float4 of output per lane and
+                // step -- the index arithmetic is paid once per four floats and the store is a single STG.128
+                const int W4 = W >> 2, total4 = kn * W4;
+                const uint32_t inv4 = (65536u + (uint32_t)W4 - 1u) / (uint32_t)W4;
+                for (int f0 = 0; f0 < total4; f0 += 32) {
+                    const int f = f0 + lane;
+                    const int k = (int)(((uint32_t)min(f, total4 - 1) * inv4) >> 16), c4 = f - k * W4;
+                    const int s = __shfl_sync(PCNBR_FULL, mine, k);
+                    const float vx = __shfl_sync(PCNBR_FULL, lx, k), vy = __shfl_sync(PCNBR_FULL, ly, k), vz = __shfl_sync(PCNBR_FULL, lz, k);
+                    if (f < total4) {
+                        const float* __restrict__ fs = fb + (size_t)s * D;
+                        const int cb = 4 * c4 - 3;                     // feature column of the float4's first element
+                        float4 v;
+                        v.x = c4 == 0 ? vx : (cb < D ? fs[cb] : 0.f);
+                        v.y = c4 == 0 ? vy : (cb + 1 < D ? fs[cb + 1] : 0.f);
+                        v.z = c4 == 0 ? vz : (cb + 2 < D ? fs[cb + 2] : 0.f);
+                        v.w = cb + 3 < D ? fs[cb + 3] : 0.f;
+                        *reinterpret_cast<float4*>(oc + 4 * f) = v;
+                    }
+                }
+                continue;
+            }
             const uint32_t inv = (65536u + (uint32_t)W - 1u) / (uint32_t)W;   // e / W == (e * inv) >> 16 for e < 1024, W <= 32
 #pragma unroll 2
             for (int e0 = 0; e0 < total; e0 += 32) {              // warp-uniform trip count: every lane takes part in the shuffles
