@@ -112,3 +112,19 @@ def test_pointnetpp_msg_vs_oracle_model(pkg, dev):
     pr, pr64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
     for k, p in net.named_parameters():
         _as_good_as_reference(p.grad, pr[k].grad, pr64[k].grad, f"grad {k}")
+
+
+def test_set_abstraction_msg_golden(pkg, dev, golden):
+    """Against the composition of the unmodified reference's own functions (oracle/make_golden_msg.py): centroids and
+    all three neighbour tables bit-exact, features to 1e-4."""
+    g = golden("msg")
+    xyz, feat = g["coords"].to(dev), g["features"].to(dev)
+    tables = pkg.ops.query_ball_point_multi(g["radii"], g["Ks"], xyz, g["centroids"].to(dev))
+    for got, want in zip(tables, g["tables"]):
+        assert torch.equal(got.cpu(), want)
+    torch.manual_seed(g["seed"])
+    net = pkg.common.SetAbstractionMSG(g["C"], g["radii"], g["cin"], g["mlps"], g["Ks"]).to(dev)
+    net.fps_start = g["start"].to(dev)
+    cen, out = net(xyz, feat)
+    assert torch.equal(cen.cpu(), g["centroids"])
+    _close(out, g["out"])

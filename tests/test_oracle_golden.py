@@ -156,3 +156,18 @@ def test_metrics_match_reference_golden(golden):
     assert torch.equal(inter, g["inter"]) and torch.equal(union, g["union"])
     miou, ious = O.metrics_iou(g["pred"], g["labels"], g["mask"])
     assert torch.equal(ious, g["ious"]) and abs(miou - g["miou"]) < 1e-7
+
+
+def test_msg_composition_matches_reference_functions(golden):
+    """BASELINE configs[2]: the oracle's multi-scale set abstraction against the composition of the unmodified
+    reference's sample / group / MiniPointNet / reduce (oracle/make_golden_msg.py)."""
+    g = golden("msg")
+    for r, K, want in zip(g["radii"], g["Ks"], g["tables"]):
+        got = O.ball_query_indices(g["centroids"], g["coords"], r, K, tie="canon")
+        assert torch.equal(got.to(torch.int32), want)
+        assert torch.equal(canon.ball_query(g["centroids"], g["coords"], r, K), want)       # the C restatement
+    torch.manual_seed(g["seed"])
+    m = O.SetAbstractionMSG(g["C"], g["radii"], g["cin"], g["mlps"], g["Ks"])
+    m.fps_start = g["start"]
+    cen, out = m(g["coords"], g["features"])
+    assert torch.equal(cen, g["centroids"]) and torch.equal(out.detach(), g["out"])
