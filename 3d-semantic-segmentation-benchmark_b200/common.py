@@ -211,12 +211,17 @@ class SetAbstractionMSG(nn.Module):
         self.grouping_norm = grouping_norm
         self.fps_start = None          # optional (B,) first FPS pick (tests); None = reference's randint
 
-    def forward(self, coords: torch.Tensor, features: torch.Tensor):
-        centroid_coords = sample(coords, self.C, self.fps_start)
-        tables = ops.query_ball_point_multi(self.radii, self.Ks, coords, centroid_coords)
+    def forward(self, coords: torch.Tensor, features: torch.Tensor, _geom=None):
+        """_geom (internal): (centroid coords, [NeighborIndex per scale]) precomputed by ops.PyramidGeometry on the side
+        stream; None computes them here."""
+        if _geom is not None:
+            centroid_coords, nbrs = _geom
+        else:
+            centroid_coords = sample(coords, self.C, self.fps_start)
+            nbrs = [ops.NeighborIndex(idx, coords.shape[1])
+                    for idx in ops.query_ball_point_multi(self.radii, self.Ks, coords, centroid_coords)]
         outs = []
-        for r, idx, net in zip(self.radii, tables, self.point_nets):
-            nbr = ops.NeighborIndex(idx, coords.shape[1])
+        for r, nbr, net in zip(self.radii, nbrs, self.point_nets):
             grouped = ops.group_points(coords, features, centroid_coords, nbr, r if self.grouping_norm else None, pad4=True)
             if self.pooling_type == 'max':
                 outs.append(net.forward_rows(grouped, pool_max=True))

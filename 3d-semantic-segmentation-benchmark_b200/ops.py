@@ -166,7 +166,8 @@ class PyramidGeometry:
     levels, their ball queries and the 3-NN tables of the decoder run on the side stream, concurrently with the
     feature path, and each consumer waits on the event of what it needs.
 
-    sa = [(C, radius, K), ...] per set-abstraction level; starts = per-level first FPS picks or None (drawn here, level
+    sa = [(C, radius, K), ...] per set-abstraction level (radius and K may be lists: a multi-scale level, whose
+    NeighborIndex is then a list, one per scale); starts = per-level first FPS picks or None (drawn here, level
     by level, exactly as the modules would: torch.randint(0, N_level, (B,), dtype=torch.int), common.py:22)."""
 
     def __init__(self, coords0: torch.Tensor, sa, starts=None, interp_k: int = 3):
@@ -198,6 +199,21 @@ class PyramidGeometry:
         def ball(r, K, src, cen):
             Bc, Nc, _ = src.shape
             M = cen.shape[1]
+            if isinstance(r, (list, tuple)):                 # multi-scale level: every table from one scan of the points
+                import ctypes
+                Ks = [int(k) for k in K]
+                if max(Ks) > Nc:
+                    raise RuntimeError(f"pcnbr: selected index k out of range (K={max(Ks)} > N={Nc})")
+                outs = [torch.empty(Bc, M, k, dtype=torch.int32, device=dev) for k in Ks]
+                ws = _ws(_lib.size("pcnbr_ball_query_multi_ws_bytes", Bc, M, max(Ks)), dev)
+                self._keep.append(ws)
+                R = len(Ks)
+                r2 = (ctypes.c_float * R)(*[_r2(x) for x in r])
+                ks = (ctypes.c_int * R)(*Ks)
+                ptrs = (ctypes.c_void_p * R)(*[t.data_ptr() for t in outs])
+                _lib.call("pcnbr_ball_query_multi_f32", cen.data_ptr(), src.data_ptr(), Bc, M, Nc, ctypes.addressof(r2),
+                          ctypes.addressof(ks), R, ctypes.addressof(ptrs), ws.data_ptr(), ws.numel(), _stream())
+                return [NeighborIndex(t, Nc) for t in outs]
             if K > Nc:
                 raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={Nc})")
             idx = torch.empty(Bc, M, K, dtype=torch.int32, device=dev)

@@ -68,13 +68,17 @@ class PointNetppMSG(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes)."""
         coords_0, features_0 = x[:, :, :3], x[:, :, 3:]
-        coords_1, features_1 = self.sa1(coords_0, features_0)
-        coords_2, features_2 = self.sa2(coords_1, features_1)
-        coords_3, features_3 = self.sa3(coords_2, features_2)
-        coords_4, features_4 = self.sa4(coords_3, features_3)
-        features_3 = self.fp4(coords_3, coords_4, features_3, features_4)
-        features_2 = self.fp3(coords_2, coords_3, features_2, features_3)
-        features_1 = self.fp2(coords_1, coords_2, features_1, features_2)
-        features_0 = self.fp1(coords_0, coords_1, None, features_1)
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        # as in PointNetpp.forward: the deeper FPS levels, their multi-radius ball queries and the decoder's 3-NN tables run
+        # on the side stream while the feature path of the shallower levels computes
+        geo = ops.PyramidGeometry(coords_0, [(m.C, m.radii, m.Ks) for m in sas], [m.fps_start for m in sas])
+        coords_1, features_1 = self.sa1(geo.coords[0], features_0, _geom=geo.level(0))
+        coords_2, features_2 = self.sa2(coords_1, features_1, _geom=geo.level(1))
+        coords_3, features_3 = self.sa3(coords_2, features_2, _geom=geo.level(2))
+        coords_4, features_4 = self.sa4(coords_3, features_3, _geom=geo.level(3))
+        features_3 = self.fp4(coords_3, coords_4, features_3, features_4, _geom=geo.three_nn(3))
+        features_2 = self.fp3(coords_2, coords_3, features_2, features_3, _geom=geo.three_nn(2))
+        features_1 = self.fp2(coords_1, coords_2, features_1, features_2, _geom=geo.three_nn(1))
+        features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0))
         x = self.drop(features_0)
         return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)
