@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- train points/s of the neighbourhood hot path behind the reference's model interface.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model dgcnn|pointnetpp|pointnext]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model dgcnn|pointnetpp|pointnetpp_msg|pointnext]
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --ref-device cuda ...   # the same op sequence through stock ATen kernels on cuda:0
     torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU, NCCL)
 
 A step = one full train step (forward + backward + Adam, lr 1e-3 as the reference's train.py:17,79) of
