@@ -51,8 +51,10 @@ static inline void topk_insert(orc_cand* best, int* cnt, int K, float key, int32
  * idx_out (B,C) int32; xyz_out (B,C,3) may be NULL. */
 ORC_API void orc_fps(const float* xyz, int B, int N, int C, const int32_t* start,
                      int32_t* idx_out, float* xyz_out) {
-    float* dist = (float*)malloc(sizeof(float) * (size_t)N);
+    /* clouds are independent (the batch index is an outer loop of common.py:25-31): one host thread per cloud */
+    #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
+        float* dist = (float*)malloc(sizeof(float) * (size_t)N);
         const float* p = xyz + (size_t)b * N * 3;
         for (int n = 0; n < N; ++n) dist[n] = INFINITY;           /* common.py:21 */
         int32_t far = start[b];
@@ -75,8 +77,8 @@ ORC_API void orc_fps(const float* xyz, int B, int N, int C, const int32_t* start
             }
             far = besti;
         }
+        free(dist);
     }
-    free(dist);
 }
 
 /* ------------------------------------------------------------ ball query */
@@ -84,7 +86,11 @@ ORC_API void orc_fps(const float* xyz, int B, int N, int C, const int32_t* start
  * out-of-ball points (d2 := inf) in ascending index.  idx (B,M,K) int32. */
 ORC_API void orc_ball_query(const float* q, const float* p, int B, int M, int N,
                             float r2, int K, int32_t* idx) {
+    /* rows of the (B,C,N) distance tensor are independent: host threads over (b, m), a private list each */
+    #pragma omp parallel
+    {
     orc_cand* best = (orc_cand*)malloc(sizeof(orc_cand) * (size_t)K);
+    #pragma omp for collapse(2) schedule(static)
     for (int b = 0; b < B; ++b)
         for (int m = 0; m < M; ++m) {
             const float* c = q + ((size_t)b * M + m) * 3;
@@ -100,6 +106,7 @@ ORC_API void orc_ball_query(const float* q, const float* p, int B, int M, int N,
             for (int k = 0; k < K; ++k) o[k] = best[k].idx;
         }
     free(best);
+    }
 }
 
 /* ------------------------------------------------- kNN, direct distances */
@@ -107,7 +114,10 @@ ORC_API void orc_ball_query(const float* q, const float* p, int B, int M, int N,
  * ascending (d2, idx).  idx (B,M,k) int32, d2out (B,M,k) may be NULL. */
 ORC_API void orc_knn_direct(const float* q, const float* p, int B, int M, int N, int K,
                             int32_t* idx, float* d2out) {
+    #pragma omp parallel
+    {
     orc_cand* best = (orc_cand*)malloc(sizeof(orc_cand) * (size_t)K);
+    #pragma omp for collapse(2) schedule(static)
     for (int b = 0; b < B; ++b)
         for (int m = 0; m < M; ++m) {
             const float* c = q + ((size_t)b * M + m) * 3;
@@ -124,6 +134,7 @@ ORC_API void orc_knn_direct(const float* q, const float* p, int B, int M, int N,
             }
         }
     free(best);
+    }
 }
 
 /* --------------------------------------- kNN, expanded form (DGCNN knn) */
@@ -169,7 +180,6 @@ ORC_API void orc_sumsq(const float* x, int B, int F, int N, float* xx) {
 /* dgcnn.py:16-20.  x (B,F,N) channel-first; idx (B,N,k) int32, descending pd, ties by
  * lowest index; pdout (B,N,k) may be NULL. */
 ORC_API void orc_knn_expand(const float* x, int B, int F, int N, int K, int32_t* idx, float* pdout) {
-    orc_cand* best = (orc_cand*)malloc(sizeof(orc_cand) * (size_t)K);
     float* xx = (float*)malloc(sizeof(float) * (size_t)N);
     float* xt = (float*)malloc(sizeof(float) * (size_t)N * F);   /* point-major copy */
     for (int b = 0; b < B; ++b) {
@@ -178,6 +188,11 @@ ORC_API void orc_knn_expand(const float* x, int B, int F, int N, int K, int32_t*
             xx[n] = column_sumsq(xb, F, N, n);
             for (int f = 0; f < F; ++f) xt[(size_t)n * F + f] = xb[(size_t)f * N + n];
         }
+        /* every row of the (N,N) matrix is computed independently: host threads over the rows */
+        #pragma omp parallel
+        {
+        orc_cand* best = (orc_cand*)malloc(sizeof(orc_cand) * (size_t)K);
+        #pragma omp for schedule(static)
         for (int i = 0; i < N; ++i) {
             int cnt = 0;
             const float* xi = xt + (size_t)i * F;
@@ -194,8 +209,42 @@ ORC_API void orc_knn_expand(const float* x, int B, int F, int N, int K, int32_t*
                 if (pdout) pdout[((size_t)b * N + i) * K + k] = -best[k].key;
             }
         }
+        free(best);
+        }
     }
-    free(best); free(xx); free(xt);
+    free(xx); free(xt);
+}
+
+/* dgcnn.py:16-20 for a SUBSET of the query rows of one cloud (large-N spot checks: the full (N,N) scan of a
+ * 100 k-point cloud is 1e10 pairs).  x (F,N) channel-first; rows (R) query indices; idx (R,k) int32. */
+ORC_API void orc_knn_expand_rows(const float* x, int F, int N, int K, const int32_t* rows, int R, int32_t* idx) {
+    float* xx = (float*)malloc(sizeof(float) * (size_t)N);
+    float* xt = (float*)malloc(sizeof(float) * (size_t)N * F);
+    for (int n = 0; n < N; ++n) {
+        xx[n] = column_sumsq(x, F, N, n);
+        for (int f = 0; f < F; ++f) xt[(size_t)n * F + f] = x[(size_t)f * N + n];
+    }
+    #pragma omp parallel
+    {
+    orc_cand* best = (orc_cand*)malloc(sizeof(orc_cand) * (size_t)K);
+    #pragma omp for schedule(static)
+    for (int r = 0; r < R; ++r) {
+        const int i = rows[r];
+        int cnt = 0;
+        const float* xi = xt + (size_t)i * F;
+        for (int j = 0; j < N; ++j) {
+            const float* xj = xt + (size_t)j * F;
+            float c = xi[0] * xj[0];
+            for (int f = 1; f < F; ++f) c = fmaf(xi[f], xj[f], c);
+            const float inner = -2.0f * c;
+            const float pd = ((-xx[j]) - inner) - xx[i];
+            topk_insert(best, &cnt, K, -pd, j);
+        }
+        for (int k = 0; k < K; ++k) idx[(size_t)r * K + k] = best[k].idx;
+    }
+    free(best);
+    }
+    free(xx); free(xt);
 }
 
 /* -------------------------------------------------- group gather+concat */

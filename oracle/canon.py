@@ -21,12 +21,13 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    """gcc -O2 -ffp-contract=off canon.c -> oracle/_build/liborc_canon.so"""
+    """gcc -O2 -fopenmp -ffp-contract=off canon.c -> oracle/_build/liborc_canon.so (host threads over independent
+    clouds / query rows only: every result is computed by one thread in the reference's order)"""
     os.makedirs(os.path.dirname(_SO), exist_ok=True)
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
         # -march=x86-64-v2 keeps the .so runnable on any host the snapshot travels to; fmaf()
         # then resolves to glibc's exact software/hardware-dispatched fma.
-        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+        cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
                "-fvisibility=hidden", "-o", _SO, _SRC, "-lm"]
         subprocess.run(cmd, check=True)
     return _SO
@@ -104,6 +105,17 @@ def knn_expand(x: torch.Tensor, K: int):
     pd = torch.empty(B, N, K, dtype=torch.float32)
     _load().orc_knn_expand(_fp(x), B, F, N, K, _ip(idx), _fp(pd))
     return idx, pd
+
+
+def knn_expand_rows(x: torch.Tensor, K: int, rows: torch.Tensor) -> torch.Tensor:
+    """x (F,N) one cloud, rows (R,) query indices -> idx (R,K) int32: knn_expand restricted to those rows
+    [models/dgcnn/dgcnn.py:7-21]"""
+    x = _f32(x)
+    F, N = x.shape
+    rows = rows.detach().to("cpu", torch.int32).contiguous()
+    idx = torch.empty(rows.numel(), K, dtype=torch.int32)
+    _load().orc_knn_expand_rows(_fp(x), F, N, K, _ip(rows), rows.numel(), _ip(idx))
+    return idx
 
 
 def group(q, p, feat, idx, r: float, normalize: bool) -> torch.Tensor:

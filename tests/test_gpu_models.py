@@ -188,3 +188,90 @@ def test_dgcnn_color_full_width_layers_vs_oracle(pkg, dev):
     # measured: median 1e-3, p99 6e-3 of the logit scale (neighbour swaps at the k-th/k+1-th boundary)
     assert diff.median().item() <= 5e-3 * scale, f"median {diff.median().item():.3e} scale {scale:.3e}"
     assert torch.quantile(diff, 0.99).item() <= 3e-2 * scale, f"p99 {torch.quantile(diff, 0.99).item():.3e} scale {scale:.3e}"
+
+
+# --------------------------------------------------------------------------- InvResMLP / PointNeXt
+
+def test_invresmlp_golden_output_and_gradients(pkg, dev, golden):
+    """The reference's InvResMLP (common.py:246-301) on a filled cloud: module output, input gradient and every parameter
+    gradient within 1e-4 (max-norm relative) of the UNMODIFIED reference's (oracle/make_golden_large.py)."""
+    g = golden("invresmlp")
+    gen = torch.Generator().manual_seed(g["data_seed"])
+    pc = torch.rand(2, g["N"], 3, generator=gen) * 0.15 + torch.tensor([3.0, 8.0, 0.0])
+    f = torch.randn(2, g["N"], 64, generator=gen)
+    torch.manual_seed(g["seed"])
+    blk = pkg.common.InvResMLP(g["radius"], g["cin"], g["width"], g["K"]).to(dev)
+    fd = f.to(dev).requires_grad_(True)
+    cen, out = blk(pc.to(dev), pc.to(dev), fd)
+    assert torch.equal(cen.cpu(), pc)
+    _close(out, g["out"])
+    w = torch.randn(out.shape, generator=gen)
+    (out * w.to(dev)).sum().backward()
+    _close(fd.grad, g["grad_features"])
+    params = dict(blk.named_parameters())
+    assert set(params) == set(g["grads"])
+    for k, v in g["grads"].items():
+        if k.endswith("conv.0.bias") or k.endswith("conv.1.bias"):
+            # a conv bias in front of a training-mode BatchNorm: the exact gradient is 0 (the reference returns fp32 noise)
+            assert params[k].grad.abs().max().item() <= 1e-4 * max(1.0, v.abs().max().item()) + v.abs().max().item()
+            continue
+        _close(params[k].grad, v, rtol=1e-3, scale_atol=2e-4)
+
+
+def test_pointnext_golden_logits_and_grads(pkg, dev, golden):
+    """PointNeXt logits and parameter gradients of the UNMODIFIED reference (PointNeXt.py:39-147) on a cloud where every
+    ball at every level holds >= K points (raw topk == canonical).  Same yardstick as PointNet++: as close to the float64
+    evaluation as the reference's own fp32 result."""
+    g = golden("pointnext")
+    gen = torch.Generator().manual_seed(g["data_seed"])
+    N = g["N"]
+    xyzf = torch.rand(2, N, 3, generator=gen) * 0.05 + torch.tensor([0.5, 0.25, 0.0])
+    rgb = torch.randint(0, 256, (2, N, 3), generator=gen).float()
+    x9 = torch.cat([xyzf, rgb, xyzf - xyzf.mean(dim=1, keepdim=True)], dim=-1)
+    torch.manual_seed(g["seed"])
+    net = pkg.PointNeXt(13)
+    net.drop.p = 0.0
+    torch.manual_seed(g["seed"])
+    ref64 = O.PointNeXt(13, tie="canon")
+    ref64.drop.p = 0.0
+    ref64 = ref64.double()
+    net = net.to(dev)
+    for name, st in zip(("sa1", "sa2", "sa3", "sa4"), g["fps_starts"]):
+        getattr(net, name).fps_start, getattr(ref64, name).fps_start = st.to(dev), st
+    wgt = torch.randn(2, N, 13, generator=gen)
+    logits = net(x9.to(dev))
+    (logits * wgt.to(dev)).sum().backward()
+    lo64 = ref64(x9.double())
+    (lo64 * wgt.double()).sum().backward()
+    _as_good_as_reference(logits, g["logits"], lo64, "logits")
+    params, p64 = dict(net.named_parameters()), dict(ref64.named_parameters())
+    for k, v in g["grads"].items():
+        _as_good_as_reference(params[k].grad, v, p64[k].grad, f"grad {k}")
+
+
+def test_pointnext_parameter_gradients_vs_oracle_model(pkg, dev):
+    """PointNeXt on an S3DIS-shaped block (under-filled balls, canonical ties): logits AND every parameter gradient."""
+    pts, _, _ = O.s3dis_blocks(2, 2048, seed=9)
+    torch.manual_seed(6)
+    ref = O.PointNeXt(13, tie="canon")
+    ref.drop.p = 0.0
+    net = pkg.PointNeXt(13)
+    net.drop.p = 0.0
+    _copy_model(net, ref)
+    net = net.to(dev)
+    ref64 = _fp64_twin(ref)
+    st = torch.tensor([3, 11], dtype=torch.int32)
+    for name in ("sa1", "sa2", "sa3", "sa4"):
+        getattr(net, name).fps_start = st.to(dev)
+        getattr(ref, name).fps_start = getattr(ref64, name).fps_start = st
+    w = torch.randn(2, 2048, 13, generator=torch.Generator().manual_seed(2))
+    lo = ref(pts)
+    (lo * w).sum().backward()
+    lo64 = ref64(pts.double())
+    (lo64 * w.double()).sum().backward()
+    lg = net(pts.to(dev))
+    (lg * w.to(dev)).sum().backward()
+    _as_good_as_reference(lg, lo, lo64, "logits")
+    pr, pr64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    for k, p in net.named_parameters():
+        _as_good_as_reference(p.grad, pr[k].grad, pr64[k].grad, f"grad {k}")

@@ -171,3 +171,46 @@ def test_msg_composition_matches_reference_functions(golden):
     m.fps_start = g["start"]
     cen, out = m(g["coords"], g["features"])
     assert torch.equal(cen, g["centroids"]) and torch.equal(out.detach(), g["out"])
+
+
+# --------------------------------------------------------------------------- round-2 fixtures (oracle/make_golden_large.py)
+
+def _chunk(B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    side = (N / 4096.0) ** 0.5
+    xy = torch.rand(B, N, 2, generator=g) * side + torch.randint(0, 20, (B, 1, 2), generator=g).float()
+    z = torch.rand(B, N, 1, generator=g) * 3.0
+    return torch.cat((xy, z), dim=2).contiguous()
+
+
+def test_knn_baseline_shape_matches_reference_golden(golden):
+    """F=64, N=4096, k=20 (BASELINE configs[1]): the C oracle equals the unmodified reference's knn() indices."""
+    g = golden("knn_F64_N4096")
+    x = torch.randn(1, 64, 4096, generator=torch.Generator().manual_seed(int(g["seed"])))
+    assert torch.equal(canon.knn_expand(x, int(g["k"]))[0].to(torch.int16), g["idx"])
+
+
+def test_large_fixtures_match_reference_golden(golden):
+    g = golden("fps_24k")
+    xyz = _chunk(1, g["N"], g["seed"])
+    assert torch.equal(canon.fps(xyz, g["C"], g["start"])[1], g["coords"])
+    g = golden("group_8k")
+    gen = torch.Generator().manual_seed(g["seed"])
+    p = torch.rand(1, 8192, 3, generator=gen) * 0.5
+    feat = torch.randn(1, 8192, 6, generator=gen)
+    idx = canon.ball_query(g["centroids"], p, g["r"], g["K"])
+    assert torch.equal(canon.group(g["centroids"], p, feat, idx, g["r"], True), g["out"])
+    h = golden("interp_8k")
+    i3, d3 = canon.knn_direct(p, g["centroids"], 3)
+    out = canon.interp(h["points"], i3, d3)
+    assert torch.equal(out[:, :512], h["out_first"]) and torch.equal(out.double().sum(dim=1), h["out_sum"])
+
+
+def test_invresmlp_and_pointnext_oracle_match_reference_golden(golden):
+    g = golden("invresmlp")
+    gen = torch.Generator().manual_seed(g["data_seed"])
+    pc = torch.rand(2, g["N"], 3, generator=gen) * 0.15 + torch.tensor([3.0, 8.0, 0.0])
+    f = torch.randn(2, g["N"], 64, generator=gen)
+    torch.manual_seed(g["seed"])
+    blk = O.InvResMLP(g["radius"], g["cin"], g["width"], g["K"], tie="canon")
+    assert torch.equal(blk(pc, pc, f)[1], g["out"])
