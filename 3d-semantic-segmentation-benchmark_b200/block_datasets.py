@@ -46,8 +46,18 @@ def draw_rows_host(counts, block_ids, sampling: int) -> torch.Tensor:
     return sel
 
 
+def plan_steps(num_blocks: int, batch_size: int, world_size: int = 1, drop_last: bool | None = None) -> int:
+    """Batches EVERY rank runs per epoch.  One rank: ceil(blocks / batch) (the reference's DataLoader, drop_last=False).
+    Several ranks: the short last batch is dropped (a fixed batch shape: the captured train step has static inputs) and the
+    epoch is truncated to a multiple of world_size batches, so all ranks issue the same number of gradient all-reduces."""
+    if drop_last is None:
+        drop_last = world_size > 1
+    total = num_blocks // batch_size if drop_last else (num_blocks + batch_size - 1) // batch_size
+    return total // world_size
+
+
 def loader_plan(num_blocks: int, counts, batch_size: int, shuffle: bool, sampling: int | None, host_draws: bool = True,
-                rank: int = 0, world_size: int = 1):
+                rank: int = 0, world_size: int = 1, drop_last: bool | None = None):
     """Host side of one epoch: yields (block ids, sel (B,S) int32 or None) per batch, consuming torch's host generator
     exactly like `iter(DataLoader(dataset, batch_size, shuffle, num_workers=0))` over the reference's dataset does:
     the iterator's base-seed draw (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__), RandomSampler's seed
@@ -55,12 +65,15 @@ def loader_plan(num_blocks: int, counts, batch_size: int, shuffle: bool, samplin
 
     world_size > 1 (one process per GPU, same seed on every rank): rank r takes batches r, r + world_size, ... of that
     same epoch plan -- the batch dimension is sharded, no rank sees another rank's blocks, and every rank makes all the
-    draws so the generators stay in lockstep (the union over the ranks is exactly the single-process epoch)."""
+    draws so the generators stay in lockstep (the union over the ranks is the single-process epoch, minus the tail that
+    plan_steps() cuts so that every rank runs the same number of equally shaped steps -- a rank with one batch more would
+    wait for ever in its gradient all-reduce)."""
     torch.empty((), dtype=torch.int64).random_()
     sampler = RandomSampler(range(num_blocks)) if shuffle else SequentialSampler(range(num_blocks))
+    usable = plan_steps(num_blocks, batch_size, world_size, drop_last) * world_size
     for i, ids in enumerate(BatchSampler(sampler, batch_size, drop_last=False)):
-        sel = draw_rows_host(counts, ids, sampling) if (sampling is not None and host_draws) else None
-        if i % world_size == rank:
+        sel = draw_rows_host(counts, ids, sampling) if (sampling is not None and host_draws) else None     # all ranks draw: lockstep
+        if i < usable and i % world_size == rank:
             yield ids, sel
 
 
@@ -205,21 +218,21 @@ class BlockLoader:
     num_workers=0 DataLoader (torch's own RandomSampler / BatchSampler produce the order)."""
 
     def __init__(self, dataset: BlockS3DISDataset, batch_size: int, shuffle: bool, device_sampling: bool = False,
-                 generator: torch.Generator | None = None, rank: int = 0, world_size: int = 1):
+                 generator: torch.Generator | None = None, rank: int = 0, world_size: int = 1, drop_last: bool | None = None):
         if not 0 <= rank < world_size:
             raise ValueError(f"rank {rank} outside [0, {world_size})")
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
         self.device_sampling, self.generator = device_sampling, generator
-        self.rank, self.world_size = rank, world_size
+        self.rank, self.world_size, self.drop_last = rank, world_size, drop_last
 
     def __len__(self) -> int:
-        total = (len(self.dataset) + self.batch_size - 1) // self.batch_size
-        return (total - self.rank + self.world_size - 1) // self.world_size
+        return plan_steps(len(self.dataset), self.batch_size, self.world_size, self.drop_last)
 
     def __iter__(self):
         packed, S = self.dataset.packed, self.dataset.sampling
         for ids, sel in loader_plan(len(packed), packed.counts_host, self.batch_size, self.shuffle, S,
-                                    host_draws=not self.device_sampling, rank=self.rank, world_size=self.world_size):
+                                    host_draws=not self.device_sampling, rank=self.rank, world_size=self.world_size,
+                                    drop_last=self.drop_last):
             if S is not None and self.device_sampling:
                 sel = packed.draw_device(ids, S, self.generator)
             yield packed.batch(ids, S, sel)

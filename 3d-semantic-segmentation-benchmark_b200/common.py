@@ -79,6 +79,7 @@ class MiniPointNet(nn.Module):
         B, _, C, K = x.shape
         rows = x.permute(0, 2, 3, 1)
         if not (x.is_cuda and rows.is_contiguous()):
+            ops.note_fallback("MiniPointNet.forward: input is not a channels-last view (cuDNN convolutions)")
             for conv, bn in zip(self.conv, self.batch):
                 x = F.relu(bn(conv(x)))
             return x
@@ -103,6 +104,7 @@ class MiniPointNet(nn.Module):
 def _batch_norm_rows(bn: nn.modules.batchnorm._BatchNorm, rows: torch.Tensor) -> torch.Tensor:
     """nn.BatchNorm{1,2}d applied to a (rows, channels) matrix: same statistics, running-stat update and
     num_batches_tracked bookkeeping as the module's own forward."""
+    ops.note_fallback("F.batch_norm on rows")
     training = bn.training or bn.running_mean is None
     momentum = bn.momentum
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -134,6 +136,7 @@ class UnitPointNet(nn.Module):
         B, _, N = x.shape
         rows = x.permute(0, 2, 1)
         if not (x.is_cuda and rows.is_contiguous()):
+            ops.note_fallback("UnitPointNet.forward: input is not a transposed point-major view (cuDNN convolutions)")
             for conv, bn in zip(self.conv, self.batch):
                 x = F.relu(bn(conv(x)))
             return x

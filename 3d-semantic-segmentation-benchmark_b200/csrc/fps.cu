@@ -55,7 +55,7 @@ fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
         }
     }
 
-    int cur = start[b];
+    int cur = min(max(start[b], 0), N - 1);        // a caller-supplied first pick outside [0, N) is clamped, never dereferenced
     float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
 
     for (int i = 0; i < C; ++i) {
@@ -153,7 +153,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
             md[j] = 0.f;
         }
     }
-    int cur = start[b];
+    int cur = min(max(start[b], 0), N - 1);        // a caller-supplied first pick outside [0, N) is clamped, never dereferenced
     float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
     cluster.sync();                                            // every CTA of the cluster is resident before remote stores
 
@@ -264,7 +264,7 @@ fps_big_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
     const float* __restrict__ p = xyz + (size_t)b * N * 3;
     float* __restrict__ md = ws + (size_t)b * N;
     for (int n = tid; n < N; n += T) md[n] = __int_as_float(0x7f800000);
-    int cur = start[b];
+    int cur = min(max(start[b], 0), N - 1);        // a caller-supplied first pick outside [0, N) is clamped, never dereferenced
     for (int i = 0; i < C; ++i) {
         const float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
         if (tid == 0) {

@@ -23,6 +23,26 @@ __all__ = [
 # ----------------------------------------------------------------------------- plumbing
 
 
+FALLBACKS: dict = {}          # library (cuBLAS / cuDNN / ATen) code paths taken instead of a libpcnbr kernel: name -> count
+_STRICT = __import__("os").environ.get("PCNBR_STRICT") is not None
+
+
+def note_fallback(name: str) -> None:
+    """Record that a shape outside the kernels' coverage went to a torch library op.  The bench / drop-in configurations
+    must not hit any (tests assert `fallbacks() == {}`); PCNBR_STRICT=1 turns every fallback into an error."""
+    if _STRICT:
+        raise RuntimeError(f"pcnbr: library fallback '{name}' taken with PCNBR_STRICT set")
+    FALLBACKS[name] = FALLBACKS.get(name, 0) + 1
+
+
+def fallbacks() -> dict:
+    return dict(FALLBACKS)
+
+
+def reset_fallbacks() -> None:
+    FALLBACKS.clear()
+
+
 _STREAM_OVERRIDE = None       # raw stream handle the C-ABI calls go to instead of the current stream (see on_stream)
 
 
@@ -158,6 +178,24 @@ class NeighborIndex:
             self._event, self._keep = None, None
         return self._csr
 
+    def __del__(self):
+        # A prefetched inverse that no backward ever consumed (validation with grad enabled, a discarded loss, an exception):
+        # its buffers go back to the allocator of the CURRENT stream while the side stream may still be writing them.  Order
+        # every later use of those blocks after the build before letting them go.
+        _release_after(getattr(self, "_event", None))
+
+
+def _release_after(ev) -> None:
+    """The current stream waits on a side-stream event whose consumer never came (see NeighborIndex.__del__)."""
+    if ev is None:
+        return
+    try:
+        if ev in _PENDING_AUX:
+            _PENDING_AUX.remove(ev)
+        torch.cuda.current_stream().wait_event(ev)
+    except Exception:                                   # interpreter shutdown / device already torn down
+        pass
+
 
 class PyramidGeometry:
     """All index-only work of a PointNet++ encoder/decoder for one batch (models/PointNetpp/PointNetpp.py:26-41 call
@@ -270,12 +308,20 @@ class PyramidGeometry:
     def level(self, l: int):
         """(centroid coords, ball-query NeighborIndex) of set-abstraction level l (0-based), ready on the current stream."""
         self._wait(self.ball_events[l])
+        self.ball_events[l] = None
         return self.coords[l + 1], self.balls[l]
 
     def three_nn(self, l: int):
         """(NeighborIndex, d2) for interpolating level l+1 features onto level l, ready on the current stream."""
         self._wait(self.knn_events[l])
+        self.knn_events[l] = None
         return self.knn[l]
+
+    def __del__(self):
+        # tables nobody asked for (a forward that stopped early): same hazard as NeighborIndex.__del__
+        for ev in list(getattr(self, "ball_events", [])) + list(getattr(self, "knn_events", {}).values()):
+            if ev is not None and ev in _PENDING_AUX:
+                _release_after(ev)
 
 
 class _NullCtx:
@@ -769,6 +815,7 @@ def batchnorm_act_rows(rows: torch.Tensor, bn, negative_slope: float) -> torch.T
     R = rows.numel() // max(C, 1)
     training, momentum, rm, rv = _bn_mode(bn)
     if not (rows.is_cuda and rows.dtype == torch.float32 and _lib.size("pcnbr_bn_supported", R, C)):
+        note_fallback(f"batch_norm[C={C}]")
         y = torch.nn.functional.batch_norm(rows.reshape(R, C), rm, rv, bn.weight, bn.bias, training, momentum, bn.eps)
         return torch.nn.functional.leaky_relu(y, negative_slope).view(rows.shape)
     y = _BnActRowsFn.apply(_c(rows).view(R, C), bn.weight, bn.bias, rm, rv, training, momentum, float(bn.eps),
@@ -958,7 +1005,7 @@ def linear_bn_act_maxpool_rows(rows: torch.Tensor, weight: torch.Tensor, bias, b
     cout = weight.shape[0]
     nrows = Bc * Cc * K
     fused = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
-             and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4 and K <= 255
+             and cin % 4 == 0 and cout % 4 == 0 and K <= 255
              and _lib.size("pcnbr_bn_supported", nrows, cout) and _lib.size("pcnbr_bn_supported", Bc * Cc, cout))
     if not fused:
         return max_pool_neighbors(linear_bn_act_rows(rows, weight, bias, bn, negative_slope), 2)
@@ -1042,7 +1089,7 @@ def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: tor
     cout = weight.shape[0]
     nrows = rows1.numel() // max(k1, 1)
     fused = (not _GEMM_LIBRARY and rows1.is_cuda and rows1.dtype == torch.float32 and rows2.dtype == torch.float32
-             and weight.dtype == torch.float32 and nrows >= 1024 and k1 % 32 == 0 and k2 % 4 == 0 and cout % 4 == 0
+             and weight.dtype == torch.float32 and k1 % 32 == 0 and k2 % 4 == 0 and cout % 4 == 0
              and weight.shape[1] == k1 + k2 and _lib.size("pcnbr_bn_supported", nrows, cout))
     if not fused:
         return linear_bn_act_rows(torch.cat((rows1, rows2), dim=-1), weight, bias, bn, negative_slope, dropout_p)
@@ -1059,8 +1106,12 @@ def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negat
     dropout_p > 0 fuses the nn.Dropout(dropout_p) (training mode) that follows the activation (dgcnn.py:117,122)."""
     cin, cout = weight.shape[1], weight.shape[0]
     nrows = rows.numel() // max(cin, 1)
+    if cin % 4 and rows.is_cuda:                               # e.g. the 9-channel stem: 16-byte row pitch for TMA
+        pad = (-cin) % 4
+        rows, weight = torch.nn.functional.pad(rows, (0, pad)), torch.nn.functional.pad(weight, (0, pad))
+        cin += pad
     fused = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
-             and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4 and _lib.size("pcnbr_bn_supported", nrows, cout))
+             and cout % 4 == 0 and _lib.size("pcnbr_bn_supported", nrows, cout))
     if not fused:
         y = batchnorm_act_rows(linear_rows(rows, weight, bias), bn, negative_slope)
         return torch.nn.functional.dropout(y, dropout_p, True) if dropout_p > 0.0 else y
@@ -1075,25 +1126,25 @@ _GEMM_LIBRARY = __import__("os").environ.get("PCNBR_GEMM_LIBRARY") is not None
 
 def linear_rows(rows: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
     """rows (..., Cin) @ weight (Cout, Cin)^T + bias: the 1x1 convolutions of models/utils/common.py:125-178 and
-    models/dgcnn/dgcnn.py:66-126 on point-major rows.  Layers with 4-aligned channel counts and >= 1024 rows run all
-    three GEMMs on the hand-written 3xTF32 tcgen05 kernel; the rest (odd widths such as the 13-class head) stay on the
-    library SGEMM (PCNBR_GEMM_LIBRARY=1 forces the library everywhere).  `rows` may be a row-pitched view (unit inner
-    stride, uniform row pitch that is a multiple of 4 floats)."""
+    models/dgcnn/dgcnn.py:66-126 on point-major rows.  All three GEMMs of the layer run on the hand-written tcgen05
+    kernel; channel counts that are not multiples of 4 (the 9-channel stem, the 13 / 14-class heads) are zero-padded to
+    the 16-byte pitch TMA needs (autograd slices the pad away again).  PCNBR_GEMM_LIBRARY=1 forces the library SGEMM
+    (A/B measurements only).  `rows` may be a row-pitched view (unit inner stride, uniform row pitch that is a multiple
+    of 4 floats)."""
     cin, cout = weight.shape[1], weight.shape[0]
     nrows = rows.numel() // max(cin, 1)
-    if (cout % 4 and cout >= 8 and cin % 4 == 0 and nrows >= 16384 and not _GEMM_LIBRARY and rows.is_cuda
-            and rows.dtype == torch.float32 and weight.dtype == torch.float32):
-        # class heads (13 / 14 outputs): zero-pad the output channels to a multiple of 4 so that the layer -- above all its
-        # weight gradient over all the points, which the library runs on one or two CTAs -- goes through the tensor-core
-        # GEMM; the pad outputs are sliced away again (autograd slices the gradients of the padded weight and bias)
+    usable = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32 and nrows >= 1)
+    if not usable:
+        note_fallback(f"linear[{cin}->{cout}]")
+        return torch.nn.functional.linear(rows, weight, bias)
+    if cout % 4:
         pad = (-cout) % 4
         wp = torch.nn.functional.pad(weight, (0, 0, 0, pad))
         bp = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
         return linear_rows(rows, wp, bp)[..., :cout]
-    usable = (not _GEMM_LIBRARY and rows.is_cuda and rows.dtype == torch.float32 and weight.dtype == torch.float32
-              and nrows >= 1024 and cin % 4 == 0 and cout % 4 == 0 and cin >= 4)
-    if not usable:
-        return torch.nn.functional.linear(rows, weight, bias)
+    if cin % 4:
+        pad = (-cin) % 4
+        return linear_rows(torch.nn.functional.pad(rows, (0, pad)), torch.nn.functional.pad(weight, (0, pad)), bias)
     x2 = _c(rows).view(nrows, cin)
     y = _LinearRowsFn.apply(x2, _c(weight), bias)
     return y.view(*rows.shape[:-1], cout)

@@ -42,6 +42,8 @@ def masked_onehot_cross_entropy(logits: torch.Tensor, targets_onehot: torch.Tens
         onehot = targets_onehot.to(device=logits.device, dtype=torch.uint8).contiguous()
         lens = pad_starts.to(device=logits.device, dtype=torch.int64).contiguous()
         return _MaskedCEFn.apply(logits.contiguous(), onehot, lens)
+    from .ops import note_fallback
+    note_fallback("masked_onehot_cross_entropy: torch ops")
     logp = F.log_softmax(logits, dim=-1)
     tok = -(targets_onehot.to(logp.dtype) * logp).sum(dim=-1)
     mask = (torch.arange(L, device=logits.device).unsqueeze(0) < pad_starts.to(logits.device).long().unsqueeze(1)).to(logp.dtype)

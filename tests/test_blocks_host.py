@@ -92,8 +92,8 @@ def test_block_store_and_scene_inference_need_cuda(pkg):
 
 
 def test_loader_plan_shards_batches_across_ranks(pkg, golden):
-    """world_size 3: the ranks' batches are disjoint, their union in batch order is the single-process epoch, and every
-    rank leaves the host generator in the same state (lockstep draws)."""
+    """world_size 3: the ranks' batches are disjoint, interleave to the single-process epoch (up to the tail cut for equal
+    step counts), and every rank leaves the host generator in the same state (lockstep draws)."""
     g = golden("blocks")
     blocks = g["train_blocks"]
     counts = [b[0].shape[0] for b in blocks]
@@ -106,9 +106,33 @@ def test_loader_plan_shards_batches_across_ranks(pkg, golden):
         torch.manual_seed(7)
         per_rank.append(list(plan(len(blocks), counts, 2, True, g["sampling"], rank=r, world_size=3)))
         assert torch.equal(torch.get_rng_state(), state)
-    assert sum(len(p) for p in per_rank) == len(whole)
-    for i, (ids, sel) in enumerate(whole):
+    steps = pkg.block_datasets.plan_steps(len(blocks), 2, 3)
+    assert [len(p) for p in per_rank] == [steps] * 3 and steps == (len(blocks) // 2) // 3
+    for i in range(3 * steps):
+        ids, sel = whole[i]
         rid, rsel = per_rank[i % 3][i // 3]
         assert rid == ids and torch.equal(rsel, sel)
     seen = [tuple(ids) for p in per_rank for ids, _ in p]
     assert len(set(seen)) == len(seen)
+
+
+def test_every_rank_runs_the_same_number_of_equally_shaped_steps(pkg):
+    """with n_batches % world != 0 (or a short last batch) ranks used to run different step counts and the
+    epoch ended in a hung all-reduce.  Every (blocks, batch, world) combination now gives all ranks the same number of
+    batches, all of them full."""
+    plan, steps_of = pkg.block_datasets.loader_plan, pkg.block_datasets.plan_steps
+    for nblocks in (5, 7, 16, 23):
+        counts = [100 + i for i in range(nblocks)]
+        for bs in (2, 3, 4):
+            for world in (2, 3, 4, 8):
+                lens = []
+                for r in range(world):
+                    torch.manual_seed(1)
+                    batches = list(plan(nblocks, counts, bs, True, 64, rank=r, world_size=world))
+                    assert all(len(ids) == bs for ids, _ in batches)
+                    lens.append(len(batches))
+                assert lens == [steps_of(nblocks, bs, world)] * world
+    # one rank keeps the reference's DataLoader semantics: the short last batch is yielded
+    torch.manual_seed(1)
+    single = list(plan(7, [50] * 7, 2, False, None))
+    assert [len(ids) for ids, _ in single] == [2, 2, 2, 1] and steps_of(7, 2) == 4

@@ -120,13 +120,27 @@ def test_gemm3x_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K):
     assert torch.equal(out, pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K))
 
 
-def test_linear_rows_narrow_layers_stay_on_the_library(pkg, dev):
-    x = torch.randn(4096, 9, device=dev)
-    w = torch.randn(32, 9, device=dev)
+@pytest.mark.parametrize("R,Cin,Cout", [(4096, 9, 32), (512, 768, 256), (32, 512, 256), (65536, 256, 13), (100, 7, 5)])
+def test_linear_rows_odd_widths_and_few_rows_run_on_libpcnbr(pkg, dev, R, Cin, Cout):
+    """Channel counts that are not multiples of 4 (9-channel stem, 13-class head) are zero-padded to the TMA pitch and
+    tiny row counts (the deepest PointNet++ levels at small batches) take the same tensor-core kernel: no shape of the
+    models falls back to the library SGEMM (ops.fallbacks() stays empty)."""
+    g = torch.Generator().manual_seed(R + Cin)
+    x, w, b = torch.randn(R, Cin, generator=g), torch.randn(Cout, Cin, generator=g), torch.randn(Cout, generator=g)
+    gy = torch.randn(R, Cout, generator=g)
+    pkg.ops.reset_fallbacks()
+    xd, wd, bd = (t.to(dev).requires_grad_(True) for t in (x, w, b))
     launches0 = pkg._lib.launches
-    y = pkg.ops.linear_rows(x, w, None)
-    assert pkg._lib.launches == launches0
-    _close(y, x.double() @ w.double().t(), 1e-5)
+    y = pkg.ops.linear_rows(xd, wd, bd)
+    y.backward(gy.to(dev))
+    assert pkg._lib.launches > launches0 and pkg.ops.fallbacks() == {}
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    y64 = torch.nn.functional.linear(x64, w64, b64)
+    y64.backward(gy.double())
+    _close(y, y64, 3e-5)
+    _close(xd.grad, x64.grad, 3e-5)
+    _close(wd.grad, w64.grad, 3e-5)
+    _close(bd.grad, b64.grad, 1e-5)
 
 
 # --------------------------------------------------------------------------- fused BatchNorm + (Leaky)ReLU over rows
