@@ -426,8 +426,12 @@ static int gm_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int units = ((M + GM_BM - 1) / GM_BM) * ((N + BN - 1) / BN) * splits;
     const int grid = units < sms ? units : sms;
-    // algorithmic work: 2 M N K flop counted once (the kernel issues 3x); operands once + result bytes
-    PCNBR_TIMED("gemm3x_kernel", s, 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), 2.0 * M * (double)N * K,
+    // algorithmic work: 2 M N K flop counted once (the kernel issues 3x); operands once + result bytes.  The profiler
+    // keeps two shape classes apart: launches whose tensor-pipe time bound (TF32 peak) exceeds their HBM time bound, and
+    // the narrow layers for which the bytes bind (measured peaks: 678 TFLOP/s, 6551 GB/s)
+    const double gm_bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), gm_flops = 2.0 * M * (double)N * K;
+    const char* gm_name = gm_flops / 678.35e12 > gm_bytes / 6551e9 ? "gemm3x_kernel[tensor]" : "gemm3x_kernel[hbm]";
+    PCNBR_TIMED(gm_name, s, gm_bytes, gm_flops,
                 (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias)));
     PCNBR_CHECK_LAUNCH();
     return 0;

@@ -2,15 +2,21 @@
 """bench.py -- train points/s of the neighbourhood hot path behind the reference's model interface.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--model dgcnn|pointnetpp|pointnetpp_msg|pointnext]
-    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on host cores
-    python bench.py --impl reference --ref-device cuda ...   # the same op sequence through stock ATen kernels on cuda:0
-    torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU, NCCL)
+                    [--scaling weak|strong] [--no-extras]
+    python bench.py --impl reference ...                     # the UNMODIFIED reference (oracle/_ref) on the host cores
+    python bench.py --impl reference --ref-device cuda ...   # the same reference code through stock ATen kernels on cuda:0
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, NCCL
 
-A step = one full train step (forward + backward + Adam, lr 1e-3 as the reference's train.py:17,79) of
-the model on one batch of synthetic S3DIS-shaped blocks; every neighbourhood op runs in libpcnbr
-(hand-written sm_100a kernels through the C ABI), the 1x1 convolutions / BatchNorm are library calls.
-Default workload = BASELINE.json configs[1]: DGCNN (DGCNNWithColor, the class train.py builds) k=20,
-batch 16 x 4096 points per GPU, 13 classes, strict fp32 (TF32 off).  Prints ONE JSON line.
+A step = one full train step (forward + backward + Adam, lr 1e-3 as the reference's train.py:17,79) of the model on one
+batch of synthetic S3DIS-shaped blocks; every op of the step runs in libpcnbr (hand-written sm_100a kernels through the
+C ABI) except Adam (torch's fused multi-tensor kernel) and the NCCL all-reduce.  Default workload = BASELINE.json
+configs[1]: DGCNN (DGCNNWithColor, the class train.py builds) k=20, batch 16 x 4096 points per GPU, 13 classes, strict
+fp32.  Prints ONE JSON line.  With the default model the line also carries (unless --no-extras)
+  "pointnetpp"     the co-headline model of the north star (PointNet++ SSG, 32 x 4096 per GPU), same measurement;
+  "reference_gpu"  SURVEY 8d "also time": the unmodified reference's train step through stock ATen / cuBLAS / cuDNN on
+                   the same B200, same batch (N=1 only);
+  "strong"         N>1 only: the same models with the GLOBAL batch fixed at the BASELINE batch (16 / 32 clouds split over
+                   the ranks), i.e. the strong-scaling point next to the weak one.
 """
 from __future__ import annotations
 
@@ -26,12 +32,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+def _argv_value(flag, default):
+    for i, a in enumerate(sys.argv):
+        if a == flag and i + 1 < len(sys.argv):
+            return sys.argv[i + 1]
+        if a.startswith(flag + "="):
+            return a.split("=", 1)[1]
+    return default
+
+
+# the reference's CPU path must not see a GPU: models/dgcnn/dgcnn.py:39 picks its device from torch.cuda.is_available(),
+# not from its input, so on a CUDA box the unmodified DGCNN cannot run on CPU tensors unless CUDA is hidden
+if _argv_value("--impl", "ours") == "reference" and _argv_value("--ref-device", "cpu") == "cpu":
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
 import torch  # noqa: E402
 
 N_POINTS = 4096
 N_CLASSES = 13
 METRIC = "train_points_per_sec"
 UNIT = "points/s"
+REF_TREE = os.path.join(ROOT, "oracle", "_ref")
 
 
 def parse():
@@ -41,13 +62,16 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="dgcnn", choices=["dgcnn", "pointnetpp", "pointnetpp_msg", "pointnext"])
-    ap.add_argument("--batch", type=int, default=0, help="clouds per GPU (default 16 dgcnn / 32 pointnet++)")
+    ap.add_argument("--batch", type=int, default=0, help="clouds per GPU (default 16 dgcnn / 32 pointnet++ / 4 pointnext)")
     ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch clouds per GPU; strong: the BASELINE batch split over the ranks")
+    ap.add_argument("--no-extras", action="store_true", help="only the requested model (no pointnetpp / reference_gpu / strong records)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
-    ap.add_argument("--cpu-batch", type=int, default=2, help="clouds per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="clouds per CPU-reference step (0 = sized to ~120 s of CPU work)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
-                    help="--impl reference only: 'cuda' runs the same oracle port on cuda:0 with stock ATen / cuBLAS / cuDNN "
+                    help="--impl reference only: 'cuda' runs the same reference code on cuda:0 with stock ATen / cuBLAS / cuDNN "
                          "kernels at the full per-GPU batch (SURVEY 8d 'also time': the reference's own GPU path)")
     return ap.parse_args()
 
@@ -63,6 +87,13 @@ def workload_name(model, B, N):
         "pointnetpp_msg": f"PointNet++ MSG semseg (two radii per level, one multi-radius ball query), batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
         "pointnext": f"PointNeXt semseg, batch {B} x {N} pts x 9 ch per GPU, {N_CLASSES} classes, fwd+bwd+Adam",
     }[model]
+
+
+def config_for(model, B, N, world):
+    """The `config` object: identical for our arm and the reference arm of the same command line."""
+    return {"workload": workload_name(model, B, N), "global_batch": B * world, "parallelism": f"dp{world}",
+            "precision": "strict fp32 (TF32 disabled for cuBLAS and cuDNN)",
+            "l2": "no explicit flush: per-step activations (GBs) far exceed the 126 MB L2; 4 input batches rotate"}
 
 
 # --------------------------------------------------------------------------- clocks
@@ -84,6 +115,7 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -106,7 +138,7 @@ class ClockSampler:
 
 
 def model_input(model, pts):
-    # train.py feeds (B,N,9); DGCNNWithColor wants (B,6,N) (SURVEY.md §7-7: adapter outside the reference files)
+    # train.py feeds (B,N,9); DGCNNWithColor wants (B,6,N) (SURVEY.md 7-7: adapter outside the reference files)
     return pts[:, :, :6].transpose(1, 2) if model == "dgcnn" else pts
 
 
@@ -124,38 +156,58 @@ def logits_of(out):
     return out[0] if isinstance(out, tuple) else out
 
 
-# --------------------------------------------------------------------------- reference arm / cpu baseline
+# --------------------------------------------------------------------------- the reference (oracle/_ref, else the oracle port)
 
 
-def cpu_reference_steps(model, cloud_batch, N, steps, warmup, device="cpu"):
-    """The reference's own implementation of the path (oracle/ref_ops.py: the same ATen op sequence, raw torch.topk
-    selection): fwd + bwd + Adam on `cloud_batch` clouds, timed on the host cores -- or, with device="cuda", on cuda:0
-    through the stock ATen / cuBLAS / cuDNN kernels the reference would launch there (torch defaults, as train.py)."""
+def reference_factory(model):
+    """-> (constructor, criterion, kind).  kind "reference": the UNMODIFIED reference classes from oracle/_ref (a verbatim
+    copy made by oracle/make_ref.py; /root/reference itself does not exist on the GPU box) with the reference's own
+    criterion (Training/train_model.py:15-57).  kind "port": oracle/ref_ops.py (same ATen op sequence, raw torch.topk
+    selection) -- only when the copy is missing, or for the MSG network, which the reference does not ship."""
+    have = os.path.isdir(os.path.join(REF_TREE, "models", "utils"))
+    if have and model in ("dgcnn", "pointnetpp", "pointnext"):
+        if REF_TREE not in sys.path:
+            sys.path.insert(0, REF_TREE)
+        from Training.train_model import masked_onehot_cross_entropy as crit
+        if model == "dgcnn":
+            from models.dgcnn.dgcnn import DGCNNWithColor
+            return (lambda: DGCNNWithColor(num_classes=N_CLASSES, k=20)), crit, "reference"
+        if model == "pointnetpp":
+            from models.PointNetpp.PointNetpp import PointNetpp
+            return (lambda: PointNetpp(N_CLASSES)), crit, "reference"
+        from models.PointNeXt.PointNeXt import PointNeXt
+        return (lambda: PointNeXt(N_CLASSES)), crit, "reference"
     from oracle import ref_ops as O
-    s3dis_blocks = O.s3dis_blocks
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    dev = torch.device(device)
-    net = {"dgcnn": lambda: O.DGCNNWithColor(N_CLASSES, k=20, tie="raw"),
-           "pointnetpp": lambda: O.PointNetpp(N_CLASSES, tie="raw"),
-           "pointnetpp_msg": lambda: O.PointNetppMSG(N_CLASSES, tie="raw"),
-           "pointnext": lambda: O.PointNeXt(N_CLASSES, tie="raw")}[model]().to(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-    pts, lab, lens = (t.to(dev) for t in s3dis_blocks(cloud_batch, N, 0, N_CLASSES))
 
     def ce(logits, onehot, lens):
         logp = torch.log_softmax(logits, dim=-1)
         tok = -(onehot.float() * logp).sum(-1)
-        mask = (torch.arange(logits.shape[1], device=dev).unsqueeze(0) < lens.unsqueeze(1)).float()
+        mask = (torch.arange(logits.shape[1], device=logits.device).unsqueeze(0) < lens.to(logits.device).unsqueeze(1)).float()
         return (tok * mask).sum() / mask.sum()
+    ctor = {"dgcnn": lambda: O.DGCNNWithColor(N_CLASSES, k=20, tie="raw"), "pointnetpp": lambda: O.PointNetpp(N_CLASSES, tie="raw"),
+            "pointnetpp_msg": lambda: O.PointNetppMSG(N_CLASSES, tie="raw"), "pointnext": lambda: O.PointNeXt(N_CLASSES, tie="raw")}[model]
+    return ctor, ce, "port"
 
+
+def reference_steps(model, cloud_batch, N, steps, warmup, device="cpu"):
+    """fwd + bwd + Adam of the reference on `cloud_batch` clouds, wall-clock per step (device synchronised on CUDA).
+    -> (times [s], threads, kind)."""
+    from oracle.ref_ops import s3dis_blocks
+    ctor, crit, kind = reference_factory(model)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    dev = torch.device(device)
+    net = ctor().to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    pts, lab, lens = s3dis_blocks(cloud_batch, N, 0, N_CLASSES)
+    pts, lab = pts.to(dev), lab.to(dev)
     times = []
     for i in range(warmup + steps):
         if dev.type == "cuda":
             torch.cuda.synchronize()
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss = ce(logits_of(net(model_input(model, pts))), lab, lens)
+        loss = crit(logits_of(net(model_input(model, pts))), lab, lens)
         loss.backward()
         opt.step()
         if dev.type == "cuda":
@@ -163,7 +215,30 @@ def cpu_reference_steps(model, cloud_batch, N, steps, warmup, device="cpu"):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times, torch.get_num_threads()
+    return times, torch.get_num_threads(), kind
+
+
+def cpu_sample_batch(model, full_batch, N, steps, warmup, budget_s=75.0):
+    """Clouds per CPU step so that warmup + steps fit `budget_s` of host time: one calibration step on 2 clouds (points/s is
+    batch-independent on the CPU within ~10 %: the ops are per cloud), then the largest batch <= the full per-GPU batch."""
+    t, _, _ = reference_steps(model, 2, N, 1, 1)
+    per_cloud = t[0] / 2
+    fit = int(budget_s / max(1, steps + warmup) / max(per_cloud, 1e-6))
+    return max(2, min(full_batch, fit)), per_cloud
+
+
+def cpu_baseline_subprocess(model, clouds, N):
+    """The `cpu_baseline` leg of our arm: the reference arm of this script on a bounded sample, in a child process that
+    cannot see the GPU (the unmodified reference picks 'cuda' whenever it is available, dgcnn.py:39)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--model", model, "--cpu-batch", str(clouds),
+           "--points", str(N), "--steps", "2", "--warmup", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        return line["cpu_baseline"]
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"[:300]}
 
 
 def run_reference(args):
@@ -171,33 +246,52 @@ def run_reference(args):
     if rank != 0:
         return
     on_gpu = args.ref_device == "cuda"
-    B = (args.batch or default_batch(args.model)) if on_gpu else args.cpu_batch
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    times, cores = cpu_reference_steps(args.model, B, args.points, steps, warmup, args.ref_device)
+    full = args.batch or default_batch(args.model)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    if on_gpu:
+        B = full
+        steps, warmup = min(steps, 5), min(warmup, 2)
+    elif args.cpu_batch:
+        B = args.cpu_batch
+    else:
+        B, _ = cpu_sample_batch(args.model, full, args.points, steps, warmup)
+    clocks = ClockSampler(0).start() if on_gpu else None
+    times, cores, kind = reference_steps(args.model, B, args.points, steps, warmup, args.ref_device)
+    clk = clocks.stop() if clocks else None
     ms = 1e3 * sum(times) / len(times)
     value = B * args.points / (ms / 1e3)
-    sample = (f"{steps} steps of {B} clouds x {args.points} pts (" + ("the full per-GPU batch on cuda:0, stock ATen kernels"
-              if on_gpu else "bounded sample of the per-GPU batch") + f"), {warmup} warm-up, mean")
+    what = ("the unmodified reference (oracle/_ref: verbatim copy of /root/reference's models/ + Training/)" if kind == "reference"
+            else "oracle port of the reference (oracle/ref_ops.py)")
+    sample = (f"{steps} steps of {B} clouds x {args.points} pts" + (" = the full per-GPU batch" if B == full else f" (bounded sample of the {full}-cloud batch)")
+              + f", {warmup} warm-up, mean; {what}; " + ("cuda:0, stock ATen / cuBLAS / cuDNN kernels, torch defaults" if on_gpu else f"{cores} host threads"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic S3DIS-shaped blocks, random-init weights",
-        "config": {"workload": workload_name(args.model, args.batch or default_batch(args.model), args.points),
-                   "reference_path": "oracle port of the reference's torch " + ("CUDA path (stock ATen / cuBLAS / cuDNN kernels, torch defaults)"
-                                     if on_gpu else "CPU path") + " (the Python reference does not travel to the GPU box)",
-                   "ref_device": args.ref_device},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic S3DIS-shaped blocks (SURVEY.md 8d generator), random-init weights",
+        "config": config_for(args.model, full, args.points, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "ref_device": args.ref_device,
     }
+    if clk:
+        line["clocks"] = clk
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------- our arm
+# --------------------------------------------------------------------------- roofline bookkeeping
 
 
 FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12                  # CUDA-core FMA peak of one B200 at the sustained SM clock
-TENSOR_KERNELS = {"knn_tc_kernel", "gemm3x_kernel"}          # tcgen05 kernels: roofline = tensor pipe (TF32); everything else moves bytes
+# tcgen05 kernels whose binding roofline can be the tensor pipe; gemm kernels are profiled per shape class ("[tensor]" = the
+# launch's 2MNK / tensor peak exceeds its bytes / HBM peak, "[hbm]" otherwise), so one model's wide layers and another
+# model's narrow layers are never averaged into one figure
+TENSOR_KERNELS = {"knn_tc_kernel", "gemm3x_kernel[tensor]", "gemm3x_kernel[hbm]", "gemm2h_kernel[tensor]", "gemm2h_kernel[hbm]"}
+# kernels whose stated flops are CUDA-core work (lane-ops / flops on the FP32 pipe): the roofline that can bind them
+# besides HBM is the FP32 issue rate.  FPS occupies one SM (or one cluster) per cloud: its stated work is already scaled
+# to the SMs it uses.
+ALU_KERNELS = {"fps_reg_kernel", "fps_big_kernel", "fps_cluster_kernel", "select_xyz_kernel<ball>", "select_xyz_kernel<knn>",
+               "knn_expand_kernel", "ball_grid_kernel", "knn3_grid_kernel"}
 
 
 def ncu_traffic(kernel):
@@ -206,13 +300,8 @@ def ncu_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
-    ent = json.load(open(p)).get(kernel)
-    return ent if ent else None
-
-
-# kernels whose stated flops are CUDA-core work (lane-ops / flops on the FP32 pipe): the roofline that can bind them
-# besides HBM is the FP32 issue rate.  FPS occupies one SM per cloud, so its ceiling is scaled by the SMs it uses.
-ALU_KERNELS = {"fps_reg_kernel", "fps_big_kernel", "select_xyz_kernel<ball>", "select_xyz_kernel<knn>", "knn_expand_kernel"}
+    table = json.load(open(p))
+    return table.get(kernel) or table.get(kernel.split("[")[0]) or None
 
 
 def kernel_bound(name, d, peaks):
@@ -222,7 +311,8 @@ def kernel_bound(name, d, peaks):
     sec = d["ms"] / 1e3
     t_hbm = d["bytes"] / (peaks["hbm_gbs"] * 1e9)
     if name in TENSOR_KERNELS:
-        t_fl, fl_unit, fl_peak, fl_name = d["flops"] / (peaks["tf32_tflops"] * 1e12), "TFLOP/s", peaks["tf32_tflops"], "tensor"
+        pk = peaks["f16_tflops"] if name.startswith("gemm2h") else peaks["tf32_tflops"]
+        t_fl, fl_unit, fl_peak, fl_name = d["flops"] / (pk * 1e12), "TFLOP/s", pk, "tensor"
     elif name in ALU_KERNELS:
         t_fl, fl_unit, fl_peak, fl_name = d["flops"] / (peaks["fp32_tflops"] * 1e12), "TFLOP/s", peaks["fp32_tflops"], "alu"
     else:
@@ -235,23 +325,23 @@ def kernel_bound(name, d, peaks):
 
 
 def roofline_for(kernels, peaks):
-    """Dominant libpcnbr KERNEL of the profiled steps against the roofline that bounds it.
+    """Dominant libpcnbr KERNEL (per shape class) of the profiled steps against the roofline that bounds it.
     `achieved` = algorithmic bytes (or flops) of its launches, as stated by the launch sites from the SURVEY.md 8d
     formulas, / their summed duration (CUDA events on the launch stream, csrc/prof.cu)."""
     if not kernels:
         return None
     name, d = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     b = kernel_bound(name, d, peaks)
+    t = ncu_traffic(name) or {}
     out = {"kernel": name, "bound": b["bound"], "achieved": b["achieved"], "peak": b["peak"], "unit": b["unit"], "frac": b["frac"],
-           "traffic": (ncu_traffic(name) or {}).get("dram_bytes_per_launch"),
-           "traffic_shape": (ncu_traffic(name) or {}).get("shape"),
-           "traffic_algorithmic_bytes_same_shape": (ncu_traffic(name) or {}).get("algorithmic_bytes_same_shape"),
+           "traffic": t.get("dram_bytes_per_launch"), "traffic_shape": t.get("shape"),
+           "traffic_algorithmic_bytes_same_shape": t.get("algorithmic_bytes_same_shape"),
            "avg_launch_ms": d["ms"] / d["calls"], "calls": d["calls"], "peak_source": peaks["source"],
            "algorithmic_per_launch": b["algorithmic"] / d["calls"]}
-    if name == "gemm3x_kernel" and b["bound"] == "tensor":
-        # fp32-grade accuracy costs three TF32 instructions per algorithmic flop: the kernel's own ceiling is peak / 3
+    if name.startswith("gemm") and b["bound"] == "tensor":
+        out["issued_per_algorithmic_flop"] = 3.0          # hi.hi' + lo.hi' + hi.lo': three tensor instructions per product
         out["issued_frac"] = 3.0 * b["frac"]
-    out["note"] = ("flops counted once (2 M N K per GEMM, 2 N^2 F per kNN cloud), whatever the 3xTF32 kernel issues" if b["bound"] == "tensor" else
+    out["note"] = ("flops counted once (2 M N K per GEMM, 2 N^2 F per kNN cloud), whatever the split kernel issues" if b["bound"] == "tensor" else
                    "algorithmic (compulsory) bytes; gathers that hit L2 are not counted" if b["bound"] == "hbm" else
                    "algorithmic lane-ops / flops on the FP32 pipe")
     return out
@@ -261,147 +351,197 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "tf32_tflops": d["bf16_tflops_sustained"] / 2, "fp32_tflops": FP32_TFLOPS,
-                "source": "MEASURED_PEAKS.json (tf32 = sustained bf16 / 2; fp32 = 148 SMs x 128 lanes x 2 x 1.965 GHz)"}
-    return {"hbm_gbs": 6650.0, "tf32_tflops": 700.0, "fp32_tflops": FP32_TFLOPS, "source": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "tf32_tflops": d["bf16_tflops_sustained"] / 2, "f16_tflops": d["bf16_tflops_sustained"],
+                "fp32_tflops": FP32_TFLOPS,
+                "source": "MEASURED_PEAKS.json (f16 = sustained bf16; tf32 = sustained bf16 / 2; fp32 = 148 SMs x 128 lanes x 2 x 1.965 GHz)"}
+    return {"hbm_gbs": 6650.0, "tf32_tflops": 700.0, "f16_tflops": 1400.0, "fp32_tflops": FP32_TFLOPS, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------- our arm
+
+
+class Harness:
+    """Process-wide state of our arm: device, ranks, package."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        import __graft_entry__ as ge
+        self.args, self.dist = args, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version / debug lines off stdout (one JSON line)
+            dist.init_process_group("nccl", device_id=self.dev)
+        torch.backends.cuda.matmul.allow_tf32 = False       # strict fp32, as the north-star parity bar
+        torch.backends.cudnn.allow_tf32 = False
+        self.pkg = ge.load_package()
+        self.pkg._lib.load()
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(self, model, B, N, steps, warmup, profile=True, cpu_baseline=False):
+        """Train-step throughput of `model` at B clouds per GPU: device-resident (`value`) and end to end from pinned host
+        batches (`e2e`), clocks sampled over both timed regions, then the per-kernel map from eager profiled steps."""
+        args, pkg, dev, world, rank = self.args, self.pkg, self.dev, self.world, self.rank
+        torch.manual_seed(0)
+        net = build_model(pkg, model).to(dev)
+        pkg.train.broadcast_parameters(net)
+        bucket = pkg.train.FlatGradBucket(net, steal_grads=True)
+        # torch's fused Adam: one multi-tensor kernel per step (same update rule as the reference's Adam(lr=1e-3))
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
+        n_batches = 4                                        # rotate inputs; activations (GBs) >> L2 anyway
+        host, devb = [], []
+        for i in range(n_batches):
+            pts, lab, lens = pkg.synthetic.s3dis_blocks(B, N, seed=1000 * rank + i, classes=N_CLASSES)
+            host.append((pts.pin_memory(), lab.pin_memory(), lens.pin_memory()))
+            devb.append((pts.to(dev), lab.to(dev), lens.to(dev)))
+
+        def loss_of(m, pts, lab, lens):
+            return pkg.train.masked_onehot_cross_entropy(logits_of(m(model_input(model, pts))), lab, lens)
+
+        def eager_step(pts, lab, lens):
+            bucket.zero()
+            loss = loss_of(net, pts, lab, lens)
+            loss.backward()
+            pkg.ops.join_aux()
+            bucket.all_reduce_mean()
+            opt.step()
+            return loss
+
+        pkg.ops.reset_fallbacks()
+        for i in range(max(warmup, 3)):
+            eager_step(*devb[i % n_batches])
+        step = eager_step if args.no_graph else pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, devb[0], warmup=2)
+
+        def timed(region_steps, from_host):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.barrier()
+            ev0.record()
+            last = None
+            for i in range(region_steps):
+                if from_host:
+                    hp, hl, hn = host[i % n_batches]         # pinned host batch -> H2D copies inside the timed region
+                    if args.no_graph:
+                        hp, hl, hn = hp.to(dev, non_blocking=True), hl.to(dev, non_blocking=True), hn.to(dev, non_blocking=True)
+                    last = step(hp, hl, hn).item()           # (graph: copied straight into the static inputs); D2H loss read
+                else:
+                    last = step(*devb[i % n_batches])
+            ev1.record()
+            self.barrier()
+            ms = ev0.elapsed_time(ev1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+                ms = t.item()
+            return ms, last
+
+        for i in range(max(warmup, 3)):
+            step(*devb[i % n_batches])
+        clocks = ClockSampler(self.local).start() if rank == 0 else None
+        ms_total, _ = timed(steps, from_host=False)
+        ms_e2e, last_loss = timed(steps, from_host=True)
+        clk = clocks.stop() if clocks else None
+        out = {"ms_per_step": ms_total / steps, "value": B * N * world * steps / (ms_total / 1e3),
+               "e2e": {"value": B * N * world * steps / (ms_e2e / 1e3), "unit": UNIT,
+                       "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]), "d2h_bytes_per_step": 4,
+                       "ms_per_step": ms_e2e / steps, "loss": last_loss},
+               "clocks": clk, "library_fallbacks": pkg.ops.fallbacks()}
+        if profile:
+            # per-kernel durations: the same kernels launched eagerly with CUDA events around every libpcnbr kernel
+            # (events cannot be recorded inside a graph replay); also counts the libpcnbr launches of one step
+            prof_steps = 3
+            pkg._lib.prof_enable(True)
+            for i in range(prof_steps):
+                eager_step(*devb[i % n_batches])
+            kernels = pkg._lib.prof_collect()
+            pkg._lib.prof_enable(False)
+            out["gpu_launches"] = sum(d["calls"] for d in kernels.values()) // prof_steps * steps
+            out["roofline"] = roofline_for(kernels, self.peaks)
+            order = sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])
+            out["kernel_ms_per_step"] = {k: round(v["ms"] / prof_steps, 4) for k, v in order}
+            out["kernel_roofline_frac"] = {k: [kernel_bound(k, v, self.peaks)["bound"], round(kernel_bound(k, v, self.peaks)["frac"], 4)] for k, v in order}
+        if cpu_baseline and rank == 0 and world == 1:
+            out["cpu_baseline"] = cpu_baseline_subprocess(model, args.cpu_batch or 2, N)
+        if world > 1 and not args.no_graph:
+            del step                                         # a captured graph holds NCCL work: drop it before the next capture
+        del net, opt, bucket
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return out
+
+    def reference_on_gpu(self, model, B, N):
+        """SURVEY 8d 'also time': the unmodified reference's own train step on this B200 (stock ATen / cuBLAS / cuDNN
+        kernels, torch defaults as train.py), full per-GPU batch, wall clock around synchronised steps."""
+        tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = False, True      # torch's defaults
+        try:
+            clocks = ClockSampler(self.local).start()
+            times, _, kind = reference_steps(model, B, N, 3, 2, device=str(self.dev))
+            clk = clocks.stop()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+        ms = 1e3 * sum(times) / len(times)
+        return {"ms_per_step": ms, "value": B * N / (ms / 1e3), "unit": UNIT, "kind": kind, "steps": 3, "warmup": 2,
+                "batch": B, "clocks": clk, "timing": "wall clock around device-synchronised steps (the reference syncs per FPS pick itself)"}
 
 
 def run_ours(args):
-    import torch.distributed as dist
-    import __graft_entry__ as ge
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version / debug lines off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
-    torch.backends.cuda.matmul.allow_tf32 = False       # strict fp32, as the north-star parity bar
-    torch.backends.cudnn.allow_tf32 = False
-
-    pkg = ge.load_package()
-    pkg._lib.load()
-    s3dis_blocks = pkg.synthetic.s3dis_blocks
-    B = args.batch or default_batch(args.model)
+    h = Harness(args)
+    world, rank = h.world, h.rank
     N = args.points
-    torch.manual_seed(0)
-    net = build_model(pkg, args.model).to(dev)
-    pkg.train.broadcast_parameters(net)
-    bucket = pkg.train.FlatGradBucket(net, steal_grads=True)
-    # torch's fused Adam: one multi-tensor kernel per step instead of ~8 (same update rule as the reference's Adam(lr=1e-3))
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
-
-    n_batches = 4                                        # rotate inputs; activations (GBs) >> L2 anyway
-    host, devb = [], []
-    for i in range(n_batches):
-        pts, lab, lens = s3dis_blocks(B, N, seed=1000 * rank + i, classes=N_CLASSES)
-        host.append((pts.pin_memory(), lab.pin_memory(), lens.pin_memory()))
-        devb.append((pts.to(dev), lab.to(dev), lens.to(dev)))
-
-    def loss_of(model, pts, lab, lens):
-        return pkg.train.masked_onehot_cross_entropy(logits_of(model(model_input(args.model, pts))), lab, lens)
-
-    def eager_step(pts, lab, lens):
-        bucket.zero()
-        loss = loss_of(net, pts, lab, lens)
-        loss.backward()
-        pkg.ops.join_aux()
-        bucket.all_reduce_mean()
-        opt.step()
-        return loss
-
-    for i in range(args.warmup):
-        eager_step(*devb[i % n_batches])
-    step = eager_step if args.no_graph else pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, devb[0], warmup=2)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(region_steps, from_host):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        last = None
-        for i in range(region_steps):
-            if from_host:
-                hp, hl, hn = host[i % n_batches]         # pinned host batch -> H2D copies inside the timed region
-                if args.no_graph:
-                    hp, hl, hn = hp.to(dev, non_blocking=True), hl.to(dev, non_blocking=True), hn.to(dev, non_blocking=True)
-                last = step(hp, hl, hn).item()           # (graph: copied straight into the static inputs); D2H loss read
-            else:
-                last = step(*devb[i % n_batches])
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, last
-
-    for i in range(args.warmup):
-        step(*devb[i % n_batches])
-    clocks = ClockSampler(local)
+    full = args.batch or default_batch(args.model)
+    strong = args.scaling == "strong"
+    B = max(1, full // world) if strong else full
+    extras = (not args.no_extras) and args.model == "dgcnn" and not args.batch and N == N_POINTS and not strong
+    main = h.measure(args.model, B, N, args.steps, args.warmup, profile=True, cpu_baseline=not args.no_cpu_baseline)
+    line = {
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic S3DIS-shaped blocks (SURVEY.md 8d generator), random-init weights",
+        "config": config_for(args.model, B, N, world),
+        "e2e": main["e2e"], "gpu_launches": main.get("gpu_launches"), "clocks": main["clocks"], "roofline": main.get("roofline"),
+        "cpu_baseline": main.get("cpu_baseline"), "kernel_ms_per_step": main.get("kernel_ms_per_step"),
+        "kernel_roofline_frac": main.get("kernel_roofline_frac"), "library_fallbacks": main["library_fallbacks"],
+        "launch_mode": "eager" if args.no_graph else "whole train step captured in one CUDA graph, replayed per batch",
+    }
+    if extras:
+        pb = default_batch("pointnetpp")
+        pn = h.measure("pointnetpp", pb, N, args.steps, args.warmup, profile=True)
+        pn["config"] = config_for("pointnetpp", pb, N, world)
+        pn["unit"] = UNIT
+        line["pointnetpp"] = pn
+        if world == 1:
+            try:
+                line["reference_gpu"] = {"dgcnn": h.reference_on_gpu("dgcnn", full, N), "pointnetpp": h.reference_on_gpu("pointnetpp", pb, N)}
+            except Exception as e:                           # never lose the headline line to the side measurement
+                line["reference_gpu"] = {"error": repr(e)[:300]}
+        else:
+            st = {}
+            for m in ("dgcnn", "pointnetpp"):
+                g = default_batch(m)
+                if g % world:
+                    continue
+                r = h.measure(m, g // world, N, args.steps, args.warmup, profile=False)
+                st[m] = {"global_batch": g, "clouds_per_gpu": g // world, "ms_per_step": r["ms_per_step"], "value": r["value"],
+                         "e2e": r["e2e"], "unit": UNIT, "clocks": r["clocks"]}
+            line["strong"] = st
     if rank == 0:
-        clocks.start()
-    ms_total, _ = timed(args.steps, from_host=False)
-    ms_e2e, last_loss = timed(args.steps, from_host=True)
-    clk = clocks.stop() if rank == 0 else None
-    # per-kernel durations: the same kernels launched eagerly with CUDA events around every libpcnbr call
-    # (events cannot be recorded inside a graph replay); also counts the libpcnbr launches of one step
-    prof_steps = 3
-    pkg._lib.prof_enable(True)
-    for i in range(prof_steps):
-        eager_step(*devb[i % n_batches])
-    kernels = pkg._lib.prof_collect()
-    pkg._lib.prof_enable(False)
-    launches = sum(d["calls"] for d in kernels.values()) // prof_steps * args.steps
-
-    pts_per_step = B * N * world
-    value = pts_per_step * args.steps / (ms_total / 1e3)
-    e2e = pts_per_step * args.steps / (ms_e2e / 1e3)
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
-    peaks = load_peaks()
-
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, cores = cpu_reference_steps(args.model, args.cpu_batch, N, 2, 1)
-        cms = sum(times) / len(times)
-        cpu_base = {"value": args.cpu_batch * N / cms, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"2 steps of {args.cpu_batch} clouds x {N} pts (oracle port of the reference's torch CPU path), 1 warm-up, mean"}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic S3DIS-shaped blocks (SURVEY.md 8d generator), random-init weights",
-            "config": {"workload": workload_name(args.model, B, N), "global_batch": B * world, "parallelism": f"dp{world}",
-                       "precision": "strict fp32 (TF32 disabled for cuBLAS and cuDNN)",
-                       "l2": "no explicit flush: per-step activations (GBs) far exceed the 126 MB L2; 4 input batches rotate"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                    "loss": last_loss},
-            "gpu_launches": launches,
-            "clocks": clk,
-            "roofline": roofline_for(kernels, peaks),
-            "cpu_baseline": cpu_base,
-            "kernel_ms_per_step": {k: round(v["ms"] / prof_steps, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
-            "kernel_roofline_frac": {k: [kernel_bound(k, v, peaks)["bound"], round(kernel_bound(k, v, peaks)["frac"], 4)]
-                                     for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
-            "launch_mode": "eager" if args.no_graph else "whole train step captured in one CUDA graph, replayed per batch",
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
-        # a captured graph holds NCCL work: tear down in order (graph, then a device sync, then the group) and
-        # leave without the interpreter's atexit pass, which can block on the communicator
-        del step
+        # captured graphs held NCCL work: tear down in order (device sync, then the group) and leave without the
+        # interpreter's atexit pass, which can block on the communicator
         torch.cuda.synchronize()
-        dist.barrier()
+        h.dist.barrier()
         sys.stdout.flush()
         os._exit(0)
 
