@@ -14,7 +14,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out, steal=False):
+def _worker(rank, world, port, out, steal=False, overlap=True):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -25,14 +25,22 @@ def _worker(rank, world, port, out, steal=False):
     torch.manual_seed(100 + rank)                      # different init per rank on purpose
     net = torch.nn.Sequential(torch.nn.Linear(9, 16), torch.nn.ReLU(), torch.nn.Linear(16, 13))
     pkg.train.broadcast_parameters(net)                # -> rank 0's parameters everywhere
-    bucket = pkg.train.FlatGradBucket(net, steal_grads=steal)
+    bucket = pkg.train.FlatGradBucket(net, steal_grads=steal, overlap=overlap, late_fraction=0.5)
+    assert bucket.overlap == overlap and (bucket.split == 2 if overlap else bucket.split == 0)     # late part = the first Linear
     pts, lab, lens = pkg.synthetic.s3dis_blocks(4, 64, seed=0)
     sl = pkg.train.shard_batch(4, rank, world)
     bucket.zero()
     loss = pkg.train.masked_onehot_cross_entropy(net(pts[sl]), lab[sl], lens[sl])
     loss.backward()
+    assert (bucket._pending is not None) == overlap    # the head's all-reduce was started from the backward hook
     bucket.all_reduce_mean()
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))   # grads live in the bucket
+    # a second step through the same bucket (hooks re-arm, views are reused)
+    first = bucket.flat.clone()
+    bucket.zero()
+    pkg.train.masked_onehot_cross_entropy(net(pts[sl]), lab[sl], lens[sl]).backward()
+    bucket.all_reduce_mean()
+    assert torch.allclose(bucket.flat, first, rtol=1e-6, atol=1e-8)
     out[rank] = (bucket.flat.clone(), torch.cat([p.detach().flatten() for p in net.parameters()]), (sl.start, sl.stop))
     dist.destroy_process_group()
 
@@ -40,12 +48,12 @@ def _worker(rank, world, port, out, steal=False):
 import pytest
 
 
-@pytest.mark.parametrize("steal", [False, True])
-def test_flat_bucket_allreduce_matches_full_batch(pkg, steal):
+@pytest.mark.parametrize("steal,overlap", [(False, True), (True, True), (True, False)])
+def test_flat_bucket_allreduce_matches_full_batch(pkg, steal, overlap):
     world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out, steal), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), out, steal, overlap), nprocs=world, join=True)
         res = dict(out)
     g0, p0, s0 = res[0]
     g1, p1, s1 = res[1]

@@ -94,7 +94,7 @@ def test_unmodified_reference_train_loop_runs_on_the_shims(reference_tree, pkg, 
     assert os.path.realpath(shim_common.__file__).startswith(os.path.realpath(DROPIN))
     assert shim_common.SetAbstraction is pkg.common.SetAbstraction
 
-    _write_blocks(str(tmp_path), areas=(1, 2, 6), n_blocks=6, seed=1)
+    _write_blocks(str(tmp_path), areas=(1, 2, 3, 4, 5, 6), n_blocks=3, seed=1)     # 15 train blocks -> 2 batches of 8 / 7
     train_loader, test_loader = create_block_dataloaders(
         data_dir=str(tmp_path), test_areas={6}, train_batch_size=8, test_batch_size=2, num_workers=2,
         train_sampling=4096, test_sampling=None, train_shuffle=True, test_shuffle=False)          # train.py:64-74

@@ -210,10 +210,20 @@ def test_invresmlp_golden_output_and_gradients(pkg, dev, golden):
     _close(fd.grad, g["grad_features"])
     params = dict(blk.named_parameters())
     assert set(params) == set(g["grads"])
+    # float64 twin of the oracle: tells which gradients are STRUCTURALLY zero here (a conv bias in front of a training-mode
+    # BatchNorm; the pooled BatchNorm's beta when every pooled pre-activation is positive: a per-channel shift that the
+    # next BatchNorm removes).  For those any fp32 evaluation returns summation noise (the reference: 4e-5 .. 5e-4); they
+    # are bounded by 1e-4 of the largest gradient of the same kind (weights / biases).
+    torch.manual_seed(g["seed"])
+    twin = O.InvResMLP(g["radius"], g["cin"], g["width"], g["K"], tie="canon").double()
+    f64 = f.double().requires_grad_(True)
+    (twin(pc.double(), pc.double(), f64)[1] * w.double()).sum().backward()
+    g64 = {k: p.grad for k, p in twin.named_parameters()}
+    kind_max = {kind: max(v.abs().max().item() for k, v in g["grads"].items() if k.endswith(kind)) for kind in ("weight", "bias")}
     for k, v in g["grads"].items():
-        if k.endswith("conv.0.bias") or k.endswith("conv.1.bias"):
-            # a conv bias in front of a training-mode BatchNorm: the exact gradient is 0 (the reference returns fp32 noise)
-            assert params[k].grad.abs().max().item() <= 1e-4 * max(1.0, v.abs().max().item()) + v.abs().max().item()
+        kmax = kind_max["weight" if k.endswith("weight") else "bias"]
+        if g64[k].abs().max().item() < 1e-6 * kmax:
+            assert params[k].grad.abs().max().item() <= 1e-4 * kmax, k
             continue
         _close(params[k].grad, v, rtol=1e-3, scale_atol=2e-4)
 
