@@ -32,6 +32,8 @@ PROTOTYPES = {
     "pcnbr_group_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "pcnbr_csr_ws_bytes": (_Z, [_I, _I, _I]),
     "pcnbr_csr_build": (_I, [_P, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "pcnbr_csr_rows_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "pcnbr_csr_build_rows": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "pcnbr_group_bwd_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P, _P]),
     "pcnbr_maxpool_f32": (_I, [_P, _L, _I, _I, _L, _L, _L, _P, _P, _P]),
     "pcnbr_maxpool_bwd_f32": (_I, [_P, _P, _L, _I, _I, _L, _L, _L, _P, _P]),
@@ -66,7 +68,7 @@ PROTOTYPES = {
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
-KERNELS_PER_CALL = {"pcnbr_ball_query_multi_f32": 2, "pcnbr_masked_ce_f32": 2, "pcnbr_csr_build": 4, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_tc_debug_f32": 5}
+KERNELS_PER_CALL = {"pcnbr_ball_query_multi_f32": 2, "pcnbr_masked_ce_f32": 2, "pcnbr_csr_build": 4, "pcnbr_csr_build_rows": 3, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_tc_debug_f32": 5}
 
 _lib = None
 launches = 0          # number of libpcnbr CUDA kernels launched by this process (bench.py reports it)

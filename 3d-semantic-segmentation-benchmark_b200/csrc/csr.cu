@@ -242,6 +242,151 @@ csr_place_kernel(const int32_t* __restrict__ idx, int E, int N, int P, const uin
     }
 }
 
+
+// ------------------------------------------------------------------------------------ bitmap transposition (row-structured tables)
+// A neighbour table is a sparse (M queries x N sources) matrix with K entries per row; its CSR-by-source inverse with
+// ascending positions is the TRANSPOSE with sorted columns.  Sorted order falls out for free from a bitmap: bit (s, m)
+// of a (N x M)-bit matrix says "row m references source s".
+//   csr_mark_kernel : one thread per table entry: cnt[s] += 1, bm[s][m] |= 1 (integer atomics: order-independent results)
+//   csr_scan1_kernel: exclusive scan of the counts -> offsets                     (one CTA per cloud, one pass)
+//   csr_emit_kernel : one warp per source s walks its M bits in ascending m; for every set bit it re-reads row m of the
+//                     table (K entries, one or a few 16-byte loads) and emits the matching position(s) m*K + r.
+// No sort, no per-range count matrix, every SM busy (the old stable counting sort walked 2048-position ranges with one
+// warp each: a serial chain of exposed global-load latencies, 0.68 ms per DGCNN step on 10-16 CTAs).  Rows that hold the
+// same source twice (possible only in caller-made tables; kNN / ball-query rows are distinct) are flagged by the mark
+// kernel; the emit kernel then counts matches per bit before placing them.
+constexpr size_t CSR_BITMAP_BUDGET = (size_t)512 << 20;       // bytes of bitmap the workspace may take
+
+__global__ void __launch_bounds__(256)
+csr_mark_kernel(const int32_t* __restrict__ idx, int M, int K, int N, int W, int32_t* __restrict__ cnt,
+                uint32_t* __restrict__ bm, int32_t* __restrict__ dupflag) {
+    const int b = blockIdx.y;
+    const long E = (long)M * K;
+    const int32_t* __restrict__ ib = idx + (size_t)b * E;
+    bool any_dup = false;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(e / K), r = (int)(e - (long)m * K);
+        const int s = ib[e];
+        if ((unsigned)s >= (unsigned)N) continue;                       // out-of-range entries are ignored, never dereferenced
+        bool dup = false;
+        for (int r2 = 0; r2 < r; ++r2) dup |= (ib[(long)m * K + r2] == s);           // the row is L1-resident
+        atomicAdd(&cnt[(size_t)b * (N + 1) + s], 1);
+        if (!dup) atomicOr(&bm[((size_t)b * N + s) * W + (m >> 5)], 1u << (m & 31));
+        any_dup |= dup;
+    }
+    if (__any_sync(PCNBR_FULL, any_dup) && (threadIdx.x & 31) == 0) atomicOr(&dupflag[b], 1);
+}
+
+// offsets[b, 0..N] = exclusive scan of cnt[b, 0..N-1]: 1024 threads x ITEMS contiguous counts each, one pass
+__global__ void __launch_bounds__(1024)
+csr_scan1_kernel(const int32_t* __restrict__ cnt, int N, int32_t* __restrict__ offsets) {
+    __shared__ int s_warp[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* __restrict__ c = cnt + (size_t)b * (N + 1);
+    int32_t* __restrict__ o = offsets + (size_t)b * (N + 1);
+    const int items = (N + 1 + 1023) / 1024;
+    const int i0 = tid * items, i1 = min(N + 1, i0 + items);
+    int sum = 0;
+    for (int i = i0; i < i1; ++i) sum += (i < N) ? c[i] : 0;
+    int x = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(PCNBR_FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(PCNBR_FULL, w, d);
+            if (lane >= d) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int run = (warp ? s_warp[warp - 1] : 0) + x - sum;
+    for (int i = i0; i < i1; ++i) {
+        o[i] = run;
+        run += (i < N) ? c[i] : 0;
+    }
+}
+
+// number of entries of table row `row` (K ints) equal to s; the first match position goes to r_first
+__device__ __forceinline__ int csr_row_matches(const int32_t* __restrict__ row, int K, int s, int& r_first) {
+    int n = 0;
+    r_first = -1;
+    if ((K & 3) == 0) {
+        const int4* __restrict__ v = reinterpret_cast<const int4*>(row);
+#pragma unroll 4
+        for (int q = 0; q < K / 4; ++q) {
+            const int4 t = v[q];
+            if (t.x == s) { if (!n) r_first = 4 * q; ++n; }
+            if (t.y == s) { if (!n) r_first = 4 * q + 1; ++n; }
+            if (t.z == s) { if (!n) r_first = 4 * q + 2; ++n; }
+            if (t.w == s) { if (!n) r_first = 4 * q + 3; ++n; }
+        }
+    } else {
+        for (int r = 0; r < K; ++r)
+            if (row[r] == s) { if (!n) r_first = r; ++n; }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256)
+csr_emit_kernel(const int32_t* __restrict__ idx, int M, int K, int N, int W, const int32_t* __restrict__ offsets,
+                const uint32_t* __restrict__ bm, const int32_t* __restrict__ dupflag, int32_t* __restrict__ perm) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long E = (long)M * K;
+    const int32_t* __restrict__ ib = idx + (size_t)b * E;
+    int32_t* __restrict__ pm = perm + (size_t)b * E;
+    const int32_t* __restrict__ off = offsets + (size_t)b * (N + 1);
+    const bool multi = dupflag[b] != 0;
+    for (int s = blockIdx.x * 8 + warp; s < N; s += gridDim.x * 8) {
+        int out = off[s];
+        if (off[s + 1] == out) continue;
+        const uint32_t* __restrict__ bits_row = bm + ((size_t)b * N + s) * W;
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const uint32_t word = (w0 + lane < W) ? bits_row[w0 + lane] : 0u;
+            if (!__any_sync(PCNBR_FULL, word != 0u)) continue;
+            int c = __popc(word);
+            if (multi) {                                               // rows may hold s more than once: count first
+                c = 0;
+                uint32_t bits = word;
+                while (bits) {
+                    const int m = ((w0 + lane) << 5) + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    int rf;
+                    c += csr_row_matches(ib + (long)m * K, K, s, rf);
+                }
+            }
+            int x = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(PCNBR_FULL, x, d);
+                if (lane >= d) x += y;
+            }
+            int base = out + x - c;
+            out += __shfl_sync(PCNBR_FULL, x, 31);
+            uint32_t bits = word;
+            while (bits) {
+                const int m = ((w0 + lane) << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int32_t* __restrict__ row = ib + (long)m * K;
+                if (!multi) {
+                    int rf;
+                    csr_row_matches(row, K, s, rf);
+                    pm[base++] = m * K + rf;
+                } else {
+                    for (int r = 0; r < K; ++r)
+                        if (row[r] == s) pm[base++] = m * K + r;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace pcnbr
 
 using namespace pcnbr;
@@ -307,6 +452,50 @@ extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t*
     }
     PCNBR_TIMED("csr_sort_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0,
                 (csr_sort_kernel<<<dim3(gs, B), 256, bm_bytes, s>>>(offsets, tmp, E, N, perm, use_bitmap)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+
+static bool csr_rows_use_bitmap(int B, int M, int N) {
+    const size_t W = ((size_t)M + 31) / 32;
+    return (size_t)B * N * W * 4 <= CSR_BITMAP_BUDGET;
+}
+
+extern "C" size_t pcnbr_csr_rows_ws_bytes(int B, int M, int K, int N) {
+    const long E = (long)M * K;
+    if (E > 0x7fffffffL) return 0;
+    if (!csr_rows_use_bitmap(B, M, N)) return pcnbr_csr_ws_bytes(B, (int)E, N);
+    const size_t W = ((size_t)M + 31) / 32;
+    // cnt (B,N+1) + duplicate flags (B, padded to 64 words) + bitmap (B,N,W)
+    return sizeof(int32_t) * ((size_t)B * (N + 1) + (size_t)((B + 63) / 64 * 64) + (size_t)B * N * W);
+}
+
+// Inverse of a row-structured table idx (B,M,K) into N sources: same result as pcnbr_csr_build(idx, B, M*K, N, ...).
+extern "C" int pcnbr_csr_build_rows(const int32_t* idx, int B, int M, int K, int N, int32_t* offsets, int32_t* perm,
+                                    void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (!idx || !offsets || !perm || B <= 0 || M <= 0 || K <= 0 || N <= 0) return PCNBR_E_BADARG;
+    const long E = (long)M * K;
+    if (E > 0x7fffffffL) return PCNBR_E_TOOLARGE;
+    if (!ws || ws_bytes < pcnbr_csr_rows_ws_bytes(B, M, K, N)) return PCNBR_E_WORKSPACE;
+    if (!csr_rows_use_bitmap(B, M, N)) return pcnbr_csr_build(idx, B, (int)E, N, offsets, perm, ws, ws_bytes, stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int W = (M + 31) / 32;
+    int32_t* cnt = (int32_t*)ws;
+    int32_t* dup = cnt + (size_t)B * (N + 1);
+    uint32_t* bm = (uint32_t*)(dup + (size_t)((B + 63) / 64 * 64));
+    cudaError_t e = cudaMemsetAsync(ws, 0, pcnbr_csr_rows_ws_bytes(B, M, K, N), s);
+    if (e != cudaSuccess) return (int)e;
+    const int gx = (int)((E + 255) / 256 < 2368 ? (E + 255) / 256 : 2368);
+    // algorithmic bytes: the table (4E) is read by mark and emit, perm (4E) and offsets are written; the bitmap is scratch
+    PCNBR_TIMED("csr_mark_kernel", s, (double)B * (4.0 * E + 4.0 * N), 0.0,
+                (csr_mark_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, M, K, N, W, cnt, bm, dup)));
+    PCNBR_CHECK_LAUNCH();
+    PCNBR_TIMED("csr_scan1_kernel", s, (double)B * 8.0 * N, 0.0, (csr_scan1_kernel<<<B, 1024, 0, s>>>(cnt, N, offsets)));
+    PCNBR_CHECK_LAUNCH();
+    const int gs = (N + 7) / 8 < 2368 ? (N + 7) / 8 : 2368;
+    PCNBR_TIMED("csr_emit_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0,
+                (csr_emit_kernel<<<dim3(gs, B), 256, 0, s>>>(idx, M, K, N, W, offsets, bm, dup, perm)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -147,6 +147,13 @@ class NeighborIndex:
         dev = self.idx.device
         offsets = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
         perm = torch.empty(B, E, dtype=torch.int32, device=dev)
+        if self.idx.dim() == 3:                       # (B,M,K): bitmap transposition, no sort pass (csrc/csr.cu)
+            M, K = self.idx.shape[1], self.idx.shape[2]
+            nb = _lib.size("pcnbr_csr_rows_ws_bytes", B, M, K, N)
+            ws = _ws(nb, dev)
+            _lib.call("pcnbr_csr_build_rows", self.idx.data_ptr(), B, M, K, N, offsets.data_ptr(), perm.data_ptr(),
+                      ws.data_ptr(), nb, stream_handle)
+            return offsets, perm, ws
         nb = _lib.size("pcnbr_csr_ws_bytes", B, E, N)
         ws = _ws(nb, dev)
         _lib.call("pcnbr_csr_build", self.idx.data_ptr(), B, E, N, offsets.data_ptr(), perm.data_ptr(),

@@ -108,6 +108,13 @@ PCNBR_API int pcnbr_group_f32(const float* p, const float* feat, const float* q,
 PCNBR_API size_t pcnbr_csr_ws_bytes(int B, int E, int N);
 PCNBR_API int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t* offsets, int32_t* perm,
                     void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+/* The same inverse for a row-structured table idx (B,M,K) (every neighbour table of the path: E = M*K): built by bitmap
+ * transposition -- mark (source, row) bits, scan the counts, emit every source's rows in ascending order -- with no sort
+ * pass; rows may hold a source more than once.  Falls back to pcnbr_csr_build when the (N x M)-bit matrices would not fit
+ * the workspace budget.  ws: pcnbr_csr_rows_ws_bytes(B,M,K,N). */
+PCNBR_API size_t pcnbr_csr_rows_ws_bytes(int B, int M, int K, int N);
+PCNBR_API int pcnbr_csr_build_rows(const int32_t* idx, int B, int M, int K, int N, int32_t* offsets, int32_t* perm,
+                    void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
 /* Backward of K5 w.r.t. feat (autograd IndexBackward of common.py:65):
  * gout (B,M,K,*) with row pitch ldg >= 3+D -> gfeat (B,N,D) = sum over incoming (m,k) of gout[..., 3:3+D], fixed order. */

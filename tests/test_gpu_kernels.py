@@ -157,6 +157,50 @@ def test_csr_is_sorted_inverse(pkg, dev):
         assert torch.equal(offsets[b, 1:].long(), torch.cumsum(counts, 0)) and offsets[b, 0] == 0
 
 
+def _check_csr(idx, N, offsets, perm):
+    B = idx.shape[0]
+    flat = idx.reshape(B, -1)
+    for b in range(B):
+        order = torch.sort(flat[b].long(), stable=True).indices.int()    # ascending (source, position)
+        assert torch.equal(perm[b], order)
+        counts = torch.bincount(flat[b].long(), minlength=N)
+        assert torch.equal(offsets[b, 1:].long(), torch.cumsum(counts, 0)) and offsets[b, 0] == 0
+
+
+@pytest.mark.parametrize("kind,B,N,M,K", [("knn", 2, 4096, 4096, 20), ("ball", 3, 4096, 1024, 32), ("nn3", 2, 1024, 4096, 3),
+                                          ("knn", 2, 1000, 1000, 33), ("ball", 2, 777, 45, 16), ("rand", 2, 50, 1000, 7),
+                                          ("knn", 1, 12345, 12345, 16)])
+def test_csr_bitmap_transposition_all_table_kinds(pkg, dev, kind, B, N, M, K):
+    """pcnbr_csr_build_rows (mark / scan / emit, csrc/csr.cu) == stable sort of the flattened table, for distinct-row
+    tables (kNN, 3-NN), hub-heavy padded ball tables and caller-made tables with repeated sources inside a row; the flat
+    entry point pcnbr_csr_build must give the same inverse."""
+    g = _gen(N + M + K)
+    if kind == "knn" or kind == "nn3":           # distinct sources per row, a few popular hubs
+        score = torch.rand(B, M, N, generator=g)
+        score[:, :, : max(1, N // 100)] += 0.5
+        idx = score.topk(K, dim=2).indices.int()
+    elif kind == "ball":                           # under-filled balls: a handful of in-ball points, then 0,1,2,... padding
+        idx = torch.empty(B, M, K, dtype=torch.int32)
+        for b in range(B):
+            for m in range(M):
+                c = int(torch.randint(1, K // 2, (1,), generator=g))
+                inball = torch.randperm(N - K, generator=g)[:c] + K
+                idx[b, m] = torch.cat((inball, torch.arange(K - c))).int()
+    else:
+        idx = torch.randint(0, N, (B, M, K), generator=g, dtype=torch.int32)
+    offsets, perm = pkg.ops.NeighborIndex(idx.to(dev), N).csr()
+    _check_csr(idx, N, offsets.cpu(), perm.cpu())
+    # the flat entry point (no row structure given)
+    E = M * K
+    off2 = torch.empty(B, N + 1, dtype=torch.int32, device=dev)
+    perm2 = torch.empty(B, E, dtype=torch.int32, device=dev)
+    nb = pkg._lib.size("pcnbr_csr_ws_bytes", B, E, N)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    pkg._lib.call("pcnbr_csr_build", idx.to(dev).data_ptr(), B, E, N, off2.data_ptr(), perm2.data_ptr(), ws.data_ptr(), nb,
+                  torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(off2, offsets) and torch.equal(perm2, perm)
+
+
 def test_group_backward_is_deterministic(pkg, dev):
     B, N, M, K, D = 2, 512, 128, 32, 64
     pts, _, _ = O.s3dis_blocks(B, N, seed=3)
