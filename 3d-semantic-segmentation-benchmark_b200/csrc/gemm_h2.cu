@@ -1,0 +1,483 @@
+// gemm_h2.cu -- fp32-accurate GEMM on the tensor cores with a TWO-TERM FP16 SPLIT (kind::f16: twice the TF32 rate).
+//
+// Reference: the wide 1x1 convolutions of models/dgcnn/dgcnn.py:95-126 (conv5 384->1024, conv6 1408->512, conv7 512->256
+// over 65536 rows) are tensor-bound GEMMs.  gemm_tc.cu runs them as three TF32 products and sits at that design's ceiling
+// (89 % of the TF32 issue rate).  kind::f16 issues at twice the TF32 rate, and an fp32 value splits into two fp16 terms
+// as exactly as into two tf32 terms once the tensor is brought into fp16's range:
+//     y  = x * s            s = power of two with  max|x| * s  in [2^14, 2^15)      (exact)
+//     hi = fp16_rn(y)       lo = fp16_rn(y - hi)                                   y = hi + lo + e,  |e| <= 2^-24 |y|
+//     C  = (hi.hi' + lo.hi' + hi.lo') / (s s')                                     dropped: lo.lo' <= 2^-24 |y||y'|
+// (for |y| < 2^-9 the residual lo falls into fp16 subnormals: its ABSOLUTE error is 2^-25, i.e. 2^-40 of the tensor's
+// largest element -- irrelevant against the 2^-24 of the large elements it is added to).  Per product the error is
+// ~3 * 2^-24, better than the 3xTF32 kernel's 2^-21 (whose `hi` is a truncation).
+//
+// max|x| per operand comes from pcnbr_absmax_f32 (one extra read of the tensor: 256 per-block maxima, reduced here).
+// Structure as gemm_tc.cu: warp 0 TMA producer (fp32 tiles exactly as they lie in HBM, K-major or MN-major), warp 1 MMA
+// issuer, warps 2-5 epilogue (tcgen05.ld -> * 1/(s s') (+ bias) -> swizzled staging -> TMA store), warps 6-13 converters.
+// The converters rewrite each landed fp32 tile IN PLACE (4 B per element before and after) as [hi | lo] fp16 tiles in the
+// K-major 64-byte-swizzle UMMA layout -- MN-major operands are transposed on the way, so the MMA only ever sees K-major
+// fp16 -- with one named barrier between "everything read into registers" and "first store".
+#include "gemm_common.cuh"
+#include <cuda_fp16.h>
+
+namespace pcnbr {
+
+constexpr int H2_AMAX_SLOTS = 256;         // per-block maxima written by absmax_kernel
+constexpr int H2_CONV_THREADS = 32 * GM_CONV_WARPS;
+
+// kind::f16 (A, B = fp16, both K-major), D = fp32, M = 128, N = BN (cute::UMMA::InstrDescriptor)
+template <int BN>
+__device__ __forceinline__ void h2_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, bool accumulate) {
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, 64-byte swizzle (rows of 32 fp16 = 64 B, 8-row groups 512 B apart; layout type 4 = SWIZZLE_64B);
+// a K step of 16 fp16 = +32 B inside the swizzle atom
+__device__ __forceinline__ uint64_t h2_desc(uint32_t saddr) {
+    const uint64_t lo = (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16);
+    const uint64_t hi = (uint64_t)(512 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)4 << 29);
+    return lo | (hi << 32);
+}
+// byte offset of the 16-byte chunk g (8 fp16 of K) of row r in a [rows x 32 fp16] K-major SWIZZLE_64B tile
+__device__ __forceinline__ uint32_t h2_dst_off(int r, int g) { return (uint32_t)(r * 64 + ((g ^ ((r >> 1) & 3)) << 4)); }
+
+// scale s = 2^e with amax * s in [2^14, 2^15), and 1/s; degenerate tensors (all zero / denormal / non-finite) get s = 1
+__device__ __forceinline__ void h2_scale_of(float amax, float& s, float& inv) {
+    const uint32_t E = (__float_as_uint(amax) >> 23) & 0xffu;
+    if (E < 16u || E == 255u) { s = 1.f; inv = 1.f; return; }
+    s = __uint_as_float((268u - E) << 23);
+    inv = __uint_as_float((E - 14u) << 23);
+}
+
+// 8 consecutive K values of one row -> hi / lo fp16 chunks (16 bytes each)
+__device__ __forceinline__ void h2_split8(const float (&v)[8], float s, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float y0 = __fmul_rn(v[2 * j], s), y1 = __fmul_rn(v[2 * j + 1], s);
+        const __half2 hh = __floats2half2_rn(y0, y1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
+        h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Read the 8 K values [8g, 8g+8) of row `r` of a landed fp32 tile (TMA SWIZZLE_128B in both layouts).
+//   K-major : rows of 32 floats (128 B); tiles of more than 128 rows are stacked 128-row boxes.
+//   MN-major: chunks of 32 rows; inside a chunk K row k holds the 32 row-values as 128 B (so a lane per row reads
+//             consecutive words: conflict-free).
+template <bool MN>
+__device__ __forceinline__ void h2_load8(const uint8_t* tile, int r, int g, float (&v)[8]) {
+    if (MN) {
+        const uint8_t* ch = tile + (r >> 5) * GM_CHUNK;
+        const int rl = r & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * g + j;
+            v[j] = *reinterpret_cast<const float*>(ch + k * 128 + (((rl >> 2) ^ (k & 7)) << 4) + (rl & 3) * 4);
+        }
+    } else {
+        const uint8_t* row = tile + (r >> 7) * GM_SLAB + (r & 127) * 128;
+        const float4 a = *reinterpret_cast<const float4*>(row + (((2 * g) ^ (r & 7)) << 4));
+        const float4 b = *reinterpret_cast<const float4*>(row + (((2 * g + 1) ^ (r & 7)) << 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+              const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c, int M, int N, int K,
+              int kb_split, int splits, const float* __restrict__ bias, const float* __restrict__ amax_a,
+              const float* __restrict__ amax_a2, const float* __restrict__ amax_b) {
+    extern __shared__ uint8_t gm_smem_raw[];
+    uint8_t* smem = gm_smem_raw + ((1024u - (gm_smem_u32(gm_smem_raw) & 1023u)) & 1023u);
+    constexpr uint32_t A_BYTES = GM_SLAB, B_BYTES = (uint32_t)BN * 128u;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;               // fp32 landing zone == [hi | lo] fp16 afterwards
+    constexpr int NBUF = (512 / BN) < 8 ? (512 / BN) : 8;             // TMEM accumulators of BN columns
+    uint8_t* cstage = smem + STAGES * STAGE_BYTES;                    // 2 x (128 rows x 128 B), swizzled: TMA-store staging
+    uint64_t* bars = (uint64_t*)(cstage + 2 * GM_SLAB);
+    uint64_t* full = bars;                                            // [STAGES]  TMA landed          (count 1 + tx)
+    uint64_t* conv = bars + STAGES;                                   // [STAGES]  fp16 tiles ready     (count GM_CONV_WARPS)
+    uint64_t* empty = bars + 2 * STAGES;                              // [STAGES]  MMAs retired        (count 1)
+    uint64_t* tmem_full = bars + 3 * STAGES;                          // [NBUF]
+    uint64_t* tmem_empty = bars + 3 * STAGES + NBUF;                  // [NBUF]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * STAGES + 2 * NBUF);
+    float* s_scale = (float*)(tmem_slot + 2);                         // {s_a, s_b, 1/s_a, 1/s_b}
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MT = (M + GM_BM - 1) / GM_BM, NT = (N + BN - 1) / BN;
+    const int KB = (K + GM_BK - 1) / GM_BK;
+    const int kb_per = (KB + splits - 1) / splits;
+    const int units = MT * NT * splits;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
+        for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&conv[i], GM_CONV_WARPS); gm_mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NBUF; ++i) { gm_mbar_init(&tmem_full[i], 1); gm_mbar_init(&tmem_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gm_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 2) {
+        // per-tensor scales from the per-block maxima of pcnbr_absmax_f32 (A and its concatenated second half share one)
+        float ma = 0.f, mb = 0.f;
+        for (int i = lane; i < H2_AMAX_SLOTS; i += 32) {
+            ma = fmaxf(ma, amax_a[i]);
+            if (amax_a2) ma = fmaxf(ma, amax_a2[i]);
+            mb = fmaxf(mb, amax_b[i]);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ma = fmaxf(ma, __shfl_xor_sync(PCNBR_FULL, ma, d));
+            mb = fmaxf(mb, __shfl_xor_sync(PCNBR_FULL, mb, d));
+        }
+        if (lane == 0) {
+            h2_scale_of(ma, s_scale[0], s_scale[2]);
+            h2_scale_of(mb, s_scale[1], s_scale[3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (fp32 tiles, as in gemm3x_kernel)
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
+                const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    gm_mbar_wait(&empty[stage], phase ^ 1);
+                    gm_mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+                    const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
+                    if (A_MN) {
+#pragma unroll
+                        for (int c = 0; c < GM_BM / 32; ++c)
+                            gm_tma_load_2d(st + c * GM_CHUNK, &tm_a, &full[stage], mt * GM_BM + c * 32, kb * GM_BK);
+                    } else {
+                        if (kb < kb_split) gm_tma_load_2d(st, &tm_a, &full[stage], kb * GM_BK, mt * GM_BM);
+                        else               gm_tma_load_2d(st, &tm_a2, &full[stage], (kb - kb_split) * GM_BK, mt * GM_BM);
+                    }
+                    const uint32_t sb = st + A_BYTES;
+                    if (B_MN) {
+#pragma unroll
+                        for (int c = 0; c < BN / 32; ++c)
+                            gm_tma_load_2d(sb + c * GM_CHUNK, &tm_b, &full[stage], nt * BN + c * 32, kb * GM_BK);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < (BN + 127) / 128; ++h)
+                            gm_tma_load_2d(sb + h * GM_SLAB, &tm_b, &full[stage], kb * GM_BK, nt * BN + h * 128);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer: 3 products x 2 K steps of 16 per stage
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        uint32_t stage = 0, phase = 0, tile = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
+            const int sp = unit / (MT * NT);
+            const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
+            const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
+            gm_mbar_wait(&tmem_empty[buf], tphase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = tmem_base + buf * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
+                const uint64_t ah = h2_desc(st), al = h2_desc(st + A_BYTES / 2);
+                const uint64_t bh = h2_desc(st + A_BYTES), bl = h2_desc(st + A_BYTES + B_BYTES / 2);
+                gm_mbar_wait(&conv[stage], phase);                    // [hi | lo] tiles written and published
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (leader) {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) h2_umma<BN>(d, ah + 2 * s, bh + 2 * s, kb > kb0 || s > 0);    // hi . hi'
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) h2_umma<BN>(d, al + 2 * s, bh + 2 * s, true);                 // lo . hi'
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) h2_umma<BN>(d, ah + 2 * s, bl + 2 * s, true);                 // hi . lo'
+                    gm_umma_commit(&empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (leader) gm_umma_commit(&tmem_full[buf]);
+            __syncwarp();
+        }
+    } else if (warp < 6) {
+        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int quarter = warp & 3;
+        const uint32_t tlane = (uint32_t)(quarter * 32) << 16;
+        const int rloc = quarter * 32 + lane;
+        const bool issuer = (warp == 2 && lane == 0);
+        const float inv_a = s_scale[2], inv_b = s_scale[3];
+        uint32_t tile = 0, slab = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
+            const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
+            const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
+            const int ncols = min(BN, N - nt * BN);
+            const int nq = (ncols + 31) / 32;
+            gm_mbar_wait(&tmem_full[buf], tphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int q = 0; q < nq; ++q, ++slab) {
+                uint32_t r[32];
+                gm_tmem_ld32(tmem_base + tlane + buf * BN + q * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (q == nq - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) gm_mbar_arrive(&tmem_empty[buf]);
+                }
+                const int c0 = nt * BN + q * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float v = __fmul_rn(__fmul_rn(__uint_as_float(r[i]), inv_a), inv_b);      // exact: powers of two
+                    if (bias && c0 + i < N) v += __ldg(bias + c0 + i);
+                    r[i] = __float_as_uint(v);
+                }
+                uint8_t* sb = cstage + (slab & 1) * GM_SLAB;
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                gm_epi_barrier();
+                uint8_t* rowp = sb + rloc * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(rowp + ((c ^ (rloc & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                gm_epi_barrier();
+                if (issuer) {
+                    gm_tma_store_3d(&tm_c, gm_smem_u32(sb), nt * BN + q * 32, mt * GM_BM, sp);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+        // ===================================================== converters: fp32 tile -> [hi | lo] fp16 tiles, in place
+        const int t = threadIdx.x - 192;                              // 0 .. 255
+        constexpr int TA = (GM_BM * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;      // (row, 8-wide K group) tasks per thread
+        constexpr int TB = (BN * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;
+        const float sa = s_scale[0], sbs = s_scale[1];
+        uint32_t stage = 0, phase = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int sp = unit / (MT * NT);
+            const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                uint8_t* st = smem + stage * STAGE_BYTES;
+                uint8_t* sb = st + A_BYTES;
+                gm_mbar_wait(&full[stage], phase);
+                float va[TA][8], vb[TB][8];
+#pragma unroll
+                for (int i = 0; i < TA; ++i) {
+                    const int q = t + i * H2_CONV_THREADS;
+                    if (q < GM_BM * 4) h2_load8<A_MN>(st, q % GM_BM, q / GM_BM, va[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                    const int q = t + i * H2_CONV_THREADS;
+                    if (q < BN * 4) h2_load8<B_MN>(sb, q % BN, q / BN, vb[i]);
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");       // every fp32 word is in registers: overwrite in place
+#pragma unroll
+                for (int i = 0; i < TA; ++i) {
+                    const int q = t + i * H2_CONV_THREADS;
+                    if (q < GM_BM * 4) {
+                        uint4 hi, lo;
+                        h2_split8(va[i], sa, hi, lo);
+                        const uint32_t off = h2_dst_off(q % GM_BM, q / GM_BM);
+                        *reinterpret_cast<uint4*>(st + off) = hi;
+                        *reinterpret_cast<uint4*>(st + A_BYTES / 2 + off) = lo;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                    const int q = t + i * H2_CONV_THREADS;
+                    if (q < BN * 4) {
+                        uint4 hi, lo;
+                        h2_split8(vb[i], sbs, hi, lo);
+                        const uint32_t off = h2_dst_off(q % BN, q / BN);
+                        *reinterpret_cast<uint4*>(sb + off) = hi;
+                        *reinterpret_cast<uint4*>(sb + B_BYTES / 2 + off) = lo;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) gm_mbar_arrive(&conv[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// partial[blockIdx.x] = max |x| over this block's share of a (rows x cols) fp32 matrix with row pitch ld (cols, ld
+// multiples of 4, 16-byte aligned base); every one of the H2_AMAX_SLOTS slots is written
+__global__ void __launch_bounds__(512)
+absmax_kernel(const float* __restrict__ x, long rows, int cols, long ld, float* __restrict__ partial) {
+    __shared__ float red[16];
+    const int c4 = cols >> 2;
+    const long total = rows * c4;
+    float m = 0.f;
+    if (ld == cols) {
+        const float4* __restrict__ v = reinterpret_cast<const float4*>(x);
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+            const float4 a = v[i];
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        }
+    } else {
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+            const long r = i / c4;
+            const int c = (int)(i - r * c4);
+            const float4 a = *reinterpret_cast<const float4*>(x + r * ld + 4 * c);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(PCNBR_FULL, m, d));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < 16 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(PCNBR_FULL, m, d));
+        if (threadIdx.x == 0) partial[blockIdx.x] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+// fp32 matrix of `outer` rows x `inner` contiguous floats, box = 32 floats x box_rows, plain 128-byte swizzle (the
+// converters, not the MMA, read the landed tile); out-of-range elements read as 0
+static int h2_make_map(CUtensorMap* map, const float* base, long inner, long outer, long ld, int box_rows) {
+    GmEncodeFn enc = gm_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int h2_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
+                     int M, int N, int K, int splits, const float* bias, const float* amax_a, const float* amax_a2,
+                     const float* amax_b, cudaStream_t s) {
+    const size_t smem = (size_t)STAGES * (GM_SLAB + (size_t)BN * 128) + 2 * GM_SLAB + 64 * 8 + 64 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(gemm2h_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int units = ((M + GM_BM - 1) / GM_BM) * ((N + BN - 1) / BN) * splits;
+    const int grid = units < sms ? units : sms;
+    // algorithmic work as gemm3x_kernel: 2 M N K flop counted once (3 fp16 products are issued); operands once + result
+    const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), flops = 2.0 * M * (double)N * K;
+    const char* name = flops / 678.35e12 > bytes / 6551e9 ? "gemm2h_kernel[tensor]" : "gemm2h_kernel[hbm]";
+    PCNBR_TIMED(name, s, bytes, flops,
+                (gemm2h_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias,
+                                                                                      amax_a, amax_a2, amax_b)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int h2_dispatch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
+                       int M, int N, int K, int splits, const float* bias, const float* amax_a, const float* amax_a2,
+                       const float* amax_b, cudaStream_t s) {
+    switch (gm_tile_n(M, N, K)) {                                            // stages: 48 / 32 / 24 / 20 KB each beside 32 KB of staging
+        case 256: return h2_launch<256, 4, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        case 128: return h2_launch<128, 5, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        case 64:  return h2_launch<64, 6, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        default:  return h2_launch<32, 6, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+    }
+}
+
+}  // namespace pcnbr
+
+using namespace pcnbr;
+
+extern "C" int pcnbr_amax_slots(void) { return H2_AMAX_SLOTS; }
+
+extern "C" int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, float* partial, pcnbr_stream_t stream) {
+    if (!x || !partial || rows <= 0 || cols <= 0 || (cols % 4) || (ld % 4) || ld < cols || ((uintptr_t)x & 15)) return PCNBR_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    PCNBR_TIMED("absmax_kernel", s, 4.0 * (double)rows * cols, 0.0,
+                (absmax_kernel<<<H2_AMAX_SLOTS, 512, 0, s>>>(x, rows, (int)cols, ld, partial)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+// 1 when the two-term fp16 kernel should take this GEMM: its tensor-pipe time bound (at the TF32 rate the 3xTF32 kernel
+// is tied to) exceeds its HBM time bound, i.e. the 3xTF32 kernel would sit at its 3-instructions-per-product ceiling
+extern "C" int pcnbr_gemm2h_preferred(int M, int N, int K) {
+    const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N), flops = 2.0 * M * (double)N * K;
+    return flops / 678.35e12 > bytes / 6551e9 ? 1 : 0;
+}
+
+// Same contract as pcnbr_gemm3x_ex_f32 (splits from pcnbr_gemm3x_splits, ws from pcnbr_gemm3x_ws_bytes) plus the
+// per-block maxima (pcnbr_amax_slots() floats each, from pcnbr_absmax_f32) of A, of A2 when given, and of B.
+extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
+                                   int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
+                                   size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
+                                   pcnbr_stream_t stream) {
+    if (!A || !B || !C || !amax_a || !amax_b || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
+    if ((lda % 4) || (ldb % 4) || (((uintptr_t)A | (uintptr_t)B) & 15)) return PCNBR_E_BADARG;
+    const int Ka = A2 ? K1 : K;
+    if (lda < (a_mn ? M : Ka) || ldb < (b_mn ? N : K)) return PCNBR_E_BADARG;
+    if (A2 && (!amax_a2 || a_mn || K1 <= 0 || K1 >= K || (K1 % GM_BK) || (lda2 % 4) || ((uintptr_t)A2 & 15) || lda2 < K - K1)) return PCNBR_E_BADARG;
+    if (ldc < N || (ldc % 4) || ((uintptr_t)C & 15)) return PCNBR_E_BADARG;
+    if (splits > 1 && (!ws || ws_bytes < sizeof(float) * (size_t)splits * (size_t)M * (size_t)N)) return PCNBR_E_WORKSPACE;
+    if (splits > 1 && bias) return PCNBR_E_BADARG;
+    {
+        const int kb = (K + GM_BK - 1) / GM_BK, per = (kb + splits - 1) / splits;
+        if ((kb + per - 1) / per != splits) return PCNBR_E_BADARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int bn = gm_tile_n(M, N, K);
+    CUtensorMap ta, ta2, tb;
+    int rc = a_mn ? h2_make_map(&ta, A, M, K, lda, 32) : h2_make_map(&ta, A, Ka, M, lda, 128);
+    if (!rc && A2) rc = h2_make_map(&ta2, A2, K - K1, M, lda2, 128);
+    if (!A2) ta2 = ta;
+    if (!rc) rc = b_mn ? h2_make_map(&tb, B, N, K, ldb, 32) : h2_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128);
+    if (rc) return rc;
+    const int kb_split = A2 ? K1 / GM_BK : (K + GM_BK - 1) / GM_BK;
+    float* out = splits > 1 ? (float*)ws : C;
+    const float* b = splits > 1 ? nullptr : bias;
+    if ((uintptr_t)out & 15) return PCNBR_E_BADARG;
+    CUtensorMap tc;
+    rc = gm_make_map_c(&tc, out, M, N, splits > 1 ? N : ldc, splits);
+    if (rc) return rc;
+    const float* am2 = A2 ? amax_a2 : nullptr;
+    if (a_mn) rc = b_mn ? h2_dispatch<true, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
+                        : h2_dispatch<true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+    else      rc = b_mn ? h2_dispatch<false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
+                        : h2_dispatch<false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+    if (rc) return rc;
+    if (splits > 1) rc = gm_launch_reduce((const float*)ws, M, N, ldc, splits, C, s);
+    return rc;
+}

@@ -833,8 +833,32 @@ def batchnorm_act_rows(rows: torch.Tensor, bn, negative_slope: float) -> torch.T
 # ----------------------------------------------------------------------------- 1x1 convolution as a tensor-core GEMM
 
 
-def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=None, K1: int = 0, out=None) -> torch.Tensor:
-    """C (M,N) = A (M,K) . B (N,K)^T (+ bias) on tcgen05, 3xTF32 from the fp32 operands (fp32-grade accuracy).
+_GEMM_3XTF32_ONLY = __import__("os").environ.get("PCNBR_GEMM_3XTF32") is not None     # A/B switch: never take the fp16-split kernel
+
+
+def _absmax(t: torch.Tensor):
+    """Per-block maxima of |t| (pcnbr_amax_slots floats) for a 2-D fp32 matrix with unit inner stride, or None when the
+    matrix does not meet the kernel's alignment (the 3xTF32 GEMM then takes the product)."""
+    rows, cols = t.shape
+    ld = t.stride(0)
+    if t.stride(1) != 1 or cols % 4 or ld % 4 or t.data_ptr() % 16:
+        return None
+    out = torch.empty(_lib.size("pcnbr_amax_slots"), dtype=torch.float32, device=t.device)
+    _lib.call("pcnbr_absmax_f32", t.data_ptr(), rows, cols, ld, out.data_ptr(), _stream())
+    return out
+
+
+def _gemm_h2_wanted(M: int, N: int, K: int) -> bool:
+    """The two-term fp16 kernel takes the GEMMs whose tensor-pipe bound exceeds their HBM bound (symmetric in M, N, K: the
+    three GEMMs of a layer -- output, input gradient, weight gradient -- are classified alike)."""
+    return (not _GEMM_3XTF32_ONLY) and bool(_lib.size("pcnbr_gemm2h_preferred", M, N, K))
+
+
+def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=None, K1: int = 0, out=None,
+            amax_a=None, amax_b=None, amax_a2=None) -> torch.Tensor:
+    """C (M,N) = A (M,K) . B (N,K)^T (+ bias) on tcgen05 with fp32-grade accuracy: 3xTF32 from the fp32 operands, or -- for
+    tensor-bound shapes -- the two-term fp16 split at twice the instruction rate (csrc/gemm_h2.cu; needs max |x| of each
+    operand: amax_* = per-block maxima from _absmax, computed here when not handed in).
     a_mn / b_mn: the operand is stored transposed ((K,M) / (K,N) row-major).  Operands are 2-D, unit inner stride, any
     16-byte row pitch.  A2: A is the channel concatenation [A (M,K1) | A2 (M,K-K1)] (never materialised).  out: a
     preallocated (M,N) view with unit inner stride (e.g. a column block of a wider matrix)."""
@@ -843,13 +867,24 @@ def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=
     ws = _ws(nb, A.device)
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    if _gemm_h2_wanted(M, N, K):
+        amax_a = amax_a if amax_a is not None else _absmax(A)
+        amax_b = amax_b if amax_b is not None else _absmax(B)
+        if A2 is not None and amax_a2 is None:
+            amax_a2 = _absmax(A2)
+        if amax_a is not None and amax_b is not None and (A2 is None or amax_a2 is not None):
+            _lib.call("pcnbr_gemm2h_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
+                      A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+                      bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0), splits, ws.data_ptr(), nb,
+                      amax_a.data_ptr(), amax_a2.data_ptr() if amax_a2 is not None else None, amax_b.data_ptr(), _stream())
+            return out
     _lib.call("pcnbr_gemm3x_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
               A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
               bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0), splits, ws.data_ptr(), nb, _stream())
     return out
 
 
-def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None) -> torch.Tensor:
+def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None, amax_gy=None, amax_x=None) -> torch.Tensor:
     """dW (Cout,Cin) = gy^T x for gy (R,Cout), x (R,Cin), both contiguous.  For narrow layers the 128 x BN tile of the
     split-K GEMM would be mostly zero padding (too few useful bytes in flight per SM), so p consecutive rows are viewed
     as one row of p*Cout / p*Cin channels: the (p*Cout, p*Cin) product of the two views has dW as the sum of its p
@@ -860,21 +895,31 @@ def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None) -> torch.Tensor:
     while 2 * p * Cout <= 128 and 2 * p * Cin <= 256 and R % (2 * p) == 0 and R // (2 * p) >= 4096:
         p *= 2
     if p == 1 or out is not None:
-        return _gemm3x(gy, True, x, True, Cout, Cin, R, out=out)
+        return _gemm3x(gy, True, x, True, Cout, Cin, R, out=out, amax_a=amax_gy, amax_b=amax_x)
     big = _gemm3x(gy.view(R // p, p * Cout), True, x.view(R // p, p * Cin), True, p * Cout, p * Cin, R // p)
     return big.view(p, Cout, p, Cin).diagonal(dim1=0, dim2=2).sum(dim=-1)
 
 
+def _layer_amax(x, w, R, Cout, Cin):
+    """(amax_x, amax_w) when the layer's GEMMs go to the fp16-split kernel (each tensor is scanned ONCE and the maxima are
+    shared by the forward, input-gradient and weight-gradient GEMMs), else (None, None)."""
+    if not _gemm_h2_wanted(R, Cout, Cin):
+        return None, None
+    return _absmax(x), _absmax(w)
+
+
 class _LinearRowsFn(torch.autograd.Function):
     """y = x W^T + b over the rows of x, all three GEMMs of the layer (output, input gradient, weight gradient) on the
-    tensor cores in 3xTF32, each reading x, W and gy exactly as they lie in memory (no split or transposed copies)."""
+    tensor cores with fp32-grade accuracy, each reading x, W and gy exactly as they lie in memory (no split or transposed
+    copies)."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
         R, Cin = x.shape
-        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b)
+        ctx.amax = _layer_amax(x, w, R, w.shape[0], Cin)
+        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1])
 
     @staticmethod
     def backward(ctx, gy):
@@ -882,8 +927,10 @@ class _LinearRowsFn(torch.autograd.Function):
         R, Cin = x.shape
         Cout = w.shape[0]
         gy = _c(gy)
-        dx = _gemm3x(gy, False, w, True, R, Cin, Cout) if ctx.needs_input_grad[0] else None       # gy (R,Cout) . W (Cout,Cin)
-        dw = _wgrad3x(gy, x) if ctx.needs_input_grad[1] else None                                  # gy^T . x, split along R
+        ax, aw = ctx.amax
+        ag = _absmax(gy) if ax is not None else None
+        dx = _gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None    # gy (R,Cout) . W (Cout,Cin)
+        dw = _wgrad3x(gy, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None                                # gy^T . x, split along R
         db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 
@@ -899,7 +946,8 @@ class _LinearBnActFn(torch.autograd.Function):
         R, Cin = x.shape
         C = w.shape[0]
         dev = x.device
-        h = _gemm3x(x, False, w, False, R, C, Cin, b)
+        ctx.amax = _layer_amax(x, w, R, C, Cin)
+        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1])
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -938,8 +986,10 @@ class _LinearBnActFn(torch.autograd.Function):
         dh = torch.empty_like(h)
         _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
                   dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
-        dx = _gemm3x(dh, False, w, True, R, Cin, C) if ctx.needs_input_grad[0] else None
-        dw = _wgrad3x(dh, x) if ctx.needs_input_grad[1] else None
+        ax, aw = ctx.amax
+        ag = _absmax(dh) if ax is not None else None
+        dx = _gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None
+        dw = _wgrad3x(dh, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
@@ -958,7 +1008,8 @@ class _LinearBnActPoolFn(torch.autograd.Function):
         C = w.shape[0]
         G = R // K
         dev = x.device
-        h = _gemm3x(x, False, w, False, R, C, Cin, b)
+        ctx.amax = _layer_amax(x, w, R, C, Cin)
+        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1])
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -997,8 +1048,10 @@ class _LinearBnActPoolFn(torch.autograd.Function):
         dh = torch.empty_like(h)
         _lib.call("pcnbr_pool_bn_bwd_apply_f32", h.data_ptr(), gs.data_ptr(), arg.data_ptr(), G, K, C, coef.data_ptr(),
                   dh.data_ptr(), _stream())
-        dx = _gemm3x(dh, False, w, True, R, Cin, C) if ctx.needs_input_grad[0] else None
-        dw = _wgrad3x(dh, x) if ctx.needs_input_grad[1] else None
+        ax, aw = ctx.amax
+        ag = _absmax(dh) if ax is not None else None
+        dx = _gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None
+        dw = _wgrad3x(dh, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
@@ -1034,7 +1087,11 @@ class _LinearBnActCatFn(torch.autograd.Function):
         K2 = x2.shape[1]
         C = w.shape[0]
         dev = x1.device
-        h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1)
+        if _gemm_h2_wanted(R, C, K1 + K2):
+            ctx.amax = (_absmax(x1), _absmax(x2), _absmax(w))
+        else:
+            ctx.amax = (None, None, None)
+        h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1, amax_a=ctx.amax[0], amax_a2=ctx.amax[1], amax_b=ctx.amax[2])
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -1075,13 +1132,15 @@ class _LinearBnActCatFn(torch.autograd.Function):
         _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
                   dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
-        dx1 = _gemm3x(dh, False, w[:, :K1], True, R, K1, C) if ctx.needs_input_grad[0] else None
-        dx2 = _gemm3x(dh, False, w[:, K1:], True, R, K2, C) if ctx.needs_input_grad[1] else None
+        a1, a2, aw = ctx.amax
+        ag = _absmax(dh) if aw is not None else None                # one scan of dh serves the four GEMMs below
+        dx1 = _gemm3x(dh, False, w[:, :K1], True, R, K1, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None
+        dx2 = _gemm3x(dh, False, w[:, K1:], True, R, K2, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[1] else None
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(w)
-            _wgrad3x(dh, x1, out=dw[:, :K1])
-            _wgrad3x(dh, x2, out=dw[:, K1:])
+            _wgrad3x(dh, x1, out=dw[:, :K1], amax_gy=ag, amax_x=a1)
+            _wgrad3x(dh, x2, out=dw[:, K1:], amax_gy=ag, amax_x=a2)
         db = None
         if has_b and ctx.needs_input_grad[3]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta

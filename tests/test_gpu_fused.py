@@ -120,6 +120,52 @@ def test_gemm3x_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K):
     assert torch.equal(out, pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K))
 
 
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,K,scale_a,scale_b", [(4096, 512, 1408, 1.0, 1.0), (4000, 500, 1400, 3e-7, 2e3), (2048, 1024, 384, 40.0, 1e-3),
+                                                   (512, 1408, 16384, 1e-4, 1.0), (130, 260, 30000, 1.0, 1.0)])
+def test_gemm_fp16_split_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K, scale_a, scale_b):
+    """csrc/gemm_h2.cu (two-term fp16 split on kind::f16, per-tensor power-of-two scales from pcnbr_absmax_f32): K-major and
+    MN-major operands (transposed by the in-kernel converters), ragged sizes, split-K, operands far outside fp16's range,
+    wide dynamic range inside one operand -- all against float64 at the 3xTF32 kernel's bar."""
+    assert pkg._lib.size("pcnbr_gemm2h_preferred", M, N, K) == 1
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, generator=g) + 0.25) * scale_a
+    Bm = (torch.randn(N, K, generator=g) - 0.1) * scale_b
+    A[::7] *= 1e-4                                      # rows 10^4 below the tensor's maximum: lo falls into fp16 subnormals
+    Bm[:, ::5] *= 1e-3
+    pad = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 4))
+    Am = pad(A.t().contiguous() if a_mn else A).to(dev)
+    Bmm = pad(Bm.t().contiguous() if b_mn else Bm).to(dev)
+    pkg._lib.prof_enable(True)
+    pkg._lib.prof_collect()
+    out = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K)
+    ran = pkg._lib.prof_collect()
+    pkg._lib.prof_enable(False)
+    assert any(k.startswith("gemm2h_kernel") for k in ran) and "absmax_kernel" in ran, sorted(ran)
+    ref = A.double() @ Bm.double().t()
+    _close(out, ref, 3e-5)
+    # error against the per-element bound sum_k |a||b|: the split itself must be fp32-grade (<= 2^-20)
+    bound = A.double().abs() @ Bm.double().abs().t()
+    rel = ((out.cpu().double() - ref).abs() / (bound + 1e-300)).max().item()
+    assert rel <= 2.0 ** -20, f"max error / sum|a||b| = {rel:.3e}"
+    assert torch.equal(out, pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K))
+
+
+def test_gemm_fp16_split_concatenated_input_and_degenerate_operands(pkg, dev):
+    """A = [A1 | A2] read from two matrices with different magnitudes (one shared scale); an all-zero operand; a bias."""
+    g = torch.Generator().manual_seed(5)
+    M, K1, K2, N = 4096, 384, 1024, 512
+    A1, A2 = torch.randn(M, K1, generator=g) * 30.0, torch.randn(M, K2, generator=g) * 0.02
+    W = torch.randn(N, K1 + K2, generator=g) / 40.0
+    b = torch.randn(N, generator=g)
+    out = pkg.ops._gemm3x(A1.to(dev), False, W.to(dev), False, M, N, K1 + K2, b.to(dev), A2=A2.to(dev), K1=K1)
+    ref = torch.cat((A1, A2), 1).double() @ W.double().t() + b.double()
+    _close(out, ref, 3e-5)
+    z = pkg.ops._gemm3x(torch.zeros(M, K1 + K2, device=dev), False, W.to(dev), False, M, N, K1 + K2)
+    assert float(z.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("R,Cin,Cout", [(4096, 9, 32), (512, 768, 256), (32, 512, 256), (65536, 256, 13), (100, 7, 5)])
 def test_linear_rows_odd_widths_and_few_rows_run_on_libpcnbr(pkg, dev, R, Cin, Cout):
     """Channel counts that are not multiples of 4 (9-channel stem, 13-class head) are zero-padded to the TMA pitch and
