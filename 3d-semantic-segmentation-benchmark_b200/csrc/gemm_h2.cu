@@ -46,6 +46,12 @@ __device__ __forceinline__ uint64_t h2_desc(uint32_t saddr) {
 // byte offset of the 16-byte chunk g (8 fp16 of K) of row r in a [rows x 32 fp16] K-major SWIZZLE_64B tile
 __device__ __forceinline__ uint32_t h2_dst_off(int r, int g) { return (uint32_t)(r * 64 + ((g ^ ((r >> 1) & 3)) << 4)); }
 
+__device__ __forceinline__ void h2_tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(gm_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // scale s = 2^e with amax * s in [2^14, 2^15), and 1/s; degenerate tensors (all zero / denormal / non-finite) get s = 1
 __device__ __forceinline__ void h2_scale_of(float amax, float& s, float& inv) {
     const uint32_t E = (__float_as_uint(amax) >> 23) & 0xffu;
@@ -93,7 +99,10 @@ __device__ __forceinline__ void h2_load8(const uint8_t* tile, int r, int g, floa
     }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// B_PRE: the B operand arrives already split ([hi | lo] fp16 planes written once by split_f16_kernel -- the weights of a
+// forward / input-gradient GEMM, which every CTA would otherwise convert again): TMA drops the two planes straight into
+// the UMMA layout (SWIZZLE_64B) and the converters only handle A (a third of the work at BN = 256).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
               const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c, int M, int N, int K,
@@ -176,7 +185,10 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                         else               gm_tma_load_2d(st, &tm_a2, &full[stage], (kb - kb_split) * GM_BK, mt * GM_BM);
                     }
                     const uint32_t sb = st + A_BYTES;
-                    if (B_MN) {
+                    if (B_PRE) {
+                        h2_tma_load_3d(sb, &tm_b, &full[stage], kb * GM_BK, nt * BN, 0);                      // hi plane
+                        h2_tma_load_3d(sb + B_BYTES / 2, &tm_b, &full[stage], kb * GM_BK, nt * BN, 1);        // lo plane
+                    } else if (B_MN) {
 #pragma unroll
                         for (int c = 0; c < BN / 32; ++c)
                             gm_tma_load_2d(sb + c * GM_CHUNK, &tm_b, &full[stage], nt * BN + c * 32, kb * GM_BK);
@@ -274,7 +286,7 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         // ===================================================== converters: fp32 tile -> [hi | lo] fp16 tiles, in place
         const int t = threadIdx.x - 192;                              // 0 .. 255
         constexpr int TA = (GM_BM * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;      // (row, 8-wide K group) tasks per thread
-        constexpr int TB = (BN * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;
+        constexpr int TB = B_PRE ? 0 : (BN * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;
         const float sa = s_scale[0], sbs = s_scale[1];
         uint32_t stage = 0, phase = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -284,7 +296,7 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                 uint8_t* st = smem + stage * STAGE_BYTES;
                 uint8_t* sb = st + A_BYTES;
                 gm_mbar_wait(&full[stage], phase);
-                float va[TA][8], vb[TB][8];
+                float va[TA][8], vb[TB > 0 ? TB : 1][8];
 #pragma unroll
                 for (int i = 0; i < TA; ++i) {
                     const int q = t + i * H2_CONV_THREADS;
@@ -367,7 +379,54 @@ absmax_kernel(const float* __restrict__ x, long rows, int cols, long ld, float* 
     }
 }
 
+// out[plane][r][k] (plane 0 = hi, 1 = lo; row pitch ldo halfs, plane pitch `plane` halfs) = the split of
+// src[r][k] (transpose = 0) or src[k][r] (transpose = 1), scaled by the power of two derived from the per-block maxima --
+// the same derivation as in gemm2h_kernel, so the epilogue's 1/s matches.  Weights only: a few MB.
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ src, int rows, int cols, long ld, int transpose, const float* __restrict__ amax,
+                 __half* __restrict__ out, long ldo, long plane) {
+    __shared__ float s_s;
+    if (threadIdx.x < 32) {
+        float m = 0.f;
+        for (int i = threadIdx.x; i < H2_AMAX_SLOTS; i += 32) m = fmaxf(m, amax[i]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(PCNBR_FULL, m, d));
+        float s, inv;
+        h2_scale_of(m, s, inv);
+        if (threadIdx.x == 0) s_s = s;
+    }
+    __syncthreads();
+    const float s = s_s;
+    const long total = (long)rows * cols;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        // consecutive threads walk the SOURCE's inner dimension (coalesced reads; the scattered 2-byte writes of the
+        // transposed case stay in L2: the matrices are a few MB)
+        int r, k;
+        float v;
+        if (transpose) { k = (int)(i / rows); r = (int)(i - (long)k * rows); v = src[(long)k * ld + r]; }
+        else           { r = (int)(i / cols); k = (int)(i - (long)r * cols); v = src[(long)r * ld + k]; }
+        const float y = __fmul_rn(v, s);
+        const __half h = __float2half_rn(y);
+        const __half l = __float2half_rn(__fsub_rn(y, __half2float(h)));
+        out[(long)r * ldo + k] = h;
+        out[plane + (long)r * ldo + k] = l;
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
+
+// pre-split B: fp16 tensor (K, rows, 2 planes), box = 32 halfs x box_rows x 1 plane, 64-byte swizzle = the UMMA layout
+static int h2_make_map_split(CUtensorMap* map, const void* base, long K, long rows, long ldo, long plane, int box_rows) {
+    GmEncodeFn enc = gm_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, 2};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldo * 2, (cuuint64_t)plane * 2};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
 
 // fp32 matrix of `outer` rows x `inner` contiguous floats, box = 32 floats x box_rows, plain 128-byte swizzle (the
 // converters, not the MMA, read the landed tile); out-of-range elements read as 0
@@ -383,12 +442,12 @@ static int h2_make_map(CUtensorMap* map, const float* base, long inner, long out
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE>
 static int h2_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
                      int M, int N, int K, int splits, const float* bias, const float* amax_a, const float* amax_a2,
                      const float* amax_b, cudaStream_t s) {
     const size_t smem = (size_t)STAGES * (GM_SLAB + (size_t)BN * 128) + 2 * GM_SLAB + 64 * 8 + 64 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(gemm2h_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -399,21 +458,21 @@ static int h2_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split
     const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), flops = 2.0 * M * (double)N * K;
     const char* name = flops / 678.35e12 > bytes / 6551e9 ? "gemm2h_kernel[tensor]" : "gemm2h_kernel[hbm]";
     PCNBR_TIMED(name, s, bytes, flops,
-                (gemm2h_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias,
+                (gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias,
                                                                                       amax_a, amax_a2, amax_b)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool B_PRE>
 static int h2_dispatch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
                        int M, int N, int K, int splits, const float* bias, const float* amax_a, const float* amax_a2,
                        const float* amax_b, cudaStream_t s) {
     switch (gm_tile_n(M, N, K)) {                                            // stages: 48 / 32 / 24 / 20 KB each beside 32 KB of staging
-        case 256: return h2_launch<256, 4, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
-        case 128: return h2_launch<128, 5, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
-        case 64:  return h2_launch<64, 6, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
-        default:  return h2_launch<32, 6, A_MN, B_MN>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        case 256: return h2_launch<256, 4, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        case 128: return h2_launch<128, 5, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        case 64:  return h2_launch<64, 6, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+        default:  return h2_launch<32, 6, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
     }
 }
 
@@ -439,16 +498,36 @@ extern "C" int pcnbr_gemm2h_preferred(int M, int N, int K) {
     return flops / 678.35e12 > bytes / 6551e9 ? 1 : 0;
 }
 
+// Weights pre-split once for the forward (transpose = 0: B = W as stored, (rows, cols) = (N, K)) or the input-gradient GEMM
+// (transpose = 1: B[n][k] = W[k][n], src is (cols, rows) row-major): out = 2 planes (hi, lo) of `rows` rows with pitch ldo
+// halfs (a multiple of 8), `plane` halfs apart.  amax = pcnbr_absmax_f32 of the source.
+extern "C" int pcnbr_split_f16(const float* src, int rows, int cols, long ld, int transpose, const float* amax, void* out,
+                               long ldo, long plane, pcnbr_stream_t stream) {
+    if (!src || !amax || !out || rows <= 0 || cols <= 0 || ldo < cols || (ldo % 8) || plane < (long)rows * ldo || ((uintptr_t)out & 15))
+        return PCNBR_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long total = (long)rows * cols;
+    const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    PCNBR_TIMED("split_f16_kernel", s, 8.0 * (double)total, 0.0,
+                (split_f16_kernel<<<grid, 256, 0, s>>>(src, rows, cols, ld, transpose, amax, (__half*)out, ldo, plane)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
 // Same contract as pcnbr_gemm3x_ex_f32 (splits from pcnbr_gemm3x_splits, ws from pcnbr_gemm3x_ws_bytes) plus the
 // per-block maxima (pcnbr_amax_slots() floats each, from pcnbr_absmax_f32) of A, of A2 when given, and of B.
+// b_split != NULL: B is taken from the planes written by pcnbr_split_f16 (rows = N, cols = K; B / ldb / b_mn are ignored),
+// amax_b must be the array that call was given.
 extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
                                    int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
                                    size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
-                                   pcnbr_stream_t stream) {
-    if (!A || !B || !C || !amax_a || !amax_b || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
-    if ((lda % 4) || (ldb % 4) || (((uintptr_t)A | (uintptr_t)B) & 15)) return PCNBR_E_BADARG;
+                                   const void* b_split, long b_split_ld, long b_split_plane, pcnbr_stream_t stream) {
+    if (!A || (!B && !b_split) || !C || !amax_a || !amax_b || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
+    if ((lda % 4) || ((uintptr_t)A & 15)) return PCNBR_E_BADARG;
+    if (!b_split && ((ldb % 4) || ((uintptr_t)B & 15) || ldb < (b_mn ? N : K))) return PCNBR_E_BADARG;
+    if (b_split && ((b_split_ld % 8) || b_split_ld < K || ((uintptr_t)b_split & 15) || b_split_plane < (long)N * b_split_ld)) return PCNBR_E_BADARG;
     const int Ka = A2 ? K1 : K;
-    if (lda < (a_mn ? M : Ka) || ldb < (b_mn ? N : K)) return PCNBR_E_BADARG;
+    if (lda < (a_mn ? M : Ka)) return PCNBR_E_BADARG;
     if (A2 && (!amax_a2 || a_mn || K1 <= 0 || K1 >= K || (K1 % GM_BK) || (lda2 % 4) || ((uintptr_t)A2 & 15) || lda2 < K - K1)) return PCNBR_E_BADARG;
     if (ldc < N || (ldc % 4) || ((uintptr_t)C & 15)) return PCNBR_E_BADARG;
     if (splits > 1 && (!ws || ws_bytes < sizeof(float) * (size_t)splits * (size_t)M * (size_t)N)) return PCNBR_E_WORKSPACE;
@@ -463,7 +542,10 @@ extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const flo
     int rc = a_mn ? h2_make_map(&ta, A, M, K, lda, 32) : h2_make_map(&ta, A, Ka, M, lda, 128);
     if (!rc && A2) rc = h2_make_map(&ta2, A2, K - K1, M, lda2, 128);
     if (!A2) ta2 = ta;
-    if (!rc) rc = b_mn ? h2_make_map(&tb, B, N, K, ldb, 32) : h2_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128);
+    if (!rc) {
+        if (b_split) rc = h2_make_map_split(&tb, b_split, K, N, b_split_ld, b_split_plane, bn);
+        else         rc = b_mn ? h2_make_map(&tb, B, N, K, ldb, 32) : h2_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128);
+    }
     if (rc) return rc;
     const int kb_split = A2 ? K1 / GM_BK : (K + GM_BK - 1) / GM_BK;
     float* out = splits > 1 ? (float*)ws : C;
@@ -473,10 +555,16 @@ extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const flo
     rc = gm_make_map_c(&tc, out, M, N, splits > 1 ? N : ldc, splits);
     if (rc) return rc;
     const float* am2 = A2 ? amax_a2 : nullptr;
-    if (a_mn) rc = b_mn ? h2_dispatch<true, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
-                        : h2_dispatch<true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
-    else      rc = b_mn ? h2_dispatch<false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
-                        : h2_dispatch<false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+    if (b_split) {
+        rc = a_mn ? h2_dispatch<true, false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
+                  : h2_dispatch<false, false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+    } else if (a_mn) {
+        rc = b_mn ? h2_dispatch<true, true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
+                  : h2_dispatch<true, false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+    } else {
+        rc = b_mn ? h2_dispatch<false, true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
+                  : h2_dispatch<false, false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+    }
     if (rc) return rc;
     if (splits > 1) rc = gm_launch_reduce((const float*)ws, M, N, ldc, splits, C, s);
     return rc;

@@ -848,6 +848,18 @@ def _absmax(t: torch.Tensor):
     return out
 
 
+def _presplit(w: torch.Tensor, transpose: bool, amax: torch.Tensor) -> torch.Tensor:
+    """[hi | lo] fp16 planes (2, rows, pitch) of a weight matrix for the B operand of the fp16-split GEMM: w as stored
+    (forward GEMM: rows = Cout) or transposed (input-gradient GEMM: rows = Cin).  Written once per layer and pass instead of
+    being converted again by every CTA of the GEMM."""
+    rows, cols = (w.shape[1], w.shape[0]) if transpose else (w.shape[0], w.shape[1])
+    pitch = (cols + 7) // 8 * 8
+    out = torch.empty(2, rows, pitch, dtype=torch.float16, device=w.device)
+    _lib.call("pcnbr_split_f16", w.data_ptr(), rows, cols, w.stride(0), int(transpose), amax.data_ptr(), out.data_ptr(), pitch,
+              out.stride(0), _stream())
+    return out
+
+
 def _gemm_h2_wanted(M: int, N: int, K: int) -> bool:
     """The two-term fp16 kernel takes the GEMMs whose tensor-pipe bound exceeds their HBM bound (symmetric in M, N, K: the
     three GEMMs of a layer -- output, input gradient, weight gradient -- are classified alike)."""
@@ -855,13 +867,14 @@ def _gemm_h2_wanted(M: int, N: int, K: int) -> bool:
 
 
 def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=None, K1: int = 0, out=None,
-            amax_a=None, amax_b=None, amax_a2=None) -> torch.Tensor:
+            amax_a=None, amax_b=None, amax_a2=None, b_split=None) -> torch.Tensor:
     """C (M,N) = A (M,K) . B (N,K)^T (+ bias) on tcgen05 with fp32-grade accuracy: 3xTF32 from the fp32 operands, or -- for
     tensor-bound shapes -- the two-term fp16 split at twice the instruction rate (csrc/gemm_h2.cu; needs max |x| of each
     operand: amax_* = per-block maxima from _absmax, computed here when not handed in).
     a_mn / b_mn: the operand is stored transposed ((K,M) / (K,N) row-major).  Operands are 2-D, unit inner stride, any
     16-byte row pitch.  A2: A is the channel concatenation [A (M,K1) | A2 (M,K-K1)] (never materialised).  out: a
-    preallocated (M,N) view with unit inner stride (e.g. a column block of a wider matrix)."""
+    preallocated (M,N) view with unit inner stride (e.g. a column block of a wider matrix).  b_split: B pre-split by
+    _presplit (with the same amax_b), only used on the fp16 path."""
     splits = 1 if bias is not None else _lib.size("pcnbr_gemm3x_splits", M, N, K)
     nb = _lib.size("pcnbr_gemm3x_ws_bytes", M, N, K, splits)
     ws = _ws(nb, A.device)
@@ -876,7 +889,9 @@ def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=
             _lib.call("pcnbr_gemm2h_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
                       A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
                       bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0), splits, ws.data_ptr(), nb,
-                      amax_a.data_ptr(), amax_a2.data_ptr() if amax_a2 is not None else None, amax_b.data_ptr(), _stream())
+                      amax_a.data_ptr(), amax_a2.data_ptr() if amax_a2 is not None else None, amax_b.data_ptr(),
+                      b_split.data_ptr() if b_split is not None else None, b_split.stride(1) if b_split is not None else 0,
+                      b_split.stride(0) if b_split is not None else 0, _stream())
             return out
     _lib.call("pcnbr_gemm3x_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
               A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
@@ -900,6 +915,10 @@ def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None, amax_gy=None, amax_x=N
     return big.view(p, Cout, p, Cin).diagonal(dim1=0, dim2=2).sum(dim=-1)
 
 
+def _wsplit(w, transpose, amax_w):
+    return _presplit(w, transpose, amax_w) if amax_w is not None else None
+
+
 def _layer_amax(x, w, R, Cout, Cin):
     """(amax_x, amax_w) when the layer's GEMMs go to the fp16-split kernel (each tensor is scanned ONCE and the maxima are
     shared by the forward, input-gradient and weight-gradient GEMMs), else (None, None)."""
@@ -919,7 +938,7 @@ class _LinearRowsFn(torch.autograd.Function):
         ctx.has_bias = b is not None
         R, Cin = x.shape
         ctx.amax = _layer_amax(x, w, R, w.shape[0], Cin)
-        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1])
+        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
 
     @staticmethod
     def backward(ctx, gy):
@@ -929,7 +948,8 @@ class _LinearRowsFn(torch.autograd.Function):
         gy = _c(gy)
         ax, aw = ctx.amax
         ag = _absmax(gy) if ax is not None else None
-        dx = _gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None    # gy (R,Cout) . W (Cout,Cin)
+        dx = (_gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw))
+              if ctx.needs_input_grad[0] else None)                                                                     # gy (R,Cout) . W (Cout,Cin)
         dw = _wgrad3x(gy, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None                                # gy^T . x, split along R
         db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
@@ -947,7 +967,7 @@ class _LinearBnActFn(torch.autograd.Function):
         C = w.shape[0]
         dev = x.device
         ctx.amax = _layer_amax(x, w, R, C, Cin)
-        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1])
+        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -988,7 +1008,8 @@ class _LinearBnActFn(torch.autograd.Function):
                   dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         ax, aw = ctx.amax
         ag = _absmax(dh) if ax is not None else None
-        dx = _gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None
+        dx = (_gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw))
+              if ctx.needs_input_grad[0] else None)
         dw = _wgrad3x(dh, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
@@ -1009,7 +1030,7 @@ class _LinearBnActPoolFn(torch.autograd.Function):
         G = R // K
         dev = x.device
         ctx.amax = _layer_amax(x, w, R, C, Cin)
-        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1])
+        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -1050,7 +1071,8 @@ class _LinearBnActPoolFn(torch.autograd.Function):
                   dh.data_ptr(), _stream())
         ax, aw = ctx.amax
         ag = _absmax(dh) if ax is not None else None
-        dx = _gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None
+        dx = (_gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw))
+              if ctx.needs_input_grad[0] else None)
         dw = _wgrad3x(dh, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
@@ -1091,7 +1113,8 @@ class _LinearBnActCatFn(torch.autograd.Function):
             ctx.amax = (_absmax(x1), _absmax(x2), _absmax(w))
         else:
             ctx.amax = (None, None, None)
-        h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1, amax_a=ctx.amax[0], amax_a2=ctx.amax[1], amax_b=ctx.amax[2])
+        h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1, amax_a=ctx.amax[0], amax_a2=ctx.amax[1], amax_b=ctx.amax[2],
+                    b_split=_wsplit(w, False, ctx.amax[2]))
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -1134,8 +1157,11 @@ class _LinearBnActCatFn(torch.autograd.Function):
         # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
         a1, a2, aw = ctx.amax
         ag = _absmax(dh) if aw is not None else None                # one scan of dh serves the four GEMMs below
-        dx1 = _gemm3x(dh, False, w[:, :K1], True, R, K1, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[0] else None
-        dx2 = _gemm3x(dh, False, w[:, K1:], True, R, K2, C, amax_a=ag, amax_b=aw) if ctx.needs_input_grad[1] else None
+        wt = _wsplit(w, True, aw)                                     # (2, K1 + K2, C): the transposed weight, split once
+        dx1 = (_gemm3x(dh, False, w[:, :K1], True, R, K1, C, amax_a=ag, amax_b=aw, b_split=wt[:, :K1] if wt is not None else None)
+               if ctx.needs_input_grad[0] else None)
+        dx2 = (_gemm3x(dh, False, w[:, K1:], True, R, K2, C, amax_a=ag, amax_b=aw, b_split=wt[:, K1:] if wt is not None else None)
+               if ctx.needs_input_grad[1] else None)
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(w)

@@ -229,15 +229,21 @@ PCNBR_API int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* 
  * tensor-pipe time bound exceeds their HBM time bound (the wide DGCNN layers, models/dgcnn/dgcnn.py:95-126).
  * Each operand is scaled by a power of two that brings its largest element to [2^14, 2^15), split into hi + lo fp16 terms
  * inside the kernel (fp32 tiles arrive by TMA exactly as for pcnbr_gemm3x_ex_f32) and C = (hi.hi' + lo.hi' + hi.lo') / (s s').
+ * pcnbr_split_f16 pre-splits a weight matrix once ([hi | lo] fp16 planes, optionally transposed) so that the B operand of a
+ * forward / input-gradient GEMM needs no in-kernel conversion (b_split / b_split_ld / b_split_plane; NULL = convert B in
+ * the kernel like A).
  * pcnbr_absmax_f32 writes pcnbr_amax_slots() per-block maxima of |x| for a (rows x cols) matrix (row pitch ld; cols, ld
  * multiples of 4); pcnbr_gemm2h_ex_f32 takes those arrays for A, A2 (when given) and B.  Otherwise the contract --
  * operand layouts, split-K (pcnbr_gemm3x_splits / pcnbr_gemm3x_ws_bytes), bias, C pitch -- is that of pcnbr_gemm3x_ex_f32. */
 PCNBR_API int pcnbr_amax_slots(void);
 PCNBR_API int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, float* partial, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_gemm2h_preferred(int M, int N, int K);
+PCNBR_API int pcnbr_split_f16(const float* src, int rows, int cols, long ld, int transpose, const float* amax, void* out,
+                    long ldo, long plane, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
                     int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
-                    size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b, pcnbr_stream_t stream);
+                    size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
+                    const void* b_split, long b_split_ld, long b_split_plane, pcnbr_stream_t stream);
 /* Extended form.  A2 != NULL: A is the K-concatenation [A (M,K1) | A2 (M,K-K1)] of two row-major matrices (pitches lda,
  * lda2; K1 % 32 == 0, a_mn must be 0) -- a torch.cat along the channels in front of a convolution (dgcnn.py:147,
  * cat((x1..x4, x5)) -> conv6) that is never materialised.  ldc: row pitch of C (>= N, % 4 == 0), so a GEMM can write a
