@@ -61,15 +61,17 @@ class EdgeConv(nn.Module):
         # (SURVEY.md 8f-2).  fused=False runs the reference's op sequence literally on the K9/K6 kernels.
         self.fused = os.environ.get("PCNBR_EDGECONV_EXACT") is None and out_channels in (32, 64, 128, 256)
 
-    def forward(self, x):
+    def forward(self, x, _nbr=None):
+        """_nbr (internal): the layer's kNN table (ops.NeighborIndex) when it was computed ahead of time -- only the first
+        layer's graph depends on the input coordinates alone (DGCNN.prepare_geometry)."""
         if not self.fused:
-            x = get_graph_feature(x, k=self.k)
+            x = get_graph_feature(x, k=self.k, idx=_nbr.idx if _nbr is not None else None)
             x = self.conv(x)
             return ops.max_pool_neighbors(x, -1)
         conv, bn, act = self.conv[0], self.conv[1], self.conv[2]
         B, F, N = x.shape
         O = conv.out_channels
-        nbr = ops.NeighborIndex(ops.knn_graph(x, self.k), N)
+        nbr = _nbr if _nbr is not None else ops.NeighborIndex(ops.knn_graph(x, self.k), N)
         W = conv.weight.view(O, 2 * F)
         Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
         rows = _point_major(x)
@@ -146,6 +148,29 @@ def _run_pointwise_cat(seq, rows1: torch.Tensor, rows2: torch.Tensor) -> torch.T
     return y
 
 
+def _first_layer_graph(xyz: torch.Tensor, k: int, stream=None):
+    """The kNN table of the first EdgeConv (dgcnn.py:73-74 on the input coordinates) with its CSR inverse, as a list of
+    tensors [idx, offsets, perm] (+ a trailing keep-alive object): the only graph of the network that depends on the input
+    alone, so a training loop can compute it for the NEXT batch on the side stream (train.GraphedTrainStep).  stream: run
+    the kernels there, after the torch-side preparation on the current stream (the caller waits on it before use)."""
+    xc = xyz.contiguous()
+    if stream is not None:
+        stream.wait_event(torch.cuda.current_stream().record_event())
+    with (ops.on_stream(stream) if stream is not None else ops._NullCtx()):
+        nbr = ops.NeighborIndex(ops.knn_graph(xc, k), xc.shape[2])
+        off, perm, ws = nbr._build(ops._stream())
+    nbr._csr = (off, perm)
+    return [nbr.idx, off, perm, (nbr, ws, xc)]
+
+
+def _graph_from(geometry, n_src: int):
+    if geometry is None:
+        return None
+    nbr = ops.NeighborIndex(geometry[0], n_src)
+    nbr._csr = (geometry[1], geometry[2])
+    return nbr
+
+
 def _pointwise(cin, cout, dropout=None):
     layers = [nn.Conv1d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm1d(cout), nn.LeakyReLU(negative_slope=0.2)]
     if dropout is not None:
@@ -169,9 +194,12 @@ class DGCNN(nn.Module):
         self.conv7 = _pointwise(512, 256, dropout)
         self.conv8 = nn.Conv1d(256, num_classes, kernel_size=1)
 
-    def forward(self, x):
+    def prepare_geometry(self, x, stream=None):
+        return _first_layer_graph(x[:, :3, :] if x.size(1) == 6 else x, self.k, stream)
+
+    def forward(self, x, geometry=None):
         xyz = x[:, :3, :] if x.size(1) == 6 else x
-        x1 = self.conv1(xyz)
+        x1 = self.conv1(xyz, _nbr=_graph_from(geometry, xyz.shape[2]))
         x2 = self.conv2(x1)
         x3 = self.conv3(x2)
         x4 = self.conv4(x3)
@@ -200,10 +228,13 @@ class DGCNNWithColor(nn.Module):
         self.conv7 = _pointwise(512, 256, dropout)
         self.conv8 = nn.Conv1d(256, num_classes, kernel_size=1)
 
-    def forward(self, x):
+    def prepare_geometry(self, x, stream=None):
+        return _first_layer_graph(x[:, :3, :], self.k, stream)
+
+    def forward(self, x, geometry=None):
         if x.size(1) != 6:
             raise ValueError("DGCNNWithColor expects 6-channel input (xyz + rgb)")
-        x1 = self.conv1(x[:, :3, :])
+        x1 = self.conv1(x[:, :3, :], _nbr=_graph_from(geometry, x.shape[2]))
         x2 = self.conv2(x1)
         x3 = self.conv3(x2)
         x4 = self.conv4(x3)

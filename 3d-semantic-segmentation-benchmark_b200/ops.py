@@ -99,16 +99,18 @@ def _as_i32(idx: torch.Tensor) -> torch.Tensor:
 _AUX_STREAMS: dict = {}
 
 
-def aux_stream(device) -> torch.cuda.Stream:
+def aux_stream(device, which: int = 0) -> torch.cuda.Stream:
     """The side stream (one per device) on which index-only work runs concurrently with the feature path: CSR inverses
     (needed only by the backward) and, for PointNet++, the geometry of the deeper levels.  Work is launched on it by
     handing its handle to the C ABI; every buffer is allocated on the CURRENT stream beforehand and released only after
     the consumer has waited on the producing event, so no allocator stream bookkeeping is involved (CUDA-graph safe:
-    the side stream joins a capture through the event it waits on, and is joined back by the consumer's wait)."""
+    the side stream joins a capture through the event it waits on, and is joined back by the consumer's wait).
+    which = 1: a second side stream, used for the NEXT batch's geometry (train.GraphedTrainStep) so that it never queues
+    in front of work the current step is waiting for."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    st = _AUX_STREAMS.get(idx)
+    st = _AUX_STREAMS.get((idx, which))
     if st is None:
-        st = _AUX_STREAMS[idx] = torch.cuda.Stream(device=idx)
+        st = _AUX_STREAMS[(idx, which)] = torch.cuda.Stream(device=idx)
     return st
 
 
@@ -215,7 +217,11 @@ class PyramidGeometry:
     NeighborIndex is then a list, one per scale); starts = per-level first FPS picks or None (drawn here, level
     by level, exactly as the modules would: torch.randint(0, N_level, (B,), dtype=torch.int), common.py:22)."""
 
-    def __init__(self, coords0: torch.Tensor, sa, starts=None, interp_k: int = 3):
+    def __init__(self, coords0: torch.Tensor, sa, starts=None, interp_k: int = 3, inline: bool = False, stream=None):
+        """inline: run EVERYTHING on one stream -- `stream` (which first waits for the torch-side preparation done here on
+        the current stream) or the current stream -- and build the CSR inverse of every table right away: the form used to
+        compute the geometry of the NEXT batch on the side stream while the current step runs (train.GraphedTrainStep).
+        The caller orders its consumer after `stream` itself."""
         dev = coords0.device
         B = coords0.shape[0]
         coords0 = _c(coords0)
@@ -275,13 +281,17 @@ class PyramidGeometry:
             _lib.call("pcnbr_knn_direct_f32", query.data_ptr(), src.data_ptr(), Bc, M, Nc, k, idx.data_ptr(), d2.data_ptr(), _stream())
             return NeighborIndex(idx, Nc), d2
 
-        # level 1 on the current stream
+        # level 1 on the current stream (inline: on `stream`, after the preparation above)
+        side = stream if inline else None
+        if side is not None:
+            side.wait_event(torch.cuda.current_stream().record_event())
         C, r, K = sa[0]
-        self.coords.append(fps(coords0, C, draws[0]))
-        self.balls.append(ball(r, K, coords0, self.coords[1]))
+        with (on_stream(side) if side is not None else _NullCtx()):
+            self.coords.append(fps(coords0, C, draws[0]))
+            self.balls.append(ball(r, K, coords0, self.coords[1]))
         self.ball_events.append(None)
-        aux = aux_stream(dev) if _ASYNC_INDEX else None
-        if aux is not None:
+        aux = side if inline else (aux_stream(dev) if _ASYNC_INDEX else None)
+        if aux is not None and not inline:
             aux.wait_event(torch.cuda.current_stream().record_event())
         ctx = on_stream(aux) if aux is not None else _NullCtx()
         with ctx:
@@ -290,12 +300,52 @@ class PyramidGeometry:
                 src = self.coords[l]
                 self.coords.append(fps(src, C, draws[l]))
                 self.balls.append(ball(r, K, src, self.coords[l + 1]))
-                self.ball_events.append(self._mark(aux))
+                self.ball_events.append(self._mark(None if inline else aux))
             # decoder: level l features are interpolated from level l+1 (fine = l, coarse = l+1), deepest first
             self.knn, self.knn_events = {}, {}
             for l in range(len(sa) - 1, -1, -1):
                 self.knn[l] = knn3(self.coords[l], self.coords[l + 1], interp_k)
-                self.knn_events[l] = self._mark(aux)
+                self.knn_events[l] = self._mark(None if inline else aux)
+            if inline:
+                for nbr in self._tables():
+                    off, perm, ws = nbr._build(_stream())
+                    nbr._csr = (off, perm)
+                    self._keep.append(ws)
+
+    def _tables(self):
+        out = []
+        for b in self.balls:
+            out += b if isinstance(b, list) else [b]
+        return out + [self.knn[l][0] for l in sorted(self.knn)]
+
+    def export(self):
+        """Every tensor of the geometry as a flat list (fixed order), for copying into persistent buffers."""
+        t = list(self.coords[1:])
+        for nbr in self._tables():
+            t += [nbr.idx, nbr._csr[0], nbr._csr[1]]
+        t += [self.knn[l][1] for l in sorted(self.knn)]
+        return t
+
+    @classmethod
+    def from_export(cls, coords0: torch.Tensor, n_levels: int, tensors):
+        """Rebuild a ready-to-use geometry (single-scale levels, all tables with their CSR inverse) from export()'s list."""
+        self = cls.__new__(cls)
+        tensors = list(tensors)
+        self.coords = [_c(coords0)] + tensors[:n_levels]
+        pos = n_levels
+        tables = []
+        for i in range(2 * n_levels):
+            nsrc = self.coords[i].shape[1] if i < n_levels else self.coords[i - n_levels + 1].shape[1]
+            nbr = NeighborIndex(tensors[pos], nsrc)
+            nbr._csr = (tensors[pos + 1], tensors[pos + 2])
+            tables.append(nbr)
+            pos += 3
+        self.balls, self.ball_events = tables[:n_levels], [None] * n_levels
+        d2 = tensors[pos:pos + n_levels]
+        self.knn = {l: (tables[n_levels + l], d2[l]) for l in range(n_levels)}
+        self.knn_events = {l: None for l in range(n_levels)}
+        self._keep = []
+        return self
 
     @staticmethod
     def _mark(aux):

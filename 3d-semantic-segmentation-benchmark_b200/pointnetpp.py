@@ -23,14 +23,31 @@ class PointNetpp(nn.Module):
         self.drop = nn.Dropout(0.5)
         self.conv = nn.Conv1d(128, part_classes, 1)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes)."""
+    def prepare_geometry(self, x: torch.Tensor, stream=None):
+        """Every index of the network for the batch x (B,N,9) -- FPS picks, ball-query tables, the decoder's 3-NN tables and
+        the CSR inverses their backward kernels need -- as a flat list of tensors (ops.PyramidGeometry.export).  It depends
+        on the coordinates only, so a training loop can compute it for the NEXT batch on the side stream while the current
+        step runs (train.GraphedTrainStep(geometry_fn=...)) and hand it to forward(x, geometry=...).  stream: run the
+        kernels there (the caller waits on it before using the tensors)."""
+        sas = (self.sa1, self.sa2, self.sa3, self.sa4)
+        geo = ops.PyramidGeometry(x[:, :, :3], [(m.C, m.radius, m.K) for m in sas], [m.fps_start for m in sas], inline=True,
+                                  stream=stream)
+        out = geo.export()
+        out.append(geo)                                  # keeps the workspaces alive until the caller has copied the tensors
+        return out
+
+    def forward(self, x: torch.Tensor, geometry=None) -> torch.Tensor:
+        """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes).  geometry: prepare_geometry(x)'s tensors
+        (without the trailing keep-alive object) when they were computed ahead of time."""
         coords_0, features_0 = x[:, :, :3], x[:, :, 3:]
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
         # every index of the network depends on coordinates only: FPS / ball query of the deeper levels and the decoder's
         # 3-NN tables run on a side stream while the feature path of the shallower levels computes (same picks, same
         # generator consumption as calling sample() level by level)
-        geo = ops.PyramidGeometry(coords_0, [(m.C, m.radius, m.K) for m in sas], [m.fps_start for m in sas])
+        if geometry is not None:
+            geo = ops.PyramidGeometry.from_export(coords_0, 4, geometry)
+        else:
+            geo = ops.PyramidGeometry(coords_0, [(m.C, m.radius, m.K) for m in sas], [m.fps_start for m in sas])
         coords_1, features_1 = self.sa1(geo.coords[0], features_0, _geom=geo.level(0))
         coords_2, features_2 = self.sa2(coords_1, features_1, _geom=geo.level(1))
         coords_3, features_3 = self.sa3(coords_2, features_2, _geom=geo.level(2))

@@ -178,12 +178,26 @@ class GraphedTrainStep:
 
     Every libpcnbr entry point is capture-safe (asynchronous on the given stream, no host sync, workspaces come from
     torch's graph-private pool).  Inputs are copied into static buffers; the loss comes back as a static tensor.
-    """
+
+    geometry_fn (optional): `geometry_fn(model, *batch, stream=...)` -> list of tensors (+ trailing keep-alive objects) and
+    `forward_fn(model, *batch, geometry=tensors)` consumes them (PointNetpp / DGCNN.prepare_geometry: FPS picks, ball-query /
+    kNN tables and their CSR inverses depend on the input coordinates only).  The step is then software-pipelined over
+    two batches: a call hands in batch i+1, whose geometry is computed on the side stream while the captured step trains on
+    batch i (handed in by the previous call) -- FPS of a 4096-point cloud occupies one SM per cloud for 0.6 ms and no
+    longer sits at the head of the step.  __call__ therefore returns the loss of the PREVIOUS call's batch (the first
+    call trains on the example batch given at construction); flush() trains on the batch still in the pipeline."""
 
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, bucket: FlatGradBucket,
-                 forward_fn, example_batch, warmup: int = 3):
+                 forward_fn, example_batch, warmup: int = 3, geometry_fn=None):
         self.model, self.opt, self.bucket, self.forward_fn = model, optimizer, bucket, forward_fn
+        self.geometry_fn = geometry_fn
         self.static = [t.clone() for t in example_batch]
+        if geometry_fn is not None:
+            self.static_next = [t.clone() for t in example_batch]
+            first = [t for t in geometry_fn(model, *self.static_next) if isinstance(t, torch.Tensor)]
+            self.geo_next = [t.clone() for t in first]               # geometry of static_next (ready before a replay)
+            self.geo_cur = [t.clone() for t in first]                # geometry of static (read by the captured forward)
+            torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -197,16 +211,44 @@ class GraphedTrainStep:
 
     def _step_body(self):
         from . import ops
+        tmp = ev = None
+        if self.geometry_fn is not None:
+            torch._foreach_copy_(self.geo_cur, self.geo_next)       # the geometry of `static`, computed during the previous step
+            aux = ops.aux_stream(self.static[0].device, which=1)
+            tmp = self.geometry_fn(self.model, *self.static_next, stream=aux)      # next batch's geometry, side stream
+            ev = aux.record_event()
         self.bucket.zero()
-        loss = self.forward_fn(self.model, *self.static)
+        if self.geometry_fn is not None:
+            loss = self.forward_fn(self.model, *self.static, geometry=self.geo_cur)
+        else:
+            loss = self.forward_fn(self.model, *self.static)
         loss.backward()
         ops.join_aux()                                       # side-stream index work is consumed by the backward; belt and braces
         self.bucket.all_reduce_mean()
         self.opt.step()
+        if tmp is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            torch._foreach_copy_(self.geo_next, [t for t in tmp if isinstance(t, torch.Tensor)])
+            del tmp
         return loss.detach()
 
     def __call__(self, *batch):
-        for dst, src in zip(self.static, batch):
-            dst.copy_(src, non_blocking=True)
+        if self.geometry_fn is not None:
+            for cur, nxt in zip(self.static, self.static_next):
+                cur.copy_(nxt, non_blocking=True)            # the batch handed in by the previous call becomes current
+            for dst, src in zip(self.static_next, batch):
+                dst.copy_(src, non_blocking=True)
+        else:
+            for dst, src in zip(self.static, batch):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def flush(self):
+        """Train on the batch still in the pipeline (geometry_fn mode): replays once more with the same next batch."""
+        if self.geometry_fn is None:
+            return None
+        for cur, nxt in zip(self.static, self.static_next):
+            cur.copy_(nxt, non_blocking=True)
         self.graph.replay()
         return self.loss

@@ -133,9 +133,24 @@ def main():
         w = (torch.randn(Cout, Cin, generator=g) / Cin ** 0.5).to(dev)
         gy = torch.randn(R, Cout, generator=g).to(dev)
         sh = f"R={R} Cin={Cin} Cout={Cout}"
-        run("conv1x1 y=xW^T", sh, lambda: ops._gemm3x(x, False, w, False, R, Cout, Cin))
-        run("conv1x1 dx=gyW", sh, lambda: ops._gemm3x(gy, False, w, True, R, Cin, Cout))
-        run("conv1x1 dW=gy^Tx", sh, lambda: ops._gemm3x(gy, True, x, True, Cout, Cin, R))
+        # as the layer functions of ops.py issue them: on the fp16-split path every operand's absmax is scanned once per
+        # tensor and the weight is pre-split once per GEMM (absmax_kernel / split_f16_kernel rows)
+        h2 = ops._gemm_h2_wanted(R, Cout, Cin)
+
+        def fwd():
+            ax, aw = (ops._absmax(x), ops._absmax(w)) if h2 else (None, None)
+            return ops._gemm3x(x, False, w, False, R, Cout, Cin, amax_a=ax, amax_b=aw, b_split=ops._wsplit(w, False, aw))
+
+        def dgrad():
+            ag, aw = (ops._absmax(gy), ops._absmax(w)) if h2 else (None, None)
+            return ops._gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw, b_split=ops._wsplit(w, True, aw))
+
+        def wgrad():
+            ag, ax = (ops._absmax(gy), ops._absmax(x)) if h2 else (None, None)
+            return ops._gemm3x(gy, True, x, True, Cout, Cin, R, amax_a=ag, amax_b=ax)
+        run("conv1x1 y=xW^T", sh, fwd)
+        run("conv1x1 dx=gyW", sh, dgrad)
+        run("conv1x1 dW=gy^Tx", sh, wgrad)
         del x, w, gy
 
     # ---- the data formats either side of the path: packed block batches, sliding-window merge

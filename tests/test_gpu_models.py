@@ -285,3 +285,69 @@ def test_pointnext_parameter_gradients_vs_oracle_model(pkg, dev):
     pr, pr64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
     for k, p in net.named_parameters():
         _as_good_as_reference(p.grad, pr[k].grad, pr64[k].grad, f"grad {k}")
+
+
+# --------------------------------------------------------------------------- geometry computed ahead of time (side-stream prefetch)
+
+def test_precomputed_geometry_gives_identical_results(pkg, dev):
+    """forward(x, geometry=prepare_geometry(x)) == forward(x): the same kernels produce the indices, only earlier."""
+    pts, _, _ = O.s3dis_blocks(2, 2048, seed=4)
+    torch.manual_seed(1)
+    net = pkg.PointNetpp(13).to(dev)
+    net.drop.p = 0.0
+    st = torch.tensor([5, 9], dtype=torch.int32, device=dev)
+    for m in (net.sa1, net.sa2, net.sa3, net.sa4):
+        m.fps_start = st
+    x = pts.to(dev)
+    a = net(x)
+    a.square().sum().backward()
+    ga = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
+    geo = net.prepare_geometry(x, stream=pkg.ops.aux_stream(dev, which=1))
+    torch.cuda.current_stream().wait_stream(pkg.ops.aux_stream(dev, which=1))
+    b = net(x, geometry=[t for t in geo if isinstance(t, torch.Tensor)])
+    b.square().sum().backward()
+    assert torch.equal(a, b)
+    for k, p in net.named_parameters():
+        assert torch.equal(ga[k], p.grad), k
+    xd = pts[:, :, :6].transpose(1, 2).to(dev)
+    torch.manual_seed(2)
+    dg = pkg.DGCNNWithColor(13, k=20, emb_dims=64, dropout=0.0).to(dev)
+    la = dg(xd)[0]
+    g = dg.prepare_geometry(xd)
+    lb = dg(xd, geometry=[t for t in g if isinstance(t, torch.Tensor)])[0]
+    assert torch.equal(la, lb)
+
+
+@pytest.mark.parametrize("model", ["pointnetpp", "dgcnn"])
+def test_pipelined_graphed_step_matches_plain_graphed_step(pkg, dev, model):
+    """train.GraphedTrainStep(geometry_fn=...): a call trains on the PREVIOUS call's batch with the geometry that was
+    computed on the side stream meanwhile -- the loss sequence equals the unpipelined captured step's on the same batches."""
+    N, B = 1024, 2
+    batches = [tuple(t.to(dev) for t in pkg.synthetic.s3dis_blocks(B, N, seed=s)) for s in range(4)]
+    inp = (lambda p: p[:, :, :6].transpose(1, 2)) if model == "dgcnn" else (lambda p: p)
+
+    def build():
+        torch.manual_seed(3)
+        if model == "dgcnn":
+            net = pkg.DGCNNWithColor(13, k=20, emb_dims=64, dropout=0.0).to(dev)
+        else:
+            net = pkg.PointNetpp(13).to(dev)
+            net.drop.p = 0.0
+            for m in (net.sa1, net.sa2, net.sa3, net.sa4):
+                m.fps_start = torch.tensor([1, 2], dtype=torch.int32, device=dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True, fused=True)
+        return net, opt, pkg.train.FlatGradBucket(net, steal_grads=True)
+
+    def loss_of(m, pts, lab, lens, geometry=None):
+        out = m(inp(pts), geometry=geometry) if geometry is not None else m(inp(pts))
+        return pkg.train.masked_onehot_cross_entropy(out[0] if isinstance(out, tuple) else out, lab, lens)
+
+    net, opt, bucket = build()
+    plain = pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, batches[0], warmup=0)
+    want = [float(plain(*b)) for b in batches]
+    net, opt, bucket = build()
+    geo_fn = lambda m, pts, lab, lens, stream=None: m.prepare_geometry(inp(pts), stream=stream)
+    piped = pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, batches[0], warmup=0, geometry_fn=geo_fn)
+    got = [float(piped(*b)) for b in batches[1:]] + [float(piped.flush())]
+    assert got == want, (got, want)
