@@ -494,10 +494,12 @@ extern "C" int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, f
 // 1 when the two-term fp16 kernel should take this GEMM: its tensor-pipe time at the TF32 rate (what the 3xTF32 kernel is
 // tied to, three instructions per product) reaches 60 % of its HBM time bound -- from there on the 3xTF32 kernel is
 // limited by instruction issue, not by bytes (measured: 65536 x 512 -> 256 runs at 0.30 of either bound on it), and the
-// extra absmax scan of the activations (one read) costs less than the halved issue time saves.
+// extra absmax scan of the activations (one read) costs less than the halved issue time saves.  GEMMs below 10 GFLOP stay
+// on the 3xTF32 kernel whatever their ratio: they are launch / pipeline-fill bound and the three extra launches (two
+// absmax scans, one weight split) cost more than they save (measured on the PointNet++ decoder layers: +0.37 ms per step).
 extern "C" int pcnbr_gemm2h_preferred(int M, int N, int K) {
     const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N), flops = 2.0 * M * (double)N * K;
-    return flops / 678.35e12 > 0.6 * (bytes / 6551e9) ? 1 : 0;
+    return (flops / 678.35e12 > 0.6 * (bytes / 6551e9) && flops >= 1.0e10) ? 1 : 0;
 }
 
 // Weights pre-split once for the forward (transpose = 0: B = W as stored, (rows, cols) = (N, K)) or the input-gradient GEMM

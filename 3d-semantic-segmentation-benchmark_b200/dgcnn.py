@@ -156,11 +156,12 @@ def _first_layer_graph(xyz: torch.Tensor, k: int, stream=None):
     xc = xyz.contiguous()
     if stream is not None:
         stream.wait_event(torch.cuda.current_stream().record_event())
+    keep = [xc]
     with (ops.on_stream(stream) if stream is not None else ops._NullCtx()):
-        nbr = ops.NeighborIndex(ops.knn_graph(xc, k), xc.shape[2])
+        nbr = ops.NeighborIndex(ops.knn_graph(xc, k, _keep=keep), xc.shape[2])
         off, perm, ws = nbr._build(ops._stream())
     nbr._csr = (off, perm)
-    return [nbr.idx, off, perm, (nbr, ws, xc)]
+    return [nbr.idx, off, perm, (nbr, ws, keep)]
 
 
 def _graph_from(geometry, n_src: int):

@@ -268,7 +268,7 @@ class PyramidGeometry:
             if K > Nc:
                 raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={Nc})")
             idx = torch.empty(Bc, M, K, dtype=torch.int32, device=dev)
-            _lib.call("pcnbr_ball_query_f32", cen.data_ptr(), src.data_ptr(), Bc, M, Nc, _r2(r), K, idx.data_ptr(), _stream())
+            _ball_query_into(cen, src, Bc, M, Nc, _r2(r), K, idx, self._keep)
             return NeighborIndex(idx, Nc)
 
         def knn3(query, src, k):
@@ -278,7 +278,7 @@ class PyramidGeometry:
                 raise RuntimeError(f"pcnbr: selected index k out of range (k={k} > N={Nc})")
             idx = torch.empty(Bc, M, k, dtype=torch.int32, device=dev)
             d2 = torch.empty(Bc, M, k, dtype=torch.float32, device=dev)
-            _lib.call("pcnbr_knn_direct_f32", query.data_ptr(), src.data_ptr(), Bc, M, Nc, k, idx.data_ptr(), d2.data_ptr(), _stream())
+            _knn_direct_into(query, src, Bc, M, Nc, k, idx, d2, self._keep)
             return NeighborIndex(idx, Nc), d2
 
         # level 1 on the current stream (inline: on `stream`, after the preparation above)
@@ -421,6 +421,35 @@ def farthest_point_sample(xyz: torch.Tensor, C: int, start_idx: torch.Tensor | N
     return (idx, out) if return_coords else idx
 
 
+_NO_GRID = __import__("os").environ.get("PCNBR_NO_GRID") is not None      # A/B switch: always the brute-force M x N scan
+
+
+def _ball_query_into(q, p, B, M, N, r2, K, idx, keep=None):
+    """Single-radius ball query into a preallocated table: the cell grid (csrc/grid.cu) for clouds of >= 2048 points, the
+    M x N scan below that (identical tables).  keep: list that takes the workspace when the launch goes to a side stream."""
+    if N >= 2048 and not _NO_GRID:
+        nb = _lib.size("pcnbr_grid_ws_bytes", B, N)
+        ws = _ws(nb, p.device)
+        if keep is not None:
+            keep.append(ws)
+        _lib.call("pcnbr_ball_query_grid_f32", q.data_ptr(), p.data_ptr(), B, M, N, r2, K, idx.data_ptr(), ws.data_ptr(), nb, _stream())
+    else:
+        _lib.call("pcnbr_ball_query_f32", q.data_ptr(), p.data_ptr(), B, M, N, r2, K, idx.data_ptr(), _stream())
+
+
+def _knn_direct_into(q, p, B, M, N, k, idx, d2, keep=None):
+    """k nearest sources (direct distances) into preallocated tables: cell grid with ring search when the scan would be
+    large (>= 512 sources, >= 2^20 pairs per cloud, k <= 32), else the M x N scan (identical tables)."""
+    if N >= 512 and M * N >= (1 << 20) and k <= 32 and not _NO_GRID:
+        nb = _lib.size("pcnbr_grid_ws_bytes", B, N)
+        ws = _ws(nb, p.device)
+        if keep is not None:
+            keep.append(ws)
+        _lib.call("pcnbr_knn_direct_grid_f32", q.data_ptr(), p.data_ptr(), B, M, N, k, idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), nb, _stream())
+    else:
+        _lib.call("pcnbr_knn_direct_f32", q.data_ptr(), p.data_ptr(), B, M, N, k, idx.data_ptr(), d2.data_ptr(), _stream())
+
+
 def _r2(r: float) -> float:
     # the reference compares fp32 distances with the python double r**2 -> fp32(double(r)**2)
     return torch.tensor(float(r) ** 2, dtype=torch.float32).item()
@@ -440,8 +469,7 @@ def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
         raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={N})")   # torch.topk's error
     xyz, new_xyz = _c(xyz), _c(new_xyz)
     idx = torch.empty(B, M, K, dtype=torch.int32, device=xyz.device)
-    _lib.call("pcnbr_ball_query_f32", new_xyz.data_ptr(), xyz.data_ptr(), B, M, N, _r2(radius), K,
-              idx.data_ptr(), _stream())
+    _ball_query_into(new_xyz, xyz, B, M, N, _r2(radius), K, idx)
     return idx
 
 
@@ -483,12 +511,11 @@ def knn_points(query: torch.Tensor, src: torch.Tensor, k: int):
     query, src = _c(query), _c(src)
     idx = torch.empty(B, M, k, dtype=torch.int32, device=src.device)
     d2 = torch.empty(B, M, k, dtype=torch.float32, device=src.device)
-    _lib.call("pcnbr_knn_direct_f32", query.data_ptr(), src.data_ptr(), B, M, N, k, idx.data_ptr(),
-              d2.data_ptr(), _stream())
+    _knn_direct_into(query, src, B, M, N, k, idx, d2)
     return idx, d2
 
 
-def knn_graph(x: torch.Tensor, k: int) -> torch.Tensor:
+def knn_graph(x: torch.Tensor, k: int, _keep: list | None = None) -> torch.Tensor:
     """K3/K4 (expanded form).  x (B,F,N) in any (F,N) layout -> idx (B,N,k) int32: the k largest
     -xx_j + 2 x_i.x_j - xx_i per row, i.e. models/dgcnn/dgcnn.py:16-20 with lowest index on ties."""
     _check(x, "x")
@@ -507,6 +534,8 @@ def knn_graph(x: torch.Tensor, k: int) -> torch.Tensor:
     ws = _ws(nb, x.device)
     _lib.call("pcnbr_knn_expand_f32", x.data_ptr(), B, F, N, sf, sn, k, idx.data_ptr(), ws.data_ptr(), nb, _stream(),
               tag=f"[F={F}]")
+    if _keep is not None:                # launched on a side stream (on_stream): the caller keeps the workspace and the input
+        _keep += [ws, x]                 # alive until it has waited for that stream
     return idx
 
 

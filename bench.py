@@ -416,6 +416,15 @@ class Harness:
         geo_fn = None
         if model in ("dgcnn", "pointnetpp") and not args.no_prefetch and not args.no_graph:
             geo_fn = lambda m, pts, lab, lens, stream=None: m.prepare_geometry(model_input(model, pts), stream=stream)
+            if os.environ.get("PCNBR_FAKE_PREFETCH"):            # diagnostic only: geometry computed once, never again (an INVALID
+                cache = {}                                         # measurement: shows the step time with no geometry work at all)
+
+                def geo_fn(m, pts, lab, lens, stream=None, _real=geo_fn):
+                    if "g" not in cache:
+                        cache["g"] = _real(m, pts, lab, lens, stream=stream)
+                    elif stream is not None:
+                        stream.wait_event(torch.cuda.current_stream().record_event())     # keep the fork / join structure
+                    return cache["g"]
 
         def eager_step(pts, lab, lens):
             bucket.zero()

@@ -65,6 +65,17 @@ PCNBR_API int pcnbr_ball_query_f32(const float* q, const float* p, int B, int M,
 PCNBR_API int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M, int N, int K,
                          int32_t* idx, float* d2, pcnbr_stream_t stream);
 
+/* ---- K2 / K3 on a uniform cell grid (csrc/grid.cu): the same tables as pcnbr_ball_query_f32 / pcnbr_knn_direct_f32 (k <= 32),
+ * bit for bit, without the M x N scan: every cloud is binned once into cells of edge >= 1.001 r (ball query) or ~2 points
+ * per cell (k-NN), a query reads the 27 cells around it (k-NN: rings of cells until the k-th distance is inside the
+ * scanned cube), and under-filled balls are padded from the member list (lowest indices not in the ball).
+ * ws: pcnbr_grid_ws_bytes(B, N) with N = number of SOURCE points per cloud. */
+PCNBR_API size_t pcnbr_grid_ws_bytes(int B, int N);
+PCNBR_API int pcnbr_ball_query_grid_f32(const float* q, const float* p, int B, int M, int N, float r2, int K, int32_t* idx,
+                    void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_knn_direct_grid_f32(const float* q, const float* p, int B, int M, int N, int K, int32_t* idx, float* d2,
+                    void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
 /* Multi-radius ball query ("MSG": several group() calls on ONE centroid set with different (r, K); BASELINE configs[2]).
  * Each idx[i] (B,M,K[i]) is bit-identical to pcnbr_ball_query_f32(q, p, .., r2[i], K[i], idx[i]), but the points are
  * scanned once: one selection with the largest radius and the largest K, the other scales are derived from its sorted

@@ -146,3 +146,81 @@ def test_large_goldens_from_reference(pkg, dev, golden):
     h = golden("interp_8k")
     up = pkg.common.interpolate(h["points"].to(dev), p.to(dev), g["centroids"].to(dev)).cpu()
     assert torch.equal(up[:, :512], h["out_first"]) and torch.equal(up.double().sum(dim=1), h["out_sum"])
+
+
+# --------------------------------------------------------------------------- cell-grid selection == M x N scan (csrc/grid.cu)
+
+def _brute_ball(pkg, q, p, r, K):
+    B, M, N = q.shape[0], q.shape[1], p.shape[1]
+    idx = torch.empty(B, M, K, dtype=torch.int32, device=q.device)
+    pkg._lib.call("pcnbr_ball_query_f32", q.data_ptr(), p.data_ptr(), B, M, N, pkg.ops._r2(r), K, idx.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
+    return idx
+
+
+def _grid_ball(pkg, q, p, r, K):
+    B, M, N = q.shape[0], q.shape[1], p.shape[1]
+    idx = torch.empty(B, M, K, dtype=torch.int32, device=q.device)
+    nb = pkg._lib.size("pcnbr_grid_ws_bytes", B, N)
+    ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
+    pkg._lib.call("pcnbr_ball_query_grid_f32", q.data_ptr(), p.data_ptr(), B, M, N, pkg.ops._r2(r), K, idx.data_ptr(), ws.data_ptr(), nb,
+                  torch.cuda.current_stream().cuda_stream)
+    return idx
+
+
+def _knn_both(pkg, q, p, k):
+    B, M, N = q.shape[0], q.shape[1], p.shape[1]
+    out = []
+    for name in ("pcnbr_knn_direct_f32", "pcnbr_knn_direct_grid_f32"):
+        idx = torch.empty(B, M, k, dtype=torch.int32, device=q.device)
+        d2 = torch.empty(B, M, k, dtype=torch.float32, device=q.device)
+        if name.endswith("grid_f32"):
+            nb = pkg._lib.size("pcnbr_grid_ws_bytes", B, N)
+            ws = torch.empty(nb, dtype=torch.uint8, device=q.device)
+            pkg._lib.call(name, q.data_ptr(), p.data_ptr(), B, M, N, k, idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), nb,
+                          torch.cuda.current_stream().cuda_stream)
+        else:
+            pkg._lib.call(name, q.data_ptr(), p.data_ptr(), B, M, N, k, idx.data_ptr(), d2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        out.append((idx, d2))
+    return out
+
+
+def _clouds(kind, B, N, seed):
+    g = _gen(seed)
+    if kind == "block":                       # S3DIS-shaped block at a room offset
+        return _chunk(B, N, seed)
+    if kind == "flat":                        # a wall: zero extent along y
+        p = _chunk(B, N, seed)
+        p[:, :, 1] = 7.25
+        return p
+    if kind == "lattice":                     # exact ties in d2, duplicated points
+        p = torch.randint(-40, 41, (B, N, 3), generator=g).float() / 64
+        p[:, N // 2:] = p[:, : N - N // 2]
+        return p
+    if kind == "clustered":                   # 90 % of the points in 1 % of the volume
+        p = torch.rand(B, N, 3, generator=g)
+        p[:, : int(0.9 * N)] = p[:, : int(0.9 * N)] * 0.05 + 0.4
+        return p
+    if kind == "point":                       # every point identical
+        return torch.full((B, N, 3), 1.5)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["block", "flat", "lattice", "clustered", "point"])
+@pytest.mark.parametrize("N,M,r,K", [(4096, 1024, 0.1, 32), (2500, 300, 0.2, 16), (5000, 64, 0.05, 64), (3000, 100, 0.3, 100)])
+def test_grid_ball_query_equals_brute_force(pkg, dev, kind, N, M, r, K):
+    p = _clouds(kind, 2, N, seed=N + M).to(dev)
+    q = p[:, torch.randperm(N, generator=_gen(1))[:M]].contiguous()
+    q[:, : M // 8] += 0.37                      # some queries off the points, a few outside the bounding box
+    q[:, 0] = torch.tensor([-50.0, 80.0, 3.0], device=dev)
+    assert torch.equal(_grid_ball(pkg, q, p, r, K), _brute_ball(pkg, q, p, r, K))
+
+
+@pytest.mark.parametrize("kind", ["block", "flat", "lattice", "clustered", "point"])
+@pytest.mark.parametrize("N,M,k", [(1024, 4096, 3), (600, 2000, 8), (4096, 1000, 20), (700, 300, 32), (50, 64, 3)])
+def test_grid_knn_equals_brute_force(pkg, dev, kind, N, M, k):
+    p = _clouds(kind, 2, N, seed=N + k).to(dev)
+    q = _clouds(kind, 2, M, seed=M + k + 1).to(dev)
+    q[:, 0] = torch.tensor([-50.0, 80.0, 3.0], device=dev)
+    (bi, bd), (gi, gd) = _knn_both(pkg, q, p, k)
+    assert torch.equal(gi, bi) and torch.equal(gd, bd)
