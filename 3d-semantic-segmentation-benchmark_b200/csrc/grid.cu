@@ -65,18 +65,27 @@ grid_bbox_kernel(const float* __restrict__ p, int N, float h_req, float ppc, Gri
             h = cbrtf(ex * ey * ez * ppc / (float)N);
         }
         h = fmaxf(h, emax / (float)(GRID_DIM_CAP - 1));
-        int nx, ny, nz;
-        for (;;) {
-            nx = (int)(ext[0] / h) + 1; ny = (int)(ext[1] / h) + 1; nz = (int)(ext[2] / h) + 1;
+        if (!(h > 0.f) || !(h < 3.0e38f)) h = 1.0f;             // non-finite coordinates: one cell, every query scans everything
+        int nx = 1, ny = 1, nz = 1;
+        for (int it = 0; it < 200; ++it) {
+            nx = (int)fminf(ext[0] / h, (float)GRID_DIM_CAP) + 1; ny = (int)fminf(ext[1] / h, (float)GRID_DIM_CAP) + 1;
+            nz = (int)fminf(ext[2] / h, (float)GRID_DIM_CAP) + 1;
             if ((long)nx * ny * nz <= GRID_CELL_CAP) break;
             h *= 1.25f;
         }
+        if ((long)nx * ny * nz > GRID_CELL_CAP) { nx = ny = nz = 1; h = 3.0e37f; }
         g.h = h; g.inv_h = 1.0f / h; g.nx = nx; g.ny = ny; g.nz = nz; g.ncell = nx * ny * nz;
         gp[b] = g;
     }
 }
 
-__device__ __forceinline__ int grid_coord(float x, float o, float inv_h) { return (int)floorf((x - o) * inv_h); }
+// cell coordinate along one axis, clamped to [-1, n] BEFORE the conversion to int (a query far outside the bounding box, or
+// a degenerate cloud with a tiny cell edge, would overflow the conversion): -1 / n mean "outside, below / above the grid",
+// which is all the consumers need (no point lives there)
+__device__ __forceinline__ int grid_coord(float x, float o, float inv_h, int n) {
+    const float t = floorf((x - o) * inv_h);
+    return (int)fminf(fmaxf(t, -1.0f), (float)n);
+}
 __device__ __forceinline__ int grid_clamp(int c, int n) { return c < 0 ? 0 : (c >= n ? n - 1 : c); }
 
 // cell of every point (clamped into the grid) + per-cell counts (integer atomics: the counts do not depend on the order)
@@ -87,8 +96,8 @@ grid_count_kernel(const float* __restrict__ p, int N, const GridParams* __restri
     if (n >= N) return;
     const GridParams g = gp[b];
     const float* __restrict__ s = p + ((size_t)b * N + n) * 3;
-    const int cx = grid_clamp(grid_coord(s[0], g.ox, g.inv_h), g.nx), cy = grid_clamp(grid_coord(s[1], g.oy, g.inv_h), g.ny),
-              cz = grid_clamp(grid_coord(s[2], g.oz, g.inv_h), g.nz);
+    const int cx = grid_clamp(grid_coord(s[0], g.ox, g.inv_h, g.nx), g.nx), cy = grid_clamp(grid_coord(s[1], g.oy, g.inv_h, g.ny), g.ny),
+              cz = grid_clamp(grid_coord(s[2], g.oz, g.inv_h, g.nz), g.nz);
     const int c = (cz * g.ny + cy) * g.nx + cx;
     cellid[(size_t)b * N + n] = c;
     atomicAdd(&count[(size_t)b * (GRID_CELL_CAP + 1) + c], 1);
@@ -184,7 +193,7 @@ ball_grid_kernel(const float* __restrict__ q, int M, int N, float r2, int K, con
     const float qx = c[0], qy = c[1], qz = c[2];
     const int32_t* __restrict__ st = start + (size_t)b * (GRID_CELL_CAP + 1);
     const float4* __restrict__ pts = sorted + (size_t)b * N;
-    const int cx = grid_coord(qx, g.ox, g.inv_h), cy = grid_coord(qy, g.oy, g.inv_h), cz = grid_coord(qz, g.oz, g.inv_h);
+    const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
     WarpList<NSLOT> list;
     list.init();
     u64 thr = PCNBR_KEY_MAX;
@@ -230,12 +239,13 @@ knn_grid_kernel(const float* __restrict__ q, int M, int N, int K, const GridPara
     const float qx = c[0], qy = c[1], qz = c[2];
     const int32_t* __restrict__ st = start + (size_t)b * (GRID_CELL_CAP + 1);
     const float4* __restrict__ pts = sorted + (size_t)b * N;
-    const int cx = grid_coord(qx, g.ox, g.inv_h), cy = grid_coord(qy, g.oy, g.inv_h), cz = grid_coord(qz, g.oz, g.inv_h);
+    const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
     WarpList<1> list;
     list.init();
     u64 thr = PCNBR_KEY_MAX;
     const float slack = 2e-3f * g.h;                    // cells are assigned with fp32 rounding: shrink the safe margin
-    for (int R = 0;; ++R) {
+    const int rmax = max(g.nx, max(g.ny, g.nz)) + 2;   // the query cell is within [-1, n]: the cube covers the grid by then
+    for (int R = 0; R <= rmax; ++R) {
         // shell R: cells with max(|dx|, |dy|, |dz|) == R, clipped to the grid
         for (int z = max(cz - R, 0); z <= min(cz + R, g.nz - 1); ++z)
             for (int y = max(cy - R, 0); y <= min(cy + R, g.ny - 1); ++y) {
