@@ -128,7 +128,6 @@ def test_gemm_fp16_split_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K, scal
     """csrc/gemm_h2.cu (two-term fp16 split on kind::f16, per-tensor power-of-two scales from pcnbr_absmax_f32): K-major and
     MN-major operands (transposed by the in-kernel converters), ragged sizes, split-K, operands far outside fp16's range,
     wide dynamic range inside one operand -- all against float64 at the 3xTF32 kernel's bar."""
-    assert pkg._lib.size("pcnbr_gemm2h_preferred", M, N, K) == 1
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A = (torch.randn(M, K, generator=g) + 0.25) * scale_a
     Bm = (torch.randn(N, K, generator=g) - 0.1) * scale_b
@@ -139,7 +138,7 @@ def test_gemm_fp16_split_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K, scal
     Bmm = pad(Bm.t().contiguous() if b_mn else Bm).to(dev)
     pkg._lib.prof_enable(True)
     pkg._lib.prof_collect()
-    out = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K)
+    out = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K, force_h2=True)
     ran = pkg._lib.prof_collect()
     pkg._lib.prof_enable(False)
     assert any(k.startswith("gemm2h_kernel") for k in ran) and "absmax_kernel" in ran, sorted(ran)
@@ -152,12 +151,12 @@ def test_gemm_fp16_split_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K, scal
     rel = ((out.cpu().double() - ref).abs() / (bound + 1e-300)).max().item()
     print(f"gemm2h M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn}: max |err| / sum|a||b| = {rel:.3e}")
     assert rel <= 4e-6, f"max error / sum|a||b| = {rel:.3e}"
-    assert torch.equal(out, pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K))
+    assert torch.equal(out, pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K, force_h2=True))
     # B pre-split once (pcnbr_split_f16, the weight path of the layers): the same products, bit for bit
     amax_b = pkg.ops._absmax(Bmm)
     bs = pkg.ops._presplit(Bmm, b_mn, amax_b)
     assert bs.shape[:2] == (2, N)
-    out2 = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K, amax_b=amax_b, b_split=bs)
+    out2 = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K, amax_b=amax_b, b_split=bs, force_h2=True)
     assert torch.equal(out2, out)
 
 
@@ -168,10 +167,10 @@ def test_gemm_fp16_split_concatenated_input_and_degenerate_operands(pkg, dev):
     A1, A2 = torch.randn(M, K1, generator=g) * 30.0, torch.randn(M, K2, generator=g) * 0.02
     W = torch.randn(N, K1 + K2, generator=g) / 40.0
     b = torch.randn(N, generator=g)
-    out = pkg.ops._gemm3x(A1.to(dev), False, W.to(dev), False, M, N, K1 + K2, b.to(dev), A2=A2.to(dev), K1=K1)
+    out = pkg.ops._gemm3x(A1.to(dev), False, W.to(dev), False, M, N, K1 + K2, b.to(dev), A2=A2.to(dev), K1=K1, force_h2=True)
     ref = torch.cat((A1, A2), 1).double() @ W.double().t() + b.double()
     _close(out, ref, 3e-5)
-    z = pkg.ops._gemm3x(torch.zeros(M, K1 + K2, device=dev), False, W.to(dev), False, M, N, K1 + K2)
+    z = pkg.ops._gemm3x(torch.zeros(M, K1 + K2, device=dev), False, W.to(dev), False, M, N, K1 + K2, force_h2=True)
     assert float(z.abs().max()) == 0.0
 
 
