@@ -51,10 +51,10 @@ PROTOTYPES = {
     "pcnbr_bn_blocks": (_I, [_L, _I]),
     "pcnbr_bn_stats_f32": (_I, [_P, _L, _I, _P, _P]),
     "pcnbr_bn_finalize_f32": (_I, [_P, _I, _P, _D, _I, _P, _P, _F, _F, _P, _P, _P, _P]),
-    "pcnbr_bn_act_fwd_f32": (_I, [_P, _L, _P, _L, _L, _I, _P, _F, _P, _P, _F, _P]),
+    "pcnbr_bn_act_fwd_f32": (_I, [_P, _L, _P, _L, _L, _I, _P, _F, _P, _P, _F, _P, _P]),
     "pcnbr_bn_act_bwd_reduce_f32": (_I, [_P, _P, _L, _P, _L, _L, _I, _P, _F, _P, _P, _P, _F, _P]),
     "pcnbr_bn_bwd_finalize_f32": (_I, [_P, _I, _P, _D, _I, _I, _P, _P, _P, _P]),
-    "pcnbr_bn_act_bwd_apply_f32": (_I, [_P, _P, _L, _I, _P, _P, _F, _P, _P, _F, _P]),
+    "pcnbr_bn_act_bwd_apply_f32": (_I, [_P, _P, _L, _I, _P, _P, _F, _P, _P, _F, _P, _P]),
     "pcnbr_pool_bn_act_fwd_f32": (_I, [_P, _L, _I, _I, _P, _F, _P, _P, _P, _P]),
     "pcnbr_pool_bn_bwd_apply_f32": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P]),
     "pcnbr_gemm3x_splits": (_I, [_I, _I, _I]),

@@ -177,6 +177,27 @@ bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __r
     stats[3 * C + c] = beta ? beta[c] : 0.f;
 }
 
+// Per-block maximum of |value written| for the fp16-split GEMM that consumes this kernel's output (gemm_h2.cu): slot
+// blockIdx.x of `amax` (PCNBR_AMAX_SLOTS floats) takes the block's maximum, the slots no block owns are zeroed -- the
+// consumer reduces all slots, so no separate absmax pass over the tensor is needed.
+constexpr int BA_AMAX_SLOTS = 1280;
+__device__ __forceinline__ void ba_store_amax(float mx, float* __restrict__ amax) {
+    __shared__ float s_mx[BA_T / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PCNBR_FULL, mx, d));
+    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < BA_T / 32; ++w) mx = fmaxf(mx, s_mx[w]);
+        amax[blockIdx.x] = mx;
+        for (int i = blockIdx.x + gridDim.x; i < BA_AMAX_SLOTS; i += gridDim.x) amax[i] = 0.f;
+    }
+}
+__device__ __forceinline__ float ba_amax4(float m, const float4& o) {
+    return fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+}
+
 __device__ __forceinline__ float ba_act(float x, float mean, float scale, float beta, float slope) {
     const float y = fmaf(x - mean, scale, beta);
     return y > 0.f ? y : y * slope;
@@ -206,8 +227,9 @@ template <int NCOL>
 __global__ void __launch_bounds__(BA_T)
 bn_act_fwd_kernel(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb, long R, int C,
                   const float* __restrict__ stats, float slope, float* __restrict__ y,
-                  const unsigned long long* __restrict__ drop_seed, float drop_p) {
+                  const unsigned long long* __restrict__ drop_seed, float drop_p, float* __restrict__ amax) {
     const BaMap m = ba_map(C);
+    float mx = 0.f;
     float4 mu[NCOL], sc[NCOL], be[NCOL];
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
@@ -231,9 +253,11 @@ bn_act_fwd_kernel(const float* __restrict__ a, long lda, const float* __restrict
                 const float4 k = ba_keep4(drop_seed, r, C, c, drop_p);
                 o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
             }
+            mx = ba_amax4(mx, o);
             *reinterpret_cast<float4*>(y + r * C + c) = o;
         }
     }
+    if (amax) ba_store_amax(mx, amax);
 }
 
 // g' = gy * act'(pre);  partial[blk] = { sum_r g', sum_r g' * xhat };  optionally gs = g' is written out.
@@ -306,8 +330,9 @@ template <int NCOL>
 __global__ void __launch_bounds__(BA_T)
 bn_act_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ x, long R, int C,
                         const float* __restrict__ stats, const float* __restrict__ coef, float slope, float* __restrict__ dx,
-                        const unsigned long long* __restrict__ drop_seed, float drop_p) {
+                        const unsigned long long* __restrict__ drop_seed, float drop_p, float* __restrict__ amax) {
     const BaMap m = ba_map(C);
+    float mx = 0.f;
     float4 mu[NCOL], sc[NCOL], be[NCOL], gr[NCOL], c1[NCOL], c2[NCOL];
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
@@ -340,9 +365,11 @@ bn_act_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ 
             o.y = fmaf(gr[j].y, g.y, -c1[j].y) - c2[j].y * ey;
             o.z = fmaf(gr[j].z, g.z, -c1[j].z) - c2[j].z * ez;
             o.w = fmaf(gr[j].w, g.w, -c1[j].w) - c2[j].w * ew;
+            mx = ba_amax4(mx, o);
             *reinterpret_cast<float4*>(dx + r * C + c) = o;
         }
     }
+    if (amax) ba_store_amax(mx, amax);
 }
 
 // ---- BatchNorm + activation + max over the K rows of a group, without writing the activated (G*K, C) tensor.
@@ -483,7 +510,7 @@ extern "C" int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float
 
 extern "C" int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, long ldb, long R, int C, const float* stats,
                                     float slope, float* y, const unsigned long long* drop_seed, float drop_p,
-                                    pcnbr_stream_t stream) {
+                                    float* amax_out, pcnbr_stream_t stream) {
     if (drop_seed && !(drop_p >= 0.f && drop_p < 1.f)) return PCNBR_E_BADARG;
     if (!a || !stats || !y) return PCNBR_E_BADARG;
     if (!ba_supported(R, C) || (lda % 4) || (b && (ldb % 4)) || (((uintptr_t)a | (uintptr_t)b | (uintptr_t)y | (uintptr_t)stats) & 15))
@@ -491,8 +518,8 @@ extern "C" int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, lo
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = ba_grid(R, C);
     const double wb = 4.0 * R * C * (b ? 3.0 : 2.0), wf = 4.0 * R * C;
-    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<2><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y, drop_seed, drop_p)));
-    else              PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<1><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y, drop_seed, drop_p)));
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<2><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y, drop_seed, drop_p, amax_out)));
+    else              PCNBR_TIMED("bn_act_fwd_kernel", s, wb, wf, (bn_act_fwd_kernel<1><<<grid, BA_T, 0, s>>>(a, lda, b, ldb, R, C, stats, slope, y, drop_seed, drop_p, amax_out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -527,7 +554,7 @@ extern "C" int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const f
 
 extern "C" int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
                                           float slope, float* dx, const unsigned long long* drop_seed, float drop_p,
-                                          pcnbr_stream_t stream) {
+                                          float* amax_out, pcnbr_stream_t stream) {
     if (drop_seed && !(drop_p >= 0.f && drop_p < 1.f)) return PCNBR_E_BADARG;
     if (!gy || !x || !stats || !coef || !dx) return PCNBR_E_BADARG;
     if (!ba_supported(R, C) || (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)dx | (uintptr_t)stats | (uintptr_t)coef) & 15))
@@ -535,8 +562,8 @@ extern "C" int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long 
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = ba_grid(R, C);
     const double wb = 12.0 * R * C, wf = 8.0 * R * C;
-    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<2><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx, drop_seed, drop_p)));
-    else              PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<1><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx, drop_seed, drop_p)));
+    if (C / 4 > BA_T) PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<2><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx, drop_seed, drop_p, amax_out)));
+    else              PCNBR_TIMED("bn_act_bwd_apply_kernel", s, wb, wf, (bn_act_bwd_apply_kernel<1><<<grid, BA_T, 0, s>>>(gy, x, R, C, stats, coef, slope, dx, drop_seed, drop_p, amax_out)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -22,7 +22,7 @@
 
 namespace pcnbr {
 
-constexpr int H2_AMAX_SLOTS = 256;         // per-block maxima written by absmax_kernel
+constexpr int H2_AMAX_SLOTS = 1280;        // per-block maxima: absmax_kernel fills 256, the fused producers (bnact.cu) up to 1184
 constexpr int H2_CONV_THREADS = 32 * GM_CONV_WARPS;
 
 // kind::f16 (A, B = fp16, both K-major), D = fp32, M = 128, N = BN (cute::UMMA::InstrDescriptor)
@@ -375,7 +375,10 @@ absmax_kernel(const float* __restrict__ x, long rows, int cols, long ld, float* 
         m = threadIdx.x < 16 ? red[threadIdx.x] : 0.f;
 #pragma unroll
         for (int d = 8; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(PCNBR_FULL, m, d));
-        if (threadIdx.x == 0) partial[blockIdx.x] = m;
+        if (threadIdx.x == 0) {
+            partial[blockIdx.x] = m;
+            for (int i = blockIdx.x + gridDim.x; i < H2_AMAX_SLOTS; i += gridDim.x) partial[i] = 0.f;     // slots no block owns
+        }
     }
 }
 
@@ -486,7 +489,7 @@ extern "C" int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, f
     if (!x || !partial || rows <= 0 || cols <= 0 || (cols % 4) || (ld % 4) || ld < cols || ((uintptr_t)x & 15)) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
     PCNBR_TIMED("absmax_kernel", s, 4.0 * (double)rows * cols, 0.0,
-                (absmax_kernel<<<H2_AMAX_SLOTS, 512, 0, s>>>(x, rows, (int)cols, ld, partial)));
+                (absmax_kernel<<<256, 512, 0, s>>>(x, rows, (int)cols, ld, partial)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

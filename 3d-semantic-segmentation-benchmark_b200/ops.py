@@ -772,7 +772,7 @@ class _EdgeConvFusedFn(torch.autograd.Function):
         out = torch.empty(B, N, O, dtype=torch.float32, device=dev)
         # out = LeakyReLU(BatchNorm(psel + Q)): the two-source form of the fused row kernel, Q read in place from PQ
         _lib.call("pcnbr_bn_act_fwd_f32", psel.data_ptr(), O, PQ.data_ptr() + 4 * O, 2 * O, B * N, O, stats.data_ptr(),
-                  float(slope), out.data_ptr(), None, 0.0, _stream())
+                  float(slope), out.data_ptr(), None, 0.0, None, _stream())
         ctx.nbr, ctx.consts = nbr, (B, N, O, K, M, bool(training), float(slope))
         ctx.save_for_backward(PQ, psel, arg, s1, stats)
         if ctx.needs_input_grad[0]:
@@ -866,7 +866,7 @@ class _BnActRowsFn(torch.autograd.Function):
         else:
             stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
         y = torch.empty_like(x)
-        _lib.call("pcnbr_bn_act_fwd_f32", x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), None, 0.0, _stream())
+        _lib.call("pcnbr_bn_act_fwd_f32", x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), None, 0.0, None, _stream())
         ctx.save_for_backward(x, stats)
         ctx.consts = (bool(training), float(slope), gamma is not None, beta is not None)
         return y
@@ -891,7 +891,7 @@ class _BnActRowsFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), x.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
-                      dx.data_ptr(), None, 0.0, _stream())
+                      dx.data_ptr(), None, 0.0, None, _stream())
         return dx, (dgamma if has_gamma else None), (dbeta if has_beta else None), None, None, None, None, None, None
 
 
@@ -928,6 +928,24 @@ def _absmax(t: torch.Tensor):
     out = torch.empty(_lib.size("pcnbr_amax_slots"), dtype=torch.float32, device=t.device)
     _lib.call("pcnbr_absmax_f32", t.data_ptr(), rows, cols, ld, out.data_ptr(), _stream())
     return out
+
+
+def _amax_buffer(device) -> torch.Tensor:
+    return torch.empty(_lib.size("pcnbr_amax_slots"), dtype=torch.float32, device=device)
+
+
+def _amax_hint(t: torch.Tensor):
+    """The per-block maxima recorded for tensor object t by the kernel that wrote it (or by an earlier scan), if t has not
+    been modified in place since."""
+    rec = getattr(t, "_pcnbr_amax", None)
+    if rec is not None and rec[1] == t._version and rec[0].device == t.device:
+        return rec[0]
+    return None
+
+
+def _set_amax(t: torch.Tensor, amax) -> None:
+    if amax is not None:
+        t._pcnbr_amax = (amax, t._version)
 
 
 def _presplit(w: torch.Tensor, transpose: bool, amax: torch.Tensor) -> torch.Tensor:
@@ -1001,12 +1019,13 @@ def _wsplit(w, transpose, amax_w):
     return _presplit(w, transpose, amax_w) if amax_w is not None else None
 
 
-def _layer_amax(x, w, R, Cout, Cin):
-    """(amax_x, amax_w) when the layer's GEMMs go to the fp16-split kernel (each tensor is scanned ONCE and the maxima are
-    shared by the forward, input-gradient and weight-gradient GEMMs), else (None, None)."""
+def _layer_amax(x, w, R, Cout, Cin, amax_x=None):
+    """(amax_x, amax_w) when the layer's GEMMs go to the fp16-split kernel (each tensor is scanned ONCE -- or not at all
+    when its producer recorded the maxima, amax_x -- and the maxima are shared by the forward, input-gradient and
+    weight-gradient GEMMs), else (None, None)."""
     if not _gemm_h2_wanted(R, Cout, Cin):
         return None, None
-    return _absmax(x), _absmax(w)
+    return (amax_x if amax_x is not None else _absmax(x)), _absmax(w)
 
 
 class _LinearRowsFn(torch.autograd.Function):
@@ -1044,11 +1063,12 @@ class _LinearBnActFn(torch.autograd.Function):
     (BatchNorm removes any per-channel shift) and gamma*rstd*sum(g') in eval mode."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0):
+    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0, amax_x=None, amax_y=None):
+        """amax_x: per-block maxima of x when its producer recorded them; amax_y: buffer that receives those of y."""
         R, Cin = x.shape
         C = w.shape[0]
         dev = x.device
-        ctx.amax = _layer_amax(x, w, R, C, Cin)
+        ctx.amax = _layer_amax(x, w, R, C, Cin, amax_x)
         h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
@@ -1062,7 +1082,7 @@ class _LinearBnActFn(torch.autograd.Function):
         # so it is redrawn on every CUDA-graph replay); the backward recomputes the mask from it
         seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=dev) if drop_p > 0.0 else None
         _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(),
-                  seed.data_ptr() if seed is not None else None, float(drop_p), _stream())
+                  seed.data_ptr() if seed is not None else None, float(drop_p), amax_y.data_ptr() if amax_y is not None else None, _stream())
         ctx.drop = (seed, float(drop_p))
         ctx.save_for_backward(x, w, h, stats)
         ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None)
@@ -1086,17 +1106,18 @@ class _LinearBnActFn(torch.autograd.Function):
         _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
                   dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
         dh = torch.empty_like(h)
-        _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
-                  dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
         ax, aw = ctx.amax
-        ag = _absmax(dh) if ax is not None else None
+        ag = _amax_buffer(dev) if ax is not None else None            # the max |dh| comes out of the kernel that writes dh
+        _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
+                  dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1],
+                  ag.data_ptr() if ag is not None else None, _stream())
         dx = (_gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw))
               if ctx.needs_input_grad[0] else None)
         dw = _wgrad3x(dh, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None
         db = None
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
-        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None, None, None, None, None, None, None, None)
+        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 9
 
 
 class _LinearBnActPoolFn(torch.autograd.Function):
@@ -1186,13 +1207,14 @@ class _LinearBnActCatFn(torch.autograd.Function):
     writes the two input gradients and the two column blocks of the weight gradient directly."""
 
     @staticmethod
-    def forward(ctx, x1, x2, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0):
+    def forward(ctx, x1, x2, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0, amax_x1=None, amax_x2=None,
+                amax_y=None):
         R, K1 = x1.shape
         K2 = x2.shape[1]
         C = w.shape[0]
         dev = x1.device
         if _gemm_h2_wanted(R, C, K1 + K2):
-            ctx.amax = (_absmax(x1), _absmax(x2), _absmax(w))
+            ctx.amax = (amax_x1 if amax_x1 is not None else _absmax(x1), amax_x2 if amax_x2 is not None else _absmax(x2), _absmax(w))
         else:
             ctx.amax = (None, None, None)
         h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1, amax_a=ctx.amax[0], amax_a2=ctx.amax[1], amax_b=ctx.amax[2],
@@ -1209,7 +1231,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
         # so it is redrawn on every CUDA-graph replay); the backward recomputes the mask from it
         seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=dev) if drop_p > 0.0 else None
         _lib.call("pcnbr_bn_act_fwd_f32", h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(),
-                  seed.data_ptr() if seed is not None else None, float(drop_p), _stream())
+                  seed.data_ptr() if seed is not None else None, float(drop_p), amax_y.data_ptr() if amax_y is not None else None, _stream())
         ctx.drop = (seed, float(drop_p))
         ctx.save_for_backward(x1, x2, w, h, stats)
         ctx.consts = (bool(training), float(slope), b is not None, gamma is not None, beta is not None)
@@ -1234,11 +1256,12 @@ class _LinearBnActCatFn(torch.autograd.Function):
         _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
                   dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
         dh = torch.empty_like(h)
-        _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
-                  dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
-        # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
         a1, a2, aw = ctx.amax
-        ag = _absmax(dh) if aw is not None else None                # one scan of dh serves the four GEMMs below
+        ag = _amax_buffer(dev) if aw is not None else None            # the max |dh| comes out of the kernel that writes dh
+        _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
+                  dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1],
+                  ag.data_ptr() if ag is not None else None, _stream())
+        # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
         wt = _wsplit(w, True, aw)                                     # (2, K1 + K2, C): the transposed weight, split once
         dx1 = (_gemm3x(dh, False, w[:, :K1], True, R, K1, C, amax_a=ag, amax_b=aw, b_split=wt[:, :K1] if wt is not None else None)
                if ctx.needs_input_grad[0] else None)
@@ -1252,7 +1275,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
         db = None
         if has_b and ctx.needs_input_grad[3]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
-        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 7
+        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 10
 
 
 def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float,
@@ -1268,9 +1291,21 @@ def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: tor
     if not fused:
         return linear_bn_act_rows(torch.cat((rows1, rows2), dim=-1), weight, bias, bn, negative_slope, dropout_p)
     training, momentum, rm, rv = _bn_mode(bn)
-    y = _LinearBnActCatFn.apply(_c(rows1).view(nrows, k1), _c(rows2).view(nrows, k2), _c(weight), bias, bn.weight, bn.bias,
-                                rm, rv, training, momentum, float(bn.eps), float(negative_slope), float(dropout_p))
-    return y.view(*rows1.shape[:-1], cout)
+    h2 = _gemm_h2_wanted(nrows, cout, k1 + k2)
+    x1, x2 = _c(rows1).view(nrows, k1), _c(rows2).view(nrows, k2)
+    a1 = a2 = ay = None
+    if h2:                                               # maxima recorded by the producers, else scanned once and remembered
+        a1 = _amax_hint(rows1) if _amax_hint(rows1) is not None else _absmax(x1)
+        a2 = _amax_hint(rows2) if _amax_hint(rows2) is not None else _absmax(x2)
+        _set_amax(rows1, a1)
+        _set_amax(rows2, a2)
+    if nrows * cout >= (1 << 22):
+        ay = _amax_buffer(rows1.device)
+    y = _LinearBnActCatFn.apply(x1, x2, _c(weight), bias, bn.weight, bn.bias,
+                                rm, rv, training, momentum, float(bn.eps), float(negative_slope), float(dropout_p), a1, a2, ay)
+    out = y.view(*rows1.shape[:-1], cout)
+    _set_amax(out, ay)
+    return out
 
 
 def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float,
@@ -1290,9 +1325,18 @@ def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negat
         y = batchnorm_act_rows(linear_rows(rows, weight, bias), bn, negative_slope)
         return torch.nn.functional.dropout(y, dropout_p, True) if dropout_p > 0.0 else y
     training, momentum, rm, rv = _bn_mode(bn)
-    y = _LinearBnActFn.apply(_c(rows).view(nrows, cin), _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
-                             float(bn.eps), float(negative_slope), float(dropout_p))
-    return y.view(*rows.shape[:-1], cout)
+    x2 = _c(rows).view(nrows, cin)
+    ax = ay = None
+    if _gemm_h2_wanted(nrows, cout, cin):                # maxima recorded by the producer, else scanned once and remembered
+        ax = _amax_hint(rows) if _amax_hint(rows) is not None else _absmax(x2)
+        _set_amax(rows, ax)
+    if nrows * cout >= (1 << 22):                        # a big output may feed a tensor-bound GEMM: record its maxima for free
+        ay = _amax_buffer(rows.device)
+    y = _LinearBnActFn.apply(x2, _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
+                             float(bn.eps), float(negative_slope), float(dropout_p), ax, ay)
+    out = y.view(*rows.shape[:-1], cout)
+    _set_amax(out, ay)
+    return out
 
 
 _GEMM_LIBRARY = __import__("os").environ.get("PCNBR_GEMM_LIBRARY") is not None

@@ -199,14 +199,16 @@ PCNBR_API int pcnbr_bn_finalize_f32(const float* partial, int nblk, const float*
                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                           float* running_var, float* stats, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_act_fwd_f32(const float* a, long lda, const float* b, long ldb, long R, int C, const float* stats,
-                         float slope, float* y, const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream);
+                         float slope, float* y, const unsigned long long* drop_seed, float drop_p, float* amax_out,
+                         pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_act_bwd_reduce_f32(const float* gy, const float* a, long lda, const float* b, long ldb, long R, int C,
                                 const float* stats, float slope, float* partial, float* gs,
                                 const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_bwd_finalize_f32(const float* partial, int nblk, const float* stats, double count, int C, int training,
                               float* dgamma, float* dbeta, float* coef, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_bn_act_bwd_apply_f32(const float* gy, const float* x, long R, int C, const float* stats, const float* coef,
-                               float slope, float* dx, const unsigned long long* drop_seed, float drop_p, pcnbr_stream_t stream);
+                               float slope, float* dx, const unsigned long long* drop_seed, float drop_p, float* amax_out,
+                               pcnbr_stream_t stream);
 
 /* ---- BatchNorm + (Leaky)ReLU + max over the K rows of a group, fused ---- common.py:141-147 + 85-86 (SetAbstraction / InvResMLP)
  * h (G*K, C) pre-BatchNorm rows, stats as above.  act(bn(.)) is monotone per channel, so the max over K is taken on h (max
@@ -246,6 +248,8 @@ PCNBR_API int pcnbr_gemm3x_f32(const float* A, long lda, int a_mn, const float* 
  * pcnbr_absmax_f32 writes pcnbr_amax_slots() per-block maxima of |x| for a (rows x cols) matrix (row pitch ld; cols, ld
  * multiples of 4); pcnbr_gemm2h_ex_f32 takes those arrays for A, A2 (when given) and B.  Otherwise the contract --
  * operand layouts, split-K (pcnbr_gemm3x_splits / pcnbr_gemm3x_ws_bytes), bias, C pitch -- is that of pcnbr_gemm3x_ex_f32. */
+/* amax_out of pcnbr_bn_act_fwd_f32 / pcnbr_bn_act_bwd_apply_f32 (optional, pcnbr_amax_slots() floats): the same per-block
+ * maxima for the tensor those kernels WRITE, so the GEMM that consumes it needs no separate pcnbr_absmax_f32 pass. */
 PCNBR_API int pcnbr_amax_slots(void);
 PCNBR_API int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, float* partial, pcnbr_stream_t stream);
 PCNBR_API int pcnbr_gemm2h_preferred(int M, int N, int K);
