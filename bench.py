@@ -69,8 +69,9 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="only the requested model (no pointnetpp / reference_gpu / strong records)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
-    ap.add_argument("--no-prefetch", action="store_true",
-                    help="compute every step's geometry (FPS / ball query / kNN tables) inside that step instead of one step ahead on the side stream")
+    ap.add_argument("--prefetch", action="store_true",
+                    help="software-pipeline the step: the NEXT batch's geometry (FPS / ball query / kNN tables + CSR inverses) is computed on a "
+                         "side stream during the current step (train.GraphedTrainStep(geometry_fn)); measured neutral on B200 (DESIGN.md 7), off by default")
     ap.add_argument("--cpu-batch", type=int, default=0, help="clouds per CPU-reference step (0 = sized to ~120 s of CPU work)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same reference code on cuda:0 with stock ATen / cuBLAS / cuDNN "
@@ -414,7 +415,7 @@ class Harness:
         # index-only work of the NEXT batch (FPS picks, ball-query / first-layer kNN tables, their CSR inverses) runs on a side
         # stream during the current step: the captured step is software-pipelined over two batches (train.GraphedTrainStep)
         geo_fn = None
-        if model in ("dgcnn", "pointnetpp") and not args.no_prefetch and not args.no_graph:
+        if model in ("dgcnn", "pointnetpp") and args.prefetch and not args.no_graph:
             geo_fn = lambda m, pts, lab, lens, stream=None: m.prepare_geometry(model_input(model, pts), stream=stream)
             if os.environ.get("PCNBR_FAKE_PREFETCH"):            # diagnostic only: geometry computed once, never again (an INVALID
                 cache = {}                                         # measurement: shows the step time with no geometry work at all)
