@@ -354,13 +354,14 @@ __device__ __forceinline__ int csr_row_matches(const int32_t* __restrict__ row, 
 
 __global__ void __launch_bounds__(256)
 csr_emit_kernel(const int32_t* __restrict__ idx, int M, int K, int N, int W, const int32_t* __restrict__ offsets,
-                const uint32_t* __restrict__ bm, const int32_t* __restrict__ dupflag, int32_t* __restrict__ perm) {
+                const uint32_t* __restrict__ bm, const int32_t* __restrict__ dupflag, int32_t* __restrict__ perm, int only_flagged) {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long E = (long)M * K;
     const int32_t* __restrict__ ib = idx + (size_t)b * E;
     int32_t* __restrict__ pm = perm + (size_t)b * E;
     const int32_t* __restrict__ off = offsets + (size_t)b * (N + 1);
     const bool multi = dupflag[b] != 0;
+    if (only_flagged && !multi) return;                  // this cloud was handled by csr_emit_entries_kernel
     for (int s = blockIdx.x * 8 + warp; s < N; s += gridDim.x * 8) {
         int out = off[s];
         if (off[s + 1] == out) continue;
@@ -475,6 +476,43 @@ extern "C" int pcnbr_csr_build(const int32_t* idx, int B, int E, int N, int32_t*
 }
 
 
+namespace pcnbr {
+// Entry-side emit for tables whose rows hold distinct sources (every kNN / ball-query / 3-NN table): the position of entry
+// (m, r) inside its source's segment is the number of rows below m that reference the same source = a prefix popcount of
+// that source's bitmap row.  One thread per entry, at most W/4 16-byte loads each, the same cost for a hub referenced by
+// every row as for a leaf -- the source-side walk above spends 32 x K loads per lane on a hub (139 us for the SA1 ball
+// table, whose 32 padding indices appear in almost every row).  Clouds flagged by csr_mark_kernel (a row holds a source
+// twice) are left to csr_emit_kernel.
+__global__ void __launch_bounds__(256)
+csr_emit_entries_kernel(const int32_t* __restrict__ idx, int M, int K, int N, int W, const int32_t* __restrict__ offsets,
+                        const uint32_t* __restrict__ bm, const int32_t* __restrict__ dupflag, int32_t* __restrict__ perm) {
+    const int b = blockIdx.y;
+    if (dupflag[b] != 0) return;
+    const long E = (long)M * K;
+    const int32_t* __restrict__ ib = idx + (size_t)b * E;
+    int32_t* __restrict__ pm = perm + (size_t)b * E;
+    const int32_t* __restrict__ off = offsets + (size_t)b * (N + 1);
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(e / K);
+        const int s = ib[e];
+        if ((unsigned)s >= (unsigned)N) continue;
+        const uint32_t* __restrict__ row = bm + ((size_t)b * N + s) * W;
+        const int wfull = m >> 5;
+        int rank = 0, w = 0;
+        if ((W & 3) == 0) {
+            const uint4* __restrict__ row4 = reinterpret_cast<const uint4*>(row);
+            for (; w + 4 <= wfull; w += 4) {
+                const uint4 v = row4[w >> 2];
+                rank += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+            }
+        }
+        for (; w < wfull; ++w) rank += __popc(row[w]);
+        rank += __popc(row[wfull] & ((1u << (m & 31)) - 1u));
+        pm[off[s] + rank] = (int32_t)e;
+    }
+}
+}  // namespace pcnbr
+
 static bool csr_rows_use_bitmap(int B, int M, int N) {
     const size_t W = ((size_t)M + 31) / 32;
     return (size_t)B * N * W * 4 <= CSR_BITMAP_BUDGET;
@@ -486,7 +524,7 @@ extern "C" size_t pcnbr_csr_rows_ws_bytes(int B, int M, int K, int N) {
     if (csr_use_stable((int)E, N) || !csr_rows_use_bitmap(B, M, N)) return pcnbr_csr_ws_bytes(B, (int)E, N);
     const size_t W = ((size_t)M + 31) / 32;
     // cnt (B,N+1) + duplicate flags (B, padded to 64 words) + bitmap (B,N,W)
-    return sizeof(int32_t) * ((size_t)B * (N + 1) + (size_t)((B + 63) / 64 * 64) + (size_t)B * N * W);
+    return sizeof(int32_t) * ((((size_t)B * (N + 1) + 3) & ~(size_t)3) + (size_t)((B + 63) / 64 * 64) + (size_t)B * N * W);
 }
 
 // Inverse of a row-structured table idx (B,M,K) into N sources: same result as pcnbr_csr_build(idx, B, M*K, N, ...).
@@ -504,7 +542,7 @@ extern "C" int pcnbr_csr_build_rows(const int32_t* idx, int B, int M, int K, int
     cudaStream_t s = (cudaStream_t)stream;
     const int W = (M + 31) / 32;
     int32_t* cnt = (int32_t*)ws;
-    int32_t* dup = cnt + (size_t)B * (N + 1);
+    int32_t* dup = cnt + (((size_t)B * (N + 1) + 3) & ~(size_t)3);          // keeps the bitmap 16-byte aligned (uint4 reads)
     uint32_t* bm = (uint32_t*)(dup + (size_t)((B + 63) / 64 * 64));
     cudaError_t e = cudaMemsetAsync(ws, 0, pcnbr_csr_rows_ws_bytes(B, M, K, N), s);
     if (e != cudaSuccess) return (int)e;
@@ -516,8 +554,17 @@ extern "C" int pcnbr_csr_build_rows(const int32_t* idx, int B, int M, int K, int
     PCNBR_TIMED("csr_scan1_kernel", s, (double)B * 8.0 * N, 0.0, (csr_scan1_kernel<<<B, 1024, 0, s>>>(cnt, N, offsets)));
     PCNBR_CHECK_LAUNCH();
     const int gs = (N + 7) / 8 < 2368 ? (N + 7) / 8 : 2368;
-    PCNBR_TIMED("csr_emit_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0,
-                (csr_emit_kernel<<<dim3(gs, B), 256, 0, s>>>(idx, M, K, N, W, offsets, bm, dup, perm)));
+    if (W <= 256) {
+        // rows with distinct sources (the normal case): one thread per entry; flagged clouds fall through to the walk below
+        PCNBR_TIMED("csr_emit_entries_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0,
+                    (csr_emit_entries_kernel<<<dim3(gx, B), 256, 0, s>>>(idx, M, K, N, W, offsets, bm, dup, perm)));
+        PCNBR_CHECK_LAUNCH();
+        PCNBR_TIMED("csr_emit_kernel", s, 0.0, 0.0,
+                    (csr_emit_kernel<<<dim3(gs, B), 256, 0, s>>>(idx, M, K, N, W, offsets, bm, dup, perm, 1)));
+    } else {
+        PCNBR_TIMED("csr_emit_kernel", s, (double)B * (8.0 * E + 4.0 * N), 0.0,
+                    (csr_emit_kernel<<<dim3(gs, B), 256, 0, s>>>(idx, M, K, N, W, offsets, bm, dup, perm, 0)));
+    }
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -180,6 +180,56 @@ __device__ __forceinline__ void grid_scan_range(const float4* __restrict__ pts, 
     }
 }
 
+// The 3 x 3 x 3 cells around (cx, cy, cz) as ONE flattened candidate stream: lanes 0..8 fetch the bounds of the nine
+// x-adjacent runs at once (one load latency instead of nine dependent ones), an exclusive prefix over the run lengths maps
+// a flat candidate number to (run, offset), and the warp walks the stream 32 candidates at a time.
+template <int NSLOT, bool RADIUS>
+__device__ __forceinline__ void grid_scan_cube1(const float4* __restrict__ pts, const int32_t* __restrict__ st, const GridParams& g,
+                                                int cx, int cy, int cz, float qx, float qy, float qz, float r2, int K,
+                                                WarpList<NSLOT>& list, u64& thr, int lane) {
+    int beg = 0, len = 0;
+    if (lane < 9) {
+        const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+        if (z >= 0 && z < g.nz && y >= 0 && y < g.ny && x0 <= x1) {
+            const int row = (z * g.ny + y) * g.nx;
+            beg = st[row + x0];
+            len = st[row + x1 + 1] - beg;
+        }
+    }
+    int off = len;                                       // inclusive prefix over lanes 0..8
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const int y = __shfl_up_sync(PCNBR_FULL, off, d);
+        if (lane >= d) off += y;
+    }
+    const int total = __shfl_sync(PCNBR_FULL, off, 8);
+    off -= len;                                          // exclusive
+    for (int c0 = 0; c0 < total; c0 += 32) {
+        const int t = c0 + lane;
+        int run = 0;
+#pragma unroll
+        for (int r = 1; r < 9; ++r) run += (t >= __shfl_sync(PCNBR_FULL, off, r)) ? 1 : 0;      // offsets are non-decreasing
+        const int rb = __shfl_sync(PCNBR_FULL, beg, run), ro = __shfl_sync(PCNBR_FULL, off, run);
+        u64 key = PCNBR_KEY_MAX;
+        if (t < total) {
+            const float4 s = pts[rb + (t - ro)];
+            const float d2 = d2_direct(s.x, s.y, s.z, qx, qy, qz);
+            if (!RADIUS || d2 <= r2) key = pack_key(f2ord(d2), (uint32_t)__float_as_int(s.w));
+        }
+        uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
+        while (pass) {
+            const int src = __ffs(pass) - 1;
+            pass &= pass - 1;
+            const u64 cand = shfl64(key, src);
+            if (cand < thr) {
+                list.insert(cand, lane);
+                thr = list.at(K - 1);
+            }
+        }
+    }
+}
+
 // Ball query: one warp per query, the 3 x 3 x 3 cells around it (3 x-adjacent cells are one contiguous run).
 template <int NSLOT>
 __global__ void __launch_bounds__(256)
@@ -197,13 +247,7 @@ ball_grid_kernel(const float* __restrict__ q, int M, int N, float r2, int K, con
     WarpList<NSLOT> list;
     list.init();
     u64 thr = PCNBR_KEY_MAX;
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-    if (x0 <= x1)
-        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
-                const int row = (z * g.ny + y) * g.nx;
-                grid_scan_range<NSLOT, true>(pts, st[row + x0], st[row + x1 + 1], qx, qy, qz, r2, K, list, thr, lane);
-            }
+    grid_scan_cube1<NSLOT, true>(pts, st, g, cx, cy, cz, qx, qy, qz, r2, K, list, thr, lane);
     // members first (ascending (d2, index)), then the lowest indices that are not members
     int cnt = 0;
 #pragma unroll
@@ -245,8 +289,10 @@ knn_grid_kernel(const float* __restrict__ q, int M, int N, int K, const GridPara
     u64 thr = PCNBR_KEY_MAX;
     const float slack = 2e-3f * g.h;                    // cells are assigned with fp32 rounding: shrink the safe margin
     const int rmax = max(g.nx, max(g.ny, g.nz)) + 2;   // the query cell is within [-1, n]: the cube covers the grid by then
-    for (int R = 0; R <= rmax; ++R) {
-        // shell R: cells with max(|dx|, |dy|, |dz|) == R, clipped to the grid
+    grid_scan_cube1<1, false>(pts, st, g, cx, cy, cz, qx, qy, qz, 0.f, K, list, thr, lane);      // R = 0 and R = 1 in one stream
+    for (int R = 1; R <= rmax; ++R) {
+        // shell R >= 2: cells with max(|dx|, |dy|, |dz|) == R, clipped to the grid (the cube above covered R <= 1)
+        if (R >= 2)
         for (int z = max(cz - R, 0); z <= min(cz + R, g.nz - 1); ++z)
             for (int y = max(cy - R, 0); y <= min(cy + R, g.ny - 1); ++y) {
                 const int row = (z * g.ny + y) * g.nx;
