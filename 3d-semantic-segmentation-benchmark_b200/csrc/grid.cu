@@ -217,6 +217,12 @@ __device__ __forceinline__ void grid_scan_cube1(const float4* __restrict__ pts, 
             const float d2 = d2_direct(s.x, s.y, s.z, qx, qy, qz);
             if (!RADIUS || d2 <= r2) key = pack_key(f2ord(d2), (uint32_t)__float_as_int(s.w));
         }
+        if (c0 == 0 && !RADIUS) {
+            // the first 32 candidates all enter the empty list: ONE warp sort instead of 32 sequential inserts
+            list.v[0] = warp_sort64(key, lane);
+            thr = list.at(K - 1);
+            continue;
+        }
         uint32_t pass = __ballot_sync(PCNBR_FULL, key < thr);
         while (pass) {
             const int src = __ffs(pass) - 1;

@@ -19,22 +19,6 @@ namespace pcnbr {
 
 constexpr int SEL_TILE = 1024;   // source points per shared-memory tile (12 KB SoA)
 
-// ascending bitonic sort of one 64-bit key per lane across the warp (15 compare-exchange steps)
-__device__ __forceinline__ u64 warp_sort64(u64 key, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t lo = __shfl_xor_sync(PCNBR_FULL, (uint32_t)key, j);
-            const uint32_t hi = __shfl_xor_sync(PCNBR_FULL, (uint32_t)(key >> 32), j);
-            const u64 other = ((u64)hi << 32) | lo;
-            const bool take_min = ((lane & j) == 0) == ((lane & k) == 0);
-            key = (take_min == (other < key)) ? other : key;
-        }
-    }
-    return key;
-}
-
 constexpr int SEL_WARPS = 16;    // queries per CTA: the tile staging is shared by 16 warps
 
 template <int NSLOT, bool RADIUS>
