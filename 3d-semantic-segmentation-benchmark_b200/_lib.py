@@ -22,6 +22,11 @@ PROTOTYPES = {
     "pcnbr_error_string": (c_char_p, [_I]),
     "pcnbr_fps_ws_bytes": (_Z, [_I, _I]),
     "pcnbr_fps_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "pcnbr_fps_len_f32": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "pcnbr_ball_query_len_f32": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _Z, _P]),
+    "pcnbr_knn_direct_len_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "pcnbr_ball_query_multi_len_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _Z, _P]),
+    "pcnbr_knn_expand_len_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _P, _Z, _P]),
     "pcnbr_ball_query_f32": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
     "pcnbr_knn_direct_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "pcnbr_grid_ws_bytes": (_Z, [_I, _I]),
@@ -76,7 +81,7 @@ PROTOTYPES = {
 }
 
 # CUDA kernels launched per C-ABI call (csr_build = count + scan + fill + sort; knn_expand = sumsq + select)
-KERNELS_PER_CALL = {"pcnbr_ball_query_multi_f32": 2, "pcnbr_masked_ce_f32": 2, "pcnbr_ball_query_grid_f32": 5, "pcnbr_knn_direct_grid_f32": 5, "pcnbr_csr_build": 4, "pcnbr_csr_build_rows": 3, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_tc_debug_f32": 5}
+KERNELS_PER_CALL = {"pcnbr_ball_query_multi_f32": 2, "pcnbr_masked_ce_f32": 2, "pcnbr_ball_query_grid_f32": 5, "pcnbr_knn_direct_grid_f32": 5, "pcnbr_csr_build": 4, "pcnbr_csr_build_rows": 3, "pcnbr_knn_expand_f32": 5, "pcnbr_knn_expand_len_f32": 5, "pcnbr_ball_query_len_f32": 5, "pcnbr_knn_direct_len_f32": 5, "pcnbr_ball_query_multi_len_f32": 2, "pcnbr_knn_tc_debug_f32": 5}
 
 _lib = None
 launches = 0          # number of libpcnbr CUDA kernels launched by this process (bench.py reports it)

@@ -19,25 +19,28 @@ __all__ = ["sample", "group", "reduce", "interpolate", "MiniPointNet", "UnitPoin
            "SetAbstractionMSG", "FeaturePropagation", "InvResMLP"]
 
 
-def sample(coords: torch.Tensor, C: int, start_idx: torch.Tensor | None = None) -> torch.Tensor:
+def sample(coords: torch.Tensor, C: int, start_idx: torch.Tensor | None = None, lengths=None) -> torch.Tensor:
     """Farthest point sampling -> coordinates (B,C,3) of the picks   [reference common.py:6-34].
 
     The first pick is drawn like the reference (one torch.randint on coords.device) unless
-    `start_idx` (B,) is given."""
-    return ops.farthest_point_sample(coords, C, start_idx, return_coords=True)[1]
+    `start_idx` (B,) is given.  lengths (B,), here and below: the length-aware form for the zero-padded batches of the
+    evaluation loader (data_processing/block_datasets.py:19-25) -- the padding rows take no part, the
+    result for the real rows is the reference's on the cloud passed alone.  None = the reference's behaviour (padding
+    participates)."""
+    return ops.farthest_point_sample(coords, C, start_idx, return_coords=True, lengths=lengths)[1]
 
 
 def group(centroid_coords: torch.Tensor, coords: torch.Tensor, features: torch.Tensor, r: float, K: int,
-          normalize: bool = False) -> torch.Tensor:
+          normalize: bool = False, lengths=None) -> torch.Tensor:
     """Ball query + gather + centre-subtract (+ /r) + concat -> (B,C,K,3+D)   [common.py:37-71]."""
-    nbr = ops.NeighborIndex(ops.query_ball_point(r, K, coords, centroid_coords), coords.shape[1])
+    nbr = ops.NeighborIndex(ops.query_ball_point(r, K, coords, centroid_coords, lengths=lengths), coords.shape[1])
     return ops.group_points(coords, features, centroid_coords, nbr, r if normalize else None)
 
 
-def _group_rows(centroid_coords, coords, features, r, K, normalize):
+def _group_rows(centroid_coords, coords, features, r, K, normalize, lengths=None):
     """group() for the modules below: the same tensor with its rows zero-padded to a multiple of 4 floats, the pitch
     the tensor-core GEMM of the first 1x1 convolution reads in place (MiniPointNet.forward_rows)."""
-    nbr = ops.NeighborIndex(ops.query_ball_point(r, K, coords, centroid_coords), coords.shape[1])
+    nbr = ops.NeighborIndex(ops.query_ball_point(r, K, coords, centroid_coords, lengths=lengths), coords.shape[1])
     return ops.group_points(coords, features, centroid_coords, nbr, r if normalize else None, pad4=True)
 
 
@@ -53,9 +56,9 @@ def reduce(x: torch.Tensor, type: str) -> torch.Tensor:
     raise ValueError(f"'{type}' pooling not supported; use 'max' or 'avg'.")
 
 
-def interpolate(points: torch.Tensor, coords_1: torch.Tensor, coords_2: torch.Tensor, k: int = 3) -> torch.Tensor:
-    """k-NN inverse-squared-distance interpolation (B,M,D) -> (B,N,D)   [common.py:94-122]."""
-    idx, d2 = ops.knn_points(coords_1, coords_2, k)
+def interpolate(points: torch.Tensor, coords_1: torch.Tensor, coords_2: torch.Tensor, k: int = 3, lengths=None) -> torch.Tensor:
+    """k-NN inverse-squared-distance interpolation (B,M,D) -> (B,N,D)   [common.py:94-122].  lengths: real rows of coords_1."""
+    idx, d2 = ops.knn_points(coords_1, coords_2, k, query_lengths=lengths)
     return ops.three_interpolate(points, ops.NeighborIndex(idx, coords_2.shape[1]), d2)
 
 
@@ -177,15 +180,15 @@ class SetAbstraction(nn.Module):
         self.grouping_norm = grouping_norm
         self.fps_start = None          # optional (B,) first FPS pick (tests); None = reference's randint
 
-    def forward(self, coords: torch.Tensor, features: torch.Tensor, _geom=None):
+    def forward(self, coords: torch.Tensor, features: torch.Tensor, _geom=None, lengths=None):
         """_geom (internal): (centroid coords, ball-query NeighborIndex) precomputed by ops.PyramidGeometry on the side
-        stream; None computes them here, as the reference does."""
+        stream; None computes them here, as the reference does.  lengths: real points per cloud (see sample())."""
         if _geom is not None:
             centroid_coords, nbr = _geom
             grouped = ops.group_points(coords, features, centroid_coords, nbr, self.radius if self.grouping_norm else None, pad4=True)
         else:
-            centroid_coords = sample(coords, self.C, self.fps_start)
-            grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm)
+            centroid_coords = sample(coords, self.C, self.fps_start, lengths)
+            grouped = _group_rows(centroid_coords, coords, features, self.radius, self.K, self.grouping_norm, lengths)
         if self.pooling_type == 'max':
             return centroid_coords, self.point_net.forward_rows(grouped, pool_max=True)   # (B,C,mlp[-1])
         x = self.point_net.forward_rows(grouped)             # point-major rows (B,C,K,*): no permute, no copy
@@ -214,15 +217,15 @@ class SetAbstractionMSG(nn.Module):
         self.grouping_norm = grouping_norm
         self.fps_start = None          # optional (B,) first FPS pick (tests); None = reference's randint
 
-    def forward(self, coords: torch.Tensor, features: torch.Tensor, _geom=None):
+    def forward(self, coords: torch.Tensor, features: torch.Tensor, _geom=None, lengths=None):
         """_geom (internal): (centroid coords, [NeighborIndex per scale]) precomputed by ops.PyramidGeometry on the side
-        stream; None computes them here."""
+        stream; None computes them here.  lengths: real points per cloud (see sample())."""
         if _geom is not None:
             centroid_coords, nbrs = _geom
         else:
-            centroid_coords = sample(coords, self.C, self.fps_start)
+            centroid_coords = sample(coords, self.C, self.fps_start, lengths)
             nbrs = [ops.NeighborIndex(idx, coords.shape[1])
-                    for idx in ops.query_ball_point_multi(self.radii, self.Ks, coords, centroid_coords)]
+                    for idx in ops.query_ball_point_multi(self.radii, self.Ks, coords, centroid_coords, lengths=lengths)]
         outs = []
         for r, nbr, net in zip(self.radii, nbrs, self.point_nets):
             grouped = ops.group_points(coords, features, centroid_coords, nbr, r if self.grouping_norm else None, pad4=True)
@@ -240,9 +243,10 @@ class FeaturePropagation(nn.Module):
         super().__init__()
         self.point_net = UnitPointNet(in_channels, mlps)
 
-    def forward(self, coords_1, coords_2, features_1, features_2, _geom=None):
-        """_geom (internal): (NeighborIndex, d2) of the 3-NN table precomputed by ops.PyramidGeometry."""
-        up = interpolate(features_2, coords_1, coords_2) if _geom is None else ops.three_interpolate(features_2, _geom[0], _geom[1])
+    def forward(self, coords_1, coords_2, features_1, features_2, _geom=None, lengths=None):
+        """_geom (internal): (NeighborIndex, d2) of the 3-NN table precomputed by ops.PyramidGeometry.  lengths: real rows
+        of coords_1 (see sample())."""
+        up = interpolate(features_2, coords_1, coords_2, lengths=lengths) if _geom is None else ops.three_interpolate(features_2, _geom[0], _geom[1])
         if features_1 is None:
             return self.point_net(up.permute(0, 2, 1)).permute(0, 2, 1)
         return self.point_net.forward_rows_cat(features_1, up)

@@ -50,6 +50,20 @@ __device__ __forceinline__ float d2_direct(float px, float py, float pz, float q
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Length-aware forms (zero-padded evaluation batches, data_processing/block_datasets.py:19-25): cloud b holds len[b] real
+// rows (clamped to [1, n_alloc]; len == NULL: all n_alloc), the rest is padding that takes no part -- the result for the
+// real rows is what the reference computes when the cloud is passed alone, unpadded.
+__device__ __forceinline__ int len_valid(const int32_t* __restrict__ len, int b, int n_alloc) {
+    return len ? min(max(len[b], 1), n_alloc) : n_alloc;
+}
+// output row of a padding query: in-range indices 0..K-1 and zero distances, so downstream gathers stay in bounds
+__device__ __forceinline__ void len_fill_row(int32_t* __restrict__ idx, float* __restrict__ d2, size_t row, int K, int lane) {
+    for (int pos = lane; pos < K; pos += 32) {
+        idx[row + pos] = pos;
+        if (d2) d2[row + pos] = 0.f;
+    }
+}
+
 // Sorted K-list spread over a warp: position p = slot*32 + lane holds the p-th smallest key.
 // NSLOT*32 >= K.  All lanes call insert() with the same candidate.
 template <int NSLOT>
@@ -112,10 +126,14 @@ struct ProfScope {
     } while (0)
 
 // cross-file host helpers
-int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, float* xx, cudaStream_t s);     // select.cu
+int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, const int32_t* n_valid, float* xx, cudaStream_t s);     // select.cu
+int select_ball_len(const float* q, const float* p, int B, int M, int N, float r2, int K, const int32_t* n_qry, const int32_t* n_src,
+                    int32_t* idx, cudaStream_t s);
+int select_knn_len(const float* q, const float* p, int B, int M, int N, int K, const int32_t* n_qry, const int32_t* n_src,
+                   int32_t* idx, float* d2, cudaStream_t s);
 bool knn_tc_supported(int F, int N, int K);                                                              // knn_tc.cu
 size_t knn_tc_ws_bytes(int B, int F, int N);
-int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int32_t* idx, void* ws, float* dump,
-               int32_t* stats_out, cudaStream_t s);
+int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, const int32_t* n_valid, int32_t* idx, void* ws,
+               float* dump, int32_t* stats_out, cudaStream_t s);
 
 }  // namespace pcnbr

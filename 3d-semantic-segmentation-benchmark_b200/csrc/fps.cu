@@ -24,6 +24,12 @@ __device__ __forceinline__ float fps_dist2(float x, float y, float z, float cx, 
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// points of cloud b that exist: N, or n_valid[b] clamped to [1, N] (length-aware form: zero-padded evaluation batches,
+// data_processing/block_datasets.py:19-25 -- the padding rows take no part, as if the cloud had been passed alone)
+__device__ __forceinline__ int fps_valid(const int32_t* __restrict__ n_valid, int b, int N) {
+    return n_valid ? min(max(n_valid[b], 1), N) : N;
+}
+
 // warp-wide max of (hi, lo) pairs in lexicographic order, result broadcast to all lanes
 __device__ __forceinline__ void warp_max_pair(uint32_t& hi, uint32_t& lo) {
     const uint32_t mh = __reduce_max_sync(PCNBR_FULL, hi);
@@ -35,18 +41,19 @@ __device__ __forceinline__ void warp_max_pair(uint32_t& hi, uint32_t& lo) {
 template <int PPT, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __restrict__ start,
-               int32_t* __restrict__ idx_out, float* __restrict__ xyz_out) {
+               const int32_t* __restrict__ n_valid, int32_t* __restrict__ idx_out, float* __restrict__ xyz_out) {
     constexpr int W = T / 32;
     __shared__ uint32_t s_hi[2][W], s_lo[2][W];
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* __restrict__ p = xyz + (size_t)b * N * 3;
+    const int NV = fps_valid(n_valid, b, N);               // rows >= NV are padding of a zero-padded batch: they do not exist
 
     float x[PPT], y[PPT], z[PPT], md[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
         const int n = j * T + tid;
-        if (n < N) {
+        if (n < NV) {
             x[j] = p[n * 3 + 0]; y[j] = p[n * 3 + 1]; z[j] = p[n * 3 + 2];
             md[j] = __int_as_float(0x7f800000);          // +inf (common.py:21)
         } else {
@@ -55,7 +62,7 @@ fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
         }
     }
 
-    int cur = min(max(start[b], 0), N - 1);        // a caller-supplied first pick outside [0, N) is clamped, never dereferenced
+    int cur = min(max(start[b], 0), NV - 1);       // a caller-supplied first pick outside [0, NV) is clamped, never dereferenced
     float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
 
     for (int i = 0; i < C; ++i) {
@@ -125,7 +132,7 @@ constexpr int FPS_CL_MAX = 8;
 template <int PPT, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __restrict__ start,
-                   int32_t* __restrict__ idx_out, float* __restrict__ xyz_out) {
+                   const int32_t* __restrict__ n_valid, int32_t* __restrict__ idx_out, float* __restrict__ xyz_out) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int W = T / 32;
@@ -138,6 +145,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* __restrict__ p = xyz + (size_t)b * N * 3;
+    const int NV = fps_valid(n_valid, b, N);
     const int Q = (N + CL - 1) / CL;                          // points per CTA, contiguous share
     const int n0 = rank * Q;
 
@@ -145,7 +153,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
         const int q = j * T + tid, n = n0 + q;
-        if (q < Q && n < N) {
+        if (q < Q && n < NV) {
             x[j] = p[n * 3 + 0]; y[j] = p[n * 3 + 1]; z[j] = p[n * 3 + 2];
             md[j] = __int_as_float(0x7f800000);
         } else {
@@ -153,7 +161,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
             md[j] = 0.f;
         }
     }
-    int cur = min(max(start[b], 0), N - 1);        // a caller-supplied first pick outside [0, N) is clamped, never dereferenced
+    int cur = min(max(start[b], 0), NV - 1);       // a caller-supplied first pick outside [0, NV) is clamped, never dereferenced
     float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
     cluster.sync();                                            // every CTA of the cluster is resident before remote stores
 
@@ -193,7 +201,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
         // padding slots (beyond the share or the cloud) carry md = 0 and the lowest-priority index: their slot numbers would
         // otherwise alias real points of the next CTA's share
         const int bq = bj * T + tid;
-        const uint32_t bl = (bq < Q && n0 + bq < N) ? 0xffffffffu - (uint32_t)(n0 + bq) : 0u;
+        const uint32_t bl = (bq < Q && n0 + bq < NV) ? 0xffffffffu - (uint32_t)(n0 + bq) : 0u;
         uint32_t wh = bh, wl = bl;
         warp_max_pair(wh, wl);
         if (bh == wh && bl == wl) {
@@ -236,8 +244,8 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
 }
 
 template <int PPT, int T>
-static int fps_launch_cluster(int CL, int B, const float* xyz, int N, int C, const int32_t* start, int32_t* idx_out, float* xyz_out,
-                              cudaStream_t s) {
+static int fps_launch_cluster(int CL, int B, const float* xyz, int N, int C, const int32_t* start, const int32_t* n_valid,
+                              int32_t* idx_out, float* xyz_out, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CL));
     cfg.blockDim = dim3(T);
@@ -250,21 +258,22 @@ static int fps_launch_cluster(int CL, int B, const float* xyz, int N, int C, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, T>, xyz, N, C, start, idx_out, xyz_out);
+    return (int)cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, T>, xyz, N, C, start, n_valid, idx_out, xyz_out);
 }
 
 // Any N: running distances live in a global workspace, coordinates are re-read through L1/L2.
 template <int T>
 __global__ void __launch_bounds__(T, 1)
 fps_big_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __restrict__ start,
-               int32_t* __restrict__ idx_out, float* __restrict__ xyz_out, float* __restrict__ ws) {
+               const int32_t* __restrict__ n_valid, int32_t* __restrict__ idx_out, float* __restrict__ xyz_out, float* __restrict__ ws) {
     constexpr int W = T / 32;
     __shared__ uint32_t s_hi[2][W], s_lo[2][W];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* __restrict__ p = xyz + (size_t)b * N * 3;
     float* __restrict__ md = ws + (size_t)b * N;
-    for (int n = tid; n < N; n += T) md[n] = __int_as_float(0x7f800000);
-    int cur = min(max(start[b], 0), N - 1);        // a caller-supplied first pick outside [0, N) is clamped, never dereferenced
+    const int NV = fps_valid(n_valid, b, N);
+    for (int n = tid; n < NV; n += T) md[n] = __int_as_float(0x7f800000);
+    int cur = min(max(start[b], 0), NV - 1);       // a caller-supplied first pick outside [0, NV) is clamped, never dereferenced
     for (int i = 0; i < C; ++i) {
         const float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
         if (tid == 0) {
@@ -277,7 +286,7 @@ fps_big_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
         if (i + 1 == C) break;
         const int buf = i & 1;
         uint32_t bh = 0, bl = 0;
-        for (int n = tid; n < N; n += T) {
+        for (int n = tid; n < NV; n += T) {
             const float d = fps_dist(p[n * 3 + 0], p[n * 3 + 1], p[n * 3 + 2], cx, cy, cz);
             const float m = fminf(md[n], d);
             md[n] = m;
@@ -302,6 +311,11 @@ extern "C" size_t pcnbr_fps_ws_bytes(int B, int N) {
 
 extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_t* start, int32_t* idx_out,
                              float* xyz_out, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    return pcnbr_fps_len_f32(xyz, B, N, C, start, nullptr, idx_out, xyz_out, ws, ws_bytes, stream);
+}
+
+extern "C" int pcnbr_fps_len_f32(const float* xyz, int B, int N, int C, const int32_t* start, const int32_t* n_valid,
+                                 int32_t* idx_out, float* xyz_out, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
     using namespace pcnbr;
     if (!xyz || !start || !idx_out || B <= 0 || N <= 0 || C <= 0) return PCNBR_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
@@ -323,7 +337,7 @@ extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_
 #define PCNBR_FPS_CASE(P, TT)                                                                                        \
     if (ppt == P && T == TT) {                                                                                       \
         PCNBR_TIMED("fps_reg_kernel", s, wb, wf,                                                                     \
-                    (fps_reg_kernel<P, TT><<<B, TT, 0, s>>>(xyz, N, C, start, idx_out, xyz_out)));                   \
+                    (fps_reg_kernel<P, TT><<<B, TT, 0, s>>>(xyz, N, C, start, n_valid, idx_out, xyz_out)));                   \
         PCNBR_CHECK_LAUNCH();                                                                                        \
         return 0;                                                                                                    \
     }
@@ -343,11 +357,11 @@ extern "C" int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_
         const int CL = N <= 4 * 8192 ? 4 : 8;
         const double wfc = 10.0 * B * (double)N * C * 2.0 * 148.0 / (double)(B * CL < 148 ? B * CL : 148);
         int rc = 0;
-        PCNBR_TIMED("fps_cluster_kernel", s, wb, wfc, (rc = fps_launch_cluster<8, 1024>(CL, B, xyz, N, C, start, idx_out, xyz_out, s)));
+        PCNBR_TIMED("fps_cluster_kernel", s, wb, wfc, (rc = fps_launch_cluster<8, 1024>(CL, B, xyz, N, C, start, n_valid, idx_out, xyz_out, s)));
         if (rc) return rc;
     } else {
         if (!ws || ws_bytes < pcnbr_fps_ws_bytes(B, N)) return PCNBR_E_WORKSPACE;
-        PCNBR_TIMED("fps_big_kernel", s, wb, wf, (fps_big_kernel<1024><<<B, 1024, 0, s>>>(xyz, N, C, start, idx_out, xyz_out, (float*)ws)));
+        PCNBR_TIMED("fps_big_kernel", s, wb, wf, (fps_big_kernel<1024><<<B, 1024, 0, s>>>(xyz, N, C, start, n_valid, idx_out, xyz_out, (float*)ws)));
     }
     PCNBR_CHECK_LAUNCH();
     return 0;

@@ -27,10 +27,12 @@ constexpr int GRID_DIM_CAP = 512;          // cells per axis (keeps fp32 cell co
 // One CTA per cloud: bounding box -> grid origin, cell edge, dimensions.  h_req > 0: requested edge (ball query);
 // h_req <= 0: edge from the density, ~ppc points per cell of the bounding box (k-NN).
 __global__ void __launch_bounds__(256)
-grid_bbox_kernel(const float* __restrict__ p, int N, float h_req, float ppc, GridParams* __restrict__ gp) {
+grid_bbox_kernel(const float* __restrict__ p, int N_alloc, const int32_t* __restrict__ n_src, float h_req, float ppc,
+                 GridParams* __restrict__ gp) {
     __shared__ float red[6][8];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* __restrict__ pb = p + (size_t)b * N * 3;
+    const int N = len_valid(n_src, b, N_alloc);              // length-aware form: the padding rows are not binned
+    const float* __restrict__ pb = p + (size_t)b * N_alloc * 3;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (int n = threadIdx.x; n < N; n += 256)
 #pragma unroll
@@ -90,10 +92,10 @@ __device__ __forceinline__ int grid_clamp(int c, int n) { return c < 0 ? 0 : (c 
 
 // cell of every point (clamped into the grid) + per-cell counts (integer atomics: the counts do not depend on the order)
 __global__ void __launch_bounds__(256)
-grid_count_kernel(const float* __restrict__ p, int N, const GridParams* __restrict__ gp, int32_t* __restrict__ cellid,
-                  int32_t* __restrict__ count) {
+grid_count_kernel(const float* __restrict__ p, int N, const int32_t* __restrict__ n_src, const GridParams* __restrict__ gp,
+                  int32_t* __restrict__ cellid, int32_t* __restrict__ count) {
     const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-    if (n >= N) return;
+    if (n >= len_valid(n_src, b, N)) return;
     const GridParams g = gp[b];
     const float* __restrict__ s = p + ((size_t)b * N + n) * 3;
     const int cx = grid_clamp(grid_coord(s[0], g.ox, g.inv_h, g.nx), g.nx), cy = grid_clamp(grid_coord(s[1], g.oy, g.inv_h, g.ny), g.ny),
@@ -145,10 +147,10 @@ grid_scan_kernel(int32_t* __restrict__ count, int32_t* __restrict__ cursor, cons
 // points grouped by cell: (x, y, z, index) as one float4 each (the order inside a cell is arbitrary: every consumer sorts
 // its candidates by (d2, index))
 __global__ void __launch_bounds__(256)
-grid_fill_kernel(const float* __restrict__ p, int N, const int32_t* __restrict__ cellid, int32_t* __restrict__ cursor,
-                 float4* __restrict__ sorted) {
+grid_fill_kernel(const float* __restrict__ p, int N, const int32_t* __restrict__ n_src, const int32_t* __restrict__ cellid,
+                 int32_t* __restrict__ cursor, float4* __restrict__ sorted) {
     const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-    if (n >= N) return;
+    if (n >= len_valid(n_src, b, N)) return;
     const float* __restrict__ s = p + ((size_t)b * N + n) * 3;
     const int c = cellid[(size_t)b * N + n];
     const int pos = atomicAdd(&cursor[(size_t)b * GRID_CELL_CAP + c], 1);
@@ -239,16 +241,19 @@ __device__ __forceinline__ void grid_scan_cube1(const float4* __restrict__ pts, 
 // Ball query: one warp per query, the 3 x 3 x 3 cells around it (3 x-adjacent cells are one contiguous run).
 template <int NSLOT>
 __global__ void __launch_bounds__(256)
-ball_grid_kernel(const float* __restrict__ q, int M, int N, float r2, int K, const GridParams* __restrict__ gp,
+ball_grid_kernel(const float* __restrict__ q, int M, int N_alloc, float r2, int K, const int32_t* __restrict__ n_qry,
+                 const int32_t* __restrict__ n_src, const GridParams* __restrict__ gp,
                  const int32_t* __restrict__ start, const float4* __restrict__ sorted, int32_t* __restrict__ idx) {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = blockIdx.x * 8 + warp;
     if (m >= M) return;
+    const int N = len_valid(n_src, b, N_alloc);
+    if (m >= len_valid(n_qry, b, M)) { len_fill_row(idx, nullptr, ((size_t)b * M + m) * K, K, lane); return; }
     const GridParams g = gp[b];
     const float* __restrict__ c = q + ((size_t)b * M + m) * 3;
     const float qx = c[0], qy = c[1], qz = c[2];
     const int32_t* __restrict__ st = start + (size_t)b * (GRID_CELL_CAP + 1);
-    const float4* __restrict__ pts = sorted + (size_t)b * N;
+    const float4* __restrict__ pts = sorted + (size_t)b * N_alloc;
     const int cx = grid_coord(qx, g.ox, g.inv_h, g.nx), cy = grid_coord(qy, g.oy, g.inv_h, g.ny), cz = grid_coord(qz, g.oz, g.inv_h, g.nz);
     WarpList<NSLOT> list;
     list.init();
@@ -278,12 +283,14 @@ ball_grid_kernel(const float* __restrict__ q, int M, int N, float r2, int K, con
 
 // k-NN (k <= 32): rings of cells until the k-th best distance lies strictly inside the scanned cube.
 __global__ void __launch_bounds__(256)
-knn_grid_kernel(const float* __restrict__ q, int M, int N, int K, const GridParams* __restrict__ gp,
+knn_grid_kernel(const float* __restrict__ q, int M, int N, int K, const int32_t* __restrict__ n_qry,
+                const GridParams* __restrict__ gp,
                 const int32_t* __restrict__ start, const float4* __restrict__ sorted, int32_t* __restrict__ idx,
                 float* __restrict__ d2out) {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = blockIdx.x * 8 + warp;
     if (m >= M) return;
+    if (m >= len_valid(n_qry, b, M)) { len_fill_row(idx, d2out, ((size_t)b * M + m) * K, K, lane); return; }
     const GridParams g = gp[b];
     const float* __restrict__ c = q + ((size_t)b * M + m) * 3;
     const float qx = c[0], qy = c[1], qz = c[2];
@@ -330,7 +337,7 @@ knn_grid_kernel(const float* __restrict__ q, int M, int N, int K, const GridPara
     }
     if (lane < K) {
         const size_t o = ((size_t)b * M + m) * K + lane;
-        idx[o] = (int32_t)(uint32_t)list.v[0];
+        idx[o] = (int32_t)min((uint32_t)list.v[0], (uint32_t)(N - 1));     // (an empty slot -- K > valid sources -- stays in range)
         if (d2out) d2out[o] = ord2f((uint32_t)(list.v[0] >> 32));
     }
 }
@@ -358,17 +365,17 @@ static GridWs grid_carve(void* ws, int B, int N) {
 }
 
 // bin the B clouds p (B,N,3): edge h_req (ball query) or from the density (k-NN, ~ppc points per cell)
-static int grid_build(const float* p, int B, int N, float h_req, float ppc, const GridWs& w, cudaStream_t s) {
+static int grid_build(const float* p, int B, int N, const int32_t* n_src, float h_req, float ppc, const GridWs& w, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(w.count, 0, 4 * (size_t)B * (GRID_CELL_CAP + 1), s);
     if (e != cudaSuccess) return (int)e;
-    PCNBR_TIMED("grid_bbox_kernel", s, 12.0 * B * N, 0.0, (grid_bbox_kernel<<<B, 256, 0, s>>>(p, N, h_req, ppc, w.gp)));
+    PCNBR_TIMED("grid_bbox_kernel", s, 12.0 * B * N, 0.0, (grid_bbox_kernel<<<B, 256, 0, s>>>(p, N, n_src, h_req, ppc, w.gp)));
     PCNBR_CHECK_LAUNCH();
     const dim3 gn((N + 255) / 256, B);
-    PCNBR_TIMED("grid_count_kernel", s, 16.0 * B * N, 0.0, (grid_count_kernel<<<gn, 256, 0, s>>>(p, N, w.gp, w.cellid, w.count)));
+    PCNBR_TIMED("grid_count_kernel", s, 16.0 * B * N, 0.0, (grid_count_kernel<<<gn, 256, 0, s>>>(p, N, n_src, w.gp, w.cellid, w.count)));
     PCNBR_CHECK_LAUNCH();
     PCNBR_TIMED("grid_scan_kernel", s, 12.0 * B * GRID_CELL_CAP, 0.0, (grid_scan_kernel<<<B, 1024, 0, s>>>(w.count, w.cursor, w.gp)));
     PCNBR_CHECK_LAUNCH();
-    PCNBR_TIMED("grid_fill_kernel", s, 32.0 * B * N, 0.0, (grid_fill_kernel<<<gn, 256, 0, s>>>(p, N, w.cellid, w.cursor, w.sorted)));
+    PCNBR_TIMED("grid_fill_kernel", s, 32.0 * B * N, 0.0, (grid_fill_kernel<<<gn, 256, 0, s>>>(p, N, n_src, w.cellid, w.cursor, w.sorted)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -382,6 +389,13 @@ extern "C" size_t pcnbr_grid_ws_bytes(int B, int N) { return grid_carve(nullptr,
 // Same result as pcnbr_ball_query_f32, bit for bit.  ws: pcnbr_grid_ws_bytes(B, N).
 extern "C" int pcnbr_ball_query_grid_f32(const float* q, const float* p, int B, int M, int N, float r2, int K, int32_t* idx,
                                          void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    return pcnbr_ball_query_len_f32(q, p, B, M, N, r2, K, nullptr, nullptr, idx, ws, ws_bytes, stream);
+}
+
+// Length-aware ball query: cloud b has n_src[b] real points and n_qry[b] real centroids (NULL: all).  ws == NULL: M x N scan.
+extern "C" int pcnbr_ball_query_len_f32(const float* q, const float* p, int B, int M, int N, float r2, int K, const int32_t* n_qry,
+                                        const int32_t* n_src, int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    if (!ws) return select_ball_len(q, p, B, M, N, r2, K, n_qry, n_src, idx, (cudaStream_t)stream);
     if (!q || !p || !idx || B <= 0 || M <= 0 || N <= 0 || K <= 0 || K > N || !(r2 >= 0.f)) return PCNBR_E_BADARG;
     if (K > 128) return PCNBR_E_TOOLARGE;
     if (!ws || ws_bytes < pcnbr_grid_ws_bytes(B, N)) return PCNBR_E_WORKSPACE;
@@ -390,15 +404,15 @@ extern "C" int pcnbr_ball_query_grid_f32(const float* q, const float* p, int B, 
     // cell edge: 0.1 % above the radius -- the fp32 test d2 <= r2 can accept a point a few ulps beyond r, and the cell
     // coordinates carry ~1e-5 cells of rounding
     const float h = sqrtf(r2) * 1.001f + 1e-30f;
-    int rc = grid_build(p, B, N, h, 0.f, w, s);
+    int rc = grid_build(p, B, N, n_src, h, 0.f, w, s);
     if (rc) return rc;
     const dim3 grid((M + 7) / 8, B);
     // K2: compulsory bytes 12 (N + M) + 4 M K per cloud; the flops are what the scan of 27 cells costs
     // (~27 * N / ncell candidates per query), stated as 8 flop per candidate pair at the mean cell occupancy
     const double wb = (double)B * (12.0 * (N + M) + 4.0 * M * K), wf = 8.0 * B * (double)M * 27.0 * 2.0;
-    if (K <= 32)      PCNBR_TIMED("ball_grid_kernel", s, wb, wf, (ball_grid_kernel<1><<<grid, 256, 0, s>>>(q, M, N, r2, K, w.gp, w.count, w.sorted, idx)));
-    else if (K <= 64) PCNBR_TIMED("ball_grid_kernel", s, wb, wf, (ball_grid_kernel<2><<<grid, 256, 0, s>>>(q, M, N, r2, K, w.gp, w.count, w.sorted, idx)));
-    else              PCNBR_TIMED("ball_grid_kernel", s, wb, wf, (ball_grid_kernel<4><<<grid, 256, 0, s>>>(q, M, N, r2, K, w.gp, w.count, w.sorted, idx)));
+    if (K <= 32)      PCNBR_TIMED("ball_grid_kernel", s, wb, wf, (ball_grid_kernel<1><<<grid, 256, 0, s>>>(q, M, N, r2, K, n_qry, n_src, w.gp, w.count, w.sorted, idx)));
+    else if (K <= 64) PCNBR_TIMED("ball_grid_kernel", s, wb, wf, (ball_grid_kernel<2><<<grid, 256, 0, s>>>(q, M, N, r2, K, n_qry, n_src, w.gp, w.count, w.sorted, idx)));
+    else              PCNBR_TIMED("ball_grid_kernel", s, wb, wf, (ball_grid_kernel<4><<<grid, 256, 0, s>>>(q, M, N, r2, K, n_qry, n_src, w.gp, w.count, w.sorted, idx)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -406,16 +420,24 @@ extern "C" int pcnbr_ball_query_grid_f32(const float* q, const float* p, int B, 
 // Same result as pcnbr_knn_direct_f32 (k <= 32), bit for bit.  ws: pcnbr_grid_ws_bytes(B, N).
 extern "C" int pcnbr_knn_direct_grid_f32(const float* q, const float* p, int B, int M, int N, int K, int32_t* idx, float* d2,
                                          void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    return pcnbr_knn_direct_len_f32(q, p, B, M, N, K, nullptr, nullptr, idx, d2, ws, ws_bytes, stream);
+}
+
+// Length-aware k-NN (direct distances): n_qry[b] real queries, n_src[b] real sources (NULL: all).  ws == NULL: M x N scan.
+extern "C" int pcnbr_knn_direct_len_f32(const float* q, const float* p, int B, int M, int N, int K, const int32_t* n_qry,
+                                        const int32_t* n_src, int32_t* idx, float* d2, void* ws, size_t ws_bytes,
+                                        pcnbr_stream_t stream) {
+    if (!ws) return select_knn_len(q, p, B, M, N, K, n_qry, n_src, idx, d2, (cudaStream_t)stream);
     if (!q || !p || !idx || B <= 0 || M <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
     if (K > 32) return PCNBR_E_TOOLARGE;
     if (!ws || ws_bytes < pcnbr_grid_ws_bytes(B, N)) return PCNBR_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     const GridWs w = grid_carve(ws, B, N);
-    int rc = grid_build(p, B, N, 0.f, 2.0f, w, s);
+    int rc = grid_build(p, B, N, n_src, 0.f, 2.0f, w, s);
     if (rc) return rc;
     const double wb = (double)B * (12.0 * (N + M) + 8.0 * M * K), wf = 8.0 * B * (double)M * 27.0 * 2.0;
     PCNBR_TIMED("knn_grid_kernel", s, wb, wf,
-                (knn_grid_kernel<<<dim3((M + 7) / 8, B), 256, 0, s>>>(q, M, N, K, w.gp, w.count, w.sorted, idx, d2)));
+                (knn_grid_kernel<<<dim3((M + 7) / 8, B), 256, 0, s>>>(q, M, N, K, n_qry, w.gp, w.count, w.sorted, idx, d2)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

@@ -183,13 +183,15 @@ __device__ __host__ __forceinline__ uint32_t tail_offset(int r, int c) {
 constexpr int TC_MEAN_CHUNKS = 16;
 constexpr int TC_PART = 65;
 __global__ void __launch_bounds__(256)
-knn_tc_mean_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, float* __restrict__ part) {
+knn_tc_mean_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, const int32_t* __restrict__ n_valid,
+                   float* __restrict__ part) {
     __shared__ float red[256], redm[256];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int groups = 256 / F;                                   // F <= 64
     const int f = threadIdx.x % F, g = threadIdx.x / F;
-    const int per = (N + TC_MEAN_CHUNKS - 1) / TC_MEAN_CHUNKS;
-    const int n0 = chunk * per, n1 = min(N, n0 + per);
+    const int NV = len_valid(n_valid, b, N);                      // length-aware form: the padding rows do not exist
+    const int per = (NV + TC_MEAN_CHUNKS - 1) / TC_MEAN_CHUNKS;
+    const int n0 = min(NV, chunk * per), n1 = min(NV, n0 + per);
     const float* __restrict__ xb = x + (size_t)b * F * N;
     float acc = 0.f, mx = 0.f;
     if (g < groups)
@@ -219,16 +221,17 @@ knn_tc_mean_kernel(const float* __restrict__ x, int F, int N, long sf, long sn, 
 // scal[b] = {max |x|^2, max |x'|^2, S, -}
 __global__ void __launch_bounds__(256)
 knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, const float* __restrict__ xx,
-                   int F, int N, int Npad, long sf, long sn, float* __restrict__ xt, __half* __restrict__ ymain,
-                   uint8_t* __restrict__ tailb, float* __restrict__ xxc, uint32_t* __restrict__ scal) {
+                   int F, int N, int Npad, long sf, long sn, const int32_t* __restrict__ n_valid, float* __restrict__ xt,
+                   __half* __restrict__ ymain, uint8_t* __restrict__ tailb, float* __restrict__ xxc, uint32_t* __restrict__ scal) {
     __shared__ float mu[64];
     __shared__ float s_scale;
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NV = len_valid(n_valid, b, N);                      // rows >= NV are treated like the rows >= N: padding columns
     if (threadIdx.x < 64) {
         float m = 0.f;
         if (threadIdx.x < F)
             for (int c = 0; c < TC_MEAN_CHUNKS; ++c) m += part[((size_t)b * TC_MEAN_CHUNKS + c) * TC_PART + threadIdx.x];
-        mu[threadIdx.x] = m / (float)N;
+        mu[threadIdx.x] = m / (float)NV;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -249,7 +252,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, 
     for (int n = blockIdx.x * 8 + warp; n < Npad; n += gridDim.x * 8) {
         const int f0 = 2 * lane, f1 = 2 * lane + 1;
         float v0 = 0.f, v1 = 0.f;
-        if (n < N) {
+        if (n < NV) {
             if (f0 < F) {
                 const float v = xb[(size_t)f0 * sf + (size_t)n * sn];
                 v0 = __fsub_rn(v, mu[f0]);
@@ -271,7 +274,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, 
             __half t[8];
             for (int i = 0; i < 8; ++i) t[i] = __float2half_rn(0.f);
             t[3] = t[4] = t[5] = __float2half_rn(1.0f);
-            if (n < N) {
+            if (n < NV) {
                 xxc[(size_t)b * N + n] = ss;
                 split3_f16(-0.5f * ss * inv * inv, t[0], t[1], t[2]);
                 t[6] = __float2half_ru(sqrtf(ss) * inv * 1.0001f);            // nb_j >= |a_j|
@@ -284,7 +287,7 @@ knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, 
         } else if (lane == 1) {
             *reinterpret_cast<uint4*>(trow + tail_offset(r, 1)) = make_uint4(0, 0, 0, 0);
         }
-        if (n < N) {
+        if (n < NV) {
             mxc = fmaxf(mxc, ss);
             mx = fmaxf(mx, xx[(size_t)b * N + n]);
         }
@@ -301,7 +304,7 @@ template <int KSTEPS, bool DUMP>      // KSTEPS = ceil(F / 16); DUMP: also write
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __restrict__ tailb,
               const float* __restrict__ xx, const float* __restrict__ xxc, const uint32_t* __restrict__ scal,
-              int B, int N, int Npad, int K, float c_ref,
+              int B, int N, int Npad, int K, float c_ref, const int32_t* __restrict__ n_valid,
               int32_t* __restrict__ qcnt, uint16_t* __restrict__ qidx, float* __restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (128B-swizzle atoms) by OFFSET, so the compiler keeps the shared address space
@@ -321,8 +324,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
     uint32_t* tmem_slot = (uint32_t*)(bars + 11 + 2 * TC_RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int RT = (Npad + TC_ROWS - 1) / TC_ROWS, CT = Npad / TC_N;
+    const int RT = (Npad + TC_ROWS - 1) / TC_ROWS;
     const int units = B * RT;
+    // Length-aware form: cloud b has NV = n_valid[b] real points.  Work units whose rows are all padding and column tiles
+    // beyond the last real point are skipped -- by the three roles alike, so ring slots, TMEM buffers and phases stay in step.
+#define TC_UNIT_GEOMETRY()                                                     \
+    const int b = unit / RT, row0 = (unit - b * RT) * TC_ROWS;                 \
+    const int NV = len_valid(n_valid, b, N);                                   \
+    if (row0 >= NV) continue;                                                  \
+    const int CT = (NV + TC_N - 1) / TC_N
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_main) : "memory");
@@ -347,7 +357,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
         if (lane == 0) {
             uint32_t slot = 0, ring_phase = 0, a_phase = 0;
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-                const int b = unit / RT, row0 = (unit - b * RT) * TC_ROWS;
+                TC_UNIT_GEOMETRY();
                 const uint8_t* tb = tailb + (size_t)b * Npad * 32;
                 mbar_wait(a_empty, a_phase ^ 1);
                 mbar_expect_tx(a_full, 2 * TC_MAIN_BYTES);
@@ -378,6 +388,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
         const uint64_t sw_hi = ((uint64_t)(1024 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)2 << 29)) << 32 | ((uint64_t)1 << 16);
         uint32_t slot = 0, ring_phase = 0, a_phase = 0, t_phase = 0, tile = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            TC_UNIT_GEOMETRY();
             mbar_wait(a_full, a_phase);
             a_phase ^= 1;
             for (int pass = 0; pass < 2; ++pass) {
@@ -426,8 +437,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
         uint32_t tile = 0;
         const float NEG_INF = __int_as_float(0xff800000);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-            const int b = unit / RT, row = (unit - b * RT) * TC_ROWS + rloc;
-            const bool vrow = row < N;
+            TC_UNIT_GEOMETRY();
+            const int row = row0 + rloc;
+            const bool vrow = row < NV;
             const float xxi = vrow ? xx[(size_t)b * N + row] : 0.f;
             const float xxci = vrow ? xxc[(size_t)b * N + row] : 0.f;
             const float xm = __uint_as_float(scal[4 * b]), xcm = __uint_as_float(scal[4 * b + 1]);
@@ -533,7 +545,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
             const int wrow0 = (unit - b * RT) * TC_ROWS + rb * 128 + quarter * 32;
             const uint32_t* sQ32 = reinterpret_cast<const uint32_t*>(sQ + (rb * 128 + quarter * 32) * TC_QSTRIDE);
             for (int r = 0; r < 32; ++r) {
-                if (wrow0 + r >= N) break;
+                if (wrow0 + r >= NV) break;
                 uint32_t* dst = reinterpret_cast<uint32_t*>(qidx + ((size_t)b * N + wrow0 + r) * TC_QCAP);
                 dst[lane] = sQ32[r * (TC_QSTRIDE / 2) + lane];
                 if (lane < TC_QCAP / 2 - 32) dst[32 + lane] = sQ32[r * (TC_QSTRIDE / 2) + 32 + lane];
@@ -541,6 +553,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_main, const uint8_t* __rest
             __syncwarp();
         }
     }
+#undef TC_UNIT_GEOMETRY
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -584,12 +597,14 @@ __device__ __forceinline__ u64 rerank_key(const float* xj, const float* q, float
 // dynamic smem: 8 warps x (32 x RR_STRIDE + 64) floats
 __global__ void __launch_bounds__(256)
 knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx, const int32_t* __restrict__ qcnt,
-                     const uint16_t* __restrict__ qidx, int N, int F, int K, int32_t* __restrict__ idx,
-                     int32_t* __restrict__ stats) {
+                     const uint16_t* __restrict__ qidx, int N, int F, int K, const int32_t* __restrict__ n_valid,
+                     int32_t* __restrict__ idx, int32_t* __restrict__ stats) {
     extern __shared__ __align__(16) float rr_smem[];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * 8 + warp;
     if (i >= N) return;
+    const int NV = len_valid(n_valid, b, N);
+    if (i >= NV) { len_fill_row(idx, nullptr, ((size_t)b * N + i) * K, K, lane); return; }
     float* xs = rr_smem + warp * (32 * RR_STRIDE + 64);      // [32][RR_STRIDE]
     float* myq = xs + 32 * RR_STRIDE;                         // [64]
     const float* __restrict__ xb = xt + (size_t)b * N * F;
@@ -676,10 +691,10 @@ knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx,
     WarpList<1> list;
     list.init();
     u64 thr = PCNBR_KEY_MAX;
-    for (int c0 = 0; c0 < N; c0 += 32) {
+    for (int c0 = 0; c0 < NV; c0 += 32) {
         const int c = c0 + lane;
         u64 key = PCNBR_KEY_MAX;
-        if (c < N) {
+        if (c < NV) {
             const float* __restrict__ xj = xb + (size_t)c * F;        // direct (uncoalesced) reads: rare path
             float acc = __fmul_rn(myq[0], xj[0]);
             for (int f = 1; f < F; ++f) acc = __fmaf_rn(myq[f], xj[f], acc);
@@ -698,7 +713,7 @@ knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx,
             }
         }
     }
-    if (lane < K) out[lane] = (int32_t)(uint32_t)list.v[0];
+    if (lane < K) out[lane] = (int32_t)min((uint32_t)list.v[0], (uint32_t)(NV - 1));
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -774,8 +789,8 @@ bool knn_tc_supported(int F, int N, int K) {
 }
 
 template <int KSTEPS, bool DUMP>
-static int launch_tc(const CUtensorMap& mm, const TcWorkspace& w, int B, int F, int N, int K, float c_ref, float* dump,
-                     cudaStream_t s) {
+static int launch_tc(const CUtensorMap& mm, const TcWorkspace& w, int B, int F, int N, int K, float c_ref, const int32_t* n_valid,
+                     float* dump, cudaStream_t s) {
     const size_t smem = 2 * TC_MAIN_BYTES + 2 * TC_TAIL_BYTES + TC_RING * TC_SLOT_BYTES + TC_ROWS * TC_QSTRIDE * 2 + 40 * 8 + 1024;
     cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<KSTEPS, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -788,14 +803,14 @@ static int launch_tc(const CUtensorMap& mm, const TcWorkspace& w, int B, int F, 
     // K4: 2 N^2 F flop per cloud counted ONCE (whatever the pass count issues); compulsory bytes: the
     // fp16 operands (160 B per point) and the survivor queues
     PCNBR_TIMED("knn_tc_kernel", s, (double)B * N * (160.0 + 4.0 + 2.0 * TC_QCAP), 2.0 * B * (double)N * N * F,
-                (knn_tc_kernel<KSTEPS, DUMP><<<grid, TC_THREADS, smem, s>>>(mm, w.tailb, w.xx, w.xxc, w.scal, B, N, Npad, K, c_ref,
+                (knn_tc_kernel<KSTEPS, DUMP><<<grid, TC_THREADS, smem, s>>>(mm, w.tailb, w.xx, w.xxc, w.scal, B, N, Npad, K, c_ref, n_valid,
                                                                               w.qcnt, w.qidx, dump)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
 // x: (B,F,N) with strides (sf, sn).  idx (B,N,K).  dump: optional (B,N,N) pass-1 tensor-core scores (tests).
-int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int32_t* idx, void* ws,
+int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, const int32_t* n_valid, int32_t* idx, void* ws,
                float* dump, int32_t* stats_out, cudaStream_t s) {
     const bool point_major = (sf == 1 && sn == F);
     TcWorkspace w = tc_carve(ws, B, F, N, !point_major);
@@ -804,15 +819,15 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
     cudaError_t e = cudaMemsetAsync(w.scal, 0, (size_t)((uint8_t*)w.stats + 16 - (uint8_t*)w.scal), s);   // scal + stats
     if (e != cudaSuccess) return (int)e;
     // exact |x|^2 in the reference's summation order (select.cu); channel means; centred, scaled fp16 operands
-    int rc0 = launch_sumsq(x, B, F, N, sf, sn, w.xx, s);
+    int rc0 = launch_sumsq(x, B, F, N, sf, sn, n_valid, w.xx, s);
     if (rc0) return rc0;
     PCNBR_TIMED("knn_tc_mean_kernel", s, 4.0 * B * (double)N * F, (double)B * N * F,
-                (knn_tc_mean_kernel<<<dim3(TC_MEAN_CHUNKS, B), 256, 0, s>>>(x, F, N, sf, sn, w.part)));
+                (knn_tc_mean_kernel<<<dim3(TC_MEAN_CHUNKS, B), 256, 0, s>>>(x, F, N, sf, sn, n_valid, w.part)));
     PCNBR_CHECK_LAUNCH();
     int pb = (Npad + 7) / 8;
     if (pb > 148) pb = 148;
     PCNBR_TIMED("knn_tc_prep_kernel", s, (double)B * N * (4.0 * F + 160.0 + 8.0), 6.0 * B * (double)N * F,
-                (knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, N, Npad, sf, sn, point_major ? nullptr : w.xt,
+                (knn_tc_prep_kernel<<<dim3(pb, B), 256, 0, s>>>(x, w.part, w.xx, F, N, Npad, sf, sn, n_valid, point_major ? nullptr : w.xt,
                                                                 w.ymain, w.tailb, w.xxc, w.scal)));
     PCNBR_CHECK_LAUNCH();
     CUtensorMap mm;
@@ -820,17 +835,17 @@ int knn_tc_run(const float* x, int B, int F, int N, long sf, long sn, int K, int
     if (rc) return rc;
     const float c_ref = 2.0f * (float)(F + 8) * 5.9604645e-8f;             // 2 (F+8) 2^-24, see TC_C_* above
     switch ((F + 15) / 16) {
-        case 1:  rc = dump ? launch_tc<1, true>(mm, w, B, F, N, K, c_ref, dump, s) : launch_tc<1, false>(mm, w, B, F, N, K, c_ref, dump, s); break;
-        case 2:  rc = dump ? launch_tc<2, true>(mm, w, B, F, N, K, c_ref, dump, s) : launch_tc<2, false>(mm, w, B, F, N, K, c_ref, dump, s); break;
-        case 3:  rc = dump ? launch_tc<3, true>(mm, w, B, F, N, K, c_ref, dump, s) : launch_tc<3, false>(mm, w, B, F, N, K, c_ref, dump, s); break;
-        default: rc = dump ? launch_tc<4, true>(mm, w, B, F, N, K, c_ref, dump, s) : launch_tc<4, false>(mm, w, B, F, N, K, c_ref, dump, s); break;
+        case 1:  rc = dump ? launch_tc<1, true>(mm, w, B, F, N, K, c_ref, n_valid, dump, s) : launch_tc<1, false>(mm, w, B, F, N, K, c_ref, n_valid, dump, s); break;
+        case 2:  rc = dump ? launch_tc<2, true>(mm, w, B, F, N, K, c_ref, n_valid, dump, s) : launch_tc<2, false>(mm, w, B, F, N, K, c_ref, n_valid, dump, s); break;
+        case 3:  rc = dump ? launch_tc<3, true>(mm, w, B, F, N, K, c_ref, n_valid, dump, s) : launch_tc<3, false>(mm, w, B, F, N, K, c_ref, n_valid, dump, s); break;
+        default: rc = dump ? launch_tc<4, true>(mm, w, B, F, N, K, c_ref, n_valid, dump, s) : launch_tc<4, false>(mm, w, B, F, N, K, c_ref, n_valid, dump, s); break;
     }
     if (rc) return rc;
     const size_t rr_smem = 8 * (32 * RR_STRIDE + 64) * sizeof(float);
     e = cudaFuncSetAttribute(knn_tc_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem);
     if (e != cudaSuccess) return (int)e;
     PCNBR_TIMED("knn_tc_rerank_kernel", s, (double)B * N * (4.0 * F + 8.0 + 2.0 * TC_QCAP + 4.0 * K), 2.0 * B * (double)N * F * K,
-                (knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, rr_smem, s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, idx, w.stats)));
+                (knn_tc_rerank_kernel<<<dim3((N + 7) / 8, B), 256, rr_smem, s>>>(xt, w.xx, w.qcnt, w.qidx, N, F, K, n_valid, idx, w.stats)));
     PCNBR_CHECK_LAUNCH();
     if (stats_out) {
         e = cudaMemcpyAsync(stats_out, w.stats, 8, cudaMemcpyDeviceToDevice, s);

@@ -23,13 +23,17 @@ constexpr int SEL_WARPS = 16;    // queries per CTA: the tile staging is shared 
 
 template <int NSLOT, bool RADIUS>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
-select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N, float r2, int K,
+select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N_alloc, float r2, int K,
+                  const int32_t* __restrict__ n_qry, const int32_t* __restrict__ n_src,
                   int32_t* __restrict__ idx, float* __restrict__ d2out) {
     __shared__ float4 spt[SEL_TILE];                      // (x, y, z, -) per source point: one LDS.128 per point
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
-    const bool active = m < M;
-    const float* __restrict__ pb = p + (size_t)b * N * 3;
+    // length-aware form (zero-padded batches): only the first n_src[b] sources / n_qry[b] queries of cloud b exist
+    const int N = len_valid(n_src, b, N_alloc), Mv = len_valid(n_qry, b, M);
+    if (m >= Mv && m < M) len_fill_row(idx, d2out, ((size_t)b * M + m) * K, K, lane);
+    const bool active = m < Mv;
+    const float* __restrict__ pb = p + (size_t)b * N_alloc * 3;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) {
         const float* c = q + ((size_t)b * M + m) * 3;
@@ -144,7 +148,7 @@ select_xyz_kernel(const float* __restrict__ q, const float* __restrict__ p, int 
         const int pos = s * 32 + lane;
         if (pos < K) {
             const size_t o = ((size_t)b * M + m) * K + pos;
-            idx[o] = (int32_t)(uint32_t)list.v[s];
+            idx[o] = (int32_t)min((uint32_t)list.v[s], (uint32_t)(N - 1));      // (an empty slot -- K > valid sources -- stays in range)
             if (d2out) d2out[o] = ord2f((uint32_t)(list.v[s] >> 32));
         }
     }
@@ -179,13 +183,16 @@ __device__ __forceinline__ float cascade_sumsq(const float* __restrict__ xp, int
 }
 
 __global__ void sumsq_cascade_kernel(const float* __restrict__ x, int F, int N, long sf, long sn,
-                                     float* __restrict__ xx) {
+                                     const int32_t* __restrict__ n_valid, float* __restrict__ xx) {
     const int b = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const float* __restrict__ xp = x + (size_t)b * F * N + (size_t)n * sn;
+    // which columns take ATen's vectorised cascade depends on the length of the cloud AS THE REFERENCE SEES IT: a cloud of a
+    // zero-padded batch that is evaluated alone (length-aware form) has n_valid[b] columns
+    const int NV = len_valid(n_valid, b, N);
     float r;
-    if (n < (N & ~31)) {
+    if (n < (NV & ~31)) {
         if (sf == 1 && (F & 3) == 0 && F <= 64 && (((uintptr_t)xp) & 15) == 0) {
             // point-major rows: 16-byte loads (4x fewer L1 wavefronts than scalar loads of 256-byte-strided rows);
             // same cascade: runs of 16 into acc0, folded into acc1; no higher level below 256 rows
@@ -220,8 +227,8 @@ __global__ void sumsq_cascade_kernel(const float* __restrict__ x, int F, int N, 
 // dynamic smem: xs[F][TP] (TP = tile + 1 pad when staged transposed) + xq[WARPS][F] + sxx[tile]
 template <int NSLOT>
 __global__ void __launch_bounds__(1024)
-knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int F, int N, long sf, long sn,
-                  int K, int tile, int32_t* __restrict__ idx) {
+knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int F, int N_alloc, long sf, long sn,
+                  int K, int tile, const int32_t* __restrict__ n_valid, int32_t* __restrict__ idx) {
     extern __shared__ float smem[];
     const int warps = blockDim.x >> 5;
     const int TP = tile + 1;
@@ -230,9 +237,11 @@ knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
     float* sxx = xq + (size_t)warps * F;     // [tile]
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * warps + warp;
+    const int N = len_valid(n_valid, b, N_alloc);
+    if (i >= N && i < N_alloc) len_fill_row(idx, nullptr, ((size_t)b * N_alloc + i) * K, K, lane);
     const bool active = i < N;
-    const float* __restrict__ xb = x + (size_t)b * F * N;
-    const float* __restrict__ xxb = xx + (size_t)b * N;
+    const float* __restrict__ xb = x + (size_t)b * F * N_alloc;
+    const float* __restrict__ xxb = xx + (size_t)b * N_alloc;
 
     if (active)
         for (int f = lane; f < F; f += 32) xq[warp * F + f] = xb[(size_t)f * sf + (size_t)i * sn];
@@ -286,13 +295,13 @@ knn_expand_kernel(const float* __restrict__ x, const float* __restrict__ xx, int
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         const int pos = s * 32 + lane;
-        if (pos < K) idx[((size_t)b * N + i) * K + pos] = (int32_t)(uint32_t)list.v[s];
+        if (pos < K) idx[((size_t)b * N_alloc + i) * K + pos] = (int32_t)min((uint32_t)list.v[s], (uint32_t)(N - 1));
     }
 }
 
-int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, float* xx, cudaStream_t s) {
+int launch_sumsq(const float* x, int B, int F, int N, long sf, long sn, const int32_t* n_valid, float* xx, cudaStream_t s) {
     PCNBR_TIMED("sumsq_cascade_kernel", s, 4.0 * B * ((double)N * F + N), 2.0 * B * (double)N * F,
-                (sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, sf, sn, xx)));
+                (sumsq_cascade_kernel<<<dim3((N + 255) / 256, B), 256, 0, s>>>(x, F, N, sf, sn, n_valid, xx)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -321,12 +330,13 @@ struct MsgScales {
 };
 
 __global__ void __launch_bounds__(256)
-ball_derive_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N, int Kall, float r2max,
-                   const int32_t* __restrict__ idx_all, const float* __restrict__ d2_all, MsgScales sc) {
+ball_derive_kernel(const float* __restrict__ q, const float* __restrict__ p, int M, int N_alloc, int Kall, float r2max,
+                   const int32_t* __restrict__ n_src, const int32_t* __restrict__ idx_all, const float* __restrict__ d2_all, MsgScales sc) {
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= M) return;
-    const float* __restrict__ pb = p + (size_t)b * N * 3;
+    const int N = len_valid(n_src, b, N_alloc);
+    const float* __restrict__ pb = p + (size_t)b * N_alloc * 3;
     const float* __restrict__ qp = q + ((size_t)b * M + m) * 3;
     const float qx = qp[0], qy = qp[1], qz = qp[2];
     const size_t row = ((size_t)b * M + m) * Kall;
@@ -363,30 +373,42 @@ ball_derive_kernel(const float* __restrict__ q, const float* __restrict__ p, int
 using namespace pcnbr;
 
 template <bool RADIUS>
-static int launch_select(const float* q, const float* p, int B, int M, int N, float r2, int K, int32_t* idx,
-                         float* d2, cudaStream_t s) {
+static int launch_select(const float* q, const float* p, int B, int M, int N, float r2, int K, const int32_t* n_qry,
+                         const int32_t* n_src, int32_t* idx, float* d2, cudaStream_t s) {
     if (!q || !p || !idx || B <= 0 || M <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
     if (K > 128) return PCNBR_E_TOOLARGE;
     dim3 grid((M + SEL_WARPS - 1) / SEL_WARPS, B), block(SEL_WARPS * 32);
     // K2/K3: 8 M N flop + compares; compulsory 12 (N + M) + 4 M K (+ 4 M K distances) bytes per cloud
     const double wb = (double)B * (12.0 * (N + M) + (d2 ? 8.0 : 4.0) * M * K), wf = 8.0 * B * (double)M * N;
     const char* nm = RADIUS ? "select_xyz_kernel<ball>" : "select_xyz_kernel<knn>";
-    if (K <= 32)      PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<1, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2)));
-    else if (K <= 64) PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<2, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2)));
-    else              PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<4, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, idx, d2)));
+    if (K <= 32)      PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<1, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, n_qry, n_src, idx, d2)));
+    else if (K <= 64) PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<2, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, n_qry, n_src, idx, d2)));
+    else              PCNBR_TIMED(nm, s, wb, wf, (select_xyz_kernel<4, RADIUS><<<grid, block, 0, s>>>(q, p, M, N, r2, K, n_qry, n_src, idx, d2)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int pcnbr_ball_query_f32(const float* q, const float* p, int B, int M, int N, float r2, int K,
                                     int32_t* idx, pcnbr_stream_t stream) {
-    return launch_select<true>(q, p, B, M, N, r2, K, idx, nullptr, (cudaStream_t)stream);
+    return launch_select<true>(q, p, B, M, N, r2, K, nullptr, nullptr, idx, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int pcnbr_knn_direct_f32(const float* q, const float* p, int B, int M, int N, int K, int32_t* idx,
                                     float* d2, pcnbr_stream_t stream) {
-    return launch_select<false>(q, p, B, M, N, 0.f, K, idx, d2, (cudaStream_t)stream);
+    return launch_select<false>(q, p, B, M, N, 0.f, K, nullptr, nullptr, idx, d2, (cudaStream_t)stream);
 }
+
+namespace pcnbr {
+// scan forms with per-cloud lengths (grid.cu dispatches here for small clouds)
+int select_ball_len(const float* q, const float* p, int B, int M, int N, float r2, int K, const int32_t* n_qry, const int32_t* n_src,
+                    int32_t* idx, cudaStream_t s) {
+    return launch_select<true>(q, p, B, M, N, r2, K, n_qry, n_src, idx, nullptr, s);
+}
+int select_knn_len(const float* q, const float* p, int B, int M, int N, int K, const int32_t* n_qry, const int32_t* n_src,
+                   int32_t* idx, float* d2, cudaStream_t s) {
+    return launch_select<false>(q, p, B, M, N, 0.f, K, n_qry, n_src, idx, d2, s);
+}
+}  // namespace pcnbr
 
 extern "C" size_t pcnbr_ball_query_multi_ws_bytes(int B, int M, int Kmax) {
     return (size_t)B * (size_t)M * (size_t)Kmax * (sizeof(int32_t) + sizeof(float));
@@ -394,10 +416,16 @@ extern "C" size_t pcnbr_ball_query_multi_ws_bytes(int B, int M, int Kmax) {
 
 extern "C" int pcnbr_ball_query_multi_f32(const float* q, const float* p, int B, int M, int N, const float* r2, const int* K,
                                           int R, int32_t* const* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    return pcnbr_ball_query_multi_len_f32(q, p, B, M, N, r2, K, R, nullptr, idx, ws, ws_bytes, stream);
+}
+
+extern "C" int pcnbr_ball_query_multi_len_f32(const float* q, const float* p, int B, int M, int N, const float* r2, const int* K,
+                                              int R, const int32_t* n_src, int32_t* const* idx, void* ws, size_t ws_bytes,
+                                              pcnbr_stream_t stream) {
     if (!r2 || !K || !idx || R <= 0) return PCNBR_E_BADARG;
     if (R > MSG_MAXR) return PCNBR_E_TOOLARGE;
     cudaStream_t s = (cudaStream_t)stream;
-    if (R == 1) return launch_select<true>(q, p, B, M, N, r2[0], K[0], idx[0], nullptr, s);
+    if (R == 1) return launch_select<true>(q, p, B, M, N, r2[0], K[0], nullptr, n_src, idx[0], nullptr, s);
     MsgScales sc;
     sc.R = R;
     float r2max = r2[0];
@@ -411,12 +439,12 @@ extern "C" int pcnbr_ball_query_multi_f32(const float* q, const float* p, int B,
     if (!ws || ws_bytes < pcnbr_ball_query_multi_ws_bytes(B, M, Kall)) return PCNBR_E_WORKSPACE;
     int32_t* idx_all = (int32_t*)ws;
     float* d2_all = (float*)(idx_all + (size_t)B * M * Kall);
-    int rc = launch_select<true>(q, p, B, M, N, r2max, Kall, idx_all, d2_all, s);
+    int rc = launch_select<true>(q, p, B, M, N, r2max, Kall, nullptr, n_src, idx_all, d2_all, s);
     if (rc) return rc;
     double out_bytes = 0.0;
     for (int i = 0; i < R; ++i) out_bytes += 4.0 * K[i];
     PCNBR_TIMED("ball_derive_kernel", s, (double)B * M * (8.0 * Kall + out_bytes + 12.0) + 12.0 * B * N, 0.0,
-                (ball_derive_kernel<<<dim3((M + 7) / 8, B), 256, 0, s>>>(q, p, M, N, Kall, r2max, idx_all, d2_all, sc)));
+                (ball_derive_kernel<<<dim3((M + 7) / 8, B), 256, 0, s>>>(q, p, M, N, Kall, r2max, n_src, idx_all, d2_all, sc)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }
@@ -438,19 +466,24 @@ extern "C" int pcnbr_knn_tc_debug_f32(const float* x, int B, int F, int N, long 
     if (!x || !idx || B <= 0 || F <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
     if (!knn_tc_supported(F, N, K)) return PCNBR_E_TOOLARGE;
     if (!ws || ws_bytes < pcnbr_knn_expand_ws_bytes(B, F, N, K)) return PCNBR_E_WORKSPACE;
-    return knn_tc_run(x, B, F, N, stride_f, stride_n, K, idx, ws, scores, stats, (cudaStream_t)stream);
+    return knn_tc_run(x, B, F, N, stride_f, stride_n, K, nullptr, idx, ws, scores, stats, (cudaStream_t)stream);
 }
 
 extern "C" int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
                                     int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
+    return pcnbr_knn_expand_len_f32(x, B, F, N, stride_f, stride_n, K, nullptr, idx, ws, ws_bytes, stream);
+}
+
+extern "C" int pcnbr_knn_expand_len_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
+                                        const int32_t* n_valid, int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream) {
     if (!x || !idx || B <= 0 || F <= 0 || N <= 0 || K <= 0 || K > N) return PCNBR_E_BADARG;
     if (K > 128 || F > 256) return PCNBR_E_TOOLARGE;
     if (!ws || ws_bytes < pcnbr_knn_expand_ws_bytes(B, F, N, K)) return PCNBR_E_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     if (use_tensor_cores(F, N, K))
-        return knn_tc_run(x, B, F, N, stride_f, stride_n, K, idx, ws, nullptr, nullptr, s);
+        return knn_tc_run(x, B, F, N, stride_f, stride_n, K, n_valid, idx, ws, nullptr, nullptr, s);
     float* xx = (float*)ws;
-    int rc = launch_sumsq(x, B, F, N, stride_f, stride_n, xx, s);
+    int rc = launch_sumsq(x, B, F, N, stride_f, stride_n, n_valid, xx, s);
     if (rc) return rc;
     const int warps = (F >= 16) ? 32 : 8;
     const int tile = expand_tile(F);
@@ -462,7 +495,7 @@ extern "C" int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long st
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         if (e != cudaSuccess) return (int)e;                                                             \
         PCNBR_TIMED("knn_expand_kernel", s, (double)B * (4.0 * N * F + 4.0 * N * K), 2.0 * B * (double)N * N * F,      \
-                    (knn_expand_kernel<NS><<<grid, block, smem, s>>>(x, xx, F, N, stride_f, stride_n, K, tile, idx)));  \
+                    (knn_expand_kernel<NS><<<grid, block, smem, s>>>(x, xx, F, N, stride_f, stride_n, K, tile, n_valid, idx)));  \
     } while (0)
     if (K <= 32)      PCNBR_LAUNCH_EXPAND(1);
     else if (K <= 64) PCNBR_LAUNCH_EXPAND(2);

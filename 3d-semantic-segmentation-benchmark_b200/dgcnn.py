@@ -18,10 +18,11 @@ from . import ops
 __all__ = ["knn", "get_graph_feature", "EdgeConv", "DGCNN", "DGCNNWithColor", "get_model", "get_loss"]
 
 
-def knn(x: torch.Tensor, k: int) -> torch.Tensor:
+def knn(x: torch.Tensor, k: int, lengths=None) -> torch.Tensor:
     """x (B,F,N) -> LongTensor (B,N,k) of the k nearest points in feature space, self first
-    [dgcnn.py:7-21]."""
-    return ops.knn_graph(x, k).long()
+    [dgcnn.py:7-21].  lengths (B,): length-aware form for zero-padded batches -- rows n < lengths[b] get
+    the reference's result on the cloud passed alone, the padding rows a filler."""
+    return ops.knn_graph(x, k, lengths=lengths).long()
 
 
 def _point_major(x: torch.Tensor) -> torch.Tensor:
@@ -61,27 +62,31 @@ class EdgeConv(nn.Module):
         # (SURVEY.md 8f-2).  fused=False runs the reference's op sequence literally on the K9/K6 kernels.
         self.fused = os.environ.get("PCNBR_EDGECONV_EXACT") is None and out_channels in (32, 64, 128, 256)
 
-    def forward(self, x, _nbr=None):
+    def forward(self, x, _nbr=None, lengths=None):
         """_nbr (internal): the layer's kNN table (ops.NeighborIndex) when it was computed ahead of time -- only the first
-        layer's graph depends on the input coordinates alone (DGCNN.prepare_geometry)."""
+        layer's graph depends on the input coordinates alone (DGCNN.prepare_geometry).  lengths: see knn()."""
         if not self.fused:
+            if _nbr is None and lengths is not None:
+                _nbr = ops.NeighborIndex(ops.knn_graph(x, self.k, lengths=lengths), x.shape[2])
             x = get_graph_feature(x, k=self.k, idx=_nbr.idx if _nbr is not None else None)
             x = self.conv(x)
             return ops.max_pool_neighbors(x, -1)
         conv, bn, act = self.conv[0], self.conv[1], self.conv[2]
         B, F, N = x.shape
         O = conv.out_channels
-        nbr = _nbr if _nbr is not None else ops.NeighborIndex(ops.knn_graph(x, self.k), N)
+        nbr = _nbr if _nbr is not None else ops.NeighborIndex(ops.knn_graph(x, self.k, lengths=lengths), N)
         W = conv.weight.view(O, 2 * F)
         Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
         rows = _point_major(x)
         if F % 4:
             # xyz layer.  u_ij = A (x_j - x_i) + B x_i is evaluated as P_j + Q_i with P = A x, Q = (B - A) x, which cancels
             # catastrophically when the cloud sits tens of metres from the origin (S3DIS coordinates).  A is translation
-            # invariant, so work on coordinates centred per cloud, xc = x - m:  P = A xc,  Q = (B - A) xc + B m.  The rows
+            # invariant, so work on coordinates shifted per cloud, xc = x - m:  P = A xc,  Q = (B - A) xc + B m.  The rows
             # are then zero-padded 3 -> 4 channels so that all three GEMMs (incl. the 65536-row weight gradient) run on
             # tcgen05.
-            m = rows.mean(dim=1, keepdim=True)                              # (B,1,F)
+            # Length-aware evaluation: the shift is the cloud's first point instead (any point of the cloud does; unlike the
+            # mean it does not see the zero padding and is the same whether the cloud comes alone or inside a padded batch).
+            m = rows.mean(dim=1, keepdim=True) if lengths is None else rows[:, :1, :]       # (B,1,F)
             PQ = ops.linear_rows(_pad4(rows - m), _pad4(Wcat), None)
             PQ = PQ + torch.nn.functional.pad(torch.matmul(m, W[:, F:].t()), (O, 0))        # [0 | B m] broadcast over the points
         else:
@@ -198,12 +203,14 @@ class DGCNN(nn.Module):
     def prepare_geometry(self, x, stream=None):
         return _first_layer_graph(x[:, :3, :] if x.size(1) == 6 else x, self.k, stream)
 
-    def forward(self, x, geometry=None):
+    def forward(self, x, geometry=None, lengths=None):
+        """lengths (B,): length-aware evaluation of a zero-padded batch: every kNN graph is built among the
+        real points of each cloud; in eval mode the logits of the real rows are the reference's on the cloud passed alone."""
         xyz = x[:, :3, :] if x.size(1) == 6 else x
-        x1 = self.conv1(xyz, _nbr=_graph_from(geometry, xyz.shape[2]))
-        x2 = self.conv2(x1)
-        x3 = self.conv3(x2)
-        x4 = self.conv4(x3)
+        x1 = self.conv1(xyz, _nbr=_graph_from(geometry, xyz.shape[2]), lengths=lengths)
+        x2 = self.conv2(x1, lengths=lengths)
+        x3 = self.conv3(x2, lengths=lengths)
+        x4 = self.conv4(x3, lengths=lengths)
         # the head runs point-major: (B,N,C) rows, one GEMM per layer, logits come out as (B,N,classes)
         r_cat = torch.cat([t.permute(0, 2, 1) for t in (x1, x2, x3, x4)], dim=2)
         r5 = _run_pointwise(self.conv5, r_cat)
@@ -232,13 +239,14 @@ class DGCNNWithColor(nn.Module):
     def prepare_geometry(self, x, stream=None):
         return _first_layer_graph(x[:, :3, :], self.k, stream)
 
-    def forward(self, x, geometry=None):
+    def forward(self, x, geometry=None, lengths=None):
+        """lengths: as DGCNN.forward."""
         if x.size(1) != 6:
             raise ValueError("DGCNNWithColor expects 6-channel input (xyz + rgb)")
-        x1 = self.conv1(x[:, :3, :], _nbr=_graph_from(geometry, x.shape[2]))
-        x2 = self.conv2(x1)
-        x3 = self.conv3(x2)
-        x4 = self.conv4(x3)
+        x1 = self.conv1(x[:, :3, :], _nbr=_graph_from(geometry, x.shape[2]), lengths=lengths)
+        x2 = self.conv2(x1, lengths=lengths)
+        x3 = self.conv3(x2, lengths=lengths)
+        x4 = self.conv4(x3, lengths=lengths)
         # the head runs point-major: (B,N,C) rows, one GEMM per layer, logits come out as (B,N,classes)
         color = _run_pointwise(self.color_conv, x[:, 3:6, :].permute(0, 2, 1))
         r_cat = torch.cat([t.permute(0, 2, 1) for t in (x1, x2, x3, x4)] + [color], dim=2)

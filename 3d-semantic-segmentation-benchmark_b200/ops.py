@@ -88,6 +88,23 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 4), dtype=torch.uint8, device=device)
 
 
+def _len32(lengths, B: int, device, k_min: int = 1, what: str = "lengths"):
+    """Per-cloud point counts of a zero-padded batch (the `lengths` the reference's collate_blocks returns,
+    data_processing/block_datasets.py:27: a uint64 host tensor) -> int32 device tensor (B,), or None.  k_min: the largest
+    neighbour count that will be asked of these clouds -- the reference's torch.topk raises when a cloud is shorter, and so
+    do we (checked on the host copy; a device tensor costs one sync here, evaluation only)."""
+    if lengths is None:
+        return None
+    t = torch.as_tensor(lengths)
+    if t.numel() != B:
+        raise ValueError(f"pcnbr: {what} must hold one entry per cloud ({B}), got {t.numel()}")
+    t = t.reshape(B).to(torch.int64)
+    lo = int(t.min().item())
+    if lo < max(1, k_min):
+        raise RuntimeError(f"pcnbr: selected index k out of range (k={k_min} > shortest cloud of the batch = {lo})")
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
 def _as_i32(idx: torch.Tensor) -> torch.Tensor:
     if idx.dtype == torch.int32:
         return _c(idx)
@@ -220,11 +237,15 @@ class PyramidGeometry:
     NeighborIndex is then a list, one per scale); starts = per-level first FPS picks or None (drawn here, level
     by level, exactly as the modules would: torch.randint(0, N_level, (B,), dtype=torch.int), common.py:22)."""
 
-    def __init__(self, coords0: torch.Tensor, sa, starts=None, interp_k: int = 3, inline: bool = False, stream=None):
+    def __init__(self, coords0: torch.Tensor, sa, starts=None, interp_k: int = 3, inline: bool = False, stream=None,
+                 lengths=None):
         """inline: run EVERYTHING on one stream -- `stream` (which first waits for the torch-side preparation done here on
         the current stream) or the current stream -- and build the CSR inverse of every table right away: the form used to
         compute the geometry of the NEXT batch on the side stream while the current step runs (train.GraphedTrainStep).
-        The caller orders its consumer after `stream` itself."""
+        The caller orders its consumer after `stream` itself.
+        lengths (B,): length-aware form for zero-padded batches: only the first lengths[b] points of the
+        INPUT cloud b exist -- level-1 FPS / ball query see those points only, and the last 3-NN table is filler for the
+        padding rows; every deeper level is made of real centroids."""
         dev = coords0.device
         B = coords0.shape[0]
         coords0 = _c(coords0)
@@ -237,20 +258,24 @@ class PyramidGeometry:
         # Everything a side-stream kernel reads or writes is allocated here on the CURRENT stream and kept alive by this
         # object until the consumer has waited on the producing event: a buffer released earlier (an unused FPS index
         # output, a workspace, a start draw) could be handed to a main-stream kernel while the side stream still uses it.
-        self._keep = [draws]
+        k0 = sa[0][2]
+        nv0 = _len32(lengths, B, dev, max(k0) if isinstance(k0, (list, tuple)) else k0)
+        if nv0 is not None:
+            draws[0] = torch.remainder(draws[0], nv0)
+        self._keep = [draws, nv0]
 
-        def fps(src, C, start):
+        def fps(src, C, start, nv=None):
             Bc, Nc, _ = src.shape
             idx = torch.empty(Bc, C, dtype=torch.int32, device=dev)
             out = torch.empty(Bc, C, 3, dtype=torch.float32, device=dev)
             nb = _lib.size("pcnbr_fps_ws_bytes", Bc, Nc)
             ws = _ws(nb, dev)
             self._keep += [idx, ws]
-            _lib.call("pcnbr_fps_f32", src.data_ptr(), Bc, Nc, C, start.data_ptr(), idx.data_ptr(), out.data_ptr(),
+            _lib.call("pcnbr_fps_len_f32", src.data_ptr(), Bc, Nc, C, start.data_ptr(), _ptr(nv), idx.data_ptr(), out.data_ptr(),
                       ws.data_ptr(), nb, _stream())
             return out
 
-        def ball(r, K, src, cen):
+        def ball(r, K, src, cen, nv=None):
             Bc, Nc, _ = src.shape
             M = cen.shape[1]
             if isinstance(r, (list, tuple)):                 # multi-scale level: every table from one scan of the points
@@ -265,23 +290,23 @@ class PyramidGeometry:
                 r2 = (ctypes.c_float * R)(*[_r2(x) for x in r])
                 ks = (ctypes.c_int * R)(*Ks)
                 ptrs = (ctypes.c_void_p * R)(*[t.data_ptr() for t in outs])
-                _lib.call("pcnbr_ball_query_multi_f32", cen.data_ptr(), src.data_ptr(), Bc, M, Nc, ctypes.addressof(r2),
-                          ctypes.addressof(ks), R, ctypes.addressof(ptrs), ws.data_ptr(), ws.numel(), _stream())
+                _lib.call("pcnbr_ball_query_multi_len_f32", cen.data_ptr(), src.data_ptr(), Bc, M, Nc, ctypes.addressof(r2),
+                          ctypes.addressof(ks), R, _ptr(nv), ctypes.addressof(ptrs), ws.data_ptr(), ws.numel(), _stream())
                 return [NeighborIndex(t, Nc) for t in outs]
             if K > Nc:
                 raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={Nc})")
             idx = torch.empty(Bc, M, K, dtype=torch.int32, device=dev)
-            _ball_query_into(cen, src, Bc, M, Nc, _r2(r), K, idx, self._keep)
+            _ball_query_into(cen, src, Bc, M, Nc, _r2(r), K, idx, self._keep, n_src=nv)
             return NeighborIndex(idx, Nc)
 
-        def knn3(query, src, k):
+        def knn3(query, src, k, nq=None):
             Bc, M, _ = query.shape
             Nc = src.shape[1]
             if k > Nc:
                 raise RuntimeError(f"pcnbr: selected index k out of range (k={k} > N={Nc})")
             idx = torch.empty(Bc, M, k, dtype=torch.int32, device=dev)
             d2 = torch.empty(Bc, M, k, dtype=torch.float32, device=dev)
-            _knn_direct_into(query, src, Bc, M, Nc, k, idx, d2, self._keep)
+            _knn_direct_into(query, src, Bc, M, Nc, k, idx, d2, self._keep, n_qry=nq)
             return NeighborIndex(idx, Nc), d2
 
         # level 1 on the current stream (inline: on `stream`, after the preparation above)
@@ -290,8 +315,8 @@ class PyramidGeometry:
             side.wait_event(torch.cuda.current_stream().record_event())
         C, r, K = sa[0]
         with (on_stream(side) if side is not None else _NullCtx()):
-            self.coords.append(fps(coords0, C, draws[0]))
-            self.balls.append(ball(r, K, coords0, self.coords[1]))
+            self.coords.append(fps(coords0, C, draws[0], nv0))
+            self.balls.append(ball(r, K, coords0, self.coords[1], nv0))
         self.ball_events.append(None)
         aux = side if inline else (aux_stream(dev) if _ASYNC_INDEX else None)
         if aux is not None and not inline:
@@ -307,7 +332,7 @@ class PyramidGeometry:
             # decoder: level l features are interpolated from level l+1 (fine = l, coarse = l+1), deepest first
             self.knn, self.knn_events = {}, {}
             for l in range(len(sa) - 1, -1, -1):
-                self.knn[l] = knn3(self.coords[l], self.coords[l + 1], interp_k)
+                self.knn[l] = knn3(self.coords[l], self.coords[l + 1], interp_k, nv0 if l == 0 else None)
                 self.knn_events[l] = self._mark(None if inline else aux)
             if inline:
                 for nbr in self._tables():
@@ -396,12 +421,14 @@ class _NullCtx:
 
 
 def farthest_point_sample(xyz: torch.Tensor, C: int, start_idx: torch.Tensor | None = None,
-                          return_coords: bool = False):
+                          return_coords: bool = False, lengths=None):
     """K1.  xyz (B,N,3) -> picked indices (B,C) int32 [and coords (B,C,3)].
 
     Same picks as the loop of models/utils/common.py:25-31.  `start_idx` (B,) is the first pick; when
     None it is drawn exactly as the reference does (common.py:22: torch.randint(0, N, (B,),
-    dtype=torch.int, device=coords.device)), so the generator is consumed identically."""
+    dtype=torch.int, device=coords.device)), so the generator is consumed identically.
+    lengths (B,): length-aware form for zero-padded batches -- only the first lengths[b] points of cloud b
+    exist; the picks are those of the reference on the cloud passed alone (a drawn start is folded into [0, lengths[b]))."""
     _check(xyz, "xyz")
     if xyz.dim() != 3 or xyz.shape[-1] != 3:
         raise ValueError(f"pcnbr: xyz must be (B,N,3), got {tuple(xyz.shape)}")
@@ -415,19 +442,22 @@ def farthest_point_sample(xyz: torch.Tensor, C: int, start_idx: torch.Tensor | N
     start = start_idx.to(device=xyz.device, dtype=torch.int32).contiguous()
     if start.shape != (B,):
         raise ValueError("pcnbr: start_idx must have shape (B,)")
+    nv = _len32(lengths, B, xyz.device)
+    if nv is not None:
+        start = torch.remainder(start, nv)
     idx = torch.empty(B, C, dtype=torch.int32, device=xyz.device)
     out = torch.empty(B, C, 3, dtype=torch.float32, device=xyz.device)
     nb = _lib.size("pcnbr_fps_ws_bytes", B, N)
     ws = _ws(nb, xyz.device)
-    _lib.call("pcnbr_fps_f32", xyz.data_ptr(), B, N, C, start.data_ptr(), idx.data_ptr(), out.data_ptr(),
-              ws.data_ptr(), nb, _stream())
+    _lib.call("pcnbr_fps_len_f32", xyz.data_ptr(), B, N, C, start.data_ptr(), nv.data_ptr() if nv is not None else None,
+              idx.data_ptr(), out.data_ptr(), ws.data_ptr(), nb, _stream())
     return (idx, out) if return_coords else idx
 
 
 _NO_GRID = __import__("os").environ.get("PCNBR_NO_GRID") is not None      # A/B switch: always the brute-force M x N scan
 
 
-def _ball_query_into(q, p, B, M, N, r2, K, idx, keep=None):
+def _ball_query_into(q, p, B, M, N, r2, K, idx, keep=None, n_qry=None, n_src=None):
     """Single-radius ball query into a preallocated table: the cell grid (csrc/grid.cu) for clouds of >= 2048 points, the
     M x N scan below that (identical tables).  keep: list that takes the workspace when the launch goes to a side stream."""
     if N >= 2048 and not _NO_GRID:
@@ -435,12 +465,20 @@ def _ball_query_into(q, p, B, M, N, r2, K, idx, keep=None):
         ws = _ws(nb, p.device)
         if keep is not None:
             keep.append(ws)
-        _lib.call("pcnbr_ball_query_grid_f32", q.data_ptr(), p.data_ptr(), B, M, N, r2, K, idx.data_ptr(), ws.data_ptr(), nb, _stream())
+        _lib.call("pcnbr_ball_query_len_f32", q.data_ptr(), p.data_ptr(), B, M, N, r2, K, _ptr(n_qry), _ptr(n_src), idx.data_ptr(),
+                  ws.data_ptr(), nb, _stream())
+    elif n_qry is not None or n_src is not None:
+        _lib.call("pcnbr_ball_query_len_f32", q.data_ptr(), p.data_ptr(), B, M, N, r2, K, _ptr(n_qry), _ptr(n_src), idx.data_ptr(),
+                  None, 0, _stream())
     else:
         _lib.call("pcnbr_ball_query_f32", q.data_ptr(), p.data_ptr(), B, M, N, r2, K, idx.data_ptr(), _stream())
 
 
-def _knn_direct_into(q, p, B, M, N, k, idx, d2, keep=None):
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _knn_direct_into(q, p, B, M, N, k, idx, d2, keep=None, n_qry=None, n_src=None):
     """k nearest sources (direct distances) into preallocated tables: cell grid with ring search when the scan would be
     large (>= 512 sources, >= 2^20 pairs per cloud, k <= 32), else the M x N scan (identical tables)."""
     if N >= 512 and M * N >= (1 << 20) and k <= 32 and not _NO_GRID:
@@ -448,7 +486,11 @@ def _knn_direct_into(q, p, B, M, N, k, idx, d2, keep=None):
         ws = _ws(nb, p.device)
         if keep is not None:
             keep.append(ws)
-        _lib.call("pcnbr_knn_direct_grid_f32", q.data_ptr(), p.data_ptr(), B, M, N, k, idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), nb, _stream())
+        _lib.call("pcnbr_knn_direct_len_f32", q.data_ptr(), p.data_ptr(), B, M, N, k, _ptr(n_qry), _ptr(n_src), idx.data_ptr(),
+                  d2.data_ptr(), ws.data_ptr(), nb, _stream())
+    elif n_qry is not None or n_src is not None:
+        _lib.call("pcnbr_knn_direct_len_f32", q.data_ptr(), p.data_ptr(), B, M, N, k, _ptr(n_qry), _ptr(n_src), idx.data_ptr(),
+                  d2.data_ptr(), None, 0, _stream())
     else:
         _lib.call("pcnbr_knn_direct_f32", q.data_ptr(), p.data_ptr(), B, M, N, k, idx.data_ptr(), d2.data_ptr(), _stream())
 
@@ -458,12 +500,15 @@ def _r2(r: float) -> float:
     return torch.tensor(float(r) ** 2, dtype=torch.float32).item()
 
 
-def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor, lengths=None,
+                     query_lengths=None) -> torch.Tensor:
     """K2.  xyz (B,N,3) points, new_xyz (B,M,3) centroids -> idx (B,M,nsample) int32.
 
     The selection of models/utils/common.py:54-61 with the canonical tie rule: in-ball points by
     ascending (squared distance, index), then -- if the ball holds fewer than nsample points -- the
-    out-of-ball points in ascending index (what a stable sort of the masked distance row gives)."""
+    out-of-ball points in ascending index (what a stable sort of the masked distance row gives).
+    lengths / query_lengths (B,): length-aware form -- cloud b has lengths[b] real points and
+    query_lengths[b] real centroids; real rows equal the reference's table on the unpadded cloud, padding rows are filler."""
     _check(xyz, "xyz"); _check(new_xyz, "new_xyz")
     B, N, _ = xyz.shape
     M = new_xyz.shape[1]
@@ -472,11 +517,12 @@ def query_ball_point(radius: float, nsample: int, xyz: torch.Tensor, new_xyz: to
         raise RuntimeError(f"pcnbr: selected index k out of range (K={K} > N={N})")   # torch.topk's error
     xyz, new_xyz = _c(xyz), _c(new_xyz)
     idx = torch.empty(B, M, K, dtype=torch.int32, device=xyz.device)
-    _ball_query_into(new_xyz, xyz, B, M, N, _r2(radius), K, idx)
+    _ball_query_into(new_xyz, xyz, B, M, N, _r2(radius), K, idx, n_qry=_len32(query_lengths, B, xyz.device, what="query_lengths"),
+                     n_src=_len32(lengths, B, xyz.device, K))
     return idx
 
 
-def query_ball_point_multi(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor) -> list[torch.Tensor]:
+def query_ball_point_multi(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor, lengths=None) -> list[torch.Tensor]:
     """Multi-radius ball query (PointNet++ "MSG": several group() calls on one centroid set, models/utils/common.py:37-61
     once per scale).  -> [idx_i (B,M,nsamples[i]) int32], each bit-identical to query_ball_point(radii[i], nsamples[i],
     xyz, new_xyz), from ONE scan of the points: a selection with the largest radius and the largest K, the other scales
@@ -497,12 +543,13 @@ def query_ball_point_multi(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Te
     r2 = (ctypes.c_float * R)(*[_r2(r) for r in radii])
     ks = (ctypes.c_int * R)(*nsamples)
     ptrs = (ctypes.c_void_p * R)(*[t.data_ptr() for t in out])
-    _lib.call("pcnbr_ball_query_multi_f32", new_xyz.data_ptr(), xyz.data_ptr(), B, M, N, ctypes.addressof(r2),
-              ctypes.addressof(ks), R, ctypes.addressof(ptrs), ws.data_ptr(), ws.numel(), _stream())
+    nv = _len32(lengths, B, xyz.device, max(nsamples))
+    _lib.call("pcnbr_ball_query_multi_len_f32", new_xyz.data_ptr(), xyz.data_ptr(), B, M, N, ctypes.addressof(r2),
+              ctypes.addressof(ks), R, _ptr(nv), ctypes.addressof(ptrs), ws.data_ptr(), ws.numel(), _stream())
     return out
 
 
-def knn_points(query: torch.Tensor, src: torch.Tensor, k: int):
+def knn_points(query: torch.Tensor, src: torch.Tensor, k: int, query_lengths=None, src_lengths=None):
     """K3 (direct form).  query (B,M,3), src (B,N,3) -> (idx (B,M,k) int32, d2 (B,M,k)): the k smallest
     ((src - query)**2).sum(-1), ascending, lowest index on ties (models/utils/common.py:110-114)."""
     _check(query, "query"); _check(src, "src")
@@ -514,11 +561,12 @@ def knn_points(query: torch.Tensor, src: torch.Tensor, k: int):
     query, src = _c(query), _c(src)
     idx = torch.empty(B, M, k, dtype=torch.int32, device=src.device)
     d2 = torch.empty(B, M, k, dtype=torch.float32, device=src.device)
-    _knn_direct_into(query, src, B, M, N, k, idx, d2)
+    _knn_direct_into(query, src, B, M, N, k, idx, d2, n_qry=_len32(query_lengths, B, src.device, what="query_lengths"),
+                     n_src=_len32(src_lengths, B, src.device, k, what="src_lengths"))
     return idx, d2
 
 
-def knn_graph(x: torch.Tensor, k: int, _keep: list | None = None) -> torch.Tensor:
+def knn_graph(x: torch.Tensor, k: int, _keep: list | None = None, lengths=None) -> torch.Tensor:
     """K3/K4 (expanded form).  x (B,F,N) in any (F,N) layout -> idx (B,N,k) int32: the k largest
     -xx_j + 2 x_i.x_j - xx_i per row, i.e. models/dgcnn/dgcnn.py:16-20 with lowest index on ties."""
     _check(x, "x")
@@ -535,10 +583,11 @@ def knn_graph(x: torch.Tensor, k: int, _keep: list | None = None) -> torch.Tenso
     idx = torch.empty(B, N, k, dtype=torch.int32, device=x.device)
     nb = _lib.size("pcnbr_knn_expand_ws_bytes", B, F, N, k)
     ws = _ws(nb, x.device)
-    _lib.call("pcnbr_knn_expand_f32", x.data_ptr(), B, F, N, sf, sn, k, idx.data_ptr(), ws.data_ptr(), nb, _stream(),
+    nv = _len32(lengths, B, x.device, k)
+    _lib.call("pcnbr_knn_expand_len_f32", x.data_ptr(), B, F, N, sf, sn, k, _ptr(nv), idx.data_ptr(), ws.data_ptr(), nb, _stream(),
               tag=f"[F={F}]")
     if _keep is not None:                # launched on a side stream (on_stream): the caller keeps the workspace and the input
-        _keep += [ws, x]                 # alive until it has waited for that stream
+        _keep += [ws, x, nv]             # alive until it has waited for that stream
     return idx
 
 

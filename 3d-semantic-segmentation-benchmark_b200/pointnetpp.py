@@ -36,9 +36,13 @@ class PointNetpp(nn.Module):
         out.append(geo)                                  # keeps the workspaces alive until the caller has copied the tensors
         return out
 
-    def forward(self, x: torch.Tensor, geometry=None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, geometry=None, lengths=None) -> torch.Tensor:
         """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes).  geometry: prepare_geometry(x)'s tensors
-        (without the trailing keep-alive object) when they were computed ahead of time."""
+        (without the trailing keep-alive object) when they were computed ahead of time.
+        lengths (B,): length-aware evaluation of a zero-padded batch (the loader's third output,
+        data_processing/block_datasets.py:27): the padding rows take no part in FPS / grouping / 3-NN, and in
+        eval mode the logits of the real rows are those of the reference on each cloud passed alone.  None = the
+        reference's behaviour (the padding participates, Training/training.py:112)."""
         coords_0, features_0 = x[:, :, :3], x[:, :, 3:]
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
         # every index of the network depends on coordinates only: FPS / ball query of the deeper levels and the decoder's
@@ -47,7 +51,7 @@ class PointNetpp(nn.Module):
         if geometry is not None:
             geo = ops.PyramidGeometry.from_export(coords_0, 4, geometry)
         else:
-            geo = ops.PyramidGeometry(coords_0, [(m.C, m.radius, m.K) for m in sas], [m.fps_start for m in sas])
+            geo = ops.PyramidGeometry(coords_0, [(m.C, m.radius, m.K) for m in sas], [m.fps_start for m in sas], lengths=lengths)
         coords_1, features_1 = self.sa1(geo.coords[0], features_0, _geom=geo.level(0))
         coords_2, features_2 = self.sa2(coords_1, features_1, _geom=geo.level(1))
         coords_3, features_3 = self.sa3(coords_2, features_2, _geom=geo.level(2))
@@ -82,13 +86,13 @@ class PointNetppMSG(nn.Module):
         self.drop = nn.Dropout(0.5)
         self.conv = nn.Conv1d(128, part_classes, 1)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes)."""
+    def forward(self, x: torch.Tensor, lengths=None) -> torch.Tensor:
+        """x (B,N,9): xyz, rgb, block-centred xyz -> raw logits (B,N,part_classes).  lengths: as PointNetpp.forward."""
         coords_0, features_0 = x[:, :, :3], x[:, :, 3:]
         sas = (self.sa1, self.sa2, self.sa3, self.sa4)
         # as in PointNetpp.forward: the deeper FPS levels, their multi-radius ball queries and the decoder's 3-NN tables run
         # on the side stream while the feature path of the shallower levels computes
-        geo = ops.PyramidGeometry(coords_0, [(m.C, m.radii, m.Ks) for m in sas], [m.fps_start for m in sas])
+        geo = ops.PyramidGeometry(coords_0, [(m.C, m.radii, m.Ks) for m in sas], [m.fps_start for m in sas], lengths=lengths)
         coords_1, features_1 = self.sa1(geo.coords[0], features_0, _geom=geo.level(0))
         coords_2, features_2 = self.sa2(coords_1, features_1, _geom=geo.level(1))
         coords_3, features_3 = self.sa3(coords_2, features_2, _geom=geo.level(2))

@@ -30,12 +30,13 @@ class PointNeXt(nn.Module):
         self.drop = nn.Dropout(0.5)
         self.conv = nn.Conv1d(128, part_classes, 1)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x (B,N,9) -> raw logits (B,N,part_classes)."""
+    def forward(self, x: torch.Tensor, lengths=None) -> torch.Tensor:
+        """x (B,N,9) -> raw logits (B,N,part_classes).  lengths (B,): length-aware evaluation of a zero-padded batch, as
+        PointNetpp.forward (only the input level has padding rows: every deeper level is made of real centroids)."""
         xt = x.permute(0, 2, 1)
         coords_0 = xt[:, :3, :].permute(0, 2, 1)
         features_0 = self.mlp(xt).permute(0, 2, 1)
-        coords_1, features_1 = self.sa1(coords_0, features_0)
+        coords_1, features_1 = self.sa1(coords_0, features_0, lengths=lengths)
         coords_1, features_1 = self.irmlp1(coords_1, coords_1, features_1)
         coords_2, features_2 = self.sa2(coords_1, features_1)
         coords_2, features_2 = self.irmlp2(coords_2, coords_2, features_2)
@@ -47,6 +48,6 @@ class PointNeXt(nn.Module):
         features_3 = self.fp4(coords_3, coords_4, features_3, features_4)
         features_2 = self.fp3(coords_2, coords_3, features_2, features_3)
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2)
-        features_0 = self.fp1(coords_0, coords_1, features_0, features_1)
+        features_0 = self.fp1(coords_0, coords_1, features_0, features_1, lengths=lengths)
         x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
         return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)

@@ -53,6 +53,13 @@ PCNBR_API size_t pcnbr_fps_ws_bytes(int B, int N);
 PCNBR_API int pcnbr_fps_f32(const float* xyz, int B, int N, int C, const int32_t* start,
                   int32_t* idx_out, float* xyz_out, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
+/* Length-aware K1 (zero-padded evaluation batches, data_processing/block_datasets.py:19-25,
+ * Training/training.py:80-133): cloud b holds n_valid[b] real points (device array, clamped to [1, N]; NULL = N), the rows
+ * behind them are padding and take no part -- picks and coordinates are those of the reference's sample() on the cloud
+ * passed alone, unpadded (start[b] is clamped into [0, n_valid[b])). */
+PCNBR_API int pcnbr_fps_len_f32(const float* xyz, int B, int N, int C, const int32_t* start, const int32_t* n_valid,
+                      int32_t* idx_out, float* xyz_out, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
 /* ---- K2 ball query ------------------------------------------------------- common.py:54-61
  * q (B,M,3) centroids, p (B,N,3) points, r2 = (float)((double)r*r).  idx (B,M,K):
  * in-ball points by ascending (d2, index), then out-of-ball points by ascending index.
@@ -76,6 +83,16 @@ PCNBR_API int pcnbr_ball_query_grid_f32(const float* q, const float* p, int B, i
 PCNBR_API int pcnbr_knn_direct_grid_f32(const float* q, const float* p, int B, int M, int N, int K, int32_t* idx, float* d2,
                     void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
+/* Length-aware K2 / K3: n_src[b] real source points, n_qry[b] real queries per cloud (device arrays,
+ * NULL = all).  Real rows get exactly the table of the reference's group() / interpolate() on the unpadded cloud; padding
+ * query rows get the in-range filler 0..K-1 (and d2 = 0).  K <= min_b n_src[b] is the caller's precondition (the reference's
+ * topk raises otherwise); a violated precondition yields in-range indices, never an out-of-bounds one.
+ * ws != NULL (pcnbr_grid_ws_bytes(B, N)): cell grid; ws == NULL: M x N scan.  pcnbr_knn_direct_len_f32 with ws needs K <= 32. */
+PCNBR_API int pcnbr_ball_query_len_f32(const float* q, const float* p, int B, int M, int N, float r2, int K, const int32_t* n_qry,
+                    const int32_t* n_src, int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_knn_direct_len_f32(const float* q, const float* p, int B, int M, int N, int K, const int32_t* n_qry,
+                    const int32_t* n_src, int32_t* idx, float* d2, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
 /* Multi-radius ball query ("MSG": several group() calls on ONE centroid set with different (r, K); BASELINE configs[2]).
  * Each idx[i] (B,M,K[i]) is bit-identical to pcnbr_ball_query_f32(q, p, .., r2[i], K[i], idx[i]), but the points are
  * scanned once: one selection with the largest radius and the largest K, the other scales are derived from its sorted
@@ -84,6 +101,9 @@ PCNBR_API int pcnbr_knn_direct_grid_f32(const float* q, const float* p, int B, i
 PCNBR_API size_t pcnbr_ball_query_multi_ws_bytes(int B, int M, int Kmax);
 PCNBR_API int pcnbr_ball_query_multi_f32(const float* q, const float* p, int B, int M, int N, const float* r2, const int* K,
                                int R, int32_t* const* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
+PCNBR_API int pcnbr_ball_query_multi_len_f32(const float* q, const float* p, int B, int M, int N, const float* r2, const int* K,
+                               int R, const int32_t* n_src, int32_t* const* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
 /* ---- K3/K4 kNN in the reference's expanded form ----------------------- dgcnn.py:7-21
  * x[b, f*stride_f + n*stride_n] (batch stride F*N), any layout of the (F,N) plane.
@@ -97,6 +117,13 @@ PCNBR_API int pcnbr_ball_query_multi_f32(const float* q, const float* p, int B, 
 PCNBR_API size_t pcnbr_knn_expand_ws_bytes(int B, int F, int N, int K);
 PCNBR_API int pcnbr_knn_expand_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
                          int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
+
+/* Length-aware form: cloud b holds n_valid[b] real points (NULL = N).  Rows i < n_valid[b] get the k
+ * nearest among the real points exactly as the reference's knn() on the unpadded cloud (including ATen's length-dependent
+ * summation order of |x|^2); padding rows get the filler 0..K-1.  The tensor-core path skips the all-padding work units and
+ * column tiles.  K <= min_b n_valid[b] is the caller's precondition. */
+PCNBR_API int pcnbr_knn_expand_len_f32(const float* x, int B, int F, int N, long stride_f, long stride_n, int K,
+                             const int32_t* n_valid, int32_t* idx, void* ws, size_t ws_bytes, pcnbr_stream_t stream);
 
 /* Test hook of the tensor-core path (F <= 64, 256 <= N <= 65535, K <= 32): same result as
  * pcnbr_knn_expand_f32, plus scores (B,N,N) = the pass-1 tensor-core values a_i.a_j - |a_j|^2/2 - C1|a_i||a_j| of the

@@ -68,9 +68,18 @@ def test_ball_query_and_group_large(pkg, dev, N, r, K):
     assert torch.equal(out.detach().cpu(), canon.group(cen, xyz, feat, o_idx, r, True))
     w = torch.randn(out.shape, generator=_gen(1))
     (out * w.to(dev)).sum().backward()
-    fr = feat.clone().requires_grad_(True)
-    (O.group(cen, xyz, fr, r, K, True, idx=o_idx.long()) * w).sum().backward()
-    assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=1e-4, atol=1e-5)
+    # scatter-add backward against a float64 accumulation of the same terms.  The padded balls make the lowest indices hubs
+    # (one gradient term from each of the 1024 centroids); where such a sum cancels, 1e-4 of the RESULT is below fp32
+    # rounding of the terms (torch's own fp32 index_put is 1e-4 off there), so the bound is 1e-4 relative or 2e-7 of
+    # sum |term| -- a few fp32 ulps per term.
+    ref = torch.zeros(B, N, D, dtype=torch.float64)
+    mag = torch.zeros(B, N, D, dtype=torch.float64)
+    for b in range(B):
+        terms = w[b].reshape(-1, 3 + D)[:, 3:].double()
+        ref[b].index_add_(0, o_idx[b].reshape(-1).long(), terms)
+        mag[b].index_add_(0, o_idx[b].reshape(-1).long(), terms.abs())
+    err = (fd.grad.cpu().double() - ref).abs()
+    assert bool((err <= 1e-4 * ref.abs() + 2e-7 * mag + 1e-12).all()), f"max err {err.max().item():.3e}"
 
 
 @pytest.mark.parametrize("N", [8192, 24000, 65536])

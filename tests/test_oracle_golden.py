@@ -214,3 +214,24 @@ def test_invresmlp_and_pointnext_oracle_match_reference_golden(golden):
     torch.manual_seed(g["seed"])
     blk = O.InvResMLP(g["radius"], g["cin"], g["width"], g["K"], tie="canon")
     assert torch.equal(blk(pc, pc, f)[1], g["out"])
+
+
+# --------------------------------------------------------------------------- length-aware fixtures (oracle/make_golden_lengths.py)
+
+def test_per_cloud_oracle_matches_reference_golden_on_unpadded_clouds(golden):
+    """The checker of the length-aware forms is the C oracle applied to each cloud's real rows; the fixtures are the
+    unmodified reference run on each cloud alone.  They must agree before the CUDA path is compared with either."""
+    g = golden("lengths")
+    L, xyz = g["lengths"].tolist(), g["xyz"]
+    for b, n in enumerate(L):
+        p = xyz[b:b + 1, :n].contiguous()
+        cen = canon.fps(p, g["sample"]["C"], g["sample"]["start"][b:b + 1])[1]
+        assert torch.equal(cen[0], g["sample"]["coords"][b])
+        gr = g["group"]
+        idx = canon.ball_query(cen, p, gr["r"], gr["K"])
+        assert torch.equal(canon.group(cen, p, gr["features"][b:b + 1, :n].contiguous(), idx, gr["r"], True)[0], gr["out"][b])
+        i3, d3 = canon.knn_direct(p, cen, 3)
+        assert torch.equal(canon.interp(g["interpolate"]["points"][b:b + 1], i3, d3)[0], g["interpolate"]["out"][b, :n])
+        for F in (3, 64):
+            k = g[f"knn_F{F}"]
+            assert torch.equal(canon.knn_expand(k["x"][b:b + 1, :, :n].contiguous(), k["k"])[0][0], k["idx"][b, :n])
