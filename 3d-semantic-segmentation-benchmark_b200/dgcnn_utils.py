@@ -6,7 +6,8 @@
 every window goes through the model on its own (kNN graphs never cross a window), the logits are overlap-added and
 averaged, and the prediction / confidence are the argmax / max softmax of the mean.  The reference runs the windows one
 after the other at batch 1 and makes four passes over the (N,C) accumulators; here all full-length windows form ONE batch
-(eval-mode BatchNorm keeps the windows independent, so the per-window logits are the same), and one kernel
+(eval-mode BatchNorm keeps the windows independent, so the per-window logits are the same), the shorter windows at the end
+of the scene form a second, zero-padded batch when the model has a length-aware forward (ours do), and one kernel
 (`csrc/blocks.cu: window_merge_kernel`) does overlap-add, division, argmax and confidence.  CUDA only."""
 from __future__ import annotations
 
@@ -26,9 +27,17 @@ def scene_windows(n_points: int, batch_size: int, overlap: int):
     return [(s, min(s + batch_size, n_points)) for s in range(0, n_points, step)]
 
 
-def _logits(model, x):
-    out = model(x)
+def _logits(model, x, **kw):
+    out = model(x, **kw)
     return out[0] if isinstance(out, tuple) else out
+
+
+def _takes_lengths(model) -> bool:
+    import inspect
+    try:
+        return "lengths" in inspect.signature(model.forward).parameters
+    except (TypeError, ValueError):
+        return False
 
 
 def predict_single_scene(model, points: torch.Tensor, device: str = 'cuda', batch_size: int = 4096, overlap: int = 512,
@@ -53,14 +62,25 @@ def predict_single_scene(model, points: torch.Tensor, device: str = 'cuda', batc
             for w0 in range(0, n_full, max_windows_per_call):
                 x = full[w0:min(n_full, w0 + max_windows_per_call)]
                 parts.append(_logits(model, x).reshape(x.shape[0] * batch_size, -1))
-            for s, e in windows[n_full:]:                                    # the shorter windows at the end of the scene
-                parts.append(_logits(model, points[s:e].T.unsqueeze(0)).reshape(e - s, -1))
+            tails = windows[n_full:]                                         # the shorter windows at the end of the scene
+            if len(tails) > 1 and _takes_lengths(model):
+                # length-aware models: the short windows go through the model as ONE zero-padded batch; the
+                # padding takes no part in any graph, so every window's logits are those of the window passed alone
+                xt = torch.zeros(len(tails), F, batch_size, dtype=torch.float32, device=points.device)
+                for t, (s, e) in enumerate(tails):
+                    xt[t, :, :e - s] = points[s:e].T
+                parts.append(_logits(model, xt, lengths=[e - s for s, e in tails]).reshape(len(tails) * batch_size, -1))
+                tail_rows = [batch_size] * len(tails)                        # rows each tail window occupies in `logits`
+            else:
+                for s, e in tails:
+                    parts.append(_logits(model, points[s:e].T.unsqueeze(0)).reshape(e - s, -1))
+                tail_rows = [e - s for s, e in tails]
         logits = (parts[0] if len(parts) == 1 else torch.cat(parts)).float().contiguous()
         C = logits.shape[1]
         offs, acc = [], 0
-        for s, e in windows:
+        for w, (s, e) in enumerate(windows):
             offs.append(acc)
-            acc += e - s
+            acc += (e - s) if (n <= batch_size or w < n_full) else tail_rows[w - n_full]
         win_off = torch.tensor(offs, dtype=torch.int64).to(points.device, non_blocking=True)
         mean = torch.empty(n, C, dtype=torch.float32, device=points.device) if return_logits else None
         pred = torch.empty(n, dtype=torch.int64, device=points.device)

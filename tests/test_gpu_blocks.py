@@ -171,7 +171,8 @@ def test_window_merge_golden(pkg, dev, golden):
         torch.testing.assert_close(conf, case["conf"], rtol=1e-4, atol=1e-5)
 
 
-def test_scene_inference_with_dgcnn(pkg, dev):
+@pytest.mark.parametrize("overlap", [256, 1024])      # 1024: two short windows at the end -> one zero-padded length-aware batch
+def test_scene_inference_with_dgcnn(pkg, dev, overlap):
     torch.manual_seed(0)
     model = pkg.DGCNNWithColor(num_classes=13, k=20).to(dev)
     pts, _, _ = O.s3dis_blocks(1, 6000, seed=4)
@@ -182,8 +183,8 @@ def test_scene_inference_with_dgcnn(pkg, dev):
     with torch.no_grad():
         for i in range(2):
             model(scene[i * 2048:(i + 1) * 2048].T.unsqueeze(0).to(dev))
-    pred, conf, mean = pkg.dgcnn_utils.predict_single_scene(model, scene, "cuda", 2048, 256, return_logits=True)
-    omean, opred, oconf = O.predict_single_scene(model, scene.to(dev), 2048, 256)     # window by window through the same model
+    pred, conf, mean = pkg.dgcnn_utils.predict_single_scene(model, scene, "cuda", 2048, overlap, return_logits=True)
+    omean, opred, oconf = O.predict_single_scene(model, scene.to(dev), 2048, overlap)     # window by window through the same model
     # DGCNN is discontinuous in its activations (a feature-space kNN graph can flip on a 1e-7 rounding difference between
     # the batched and the one-by-one pass, and a flipped edge spreads to ~k^2 points through the next two graphs), so the
     # comparison is statistical: measured 2 % of the elements beyond 1e-4 of the scale, none beyond 1.2e-3

@@ -116,6 +116,13 @@ def test_unmodified_reference_train_loop_runs_on_the_shims(reference_tree, pkg, 
     val_loss, acc, miou, ious, matrix = evaluate(model, test_loader, masked_onehot_cross_entropy, "cuda")
     assert 0.0 <= acc <= 1.0 and 0.0 <= miou <= 1.0 and matrix.shape == (14, 14) and int(matrix.sum()) > 0
     assert pkg.ops.fallbacks() == {}, f"library fallbacks in evaluation: {pkg.ops.fallbacks()}"
+    # ---- the package's own validation loop (one device-side confusion matrix, no per-class host syncs) returns the same tuple
+    torch.manual_seed(11)
+    r_loss, r_acc, r_miou, r_ious, r_matrix = evaluate(model, test_loader, masked_onehot_cross_entropy, "cuda")
+    torch.manual_seed(11)                                     # same FPS start draws (common.py:22)
+    o_loss, o_acc, o_miou, o_ious, o_matrix = pkg.train.evaluate(model, test_loader, masked_onehot_cross_entropy, "cuda")
+    assert torch.equal(o_matrix, r_matrix) and abs(o_acc - r_acc) < 1e-6
+    assert abs(o_miou - r_miou) < 1e-6 and torch.allclose(o_ious, r_ious, atol=1e-6) and abs(o_loss - float(r_loss)) < 1e-4
     # ---- train.py:88 saves model.state_dict(); the keys are the reference's (checkpoints interchange)
     path = tmp_path / "model.pt"
     torch.save(model.state_dict(), path)
@@ -169,3 +176,41 @@ def test_reference_written_checkpoint_loads_and_reproduces_reference_logits(refe
     ref = blob["logits"]
     err = (logits - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item() + 1e-5, f"max abs err {err:.3e} vs scale {ref.abs().max().item():.3e}"
+
+
+def test_length_aware_evaluate_equals_cloud_by_cloud(pkg, dev, tmp_path):
+    """pkg.train.evaluate(length_aware=True) over the zero-padded variable-N batches of the evaluation loader
+    (data_processing/block_datasets.py:19-25) == every block evaluated alone, unpadded."""
+    _write_blocks(str(tmp_path), areas=(1, 2, 3, 4, 5, 6), n_blocks=5, seed=3)
+    _, test_loader = pkg.block_datasets.create_block_dataloaders(
+        data_dir=str(tmp_path), test_areas={6}, train_batch_size=2, test_batch_size=3, num_workers=0,
+        train_sampling=4096, test_sampling=None, train_shuffle=False, test_shuffle=False)
+    torch.manual_seed(2)
+    model = pkg.PointNetpp(14).to(dev).eval()
+    batches = [(p.clone(), l.clone(), n.clone()) for p, l, n in test_loader]
+    assert len({int(n) for _, _, ns in batches for n in ns}) > 1, "the fixture needs clouds of different lengths"
+    loss, acc, miou, ious, matrix = pkg.train.evaluate(_PerBatchStart(model, dev), batches, None, "cuda", length_aware=True)
+    want = torch.zeros(14, 14, dtype=torch.int64)
+    with torch.no_grad():
+        for pts, lab, lens in batches:
+            for b, n in enumerate(lens.tolist()):
+                for sa in (model.sa1, model.sa2, model.sa3, model.sa4):
+                    sa.fps_start = torch.zeros(1, dtype=torch.int32, device=dev)
+                pred = model(pts[b:b + 1, :n].contiguous().to(dev))[0].argmax(-1).cpu()
+                want.index_put_((lab[b, :n].argmax(-1).long().cpu(), pred), torch.ones(n, dtype=torch.int64), accumulate=True)
+    assert int(matrix.sum()) == int(want.sum())
+    assert int((matrix - want).abs().sum()) <= 2 * max(1, int(want.sum()) // 2000), "argmax may flip on an exact near-tie only"
+    assert 0.0 <= acc <= 1.0 and loss == loss
+
+
+class _PerBatchStart(torch.nn.Module):
+    """sets the (B,) FPS start of every level to zeros for whatever batch size arrives"""
+
+    def __init__(self, model, dev):
+        super().__init__()
+        self.model, self.dev = model, dev
+
+    def forward(self, points, lengths=None):
+        for sa in (self.model.sa1, self.model.sa2, self.model.sa3, self.model.sa4):
+            sa.fps_start = torch.zeros(points.shape[0], dtype=torch.int32, device=self.dev)
+        return self.model(points, lengths=lengths)
