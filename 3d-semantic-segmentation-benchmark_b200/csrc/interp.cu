@@ -71,56 +71,109 @@ interp_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ id
     }
 }
 
-// k = 3 (the only value the models use), D % 4 == 0: one warp takes FOUR consecutive fine points per step -- lanes 0..11
-// fetch the 12 (index, distance) pairs in one coalesced request each, the weights and norms are formed once, and the
-// 12 coarse rows are in flight as float4 requests (512 B per row and warp) before the first divide.  Same arithmetic
-// order as interp_fwd_kernel, element for element.
-__global__ void __launch_bounds__(256)
+// ---- exact division by a shared divisor ---------------------------------------------------------------------------
+// The reference divides every weighted feature by the point's norm (common.py:122: points * weights / norm): N*k*D true
+// divisions.  div.rn.f32 costs ~15 SASS instructions (MUFU.RCP, FCHK, 5 FFMA, a guarded call to the slow path): they
+// were most of interp3_fwd_kernel's instructions.  All D*k quotients of a point share ONE divisor, so its correctly
+// rounded reciprocal y = RN(1/n) is formed once and each quotient takes the Markstein sequence
+//     q0 = RN(a y);  r0 = a - n q0 (exact, FMA);  q1 = RN(q0 + r0 y);  r1 = a - n q1 (exact);  q = RN(q1 + r1 y)
+// which returns the correctly rounded a / n (q1 is faithful, and a faithful quotient corrected once with the correctly
+// rounded reciprocal rounds correctly unless the significand of n is all ones -- Markstein 1990; Muller et al., Handbook
+// of Floating-Point Arithmetic, 2nd ed., sec. 4.7) as long as nothing under/overflows: n in [2^-60, 2^60] and a = 0 or
+// |a| in [2^-100, 2^100] keep q, r0 and r1 normal and the residuals exact.  Anything else takes div.rn.f32.
+struct SharedDiv {
+    float n, y;
+    bool ok;
+};
+__device__ __forceinline__ SharedDiv shared_div(float n) {
+    SharedDiv d;
+    d.n = n;
+    d.y = __frcp_rn(n);
+    const uint32_t bits = __float_as_uint(n);
+    d.ok = (n >= 8.6736174e-19f) && (n <= 1.1529215e18f) && ((bits & 0x7fffffu) != 0x7fffffu);
+    return d;
+}
+// a within the exact range of the fast sequence (0, or 2^-100 <= |a| <= 2^100): x = |a|'s bit pattern - 1 wraps to the
+// top for a = 0, so one unsigned range test covers "zero or at least 2^-100", a second one "at most 2^100 (and finite)"
+__device__ __forceinline__ bool shared_div_safe4(const float4& t) {
+    constexpr uint32_t LO = 0x0d800000u, HI = 0x71800000u;               // 2^-100, 2^100
+    const uint32_t x = (__float_as_uint(t.x) & 0x7fffffffu) - 1u, y = (__float_as_uint(t.y) & 0x7fffffffu) - 1u;
+    const uint32_t z = (__float_as_uint(t.z) & 0x7fffffffu) - 1u, w = (__float_as_uint(t.w) & 0x7fffffffu) - 1u;
+    const uint32_t lo = min(min(x, y), min(z, w));                       // smallest: must not fall in [0, LO - 1)
+    // largest finite magnitude: zeros (0xffffffff after the decrement) are taken out of the maximum first
+    const uint32_t hx = x + 1u, hy = y + 1u, hz = z + 1u, hw = w + 1u;
+    const uint32_t hi = max(max(hx, hy), max(hz, hw));
+    return lo >= LO - 1u && hi <= HI;
+}
+__device__ __forceinline__ float shared_div_fast(float a, const SharedDiv& d) {
+    float q = __fmul_rn(a, d.y);
+    float r = __fmaf_rn(-d.n, q, a);
+    q = __fmaf_rn(r, d.y, q);
+    r = __fmaf_rn(-d.n, q, a);
+    return __fmaf_rn(r, d.y, q);
+}
+__device__ __noinline__ float4 shared_div4_slow(float4 t, float n) {
+    return make_float4(__fdiv_rn(t.x, n), __fdiv_rn(t.y, n), __fdiv_rn(t.z, n), __fdiv_rn(t.w, n));
+}
+// (t.x, t.y, t.z, t.w) / d.n, each correctly rounded
+__device__ __forceinline__ float4 shared_div4(const float4& t, const SharedDiv& d) {
+    if (d.ok && shared_div_safe4(t))
+        return make_float4(shared_div_fast(t.x, d), shared_div_fast(t.y, d), shared_div_fast(t.z, d), shared_div_fast(t.w, d));
+    return shared_div4_slow(t, d.n);
+}
+
+// k = 3 (the only value the models use), D % 4 == 0: one warp takes PTS consecutive fine points per step -- the first
+// 3*PTS lanes fetch the (index, distance) pairs in one coalesced request each, the weights and norms are formed once, and
+// the 3*PTS coarse rows are in flight as float4 requests (512 B per row and warp) before the first quotient.  Same
+// arithmetic order as interp_fwd_kernel, element for element.  PTS = 2 keeps the kernel at <= 80 registers (3 CTAs per
+// SM): the kernel is a chain of dependent latencies (table -> rows -> quotients -> store), hidden by resident warps.
+template <int PTS>
+__global__ void __launch_bounds__(256, 3)
 interp3_fwd_kernel(const float* __restrict__ feat, const int32_t* __restrict__ idx, const float* __restrict__ d2,
                    int N, int M, int D, float* __restrict__ out, float* __restrict__ coef) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int nw = gridDim.x * (blockDim.x >> 5);
     const float* __restrict__ fb = feat + (size_t)b * M * D;
-    const int lp = lane / 3, lk = lane - 3 * lp;                         // this lane's (point, neighbour) slot, lane < 12
-    for (int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; n0 < N; n0 += nw * 4) {
+    const int lp = lane / 3;                                             // this lane's point slot, lane < 3 * PTS
+    for (int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PTS; n0 < N; n0 += nw * PTS) {
         const size_t base = ((size_t)b * N + n0) * 3;
-        const bool slot = lane < 12 && n0 + lp < N;
+        const bool slot = lane < 3 * PTS && n0 + lp < N;
         const int my_id = slot ? idx[base + lane] : 0;
         const float my_w = slot ? __fdiv_rn(1.0f, __fadd_rn(d2[base + lane], 1e-9f)) : 1.0f;     // common.py:119
-        int id[4][3];
-        float w[4][3], norm[4];
+        int id[PTS][3];
+        float w[PTS][3];
+        SharedDiv dv[PTS];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < PTS; ++p) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 id[p][k] = __shfl_sync(PCNBR_FULL, my_id, 3 * p + k);
                 w[p][k] = __shfl_sync(PCNBR_FULL, my_w, 3 * p + k);
             }
-            norm[p] = __fadd_rn(__fadd_rn(w[p][0], w[p][1]), w[p][2]);  // common.py:120
+            dv[p] = shared_div(__fadd_rn(__fadd_rn(w[p][0], w[p][1]), w[p][2]));  // common.py:120
         }
         if (coef && slot) {
-            float nm = norm[0];
+            float nm = dv[0].n;
 #pragma unroll
-            for (int p = 1; p < 4; ++p) if (lp == p) nm = norm[p];
+            for (int p = 1; p < PTS; ++p) if (lp == p) nm = dv[p].n;
             coef[base + lane] = __fdiv_rn(my_w, nm);
         }
-        (void)lk;
         for (int c = lane * 4; c < D; c += 128) {
-            float4 f[4][3];
+            float4 f[PTS][3];
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
+            for (int p = 0; p < PTS; ++p)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) f[p][k] = *reinterpret_cast<const float4*>(fb + (size_t)id[p][k] * D + c);
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < PTS; ++p) {
                 if (n0 + p >= N) break;
                 float4 acc;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float tx = __fdiv_rn(__fmul_rn(f[p][k].x, w[p][k]), norm[p]), ty = __fdiv_rn(__fmul_rn(f[p][k].y, w[p][k]), norm[p]);
-                    const float tz = __fdiv_rn(__fmul_rn(f[p][k].z, w[p][k]), norm[p]), tw = __fdiv_rn(__fmul_rn(f[p][k].w, w[p][k]), norm[p]);
-                    if (k == 0) acc = make_float4(tx, ty, tz, tw);
-                    else { acc.x = __fadd_rn(acc.x, tx); acc.y = __fadd_rn(acc.y, ty); acc.z = __fadd_rn(acc.z, tz); acc.w = __fadd_rn(acc.w, tw); }
+                    const float4 t = shared_div4(make_float4(__fmul_rn(f[p][k].x, w[p][k]), __fmul_rn(f[p][k].y, w[p][k]),
+                                                             __fmul_rn(f[p][k].z, w[p][k]), __fmul_rn(f[p][k].w, w[p][k])), dv[p]);
+                    if (k == 0) acc = t;
+                    else { acc.x = __fadd_rn(acc.x, t.x); acc.y = __fadd_rn(acc.y, t.y); acc.z = __fadd_rn(acc.z, t.z); acc.w = __fadd_rn(acc.w, t.w); }
                 }
                 *reinterpret_cast<float4*>(out + ((size_t)b * N + n0 + p) * D + c) = acc;
             }
@@ -152,10 +205,10 @@ extern "C" int pcnbr_interp_f32(const float* feat, const int32_t* idx, const flo
     // K8: 4 N D written + 4 M D read + 8 N k (idx, d2) read + 4 N k coef written per cloud
     const double wb = (double)B * (4.0 * N * D + 4.0 * M * D + 12.0 * N * K), wf = 3.0 * B * (double)N * D * K;
     if (K == 3 && D % 4 == 0 && ((((uintptr_t)feat | (uintptr_t)out) & 15) == 0)) {
-        int g3 = (N + 31) / 32;                                           // 8 warps x 4 points per CTA step
+        int g3 = (N + 15) / 16;                                           // 8 warps x 2 points per CTA step
         if (g3 > 148 * 8) g3 = 148 * 8;
         PCNBR_TIMED("interp_fwd_kernel", (cudaStream_t)stream, wb, wf,
-                    (interp3_fwd_kernel<<<dim3(g3, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, out, coef)));
+                    (interp3_fwd_kernel<2><<<dim3(g3, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, out, coef)));
     } else {
         PCNBR_TIMED("interp_fwd_kernel", (cudaStream_t)stream, wb, wf,
                     (interp_fwd_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(feat, idx, d2, N, M, D, K, out, coef)));

@@ -211,7 +211,8 @@ class NeighborIndex:
         # A prefetched inverse that no backward ever consumed (validation with grad enabled, a discarded loss, an exception):
         # its buffers go back to the allocator of the CURRENT stream while the side stream may still be writing them.  Order
         # every later use of those blocks after the build before letting them go.
-        _release_after(getattr(self, "_event", None))
+        if _release_after is not None:                  # None while the interpreter shuts down
+            _release_after(getattr(self, "_event", None))
 
 
 def _release_after(ev) -> None:

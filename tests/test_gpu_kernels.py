@@ -284,6 +284,34 @@ def test_interpolate_vs_oracle_with_backward(pkg, dev, N, M, D, k):
     assert torch.allclose(fd.grad.cpu(), fr.grad, rtol=RTOL, atol=ATOL)
 
 
+def test_interpolate_division_is_correctly_rounded_on_adversarial_values(pkg, dev):
+    """The k = 3 kernel divides by a per-point reciprocal (Markstein sequence, csrc/interp.cu) instead of issuing
+    N*k*D div.rn: its quotients must stay the correctly rounded (f * w) / norm of common.py:122 for EVERY float -- random
+    bit patterns (denormals, huge values, signed zeros), divisors with an all-ones significand, tiny and huge norms."""
+    B, N, M, D = 2, 3000, 64, 128
+    g = _gen(99)
+    bits = torch.randint(-2**31, 2**31 - 1, (B, M, D), generator=g, dtype=torch.int64).to(torch.int32)
+    feats = bits.view(torch.float32).clone()
+    feats[~torch.isfinite(feats)] = 0.0
+    feats[:, :8] = torch.randn(B, 8, D, generator=g)                       # ordinary rows as well
+    feats[:, 8:12] = torch.randn(B, 4, D, generator=g) * 1e-38             # denormal products
+    idx = torch.randint(0, M, (B, N, 3), generator=g, dtype=torch.int32)
+    d2 = torch.rand(B, N, 3, generator=g) * (10.0 ** torch.randint(-12, 5, (B, N, 3), generator=g).float())
+    d2[:, :50] = 0.0                                                       # w = 1e9: the largest norms
+    d2[:, 50:100] = 3.0e38                                                 # tiny norms (outside the fast range)
+    # a norm with an all-ones significand (the one divisor class Markstein's theorem excludes): weights 1, 0.5 and
+    # 0.5 - 2^-23 sum to 2 - 2^-23 = 0x3fffffff
+    d2[:, 100:150] = torch.tensor([1.0, 2.0, 2.0 * (1 + 2.0 ** -22)])
+    nbr = pkg.ops.NeighborIndex(idx.to(dev), M)
+    out = pkg.ops.three_interpolate(feats.to(dev), nbr, d2.to(dev)).cpu()
+    ref = canon.interp(feats, idx, d2)
+    same = (out.view(torch.int32) == ref.view(torch.int32)) | (torch.isnan(out) & torch.isnan(ref))
+    assert bool(same.all()), f"{int((~same).sum())} of {same.numel()} quotients differ"
+    w = 1.0 / (d2 + 1e-9)
+    norm_bits = ((w[..., 0] + w[..., 1]) + w[..., 2]).view(torch.int32) & 0x7fffff
+    assert int((norm_bits == 0x7fffff).sum()) > 0, "no all-ones divisor in the fixture"
+
+
 # --------------------------------------------------------------------------- K3/K4 knn (expanded form) + K9
 
 @pytest.mark.parametrize("name", ["knn_F3", "knn_F64", "knn_F20"])
