@@ -120,14 +120,14 @@ fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
     }
 }
 
-// 8192 < N <= 65536 (the 24 k-point chunks of PointNeXt, the N sweep): one cloud on a CLUSTER of 4 or 8 CTAs, a
+// 8192 < N <= 131072 (the 24 k-point chunks of PointNeXt, the N sweep up to 100 k): one cloud on a CLUSTER of 4, 8 or 16 CTAs, a
 // contiguous share of the points in the registers of each.  Per pick: CTA-local argmax exactly as fps_reg_kernel (same
 // keys, so the same point wins), the CTA winner (key + xyz) is stored into slot [buf][rank] of EVERY CTA of the cluster
 // through distributed shared memory, one cluster barrier, and each CTA takes the maximum of the candidates from its own
 // shared memory.  Slots are double-buffered by pick parity: a fast CTA can only run one pick ahead of a slow one.  The
 // barrier costs ~1 us per pick -- too much for N <= 8192, where one SM does a pick in 0.8 us (measured),
 // but 5x less than walking 24 k points through a global-memory distance array (fps_big_kernel: 7.1 us per pick).
-constexpr int FPS_CL_MAX = 8;
+constexpr int FPS_CL_MAX = 16;        // 16 CTAs per cluster is the non-portable maximum (one cluster per GPC)
 
 template <int PPT, int T>
 __global__ void __launch_bounds__(T, 1)
@@ -258,6 +258,10 @@ static int fps_launch_cluster(int CL, int B, const float* xyz, int N, int C, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (CL > 8) {                                              // beyond the portable cluster size: opt in once per function
+        cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT, T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return (int)e;
+    }
     return (int)cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, T>, xyz, N, C, start, n_valid, idx_out, xyz_out);
 }
 
@@ -351,10 +355,10 @@ extern "C" int pcnbr_fps_len_f32(const float* xyz, int B, int N, int C, const in
         return PCNBR_E_TOOLARGE;                            // unreachable: every (ppt, T) above is instantiated
     }
 #undef PCNBR_FPS_CASE
-    if (N <= 8 * 8192 && B * 8 <= 148 * 2) {
-
-        // cluster of 4 (N <= 32768) or 8 CTAs per cloud, 8 points per thread; ceiling: the CL SMs per cloud
-        const int CL = N <= 4 * 8192 ? 4 : 8;
+    if (N <= 16 * 8192 && B * 8 <= 148 * 2) {
+        // cluster of 4 (N <= 32768), 8 (N <= 65536) or 16 CTAs (N <= 131072, non-portable size: one cluster per GPC) per
+        // cloud, 8 points per thread; ceiling: the CL SMs per cloud
+        const int CL = N <= 4 * 8192 ? 4 : (N <= 8 * 8192 ? 8 : 16);
         const double wfc = 10.0 * B * (double)N * C * 2.0 * 148.0 / (double)(B * CL < 148 ? B * CL : 148);
         int rc = 0;
         PCNBR_TIMED("fps_cluster_kernel", s, wb, wfc, (rc = fps_launch_cluster<8, 1024>(CL, B, xyz, N, C, start, n_valid, idx_out, xyz_out, s)));

@@ -13,7 +13,8 @@
 //
 // max|x| per operand comes from pcnbr_absmax_f32 (one extra read of the tensor: 256 per-block maxima, reduced here).
 // Structure as gemm_tc.cu: warp 0 TMA producer (fp32 tiles exactly as they lie in HBM, K-major or MN-major), warp 1 MMA
-// issuer, warps 2-5 epilogue (tcgen05.ld -> * 1/(s s') (+ bias) -> swizzled staging -> TMA store), warps 6-13 converters.
+// issuer, warps 2-5 epilogue (tcgen05.ld -> * 1/(s s') (+ bias) -> swizzled staging -> TMA store), warps 6-13 (6-21 when both
+// operands are converted in the kernel: two groups on alternate stages) converters.
 // The converters rewrite each landed fp32 tile IN PLACE (4 B per element before and after) as [hi | lo] fp16 tiles in the
 // K-major 64-byte-swizzle UMMA layout -- MN-major operands are transposed on the way, so the MMA only ever sees K-major
 // fp16 -- with one named barrier between "everything read into registers" and "first store".
@@ -23,7 +24,14 @@
 namespace pcnbr {
 
 constexpr int H2_AMAX_SLOTS = 1280;        // per-block maxima: absmax_kernel fills 256, the fused producers (bnact.cu) up to 1184
-constexpr int H2_CONV_THREADS = 32 * GM_CONV_WARPS;
+constexpr int H2_CONV_THREADS = 32 * GM_CONV_WARPS;          // threads of ONE converter group
+// Converter groups: a group of 8 warps converts a whole ring stage (its in-place rewrite needs one barrier over everybody
+// who reads the stage).  When both operands are converted in the kernel (the weight gradients: 12288 values per stage at
+// BN = 256, ~80 % of the stage's MMA time in issue slots alone) ONE group leaves two warps per scheduler to hide the
+// LDS -> ALU -> STS latencies and the barrier, and the MMA warp waits for it; TWO groups take alternate stages, so the
+// conversion of stage i+1 overlaps the tail of stage i.  With a pre-split B (forward / input gradient) one group is plenty.
+template <bool B_PRE> constexpr int h2_groups() { return B_PRE ? 1 : 2; }
+template <bool B_PRE> constexpr int h2_threads() { return 192 + h2_groups<B_PRE>() * H2_CONV_THREADS; }
 
 // kind::f16 (A, B = fp16, both K-major), D = fp32, M = 128, N = BN (cute::UMMA::InstrDescriptor)
 template <int BN>
@@ -99,11 +107,41 @@ __device__ __forceinline__ void h2_load8(const uint8_t* tile, int r, int g, floa
     }
 }
 
+// one operand tile of `ROWS` rows, a task = (row, 8-wide K group): load phase / store phase of the in-place conversion.
+// (Tried: MN-major tiles as (4 rows, K group) tasks with one LDS.128 per K row -- a quarter of the load instructions, but the
+// stores of four rows of the same parity land on half of the banks (2-4-way conflicts): 369 us instead of 238 us for the
+// conv6 weight gradient.  The converters move 4 B in and 4 B out per value through the LSU, 768 wavefronts per stage at
+// BN = 256 -- as many cycles as the stage's six MMAs: the weight-gradient GEMMs are bound by that, not by issue.)
+template <int ROWS> constexpr int h2_per_thread() { return (ROWS * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS; }
+
+template <bool MN, int ROWS, int NT>
+__device__ __forceinline__ void h2_tile_load(const uint8_t* tile, int t, float (&v)[NT][8]) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const int q = t + i * H2_CONV_THREADS;
+        if (q < ROWS * 4) h2_load8<MN>(tile, q % ROWS, q / ROWS, v[i]);
+    }
+}
+template <int ROWS, int NT>
+__device__ __forceinline__ void h2_tile_store(uint8_t* tile, uint32_t plane, int t, float s, const float (&v)[NT][8]) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const int q = t + i * H2_CONV_THREADS;
+        if (q < ROWS * 4) {
+            uint4 hi, lo;
+            h2_split8(v[i], s, hi, lo);
+            const uint32_t off = h2_dst_off(q % ROWS, q / ROWS);
+            *reinterpret_cast<uint4*>(tile + off) = hi;
+            *reinterpret_cast<uint4*>(tile + plane + off) = lo;
+        }
+    }
+}
+
 // B_PRE: the B operand arrives already split ([hi | lo] fp16 planes written once by split_f16_kernel -- the weights of a
 // forward / input-gradient GEMM, which every CTA would otherwise convert again): TMA drops the two planes straight into
 // the UMMA layout (SWIZZLE_64B) and the converters only handle A (a third of the work at BN = 256).
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE>
-__global__ void __launch_bounds__(GM_THREADS, 1)
+__global__ void __launch_bounds__(h2_threads<B_PRE>(), 1)
 gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
               const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c, int M, int N, int K,
               int kb_split, int splits, const float* __restrict__ bias, const float* __restrict__ amax_a,
@@ -284,51 +322,40 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         // ===================================================== converters: fp32 tile -> [hi | lo] fp16 tiles, in place
-        const int t = threadIdx.x - 192;                              // 0 .. 255
-        constexpr int TA = (GM_BM * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;      // (row, 8-wide K group) tasks per thread
-        constexpr int TB = B_PRE ? 0 : (BN * 4 + H2_CONV_THREADS - 1) / H2_CONV_THREADS;
+        constexpr int NG = h2_groups<B_PRE>();
+        const int grp = (threadIdx.x - 192) / H2_CONV_THREADS;        // this warp's group: it converts the stages seq % NG == grp
+        const int t = (threadIdx.x - 192) % H2_CONV_THREADS;          // 0 .. 255 inside the group
+        constexpr int TA = h2_per_thread<GM_BM>();                    // conversion tasks per thread (see h2_tile_load)
+        constexpr int TB = B_PRE ? 0 : h2_per_thread<BN>();
         const float sa = s_scale[0], sbs = s_scale[1];
-        uint32_t stage = 0, phase = 0;
+        uint32_t stage = 0, phase = 0, seq = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int sp = unit / (MT * NT);
             const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb, ++seq) {
+                if (NG > 1 && (int)(seq % NG) != grp) {               // the other group's stage
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 uint8_t* st = smem + stage * STAGE_BYTES;
                 uint8_t* sb = st + A_BYTES;
                 gm_mbar_wait(&full[stage], phase);
-                float va[TA][8], vb[TB > 0 ? TB : 1][8];
-#pragma unroll
-                for (int i = 0; i < TA; ++i) {
-                    const int q = t + i * H2_CONV_THREADS;
-                    if (q < GM_BM * 4) h2_load8<A_MN>(st, q % GM_BM, q / GM_BM, va[i]);
+                // One operand tile at a time (each is rewritten in place inside its own region): every fp32 word of the tile is
+                // in registers before the first store -- one named barrier per group and tile.  Keeping the two tiles apart
+                // keeps the live registers low (the CTA's 22 warps leave 80 each).
+                {
+                    float va[TA][8];
+                    h2_tile_load<A_MN, GM_BM, TA>(st, t, va);
+                    if (grp == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+                    else          asm volatile("bar.sync 3, 256;" ::: "memory");
+                    h2_tile_store<GM_BM, TA>(st, A_BYTES / 2, t, sa, va);
                 }
-#pragma unroll
-                for (int i = 0; i < TB; ++i) {
-                    const int q = t + i * H2_CONV_THREADS;
-                    if (q < BN * 4) h2_load8<B_MN>(sb, q % BN, q / BN, vb[i]);
-                }
-                asm volatile("bar.sync 2, 256;" ::: "memory");       // every fp32 word is in registers: overwrite in place
-#pragma unroll
-                for (int i = 0; i < TA; ++i) {
-                    const int q = t + i * H2_CONV_THREADS;
-                    if (q < GM_BM * 4) {
-                        uint4 hi, lo;
-                        h2_split8(va[i], sa, hi, lo);
-                        const uint32_t off = h2_dst_off(q % GM_BM, q / GM_BM);
-                        *reinterpret_cast<uint4*>(st + off) = hi;
-                        *reinterpret_cast<uint4*>(st + A_BYTES / 2 + off) = lo;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < TB; ++i) {
-                    const int q = t + i * H2_CONV_THREADS;
-                    if (q < BN * 4) {
-                        uint4 hi, lo;
-                        h2_split8(vb[i], sbs, hi, lo);
-                        const uint32_t off = h2_dst_off(q % BN, q / BN);
-                        *reinterpret_cast<uint4*>(sb + off) = hi;
-                        *reinterpret_cast<uint4*>(sb + B_BYTES / 2 + off) = lo;
-                    }
+                if (TB > 0) {
+                    float vb[TB > 0 ? TB : 1][8];
+                    h2_tile_load<B_MN, BN, (TB > 0 ? TB : 1)>(sb, t, vb);
+                    if (grp == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+                    else          asm volatile("bar.sync 3, 256;" ::: "memory");
+                    h2_tile_store<BN, (TB > 0 ? TB : 1)>(sb, B_BYTES / 2, t, sbs, vb);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -459,9 +486,11 @@ static int h2_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split
     const int grid = units < sms ? units : sms;
     // algorithmic work as gemm3x_kernel: 2 M N K flop counted once (3 fp16 products are issued); operands once + result
     const double bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), flops = 2.0 * M * (double)N * K;
-    const char* name = flops / 678.35e12 > bytes / 6551e9 ? "gemm2h_kernel[tensor]" : "gemm2h_kernel[hbm]";
+    // shape class of the profiler label: tensor-bound when the three fp16 products the kernel issues per product need longer on
+    // the f16 pipe (1356.7 TFLOP/s sustained, MEASURED_PEAKS.json) than the operands need on HBM
+    const char* name = 3.0 * flops / 1356.7e12 > bytes / 6551e9 ? "gemm2h_kernel[tensor]" : "gemm2h_kernel[hbm]";
     PCNBR_TIMED(name, s, bytes, flops,
-                (gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias,
+                (gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE><<<grid, h2_threads<B_PRE>(), smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias,
                                                                                       amax_a, amax_a2, amax_b)));
     PCNBR_CHECK_LAUNCH();
     return 0;

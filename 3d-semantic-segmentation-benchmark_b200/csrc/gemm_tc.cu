@@ -307,7 +307,9 @@ static int gm_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split
     // keeps two shape classes apart: launches whose tensor-pipe time bound (TF32 peak) exceeds their HBM time bound, and
     // the narrow layers for which the bytes bind (measured peaks: 678 TFLOP/s, 6551 GB/s)
     const double gm_bytes = 4.0 * ((double)M * K + (double)N * K + (double)M * N * splits), gm_flops = 2.0 * M * (double)N * K;
-    const char* gm_name = gm_flops / 678.35e12 > gm_bytes / 6551e9 ? "gemm3x_kernel[tensor]" : "gemm3x_kernel[hbm]";
+    // shape class of the profiler label: tensor-bound when the three TF32 products issued per product need longer on the tf32
+    // pipe (678 TFLOP/s sustained) than the operands need on HBM
+    const char* gm_name = 3.0 * gm_flops / 678.35e12 > gm_bytes / 6551e9 ? "gemm3x_kernel[tensor]" : "gemm3x_kernel[hbm]";
     PCNBR_TIMED(gm_name, s, gm_bytes, gm_flops,
                 (gemm3x_kernel<BN, STAGES, A_MN, B_MN><<<grid, GM_THREADS, smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias)));
     PCNBR_CHECK_LAUNCH();

@@ -307,22 +307,35 @@ def ncu_traffic(kernel):
     return table.get(kernel) or table.get(kernel.split("[")[0]) or None
 
 
+# tensor instructions ISSUED per algorithmic flop: the fp32-accurate GEMMs run three products per product (hi.hi' + lo.hi' +
+# hi.lo'); the kNN kernel runs two passes over the tiles plus a 16-wide tail K-slice per 64-wide feature slab
+ISSUE_FACTOR = {"gemm3x_kernel": 3.0, "gemm2h_kernel": 3.0, "knn_tc_kernel": 2.5}
+
+
 def kernel_bound(name, d, peaks):
-    """Which roofline binds this kernel and how close it runs to it: time bound = max(algorithmic bytes / HBM peak,
-    algorithmic flops / peak of the pipe that executes them); frac = bound / measured.  `d` = {"ms","bytes","flops","calls"}
-    summed over the launches (ALGORITHMIC work as stated by the launch sites from the SURVEY.md 8d formulas)."""
+    """Which roofline binds this kernel and how close it runs to it.  `d` = {"ms","bytes","flops","calls"} summed over the
+    launches (ALGORITHMIC work as stated by the launch sites from the SURVEY.md 8d formulas).  A tensor-core kernel is
+    tensor-bound when the tensor time of the instructions it ISSUES (ISSUE_FACTOR x algorithmic flops / peak of the pipe it
+    uses: f16 for the fp16-split GEMM and the kNN kernel, tf32 for the 3xTF32 GEMM) exceeds its HBM time; its `achieved` /
+    `frac` still count every flop ONCE (so a three-product GEMM cannot exceed 1/3), `issued_frac` says how busy the pipe is.
+    Everything else: max(bytes / HBM peak, flops / FP32 peak) / measured."""
     sec = d["ms"] / 1e3
     t_hbm = d["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    base = name.split("[")[0]
     if name in TENSOR_KERNELS:
-        pk = peaks["f16_tflops"] if name.startswith("gemm2h") else peaks["tf32_tflops"]
-        t_fl, fl_unit, fl_peak, fl_name = d["flops"] / (pk * 1e12), "TFLOP/s", pk, "tensor"
-    elif name in ALU_KERNELS:
-        t_fl, fl_unit, fl_peak, fl_name = d["flops"] / (peaks["fp32_tflops"] * 1e12), "TFLOP/s", peaks["fp32_tflops"], "alu"
-    else:
-        t_fl, fl_unit, fl_peak, fl_name = 0.0, "TFLOP/s", 1.0, "alu"
-    if t_fl > t_hbm:
-        return {"bound": fl_name, "achieved": d["flops"] / 1e12 / sec, "peak": fl_peak, "unit": fl_unit, "frac": t_fl / sec,
-                "algorithmic": d["flops"]}
+        pk = peaks["tf32_tflops"] if base == "gemm3x_kernel" else peaks["f16_tflops"]
+        t_once = d["flops"] / (pk * 1e12)
+        t_issued = ISSUE_FACTOR.get(base, 1.0) * t_once
+        if t_issued > t_hbm:
+            return {"bound": "tensor", "achieved": d["flops"] / 1e12 / sec, "peak": pk, "unit": "TFLOP/s", "frac": t_once / sec,
+                    "algorithmic": d["flops"], "issued_frac": t_issued / sec, "hbm_frac": t_hbm / sec}
+        return {"bound": "hbm", "achieved": d["bytes"] / 1e9 / sec, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": t_hbm / sec,
+                "algorithmic": d["bytes"], "issued_frac": t_issued / sec}
+    if name in ALU_KERNELS:
+        t_fl = d["flops"] / (peaks["fp32_tflops"] * 1e12)
+        if t_fl > t_hbm:
+            return {"bound": "alu", "achieved": d["flops"] / 1e12 / sec, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
+                    "frac": t_fl / sec, "algorithmic": d["flops"]}
     return {"bound": "hbm", "achieved": d["bytes"] / 1e9 / sec, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": t_hbm / sec,
             "algorithmic": d["bytes"]}
 
@@ -341,9 +354,11 @@ def roofline_for(kernels, peaks):
            "traffic_algorithmic_bytes_same_shape": t.get("algorithmic_bytes_same_shape"),
            "avg_launch_ms": d["ms"] / d["calls"], "calls": d["calls"], "peak_source": peaks["source"],
            "algorithmic_per_launch": b["algorithmic"] / d["calls"]}
-    if name.startswith("gemm") and b["bound"] == "tensor":
-        out["issued_per_algorithmic_flop"] = 3.0          # hi.hi' + lo.hi' + hi.lo': three tensor instructions per product
-        out["issued_frac"] = 3.0 * b["frac"]
+    if "issued_frac" in b:
+        out["issued_per_algorithmic_flop"] = ISSUE_FACTOR.get(name.split("[")[0], 1.0)
+        out["issued_frac"] = b["issued_frac"]              # share of the tensor pipe's time the issued instructions need
+    if "hbm_frac" in b:
+        out["hbm_frac"] = b["hbm_frac"]                    # the same launches against the HBM roofline (algorithmic bytes)
     out["note"] = ("flops counted once (2 M N K per GEMM, 2 N^2 F per kNN cloud), whatever the split kernel issues" if b["bound"] == "tensor" else
                    "algorithmic (compulsory) bytes; gathers that hit L2 are not counted" if b["bound"] == "hbm" else
                    "algorithmic lane-ops / flops on the FP32 pipe")

@@ -3,6 +3,7 @@
 interpolate / edge features / scatter-add at N = 4k-100k, k = 16-32, C = 3-256, one GPU (replicas only at N GPUs).
 
     python bench_kernels.py [--quick] [--iters 10] [--md profiles/rX_kernel_sweep.md]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench_kernels.py --replicas    # "1 vs 8 GPUs"
 
 Every libpcnbr KERNEL is timed by the library's own profiler (csrc/prof.cu: CUDA events on the launch stream
 around each kernel), with L2 flushed between iterations (a 512 MB memset), after 3 warm-up iterations.  The roofline
@@ -25,8 +26,91 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 
+def replica_sweep(args):
+    """BASELINE configs[4] "1 vs 8 GPUs": every op of the path is per-cloud, so N GPUs run N independent replicas with no
+    exchange (SURVEY.md 8e "replicas only").  One process per GPU (python -m torch.distributed.run --nproc-per-node N
+    bench_kernels.py --replicas); every rank times the same op calls on its own clouds, the reported time is the MAX over
+    ranks (device events, L2 flushed between calls) and the throughput the aggregate clouds/s of all replicas."""
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    ops = pkg.ops
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator().manual_seed(rank)
+    rows = []
+
+    def timed(op, shape, B, fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = 0.0
+        for _ in range(args.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        t = torch.tensor([ms / args.iters], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        row = {"op": op, "shape": shape, "n_gpus": world, "us_per_call_max_over_ranks": round(1e3 * t.item(), 1),
+               "clouds_per_s_aggregate": round(world * B / (t.item() / 1e3), 1)}
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+
+    for N in (4096, 24000, 100000):
+        B = 32 if N <= 4096 else max(2, min(8, (1 << 18) // N))
+        pts, _, _ = pkg.synthetic.s3dis_blocks(B, N, seed=rank * 31 + N % 997)
+        xyz = pts[:, :, :3].contiguous().to(dev)
+        start = torch.zeros(B, dtype=torch.int32, device=dev)
+        sh = f"B={B} N={N}"
+        timed("fps C=1024", sh, B, lambda: ops.farthest_point_sample(xyz, 1024, start))
+        _, cen = ops.farthest_point_sample(xyz, 1024, start, return_coords=True)
+        timed("ball_query r=0.1 K=32", sh, B, lambda: ops.query_ball_point(0.1, 32, xyz, cen))
+        nbr = ops.NeighborIndex(ops.query_ball_point(0.1, 32, xyz, cen), N)
+        f = torch.randn(B, N, 64, generator=g).to(dev)
+        timed("group D=64 K=32", sh, B, lambda: ops.group_points(xyz, f, cen, nbr, 0.1, pad4=True))
+        timed("knn3 M=1024", sh, B, lambda: ops.knn_points(xyz, cen, 3))
+        i3, d3 = ops.knn_points(xyz, cen, 3)
+        coarse = torch.randn(B, 1024, 128, generator=g).to(dev)
+        n3 = ops.NeighborIndex(i3, 1024)
+        timed("interpolate D=128", sh, B, lambda: ops.three_interpolate(coarse, n3, d3))
+        del xyz, f, coarse
+    for (N, F, k) in ((4096, 64, 20), (16384, 64, 20), (4096, 64, 32), (4096, 3, 16)):
+        B = 16 if N <= 4096 else 4
+        xt = torch.randn(B, N, F, generator=g).to(dev)
+        sh = f"B={B} N={N} F={F} k={k}"
+        timed("knn_feature", sh, B, lambda: ops.knn_graph(xt.transpose(1, 2), k))
+        nbr = ops.NeighborIndex(ops.knn_graph(xt.transpose(1, 2), k), N)
+        nbr.csr()
+        if F == 64:
+            PQ = torch.randn(B, N, 128, generator=g).to(dev)
+            bn = torch.nn.BatchNorm2d(64).to(dev)
+            with torch.no_grad():
+                timed("edgeconv_fused O=64", sh, B, lambda: ops.edgeconv_fused(PQ, nbr, bn, 0.2))
+    if rank == 0 and args.md:
+        with open(args.md, "w") as fh:
+            fh.write(f"# kernel sweep, {world} replica(s) ({torch.cuda.get_device_name(0)}): op calls through the C ABI, max over ranks, aggregate clouds/s\n\n")
+            fh.write("| op | shape per GPU | GPUs | us per call (max over ranks) | clouds/s (all replicas) |\n|---|---|---:|---:|---:|\n")
+            for r in rows:
+                fh.write(f"| {r['op']} | {r['shape']} | {r['n_gpus']} | {r['us_per_call_max_over_ranks']} | {r['clouds_per_s_aggregate']} |\n")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--replicas", action="store_true",
+                    help="op-level sweep as independent replicas, one per GPU (run under torch.distributed.run for N > 1): aggregate clouds/s")
     ap.add_argument("--quick", action="store_true", help="BASELINE shapes only (no N sweep)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--md", default="")
@@ -34,6 +118,8 @@ def main():
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_kernels.py: no CUDA device; the hot path has no CPU fallback")
+    if args.replicas:
+        return replica_sweep(args)
     import __graft_entry__ as ge
     pkg = ge.load_package()
     lib, ops = pkg._lib, pkg.ops

@@ -1,8 +1,8 @@
 """GPU: parity at the sizes of BASELINE configs[3] (PointNeXt on 24 k-point chunks) and configs[4] (kernel sweep
 N = 4 k - 100 k), covering every dispatch branch of the C ABI that the 4096-point tests do not reach:
 
-  pcnbr_fps_f32      N <= 8192 register kernel | 4-CTA cluster (N <= 32768) | 8-CTA cluster (N <= 65536) |
-                     global-memory kernel (N > 65536, or more clouds than the clusters can host)
+  pcnbr_fps_f32      N <= 8192 register kernel | 4-CTA cluster (N <= 32768) | 8-CTA cluster (N <= 65536) | 16-CTA cluster
+                     (N <= 131072) | global-memory kernel (larger N, or more clouds than the clusters can host)
   pcnbr_ball_query / pcnbr_knn_direct / pcnbr_group at N in {8192, 24000, 65536}
   pcnbr_knn_expand   tensor-core path for 4096 < N <= 65535 (16-bit survivor queue) and the CUDA-core path above it
 
@@ -34,7 +34,9 @@ def _chunk(B, N, seed):
     (2, 32768, 128, "cluster4"),
     (2, 40000, 256, "cluster8"),
     (1, 65536, 64, "cluster8"),
-    (2, 100000, 64, "big"),            # configs[4] upper end
+    (2, 100000, 64, "cluster16"),      # configs[4] upper end: 16-CTA cluster (non-portable size)
+    (1, 131072, 32, "cluster16"),
+    (1, 140000, 24, "big"),            # beyond what a cluster's registers hold
     (40, 9000, 48, "big"),             # more clouds than the clusters can host at once
 ])
 def test_fps_large_every_dispatch_branch(pkg, dev, B, N, C, branch):
@@ -45,7 +47,7 @@ def test_fps_large_every_dispatch_branch(pkg, dev, B, N, C, branch):
     idx, coords = pkg.ops.farthest_point_sample(xyz.to(dev), C, start.to(dev), return_coords=True)
     ran = pkg._lib.prof_collect()
     pkg._lib.prof_enable(False)
-    want = {"cluster4": "fps_cluster_kernel", "cluster8": "fps_cluster_kernel", "big": "fps_big_kernel"}[branch]
+    want = {"cluster4": "fps_cluster_kernel", "cluster8": "fps_cluster_kernel", "cluster16": "fps_cluster_kernel", "big": "fps_big_kernel"}[branch]
     assert any(k.startswith(want) for k in ran), f"expected {want}, ran {sorted(ran)}"
     o_idx, o_coords = canon.fps(xyz, C, start)
     assert torch.equal(idx.cpu(), o_idx)

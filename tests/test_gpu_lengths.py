@@ -81,7 +81,8 @@ def test_golden_pointnetpp_eval_logits(pkg, dev, golden):
     (4096, 1024, [4096, 3000, 1500, 700], "fps_reg_kernel"),        # 700 < C: the reference re-picks point 0
     (1000, 64, [1000, 999, 33, 1], "fps_reg_kernel"),
     (24000, 512, [24000, 9000, 16001], "fps_cluster_kernel"),
-    (70000, 48, [70000, 12345], "fps_big_kernel"),
+    (70000, 48, [70000, 12345], "fps_cluster_kernel"),              # 16-CTA cluster
+    (140000, 24, [140000, 70001], "fps_big_kernel"),
 ])
 def test_fps_lengths_vs_oracle(pkg, dev, N, C, lengths, branch):
     B = len(lengths)
