@@ -122,12 +122,38 @@ fps_reg_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* __res
 
 // 8192 < N <= 131072 (the 24 k-point chunks of PointNeXt, the N sweep up to 100 k): one cloud on a CLUSTER of 4, 8 or 16 CTAs, a
 // contiguous share of the points in the registers of each.  Per pick: CTA-local argmax exactly as fps_reg_kernel (same
-// keys, so the same point wins), the CTA winner (key + xyz) is stored into slot [buf][rank] of EVERY CTA of the cluster
-// through distributed shared memory, one cluster barrier, and each CTA takes the maximum of the candidates from its own
-// shared memory.  Slots are double-buffered by pick parity: a fast CTA can only run one pick ahead of a slow one.  The
-// barrier costs ~1 us per pick -- too much for N <= 8192, where one SM does a pick in 0.8 us (measured),
-// but 5x less than walking 24 k points through a global-memory distance array (fps_big_kernel: 7.1 us per pick).
+// keys, so the same point wins); warp 0 then sends the CTA's winner (key + xyz, 20 bytes) to EVERY CTA of the cluster with
+// st.async -- a distributed-shared-memory store that signals the receiver's mbarrier (complete_tx) -- and every thread
+// waits on its OWN CTA's mbarrier until the CL messages of this pick have landed, then takes the maximum of the
+// candidates from local shared memory.  No cluster-wide hardware barrier: the first version used cluster.sync() per pick
+// and spent ~2 us per pick in it whatever N (profiles/r4_kernel_sweep.md: 2.07 ms for 1024 picks at N = 16 k .. 32 k).
+// Slots and mbarriers are double-buffered by pick parity: a CTA sends pick i+2 only after it has received every CTA's
+// pick i+1, i.e. after every CTA has finished reading the slots of pick i.
 constexpr int FPS_CL_MAX = 16;        // 16 CTAs per cluster is the non-portable maximum (one cluster per GPC)
+
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t fps_mapa(uint32_t saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void fps_send4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void fps_send1(uint32_t raddr, uint32_t rbar, uint32_t a) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(raddr), "r"(a), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
 
 template <int PPT, int T>
 __global__ void __launch_bounds__(T, 1)
@@ -138,8 +164,9 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
     constexpr int W = T / 32;
     __shared__ uint32_t s_hi[2][W], s_lo[2][W];
     __shared__ float s_xyz[2][W][3];
-    __shared__ uint32_t c_hi[2][FPS_CL_MAX], c_lo[2][FPS_CL_MAX];
-    __shared__ float c_xyz[2][FPS_CL_MAX][3];
+    __shared__ __align__(16) uint32_t c_msg[2][FPS_CL_MAX][4];   // {key hi, key lo, x, y} of every CTA's winner
+    __shared__ uint32_t c_z[2][FPS_CL_MAX];
+    __shared__ __align__(8) uint64_t c_bar[2];
 
     const int CL = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -163,7 +190,12 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
     }
     int cur = min(max(start[b], 0), NV - 1);       // a caller-supplied first pick outside [0, NV) is clamped, never dereferenced
     float cx = p[cur * 3 + 0], cy = p[cur * 3 + 1], cz = p[cur * 3 + 2];
-    cluster.sync();                                            // every CTA of the cluster is resident before remote stores
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&c_bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&c_bar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();                                            // every CTA is resident and its mbarriers exist before remote stores
 
     for (int i = 0; i < C; ++i) {
         if (rank == 0 && tid == 0) {
@@ -175,6 +207,9 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
         }
         if (i + 1 == C) break;
         const int buf = i & 1;
+        const uint32_t bar = fps_smem_u32(&c_bar[buf]);
+        if (tid == 0)                                          // this pick's CL messages: 20 bytes each
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(CL * 20)) : "memory");
         uint32_t mb = 0;
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
@@ -222,23 +257,22 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int C, const int32_t* _
             warp_max_pair(gh, gl);
             const uint32_t who = __ballot_sync(PCNBR_FULL, lane < W && mh == gh && ml == gl);
             const int w = __ffs(who) - 1;
-            if (lane < CL) {                                   // lane r publishes this CTA's winner into CTA r
-                uint32_t* rh = cluster.map_shared_rank(&c_hi[buf][rank], lane);
-                uint32_t* rl = cluster.map_shared_rank(&c_lo[buf][rank], lane);
-                float* rx = cluster.map_shared_rank(&c_xyz[buf][rank][0], lane);
-                *rh = gh; *rl = gl;
-                rx[0] = s_xyz[buf][w][0]; rx[1] = s_xyz[buf][w][1]; rx[2] = s_xyz[buf][w][2];
+            if (lane < CL) {                                   // lane r sends this CTA's winner to CTA r (slot [buf][rank] there)
+                const uint32_t rbar = fps_mapa(bar, (uint32_t)lane);
+                fps_send4(fps_mapa(fps_smem_u32(&c_msg[buf][rank][0]), (uint32_t)lane), rbar, gh, gl,
+                          __float_as_uint(s_xyz[buf][w][0]), __float_as_uint(s_xyz[buf][w][1]));
+                fps_send1(fps_mapa(fps_smem_u32(&c_z[buf][rank]), (uint32_t)lane), rbar, __float_as_uint(s_xyz[buf][w][2]));
             }
         }
-        cluster.sync();                                        // release the remote stores, acquire everybody else's
-        uint32_t gh = c_hi[buf][0], gl = c_lo[buf][0];
+        fps_mbar_wait_cluster(bar, (uint32_t)((i >> 1) & 1));     // all CL winners of this pick have landed here
+        uint32_t gh = c_msg[buf][0][0], gl = c_msg[buf][0][1];
         int w = 0;
         for (int r = 1; r < CL; ++r) {
-            const uint32_t h = c_hi[buf][r], l = c_lo[buf][r];
+            const uint32_t h = c_msg[buf][r][0], l = c_msg[buf][r][1];
             if (h > gh || (h == gh && l > gl)) { gh = h; gl = l; w = r; }
         }
         cur = (int)(0xffffffffu - gl);                       // torch.max: lowest index on ties (common.py:31)
-        cx = c_xyz[buf][w][0]; cy = c_xyz[buf][w][1]; cz = c_xyz[buf][w][2];
+        cx = __uint_as_float(c_msg[buf][w][2]); cy = __uint_as_float(c_msg[buf][w][3]); cz = __uint_as_float(c_z[buf][w]);
     }
     cluster.sync();                                            // no CTA exits while a peer may still store into it
 }
@@ -356,12 +390,17 @@ extern "C" int pcnbr_fps_len_f32(const float* xyz, int B, int N, int C, const in
     }
 #undef PCNBR_FPS_CASE
     if (N <= 16 * 8192 && B * 8 <= 148 * 2) {
-        // cluster of 4 (N <= 32768), 8 (N <= 65536) or 16 CTAs (N <= 131072, non-portable size: one cluster per GPC) per
-        // cloud, 8 points per thread; ceiling: the CL SMs per cloud
-        const int CL = N <= 4 * 8192 ? 4 : (N <= 8 * 8192 ? 8 : 16);
+        // One cloud on a cluster, 16 points per thread as in the single-CTA kernel (fat threads: the per-pick cost is the
+        // block reduction plus the exchange, both cheaper with fewer warps -- 1024 threads x 8 points cost 1.8 us per pick):
+        //   N <= 32768 : ceil(N / 4096) CTAs (2..8) of 256 threads;   N <= 65536 : 8 CTAs of 512 threads;
+        //   N <= 131072: 16 CTAs of 512 threads (non-portable cluster size: one cluster per GPC).
+        // ceiling: the CL SMs per cloud
+        const bool wide = N > 8 * 4096;
+        const int CL = !wide ? (N + 4095) / 4096 : (N <= 8 * 8192 ? 8 : 16);
         const double wfc = 10.0 * B * (double)N * C * 2.0 * 148.0 / (double)(B * CL < 148 ? B * CL : 148);
         int rc = 0;
-        PCNBR_TIMED("fps_cluster_kernel", s, wb, wfc, (rc = fps_launch_cluster<8, 1024>(CL, B, xyz, N, C, start, n_valid, idx_out, xyz_out, s)));
+        if (wide) PCNBR_TIMED("fps_cluster_kernel", s, wb, wfc, (rc = fps_launch_cluster<16, 512>(CL, B, xyz, N, C, start, n_valid, idx_out, xyz_out, s)));
+        else      PCNBR_TIMED("fps_cluster_kernel", s, wb, wfc, (rc = fps_launch_cluster<16, 256>(CL, B, xyz, N, C, start, n_valid, idx_out, xyz_out, s)));
         if (rc) return rc;
     } else {
         if (!ws || ws_bytes < pcnbr_fps_ws_bytes(B, N)) return PCNBR_E_WORKSPACE;
