@@ -8,7 +8,7 @@
 // runs as three TF32 tensor-core products  hi.hi' + lo.hi' + hi.lo'  accumulated in one fp32 TMEM accumulator
 // (error ~2^-20 |a||b|: fp32-grade).  No operand is pre-processed in HBM:
 //   * hi is the fp32 word itself: kind::tf32 reads the top 19 bits of each operand word and ignores the low 13
-//     (measured on B200, scratch/tf32_trunc_probe.py), so hi = trunc_tf32(x) costs nothing;
+//     (measured on B200, tools/tf32_trunc_probe.py), so hi = trunc_tf32(x) costs nothing;
 //   * lo = tf32_rna(x - trunc_tf32(x)) is produced INSIDE the kernel: eight converter warps read the freshly landed
 //     TMA tile from shared memory and write the residual tile next to it (same offsets, so the 128-byte swizzle is
 //     preserved without address arithmetic), publish it to the async proxy and hand the stage to the MMA warp;

@@ -279,7 +279,7 @@ def run_reference(args):
     }
     if clk:
         line["clocks"] = clk
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # --------------------------------------------------------------------------- roofline bookkeeping
@@ -574,7 +574,7 @@ def run_ours(args):
                          "e2e": r["e2e"], "unit": UNIT, "clocks": r["clocks"]}
             line["strong"] = st
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         # captured graphs held NCCL work: tear down in order (device sync, then the group) and leave without the
         # interpreter's atexit pass, which can block on the communicator
@@ -584,8 +584,36 @@ def run_ours(args):
         os._exit(0)
 
 
+class _QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on file descriptor
+    1 whatever NCCL_DEBUG_FILE says on some builds; subprocesses inherit it), so the descriptor itself is pointed at stderr
+    for the whole run and only emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str) -> None:
+        sys.stdout.flush()
+        os.write(self.real, (text.rstrip("\n") + "\n").encode())
+
+
+OUT = None
+
+
+def emit_line(line: dict) -> None:
+    text = json.dumps(line)
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global OUT
     args = parse()
+    OUT = _QuietStdout()
     if args.impl == "reference":
         run_reference(args)
     else:

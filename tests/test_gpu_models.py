@@ -97,7 +97,7 @@ def _as_good_as_reference(ours, ref32, ref64, what, factor=3.0):
 
     factor: 3 for logits.  For parameter gradients the comparison is between two samples of rounding noise amplified
     by the BatchNorm chain (the reference's own fp32 gradients are 1-3 % away from fp64 here); measured on B200
-    (scratch/noise_probe.py, ~100 parameter tensors) our error is 1.3x the reference's in the median and 5-6x for the
+    (tools/noise_probe.py, ~100 parameter tensors) our error is 1.3x the reference's in the median and 5-6x for the
     worst tensor (0.75x / 3.1x with the library SGEMM instead of the 3xTF32 tensor-core GEMM, whose products carry
     2^-21 instead of 2^-24), so gradients get factor 8.  Quantities that are mathematically zero (the gradient of a
     bias in front of a training-mode BatchNorm: ~1e5 terms of size ~1e2 cancelling to ~1e-11) are noise in ANY fp32
