@@ -292,7 +292,19 @@ knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, 
             mx = fmaxf(mx, xx[(size_t)b * N + n]);
         }
     }
-    if (lane == 0) {
+    // one pair of atomics per CTA, not per warp: 1184 warps per cloud hammering two addresses serialised in L2 (~25 of the
+    // kernel's 35 us)
+    __shared__ float s_mx[8], s_mxc[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(PCNBR_FULL, mx, d));
+        mxc = fmaxf(mxc, __shfl_xor_sync(PCNBR_FULL, mxc, d));
+    }
+    if (lane == 0) { s_mx[warp] = mx; s_mxc[warp] = mxc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { mx = fmaxf(mx, s_mx[w]); mxc = fmaxf(mxc, s_mxc[w]); }
         atomicMax(&scal[4 * b], __float_as_uint(mx));
         atomicMax(&scal[4 * b + 1], __float_as_uint(mxc));
     }
@@ -595,7 +607,7 @@ __device__ __forceinline__ u64 rerank_key(const float* xj, const float* q, float
 // (value, index) keys are sorted by rank counting across the warp: the lane with rank r < K writes idx[r].
 // Rows whose queue overflowed are re-ranked by an exact full scan with the same WarpList as the CUDA-core kernels.
 // dynamic smem: 8 warps x (32 x RR_STRIDE + 64) floats
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)       // 71 KB of shared memory allow three CTAs per SM anyway: up to 80 registers, no spills
 knn_tc_rerank_kernel(const float* __restrict__ xt, const float* __restrict__ xx, const int32_t* __restrict__ qcnt,
                      const uint16_t* __restrict__ qidx, int N, int F, int K, const int32_t* __restrict__ n_valid,
                      int32_t* __restrict__ idx, int32_t* __restrict__ stats) {
