@@ -38,6 +38,9 @@ PROTOTYPES = {
     "pcnbr_knn_expand_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P]),
     "pcnbr_knn_tc_debug_f32": (_I, [_P, _I, _I, _I, _L, _L, _I, _P, _P, _Z, _P, _P, _P]),
     "pcnbr_group_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "pcnbr_gather_rows_f32": (_I, [_P, _P, _I, _I, _L, _I, _P, _P]),
+    "pcnbr_gather_rows_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "pcnbr_square_distance_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "pcnbr_csr_ws_bytes": (_Z, [_I, _I, _I]),
     "pcnbr_csr_build": (_I, [_P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "pcnbr_csr_rows_ws_bytes": (_Z, [_I, _I, _I, _I]),

@@ -124,9 +124,82 @@ struct RowMajorDst {
     __device__ __forceinline__ void store(int b, int s, int c, float v) const { out[((size_t)b * N + s) * D + c] = v; }
 };
 
+// ---- index_points: plain row gather out[b,e,:] = src[b, idx[b,e], :]  (the `points[batch_indices, indices]` of
+// common.py:64-65,117 on its own; north-star name index_points).  One warp per output row, float4 when the rows allow it.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int N, long E, int D, float* __restrict__ out) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const long nw = (long)gridDim.x * 8;
+    const bool vec4 = (D % 4 == 0) && ((((uintptr_t)src | (uintptr_t)out) & 15) == 0);
+    for (long e = (long)blockIdx.x * 8 + (threadIdx.x >> 5); e < E; e += nw) {
+        const int n = min(max(idx[(size_t)b * E + e], 0), N - 1);                     // an out-of-range index is clamped, never dereferenced
+        const float* __restrict__ r = src + ((size_t)b * N + n) * D;
+        float* __restrict__ o = out + ((size_t)b * E + e) * D;
+        if (vec4) {
+            for (int c = lane * 4; c < D; c += 128) *reinterpret_cast<float4*>(o + c) = *reinterpret_cast<const float4*>(r + c);
+        } else {
+            for (int c = lane; c < D; c += 32) o[c] = r[c];
+        }
+    }
+}
+struct GatherBwdSrc {
+    const float* g; long E; int D;
+    __device__ __forceinline__ const float* row(int b, int e) const { return g + ((size_t)b * E + e) * D; }
+    __device__ __forceinline__ float scale(int, int) const { return 1.0f; }
+};
+
+// ---- square_distance: the (B,N,M) matrix ((dst - src)^2).sum(-1) of common.py:54-56 / 110-112, materialised.  Inspection /
+// compatibility only: no kernel of the path ever builds it.  dst tiles of 256 points in shared memory, one thread per src.
+__global__ void __launch_bounds__(256)
+square_distance_kernel(const float* __restrict__ src, const float* __restrict__ dst, int N, int M, float* __restrict__ out) {
+    __shared__ float sx[256], sy[256], sz[256];
+    const int b = blockIdx.z, n = blockIdx.x * 256 + threadIdx.x, m0 = blockIdx.y * 256;
+    const int mt = min(256, M - m0);
+    if ((int)threadIdx.x < mt) {
+        const float* d = dst + ((size_t)b * M + m0 + threadIdx.x) * 3;
+        sx[threadIdx.x] = d[0]; sy[threadIdx.x] = d[1]; sz[threadIdx.x] = d[2];
+    }
+    __syncthreads();
+    if (n >= N) return;
+    const float* s = src + ((size_t)b * N + n) * 3;
+    const float x = s[0], y = s[1], z = s[2];
+    float* __restrict__ o = out + ((size_t)b * N + n) * M + m0;
+    for (int j = 0; j < mt; ++j) o[j] = d2_direct(sx[j], sy[j], sz[j], x, y, z);          // (dst - src)^2 summed as (dx2 + dy2) + dz2
+}
+
 }  // namespace pcnbr
 
 using namespace pcnbr;
+
+extern "C" int pcnbr_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, long E, int D, float* out, pcnbr_stream_t stream) {
+    if (!src || !idx || !out || B <= 0 || N <= 0 || E <= 0 || D <= 0) return PCNBR_E_BADARG;
+    if (B > 65535) return PCNBR_E_TOOLARGE;
+    const long gx = (E + 7) / 8 < 148L * 16 ? (E + 7) / 8 : 148L * 16;
+    PCNBR_TIMED("gather_rows_kernel", (cudaStream_t)stream, (double)B * (8.0 * E * D + 4.0 * E), 0.0,
+                (gather_rows_kernel<<<dim3((unsigned)gx, B), 256, 0, (cudaStream_t)stream>>>(src, idx, N, E, D, out)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_gather_rows_bwd_f32(const float* gout, const int32_t* offsets, const int32_t* perm, int B, int N, int E, int D,
+                                         float* gsrc, pcnbr_stream_t stream) {
+    if (!gout || !offsets || !perm || !gsrc || B <= 0 || N <= 0 || E <= 0 || D <= 0) return PCNBR_E_BADARG;
+    GatherBwdSrc src{gout, (long)E, D};
+    RowMajorDst dst{gsrc, (long)N, D};
+    PCNBR_TIMED("segsum_kernel<gather_bwd>", (cudaStream_t)stream, (double)B * (4.0 * E * D + 4.0 * E + 4.0 * N + 4.0 * N * D), (double)B * E * D,
+                (segsum_kernel<<<segsum_grid(N, B), 256, 0, (cudaStream_t)stream>>>(src, dst, offsets, perm, N, E, D)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int pcnbr_square_distance_f32(const float* src, const float* dst, int B, int N, int M, float* out, pcnbr_stream_t stream) {
+    if (!src || !dst || !out || B <= 0 || N <= 0 || M <= 0) return PCNBR_E_BADARG;
+    if (B > 65535 || (M + 255) / 256 > 65535) return PCNBR_E_TOOLARGE;
+    PCNBR_TIMED("square_distance_kernel", (cudaStream_t)stream, (double)B * (4.0 * N * M + 12.0 * (N + M)), 8.0 * B * (double)N * M,
+                (square_distance_kernel<<<dim3((N + 255) / 256, (M + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(src, dst, N, M, out)));
+    PCNBR_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int pcnbr_group_f32(const float* p, const float* feat, const float* q, const int32_t* idx, int B,
                                int N, int M, int K, int D, float rdiv, float* out, int ldo, pcnbr_stream_t stream) {

@@ -593,22 +593,50 @@ def knn_graph(x: torch.Tensor, k: int, _keep: list | None = None, lengths=None) 
 
 
 def square_distance(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
-    """(B,N,3),(B,M,3) -> (B,N,M) squared distances ((dst - src)**2).sum(-1).  Debug/inspection helper
-    only (plain torch; the kernels never materialise this matrix)."""
+    """(B,N,3),(B,M,3) -> (B,N,M) squared distances ((dst - src)**2).sum(-1), the matrix of common.py:54-56 / 110-112 with the
+    reference's rounding sequence.  Compatibility / inspection only: the selection kernels never materialise it."""
     _check(src, "src"); _check(dst, "dst")
-    return ((dst.unsqueeze(1) - src.unsqueeze(2)) ** 2).sum(dim=-1)
+    if src.dim() != 3 or dst.dim() != 3 or src.shape[-1] != 3 or dst.shape[-1] != 3 or src.shape[0] != dst.shape[0]:
+        raise ValueError(f"pcnbr: square_distance wants (B,N,3) and (B,M,3), got {tuple(src.shape)} and {tuple(dst.shape)}")
+    src, dst = _c(src), _c(dst)
+    B, N, _ = src.shape
+    M = dst.shape[1]
+    out = torch.empty(B, N, M, dtype=torch.float32, device=src.device)
+    _lib.call("pcnbr_square_distance_f32", src.data_ptr(), dst.data_ptr(), B, N, M, out.data_ptr(), _stream())
+    return out
+
+
+class _GatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, nbr: NeighborIndex):
+        B, N, D = points.shape
+        E = nbr.idx[0].numel()
+        out = torch.empty(B, E, D, dtype=torch.float32, device=points.device)
+        _lib.call("pcnbr_gather_rows_f32", points.data_ptr(), nbr.idx.data_ptr(), B, N, E, D, out.data_ptr(), _stream())
+        ctx.nbr, ctx.dims = nbr, (B, N, E, D)
+        if ctx.needs_input_grad[0]:
+            nbr.prefetch_csr()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N, E, D = ctx.dims
+        offsets, perm = ctx.nbr.csr()
+        gsrc = torch.empty(B, N, D, dtype=torch.float32, device=g.device)
+        _lib.call("pcnbr_gather_rows_bwd_f32", _c(g).data_ptr(), offsets.data_ptr(), perm.data_ptr(), B, N, E, D, gsrc.data_ptr(), _stream())
+        return gsrc, None
 
 
 def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-    """points (B,N,D), idx (B,M,K) or (B,M) -> points[b, idx] (the gathers of common.py:64-65,117)."""
+    """points (B,N,D), idx (B,M,K) or (B,M) -> points[b, idx] (the gathers of common.py:64-65,117): one gather kernel,
+    atomic-free scatter-add backward.  Indices outside [0, N) are clamped (torch would raise)."""
     _check(points, "points")
-    squeeze = idx.dim() == 2
-    idx3 = idx.unsqueeze(-1) if squeeze else idx
+    if points.dim() != 3 or idx.dim() not in (2, 3) or idx.shape[0] != points.shape[0]:
+        raise ValueError(f"pcnbr: index_points wants (B,N,D) and (B,M[,K]), got {tuple(points.shape)} and {tuple(idx.shape)}")
     B, N, D = points.shape
-    zeros = torch.zeros(B, idx3.shape[1], 3, dtype=torch.float32, device=points.device)
-    pz = torch.zeros(B, N, 3, dtype=torch.float32, device=points.device)
-    out = group_points(pz, points, zeros, NeighborIndex(_as_i32(idx3), N), None)[..., 3:]
-    return out.squeeze(2) if squeeze else out
+    nbr = NeighborIndex(_as_i32(idx), N)
+    out = _GatherFn.apply(_c(points), nbr)
+    return out.view(*idx.shape, D)
 
 
 # ----------------------------------------------------------------------------- K5 group (+ K7 backward)

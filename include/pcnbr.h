@@ -140,6 +140,16 @@ PCNBR_API int pcnbr_knn_tc_debug_f32(const float* x, int B, int F, int N, long s
 PCNBR_API int pcnbr_group_f32(const float* p, const float* feat, const float* q, const int32_t* idx,
                     int B, int N, int M, int K, int D, float rdiv, float* out, int ldo, pcnbr_stream_t stream);
 
+/* ---- index_points / square_distance (north-star names; common.py:64-65,117 and :54-56) -----------------------------
+ * pcnbr_gather_rows_f32: out (B,E,D) = src[b, idx[b,e], :], src (B,N,D), idx (B,E) (out-of-range indices are clamped).
+ * pcnbr_gather_rows_bwd_f32: gsrc (B,N,D) = sum over incoming e of gout[b,e,:], CSR of idx from pcnbr_csr_build; fixed order.
+ * pcnbr_square_distance_f32: out (B,N,M) = ((dst[b,m] - src[b,n])^2).sum(-1) as (dx*dx + dy*dy) + dz*dz -- the matrix the
+ * reference materialises and no kernel of this library needs; kept for callers that inspect it. */
+PCNBR_API int pcnbr_gather_rows_f32(const float* src, const int32_t* idx, int B, int N, long E, int D, float* out, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_gather_rows_bwd_f32(const float* gout, const int32_t* offsets, const int32_t* perm, int B, int N, int E, int D,
+                              float* gsrc, pcnbr_stream_t stream);
+PCNBR_API int pcnbr_square_distance_f32(const float* src, const float* dst, int B, int N, int M, float* out, pcnbr_stream_t stream);
+
 /* ---- K7 inverse index (CSR by source point) for the atomic-free scatter-add backward
  * idx (B,E) values in [0,N).  offsets (B,N+1): segment bounds; perm (B,E): positions e grouped
  * by source, ascending e inside a segment (deterministic).  ws: pcnbr_csr_ws_bytes(B,E,N). */

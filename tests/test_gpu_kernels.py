@@ -215,6 +215,38 @@ def test_group_backward_is_deterministic(pkg, dev):
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
 
 
+# --------------------------------------------------------------------------- index_points / square_distance (north-star names)
+
+@pytest.mark.parametrize("N,D,shape", [(1024, 6, (256, 32)), (4096, 64, (1024,)), (333, 130, (77, 5)), (64, 3, (16, 32)), (50, 1, (7,))])
+def test_index_points_is_the_reference_gather_with_scatter_add_backward(pkg, dev, N, D, shape):
+    """points[batch_indices, indices] of common.py:64-65,117: values bit-exact, backward = index_put_(accumulate=True)."""
+    B = 3
+    g = _gen(N + D)
+    pts = torch.randn(B, N, D, generator=g)
+    idx = torch.randint(0, N, (B, *shape), generator=g)
+    idx[0].view(-1)[: min(8, idx[0].numel())] = 0                                        # a hub
+    pd = pts.to(dev).requires_grad_(True)
+    for ix in (idx.to(dev), idx.to(dev).int()):
+        out = pkg.ops.index_points(pd, ix)
+        want = pts[torch.arange(B).view(B, *([1] * len(shape))), idx]
+        assert out.shape == want.shape and torch.equal(out.detach().cpu(), want)
+    w = torch.randn(out.shape, generator=g)
+    (out * w.to(dev)).sum().backward()
+    pr = pts.clone().requires_grad_(True)
+    (pr[torch.arange(B).view(B, *([1] * len(shape))), idx] * w).sum().backward()
+    assert torch.allclose(pd.grad.cpu(), pr.grad, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("N,M", [(4096, 1024), (300, 77), (1, 1), (257, 513)])
+def test_square_distance_matches_the_reference_expression(pkg, dev, N, M):
+    pts, _, _ = O.s3dis_blocks(2, max(N, M), seed=N + M)
+    src, dst = pts[:, :N, :3].contiguous(), pts[:, :M, :3].flip(1).contiguous()
+    want = ((dst.unsqueeze(1) - src.unsqueeze(2)) ** 2).sum(dim=-1)                      # common.py:54-56
+    assert torch.equal(pkg.ops.square_distance(src.to(dev), dst.to(dev)).cpu(), want)
+    with pytest.raises(ValueError):
+        pkg.ops.square_distance(src.to(dev), dst[:1].to(dev))
+
+
 # --------------------------------------------------------------------------- K6 max-pool
 
 @pytest.mark.parametrize("shape", [(2, 5, 7, 11), (2, 64, 32, 64), (3, 16, 32, 513), (1, 10, 1, 4)])
