@@ -75,6 +75,7 @@ PROTOTYPES = {
     "pcnbr_split_f16": (_I, [_P, _I, _I, _L, _I, _P, _P, _L, _L, _P]),
     "pcnbr_gemm2h_ex_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _L, _I, _P, _Z, _P, _P, _P, _P, _L, _L, _P]),
     "pcnbr_confusion_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "pcnbr_confusion_ex_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "pcnbr_masked_ce_blocks": (_I, [_I]),
     "pcnbr_masked_ce_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "pcnbr_block_batch": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

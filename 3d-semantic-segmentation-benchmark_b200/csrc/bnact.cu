@@ -47,9 +47,19 @@ __device__ __forceinline__ float4 ba_ld(const float* __restrict__ a, long lda, c
     return v;
 }
 
-// block tree reduction over the row lanes of (s1, s2) per column, result written by row lane 0 to partial[blk][2][C]
+// block tree reduction over the row lanes of (s1, s2) per column, result written by row lane 0 to partial[blk][2][C].
+// pivot != nullptr: the sums were taken about pivot[j] (per column) and are moved to the common pivot x0[column] on
+// the way out: s1 + n d, s2 + 2 d s1 + n d^2, d = pivot - x0.
+__device__ __forceinline__ void ba_rebase(float& a, float& q, float piv, float x0, float n) {
+    // fp32 FMAs: each step rounds at 2^-24 of n d^2, the same order as storing the result as a float (fp64 here cost 30 us
+    // per PointNet++ step on the B200's fp64 pipe for nothing)
+    const float d = piv - x0, nd = n * d, s1 = a;
+    a = s1 + nd;
+    q = fmaf(nd, d, fmaf(2.0f * d, s1, q));
+}
 template <int NCOL>
-__device__ __forceinline__ void ba_block_reduce(const BaMap& m, float4 (&s1)[NCOL], float4 (&s2)[NCOL], int C, float* __restrict__ partial) {
+__device__ __forceinline__ void ba_block_reduce(const BaMap& m, float4 (&s1)[NCOL], float4 (&s2)[NCOL], int C, float* __restrict__ partial,
+                                                const float4* pivot = nullptr, const float* __restrict__ x0 = nullptr, float nrows = 0.f) {
     __shared__ float4 red[2 * BA_T];
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
@@ -67,28 +77,38 @@ __device__ __forceinline__ void ba_block_reduce(const BaMap& m, float4 (&s1)[NCO
             __syncthreads();
         }
         if (m.ty == 0) {
+            float4 a = red[threadIdx.x], q = red[BA_T + threadIdx.x];
+            if (pivot) {
+                const float4 z = *reinterpret_cast<const float4*>(x0 + m.col + j * 4 * BA_T);
+                ba_rebase(a.x, q.x, pivot[j].x, z.x, nrows); ba_rebase(a.y, q.y, pivot[j].y, z.y, nrows);
+                ba_rebase(a.z, q.z, pivot[j].z, z.z, nrows); ba_rebase(a.w, q.w, pivot[j].w, z.w, nrows);
+            }
             float* dst = partial + (size_t)blockIdx.x * 2 * C + m.col + j * 4 * BA_T;
-            *reinterpret_cast<float4*>(dst) = red[threadIdx.x];
-            *reinterpret_cast<float4*>(dst + C) = red[BA_T + threadIdx.x];
+            *reinterpret_cast<float4*>(dst) = a;
+            *reinterpret_cast<float4*>(dst + C) = q;
         }
         __syncthreads();
     }
 }
 
 // partial[blk] = { sum_r (x - shift), sum_r (x - shift)^2 } over the block's rows; shift = row 0 of x.
+// Every block ACCUMULATES about its own first row (a pivot inside its own data) and moves the two sums to the common pivot
+// once when it writes them: s1' = s1 + n d, s2' = s2 + 2 d s1 + n d^2 with d = pivot_block - x[0].  If row 0 of the
+// tensor is an outlier (|x0 - mean| = D sigma), accumulating about it loses ~rows-per-block * 2^-24 * D^2 of the variance
+// in the fp32 running sums; moved afterwards, only the final rounding of the partial (2^-24 * D^2) remains.
 template <int NCOL>
 __global__ void __launch_bounds__(BA_T)
 bn_stats_kernel(const float* __restrict__ x, long R, int C, int rows_per_block, float* __restrict__ partial) {
     const BaMap m = ba_map(C);
     float4 sh[NCOL], s1[NCOL], s2[NCOL];
+    const long r0 = (long)blockIdx.x * rows_per_block;
+    const long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
-        sh[j] = *reinterpret_cast<const float4*>(x + m.col + j * 4 * BA_T);
+        sh[j] = *reinterpret_cast<const float4*>(x + (r0 < R ? r0 : 0) * C + m.col + j * 4 * BA_T);      // the block's own pivot
         s1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         s2[j] = s1[j];
     }
-    const long r0 = (long)blockIdx.x * rows_per_block;
-    const long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
 #pragma unroll 4
     for (long r = r0 + m.ty; r < r1; r += m.TY) {
 #pragma unroll
@@ -100,7 +120,8 @@ bn_stats_kernel(const float* __restrict__ x, long R, int C, int rows_per_block, 
             s2[j].z = fmaf(dz, dz, s2[j].z); s2[j].w = fmaf(dw, dw, s2[j].w);
         }
     }
-    ba_block_reduce<NCOL>(m, s1, s2, C, partial);
+    const float nrows = r1 > r0 ? (float)(r1 - r0) : 0.f;
+    ba_block_reduce<NCOL>(m, s1, s2, C, partial, sh, x, nrows);
 }
 
 // Combine the block partials (fp64, ascending block order) into the BatchNorm constants

@@ -16,10 +16,10 @@ constexpr int MT_MAXC = 64;
 
 __global__ void __launch_bounds__(256)
 confusion_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ onehot, const long long* __restrict__ lengths,
-                 int N, int C, unsigned long long* __restrict__ matrix) {
-    extern __shared__ int mt_tile[];                     // C * C
+                 int N, int C, unsigned long long* __restrict__ matrix, unsigned long long* __restrict__ unlabeled) {
+    extern __shared__ int mt_tile[];                     // C * C (+ C: predictions of the rows without any label)
     const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) mt_tile[i] = 0;
+    for (int i = threadIdx.x; i < C * C + C; i += blockDim.x) mt_tile[i] = 0;
     __syncthreads();
     long long len = lengths ? lengths[b] : (long long)N;
     if (len > N) len = N;
@@ -35,11 +35,15 @@ confusion_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ one
             const uint8_t w = l[c];
             if (w > lb) { lb = w; lc = c; }
         }
-        atomicAdd(&mt_tile[lc * C + pc], 1);
+        atomicAdd(&mt_tile[lc * C + pc], 1);              // an all-zero label row counts as class 0: labels.argmax(-1), metrics.py:20,72
+        if (unlabeled && lb == 0) atomicAdd(&mt_tile[C * C + pc], 1);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C * C; i += blockDim.x)
         if (mt_tile[i]) atomicAdd(&matrix[i], (unsigned long long)mt_tile[i]);
+    if (unlabeled)
+        for (int i = threadIdx.x; i < C; i += blockDim.x)
+            if (mt_tile[C * C + i]) atomicAdd(&unlabeled[i], (unsigned long long)mt_tile[C * C + i]);
 }
 
 }  // namespace pcnbr
@@ -48,14 +52,19 @@ using namespace pcnbr;
 
 extern "C" int pcnbr_confusion_f32(const float* pred, const uint8_t* onehot, const long long* lengths, int B, int N, int C,
                                    long long* matrix, pcnbr_stream_t stream) {
+    return pcnbr_confusion_ex_f32(pred, onehot, lengths, B, N, C, matrix, nullptr, stream);
+}
+
+extern "C" int pcnbr_confusion_ex_f32(const float* pred, const uint8_t* onehot, const long long* lengths, int B, int N, int C,
+                                      long long* matrix, long long* unlabeled, pcnbr_stream_t stream) {
     if (!pred || !onehot || !matrix || B <= 0 || N <= 0 || C <= 0) return PCNBR_E_BADARG;
     if (C > MT_MAXC) return PCNBR_E_TOOLARGE;
     cudaStream_t s = (cudaStream_t)stream;
     int gx = (N + 255) / 256;
     if (gx > 148 * 4) gx = 148 * 4;
     PCNBR_TIMED("confusion_kernel", s, (double)B * N * (5.0 * C) + 8.0 * C * C, 2.0 * B * (double)N * C,
-                (confusion_kernel<<<dim3(gx, B), 256, (size_t)C * C * sizeof(int), s>>>(pred, onehot, lengths, N, C,
-                                                                                     (unsigned long long*)matrix)));
+                (confusion_kernel<<<dim3(gx, B), 256, (size_t)(C * C + C) * sizeof(int), s>>>(pred, onehot, lengths, N, C,
+                                                                                     (unsigned long long*)matrix, (unsigned long long*)unlabeled)));
     PCNBR_CHECK_LAUNCH();
     return 0;
 }

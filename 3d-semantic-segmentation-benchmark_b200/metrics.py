@@ -17,9 +17,10 @@ __all__ = ["confusion_matrix_device", "overall_accuracy", "update_accuracy", "co
 
 
 def confusion_matrix_device(predictions: torch.Tensor, labels: torch.Tensor, mask: torch.Tensor | None,
-                            out: torch.Tensor | None = None) -> torch.Tensor:
+                            out: torch.Tensor | None = None, unlabeled: torch.Tensor | None = None) -> torch.Tensor:
     """(C,C) int64 on the device, matrix[label, predicted]; accumulated into `out` when given (validation loops keep one
-    matrix for the whole set and read it once).  No host synchronisation."""
+    matrix for the whole set and read it once).  No host synchronisation.  unlabeled (C,) int64, accumulated: predictions of
+    the rows whose label row is all zero (class 0 for the matrix, no class for the IoU, see _iou_terms)."""
     if not predictions.is_cuda:
         raise RuntimeError("pcnbr: predictions must be a CUDA tensor (this build has no CPU fallback)")
     B, N, C = predictions.shape
@@ -27,9 +28,21 @@ def confusion_matrix_device(predictions: torch.Tensor, labels: torch.Tensor, mas
     lab = _c(labels.to(device=pred.device, dtype=torch.uint8))
     lens = None if mask is None else _c(mask.to(device=pred.device, dtype=torch.int64))
     m = torch.zeros(C, C, dtype=torch.int64, device=pred.device) if out is None else out
-    _lib.call("pcnbr_confusion_f32", pred.data_ptr(), lab.data_ptr(), lens.data_ptr() if lens is not None else None,
-              B, N, C, m.data_ptr(), _stream())
+    _lib.call("pcnbr_confusion_ex_f32", pred.data_ptr(), lab.data_ptr(), lens.data_ptr() if lens is not None else None,
+              B, N, C, m.data_ptr(), unlabeled.data_ptr() if unlabeled is not None else None, _stream())
     return m
+
+
+def _iou_terms(m: torch.Tensor, unl: torch.Tensor):
+    """(intersections, unions) of Training/metrics.py:97-110,131-144 from the confusion matrix and the unlabeled-row counts:
+    the reference tests `labels[..., c] == 1`, so a row without any label is in no class's label set -- it only enlarges
+    the union of the class it was predicted as -- while the matrix files it under label 0."""
+    inter = m.diagonal().clone()
+    rows = m.sum(dim=1)
+    inter[0] -= unl[0]
+    rows[0] -= unl.sum()
+    union = rows + m.sum(dim=0) - inter
+    return inter, union
 
 
 def update_accuracy(predictions, labels, mask):
@@ -52,9 +65,9 @@ def confusion_matrix(predictions, labels, mask) -> torch.Tensor:
 
 def update_intersection_over_union(predictions, labels, mask):
     """-> (intersections (C,), unions (C,)) float32 CPU tensors   [metrics.py:115-146]."""
-    m = confusion_matrix_device(predictions, labels, mask)
-    inter = m.diagonal()
-    union = m.sum(dim=0) + m.sum(dim=1) - inter
+    unl = torch.zeros(predictions.shape[-1], dtype=torch.int64, device=predictions.device)
+    m = confusion_matrix_device(predictions, labels, mask, unlabeled=unl)
+    inter, union = _iou_terms(m, unl)
     both = torch.stack((inter, union)).to(torch.float32).cpu()
     return both[0], both[1]
 

@@ -72,13 +72,13 @@ def evaluate(model: torch.nn.Module, test_loader, criterion=None, device: str = 
             loss_sum = loss if loss_sum is None else loss_sum + loss
             if matrix is None:
                 matrix = torch.zeros(outputs.shape[-1], outputs.shape[-1], dtype=torch.int64, device=outputs.device)
-            metrics.confusion_matrix_device(outputs, labels, lengths, out=matrix)      # argmax of logits == argmax of softmax
+                unl = torch.zeros(outputs.shape[-1], dtype=torch.int64, device=outputs.device)
+            metrics.confusion_matrix_device(outputs, labels, lengths, out=matrix, unlabeled=unl)   # argmax of logits == argmax of softmax
             batches += 1
     if batches == 0:
         raise ValueError("evaluate: empty loader")
     m = matrix.cpu()
-    inter = m.diagonal().to(torch.float32)
-    union = (m.sum(dim=0) + m.sum(dim=1) - m.diagonal()).to(torch.float32)
+    inter, union = (t.to(torch.float32) for t in metrics._iou_terms(m, unl.cpu()))
     eps = 1e-6
     ious = (inter + eps) / (union + eps)
     return (loss_sum / batches).item(), (m.diagonal().sum() / m.sum()).item(), ious.mean().item(), ious, m

@@ -311,6 +311,11 @@ PCNBR_API int pcnbr_gemm3x_ex_f32(const float* A, long lda, int a_mn, const floa
  * per-class intersections / unions of metrics.py are functions of it.  C <= 64. */
 PCNBR_API int pcnbr_confusion_f32(const float* pred, const uint8_t* onehot, const long long* lengths, int B, int N, int C,
                         long long* matrix, pcnbr_stream_t stream);
+/* Extended form: unlabeled (C) int64, ACCUMULATED like matrix: unlabeled[p] += rows whose label row is all zero and whose
+ * prediction is p.  The confusion matrix and the accuracy take such a row as class 0 (labels.argmax(-1), metrics.py:20,72),
+ * the IoU functions test labels[..., c] == 1 (metrics.py:103,137): it belongs to no class there. */
+PCNBR_API int pcnbr_confusion_ex_f32(const float* pred, const uint8_t* onehot, const long long* lengths, int B, int N, int C,
+                           long long* matrix, long long* unlabeled, pcnbr_stream_t stream);
 
 /* ---- training loss ---------------------------------------- Training/train_model.py:15-57
  * Masked one-hot cross entropy: loss[0] = mean over the unpadded points (n < lengths[b]) of -sum_c onehot * log_softmax

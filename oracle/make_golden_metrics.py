@@ -40,6 +40,22 @@ def main():
     torch.save(dict(pred=pred, labels=lab, mask=mask, confusion=cm, correct=correct, total=total, inter=inter, union=union,
                     miou=miou, ious=ious, acc=acc), os.path.join(ROOT, "tests", "golden", "metrics.pt"))
     print("wrote tests/golden/metrics.pt", cm.sum().item(), "points, acc", acc, "mIoU", miou)
+    # ---- malformed label rows (all zero): the confusion matrix / accuracy file them under class 0 (labels.argmax, :20,72),
+    # the IoU functions under no class (labels[..., c] == 1, :103,137)
+    lab2 = lab.clone()
+    lab2[0, ::7] = 0
+    lab2[1, :40] = 0
+    mask2 = torch.tensor([257, 100, 5], dtype=torch.int64)
+    cm2 = RM.confusion_matrix(pred, lab2, mask2)
+    c2, t2 = RM.update_accuracy(pred, lab2, mask2)
+    i2, u2 = RM.update_intersection_over_union(pred, lab2, mask2)
+    m2, ious2 = RM.intersection_over_union(pred, lab2, mask2)
+    assert torch.equal(cm2, O.metrics_confusion_matrix(pred, lab2, mask2)) and (c2, t2) == O.metrics_update_accuracy(pred, lab2, mask2)
+    oi, ou = O.metrics_update_iou(pred, lab2, mask2)
+    assert torch.equal(i2, oi) and torch.equal(u2, ou)
+    torch.save(dict(pred=pred, labels=lab2, mask=mask2, confusion=cm2, correct=c2, total=t2, inter=i2, union=u2, miou=m2, ious=ious2),
+               os.path.join(ROOT, "tests", "golden", "metrics_unlabeled.pt"))
+    print("wrote tests/golden/metrics_unlabeled.pt")
 
 
 if __name__ == "__main__":

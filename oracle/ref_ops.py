@@ -471,12 +471,20 @@ def metrics_update_accuracy(predictions, labels, mask):
 
 
 def metrics_update_iou(predictions, labels, mask):
-    """Training/metrics.py:115-146 -> (intersections (C,), unions (C,)) float32.  NB the reference tests
-    `labels[..., c] == 1` while the confusion matrix uses the label argmax: identical for one-hot rows."""
-    m = metrics_confusion_matrix(predictions, labels, mask)
-    inter = m.diagonal()
-    union = m.sum(0) + m.sum(1) - inter
-    return inter.to(torch.float32), union.to(torch.float32)
+    """Training/metrics.py:115-146 -> (intersections (C,), unions (C,)) float32.  The reference tests
+    `labels[..., c] == 1` (:137), NOT the label argmax the confusion matrix uses: a row without any 1 (malformed, or a
+    padding row inside `mask`) belongs to no class here, and only enlarges the union of the class it is predicted as."""
+    B, _, C = labels.shape
+    inter, union = torch.zeros(C), torch.zeros(C)
+    for b in range(B):
+        n = int(mask[b])
+        pc = predictions[b, :n].argmax(-1)
+        for c in range(C):
+            lm = labels[b, :n, c] == 1
+            pm = pc == c
+            inter[c] += float((lm & pm).sum())
+            union[c] += float((lm | pm).sum())
+    return inter, union
 
 
 def metrics_iou(predictions, labels, mask):

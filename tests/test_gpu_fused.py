@@ -246,6 +246,27 @@ def test_batchnorm_act_rows_matches_fp64(pkg, dev, R, C, slope, train):
     assert torch.equal(xd2.grad, xd.grad)
 
 
+@pytest.mark.parametrize("D", [30.0, 100.0])
+def test_batchnorm_statistics_survive_an_outlier_first_row(pkg, dev, D):
+    """the statistics are shifted sums about row 0.  With row 0 D sigma away from everything else, sums
+    ACCUMULATED about it lose ~rows-per-block * 2^-24 * D^2 of the variance (60 % at D = 100); every block now accumulates
+    about its own first row and moves its sums to the common pivot once -- what remains is a few 2^-24 * D^2."""
+    R, C = 200000, 64
+    g = torch.Generator().manual_seed(int(D))
+    x = 5.0 + 0.01 * torch.randn(R, C, generator=g)                  # near-constant channels: mean 5, sigma 0.01
+    x[0] += D * 0.01                                                  # the outlier pivot
+    x[R // 2, :8] -= D * 0.01                                         # and an outlier that is some block's first row or not
+    bn = torch.nn.BatchNorm1d(C).to(dev)
+    y = pkg.ops.batchnorm_act_rows(x.to(dev), bn, 1.0).cpu().double()          # slope 1: the normalised values themselves
+    x64 = x.double()
+    ref = (x64 - x64.mean(0)) / torch.sqrt(x64.var(0, unbiased=False) + bn.eps)
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 6e-7 * D * D + 1e-5, f"relative error {err:.2e}"
+    rv = bn.running_var.cpu().double()
+    want = 0.9 + 0.1 * x64.var(0, unbiased=True)
+    assert ((rv - want).abs() / want).max().item() <= 1e-5
+
+
 def test_batchnorm_act_rows_unsupported_width_uses_library(pkg, dev):
     x = torch.randn(512, 13, device=dev)
     bn = torch.nn.BatchNorm1d(13).to(dev)

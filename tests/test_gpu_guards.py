@@ -148,3 +148,68 @@ def test_gemm_writes_stay_in_bounds(pkg, dev, M, N, K, kernel):
     a.check()
     ref = A.double() @ Bm.double().t()
     assert float((out.double() - ref).abs().max()) <= 3e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("N,M,K", [(2049, 301, 32), (777, 33, 17), (9001, 130, 20)])
+def test_length_aware_entry_points_write_in_bounds_and_in_range(pkg, dev, N, M, K):
+    """pcnbr_*_len_f32: ragged per-cloud lengths, outputs in canary arenas; every index stays below the cloud's
+    own length for the real rows and is the in-range filler for the padding rows."""
+    L, a = pkg._lib, Arena(dev)
+    B = 3
+    p = _cloud(B, N, N + K, dev)
+    lens = torch.tensor([N, max(K, N // 3), max(K, 41)], dtype=torch.int32, device=dev)
+    for b in range(B):
+        p[b, int(lens[b]):] = 0.0
+    start = torch.tensor([N - 1, 5, 10 ** 6], dtype=torch.int32, device=dev)              # out-of-range start: clamped
+    C = 64
+    fi, fo = a.out((B, C), torch.int32), a.out((B, C, 3), torch.float32)
+    nb = L.size("pcnbr_fps_ws_bytes", B, N)
+    ws = a.out((max(nb, 4),), torch.uint8)
+    L.call("pcnbr_fps_len_f32", p.data_ptr(), B, N, C, start.data_ptr(), lens.data_ptr(), fi.data_ptr(), fo.data_ptr(), ws.data_ptr(), nb, _stream())
+    q = fo[:, :min(M, C)].contiguous()
+    Mq = q.shape[1]
+    qlen = torch.tensor([Mq, Mq // 2, 1], dtype=torch.int32, device=dev)
+    gnb = L.size("pcnbr_grid_ws_bytes", B, N)
+    for use_grid in (False, True):
+        wsg = a.out((gnb,), torch.uint8) if use_grid else None
+        bi = a.out((B, Mq, K), torch.int32)
+        L.call("pcnbr_ball_query_len_f32", q.data_ptr(), p.data_ptr(), B, Mq, N, pkg.ops._r2(0.2), K, qlen.data_ptr(), lens.data_ptr(),
+               bi.data_ptr(), wsg.data_ptr() if use_grid else None, gnb if use_grid else 0, _stream())
+        ki, kd = a.out((B, Mq, 3), torch.int32), a.out((B, Mq, 3), torch.float32)
+        L.call("pcnbr_knn_direct_len_f32", q.data_ptr(), p.data_ptr(), B, Mq, N, 3, qlen.data_ptr(), lens.data_ptr(), ki.data_ptr(),
+               kd.data_ptr(), wsg.data_ptr() if use_grid else None, gnb if use_grid else 0, _stream())
+        a.check()
+        for b in range(B):
+            assert int(bi[b].max()) < int(lens[b]) and int(ki[b].max()) < int(lens[b]) and int(bi[b].min()) >= 0
+    assert all(int(fi[b].max()) < int(lens[b]) for b in range(B))
+    F = 64 if N < 5000 else 3
+    x = torch.randn(B, F, N, generator=torch.Generator().manual_seed(N)).to(dev)
+    gi = a.out((B, N, K), torch.int32)
+    nb2 = L.size("pcnbr_knn_expand_ws_bytes", B, F, N, K)
+    ws2 = a.out((nb2,), torch.uint8)
+    L.call("pcnbr_knn_expand_len_f32", x.data_ptr(), B, F, N, N, 1, K, lens.data_ptr(), gi.data_ptr(), ws2.data_ptr(), nb2, _stream())
+    a.check()
+    for b in range(B):
+        n = int(lens[b])
+        assert int(gi[b, :n].max()) < n and int(gi[b].min()) >= 0 and int(gi[b, n:].max() if n < N else 0) < K
+
+
+@pytest.mark.parametrize("N,E,D", [(1000, 777, 6), (333, 4100, 130), (64, 33, 3)])
+def test_gather_rows_and_square_distance_write_in_bounds(pkg, dev, N, E, D):
+    L, a = pkg._lib, Arena(dev)
+    B = 2
+    src = torch.randn(B, N, D, device=dev)
+    idx = torch.randint(-5, N + 5, (B, E), device=dev, dtype=torch.int32)                  # out-of-range indices are clamped
+    out = a.out((B, E, D), torch.float32)
+    L.call("pcnbr_gather_rows_f32", src.data_ptr(), idx.data_ptr(), B, N, E, D, out.data_ptr(), _stream())
+    a.check()
+    assert torch.equal(out, src[torch.arange(B, device=dev)[:, None], idx.clamp(0, N - 1).long()])
+    nbr = pkg.ops.NeighborIndex(idx.clamp(0, N - 1), N)
+    off, perm = nbr.csr()
+    gs = a.out((B, N, D), torch.float32)
+    L.call("pcnbr_gather_rows_bwd_f32", out.data_ptr(), off.data_ptr(), perm.data_ptr(), B, N, E, D, gs.data_ptr(), _stream())
+    p, q = _cloud(B, N, N, dev), _cloud(B, E, E, dev)
+    d2 = a.out((B, N, E), torch.float32)
+    L.call("pcnbr_square_distance_f32", p.data_ptr(), q.data_ptr(), B, N, E, d2.data_ptr(), _stream())
+    a.check()
+    assert bool(torch.isfinite(gs).all()) and bool((d2 >= 0).all())
