@@ -74,6 +74,9 @@ PROTOTYPES = {
     "pcnbr_gemm2h_preferred": (_I, [_I, _I, _I]),
     "pcnbr_split_f16": (_I, [_P, _I, _I, _L, _I, _P, _P, _L, _L, _P]),
     "pcnbr_gemm2h_ex_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _L, _I, _P, _Z, _P, _P, _P, _P, _L, _L, _P]),
+    "pcnbr_gemm2h_ex2_f32": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, _I, _P, _P, _L, _I, _P, _Z, _P, _P, _P, _P, _L, _L,
+                                  _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P]),
+    "pcnbr_gemm2h_trace": (_I, [_P]),
     "pcnbr_confusion_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "pcnbr_confusion_ex_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "pcnbr_masked_ce_blocks": (_I, [_I]),

@@ -20,6 +20,7 @@
 // fp16 -- with one named barrier between "everything read into registers" and "first store".
 #include "gemm_common.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace pcnbr {
 
@@ -30,13 +31,20 @@ constexpr int H2_CONV_THREADS = 32 * GM_CONV_WARPS;          // threads of ONE c
 // BN = 256, ~80 % of the stage's MMA time in issue slots alone) ONE group leaves two warps per scheduler to hide the
 // LDS -> ALU -> STS latencies and the barrier, and the MMA warp waits for it; TWO groups take alternate stages, so the
 // conversion of stage i+1 overlaps the tail of stage i.  With a pre-split B (forward / input gradient) one group is plenty.
-template <bool B_PRE> constexpr int h2_groups() { return B_PRE ? 1 : 2; }
-template <bool B_PRE> constexpr int h2_threads() { return 192 + h2_groups<B_PRE>() * H2_CONV_THREADS; }
+#ifndef H2_PRE_GROUPS
+#define H2_PRE_GROUPS 1
+#endif
+template <bool B_PRE> constexpr int h2_groups() { return B_PRE ? H2_PRE_GROUPS : 2; }
+// + one "plane writer" warp behind the converters of the pre-split-B variants (forward / input gradient): it stores the
+// converted A tiles to HBM for the weight-gradient GEMM (see PRE2 below) when the caller asks for them.
+template <bool B_PRE, bool PRE2 = false> constexpr int h2_threads() {
+    return PRE2 ? 192 : 192 + h2_groups<B_PRE>() * H2_CONV_THREADS + (B_PRE ? 32 : 0);
+}
 
 // kind::f16 (A, B = fp16, both K-major), D = fp32, M = 128, N = BN (cute::UMMA::InstrDescriptor)
-template <int BN>
+template <int BN, bool MN = false>
 __device__ __forceinline__ void h2_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, bool accumulate) {
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | ((MN ? 3u : 0u) << 15) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
     const uint32_t acc = accumulate ? 1u : 0u;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -51,9 +59,21 @@ __device__ __forceinline__ uint64_t h2_desc(uint32_t saddr) {
     const uint64_t hi = (uint64_t)(512 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)4 << 29);
     return lo | (hi << 32);
 }
+// MN-major fp16 tile as TMA SWIZZLE_128B boxes of 64 MN-elements (128 B) x 32 K rows: an 8-row group is one swizzle atom
+// (1024 B, SBO), the next 64 MN-elements are one box (4096 B, LBO) further; layout type 2 = SWIZZLE_128B; a K step of 16
+// = two atoms = +2048 B
+__device__ __forceinline__ uint64_t h2_desc_mn(uint32_t saddr) {
+    const uint64_t lo = (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(4096 >> 4) << 16);
+    const uint64_t hi = (uint64_t)(1024 >> 4) | ((uint64_t)1 << 14) | ((uint64_t)2 << 29);
+    return lo | (hi << 32);
+}
 // byte offset of the 16-byte chunk g (8 fp16 of K) of row r in a [rows x 32 fp16] K-major SWIZZLE_64B tile
 __device__ __forceinline__ uint32_t h2_dst_off(int r, int g) { return (uint32_t)(r * 64 + ((g ^ ((r >> 1) & 3)) << 4)); }
 
+__device__ __forceinline__ void h2_tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void h2_tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -137,15 +157,41 @@ __device__ __forceinline__ void h2_tile_store(uint8_t* tile, uint32_t plane, int
     }
 }
 
+// Optional wait-time trace (tools/gemm_shapes.py --trace): when set, every role of every CTA adds the clock cycles it spent
+// waiting on each of its barriers into trace[blockIdx.x][slot] (16 slots of 8 bytes per CTA):
+//   0 producer: ring slot free   1 converters (group 0, warp 0): TMA landed   2 MMA: accumulator free   3 MMA: stage converted
+//   4 epilogue: accumulator full   5 epilogue: staging slab free (bulk store read)   6 CTA lifetime   7 converter busy time
+//   8 CTA lifetime in ns of %globaltimer (6 / 8 = the SM clock the kernel ran at)
+__device__ unsigned long long* g_h2_trace = nullptr;
+struct H2Wait {
+    unsigned long long* dst;
+    long long acc;
+    __device__ __forceinline__ H2Wait(unsigned long long* base, int slot) : dst(base ? base + (size_t)blockIdx.x * 16 + slot : nullptr), acc(0) {}
+    __device__ __forceinline__ long long begin() const { return dst ? clock64() : 0; }
+    __device__ __forceinline__ void end(long long t0) { if (dst) acc += clock64() - t0; }
+    __device__ __forceinline__ void flush() { if (dst) *dst = (unsigned long long)acc; }
+};
+
 // B_PRE: the B operand arrives already split ([hi | lo] fp16 planes written once by split_f16_kernel -- the weights of a
 // forward / input-gradient GEMM, which every CTA would otherwise convert again): TMA drops the two planes straight into
 // the UMMA layout (SWIZZLE_64B) and the converters only handle A (a third of the work at BN = 256).
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE>
-__global__ void __launch_bounds__(h2_threads<B_PRE>(), 1)
+// PRE2 (the weight gradients dW = gy^T x): BOTH operands arrive as [hi | lo] fp16 planes in their natural row-major
+// (rows = K = points, columns = M or N = channels) layout, i.e. MN-major -- written by the plane-writer warps of the
+// input-gradient GEMM (gy) and of the forward GEMM (x), whose converters had the split tiles in shared memory anyway.
+// tcgen05 reads MN-major fp16 straight from the TMA boxes, so this variant has no converter warps at all (they were its
+// bound: 4 B in + 4 B out per value through the LSU for BOTH operands, 0.45-0.5 of the pipe).
+// planes_out (B_PRE variants, K-major A; bit 0: A, bit 1: A2): tm_ap / tm_ap2 = the planes to write (units of the first column tile).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE, bool PRE2 = false>
+__global__ void __launch_bounds__(h2_threads<B_PRE, PRE2>(), 1)
 gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
-              const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c, int M, int N, int K,
+              const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_c,
+              const __grid_constant__ CUtensorMap tm_ap, const __grid_constant__ CUtensorMap tm_ap2, int planes_out,
+              int M, int N, int K,
               int kb_split, int splits, const float* __restrict__ bias, const float* __restrict__ amax_a,
               const float* __restrict__ amax_a2, const float* __restrict__ amax_b) {
+    static_assert(!PRE2 || (A_MN && B_MN && !B_PRE && BN >= 64 && BN % 64 == 0), "PRE2: both operands MN-major planes");
+    constexpr int WRITER_WARP = 6 + h2_groups<B_PRE>() * GM_CONV_WARPS;        // B_PRE variants only
+    const bool write_planes = B_PRE && !A_MN && !PRE2 && planes_out != 0;
     extern __shared__ uint8_t gm_smem_raw[];
     uint8_t* smem = gm_smem_raw + ((1024u - (gm_smem_u32(gm_smem_raw) & 1023u)) & 1023u);
     constexpr uint32_t A_BYTES = GM_SLAB, B_BYTES = (uint32_t)BN * 128u;
@@ -166,13 +212,22 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     const int KB = (K + GM_BK - 1) / GM_BK;
     const int kb_per = (KB + splits - 1) / splits;
     const int units = MT * NT * splits;
+    unsigned long long* const trace = g_h2_trace;
+    const long long t_cta = trace ? clock64() : 0;
+    unsigned long long ns_cta = 0;
+    if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_cta));
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
-        for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&conv[i], GM_CONV_WARPS); gm_mbar_init(&empty[i], 1); }
+        if (write_planes) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ap) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_ap2) : "memory");
+        }
+        // empty: the stage's MMAs have retired (+ the plane writer's bulk stores have read it)
+        for (int i = 0; i < STAGES; ++i) { gm_mbar_init(&full[i], 1); gm_mbar_init(&conv[i], GM_CONV_WARPS); gm_mbar_init(&empty[i], write_planes ? 2 : 1); }
         for (int i = 0; i < NBUF; ++i) { gm_mbar_init(&tmem_full[i], 1); gm_mbar_init(&tmem_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -206,15 +261,24 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     if (warp == 0) {
         // ===================================================== TMA producer (fp32 tiles, as in gemm3x_kernel)
         if (lane == 0) {
+            H2Wait w_ring(trace, 0);
             uint32_t stage = 0, phase = 0;
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
                 const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
                 const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    const long long t0 = w_ring.begin();
                     gm_mbar_wait(&empty[stage], phase ^ 1);
+                    w_ring.end(t0);
                     gm_mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
                     const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
-                    if (A_MN) {
+                    if (PRE2) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int j = 0; j < GM_BM / 64; ++j)
+                                h2_tma_load_3d(st + h * (A_BYTES / 2) + j * 4096, &tm_a, &full[stage], mt * GM_BM + j * 64, kb * GM_BK, h);
+                    } else if (A_MN) {
 #pragma unroll
                         for (int c = 0; c < GM_BM / 32; ++c)
                             gm_tma_load_2d(st + c * GM_CHUNK, &tm_a, &full[stage], mt * GM_BM + c * 32, kb * GM_BK);
@@ -223,7 +287,13 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                         else               gm_tma_load_2d(st, &tm_a2, &full[stage], (kb - kb_split) * GM_BK, mt * GM_BM);
                     }
                     const uint32_t sb = st + A_BYTES;
-                    if (B_PRE) {
+                    if (PRE2) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                h2_tma_load_3d(sb + h * (B_BYTES / 2) + j * 4096, &tm_b, &full[stage], nt * BN + j * 64, kb * GM_BK, h);
+                    } else if (B_PRE) {
                         h2_tma_load_3d(sb, &tm_b, &full[stage], kb * GM_BK, nt * BN, 0);                      // hi plane
                         h2_tma_load_3d(sb + B_BYTES / 2, &tm_b, &full[stage], kb * GM_BK, nt * BN, 1);        // lo plane
                     } else if (B_MN) {
@@ -238,6 +308,7 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            w_ring.flush();
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -245,26 +316,34 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         uint32_t stage = 0, phase = 0, tile = 0;
+        H2Wait w_acc(lane == 0 ? trace : nullptr, 2), w_conv(lane == 0 ? trace : nullptr, 3);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
             const int sp = unit / (MT * NT);
             const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
             const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
+            long long t0 = w_acc.begin();
             gm_mbar_wait(&tmem_empty[buf], tphase ^ 1);
+            w_acc.end(t0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + buf * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
                 const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
-                const uint64_t ah = h2_desc(st), al = h2_desc(st + A_BYTES / 2);
-                const uint64_t bh = h2_desc(st + A_BYTES), bl = h2_desc(st + A_BYTES + B_BYTES / 2);
-                gm_mbar_wait(&conv[stage], phase);                    // [hi | lo] tiles written and published
+                const uint64_t ah = PRE2 ? h2_desc_mn(st) : h2_desc(st), al = PRE2 ? h2_desc_mn(st + A_BYTES / 2) : h2_desc(st + A_BYTES / 2);
+                const uint64_t bh = PRE2 ? h2_desc_mn(st + A_BYTES) : h2_desc(st + A_BYTES);
+                const uint64_t bl = PRE2 ? h2_desc_mn(st + A_BYTES + B_BYTES / 2) : h2_desc(st + A_BYTES + B_BYTES / 2);
+                constexpr uint64_t KS = PRE2 ? (2048 >> 4) : 2;       // descriptor step of 16 K values
+                t0 = w_conv.begin();
+                if (PRE2) gm_mbar_wait(&full[stage], phase);          // planes land ready for the MMA
+                else      gm_mbar_wait(&conv[stage], phase);          // [hi | lo] tiles written and published
+                w_conv.end(t0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) h2_umma<BN>(d, ah + 2 * s, bh + 2 * s, kb > kb0 || s > 0);    // hi . hi'
+                    for (int s = 0; s < 2; ++s) h2_umma<BN, PRE2>(d, ah + KS * s, bh + KS * s, kb > kb0 || s > 0);    // hi . hi'
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) h2_umma<BN>(d, al + 2 * s, bh + 2 * s, true);                 // lo . hi'
+                    for (int s = 0; s < 2; ++s) h2_umma<BN, PRE2>(d, al + KS * s, bh + KS * s, true);                 // lo . hi'
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) h2_umma<BN>(d, ah + 2 * s, bl + 2 * s, true);                 // hi . lo'
+                    for (int s = 0; s < 2; ++s) h2_umma<BN, PRE2>(d, ah + KS * s, bl + KS * s, true);                 // hi . lo'
                     gm_umma_commit(&empty[stage]);
                 }
                 __syncwarp();
@@ -273,6 +352,7 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             if (leader) gm_umma_commit(&tmem_full[buf]);
             __syncwarp();
         }
+        w_acc.flush(); w_conv.flush();
     } else if (warp < 6) {
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
@@ -281,12 +361,15 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         const bool issuer = (warp == 2 && lane == 0);
         const float inv_a = s_scale[2], inv_b = s_scale[3];
         uint32_t tile = 0, slab = 0;
+        H2Wait w_full(issuer ? trace : nullptr, 4), w_slab(issuer ? trace : nullptr, 5);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
             const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
             const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
             const int ncols = min(BN, N - nt * BN);
             const int nq = (ncols + 31) / 32;
+            const long long t0 = w_full.begin();
             gm_mbar_wait(&tmem_full[buf], tphase);
+            w_full.end(t0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int q = 0; q < nq; ++q, ++slab) {
                 uint32_t r[32];
@@ -305,7 +388,11 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                     r[i] = __float_as_uint(v);
                 }
                 uint8_t* sb = cstage + (slab & 1) * GM_SLAB;
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (issuer) {
+                    const long long t1 = w_slab.begin();
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    w_slab.end(t1);
+                }
                 gm_epi_barrier();
                 uint8_t* rowp = sb + rloc * 128;
 #pragma unroll
@@ -320,7 +407,46 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             }
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    } else {
+        w_full.flush(); w_slab.flush();
+    } else if (B_PRE && warp == WRITER_WARP) {
+        // ===================================================== plane writer: converted A tiles -> HBM (first column tile only)
+        // Every A tile (mt, kb) is converted by the NT units of its row of tiles; the one with nt == hash(mt) % NT stores it (a
+        // fixed nt -- or mt % NT -- would put all the stores on a subset of the CTAs: the grid stride is a multiple of NT).  The ring slot
+        // is handed back one stage LATE -- when the next stage's stores have been issued and this stage's have read their
+        // shared memory -- so the writer never sits between a conversion and the slot's release.
+        if (write_planes && lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            int prev = -1;                                            // stage whose release is still owed
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
+                const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
+                const bool mine = nt == (int)((((uint32_t)mt * 2654435761u) >> 16) % (uint32_t)NT);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    gm_mbar_wait(&conv[stage], phase);                // the converters fenced their writes for the async proxy
+                    if (mine && (planes_out & (kb < kb_split ? 1 : 2))) {
+                        const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
+                        const CUtensorMap* map = kb < kb_split ? &tm_ap : &tm_ap2;
+                        const int kc = (kb < kb_split ? kb : kb - kb_split) * GM_BK;
+                        h2_tma_store_3d(map, st, kc, mt * GM_BM, 0);
+                        h2_tma_store_3d(map, st + A_BYTES / 2, kc, mt * GM_BM, 1);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");       // (possibly empty) group of this stage
+                    if (prev >= 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // all but this stage's group have read
+                        gm_mbar_arrive(&empty[prev]);
+                    }
+                    prev = (int)stage;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (prev >= 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                gm_mbar_arrive(&empty[prev]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+    } else if (!PRE2) {
         // ===================================================== converters: fp32 tile -> [hi | lo] fp16 tiles, in place
         constexpr int NG = h2_groups<B_PRE>();
         const int grp = (threadIdx.x - 192) / H2_CONV_THREADS;        // this warp's group: it converts the stages seq % NG == grp
@@ -329,6 +455,7 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         constexpr int TB = B_PRE ? 0 : h2_per_thread<BN>();
         const float sa = s_scale[0], sbs = s_scale[1];
         uint32_t stage = 0, phase = 0, seq = 0;
+        H2Wait w_land(threadIdx.x == 192 ? trace : nullptr, 1), w_busy(threadIdx.x == 192 ? trace : nullptr, 7);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int sp = unit / (MT * NT);
             const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
@@ -339,7 +466,10 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                 }
                 uint8_t* st = smem + stage * STAGE_BYTES;
                 uint8_t* sb = st + A_BYTES;
+                long long t0 = w_land.begin();
                 gm_mbar_wait(&full[stage], phase);
+                w_land.end(t0);
+                t0 = w_busy.begin();
                 // One operand tile at a time (each is rewritten in place inside its own region): every fp32 word of the tile is
                 // in registers before the first store -- one named barrier per group and tile.  Keeping the two tiles apart
                 // keeps the live registers low (the CTA's 22 warps leave 80 each).
@@ -360,12 +490,20 @@ gemm2h_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) gm_mbar_arrive(&conv[stage]);
+                w_busy.end(t0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        w_land.flush(); w_busy.flush();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (trace && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+        trace[(size_t)blockIdx.x * 16 + 6] = (unsigned long long)(clock64() - t_cta);
+        trace[(size_t)blockIdx.x * 16 + 8] = ns1 - ns_cta;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -472,12 +610,31 @@ static int h2_make_map(CUtensorMap* map, const float* base, long inner, long out
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE>
+// MN-major planes (the PRE2 operands): fp16 tensor (cols = M or N, rows = K, 2 planes), box = 64 halfs x 32 rows x 1 plane,
+// 128-byte swizzle; out-of-range elements read as 0
+static int h2_make_map_mnsplit(CUtensorMap* map, const void* base, long cols, long rows, long ld, long plane) {
+    GmEncodeFn enc = gm_encode_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+struct H2Planes {                       // planes of A (bit 0 of on) and A2 (bit 1) the forward / input-gradient kernel writes
+    CUtensorMap ap, ap2;
+    int on;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool B_PRE, bool PRE2 = false>
 static int h2_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
                      int M, int N, int K, int splits, const float* bias, const float* amax_a, const float* amax_a2,
-                     const float* amax_b, cudaStream_t s) {
+                     const float* amax_b, const H2Planes& pl, cudaStream_t s) {
     const size_t smem = (size_t)STAGES * (GM_SLAB + (size_t)BN * 128) + 2 * GM_SLAB + 64 * 8 + 64 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE, PRE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -490,21 +647,53 @@ static int h2_launch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split
     // the f16 pipe (1356.7 TFLOP/s sustained, MEASURED_PEAKS.json) than the operands need on HBM
     const char* name = 3.0 * flops / 1356.7e12 > bytes / 6551e9 ? "gemm2h_kernel[tensor]" : "gemm2h_kernel[hbm]";
     PCNBR_TIMED(name, s, bytes, flops,
-                (gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE><<<grid, h2_threads<B_PRE>(), smem, s>>>(ta, ta2, tb, tc, M, N, K, kb_split, splits, bias,
-                                                                                      amax_a, amax_a2, amax_b)));
+                (gemm2h_kernel<BN, STAGES, A_MN, B_MN, B_PRE, PRE2><<<grid, h2_threads<B_PRE, PRE2>(), smem, s>>>(
+                    ta, ta2, tb, tc, pl.ap, pl.ap2, pl.on, M, N, K, kb_split, splits, bias, amax_a, amax_a2, amax_b)));
     PCNBR_CHECK_LAUNCH();
     return 0;
+}
+
+// Tile width.  As gm_tile_n, plus 192 columns where that wastes fewer padding columns than 256 (N = 384: two full tiles
+// instead of one and a half -- the 384-channel skip concatenation of DGCNNWithColor is the N of conv5's input gradient
+// and weight gradient and of conv6's first K block: a quarter of their MMA time was spent on zero columns).  Not for a
+// raw K-major B, whose TMA boxes are 128-row slabs.
+static int h2_tile_n(int M, int N, int K, bool b_kmajor_raw) {
+    static const bool off = getenv("PCNBR_H2_NO192") != nullptr;               // A/B switch (tools/gemm_shapes.py)
+    const int bn = gm_tile_n(M, N, K);
+    if (bn == 256 && !off && !b_kmajor_raw && ((N + 191) / 192) * 192 < ((N + 255) / 256) * 256) return 192;
+    return bn;
 }
 
 template <bool A_MN, bool B_MN, bool B_PRE>
 static int h2_dispatch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_split, const CUtensorMap& tb, const CUtensorMap& tc,
                        int M, int N, int K, int splits, const float* bias, const float* amax_a, const float* amax_a2,
-                       const float* amax_b, cudaStream_t s) {
-    switch (gm_tile_n(M, N, K)) {                                            // stages: 48 / 32 / 24 / 20 KB each beside 32 KB of staging
-        case 256: return h2_launch<256, 4, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
-        case 128: return h2_launch<128, 5, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
-        case 64:  return h2_launch<64, 6, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
-        default:  return h2_launch<32, 6, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, s);
+                       const float* amax_b, const H2Planes& pl, cudaStream_t s) {
+    switch (h2_tile_n(M, N, K, !B_MN && !B_PRE)) {                           // stages: 48 / 40 / 32 / 24 / 20 KB each beside 32 KB of staging
+        case 256: return h2_launch<256, 4, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, pl, s);
+        case 192:
+            if constexpr (B_MN || B_PRE)
+                return h2_launch<192, 4, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, pl, s);
+            else
+                return PCNBR_E_BADARG;
+        case 128: return h2_launch<128, 5, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, pl, s);
+        case 64:  return h2_launch<64, 6, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, pl, s);
+        default:  return h2_launch<32, 6, A_MN, B_MN, B_PRE>(ta, ta2, kb_split, tb, tc, M, N, K, splits, bias, amax_a, amax_a2, amax_b, pl, s);
+    }
+}
+
+// both operands as MN-major planes (weight gradients): tile widths of whole 64-column boxes
+static bool h2_pre2_tile_ok(int M, int N, int K) { return h2_tile_n(M, N, K, false) >= 64; }
+static int h2_dispatch_pre2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, int splits,
+                            const float* amax_a, const float* amax_b, cudaStream_t s) {
+    H2Planes none;
+    none.ap = ta; none.ap2 = ta; none.on = 0;
+    const int kb_split = (K + GM_BK - 1) / GM_BK;
+    switch (h2_tile_n(M, N, K, false)) {
+        case 256: return h2_launch<256, 4, true, true, false, true>(ta, ta, kb_split, tb, tc, M, N, K, splits, nullptr, amax_a, nullptr, amax_b, none, s);
+        case 192: return h2_launch<192, 4, true, true, false, true>(ta, ta, kb_split, tb, tc, M, N, K, splits, nullptr, amax_a, nullptr, amax_b, none, s);
+        case 128: return h2_launch<128, 5, true, true, false, true>(ta, ta, kb_split, tb, tc, M, N, K, splits, nullptr, amax_a, nullptr, amax_b, none, s);
+        case 64:  return h2_launch<64, 6, true, true, false, true>(ta, ta, kb_split, tb, tc, M, N, K, splits, nullptr, amax_a, nullptr, amax_b, none, s);
+        default:  return PCNBR_E_BADARG;
     }
 }
 
@@ -513,6 +702,14 @@ static int h2_dispatch(const CUtensorMap& ta, const CUtensorMap& ta2, int kb_spl
 using namespace pcnbr;
 
 extern "C" int pcnbr_amax_slots(void) { return H2_AMAX_SLOTS; }
+
+// Diagnostic: buf = device array of 148 x 16 uint64 (or NULL to switch off) that the next gemm2h launches fill with the clock
+// cycles every role spent waiting (see H2Wait).  Synchronises the device; not for use under graph capture.
+extern "C" int pcnbr_gemm2h_trace(unsigned long long* buf) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemcpyToSymbol(g_h2_trace, &buf, sizeof(buf));
+}
 
 extern "C" int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, float* partial, pcnbr_stream_t stream) {
     if (!x || !partial || rows <= 0 || cols <= 0 || (cols % 4) || (ld % 4) || ld < cols || ((uintptr_t)x & 15)) return PCNBR_E_BADARG;
@@ -554,17 +751,22 @@ extern "C" int pcnbr_split_f16(const float* src, int rows, int cols, long ld, in
 // per-block maxima (pcnbr_amax_slots() floats each, from pcnbr_absmax_f32) of A, of A2 when given, and of B.
 // b_split != NULL: B is taken from the planes written by pcnbr_split_f16 (rows = N, cols = K; B / ldb / b_mn are ignored),
 // amax_b must be the array that call was given.
-extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
-                                   int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
-                                   size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
-                                   const void* b_split, long b_split_ld, long b_split_plane, pcnbr_stream_t stream) {
-    if (!A || (!B && !b_split) || !C || !amax_a || !amax_b || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
-    if ((lda % 4) || ((uintptr_t)A & 15)) return PCNBR_E_BADARG;
-    if (!b_split && ((ldb % 4) || ((uintptr_t)B & 15) || ldb < (b_mn ? N : K))) return PCNBR_E_BADARG;
-    if (b_split && ((b_split_ld % 8) || b_split_ld < K || ((uintptr_t)b_split & 15) || b_split_plane < (long)N * b_split_ld)) return PCNBR_E_BADARG;
-    const int Ka = A2 ? K1 : K;
-    if (lda < (a_mn ? M : Ka)) return PCNBR_E_BADARG;
-    if (A2 && (!amax_a2 || a_mn || K1 <= 0 || K1 >= K || (K1 % GM_BK) || (lda2 % 4) || ((uintptr_t)A2 & 15) || lda2 < K - K1)) return PCNBR_E_BADARG;
+// _ex2 adds the operand planes that link the three GEMMs of a layer:
+//   a_planes_out (/ a2_planes_out): with a pre-split B and a K-major A (forward: A = x; input gradient: A = gy) the kernel
+//       also WRITES the [hi | lo] fp16 split of A (of A2) it computes anyway: 2 planes of M rows, row pitch *_ld halfs (a multiple
+//       of 8, >= the operand's K), planes *_plane halfs apart -- bit-identical to pcnbr_split_f16(A, M, K, lda, 0, amax_a, ...);
+//   a_mnsplit + b_mnsplit: a_mn = b_mn = 1 (weight gradient dW = gy^T x) with BOTH operands given as such planes (rows = K):
+//       no in-kernel conversion; amax_a / amax_b must be the arrays the planes were written with.  A / B (fp32) may then be NULL.
+extern "C" int pcnbr_gemm2h_ex2_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
+                                    int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
+                                    size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
+                                    const void* b_split, long b_split_ld, long b_split_plane,
+                                    void* a_planes_out, long apo_ld, long apo_plane, void* a2_planes_out, long ap2o_ld, long ap2o_plane,
+                                    const void* a_mnsplit, long ams_ld, long ams_plane, const void* b_mnsplit, long bms_ld, long bms_plane,
+                                    pcnbr_stream_t stream) {
+    const bool pre2 = a_mnsplit && b_mnsplit;
+    if ((!A && !pre2) || (!B && !b_split && !pre2) || !C || !amax_a || !amax_b || M <= 0 || N <= 0 || K <= 0 || splits < 1) return PCNBR_E_BADARG;
+    if ((a_mnsplit != nullptr) != (b_mnsplit != nullptr)) return PCNBR_E_BADARG;
     if (ldc < N || (ldc % 4) || ((uintptr_t)C & 15)) return PCNBR_E_BADARG;
     if (splits > 1 && (!ws || ws_bytes < sizeof(float) * (size_t)splits * (size_t)M * (size_t)N)) return PCNBR_E_WORKSPACE;
     if (splits > 1 && bias) return PCNBR_E_BADARG;
@@ -573,9 +775,43 @@ extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const flo
         if ((kb + per - 1) / per != splits) return PCNBR_E_BADARG;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    const int bn = gm_tile_n(M, N, K);
+    float* out = splits > 1 ? (float*)ws : C;
+    const float* b = splits > 1 ? nullptr : bias;
+    if ((uintptr_t)out & 15) return PCNBR_E_BADARG;
+    CUtensorMap tc;
+    int rc = gm_make_map_c(&tc, out, M, N, splits > 1 ? N : ldc, splits);
+    if (rc) return rc;
+    if (pre2 && !(A && B && !h2_pre2_tile_ok(M, N, K))) {
+        // ---- both operands as MN-major planes
+        if (!a_mn || !b_mn || A2 || bias) return PCNBR_E_BADARG;
+        if ((ams_ld % 8) || ams_ld < M || ((uintptr_t)a_mnsplit & 15) || ams_plane < (long)K * ams_ld) return PCNBR_E_BADARG;
+        if ((bms_ld % 8) || bms_ld < N || ((uintptr_t)b_mnsplit & 15) || bms_plane < (long)K * bms_ld) return PCNBR_E_BADARG;
+        if (!h2_pre2_tile_ok(M, N, K)) return PCNBR_E_BADARG;
+        CUtensorMap ta, tb;
+        rc = h2_make_map_mnsplit(&ta, a_mnsplit, M, K, ams_ld, ams_plane);
+        if (!rc) rc = h2_make_map_mnsplit(&tb, b_mnsplit, N, K, bms_ld, bms_plane);
+        if (rc) return rc;
+        rc = h2_dispatch_pre2(ta, tb, tc, M, N, K, splits, amax_a, amax_b, s);
+        if (rc) return rc;
+        if (splits > 1) rc = gm_launch_reduce((const float*)ws, M, N, ldc, splits, C, s);
+        return rc;
+    }
+    if ((lda % 4) || ((uintptr_t)A & 15)) return PCNBR_E_BADARG;
+    if (!b_split && ((ldb % 4) || ((uintptr_t)B & 15) || ldb < (b_mn ? N : K))) return PCNBR_E_BADARG;
+    if (b_split && ((b_split_ld % 8) || b_split_ld < K || ((uintptr_t)b_split & 15) || b_split_plane < (long)N * b_split_ld)) return PCNBR_E_BADARG;
+    const int Ka = A2 ? K1 : K;
+    if (lda < (a_mn ? M : Ka)) return PCNBR_E_BADARG;
+    if (A2 && (!amax_a2 || a_mn || K1 <= 0 || K1 >= K || (K1 % GM_BK) || (lda2 % 4) || ((uintptr_t)A2 & 15) || lda2 < K - K1)) return PCNBR_E_BADARG;
+    const bool planes = a_planes_out != nullptr || a2_planes_out != nullptr;
+    if (planes) {
+        // written by the units of the first column tile while they convert A: needs the pre-split-B kernel and a K-major A
+        if (!b_split || a_mn || (a2_planes_out && !A2)) return PCNBR_E_BADARG;
+        if (a_planes_out && ((apo_ld % 8) || apo_ld < Ka || ((uintptr_t)a_planes_out & 15) || apo_plane < (long)M * apo_ld)) return PCNBR_E_BADARG;
+        if (a2_planes_out && ((ap2o_ld % 8) || ap2o_ld < K - K1 || ((uintptr_t)a2_planes_out & 15) || ap2o_plane < (long)M * ap2o_ld)) return PCNBR_E_BADARG;
+    }
+    const int bn = h2_tile_n(M, N, K, !b_split && !b_mn);
     CUtensorMap ta, ta2, tb;
-    int rc = a_mn ? h2_make_map(&ta, A, M, K, lda, 32) : h2_make_map(&ta, A, Ka, M, lda, 128);
+    rc = a_mn ? h2_make_map(&ta, A, M, K, lda, 32) : h2_make_map(&ta, A, Ka, M, lda, 128);
     if (!rc && A2) rc = h2_make_map(&ta2, A2, K - K1, M, lda2, 128);
     if (!A2) ta2 = ta;
     if (!rc) {
@@ -583,25 +819,36 @@ extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const flo
         else         rc = b_mn ? h2_make_map(&tb, B, N, K, ldb, 32) : h2_make_map(&tb, B, K, N, ldb, bn < 128 ? bn : 128);
     }
     if (rc) return rc;
+    H2Planes pl;
+    pl.ap = ta; pl.ap2 = ta; pl.on = 0;
+    if (planes) {
+        if (a_planes_out) rc = h2_make_map_split(&pl.ap, a_planes_out, Ka, M, apo_ld, apo_plane, 128);
+        if (!rc && a2_planes_out) rc = h2_make_map_split(&pl.ap2, a2_planes_out, K - K1, M, ap2o_ld, ap2o_plane, 128);
+        if (rc) return rc;
+        pl.on = (a_planes_out ? 1 : 0) | (a2_planes_out ? 2 : 0);           // which of A / A2 the plane writer stores
+    }
     const int kb_split = A2 ? K1 / GM_BK : (K + GM_BK - 1) / GM_BK;
-    float* out = splits > 1 ? (float*)ws : C;
-    const float* b = splits > 1 ? nullptr : bias;
-    if ((uintptr_t)out & 15) return PCNBR_E_BADARG;
-    CUtensorMap tc;
-    rc = gm_make_map_c(&tc, out, M, N, splits > 1 ? N : ldc, splits);
-    if (rc) return rc;
     const float* am2 = A2 ? amax_a2 : nullptr;
     if (b_split) {
-        rc = a_mn ? h2_dispatch<true, false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
-                  : h2_dispatch<false, false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+        rc = a_mn ? h2_dispatch<true, false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, pl, s)
+                  : h2_dispatch<false, false, true>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, pl, s);
     } else if (a_mn) {
-        rc = b_mn ? h2_dispatch<true, true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
-                  : h2_dispatch<true, false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+        rc = b_mn ? h2_dispatch<true, true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, pl, s)
+                  : h2_dispatch<true, false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, pl, s);
     } else {
-        rc = b_mn ? h2_dispatch<false, true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s)
-                  : h2_dispatch<false, false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, s);
+        rc = b_mn ? h2_dispatch<false, true, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, pl, s)
+                  : h2_dispatch<false, false, false>(ta, ta2, kb_split, tb, tc, M, N, K, splits, b, amax_a, am2, amax_b, pl, s);
     }
     if (rc) return rc;
     if (splits > 1) rc = gm_launch_reduce((const float*)ws, M, N, ldc, splits, C, s);
     return rc;
+}
+
+extern "C" int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
+                                   int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
+                                   size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
+                                   const void* b_split, long b_split_ld, long b_split_plane, pcnbr_stream_t stream) {
+    return pcnbr_gemm2h_ex2_f32(A, lda, a_mn, A2, lda2, K1, B, ldb, b_mn, M, N, K, bias, C, ldc, splits, ws, ws_bytes, amax_a, amax_a2,
+                                amax_b, b_split, b_split_ld, b_split_plane, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0, 0,
+                                stream);
 }

@@ -1038,6 +1038,56 @@ def _presplit(w: torch.Tensor, transpose: bool, amax: torch.Tensor) -> torch.Ten
     return out
 
 
+_GEMM_NO_PLANES = __import__("os").environ.get("PCNBR_GEMM_NO_PLANES") is not None   # A/B switch: weight gradients convert both operands in the kernel
+
+
+def _new_planes(x: torch.Tensor, amax):
+    """Buffer for the [hi | lo] fp16 planes (2, rows, pitch) of the (rows, cols) fp32 matrix x, written by the forward /
+    input-gradient GEMM that converts x anyway (pcnbr_gemm2h_ex2_f32: a_planes_out) and read MN-major by the weight-gradient
+    GEMM; None when the layer does not run on the fp16-split kernel."""
+    if amax is None or _GEMM_NO_PLANES:
+        return None
+    rows, cols = x.shape
+    return torch.empty(2, rows, (cols + 7) // 8 * 8, dtype=torch.float16, device=x.device)
+
+
+def _planes_hint(t: torch.Tensor, amax):
+    """The planes an earlier GEMM wrote for tensor object t with these very maxima (e.g. the skip concatenation feeds conv5
+    and conv6 of DGCNN: one split serves both weight gradients), if t has not been modified since."""
+    rec = getattr(t, "_pcnbr_planes", None)
+    if rec is not None and rec[1] == t._version and rec[2] is amax and rec[0].device == t.device:
+        return rec[0]
+    return None
+
+
+def _set_planes(t: torch.Tensor, planes) -> None:
+    """Remember planes for tensor object t -- only when the GEMM that was handed them really wrote them, together with the
+    maxima their scale was derived from (_mark_planes)."""
+    if planes is not None and getattr(planes, "_pcnbr_amax", None) is not None:
+        t._pcnbr_planes = (planes, t._version, planes._pcnbr_amax)
+
+
+def _mark_planes(planes, amax) -> None:
+    """planes now hold a split scaled by the power of two derived from amax (the weight gradient must be given the same).
+    Only _gemm3x calls this, right behind the kernel that wrote them: a GEMM that took the 3xTF32 kernel leaves them unmarked."""
+    if planes is not None:
+        planes._pcnbr_amax = amax
+
+
+def _planes_ok(planes) -> bool:
+    return planes is not None and getattr(planes, "_pcnbr_amax", None) is not None
+
+
+def _layer_planes(rows: torch.Tensor, x2d: torch.Tensor, amax, weight: torch.Tensor):
+    """(planes, ready) for a layer input: the buffer its forward GEMM writes the fp16 split of x into for the weight
+    gradient -- or, ready = True, the one an earlier layer's GEMM filled for the same tensor.  (None, False) when no weight
+    gradient will be asked for or the layer is not on the fp16-split kernel."""
+    if amax is None or _GEMM_NO_PLANES or not (torch.is_grad_enabled() and weight.requires_grad):
+        return None, False
+    hint = _planes_hint(rows, amax)
+    return (hint, True) if hint is not None else (_new_planes(x2d, amax), False)
+
+
 def _gemm_h2_wanted(M: int, N: int, K: int) -> bool:
     """The two-term fp16 kernel takes the GEMMs whose tensor-pipe bound exceeds their HBM bound (symmetric in M, N, K: the
     three GEMMs of a layer -- output, input gradient, weight gradient -- are classified alike)."""
@@ -1045,14 +1095,17 @@ def _gemm_h2_wanted(M: int, N: int, K: int) -> bool:
 
 
 def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=None, K1: int = 0, out=None,
-            amax_a=None, amax_b=None, amax_a2=None, b_split=None, force_h2: bool = False) -> torch.Tensor:
+            amax_a=None, amax_b=None, amax_a2=None, b_split=None, force_h2: bool = False,
+            a_planes_out=None, a2_planes_out=None, a_mns=None, b_mns=None) -> torch.Tensor:
     """C (M,N) = A (M,K) . B (N,K)^T (+ bias) on tcgen05 with fp32-grade accuracy: 3xTF32 from the fp32 operands, or -- for
     tensor-bound shapes -- the two-term fp16 split at twice the instruction rate (csrc/gemm_h2.cu; needs max |x| of each
     operand: amax_* = per-block maxima from _absmax, computed here when not handed in).
     a_mn / b_mn: the operand is stored transposed ((K,M) / (K,N) row-major).  Operands are 2-D, unit inner stride, any
     16-byte row pitch.  A2: A is the channel concatenation [A (M,K1) | A2 (M,K-K1)] (never materialised).  out: a
     preallocated (M,N) view with unit inner stride (e.g. a column block of a wider matrix).  b_split: B pre-split by
-    _presplit (with the same amax_b), only used on the fp16 path."""
+    _presplit (with the same amax_b), only used on the fp16 path.  a_planes_out / a2_planes_out (_new_planes; fp16 path with
+    b_split and a K-major A): the kernel also writes the split of A / A2.  a_mns + b_mns (a_mn = b_mn = True): both operands
+    are read from such planes -- the weight gradient without any in-kernel conversion."""
     splits = 1 if bias is not None else _lib.size("pcnbr_gemm3x_splits", M, N, K)
     nb = _lib.size("pcnbr_gemm3x_ws_bytes", M, N, K, splits)
     ws = _ws(nb, A.device)
@@ -1064,12 +1117,20 @@ def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=
         if A2 is not None and amax_a2 is None:
             amax_a2 = _absmax(A2)
         if amax_a is not None and amax_b is not None and (A2 is None or amax_a2 is not None):
-            _lib.call("pcnbr_gemm2h_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
+            pl = lambda t: (t.data_ptr(), t.stride(1), t.stride(0)) if t is not None else (None, 0, 0)
+            if not (_planes_ok(a_mns) and _planes_ok(b_mns) and a_mns._pcnbr_amax is amax_a and b_mns._pcnbr_amax is amax_b):
+                a_mns = b_mns = None
+            _lib.call("pcnbr_gemm2h_ex2_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
                       A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
                       bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0), splits, ws.data_ptr(), nb,
                       amax_a.data_ptr(), amax_a2.data_ptr() if amax_a2 is not None else None, amax_b.data_ptr(),
-                      b_split.data_ptr() if b_split is not None else None, b_split.stride(1) if b_split is not None else 0,
-                      b_split.stride(0) if b_split is not None else 0, _stream())
+                      *pl(b_split), *pl(a_planes_out if b_split is not None else None),
+                      *pl(a2_planes_out if b_split is not None else None), *pl(a_mns), *pl(b_mns), _stream())
+            if b_split is not None and not a_mn and (a_planes_out is not None or a2_planes_out is not None):
+                # [A | A2] are scaled with ONE power of two (that of the larger maximum): the planes carry it
+                am = amax_a if A2 is None else torch.maximum(amax_a, amax_a2)
+                _mark_planes(a_planes_out, am)
+                _mark_planes(a2_planes_out, am)
             return out
     _lib.call("pcnbr_gemm3x_ex_f32", A.data_ptr(), A.stride(0), int(a_mn), A2.data_ptr() if A2 is not None else None,
               A2.stride(0) if A2 is not None else 0, int(K1), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
@@ -1077,18 +1138,23 @@ def _gemm3x(A, a_mn: bool, B, b_mn: bool, M: int, N: int, K: int, bias=None, A2=
     return out
 
 
-def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None, amax_gy=None, amax_x=None) -> torch.Tensor:
+def _wgrad3x(gy: torch.Tensor, x: torch.Tensor, out=None, amax_gy=None, amax_x=None, gy_planes=None, x_planes=None) -> torch.Tensor:
     """dW (Cout,Cin) = gy^T x for gy (R,Cout), x (R,Cin), both contiguous.  For narrow layers the 128 x BN tile of the
     split-K GEMM would be mostly zero padding (too few useful bytes in flight per SM), so p consecutive rows are viewed
     as one row of p*Cout / p*Cin channels: the (p*Cout, p*Cin) product of the two views has dW as the sum of its p
-    diagonal blocks.  p-fold redundant flops on dense tiles -- still below the HBM time of these layers."""
+    diagonal blocks.  p-fold redundant flops on dense tiles -- still below the HBM time of these layers.
+    gy_planes / x_planes: the fp16 splits of gy and x written by the layer's input-gradient / forward GEMM (_new_planes)."""
     R, Cout = gy.shape
     Cin = x.shape[1]
     p = 1
     while 2 * p * Cout <= 128 and 2 * p * Cin <= 256 and R % (2 * p) == 0 and R // (2 * p) >= 4096:
         p *= 2
     if p == 1 or out is not None:
-        return _gemm3x(gy, True, x, True, Cout, Cin, R, out=out, amax_a=amax_gy, amax_b=amax_x)
+        if _planes_ok(gy_planes) and _planes_ok(x_planes):            # the maxima the planes were scaled with
+            amax_gy, amax_x = gy_planes._pcnbr_amax, x_planes._pcnbr_amax
+        else:
+            gy_planes = x_planes = None
+        return _gemm3x(gy, True, x, True, Cout, Cin, R, out=out, amax_a=amax_gy, amax_b=amax_x, a_mns=gy_planes, b_mns=x_planes)
     big = _gemm3x(gy.view(R // p, p * Cout), True, x.view(R // p, p * Cin), True, p * Cout, p * Cin, R // p)
     return big.view(p, Cout, p, Cin).diagonal(dim1=0, dim2=2).sum(dim=-1)
 
@@ -1117,7 +1183,9 @@ class _LinearRowsFn(torch.autograd.Function):
         ctx.has_bias = b is not None
         R, Cin = x.shape
         ctx.amax = _layer_amax(x, w, R, w.shape[0], Cin)
-        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
+        ctx.xp = _new_planes(x, ctx.amax[0]) if (ctx.needs_input_grad[1] and ctx.amax[1] is not None) else None
+        return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]),
+                       a_planes_out=ctx.xp)
 
     @staticmethod
     def backward(ctx, gy):
@@ -1127,9 +1195,11 @@ class _LinearRowsFn(torch.autograd.Function):
         gy = _c(gy)
         ax, aw = ctx.amax
         ag = _absmax(gy) if ax is not None else None
-        dx = (_gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw))
+        gp = _new_planes(gy, ag) if (ctx.xp is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) else None
+        dx = (_gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw), a_planes_out=gp)
               if ctx.needs_input_grad[0] else None)                                                                     # gy (R,Cout) . W (Cout,Cin)
-        dw = _wgrad3x(gy, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None                                # gy^T . x, split along R
+        dw = (_wgrad3x(gy, x, amax_gy=ag, amax_x=ax, gy_planes=gp, x_planes=ctx.xp)
+              if ctx.needs_input_grad[1] else None)                                                                     # gy^T . x, split along R
         db = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 
@@ -1141,13 +1211,18 @@ class _LinearBnActFn(torch.autograd.Function):
     (BatchNorm removes any per-channel shift) and gamma*rstd*sum(g') in eval mode."""
 
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0, amax_x=None, amax_y=None):
-        """amax_x: per-block maxima of x when its producer recorded them; amax_y: buffer that receives those of y."""
+    def forward(ctx, x, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0, amax_x=None, amax_y=None, x_planes=None,
+                x_planes_ready=False):
+        """amax_x: per-block maxima of x when its producer recorded them; amax_y: buffer that receives those of y; x_planes:
+        buffer for the fp16 split of x (_layer_planes) -- filled by this layer's forward GEMM unless x_planes_ready."""
         R, Cin = x.shape
         C = w.shape[0]
         dev = x.device
         ctx.amax = _layer_amax(x, w, R, C, Cin, amax_x)
-        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
+        # the split of x for the weight gradient: an earlier layer's GEMM may have written it already, else this one does
+        ctx.xp = x_planes if (ctx.needs_input_grad[1] and ctx.amax[0] is not None and ctx.amax[1] is not None) else None
+        h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]),
+                    a_planes_out=ctx.xp if not x_planes_ready else None)
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -1189,13 +1264,15 @@ class _LinearBnActFn(torch.autograd.Function):
         _lib.call("pcnbr_bn_act_bwd_apply_f32", gy.data_ptr(), h.data_ptr(), R, C, stats.data_ptr(), coef.data_ptr(), slope,
                   dh.data_ptr(), ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1],
                   ag.data_ptr() if ag is not None else None, _stream())
-        dx = (_gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw))
+        gp = _new_planes(dh, ag) if (ctx.xp is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) else None
+        dx = (_gemm3x(dh, False, w, True, R, Cin, C, amax_a=ag, amax_b=aw, b_split=_wsplit(w, True, aw), a_planes_out=gp)
               if ctx.needs_input_grad[0] else None)
-        dw = _wgrad3x(dh, x, amax_gy=ag, amax_x=ax) if ctx.needs_input_grad[1] else None
+        dw = (_wgrad3x(dh, x, amax_gy=ag, amax_x=ax, gy_planes=gp, x_planes=ctx.xp)
+              if ctx.needs_input_grad[1] else None)
         db = None
         if has_b and ctx.needs_input_grad[2]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
-        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 9
+        return (dx, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 11
 
 
 class _LinearBnActPoolFn(torch.autograd.Function):
@@ -1286,7 +1363,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x1, x2, w, b, gamma, beta, rm, rv, training, momentum, eps, slope, drop_p=0.0, amax_x1=None, amax_x2=None,
-                amax_y=None):
+                amax_y=None, x1_planes=None, x1_planes_ready=False, x2_planes=None, x2_planes_ready=False):
         R, K1 = x1.shape
         K2 = x2.shape[1]
         C = w.shape[0]
@@ -1295,8 +1372,12 @@ class _LinearBnActCatFn(torch.autograd.Function):
             ctx.amax = (amax_x1 if amax_x1 is not None else _absmax(x1), amax_x2 if amax_x2 is not None else _absmax(x2), _absmax(w))
         else:
             ctx.amax = (None, None, None)
+        # the splits of x1 / x2 for the two column blocks of the weight gradient (x1's may exist already: x1_planes)
+        want = (ctx.needs_input_grad[2] and None not in ctx.amax and x1_planes is not None and x2_planes is not None)
+        ctx.xp = (x1_planes, x2_planes) if want else (None, None)
         h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1, amax_a=ctx.amax[0], amax_a2=ctx.amax[1], amax_b=ctx.amax[2],
-                    b_split=_wsplit(w, False, ctx.amax[2]))
+                    b_split=_wsplit(w, False, ctx.amax[2]), a_planes_out=ctx.xp[0] if not x1_planes_ready else None,
+                    a2_planes_out=ctx.xp[1] if not x2_planes_ready else None)
         if training:
             nblk = _lib.size("pcnbr_bn_blocks", R, C)
             partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
@@ -1341,19 +1422,25 @@ class _LinearBnActCatFn(torch.autograd.Function):
                   ag.data_ptr() if ag is not None else None, _stream())
         # dx_i = dh . W[:, block i]: W (C, K1+K2) is the MN-major B operand, a column block is a pointer offset
         wt = _wsplit(w, True, aw)                                     # (2, K1 + K2, C): the transposed weight, split once
-        dx1 = (_gemm3x(dh, False, w[:, :K1], True, R, K1, C, amax_a=ag, amax_b=aw, b_split=wt[:, :K1] if wt is not None else None)
+        xp1, xp2 = ctx.xp
+        have_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gp = _new_planes(dh, ag) if (xp1 is not None and xp2 is not None and have_dx and ctx.needs_input_grad[2]) else None
+        dx1 = (_gemm3x(dh, False, w[:, :K1], True, R, K1, C, amax_a=ag, amax_b=aw, b_split=wt[:, :K1] if wt is not None else None,
+                       a_planes_out=gp)
                if ctx.needs_input_grad[0] else None)
-        dx2 = (_gemm3x(dh, False, w[:, K1:], True, R, K2, C, amax_a=ag, amax_b=aw, b_split=wt[:, K1:] if wt is not None else None)
+        dx2 = (_gemm3x(dh, False, w[:, K1:], True, R, K2, C, amax_a=ag, amax_b=aw, b_split=wt[:, K1:] if wt is not None else None,
+                       a_planes_out=gp if not ctx.needs_input_grad[0] else None)
                if ctx.needs_input_grad[1] else None)
         dw = None
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(w)
-            _wgrad3x(dh, x1, out=dw[:, :K1], amax_gy=ag, amax_x=a1)
-            _wgrad3x(dh, x2, out=dw[:, K1:], amax_gy=ag, amax_x=a2)
+            # with planes: _wgrad3x takes the maxima THEY were scaled with (x1's may come from an earlier layer, else the shared scale)
+            _wgrad3x(dh, x1, out=dw[:, :K1], amax_gy=ag, amax_x=a1, gy_planes=gp, x_planes=xp1)
+            _wgrad3x(dh, x2, out=dw[:, K1:], amax_gy=ag, amax_x=a2, gy_planes=gp, x_planes=xp2)
         db = None
         if has_b and ctx.needs_input_grad[3]:
             db = torch.zeros(C, dtype=torch.float32, device=dev) if training else coef[0] * dbeta
-        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 10
+        return (dx1, dx2, dw, db, dgamma if has_gamma else None, dbeta if has_beta else None) + (None,) * 14
 
 
 def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: torch.Tensor, bias, bn, negative_slope: float,
@@ -1379,10 +1466,15 @@ def linear_bn_act_cat_rows(rows1: torch.Tensor, rows2: torch.Tensor, weight: tor
         _set_amax(rows2, a2)
     if nrows * cout >= (1 << 22):
         ay = _amax_buffer(rows1.device)
+    xp1, r1 = _layer_planes(rows1, x1, a1, weight)
+    xp2, r2 = _layer_planes(rows2, x2, a2, weight)
     y = _LinearBnActCatFn.apply(x1, x2, _c(weight), bias, bn.weight, bn.bias,
-                                rm, rv, training, momentum, float(bn.eps), float(negative_slope), float(dropout_p), a1, a2, ay)
+                                rm, rv, training, momentum, float(bn.eps), float(negative_slope), float(dropout_p), a1, a2, ay,
+                                xp1, r1, xp2, r2)
     out = y.view(*rows1.shape[:-1], cout)
     _set_amax(out, ay)
+    _set_planes(rows1, xp1)
+    _set_planes(rows2, xp2)
     return out
 
 
@@ -1410,10 +1502,12 @@ def linear_bn_act_rows(rows: torch.Tensor, weight: torch.Tensor, bias, bn, negat
         _set_amax(rows, ax)
     if nrows * cout >= (1 << 22):                        # a big output may feed a tensor-bound GEMM: record its maxima for free
         ay = _amax_buffer(rows.device)
+    xp, xp_ready = _layer_planes(rows, x2, ax, weight)
     y = _LinearBnActFn.apply(x2, _c(weight), bias, bn.weight, bn.bias, rm, rv, training, momentum,
-                             float(bn.eps), float(negative_slope), float(dropout_p), ax, ay)
+                             float(bn.eps), float(negative_slope), float(dropout_p), ax, ay, xp, xp_ready)
     out = y.view(*rows.shape[:-1], cout)
     _set_amax(out, ay)
+    _set_planes(rows, xp)
     return out
 
 

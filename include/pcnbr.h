@@ -296,6 +296,25 @@ PCNBR_API int pcnbr_gemm2h_ex_f32(const float* A, long lda, int a_mn, const floa
                     int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
                     size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
                     const void* b_split, long b_split_ld, long b_split_plane, pcnbr_stream_t stream);
+/* _ex2: the three GEMMs of a layer share their operand splits.  a_planes_out (/ a2_planes_out for A2): with a pre-split B and a
+ * K-major A (forward: A = x; input gradient: A = gy) the kernel also WRITES the [hi | lo] fp16 planes of A it computes in
+ * shared memory anyway (2 planes of M rows, row pitch *_ld halfs -- a multiple of 8, >= the operand's K --, planes *_plane halfs
+ * apart; bit-identical to pcnbr_split_f16(A, M, K, lda, 0, amax_a, ...)).  a_mnsplit + b_mnsplit (a_mn = b_mn = 1, the weight
+ * gradient dW = gy^T x): BOTH operands are read as such planes (rows = K), MN-major straight into tcgen05 -- no in-kernel
+ * conversion; amax_a / amax_b must be the arrays the planes were written with; A / B may then be NULL (when given, shapes
+ * whose tile is narrower than 64 columns fall back to converting them).  All NULL: exactly pcnbr_gemm2h_ex_f32. */
+PCNBR_API int pcnbr_gemm2h_ex2_f32(const float* A, long lda, int a_mn, const float* A2, long lda2, int K1, const float* B, long ldb,
+                    int b_mn, int M, int N, int K, const float* bias, float* C, long ldc, int splits, void* ws,
+                    size_t ws_bytes, const float* amax_a, const float* amax_a2, const float* amax_b,
+                    const void* b_split, long b_split_ld, long b_split_plane,
+                    void* a_planes_out, long apo_ld, long apo_plane, void* a2_planes_out, long ap2o_ld, long ap2o_plane,
+                    const void* a_mnsplit, long ams_ld, long ams_plane, const void* b_mnsplit, long bms_ld, long bms_plane,
+                    pcnbr_stream_t stream);
+/* Diagnostic (tools/gemm_shapes.py --trace): buf = device array of 148 x 16 uint64, or NULL to switch off.  While set, every
+ * gemm2h CTA adds the clock cycles each of its warp roles spent waiting on its barriers (slots: 0 producer on a free ring
+ * slot, 1 converters on the TMA, 2 MMA on a free accumulator, 3 MMA on a converted stage, 4 epilogue on a full accumulator,
+ * 5 epilogue on a free staging slab, 6 CTA lifetime, 7 converter busy time, 8 CTA lifetime in ns of %globaltimer).  Synchronises the device; not under capture. */
+PCNBR_API int pcnbr_gemm2h_trace(unsigned long long* buf);
 /* Extended form.  A2 != NULL: A is the K-concatenation [A (M,K1) | A2 (M,K-K1)] of two row-major matrices (pitches lda,
  * lda2; K1 % 32 == 0, a_mn must be 0) -- a torch.cat along the channels in front of a convolution (dgcnn.py:147,
  * cat((x1..x4, x5)) -> conv6) that is never materialised.  ldc: row pitch of C (>= N, % 4 == 0), so a GEMM can write a

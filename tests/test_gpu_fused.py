@@ -123,11 +123,14 @@ def test_gemm3x_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K):
 @pytest.mark.parametrize("a_mn", [False, True])
 @pytest.mark.parametrize("b_mn", [False, True])
 @pytest.mark.parametrize("M,N,K,scale_a,scale_b", [(4096, 512, 1408, 1.0, 1.0), (4000, 500, 1400, 3e-7, 2e3), (2048, 1024, 384, 40.0, 1e-3),
-                                                   (512, 1408, 16384, 1e-4, 1.0), (640, 1000, 9000, 1.0, 1.0)])
+                                                   (512, 1408, 16384, 1e-4, 1.0), (640, 1000, 9000, 1.0, 1.0),
+                                                   (4096, 384, 2048, 1.0, 1.0), (1024, 384, 16384, 5e-3, 1.0), (2000, 372, 2100, 1.0, 30.0),
+                                                   (640, 576, 4096, 1.0, 1.0)])
 def test_gemm_fp16_split_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K, scale_a, scale_b):
     """csrc/gemm_h2.cu (two-term fp16 split on kind::f16, per-tensor power-of-two scales from pcnbr_absmax_f32): K-major and
     MN-major operands (transposed by the in-kernel converters), ragged sizes, split-K, operands far outside fp16's range,
-    wide dynamic range inside one operand -- all against float64 at the 3xTF32 kernel's bar."""
+    wide dynamic range inside one operand -- all against float64 at the 3xTF32 kernel's bar.  N = 384 / 372 / 576 take the
+    192-column tile (MN-major or pre-split B; a raw K-major B keeps 256), full and ragged, with and without split-K."""
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A = (torch.randn(M, K, generator=g) + 0.25) * scale_a
     Bm = (torch.randn(N, K, generator=g) - 0.1) * scale_b
@@ -158,6 +161,106 @@ def test_gemm_fp16_split_all_operand_layouts(pkg, dev, a_mn, b_mn, M, N, K, scal
     assert bs.shape[:2] == (2, N)
     out2 = pkg.ops._gemm3x(Am, a_mn, Bmm, b_mn, M, N, K, amax_b=amax_b, b_split=bs, force_h2=True)
     assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("R,Cin,Cout", [(8192, 384, 1024), (4100, 1024, 512), (16384, 512, 256), (3000, 200, 136), (40000, 64, 128)])
+def test_gemm_fp16_split_planes_link_the_three_gemms_of_a_layer(pkg, dev, R, Cin, Cout):
+    """pcnbr_gemm2h_ex2_f32: the forward GEMM (A = x) and the input-gradient GEMM (A = gy) also write the [hi | lo] fp16 planes
+    of the A tiles they convert -- bit-identical to pcnbr_split_f16 -- and the weight gradient reads BOTH operands from those
+    planes (MN-major, no in-kernel conversion): bit-identical to the weight gradient that converts gy and x itself.  Ragged
+    row counts (TMA clipping / zero fill), a 192-column tile, split-K."""
+    ops = pkg.ops
+    g = torch.Generator().manual_seed(R + Cin)
+    x = ((torch.randn(R, Cin, generator=g) + 0.3) * 7.0).to(dev)
+    w = (torch.randn(Cout, Cin, generator=g) / Cin ** 0.5).to(dev)
+    gy = (torch.randn(R, Cout, generator=g) * 1e-4).to(dev)
+    gy[::5] *= 1e-3
+    ax, aw, ag = ops._absmax(x), ops._absmax(w), ops._absmax(gy)
+    xp, gp = ops._new_planes(x, ax), ops._new_planes(gy, ag)
+    xp.fill_(float("nan")); gp.fill_(float("nan"))
+    y = ops._gemm3x(x, False, w, False, R, Cout, Cin, amax_a=ax, amax_b=aw, b_split=ops._wsplit(w, False, aw), a_planes_out=xp, force_h2=True)
+    dx = ops._gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw, b_split=ops._wsplit(w, True, aw), a_planes_out=gp, force_h2=True)
+    # the outputs do not depend on the extra stores
+    assert torch.equal(y, ops._gemm3x(x, False, w, False, R, Cout, Cin, amax_a=ax, amax_b=aw, b_split=ops._wsplit(w, False, aw), force_h2=True))
+    assert torch.equal(dx, ops._gemm3x(gy, False, w, True, R, Cin, Cout, amax_a=ag, amax_b=aw, b_split=ops._wsplit(w, True, aw), force_h2=True))
+    assert torch.equal(xp[:, :, :Cin], ops._presplit(x, False, ax)[:, :, :Cin])
+    assert torch.equal(gp[:, :, :Cout], ops._presplit(gy, False, ag)[:, :, :Cout])
+    dw_ref = ops._gemm3x(gy, True, x, True, Cout, Cin, R, amax_a=ag, amax_b=ax, force_h2=True)
+    pkg._lib.prof_enable(True)
+    pkg._lib.prof_collect()
+    dw = ops._gemm3x(gy, True, x, True, Cout, Cin, R, amax_a=ag, amax_b=ax, a_mns=gp, b_mns=xp, force_h2=True)
+    ran = pkg._lib.prof_collect()
+    pkg._lib.prof_enable(False)
+    assert any(k.startswith("gemm2h_kernel") for k in ran), sorted(ran)
+    _close(dw, gy.double().cpu().t() @ x.double().cpu(), 3e-5)
+    assert torch.equal(dw, dw_ref)
+
+
+def test_gemm_fp16_split_planes_of_a_concatenated_input(pkg, dev):
+    """A = [x1 | x2] (never materialised): the forward GEMM writes the planes of both halves -- or of the second one only,
+    when the first half's exist already -- scaled with the ONE power of two it uses for the concatenation; a GEMM that does
+    not take the fp16-split kernel leaves the buffers unmarked and the weight gradient then converts its operands itself."""
+    ops = pkg.ops
+    R, K1, K2, C = 4096, 384, 1024, 512
+    g = torch.Generator().manual_seed(11)
+    x1, x2 = torch.randn(R, K1, generator=g).to(dev), (torch.randn(R, K2, generator=g) * 3).to(dev)
+    w = (torch.randn(C, K1 + K2, generator=g) / 40).to(dev)
+    a1, a2, aw = ops._absmax(x1), ops._absmax(x2), ops._absmax(w)
+    for both in (True, False):
+        xp1, xp2 = ops._new_planes(x1, a1), ops._new_planes(x2, a2)
+        xp1.fill_(float("nan")); xp2.fill_(float("nan"))
+        ops._gemm3x(x1, False, w, False, R, C, K1 + K2, None, A2=x2, K1=K1, amax_a=a1, amax_a2=a2, amax_b=aw, b_split=ops._wsplit(w, False, aw),
+                    a_planes_out=xp1 if both else None, a2_planes_out=xp2, force_h2=True)
+        a12 = xp2._pcnbr_amax
+        assert torch.equal(a12, torch.maximum(a1, a2)) and ops._planes_ok(xp1) == both
+        assert torch.equal(xp2[:, :, :K2], ops._presplit(x2, False, a12)[:, :, :K2])
+        if both:
+            assert torch.equal(xp1[:, :, :K1], ops._presplit(x1, False, a12)[:, :, :K1])
+        else:
+            assert bool(torch.isnan(xp1.float()).all())
+    # below the fp16-split threshold the 3xTF32 kernel runs: the planes stay unmarked and unused
+    xs, ws = x1[:512].contiguous(), w[:, :K1].contiguous()
+    xp = ops._new_planes(xs, ops._absmax(xs))
+    ops._gemm3x(xs, False, ws, False, 512, C, K1, amax_a=ops._absmax(xs), amax_b=ops._absmax(ws), a_planes_out=xp)
+    assert not ops._planes_ok(xp)
+
+
+def test_fp16_split_layers_share_planes_and_match_the_converting_path(pkg, dev):
+    """conv5 / conv6 of DGCNNWithColor as the model issues them (linear_bn_act_rows on the skip concatenation, then
+    linear_bn_act_cat_rows on [skip | conv5 output]): with the operand planes (the skip tensor's split is written once, by
+    conv5's forward GEMM, and serves both layers' weight gradients) every gradient equals that of the path that converts
+    both operands inside the weight-gradient kernels (PCNBR_GEMM_NO_PLANES)."""
+    ops = pkg.ops
+    R, K1, C5, C6 = 32768, 384, 1024, 512          # every GEMM of both layers above the fp16-split threshold
+    g = torch.Generator().manual_seed(11)
+    skip0 = torch.randn(R, K1, generator=g).to(dev)
+    w5, w6 = (torch.randn(C5, K1, generator=g) / 20).to(dev), (torch.randn(C6, K1 + C5, generator=g) / 40).to(dev)
+    gout = torch.randn(R, C6, generator=g).to(dev)
+    def run(no_planes):
+        old = ops._GEMM_NO_PLANES
+        ops._GEMM_NO_PLANES = no_planes
+        try:
+            torch.manual_seed(3)
+            bn5, bn6 = torch.nn.BatchNorm1d(C5).to(dev), torch.nn.BatchNorm1d(C6).to(dev)
+            skip = skip0.clone().requires_grad_(True)
+            a5, a6 = w5.clone().requires_grad_(True), w6.clone().requires_grad_(True)
+            skip_r = skip * 1.0                       # a non-leaf like the model's concatenation
+            r5 = ops.linear_bn_act_rows(skip_r, a5, None, bn5, 0.2)
+            shared = getattr(skip_r, "_pcnbr_planes", None) is not None
+            r6 = ops.linear_bn_act_cat_rows(skip_r, r5, a6, None, bn6, 0.2)
+            r6.backward(gout)
+            return [skip.grad, a5.grad, a6.grad, bn5.weight.grad, bn6.weight.grad, r6.detach()], shared
+        finally:
+            ops._GEMM_NO_PLANES = old
+    got, shared = run(False)
+    ref, shared_ref = run(True)
+    assert shared and not shared_ref
+    for a, b in zip(got, ref):
+        # conv6 scales [skip | r5] with ONE power of two in its forward GEMM, so r5's planes carry that scale while the
+        # converting weight-gradient kernel scales r5 by its own maximum: the same fp16 split except where `lo` falls into
+        # fp16 subnormals -- differences at 2^-40 of the tensor maximum, a last-bit flip here and there
+        _close(a, b, 2e-6)
+    assert torch.equal(got[1], ref[1]) and torch.equal(got[5], ref[5])        # conv5 (own scale) and the forward: bit for bit
 
 
 def test_gemm_fp16_split_concatenated_input_and_degenerate_operands(pkg, dev):
