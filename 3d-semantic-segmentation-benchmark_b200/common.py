@@ -56,6 +56,11 @@ def reduce(x: torch.Tensor, type: str) -> torch.Tensor:
     raise ValueError(f"'{type}' pooling not supported; use 'max' or 'avg'.")
 
 
+def head_dropout_p(drop: nn.Dropout) -> float:
+    """Probability to fold into the preceding fused layer (training mode, 0 < p < 1), else 0: the caller applies the module."""
+    return float(drop.p) if (drop.training and 0.0 < drop.p < 1.0) else 0.0
+
+
 def interpolate(points: torch.Tensor, coords_1: torch.Tensor, coords_2: torch.Tensor, k: int = 3, lengths=None) -> torch.Tensor:
     """k-NN inverse-squared-distance interpolation (B,M,D) -> (B,N,D)   [common.py:94-122].  lengths: real rows of coords_1."""
     idx, d2 = ops.knn_points(coords_1, coords_2, k, query_lengths=lengths)
@@ -132,34 +137,40 @@ class UnitPointNet(nn.Module):
             self.batch.append(nn.BatchNorm1d(m))
             width = m
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, _dropout: float = 0.0) -> torch.Tensor:
         """x (B,Cin,N).  When x is the transposed view of point-major memory (B,N,Cin) -- what the feature
-        propagation / InvResMLP modules hand in -- the 1x1 convolutions run as cuBLAS SGEMMs over the (B*N, Cin)
-        rows; otherwise the plain cuDNN path is used."""
+        propagation / InvResMLP modules hand in -- the 1x1 convolutions run as tensor-core GEMMs over the (B*N, Cin)
+        rows; otherwise the plain cuDNN path is used.  _dropout (internal): probability of an nn.Dropout that FOLLOWS the
+        module in training mode (the segmentation heads, PointNetpp.py:42, PointNeXt.py:134): folded into the last layer's fused
+        BatchNorm + ReLU kernels (mask from a per-pass device seed, recomputed by the backward) instead of two more passes."""
         B, _, N = x.shape
         rows = x.permute(0, 2, 1)
         if not (x.is_cuda and rows.is_contiguous()):
             ops.note_fallback("UnitPointNet.forward: input is not a transposed point-major view (cuDNN convolutions)")
             for conv, bn in zip(self.conv, self.batch):
                 x = F.relu(bn(conv(x)))
-            return x
+            return F.dropout(x, _dropout, True) if _dropout > 0.0 else x
         h = rows
-        for conv, bn in zip(self.conv, self.batch):
-            h = ops.linear_bn_act_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias, bn, 0.0)
+        last = len(self.conv) - 1
+        for i, (conv, bn) in enumerate(zip(self.conv, self.batch)):
+            h = ops.linear_bn_act_rows(h, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias, bn, 0.0,
+                                       _dropout if i == last else 0.0)
         return h.permute(0, 2, 1)
 
 
-def _unit_forward_rows_cat(self, rows1: torch.Tensor, rows2: torch.Tensor) -> torch.Tensor:
+def _unit_forward_rows_cat(self, rows1: torch.Tensor, rows2: torch.Tensor, _dropout: float = 0.0) -> torch.Tensor:
     """UnitPointNet on the channel concatenation [rows1 | rows2] of two point-major (B,N,*) tensors -> (B,N,Cout): the
     skip connection of FeaturePropagation (torch.cat, common.py:234-237) is read by the first GEMM from the two tensors in
     place instead of being materialised."""
     h = None
+    last = len(self.conv) - 1
     for i, (conv, bn) in enumerate(zip(self.conv, self.batch)):
         w = conv.weight.view(conv.out_channels, conv.in_channels)
+        p = _dropout if i == last else 0.0                   # a following nn.Dropout, folded in (see UnitPointNet.forward)
         if i == 0:
-            h = ops.linear_bn_act_cat_rows(rows1, rows2, w, conv.bias, bn, 0.0)
+            h = ops.linear_bn_act_cat_rows(rows1, rows2, w, conv.bias, bn, 0.0, p)
         else:
-            h = ops.linear_bn_act_rows(h, w, conv.bias, bn, 0.0)
+            h = ops.linear_bn_act_rows(h, w, conv.bias, bn, 0.0, p)
     return h
 
 
@@ -243,13 +254,13 @@ class FeaturePropagation(nn.Module):
         super().__init__()
         self.point_net = UnitPointNet(in_channels, mlps)
 
-    def forward(self, coords_1, coords_2, features_1, features_2, _geom=None, lengths=None):
+    def forward(self, coords_1, coords_2, features_1, features_2, _geom=None, lengths=None, _dropout: float = 0.0):
         """_geom (internal): (NeighborIndex, d2) of the 3-NN table precomputed by ops.PyramidGeometry.  lengths: real rows
-        of coords_1 (see sample())."""
+        of coords_1 (see sample()).  _dropout (internal): see UnitPointNet.forward."""
         up = interpolate(features_2, coords_1, coords_2, lengths=lengths) if _geom is None else ops.three_interpolate(features_2, _geom[0], _geom[1])
         if features_1 is None:
-            return self.point_net(up.permute(0, 2, 1)).permute(0, 2, 1)
-        return self.point_net.forward_rows_cat(features_1, up)
+            return self.point_net(up.permute(0, 2, 1), _dropout=_dropout).permute(0, 2, 1)
+        return self.point_net.forward_rows_cat(features_1, up, _dropout)
 
 
 class InvResMLP(nn.Module):

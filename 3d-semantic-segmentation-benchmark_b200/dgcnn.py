@@ -76,7 +76,7 @@ class EdgeConv(nn.Module):
         O = conv.out_channels
         nbr = _nbr if _nbr is not None else ops.NeighborIndex(ops.knn_graph(x, self.k, lengths=lengths), N)
         W = conv.weight.view(O, 2 * F)
-        Wcat = torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)            # [A ; B - A]  (2O, F)
+        Wcat = _SplitWeightFn.apply(W)                                      # [A ; B - A]  (2O, F)
         rows = _point_major(x)
         if F % 4:
             # xyz layer.  u_ij = A (x_j - x_i) + B x_i is evaluated as P_j + Q_i with P = A x, Q = (B - A) x, which cancels
@@ -93,6 +93,22 @@ class EdgeConv(nn.Module):
             PQ = ops.linear_rows(rows, Wcat, None)                          # (B,N,F) x (F,2O): tensor-core GEMM / split-K wgrad
         out = ops.edgeconv_fused(PQ, nbr, bn, act.negative_slope)           # (B,N,O), point-major
         return out.permute(0, 2, 1)                                         # (B,O,N) view, no copy
+
+
+class _SplitWeightFn(torch.autograd.Function):
+    """W = [A | B] (O, 2F) -> [A ; B - A] (2O, F), the weights of the algebraic split, as ONE autograd node: its backward is
+    gW = [gP - gQ | gQ] in two small kernels (slicing + subtraction + concatenation through autograd were ten launches of
+    1-2 us per EdgeConv layer and pass)."""
+
+    @staticmethod
+    def forward(ctx, W):
+        F = W.shape[1] // 2
+        return torch.cat((W[:, :F], W[:, F:] - W[:, :F]), dim=0)
+
+    @staticmethod
+    def backward(ctx, g):
+        O = g.shape[0] // 2
+        return torch.cat((g[:O] - g[O:], g[O:]), dim=1)
 
 
 def _pad4(t: torch.Tensor) -> torch.Tensor:

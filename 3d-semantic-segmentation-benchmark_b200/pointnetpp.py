@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .common import FeaturePropagation, SetAbstraction, SetAbstractionMSG
+from .common import FeaturePropagation, SetAbstraction, SetAbstractionMSG, head_dropout_p
 
 
 class PointNetpp(nn.Module):
@@ -59,8 +59,9 @@ class PointNetpp(nn.Module):
         features_3 = self.fp4(coords_3, coords_4, features_3, features_4, _geom=geo.three_nn(3))
         features_2 = self.fp3(coords_2, coords_3, features_2, features_3, _geom=geo.three_nn(2))
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2, _geom=geo.three_nn(1))
-        features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0))
-        x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
+        p = head_dropout_p(self.drop)                   # nn.Dropout behind fp1 (PointNetpp.py:42): folded into its last fused layer
+        features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0), _dropout=p)
+        x = features_0 if p > 0.0 else self.drop(features_0)     # (B,N,128): the head 1x1 conv is a GEMM over the rows
         return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)
 
 
@@ -100,6 +101,7 @@ class PointNetppMSG(nn.Module):
         features_3 = self.fp4(coords_3, coords_4, features_3, features_4, _geom=geo.three_nn(3))
         features_2 = self.fp3(coords_2, coords_3, features_2, features_3, _geom=geo.three_nn(2))
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2, _geom=geo.three_nn(1))
-        features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0))
-        x = self.drop(features_0)
+        p = head_dropout_p(self.drop)
+        features_0 = self.fp1(coords_0, coords_1, None, features_1, _geom=geo.three_nn(0), _dropout=p)
+        x = features_0 if p > 0.0 else self.drop(features_0)
         return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .common import FeaturePropagation, InvResMLP, SetAbstraction, UnitPointNet
+from .common import FeaturePropagation, InvResMLP, SetAbstraction, UnitPointNet, head_dropout_p
 
 
 class PointNeXt(nn.Module):
@@ -48,6 +48,7 @@ class PointNeXt(nn.Module):
         features_3 = self.fp4(coords_3, coords_4, features_3, features_4)
         features_2 = self.fp3(coords_2, coords_3, features_2, features_3)
         features_1 = self.fp2(coords_1, coords_2, features_1, features_2)
-        features_0 = self.fp1(coords_0, coords_1, features_0, features_1, lengths=lengths)
-        x = self.drop(features_0)                       # (B,N,128): the head 1x1 conv is a GEMM over the rows
+        p = head_dropout_p(self.drop)                   # nn.Dropout behind fp1 (PointNeXt.py:134): folded into its last fused layer
+        features_0 = self.fp1(coords_0, coords_1, features_0, features_1, lengths=lengths, _dropout=p)
+        x = features_0 if p > 0.0 else self.drop(features_0)     # (B,N,128): the head 1x1 conv is a GEMM over the rows
         return ops.linear_rows(x, self.conv.weight.squeeze(-1), self.conv.bias)
