@@ -1078,11 +1078,17 @@ def _planes_ok(planes) -> bool:
     return planes is not None and getattr(planes, "_pcnbr_amax", None) is not None
 
 
+# Writing the planes costs the forward / input-gradient GEMM 5-15 % (bulk stores beside the operand loads, ring slots handed back
+# late); the weight gradient gains what its converters cost, which grows with Cout x Cin.  Measured on 65536 rows
+# (tools/gemm_shapes.py): 384 -> 1024 and 1408 -> 512 gain 50 / 90 us per layer, 512 -> 256 loses 13.
+_PLANES_MIN_WEIGHT = 1 << 18
+
+
 def _layer_planes(rows: torch.Tensor, x2d: torch.Tensor, amax, weight: torch.Tensor):
     """(planes, ready) for a layer input: the buffer its forward GEMM writes the fp16 split of x into for the weight
     gradient -- or, ready = True, the one an earlier layer's GEMM filled for the same tensor.  (None, False) when no weight
     gradient will be asked for or the layer is not on the fp16-split kernel."""
-    if amax is None or _GEMM_NO_PLANES or not (torch.is_grad_enabled() and weight.requires_grad):
+    if amax is None or _GEMM_NO_PLANES or weight.numel() < _PLANES_MIN_WEIGHT or not (torch.is_grad_enabled() and weight.requires_grad):
         return None, False
     hint = _planes_hint(rows, amax)
     return (hint, True) if hint is not None else (_new_planes(x2d, amax), False)
@@ -1183,7 +1189,8 @@ class _LinearRowsFn(torch.autograd.Function):
         ctx.has_bias = b is not None
         R, Cin = x.shape
         ctx.amax = _layer_amax(x, w, R, w.shape[0], Cin)
-        ctx.xp = _new_planes(x, ctx.amax[0]) if (ctx.needs_input_grad[1] and ctx.amax[1] is not None) else None
+        ctx.xp = (_new_planes(x, ctx.amax[0])
+                  if (ctx.needs_input_grad[1] and ctx.amax[1] is not None and w.numel() >= _PLANES_MIN_WEIGHT) else None)
         return _gemm3x(x, False, w, False, R, w.shape[0], Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]),
                        a_planes_out=ctx.xp)
 

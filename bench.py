@@ -103,38 +103,86 @@ def config_for(model, B, N, world):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock / throttle reasons WHILE the timed region runs.  In-process NVML (the library nvidia-smi reads: nvml
+    DeviceGetClockInfo / CurrentClocksEventReasons, one sample every ~4 ms with its time stamp), so that a timed region of
+    50 ms is covered by a dozen samples; `nvidia-smi -lms` as a child process (the fallback when pynvml cannot be loaded)
+    needs ~100 ms to start and mostly sampled the idle GPU behind the region.  mark(t0, t1): the wall-clock windows of the
+    timed regions -- only samples inside them count as "under load"."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
+        self.nvml, self.handle, self._stop, self.thread = None, None, threading.Event(), None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.index)      # CUDA_VISIBLE_DEVICES may renumber: go by PCI address
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
 
     def start(self):
         try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
         return self
 
+    def _poll(self):
+        n = self.nvml
+        bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append((time.time(), sm, mx, [nm for nm, b in zip(self.NAMES, bits) if rs & b]))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 6 and c[0].isdigit() and c[1].isdigit():
+                self.rows.append((time.time(), int(c[0]), int(c[1]), [nm for nm, v in zip(self.NAMES, c[2:6]) if v.lower().startswith("active")]))
+
+    def mark(self, t0: float, t1: float):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is None and self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.05)
+            self.proc.terminate()
+        rows = list(self.rows)
+        inside = [r for r in rows if any(t0 <= r[0] <= t1 for t0, t1 in self.windows)] if self.windows else rows
+        use = inside if len(inside) >= 2 else rows                 # (a region shorter than two sampling periods: every sample of the run)
+        sm = sorted(r[1] for r in use)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in use), default=None),
+                "reasons": sorted({nm for r in use for nm in r[3]}), "samples": len(use),
+                "samples_in_timed_region": len(inside), "source": "nvml" if self.nvml is not None else "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------- data / models
@@ -456,9 +504,12 @@ class Harness:
             eager_step(*devb[i % n_batches])
         step = eager_step if args.no_graph else pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, devb[0], warmup=2, geometry_fn=geo_fn)
 
+        clocks = ClockSampler(self.local).start() if rank == 0 else None     # sampling runs from before the warm-up on
+
         def timed(region_steps, from_host):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.barrier()
+            t_wall0 = time.time()
             ev0.record()
             last = None
             for i in range(region_steps):
@@ -471,6 +522,8 @@ class Harness:
                     last = step(*devb[i % n_batches])
             ev1.record()
             self.barrier()
+            if clocks:
+                clocks.mark(t_wall0, time.time())            # the samples inside this window are the ones "under load"
             ms = ev0.elapsed_time(ev1)
             if world > 1:
                 t = torch.tensor([ms], device=dev)
@@ -480,7 +533,6 @@ class Harness:
 
         for i in range(max(warmup, 3)):
             step(*devb[i % n_batches])
-        clocks = ClockSampler(self.local).start() if rank == 0 else None
         ms_total, _ = timed(steps, from_host=False)
         ms_e2e, last_loss = timed(steps, from_host=True)
         clk = clocks.stop() if clocks else None
