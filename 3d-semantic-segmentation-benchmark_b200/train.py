@@ -239,9 +239,44 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 self._step_body()
         torch.cuda.current_stream().wait_stream(side)
+        dev0 = self.static[0].device
+        torch.matmul(torch.zeros(1, 1, device=dev0), torch.zeros(1, 1, device=dev0))    # warmup = 0: the cuBLAS handle must exist before the capture
         torch.cuda.synchronize()
         with torch.cuda.graph(self.graph):
             self.loss = self._step_body()
+        self._staged = None                                  # prefetch(): (host tensors, device staging, ready event)
+        self._staging = None
+        self._copy_stream = None
+        self._consumed = None
+
+    def prefetch(self, *host_batch):
+        """Start the host -> device copy of the NEXT batch (pinned host tensors) on a copy stream, so that it overlaps the
+        step that is running; the next __call__ with these very tensors takes the staged copy (one device-side copy into
+        the static inputs) instead of copying from the host on the critical path -- what a prefetching DataLoader does for
+        an eager loop.  Any other call falls back to the plain copy."""
+        dev = self.static[0].device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = [torch.empty_like(t) for t in self.static]
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)                    # the staging buffers have been read by the previous hand-over
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._staging, host_batch):
+                dst.copy_(src, non_blocking=True)
+            ready = cs.record_event()
+        self._staged = (tuple(host_batch), ready)
+
+    def _take(self, dst_list, batch):
+        """Copy `batch` into dst_list: from the staged device copy when it is the prefetched batch, else from where it lies."""
+        if self._staged is not None and len(self._staged[0]) == len(batch) and all(a is b for a, b in zip(self._staged[0], batch)):
+            torch.cuda.current_stream().wait_event(self._staged[1])
+            torch._foreach_copy_(dst_list, self._staging)
+            self._consumed = torch.cuda.current_stream().record_event()
+            self._staged = None
+            return
+        for dst, src in zip(dst_list, batch):
+            dst.copy_(src, non_blocking=True)
 
     def _step_body(self):
         from . import ops
@@ -270,11 +305,9 @@ class GraphedTrainStep:
         if self.geometry_fn is not None:
             for cur, nxt in zip(self.static, self.static_next):
                 cur.copy_(nxt, non_blocking=True)            # the batch handed in by the previous call becomes current
-            for dst, src in zip(self.static_next, batch):
-                dst.copy_(src, non_blocking=True)
+            self._take(self.static_next, batch)
         else:
-            for dst, src in zip(self.static, batch):
-                dst.copy_(src, non_blocking=True)
+            self._take(self.static, batch)
         self.graph.replay()
         return self.loss
 

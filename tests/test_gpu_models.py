@@ -351,3 +351,42 @@ def test_pipelined_graphed_step_matches_plain_graphed_step(pkg, dev, model):
     piped = pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, batches[0], warmup=0, geometry_fn=geo_fn)
     got = [float(piped(*b)) for b in batches[1:]] + [float(piped.flush())]
     assert got == want, (got, want)
+
+
+def test_graphed_step_prefetch_of_the_next_host_batch_changes_nothing(pkg, dev):
+    """train.GraphedTrainStep.prefetch(): the next pinned host batch is copied on a copy stream under the running step and
+    handed over device-side; the loss sequence equals that of plain host copies, also when a call passes a batch that was
+    NOT the prefetched one (fallback) and when prefetches follow each other back to back."""
+    N, B = 1024, 2
+    host = [tuple(t.pin_memory() for t in pkg.synthetic.s3dis_blocks(B, N, seed=s)) for s in range(5)]
+    inp = lambda p: p[:, :, :6].transpose(1, 2)
+
+    def build():
+        torch.manual_seed(3)
+        net = pkg.DGCNNWithColor(13, k=20, emb_dims=64, dropout=0.0).to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True, fused=True)
+        return net, opt, pkg.train.FlatGradBucket(net, steal_grads=True)
+
+    def loss_of(m, pts, lab, lens):
+        return pkg.train.masked_onehot_cross_entropy(m(inp(pts))[0], lab, lens)
+
+    example = tuple(t.to(dev) for t in host[0])
+    net, opt, bucket = build()
+    plain = pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, example, warmup=0)
+    want = [float(plain(*b)) for b in host]
+    net, opt, bucket = build()
+    step = pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, example, warmup=0)
+    got = []
+    for i, b in enumerate(host):
+        loss = step(*b)
+        if i + 1 < len(host):
+            step.prefetch(*host[i + 1])
+            if i == 2:                                   # a second prefetch before the hand-over replaces the first
+                step.prefetch(*host[i + 1])
+        got.append(float(loss))
+    assert got == want, (got, want)
+    # a call with a different batch than the prefetched one copies from the host as before
+    net, opt, bucket = build()
+    step = pkg.train.GraphedTrainStep(net, opt, bucket, loss_of, example, warmup=0)
+    step.prefetch(*host[3])
+    assert float(step(*host[0])) == want[0]
