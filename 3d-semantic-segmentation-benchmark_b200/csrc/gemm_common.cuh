@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace pcnbr {
 

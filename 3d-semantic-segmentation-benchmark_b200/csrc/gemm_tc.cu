@@ -25,6 +25,7 @@
 // Weight gradients (M, N small, K = number of points) are split along K over the CTAs; the partial tiles are summed
 // in a fixed order by a second kernel (deterministic, no atomics).
 #include "gemm_common.cuh"
+#include <cstdlib>
 
 namespace pcnbr {
 
@@ -354,7 +355,11 @@ extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
     long best_cost = -1;
     int best = 1;
     const int smax = (int)(2L * sms / tiles) > 1 ? (int)(2L * sms / tiles) : 1;
-    for (int s = 1; s <= smax && s <= kb / 16; ++s) {
+    // a split owns at least 4 K blocks (16 left 84 SMs idle on the 26 us weight gradients of the deep PointNet++ / PointNeXt
+    // levels: PointNet++ 5.71 -> 5.60 ms per step, PointNeXt 7.60 -> 7.15);
+    // PCNBR_SPLIT_MIN overrides (A/B measurements)
+    static const int min_per = getenv("PCNBR_SPLIT_MIN") ? atoi(getenv("PCNBR_SPLIT_MIN")) > 0 ? atoi(getenv("PCNBR_SPLIT_MIN")) : 4 : 4;
+    for (int s = 1; s <= smax && s <= kb / min_per; ++s) {
         const long per = (kb + s - 1) / s;
         const long eff = (kb + per - 1) / per;                            // every split owns at least one K block
         const long waves = (tiles * eff + sms - 1) / sms;
