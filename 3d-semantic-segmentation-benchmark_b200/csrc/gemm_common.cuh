@@ -120,7 +120,8 @@ static int gm_make_map_c(CUtensorMap* map, float* base, long M, long N, long ldc
 }
 
 
-// Tile width: the widest BN <= N (rounded up) that still gives every SM at least two work units -- narrower tiles mean
+// Tile width: the widest BN <= N (rounded up) that still gives every SM a work unit (measured against two units per SM:
+// PointNet++ 5.63 -> 5.59 ms per step, the others unchanged; always-widest: 5.67) -- narrower tiles mean
 // more units and a deeper smem ring (more bytes in flight per SM), which is what the many small, latency-bound layer
 // GEMMs need; the big tensor-bound ones (>= 296 units at BN = 256) keep the widest tile and its operand reuse.
 // (Long-K GEMMs -- the weight gradients -- get their units from split-K instead and keep the widest tile.)
@@ -129,10 +130,22 @@ static int gm_tile_n(int M, int N, int K) {
     if (K >= 64 * GM_BK) return widest;
     const long mt = (M + GM_BM - 1) / GM_BM;
     int bn = widest;
-    while (bn > 64 && mt * ((N + bn - 1) / bn) < 2 * 148) bn >>= 1;
+    while (bn > 64 && mt * ((N + bn - 1) / bn) < 148) bn >>= 1;
     return bn;
 }
 
 int gm_launch_reduce(const float* ws, int M, int N, long ldc, int splits, float* C, cudaStream_t s);   // gemm_tc.cu
+int gm3_set_trace(unsigned long long* buf);                                                             // gemm_tc.cu
+
+// wait-time trace of the GEMM kernels' warp roles (pcnbr_gemm2h_trace): cycles spent inside [begin, end) pairs, per CTA and slot
+struct H2Wait {
+    unsigned long long* dst;
+    long long acc;
+    __device__ __forceinline__ H2Wait(unsigned long long* base, int slot) : dst(base ? base + (size_t)blockIdx.x * 16 + slot : nullptr), acc(0) {}
+    __device__ __forceinline__ long long begin() const { return dst ? clock64() : 0; }
+    __device__ __forceinline__ void end(long long t0) { if (dst) acc += clock64() - t0; }
+    __device__ __forceinline__ void flush() { if (dst) *dst = (unsigned long long)acc; }
+};
+
 
 }  // namespace pcnbr

@@ -163,14 +163,6 @@ __device__ __forceinline__ void h2_tile_store(uint8_t* tile, uint32_t plane, int
 //   4 epilogue: accumulator full   5 epilogue: staging slab free (bulk store read)   6 CTA lifetime   7 converter busy time
 //   8 CTA lifetime in ns of %globaltimer (6 / 8 = the SM clock the kernel ran at)
 __device__ unsigned long long* g_h2_trace = nullptr;
-struct H2Wait {
-    unsigned long long* dst;
-    long long acc;
-    __device__ __forceinline__ H2Wait(unsigned long long* base, int slot) : dst(base ? base + (size_t)blockIdx.x * 16 + slot : nullptr), acc(0) {}
-    __device__ __forceinline__ long long begin() const { return dst ? clock64() : 0; }
-    __device__ __forceinline__ void end(long long t0) { if (dst) acc += clock64() - t0; }
-    __device__ __forceinline__ void flush() { if (dst) *dst = (unsigned long long)acc; }
-};
 
 // B_PRE: the B operand arrives already split ([hi | lo] fp16 planes written once by split_f16_kernel -- the weights of a
 // forward / input-gradient GEMM, which every CTA would otherwise convert again): TMA drops the two planes straight into
@@ -708,7 +700,9 @@ extern "C" int pcnbr_amax_slots(void) { return H2_AMAX_SLOTS; }
 extern "C" int pcnbr_gemm2h_trace(unsigned long long* buf) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaMemcpyToSymbol(g_h2_trace, &buf, sizeof(buf));
+    e = cudaMemcpyToSymbol(g_h2_trace, &buf, sizeof(buf));
+    if (e != cudaSuccess) return (int)e;
+    return gm3_set_trace(buf);                                                 // gemm3x_kernel fills the same slots
 }
 
 extern "C" int pcnbr_absmax_f32(const float* x, long rows, long cols, long ld, float* partial, pcnbr_stream_t stream) {

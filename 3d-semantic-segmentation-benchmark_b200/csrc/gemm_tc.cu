@@ -57,6 +57,8 @@ __device__ __forceinline__ float gm_residual(float v) {
     return __uint_as_float(lb);
 }
 
+__device__ unsigned long long* g_g3_trace = nullptr;     // see pcnbr_gemm2h_trace / H2Wait: the same slots as gemm2h_kernel
+
 // Work unit = (split, m tile, n tile), n fastest: the CTAs that run side by side share the same A slab, so the
 // streamed operand (the activations) is read from HBM once and hits L2 for the other n tiles.  The C tile goes to
 // out + split * M * ldc (partials); splits == 1 writes the result (plus bias) directly.
@@ -84,6 +86,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     const int KB = (K + GM_BK - 1) / GM_BK;                           // K blocks in total
     const int kb_per = (KB + splits - 1) / splits;
     const int units = MT * NT * splits;
+    unsigned long long* const trace = g_g3_trace;
+    const long long t_cta = trace ? clock64() : 0;
+    unsigned long long ns_cta = 0;
+    if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns_cta));
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -106,12 +112,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (lane == 0) {
+            H2Wait w_ring(trace, 0);
             uint32_t stage = 0, phase = 0;
             for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
                 const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
                 const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    const long long t0 = w_ring.begin();
                     gm_mbar_wait(&empty[stage], phase ^ 1);
+                    w_ring.end(t0);
                     gm_mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
                     const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
                     if (A_MN) {
@@ -137,6 +146,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            w_ring.flush();
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -144,18 +154,23 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
         uint32_t stage = 0, phase = 0, tile = 0;
+        H2Wait w_acc(lane == 0 ? trace : nullptr, 2), w_land(lane == 0 ? trace : nullptr, 1), w_conv(lane == 0 ? trace : nullptr, 3);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
             const int sp = unit / (MT * NT);
             const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
             const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
+            long long t0 = w_acc.begin();
             gm_mbar_wait(&tmem_empty[buf], tphase ^ 1);
+            w_acc.end(t0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + buf * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
                 const uint32_t st = gm_smem_u32(smem + stage * STAGE_BYTES);
                 const uint64_t ah = gm_desc<A_MN>(st), al = gm_desc<A_MN>(st + A_BYTES);
                 const uint64_t bh = gm_desc<B_MN>(st + 2 * A_BYTES), bl = gm_desc<B_MN>(st + 2 * A_BYTES + B_BYTES);
+                t0 = w_land.begin();                                  // (slot 1 here: the MMA warp waiting for the TMA)
                 gm_mbar_wait(&full[stage], phase);                    // raw tiles landed: hi . hi' can start
+                w_land.end(t0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
 #pragma unroll
@@ -163,7 +178,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                         gm_umma_tf32<BN, A_MN, B_MN>(d, ah + gm_kstep<A_MN>(s), bh + gm_kstep<B_MN>(s), kb > kb0 || s > 0);
                 }
                 __syncwarp();
+                t0 = w_conv.begin();
                 gm_mbar_wait(&conv[stage], phase);                    // residual tiles written and published
+                w_conv.end(t0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (leader) {
 #pragma unroll
@@ -180,6 +197,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             if (leader) gm_umma_commit(&tmem_full[buf]);
             __syncwarp();
         }
+        w_acc.flush(); w_land.flush(); w_conv.flush();
     } else if (warp < 6) {
         // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
@@ -187,12 +205,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         const int rloc = quarter * 32 + lane;                         // row of the tile owned by this thread
         const bool issuer = (warp == 2 && lane == 0);                 // issues and tracks the TMA stores
         uint32_t tile = 0, slab = 0;
+        H2Wait w_full(issuer ? trace : nullptr, 4), w_slab(issuer ? trace : nullptr, 5);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++tile) {
             const int nt = unit % NT, mt = (unit / NT) % MT, sp = unit / (MT * NT);
             const uint32_t buf = tile % NBUF, tphase = (tile / NBUF) & 1;
             const int ncols = min(BN, N - nt * BN);
             const int nq = (ncols + 31) / 32;
+            const long long t0 = w_full.begin();
             gm_mbar_wait(&tmem_full[buf], tphase);
+            w_full.end(t0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int q = 0; q < nq; ++q, ++slab) {
                 uint32_t r[32];
@@ -210,7 +231,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                         if (c0 + i < N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(bias + c0 + i));
                 }
                 uint8_t* sb = cstage + (slab & 1) * GM_SLAB;
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read sb is done
+                if (issuer) {
+                    const long long t1 = w_slab.begin();
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");           // the store that last read sb is done
+                    w_slab.end(t1);
+                }
                 gm_epi_barrier();
                 uint8_t* rowp = sb + rloc * 128;
 #pragma unroll
@@ -225,17 +250,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
             }
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                 // all stores landed before exit
+        w_full.flush(); w_slab.flush();
     } else {
         // ===================================================== converters: residual tiles A_lo, B_lo from the raw tiles
         const int t = threadIdx.x - 192;                              // 0 .. 32*GM_CONV_WARPS-1
         constexpr int NT_CONV = 32 * GM_CONV_WARPS;
         uint32_t stage = 0, phase = 0;
+        H2Wait w_busy(t == 0 ? trace : nullptr, 7);
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int sp = unit / (MT * NT);
             const int kb0 = sp * kb_per, kb1 = min(KB, kb0 + kb_per);
             for (int kb = kb0; kb < kb1; ++kb) {
                 uint8_t* st = smem + stage * STAGE_BYTES;
                 gm_mbar_wait(&full[stage], phase);
+                const long long t0 = w_busy.begin();
 #pragma unroll 4
                 for (int i = t; i < (int)(A_BYTES / 16); i += NT_CONV) {
                     const float4 v = *reinterpret_cast<const float4*>(st + 16 * i);
@@ -251,12 +279,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) gm_mbar_arrive(&conv[stage]);
+                w_busy.end(t0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        w_busy.flush();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (trace && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+        trace[(size_t)blockIdx.x * 16 + 6] = (unsigned long long)(clock64() - t_cta);
+        trace[(size_t)blockIdx.x * 16 + 8] = ns1 - ns_cta;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -342,6 +378,10 @@ int gm_launch_reduce(const float* ws, int M, int N, long ldc, int splits, float*
 
 using namespace pcnbr;
 
+namespace pcnbr {
+int gm3_set_trace(unsigned long long* buf) { return (int)cudaMemcpyToSymbol(g_g3_trace, &buf, sizeof(buf)); }
+}  // namespace pcnbr
+
 extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
     // Split K when the output has too few tiles to fill the chip (weight gradients: K = number of points).
     // Cost model: waves of work units over the SMs x K blocks per unit; the smallest split count that minimises it.
@@ -363,7 +403,7 @@ extern "C" int pcnbr_gemm3x_splits(int M, int N, int K) {
         const long per = (kb + s - 1) / s;
         const long eff = (kb + per - 1) / per;                            // every split owns at least one K block
         const long waves = (tiles * eff + sms - 1) / sms;
-        const long cost = waves * (per + 4);                              // + tile prologue / epilogue
+        const long cost = waves * (per + 4);                              // + tile prologue / epilogue (2 .. 12: no measurable difference)
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = (int)eff; }
     }
     return best;

@@ -313,7 +313,8 @@ PCNBR_API int pcnbr_gemm2h_ex2_f32(const float* A, long lda, int a_mn, const flo
 /* Diagnostic (tools/gemm_shapes.py --trace): buf = device array of 148 x 16 uint64, or NULL to switch off.  While set, every
  * gemm2h CTA adds the clock cycles each of its warp roles spent waiting on its barriers (slots: 0 producer on a free ring
  * slot, 1 converters on the TMA, 2 MMA on a free accumulator, 3 MMA on a converted stage, 4 epilogue on a full accumulator,
- * 5 epilogue on a free staging slab, 6 CTA lifetime, 7 converter busy time, 8 CTA lifetime in ns of %globaltimer).  Synchronises the device; not under capture. */
+ * 5 epilogue on a free staging slab, 6 CTA lifetime, 7 converter busy time, 8 CTA lifetime in ns of %globaltimer);
+ * gemm3x_kernel fills the same slots (slot 1 there: the MMA warp waiting for the TMA).  Synchronises the device; not under capture. */
 PCNBR_API int pcnbr_gemm2h_trace(unsigned long long* buf);
 /* Extended form.  A2 != NULL: A is the K-concatenation [A (M,K1) | A2 (M,K-K1)] of two row-major matrices (pitches lda,
  * lda2; K1 % 32 == 0, a_mn must be 0) -- a torch.cat along the channels in front of a convolution (dgcnn.py:147,

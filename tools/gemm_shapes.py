@@ -16,7 +16,8 @@ def rnd(*shape): return torch.randn(*shape, generator=g).to(dev)
 def timed(fn):
     ts = []
     for _ in range(reps + 1):
-        flush.zero_()
+        for _ in range(6):                  # L2 flush, and ~0.3 ms of GPU work in front of e0: the host-side part of the call
+            flush.zero_()                   # (tensor-map encoding, ctypes) runs while the GPU is still busy, not inside [e0, e1]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
