@@ -518,7 +518,7 @@ class Harness:
                     if args.no_graph:
                         hp, hl, hn = hp.to(dev, non_blocking=True), hl.to(dev, non_blocking=True), hn.to(dev, non_blocking=True)
                     loss = step(hp, hl, hn)                  # (graph: into the static inputs -- the staged copy when prefetched)
-                    if not args.no_graph:                    # next batch's H2D copy on the copy stream, under this step
+                    if not args.no_graph and not os.environ.get("PCNBR_BENCH_NO_PREFETCH"):   # next batch's H2D copy on the copy stream, under this step
                         step.prefetch(*host[(i + 1) % n_batches])
                     last = loss.item()                       # D2H loss read
                 else:
