@@ -35,6 +35,29 @@ def test_workspace_size_helpers(pkg):
     assert pkg._lib.size("pcnbr_knn_expand_ws_bytes", 2, 64, 100, 20) == 800
 
 
+def test_split_k_plan_of_the_gemms(pkg):
+    """pcnbr_gemm3x_splits (host logic, no GPU needed): no empty split for any shape -- the kernels reject a plan with one --,
+    1 where the output tiles fill the chip or K is short, a split owns at least 4 K blocks, the big weight gradients are
+    bounded by two units per SM, the 26 us weight gradients of the deep PointNet++ levels get every K block they can use;
+    the fp16-split dispatch rule takes the tensor-bound layers of DGCNN's head and none of PointNet++'s."""
+    import random
+    rng = random.Random(0)
+    f = lambda M, N, K: pkg._lib.size("pcnbr_gemm3x_splits", M, N, K)
+    for _ in range(2000):
+        M, N, K = rng.randint(1, 2048), rng.randint(1, 2048), rng.randint(1, 1 << 20)
+        s = f(M, N, K)
+        kb = (K + 31) // 32
+        per = (kb + s - 1) // s
+        assert s >= 1 and (kb + per - 1) // per == s, (M, N, K, s)
+        assert s == 1 or per >= 4, (M, N, K, s)
+    assert f(65536, 1024, 384) == 1 and f(1 << 20, 32, 32) == 1 and f(256, 256, 1024) == 1
+    assert f(256, 512, 2048) == 16 and f(128, 256, 8192) == 64
+    assert f(1024, 384, 65536) == 9 and f(128, 128, 131072) == 147
+    h2 = lambda M, N, K: pkg._lib.size("pcnbr_gemm2h_preferred", M, N, K)
+    assert h2(65536, 1024, 384) and h2(65536, 512, 1408) and h2(65536, 256, 512) and h2(1024, 384, 65536)
+    assert not h2(131072, 128, 128) and not h2(1 << 20, 64, 32) and not h2(16384, 512, 256)
+
+
 def test_no_cpu_fallback(pkg):
     x = torch.rand(1, 64, 3)
     with pytest.raises(RuntimeError, match="CUDA"):
