@@ -104,8 +104,8 @@ def config_for(model, B, N, world):
 
 class ClockSampler:
     """SM clock / throttle reasons WHILE the timed region runs.  In-process NVML (the library nvidia-smi reads: nvml
-    DeviceGetClockInfo / CurrentClocksEventReasons, one sample every ~4 ms with its time stamp), so that a timed region of
-    50 ms is covered by a dozen samples; `nvidia-smi -lms` as a child process (the fallback when pynvml cannot be loaded)
+    DeviceGetClockInfo / CurrentClocksEventReasons, one sample every 20 ms with its time stamp), so that each timed region of
+    50 ms is covered by 2-3 samples; `nvidia-smi -lms` as a child process (the fallback when pynvml cannot be loaded)
     needs ~100 ms to start and mostly sampled the idle GPU behind the region.  mark(t0, t1): the wall-clock windows of the
     timed regions -- only samples inside them count as "under load"."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -148,15 +148,21 @@ class ClockSampler:
         n = self.nvml
         bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
                 n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+        try:
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
         while not self._stop.is_set():
             try:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
                 rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 self.rows.append((time.time(), sm, mx, [nm for nm, b in zip(self.NAMES, bits) if rs & b]))
             except Exception:
                 pass
-            time.sleep(0.004)
+            # every 20 ms: 2-3 samples per 50 ms timed region.  (Every 4 ms -- 75 NVML calls under a 100 ms measurement -- two of
+            # fourteen end-to-end regions showed a 3-5 ms host stall: NVML queries share driver locks with the CUDA calls of
+            # the thread that launches and synchronises every step.)
+            time.sleep(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -180,7 +186,7 @@ class ClockSampler:
         inside = [r for r in rows if any(t0 <= r[0] <= t1 for t0, t1 in self.windows)] if self.windows else rows
         use = inside if len(inside) >= 2 else rows                 # (a region shorter than two sampling periods: every sample of the run)
         sm = sorted(r[1] for r in use)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in use), default=None),
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in use if r[2] is not None), default=None),
                 "reasons": sorted({nm for r in use for nm in r[3]}), "samples": len(use),
                 "samples_in_timed_region": len(inside), "source": "nvml" if self.nvml is not None else "nvidia-smi -lms 20"}
 
@@ -506,7 +512,7 @@ class Harness:
 
         clocks = ClockSampler(self.local).start() if rank == 0 else None     # sampling runs from before the warm-up on
 
-        def timed(region_steps, from_host):
+        def timed(region_steps, from_host, mark=True):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.barrier()
             t_wall0 = time.time()
@@ -525,7 +531,7 @@ class Harness:
                     last = step(*devb[i % n_batches])
             ev1.record()
             self.barrier()
-            if clocks:
+            if clocks and mark:
                 clocks.mark(t_wall0, time.time())            # the samples inside this window are the ones "under load"
             ms = ev0.elapsed_time(ev1)
             if world > 1:
@@ -537,6 +543,10 @@ class Harness:
         for i in range(max(warmup, 3)):
             step(*devb[i % n_batches])
         ms_total, _ = timed(steps, from_host=False)
+        # the end-to-end loop has host code of its own (pinned-memory copies, the prefetch, .item()): W untimed steps of exactly
+        # that loop first -- on a fresh box its first executions page in library code and cost milliseconds (tools/e2e_jitter.py:
+        # the first seconds of a host-driven loop run 5.7-6.0 ms per step with 7-8 ms outliers, 5.15-5.2 after that)
+        timed(max(warmup, 3), from_host=True, mark=False)
         ms_e2e, last_loss = timed(steps, from_host=True)
         clk = clocks.stop() if clocks else None
         out = {"ms_per_step": ms_total / steps, "value": B * N * world * steps / (ms_total / 1e3),
