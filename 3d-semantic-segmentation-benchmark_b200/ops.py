@@ -928,6 +928,39 @@ def _bn_finalize(partial, nblk, shift, count, C, gamma, beta, eps, momentum, rm,
     return stats
 
 
+def _bn_row_stats(x: torch.Tensor, gamma, beta, rm, rv, training, momentum, eps) -> torch.Tensor:
+    """The (4, C) BatchNorm constants {mean, rstd, gamma*rstd, beta} of the rows of x (R, C): batch statistics (one read of x,
+    deterministic block partials combined in fp64, running statistics updated) in training mode, the running ones in eval."""
+    R, C = x.shape
+    dev = x.device
+    if training:
+        nblk = _lib.size("pcnbr_bn_blocks", R, C)
+        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+        _lib.call("pcnbr_bn_stats_f32", x.data_ptr(), R, C, partial.data_ptr(), _stream())
+        return _bn_finalize(partial, nblk, x, R, C, gamma, beta, eps, momentum, rm, rv, dev)
+    return _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+
+
+def _bn_bwd_coefficients(gy, h, stats, slope, training, drop, gs=None, rows=None):
+    """First half of the fused BatchNorm + activation backward over `rows` (default: all R) rows of (gy, h): the reduction
+    pass (sum g', sum g' xhat; optionally g' written to gs) and its finalize -> (dgamma, dbeta, coef (4, C)).  `count` of
+    the statistics is h's row count R (the pooled form reduces over the G pooled rows but normalises by R)."""
+    R, C = h.shape
+    n = R if rows is None else rows
+    dev = h.device
+    nblk = _lib.size("pcnbr_bn_blocks", n, C)
+    partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
+    _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, n, C, stats.data_ptr(), slope,
+              partial.data_ptr(), gs.data_ptr() if gs is not None else None,
+              drop[0].data_ptr() if drop[0] is not None else None, drop[1], _stream())
+    dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+    coef = torch.empty(4, C, dtype=torch.float32, device=dev)
+    _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
+              dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+    return dgamma, dbeta, coef
+
+
 class _BnActRowsFn(torch.autograd.Function):
     """y = act(BatchNorm(x)) over the rows of x (R,C): 1 read for the statistics, 1 read + 1 write to apply; the
     backward needs x and gy only (2 reads to reduce, 2 reads + 1 write for dx)."""
@@ -936,13 +969,7 @@ class _BnActRowsFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, rm, rv, training, momentum, eps, slope):
         R, C = x.shape
         dev = x.device
-        if training:
-            nblk = _lib.size("pcnbr_bn_blocks", R, C)
-            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-            _lib.call("pcnbr_bn_stats_f32", x.data_ptr(), R, C, partial.data_ptr(), _stream())
-            stats = _bn_finalize(partial, nblk, x, R, C, gamma, beta, eps, momentum, rm, rv, dev)
-        else:
-            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        stats = _bn_row_stats(x, gamma, beta, rm, rv, training, momentum, eps)
         y = torch.empty_like(x)
         _lib.call("pcnbr_bn_act_fwd_f32", x.data_ptr(), C, None, 0, R, C, stats.data_ptr(), float(slope), y.data_ptr(), None, 0.0, None, _stream())
         ctx.save_for_backward(x, stats)
@@ -1230,13 +1257,7 @@ class _LinearBnActFn(torch.autograd.Function):
         ctx.xp = x_planes if (ctx.needs_input_grad[1] and ctx.amax[0] is not None and ctx.amax[1] is not None) else None
         h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]),
                     a_planes_out=ctx.xp if not x_planes_ready else None)
-        if training:
-            nblk = _lib.size("pcnbr_bn_blocks", R, C)
-            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-            _lib.call("pcnbr_bn_stats_f32", h.data_ptr(), R, C, partial.data_ptr(), _stream())
-            stats = _bn_finalize(partial, nblk, h, R, C, gamma, beta, eps, momentum, rm, rv, dev)
-        else:
-            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        stats = _bn_row_stats(h, gamma, beta, rm, rv, training, momentum, eps)
         y = torch.empty_like(h)
         # nn.Dropout behind the activation, fused: one 64-bit seed per forward pass from torch's generator (device side,
         # so it is redrawn on every CUDA-graph replay); the backward recomputes the mask from it
@@ -1256,15 +1277,7 @@ class _LinearBnActFn(torch.autograd.Function):
         C = w.shape[0]
         dev = x.device
         gy = _c(gy)
-        nblk = _lib.size("pcnbr_bn_blocks", R, C)
-        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-        _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
-                  partial.data_ptr(), None, ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
-        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-        coef = torch.empty(4, C, dtype=torch.float32, device=dev)
-        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
-                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+        dgamma, dbeta, coef = _bn_bwd_coefficients(gy, h, stats, slope, training, ctx.drop)
         dh = torch.empty_like(h)
         ax, aw = ctx.amax
         ag = _amax_buffer(dev) if ax is not None else None            # the max |dh| comes out of the kernel that writes dh
@@ -1296,13 +1309,7 @@ class _LinearBnActPoolFn(torch.autograd.Function):
         dev = x.device
         ctx.amax = _layer_amax(x, w, R, C, Cin)
         h = _gemm3x(x, False, w, False, R, C, Cin, b, amax_a=ctx.amax[0], amax_b=ctx.amax[1], b_split=_wsplit(w, False, ctx.amax[1]))
-        if training:
-            nblk = _lib.size("pcnbr_bn_blocks", R, C)
-            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-            _lib.call("pcnbr_bn_stats_f32", h.data_ptr(), R, C, partial.data_ptr(), _stream())
-            stats = _bn_finalize(partial, nblk, h, R, C, gamma, beta, eps, momentum, rm, rv, dev)
-        else:
-            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        stats = _bn_row_stats(h, gamma, beta, rm, rv, training, momentum, eps)
         out = torch.empty(G, C, dtype=torch.float32, device=dev)
         psel = torch.empty(G, C, dtype=torch.float32, device=dev)
         arg = torch.empty(G, C, dtype=torch.uint8, device=dev)
@@ -1385,13 +1392,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
         h = _gemm3x(x1, False, w, False, R, C, K1 + K2, b, A2=x2, K1=K1, amax_a=ctx.amax[0], amax_a2=ctx.amax[1], amax_b=ctx.amax[2],
                     b_split=_wsplit(w, False, ctx.amax[2]), a_planes_out=ctx.xp[0] if not x1_planes_ready else None,
                     a2_planes_out=ctx.xp[1] if not x2_planes_ready else None)
-        if training:
-            nblk = _lib.size("pcnbr_bn_blocks", R, C)
-            partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-            _lib.call("pcnbr_bn_stats_f32", h.data_ptr(), R, C, partial.data_ptr(), _stream())
-            stats = _bn_finalize(partial, nblk, h, R, C, gamma, beta, eps, momentum, rm, rv, dev)
-        else:
-            stats = _bn_finalize(None, 0, None, R, C, gamma, beta, eps, 0.0, rm, rv, dev)
+        stats = _bn_row_stats(h, gamma, beta, rm, rv, training, momentum, eps)
         y = torch.empty_like(h)
         # nn.Dropout behind the activation, fused: one 64-bit seed per forward pass from torch's generator (device side,
         # so it is redrawn on every CUDA-graph replay); the backward recomputes the mask from it
@@ -1412,15 +1413,7 @@ class _LinearBnActCatFn(torch.autograd.Function):
         C = w.shape[0]
         dev = x1.device
         gy = _c(gy)
-        nblk = _lib.size("pcnbr_bn_blocks", R, C)
-        partial = torch.empty(nblk, 2, C, dtype=torch.float32, device=dev)
-        _lib.call("pcnbr_bn_act_bwd_reduce_f32", gy.data_ptr(), h.data_ptr(), C, None, 0, R, C, stats.data_ptr(), slope,
-                  partial.data_ptr(), None, ctx.drop[0].data_ptr() if ctx.drop[0] is not None else None, ctx.drop[1], _stream())
-        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-        coef = torch.empty(4, C, dtype=torch.float32, device=dev)
-        _lib.call("pcnbr_bn_bwd_finalize_f32", partial.data_ptr(), nblk, stats.data_ptr(), float(R), C, int(training),
-                  dgamma.data_ptr(), dbeta.data_ptr(), coef.data_ptr(), _stream())
+        dgamma, dbeta, coef = _bn_bwd_coefficients(gy, h, stats, slope, training, ctx.drop)
         dh = torch.empty_like(h)
         a1, a2, aw = ctx.amax
         ag = _amax_buffer(dev) if aw is not None else None            # the max |dh| comes out of the kernel that writes dh
